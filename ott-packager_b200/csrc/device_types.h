@@ -1,0 +1,83 @@
+// Device-visible descriptors shared by the host planner and the sm_100a kernels.
+//
+// Vocabulary: a *channel* is one transvideo pipeline (one fillet process in the reference); a *rung* is one ABR
+// rendition (core->cd->transvideo_info[i]); a *plan* is everything sws_getContext() would have produced for all rungs
+// of one channel configuration (polyphase tables + tiling); a *work item* is one output tile of one plane of one rung
+// of one channel's current frame and is executed by one CTA.
+#pragma once
+#include <cstdint>
+
+namespace ottgpu {
+
+constexpr int kMaxRungs = 8;
+constexpr int kMaxRungSlots = kMaxRungs + 1;   // slot 8 = thumbnail (transvideo.c:2155-2174)
+constexpr int kThreads = 256;
+
+enum ItemKind : uint8_t {
+    ITEM_SCALE_LUMA = 0,     // H+V polyphase of one luma tile
+    ITEM_SCALE_CHROMA = 1,   // both chroma planes of one tile (so NV12/P010 writers can interleave)
+    ITEM_COPY_LUMA = 2,      // same-size rung: libswscale's unscaled path = plane copy
+    ITEM_COPY_CHROMA = 3,    // same-size rung chroma: copy or I420->NV12 interleave (transvideo.c:543-557)
+};
+
+struct PlaneTables {
+    const int32_t *hpos;     // [dstW]   first source column of each output column
+    const uint32_t *hc_hi;   // [dstW][hq] 8-bit path: per tap quad, high bytes  (coef >> 8, signed)   packed s8x4
+    const uint32_t *hc_lo;   // [dstW][hq]                          low bytes   (coef & 255, unsigned) packed u8x4
+    const int16_t *hc16;     // [dstW][4*hq] plain 14-bit coefficients (16-bit sample path)
+    const int32_t *vpos;     // [dstH]   first source row of each output row
+    const int16_t *vc;       // [dstH][vtaps] 12-bit coefficients
+    int srcW, srcH, dstW, dstH;
+    int hq;                  // horizontal taps / 4 (tables zero-padded to a multiple of four taps)
+    int vtaps;
+    int exact_from;          // 8-bit target A: first output row computed with the exact vertical formula
+    int tw, th;              // tile size in output samples
+    int tiles_x, tiles_y;
+    int sw_words;            // shared-memory source row pitch in 32-bit words (max over tiles, + funnel slack)
+    int sr_max;              // max source rows any tile needs
+};
+
+struct RungDev {
+    PlaneTables luma, chroma;
+    int fmt;                 // OTTGPU_FMT_*
+    int scaled;              // 0: same size as the source (copy items)
+    int approx_v;            // 1: 8-bit target A vertical pass (pmulhw-style truncation) on rows < exact_from
+};
+
+struct PlanDev {
+    int src_fmt;             // OTTGPU_FMT_*
+    int bps;                 // bytes per sample (1 | 2)
+    int n_slots;             // rungs (+1 if a thumbnail slot exists)
+    int thumb_slot;          // -1: none
+    RungDev rung[kMaxRungSlots];
+};
+
+// Per channel, per launch: where this step's frame lives.
+struct Binding {
+    const PlanDev *plan;
+    int active;              // 0: channel produces nothing this step (yadif priming) -> its items exit at once
+    int thumb_active;        // thumbnail slot wanted this step
+    uint32_t skip_mask;      // rung slots already produced elsewhere this step (yadif wrote the full-size rung)
+    const uint8_t *src[3];   // Y,U,V  or  Y,UV
+    int src_pitch[3];        // bytes
+    uint8_t *dst[kMaxRungSlots][3];
+    int dst_pitch[kMaxRungSlots][3];
+};
+
+struct Item {
+    uint16_t chan;
+    uint8_t slot;
+    uint8_t kind;
+    uint16_t tx, ty;
+};
+
+// yadif work description, one per channel per launch
+struct YadifJob {
+    const uint8_t *prev, *cur, *next;   // packed planar frames (I420 / I420P10)
+    uint8_t *dst;
+    int width, height, bps;
+    int parity, tff;                    // as resolved by yadif: parity = tff ^ 1 for mode 0
+    int active;
+};
+
+}  // namespace ottgpu

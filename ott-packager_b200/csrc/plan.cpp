@@ -1,0 +1,287 @@
+#include "plan.h"
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <cuda_runtime.h>
+
+namespace ottgpu {
+
+int fmt_bps(int fmt)
+{
+    switch (fmt) {
+    case OTTGPU_FMT_I420: case OTTGPU_FMT_NV12: return 1;
+    case OTTGPU_FMT_P010: case OTTGPU_FMT_I420P10: return 2;
+    default: return 0;
+    }
+}
+
+size_t packed_frame_bytes(int fmt, int w, int h)
+{
+    const size_t cw = (w + 1) / 2, ch = (h + 1) / 2;
+    return ((size_t)w * h + 2 * cw * ch) * (size_t)fmt_bps(fmt);
+}
+
+bool rung_layout(const ottgpu_rung_cfg &r, RungLayout &out)
+{
+    const int bps = fmt_bps(r.fmt);
+    if (!bps || r.width <= 0 || r.height <= 0) return false;
+    const int cw = (r.width + 1) / 2, ch = (r.height + 1) / 2;
+    const int al = r.pitch_align > 1 ? r.pitch_align : 1;
+    auto up = [al](int v) { return (v + al - 1) / al * al; };
+    const bool semi = r.fmt == OTTGPU_FMT_NV12 || r.fmt == OTTGPU_FMT_P010;
+    out.planes = semi ? 2 : 3;
+    out.pitch[0] = up(r.width * bps);
+    out.offset[0] = 0;
+    size_t at = (size_t)out.pitch[0] * r.height;
+    if (semi) {
+        out.pitch[1] = up(2 * cw * bps);
+        out.offset[1] = at;
+        at += (size_t)out.pitch[1] * ch;
+        out.pitch[2] = 0;
+        out.offset[2] = 0;
+    } else {
+        out.pitch[1] = out.pitch[2] = up(cw * bps);
+        out.offset[1] = at;
+        at += (size_t)out.pitch[1] * ch;
+        out.offset[2] = at;
+        at += (size_t)out.pitch[2] * ch;
+    }
+    out.bytes = at;
+    return true;
+}
+
+PolyphaseTable plan_table(int src_n, int dst_n, int filter, int target, bool vertical)
+{
+    const bool exact = target == OTTGPU_TARGET_B;
+    const int align = exact ? 1 : (vertical ? 2 : 4);            // x86 filterAlign, SURVEY.md A.1
+    return make_polyphase(src_n, dst_n, filter == OTTGPU_FILTER_LANCZOS ? Kernel::Lanczos : Kernel::Bicubic, align,
+                          vertical ? 1 << 12 : 1 << 14, exact);
+}
+
+Plan::~Plan()
+{
+    cudaSetDevice(gpu);
+    for (void *p : allocations) cudaFree(p);
+}
+
+namespace {
+
+constexpr size_t kSmemBudget = 48 * 1024;    // preferred tile footprint (>= 4 CTAs per SM)
+
+template <typename T>
+const T *upload(Plan &plan, const std::vector<T> &v, std::string &err)
+{
+    void *d = nullptr;
+    if (cudaMalloc(&d, std::max<size_t>(v.size() * sizeof(T), 16)) != cudaSuccess) { err = "cudaMalloc(tables) failed"; return nullptr; }
+    plan.allocations.push_back(d);
+    if (!v.empty() && cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) {
+        err = "cudaMemcpy(tables) failed";
+        return nullptr;
+    }
+    return static_cast<const T *>(d);
+}
+
+size_t tile_bytes(int nplanes, int sr_max, int sw_words, int tw, int th, int vtaps)
+{
+    size_t b = (size_t)nplanes * sr_max * sw_words * 4 + (size_t)nplanes * sr_max * ((tw + 1) & ~1) * 2 + (size_t)th * vtaps * 2;
+    return ((b + 3) & ~(size_t)3) + (size_t)th * 4 + 16;
+}
+
+// Builds tables + tiling for one plane kind of one rung.  Host vectors are kept in `keep` only long enough to upload.
+bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int dstH, int bps, int nplanes, int filter,
+                 int target, int exact_from, size_t &smem_out, std::string &err)
+{
+    const PolyphaseTable h = plan_table(srcW, dstW, filter, target, false);
+    const PolyphaseTable v = plan_table(srcH, dstH, filter, target, true);
+    const int hq = (h.taps + 3) / 4, taps4 = 4 * hq;
+    std::vector<uint32_t> hi((size_t)dstW * hq), lo((size_t)dstW * hq);
+    std::vector<int16_t> c16((size_t)dstW * taps4, 0);
+    for (int x = 0; x < dstW; ++x)
+        for (int j = 0; j < h.taps; ++j) c16[(size_t)x * taps4 + j] = h.coef[(size_t)x * h.taps + j];
+    for (int x = 0; x < dstW; ++x)
+        for (int q = 0; q < hq; ++q) {
+            uint32_t a = 0, b = 0;
+            for (int k = 0; k < 4; ++k) {
+                const int c = c16[(size_t)x * taps4 + 4 * q + k];
+                a |= (uint32_t)((c >> 8) & 255) << (8 * k);      // signed high byte
+                b |= (uint32_t)(c & 255) << (8 * k);             // unsigned low byte
+            }
+            hi[(size_t)x * hq + q] = a;
+            lo[(size_t)x * hq + q] = b;
+        }
+    T.srcW = srcW; T.srcH = srcH; T.dstW = dstW; T.dstH = dstH;
+    T.hq = hq;
+    T.vtaps = v.taps;
+    T.exact_from = exact_from;
+    T.tw = dstW >= 128 ? 64 : 32;
+    T.tiles_x = (dstW + T.tw - 1) / T.tw;
+
+    const int spw = bps == 1 ? 4 : 2;
+    int sw_words = 0;
+    for (int tx = 0; tx < T.tiles_x; ++tx) {
+        const int x0 = tx * T.tw, x1 = std::min(x0 + T.tw, dstW) - 1;
+        const int s0 = h.pos[x0] & ~(spw - 1), s1 = h.pos[x1] + taps4;
+        sw_words = std::max(sw_words, (s1 - s0 + spw - 1) / spw + 1);
+    }
+    T.sw_words = sw_words | 1;                                   // odd pitch: row groups start in different banks
+
+    auto rows_needed = [&](int th) {
+        int m = 0;
+        for (int y0 = 0; y0 < dstH; y0 += th) {
+            const int y1 = std::min(y0 + th, dstH) - 1;
+            m = std::max(m, v.pos[y1] + v.taps - v.pos[y0]);
+        }
+        return m;
+    };
+    const int row_quant = T.tw == 64 ? 8 : 16;                   // output rows the V pass covers per sweep
+    int th = std::min((dstH + row_quant - 1) / row_quant * row_quant, 256);
+    while (th > row_quant && tile_bytes(nplanes, rows_needed(th), T.sw_words, T.tw, th, v.taps) > kSmemBudget) th -= row_quant;
+    // rebalance so the last tile row is not a sliver
+    const int nty = (dstH + th - 1) / th;
+    th = ((dstH + nty - 1) / nty + row_quant - 1) / row_quant * row_quant;
+    T.th = th;
+    T.tiles_y = (dstH + th - 1) / th;
+    T.sr_max = rows_needed(th);
+    smem_out = tile_bytes(nplanes, T.sr_max, T.sw_words, T.tw, th, v.taps);
+    if (smem_out > 200 * 1024) { err = "filter too long for one tile (shared memory)"; return false; }
+
+    T.hpos = upload(plan, h.pos, err);
+    T.hc_hi = upload(plan, hi, err);
+    T.hc_lo = upload(plan, lo, err);
+    T.hc16 = upload(plan, c16, err);
+    T.vpos = upload(plan, v.pos, err);
+    T.vc = upload(plan, v.coef, err);
+    return T.hpos && T.hc_hi && T.hc_lo && T.hc16 && T.vpos && T.vc;
+}
+
+void copy_tiling(PlaneTables &T, int w, int h)
+{
+    std::memset(&T, 0, sizeof(T));
+    T.srcW = T.dstW = w;
+    T.srcH = T.dstH = h;
+    T.tw = w;
+    T.th = 32;                                                   // rows per copy item
+    T.tiles_x = 1;
+    T.tiles_y = (h + T.th - 1) / T.th;
+}
+
+struct Key {
+    ottgpu_cfg c;
+    bool operator<(const Key &o) const { return std::memcmp(&c, &o.c, sizeof(c)) < 0; }
+};
+std::mutex g_mu;
+std::map<Key, std::weak_ptr<Plan>> g_cache;
+
+bool compatible(int src_fmt, int dst_fmt, bool same_size)
+{
+    if (fmt_bps(src_fmt) != fmt_bps(dst_fmt) || !fmt_bps(src_fmt)) return false;
+    if (src_fmt == OTTGPU_FMT_NV12) return false;                // sources are planar I420 / P010 / I420P10
+    if (same_size) return src_fmt == dst_fmt || (src_fmt == OTTGPU_FMT_I420 && dst_fmt == OTTGPU_FMT_NV12);
+    return true;
+}
+
+}  // namespace
+
+std::shared_ptr<Plan> get_plan(const ottgpu_cfg &cfg_in, std::string &err)
+{
+    // normalise the key: only fields that influence tables/tiling; unused rung entries zeroed
+    Key key;
+    std::memset(&key, 0, sizeof(key));
+    key.c.gpu = cfg_in.gpu;
+    key.c.src_width = cfg_in.src_width; key.c.src_height = cfg_in.src_height; key.c.src_fmt = cfg_in.src_fmt;
+    key.c.n_rungs = cfg_in.n_rungs;
+    for (int i = 0; i < cfg_in.n_rungs && i < OTTGPU_MAX_RUNGS; ++i) key.c.rung[i] = cfg_in.rung[i];
+    key.c.filter = cfg_in.filter; key.c.target = cfg_in.target;
+    key.c.thumb_width = cfg_in.thumb_width; key.c.thumb_height = cfg_in.thumb_height;
+    const ottgpu_cfg &cfg = key.c;
+
+    if (cfg.n_rungs < 0 || cfg.n_rungs > OTTGPU_MAX_RUNGS) { err = "n_rungs out of range"; return nullptr; }
+    if (cfg.src_width < 8 || cfg.src_height < 8 || cfg.src_width > 16384 || cfg.src_height > 16384) { err = "source size unsupported"; return nullptr; }
+    if (cfg.src_fmt != OTTGPU_FMT_I420 && cfg.src_fmt != OTTGPU_FMT_P010 && cfg.src_fmt != OTTGPU_FMT_I420P10) { err = "source format unsupported"; return nullptr; }
+    if (cfg.filter != OTTGPU_FILTER_BICUBIC && cfg.filter != OTTGPU_FILTER_LANCZOS) { err = "filter unsupported"; return nullptr; }
+    if (cfg.target != OTTGPU_TARGET_A && cfg.target != OTTGPU_TARGET_B) { err = "parity target unsupported"; return nullptr; }
+
+    std::lock_guard<std::mutex> lock(g_mu);
+    auto found = g_cache.find(key);
+    if (found != g_cache.end())
+        if (auto p = found->second.lock()) return p;
+
+    if (cudaSetDevice(cfg.gpu) != cudaSuccess) { err = "cudaSetDevice failed"; return nullptr; }
+    auto plan = std::make_shared<Plan>();
+    plan->gpu = cfg.gpu;
+    plan->cfg = cfg;
+    const int bps = fmt_bps(cfg.src_fmt);
+    const int scw = (cfg.src_width + 1) / 2, sch = (cfg.src_height + 1) / 2;
+    const bool thumb = cfg.thumb_width > 0 && cfg.thumb_height > 0;
+    plan->n_slots = cfg.n_rungs + (thumb ? 1 : 0);
+    plan->thumb_slot = thumb ? cfg.n_rungs : -1;
+
+    PlanDev &P = plan->host_copy;
+    std::memset(&P, 0, sizeof(P));
+    P.src_fmt = cfg.src_fmt;
+    P.bps = bps;
+    P.n_slots = plan->n_slots;
+    P.thumb_slot = plan->thumb_slot;
+
+    struct Sortable { Item it; int band; };
+    std::vector<Sortable> ordered;
+    for (int s = 0; s < plan->n_slots; ++s) {
+        ottgpu_rung_cfg rc;
+        if (s == plan->thumb_slot) { rc.width = cfg.thumb_width; rc.height = cfg.thumb_height; rc.fmt = bps == 1 ? OTTGPU_FMT_I420 : OTTGPU_FMT_I420P10; rc.pitch_align = 0; }
+        else rc = cfg.rung[s];
+        if (rc.width < 2 || rc.height < 2 || rc.width > 16384 || rc.height > 16384) { err = "rung size unsupported"; return nullptr; }
+        const bool same = rc.width == cfg.src_width && rc.height == cfg.src_height;
+        if (!compatible(cfg.src_fmt, rc.fmt, same)) { err = "source/rung format combination unsupported"; return nullptr; }
+        if (!rung_layout(rc, plan->layout[s])) { err = "bad rung layout"; return nullptr; }
+        RungDev &R = P.rung[s];
+        R.fmt = rc.fmt;
+        R.scaled = !same;
+        R.approx_v = bps == 1 && cfg.target == OTTGPU_TARGET_A;
+        const int dcw = (rc.width + 1) / 2, dch = (rc.height + 1) / 2;
+        std::vector<Item> &sink = s == plan->thumb_slot ? plan->thumb_items : plan->items;
+        size_t &smem = s == plan->thumb_slot ? plan->smem_thumb : plan->smem_items;
+        if (same) {
+            copy_tiling(R.luma, cfg.src_width, cfg.src_height);
+            copy_tiling(R.chroma, scw, sch);
+            for (int ty = 0; ty < R.luma.tiles_y; ++ty)
+                ordered.push_back({Item{0, (uint8_t)s, ITEM_COPY_LUMA, 0, (uint16_t)ty}, ty * R.luma.th});
+            for (int ty = 0; ty < R.chroma.tiles_y; ++ty)
+                ordered.push_back({Item{0, (uint8_t)s, ITEM_COPY_CHROMA, 0, (uint16_t)ty}, 2 * ty * R.chroma.th});
+            continue;
+        }
+        // swscale switches to the C vertical functions once dstY >= dstH-2 (luma rows);
+        // chroma row uv is emitted while dstY == 2*uv
+        const int luma_exact = R.approx_v ? std::max(rc.height - 2, 0) : 0;
+        const int chroma_exact = R.approx_v ? std::max((rc.height - 2 + 1) / 2, 0) : 0;
+        size_t s1 = 0, s2 = 0;
+        if (!build_plane(*plan, R.luma, cfg.src_width, cfg.src_height, rc.width, rc.height, bps, 1, cfg.filter, cfg.target, luma_exact, s1, err)) return nullptr;
+        if (!build_plane(*plan, R.chroma, scw, sch, dcw, dch, bps, 2, cfg.filter, cfg.target, chroma_exact, s2, err)) return nullptr;
+        smem = std::max(smem, std::max(s1, s2));
+        // order by the first source row each tile reads, so tiles of different rungs over the same band run together
+        std::vector<int32_t> lv = plan_table(cfg.src_height, rc.height, cfg.filter, cfg.target, true).pos;
+        std::vector<int32_t> cv = plan_table(sch, dch, cfg.filter, cfg.target, true).pos;
+        for (int ty = 0; ty < R.luma.tiles_y; ++ty)
+            for (int tx = 0; tx < R.luma.tiles_x; ++tx) {
+                Sortable so{Item{0, (uint8_t)s, ITEM_SCALE_LUMA, (uint16_t)tx, (uint16_t)ty}, lv[ty * R.luma.th]};
+                if (s == plan->thumb_slot) sink.push_back(so.it); else ordered.push_back(so);
+            }
+        for (int ty = 0; ty < R.chroma.tiles_y; ++ty)
+            for (int tx = 0; tx < R.chroma.tiles_x; ++tx) {
+                Sortable so{Item{0, (uint8_t)s, ITEM_SCALE_CHROMA, (uint16_t)tx, (uint16_t)ty}, 2 * cv[ty * R.chroma.th]};
+                if (s == plan->thumb_slot) sink.push_back(so.it); else ordered.push_back(so);
+            }
+    }
+    std::stable_sort(ordered.begin(), ordered.end(), [](const Sortable &a, const Sortable &b) { return a.band < b.band; });
+    for (const Sortable &so : ordered) plan->items.push_back(so.it);
+
+    void *d = nullptr;
+    if (cudaMalloc(&d, sizeof(PlanDev)) != cudaSuccess) { err = "cudaMalloc(plan) failed"; return nullptr; }
+    plan->allocations.push_back(d);
+    if (cudaMemcpy(d, &P, sizeof(PlanDev), cudaMemcpyHostToDevice) != cudaSuccess) { err = "cudaMemcpy(plan) failed"; return nullptr; }
+    plan->dev = static_cast<PlanDev *>(d);
+    g_cache[key] = plan;
+    return plan;
+}
+
+}  // namespace ottgpu

@@ -1,0 +1,695 @@
+// libottgpu runtime: channels (yadif window + per-rung surfaces), batches (one fused launch per stage over many
+// channels), pools, and the C ABI of include/ottgpu.h.
+//
+// What it stands in for in the reference: the avfilter graph + SwsContexts + packed-buffer copies that
+// video_prepare_thread / video_scale_thread own (transvideo.c:1504-1683, 1896-2429).  Frame scheduling follows
+// yadif_common.c ff_yadif_filter_frame as summarised in SURVEY.md Appendix C.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../../include/ottgpu.h"
+#include "kernels.h"
+#include "plan.h"
+
+using namespace ottgpu;
+
+namespace {
+
+thread_local std::string t_err;
+
+int fail(int code, const std::string &what)
+{
+    t_err = what;
+    return code;
+}
+int fail_cuda(cudaError_t e, const char *where)
+{
+    t_err = std::string(where) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();
+    return OTTGPU_ERR_CUDA;
+}
+#define CK(call)                                                  \
+    do {                                                          \
+        cudaError_t e_ = (call);                                  \
+        if (e_ != cudaSuccess) return fail_cuda(e_, #call);       \
+    } while (0)
+
+std::mutex g_dev_mu;
+bool g_dev_ready[64] = {false};
+
+int prepare_device(int gpu)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaGetDeviceCount");
+    if (gpu < 0 || gpu >= n || gpu >= 64) return fail(OTTGPU_ERR_ARG, "gpu ordinal out of range");
+    CK(cudaSetDevice(gpu));
+    std::lock_guard<std::mutex> lock(g_dev_mu);
+    if (!g_dev_ready[gpu]) {
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, gpu));
+        if (prop.major != 10) return fail(OTTGPU_ERR_CUDA, "libottgpu carries sm_100a code only; device is not compute capability 10.x");
+        CK(configure_kernels());
+        g_dev_ready[gpu] = true;
+    }
+    return OTTGPU_OK;
+}
+
+struct FrameRef {
+    const uint8_t *dev = nullptr;
+    int slot = -1;               // >= 0: channel-owned upload slot; -1: caller's device memory
+    int interlaced = 0, tff = 1;
+    int64_t pts = 0, dts = 0;
+    void *opaque = nullptr;
+    bool valid = false;
+};
+
+void plane_ptrs(int fmt, const uint8_t *base, int w, int h, const uint8_t *p[3], int pitch[3])
+{
+    const int bps = fmt_bps(fmt), cw = (w + 1) / 2, ch = (h + 1) / 2;
+    p[0] = base;
+    pitch[0] = w * bps;
+    p[1] = base + (size_t)w * h * bps;
+    if (fmt == OTTGPU_FMT_P010 || fmt == OTTGPU_FMT_NV12) {
+        pitch[1] = 2 * cw * bps;
+        p[2] = nullptr;
+        pitch[2] = 0;
+    } else {
+        pitch[1] = pitch[2] = cw * bps;
+        p[2] = p[1] + (size_t)cw * ch * bps;
+    }
+}
+
+}  // namespace
+
+struct ottgpu_channel {
+    ottgpu_cfg cfg{};
+    std::shared_ptr<Plan> plan;
+    int gpu = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    size_t src_bytes = 0;
+    uint8_t *slots[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool slot_used[4] = {false, false, false, false};
+    FrameRef prev, cur, next;
+    uint8_t *deint = nullptr;                          // yadif output when no rung surface can take it directly
+    uint8_t *stage[kMaxRungSlots] = {nullptr};         // device surfaces for host-destined rungs / thumbnail
+    int thumb_count = 0;
+    int direct_rung = -1;                              // rung whose surface is byte-identical to a deinterlaced frame
+    ottgpu_batch *solo = nullptr;
+};
+
+struct ottgpu_batch {
+    std::vector<ottgpu_channel *> ch;
+    int gpu = 0;
+    cudaStream_t stream = nullptr;
+    Item *d_items = nullptr, *d_thumb_items = nullptr;
+    int n_items = 0, max_thumb_items = 0;
+    std::vector<int> item_begin;                       // per channel range in d_items (unused today, kept for tooling)
+    size_t smem_items = 0, smem_thumb = 0;
+    Binding *h_binds = nullptr, *d_binds = nullptr;    // pinned / device
+    YadifJob *h_jobs = nullptr, *d_jobs = nullptr;
+    Item *h_thumb_items = nullptr;
+    int last_launches = 0, last_items = 0;
+    bool pending = false;
+    struct Thumb { void *host; const uint8_t *dev; size_t bytes; };
+    struct Readback { void *host; const uint8_t *dev; size_t bytes; };
+    std::vector<Readback> readbacks;
+};
+
+namespace {
+
+bool referenced(const ottgpu_channel *c, const uint8_t *dev)
+{
+    return (c->prev.valid && c->prev.dev == dev) || (c->cur.valid && c->cur.dev == dev) || (c->next.valid && c->next.dev == dev);
+}
+
+void release_frame(ottgpu_channel *c, const FrameRef &f, ottgpu_frame_out *out)
+{
+    if (!f.valid || referenced(c, f.dev)) return;
+    if (f.slot >= 0) c->slot_used[f.slot] = false;
+    else if (out && out->n_released < 4) out->released[out->n_released++] = f.dev;
+}
+
+int take_slot(ottgpu_channel *c)
+{
+    for (int i = 0; i < 4; ++i)
+        if (!c->slot_used[i]) {
+            if (!c->slots[i] && cudaMalloc((void **)&c->slots[i], c->src_bytes + 64) != cudaSuccess) {
+                cudaGetLastError();
+                return -1;
+            }
+            c->slot_used[i] = true;
+            return i;
+        }
+    return -1;
+}
+
+int ensure_dev(uint8_t **p, size_t bytes)
+{
+    if (*p) return OTTGPU_OK;
+    if (cudaMalloc((void **)p, bytes + 64) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(OTTGPU_ERR_NOMEM, "cudaMalloc(surface) failed");
+    }
+    return OTTGPU_OK;
+}
+
+void drop_window(ottgpu_channel *c)
+{
+    for (int i = 0; i < 4; ++i) c->slot_used[i] = false;
+    c->prev = c->cur = c->next = FrameRef();
+}
+
+}  // namespace
+
+extern "C" {
+
+int ottgpu_abi_version(void) { return OTTGPU_ABI_VERSION; }
+
+int ottgpu_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaGetDeviceCount");
+    return n;
+}
+
+const char *ottgpu_strerror(int code)
+{
+    switch (code) {
+    case OTTGPU_OK: return "ok";
+    case OTTGPU_ERR_ARG: return "bad argument";
+    case OTTGPU_ERR_CUDA: return "CUDA error";
+    case OTTGPU_ERR_NOMEM: return "out of memory / pool exhausted";
+    case OTTGPU_ERR_STATE: return "bad call sequence";
+    default: return "unknown error";
+    }
+}
+
+const char *ottgpu_last_error(void) { return t_err.c_str(); }
+
+size_t ottgpu_frame_bytes(int fmt, int width, int height) { return packed_frame_bytes(fmt, width, height); }
+
+size_t ottgpu_rung_bytes(const ottgpu_rung_cfg *r)
+{
+    RungLayout l;
+    return r && rung_layout(*r, l) ? l.bytes : 0;
+}
+
+int ottgpu_rung_layout(const ottgpu_rung_cfg *r, size_t offset[3], int pitch[3])
+{
+    RungLayout l;
+    if (!r || !rung_layout(*r, l)) return fail(OTTGPU_ERR_ARG, "bad rung");
+    for (int i = 0; i < 3; ++i) { offset[i] = l.offset[i]; pitch[i] = l.pitch[i]; }
+    return l.planes;
+}
+
+int ottgpu_filter_table(int src_n, int dst_n, int filter, int target, int vertical, int32_t *pos, int16_t *coef)
+{
+    if (src_n < 4 || dst_n < 1 || !pos || !coef) return fail(OTTGPU_ERR_ARG, "bad table request");
+    const PolyphaseTable t = plan_table(src_n, dst_n, filter, target, vertical != 0);
+    std::memcpy(pos, t.pos.data(), sizeof(int32_t) * t.pos.size());
+    std::memcpy(coef, t.coef.data(), sizeof(int16_t) * t.coef.size());
+    return t.taps;
+}
+
+/* -------------------------------------------------------------------------------------------------- channel */
+int ottgpu_channel_create(const ottgpu_cfg *cfg, ottgpu_channel **out)
+{
+    if (!cfg || !out) return fail(OTTGPU_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->deint < OTTGPU_DEINT_ALL || cfg->deint > OTTGPU_DEINT_BYPASS) return fail(OTTGPU_ERR_ARG, "bad deint mode");
+    if (cfg->deint == OTTGPU_DEINT_ALL && cfg->src_fmt == OTTGPU_FMT_P010)
+        return fail(OTTGPU_ERR_ARG, "yadif needs planar samples (vf_yadif has no P010); use I420P10 or deint=FLAGGED/BYPASS");
+    if ((cfg->thumb_width > 0) != (cfg->thumb_height > 0) || (cfg->thumb_width > 0 && cfg->thumb_period < 1))
+        return fail(OTTGPU_ERR_ARG, "bad thumbnail settings");
+    int rc = prepare_device(cfg->gpu);
+    if (rc) return rc;
+    std::string err;
+    std::shared_ptr<Plan> plan = get_plan(*cfg, err);
+    if (!plan) return fail(err.find("cuda") != std::string::npos ? OTTGPU_ERR_CUDA : OTTGPU_ERR_ARG, err);
+    std::unique_ptr<ottgpu_channel> c(new ottgpu_channel);
+    c->cfg = *cfg;
+    c->plan = plan;
+    c->gpu = cfg->gpu;
+    c->src_bytes = packed_frame_bytes(cfg->src_fmt, cfg->src_width, cfg->src_height);
+    if (cfg->stream) {
+        c->stream = (cudaStream_t)cfg->stream;
+    } else {
+        CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    for (int r = 0; r < cfg->n_rungs; ++r) {
+        const ottgpu_rung_cfg &g = cfg->rung[r];
+        if (g.width == cfg->src_width && g.height == cfg->src_height && g.fmt == cfg->src_fmt && g.pitch_align <= 1) {
+            c->direct_rung = r;
+            break;
+        }
+    }
+    ottgpu_channel *raw = c.release();
+    rc = ottgpu_batch_create(&raw, 1, &raw->solo);
+    if (rc) {
+        ottgpu_channel_destroy(raw);
+        return rc;
+    }
+    *out = raw;
+    return OTTGPU_OK;
+}
+
+int ottgpu_channel_gpu(const ottgpu_channel *ch) { return ch ? ch->gpu : OTTGPU_ERR_ARG; }
+
+int ottgpu_channel_reset(ottgpu_channel *ch)
+{
+    if (!ch) return fail(OTTGPU_ERR_ARG, "null channel");
+    cudaSetDevice(ch->gpu);
+    cudaStreamSynchronize(ch->stream);
+    drop_window(ch);
+    ch->thumb_count = 0;       // the reference rebuilds the graph; its thumbnail_count keeps running (transvideo.c:1959-1970)
+    return OTTGPU_OK;
+}
+
+void ottgpu_channel_destroy(ottgpu_channel *ch)
+{
+    if (!ch) return;
+    cudaSetDevice(ch->gpu);
+    cudaStreamSynchronize(ch->stream);
+    if (ch->solo) ottgpu_batch_destroy(ch->solo);
+    for (uint8_t *p : ch->slots) cudaFree(p);
+    cudaFree(ch->deint);
+    for (uint8_t *p : ch->stage) cudaFree(p);
+    if (ch->own_stream) cudaStreamDestroy(ch->stream);
+    delete ch;
+}
+
+int ottgpu_channel_submit(ottgpu_channel *ch, const ottgpu_frame_in *in, ottgpu_frame_out *out)
+{
+    if (!ch || !in || !out) return fail(OTTGPU_ERR_ARG, "null argument");
+    if (!in->data) return fail(OTTGPU_ERR_ARG, "frame without data");
+    return ottgpu_batch_submit(ch->solo, in, out, OTTGPU_SUBMIT_SYNC);
+}
+
+/* ---------------------------------------------------------------------------------------------------- batch */
+int ottgpu_batch_create(ottgpu_channel **channels, int n, ottgpu_batch **out)
+{
+    if (!channels || n < 1 || n > 65535 || !out) return fail(OTTGPU_ERR_ARG, "bad batch arguments");
+    *out = nullptr;
+    for (int i = 0; i < n; ++i) {
+        if (!channels[i]) return fail(OTTGPU_ERR_ARG, "null channel in batch");
+        if (channels[i]->gpu != channels[0]->gpu) return fail(OTTGPU_ERR_ARG, "channels of one batch must share a GPU");
+    }
+    std::unique_ptr<ottgpu_batch> b(new ottgpu_batch);
+    b->ch.assign(channels, channels + n);
+    b->gpu = channels[0]->gpu;
+    b->stream = channels[0]->stream;
+    CK(cudaSetDevice(b->gpu));
+    std::vector<Item> all;
+    for (int i = 0; i < n; ++i) {
+        const Plan &p = *channels[i]->plan;
+        b->item_begin.push_back((int)all.size());
+        for (Item it : p.items) { it.chan = (uint16_t)i; all.push_back(it); }
+        b->smem_items = std::max(b->smem_items, p.smem_items);
+        b->smem_thumb = std::max(b->smem_thumb, p.smem_thumb);
+        b->max_thumb_items += (int)p.thumb_items.size();
+    }
+    b->n_items = (int)all.size();
+    CK(cudaMalloc((void **)&b->d_items, std::max<size_t>(all.size(), 1) * sizeof(Item)));
+    if (!all.empty()) CK(cudaMemcpy(b->d_items, all.data(), all.size() * sizeof(Item), cudaMemcpyHostToDevice));
+    CK(cudaMalloc((void **)&b->d_thumb_items, std::max(b->max_thumb_items, 1) * sizeof(Item)));
+    CK(cudaMallocHost((void **)&b->h_thumb_items, std::max(b->max_thumb_items, 1) * sizeof(Item)));
+    CK(cudaMalloc((void **)&b->d_binds, n * sizeof(Binding)));
+    CK(cudaMallocHost((void **)&b->h_binds, n * sizeof(Binding)));
+    CK(cudaMalloc((void **)&b->d_jobs, n * sizeof(YadifJob)));
+    CK(cudaMallocHost((void **)&b->h_jobs, n * sizeof(YadifJob)));
+    *out = b.release();
+    return OTTGPU_OK;
+}
+
+void ottgpu_batch_destroy(ottgpu_batch *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->gpu);
+    cudaStreamSynchronize(b->stream);
+    cudaFree(b->d_items);
+    cudaFree(b->d_thumb_items);
+    cudaFree(b->d_binds);
+    cudaFree(b->d_jobs);
+    cudaFreeHost(b->h_binds);
+    cudaFreeHost(b->h_jobs);
+    cudaFreeHost(b->h_thumb_items);
+    delete b;
+}
+
+int ottgpu_batch_last_launches(const ottgpu_batch *b) { return b ? b->last_launches : 0; }
+int ottgpu_batch_last_items(const ottgpu_batch *b) { return b ? b->last_items : 0; }
+
+int ottgpu_batch_wait(ottgpu_batch *b)
+{
+    if (!b) return fail(OTTGPU_ERR_ARG, "null batch");
+    if (!b->pending) return OTTGPU_OK;
+    CK(cudaSetDevice(b->gpu));
+    CK(cudaStreamSynchronize(b->stream));
+    b->pending = false;
+    return OTTGPU_OK;
+}
+
+int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame_out *out, int flags)
+{
+    if (!b || !in || !out) return fail(OTTGPU_ERR_ARG, "null argument");
+    CK(cudaSetDevice(b->gpu));
+    if (b->pending) {                                   // one step in flight per batch: pinned descriptors are reused
+        int rc = ottgpu_batch_wait(b);
+        if (rc) return rc;
+    }
+    const int n = (int)b->ch.size();
+    cudaStream_t s = b->stream;
+    int n_jobs = 0, n_thumb_items = 0, max_w = 0, max_h = 0, live = 0;
+    b->readbacks.clear();
+    b->last_launches = b->last_items = 0;
+
+    for (int i = 0; i < n; ++i) {
+        ottgpu_channel *c = b->ch[i];
+        const Plan &plan = *c->plan;
+        const ottgpu_cfg &cfg = c->cfg;
+        Binding &bind = b->h_binds[i];
+        YadifJob &job = b->h_jobs[i];
+        std::memset(&bind, 0, sizeof(bind));
+        std::memset(&job, 0, sizeof(job));
+        bind.plan = plan.dev;
+        ottgpu_frame_out &o = out[i];
+        o.produced = 0;
+        o.opaque = nullptr;
+        o.pts = o.dts = 0;
+        o.interlaced = 0;
+        o.tff = 1;
+        o.thumbnail = nullptr;
+        o.n_released = 0;
+        if (!in[i].data) continue;
+
+        // ---- 1. bring the frame to the device
+        FrameRef f;
+        f.valid = true;
+        f.interlaced = in[i].interlaced != 0;
+        f.tff = in[i].tff != 0;
+        f.pts = in[i].pts;
+        f.dts = in[i].dts;
+        f.opaque = in[i].opaque;
+        if (in[i].mem == OTTGPU_MEM_HOST) {
+            f.slot = take_slot(c);
+            if (f.slot < 0) return fail(OTTGPU_ERR_NOMEM, "no device slot for the incoming frame");
+            f.dev = c->slots[f.slot];
+            CK(cudaMemcpyAsync(c->slots[f.slot], in[i].data, c->src_bytes, cudaMemcpyHostToDevice, s));
+        } else if (in[i].mem == OTTGPU_MEM_DEVICE) {
+            f.dev = static_cast<const uint8_t *>(in[i].data);
+        } else {
+            return fail(OTTGPU_ERR_ARG, "bad input memory kind");
+        }
+
+        // ---- 2. yadif frame scheduling (yadif_common.c ff_yadif_filter_frame)
+        FrameRef target;
+        bool run_yadif = false;
+        if (cfg.deint == OTTGPU_DEINT_BYPASS) {
+            target = f;
+            c->next = f;                               // held until the step completes
+        } else {
+            FrameRef old_prev = c->prev;
+            c->prev = c->cur;
+            c->cur = c->next;
+            c->next = f;
+            if (!c->cur.valid) c->cur = c->next;
+            release_frame(c, old_prev, &o);
+            if (!c->prev.valid) continue;              // first frame only primes the window
+            target = c->cur;
+            run_yadif = cfg.deint == OTTGPU_DEINT_ALL || target.interlaced;
+            if (run_yadif && cfg.src_fmt == OTTGPU_FMT_P010)
+                return fail(OTTGPU_ERR_ARG, "interlaced-flagged P010 frame: yadif needs planar samples");
+        }
+        live++;
+        o.produced = 1;
+        o.opaque = target.opaque;
+        o.pts = target.pts;
+        o.dts = target.dts;
+
+        // ---- 3. where do the rungs go
+        uint32_t skip = 0;
+        for (int r = 0; r < cfg.n_rungs; ++r) {
+            uint8_t *base;
+            if (o.dst_mem[r] == OTTGPU_MEM_DEVICE) {
+                base = static_cast<uint8_t *>(o.dst[r]);
+            } else {
+                int rc = ensure_dev(&c->stage[r], plan.layout[r].bytes);
+                if (rc) return rc;
+                base = c->stage[r];
+                b->readbacks.push_back({o.dst[r], base, plan.layout[r].bytes});
+            }
+            if (!base || (o.dst_mem[r] != OTTGPU_MEM_DEVICE && !o.dst[r])) return fail(OTTGPU_ERR_ARG, "missing destination buffer");
+            for (int p = 0; p < plan.layout[r].planes; ++p) {
+                bind.dst[r][p] = base + plan.layout[r].offset[p];
+                bind.dst_pitch[r][p] = plan.layout[r].pitch[p];
+            }
+        }
+        const uint8_t *src_base = target.dev;
+        if (run_yadif) {
+            uint8_t *ydst;
+            if (c->direct_rung >= 0) {
+                ydst = bind.dst[c->direct_rung][0];    // the full-size rung IS the deinterlaced frame
+                skip |= 1u << c->direct_rung;
+            } else {
+                int rc = ensure_dev(&c->deint, c->src_bytes);
+                if (rc) return rc;
+                ydst = c->deint;
+            }
+            job.prev = c->prev.dev;
+            job.cur = c->cur.dev;
+            job.next = c->next.dev;
+            job.dst = ydst;
+            job.width = cfg.src_width;
+            job.height = cfg.src_height;
+            job.bps = fmt_bps(cfg.src_fmt);
+            job.tff = target.interlaced ? target.tff : 1;
+            job.parity = job.tff ^ 1;
+            job.active = 1;
+            n_jobs++;
+            max_w = std::max(max_w, cfg.src_width);
+            max_h = std::max(max_h, cfg.src_height);
+            src_base = ydst;
+        }
+        plane_ptrs(cfg.src_fmt, src_base, cfg.src_width, cfg.src_height, bind.src, bind.src_pitch);
+        bind.active = 1;
+        bind.skip_mask = skip;
+
+        // ---- 4. thumbnail cadence (transvideo.c:2159-2186)
+        if (plan.thumb_slot >= 0 && ++c->thumb_count == cfg.thumb_period) {
+            c->thumb_count = 0;
+            const int ts = plan.thumb_slot;
+            int rc = ensure_dev(&c->stage[ts], plan.layout[ts].bytes);
+            if (rc) return rc;
+            for (int p = 0; p < plan.layout[ts].planes; ++p) {
+                bind.dst[ts][p] = c->stage[ts] + plan.layout[ts].offset[p];
+                bind.dst_pitch[ts][p] = plan.layout[ts].pitch[p];
+            }
+            bind.thumb_active = 1;
+            void *host = std::malloc(plan.layout[ts].bytes);
+            if (!host) return fail(OTTGPU_ERR_NOMEM, "malloc(thumbnail) failed");
+            o.thumbnail = host;
+            b->readbacks.push_back({host, c->stage[ts], plan.layout[ts].bytes});
+            for (Item it : plan.thumb_items) { it.chan = (uint16_t)i; b->h_thumb_items[n_thumb_items++] = it; }
+        }
+
+        if (cfg.deint == OTTGPU_DEINT_BYPASS) {        // nothing is kept across calls
+            FrameRef done = c->next;
+            c->next = FrameRef();
+            release_frame(c, done, &o);
+        }
+    }
+
+    // ---- 5. enqueue: descriptors, yadif, ladder, thumbnails, read-backs
+    CK(cudaMemcpyAsync(b->d_binds, b->h_binds, n * sizeof(Binding), cudaMemcpyHostToDevice, s));
+    if (n_jobs) {
+        CK(cudaMemcpyAsync(b->d_jobs, b->h_jobs, n * sizeof(YadifJob), cudaMemcpyHostToDevice, s));
+        CK(launch_yadif(b->d_jobs, n, max_w, max_h, s));
+        b->last_launches++;
+    }
+    if (live && b->n_items) {
+        CK(launch_ladder(b->d_items, b->n_items, b->d_binds, b->smem_items, s));
+        b->last_launches++;
+        b->last_items += b->n_items;
+    }
+    if (n_thumb_items) {
+        CK(cudaMemcpyAsync(b->d_thumb_items, b->h_thumb_items, n_thumb_items * sizeof(Item), cudaMemcpyHostToDevice, s));
+        CK(launch_ladder(b->d_thumb_items, n_thumb_items, b->d_binds, b->smem_thumb, s));
+        b->last_launches++;
+        b->last_items += n_thumb_items;
+    }
+    for (const ottgpu_batch::Readback &r : b->readbacks)
+        CK(cudaMemcpyAsync(r.host, r.dev, r.bytes, cudaMemcpyDeviceToHost, s));
+    b->pending = true;
+    if (flags & OTTGPU_SUBMIT_ASYNC) return OTTGPU_OK;
+    return ottgpu_batch_wait(b);
+}
+
+/* ---------------------------------------------------------------------------------------------------- pools */
+}  // extern "C"
+
+struct ottgpu_pool {
+    int gpu = 0, mem = 0;
+    size_t size = 0;
+    uint8_t *base = nullptr;
+    std::vector<void *> free_list;
+    std::vector<bool> taken;
+    int count = 0;
+    std::mutex mu;
+};
+
+extern "C" {
+
+int ottgpu_pool_create(int gpu, int mem, int buffer_count, size_t buffer_size, ottgpu_pool **out)
+{
+    if (!out || buffer_count < 1 || !buffer_size) return fail(OTTGPU_ERR_ARG, "bad pool arguments");
+    *out = nullptr;
+    int rc = prepare_device(gpu);
+    if (rc) return rc;
+    std::unique_ptr<ottgpu_pool> p(new ottgpu_pool);
+    p->gpu = gpu;
+    p->mem = mem;
+    p->count = buffer_count;
+    p->size = (buffer_size + 255) & ~(size_t)255;      // every buffer 256-byte aligned: vector stores stay legal
+    cudaError_t e = mem == OTTGPU_MEM_DEVICE ? cudaMalloc((void **)&p->base, p->size * buffer_count)
+                                             : cudaMallocHost((void **)&p->base, p->size * buffer_count);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(OTTGPU_ERR_NOMEM, "pool allocation failed");
+    }
+    p->taken.assign(buffer_count, false);
+    for (int i = buffer_count - 1; i >= 0; --i) p->free_list.push_back(p->base + (size_t)i * p->size);
+    *out = p.release();
+    return OTTGPU_OK;
+}
+
+void *ottgpu_pool_take(ottgpu_pool *p)
+{
+    if (!p) return nullptr;
+    std::lock_guard<std::mutex> lock(p->mu);
+    if (p->free_list.empty()) return nullptr;
+    void *b = p->free_list.back();
+    p->free_list.pop_back();
+    p->taken[((uint8_t *)b - p->base) / p->size] = true;
+    return b;
+}
+
+int ottgpu_pool_return(ottgpu_pool *p, void *buffer)
+{
+    if (!p || !buffer) return fail(OTTGPU_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lock(p->mu);
+    const uint8_t *b = static_cast<uint8_t *>(buffer);
+    if (b < p->base || b >= p->base + p->size * p->count || (b - p->base) % p->size) return fail(OTTGPU_ERR_ARG, "buffer is not from this pool");
+    const size_t idx = (b - p->base) / p->size;
+    if (!p->taken[idx]) return fail(OTTGPU_ERR_STATE, "buffer returned twice");
+    p->taken[idx] = false;
+    p->free_list.push_back(buffer);
+    return OTTGPU_OK;
+}
+
+int ottgpu_pool_unused(ottgpu_pool *p)
+{
+    if (!p) return 0;
+    std::lock_guard<std::mutex> lock(p->mu);
+    return (int)p->free_list.size();
+}
+
+void ottgpu_pool_destroy(ottgpu_pool *p)
+{
+    if (!p) return;
+    cudaSetDevice(p->gpu);
+    if (p->mem == OTTGPU_MEM_DEVICE) cudaFree(p->base);
+    else cudaFreeHost(p->base);
+    delete p;
+}
+
+int ottgpu_memcpy(int gpu, void *dst, int dst_mem, const void *src, int src_mem, size_t bytes)
+{
+    if (!dst || !src) return fail(OTTGPU_ERR_ARG, "null argument");
+    CK(cudaSetDevice(gpu));
+    const cudaMemcpyKind kind = dst_mem == OTTGPU_MEM_DEVICE
+                                    ? (src_mem == OTTGPU_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice)
+                                    : (src_mem == OTTGPU_MEM_DEVICE ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost);
+    CK(cudaMemcpy(dst, src, bytes, kind));
+    return OTTGPU_OK;
+}
+
+/* ----------------------------------------------------------------------------------------------- single shots */
+int ottgpu_scale_frame(int gpu, const void *src, int src_fmt, int src_w, int src_h, void *dst,
+                       const ottgpu_rung_cfg *rung, int filter, int target)
+{
+    if (!src || !dst || !rung) return fail(OTTGPU_ERR_ARG, "null argument");
+    ottgpu_cfg cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gpu = gpu;
+    cfg.src_width = src_w;
+    cfg.src_height = src_h;
+    cfg.src_fmt = src_fmt;
+    cfg.n_rungs = 1;
+    cfg.rung[0] = *rung;
+    cfg.filter = filter;
+    cfg.target = target;
+    cfg.deint = OTTGPU_DEINT_BYPASS;
+    ottgpu_channel *ch = nullptr;
+    int rc = ottgpu_channel_create(&cfg, &ch);
+    if (rc) return rc;
+    ottgpu_frame_in in;
+    std::memset(&in, 0, sizeof(in));
+    in.data = src;
+    in.mem = OTTGPU_MEM_HOST;
+    ottgpu_frame_out out;
+    std::memset(&out, 0, sizeof(out));
+    out.dst[0] = dst;
+    out.dst_mem[0] = OTTGPU_MEM_HOST;
+    rc = ottgpu_channel_submit(ch, &in, &out);
+    if (rc == OTTGPU_OK && !out.produced) rc = fail(OTTGPU_ERR_STATE, "no frame produced");
+    ottgpu_channel_destroy(ch);
+    return rc;
+}
+
+int ottgpu_yadif_frame(int gpu, const void *prev, const void *cur, const void *next, void *dst, int fmt, int width,
+                       int height, int interlaced, int tff)
+{
+    if (!prev || !cur || !next || !dst) return fail(OTTGPU_ERR_ARG, "null argument");
+    if (fmt != OTTGPU_FMT_I420 && fmt != OTTGPU_FMT_I420P10) return fail(OTTGPU_ERR_ARG, "yadif needs I420 or I420P10");
+    if (width < 8 || height < 4) return fail(OTTGPU_ERR_ARG, "frame too small");
+    int rc = prepare_device(gpu);
+    if (rc) return rc;
+    const size_t bytes = packed_frame_bytes(fmt, width, height);
+    uint8_t *d = nullptr;
+    YadifJob *dj = nullptr;
+    if (cudaMalloc((void **)&d, 4 * (bytes + 256)) != cudaSuccess || cudaMalloc((void **)&dj, sizeof(YadifJob)) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(d);
+        return fail(OTTGPU_ERR_NOMEM, "cudaMalloc failed");
+    }
+    const size_t step = (bytes + 255) & ~(size_t)255;
+    YadifJob j;
+    std::memset(&j, 0, sizeof(j));
+    j.prev = d; j.cur = d + step; j.next = d + 2 * step; j.dst = d + 3 * step;
+    j.width = width; j.height = height; j.bps = fmt_bps(fmt);
+    j.tff = interlaced ? (tff != 0) : 1;
+    j.parity = j.tff ^ 1;
+    j.active = 1;
+    cudaError_t e = cudaMemcpy(d, prev, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d + step, cur, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d + 2 * step, next, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dj, &j, sizeof(j), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_yadif(dj, 1, width, height, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(dst, d + 3 * step, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    cudaFree(dj);
+    if (e != cudaSuccess) return fail_cuda(e, "ottgpu_yadif_frame");
+    return OTTGPU_OK;
+}
+
+}  // extern "C"

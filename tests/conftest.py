@@ -111,3 +111,51 @@ def sws():
         pytest.skip("bundled libswscale (opencv_python_headless.libs) not present")
     S.load()
     return S
+
+
+# ---------------------------------------------------------------- the library under test
+import importlib
+import subprocess
+
+
+def og_module():
+    return importlib.import_module("ott-packager_b200")
+
+
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.fixture(scope="session")
+def og():
+    return og_module()
+
+
+@pytest.fixture(scope="session")
+def real_lib(og):
+    """libottgpu.so itself (host-arithmetic entry points work without a GPU; compute calls need the B200)."""
+    if not os.path.exists(og.DEFAULT_LIB):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "ott-packager_b200", "csrc")])
+    return og.Library()
+
+
+@pytest.fixture(scope="session")
+def emu_lib(og):
+    """TEST-ONLY CPU emulation of the kernel source (tests/emu) behind the same C ABI."""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "emu")])
+    return og.Library(os.path.join(ROOT, "tests", "emu", "libottgpu_emu.so"))
+
+
+@pytest.fixture(scope="session", params=[pytest.param("emu"), pytest.param("gpu", marks=pytest.mark.gpu)])
+def lib(request, og):
+    """Parity tests run twice: against the CPU emulation of the kernel source (CPU tier: catches logic errors before
+    GPU time is spent) and, marked gpu, against the real sm_100a kernels through libottgpu.so."""
+    if request.param == "emu":
+        return request.getfixturevalue("emu_lib")
+    if not _have_gpu():
+        pytest.fail("gpu tier requested but no CUDA device is visible (there is no CPU fallback)")
+    return request.getfixturevalue("real_lib")

@@ -1,0 +1,217 @@
+"""Channel / batch behaviour through the C ABI: yadif parity (vs oracle/ref_yadif.c, itself PARITY-UNPINNED, see its
+header), frame scheduling of "yadif=0:-1:0|1" (transvideo.c:2036-2052, 2132-2141), sideband association across the
+one-frame latency (transvideo.c:2103-2152), discontinuity reset (1959-1970), thumbnail cadence (2159-2186), the fused
+multi-channel launch, and device-resident inputs/outputs (zero-copy surfaces)."""
+import ctypes
+import numpy as np
+import pytest
+from conftest import noise_i420, noise_p010, natural_i420, interlaced_sequence, split_i420
+
+
+@pytest.mark.parametrize("size", [(64, 48), (130, 74), (854, 480), (36, 22)])
+@pytest.mark.parametrize("tff", [1, 0])
+def test_yadif_frame_vs_oracle(lib, og, oracle, size, tff):
+    w, h = size
+    fr = interlaced_sequence(w, h, 3, seed=w, tff=bool(tff))
+    got = lib.yadif_frame(fr[0], fr[1], fr[2], og.FMT_I420, w, h, 1, tff)
+    assert np.array_equal(got, oracle.yadif_frame(fr[0], fr[1], fr[2], w, h, 1, tff))
+    n = [noise_i420(w, h, s) for s in (1, 2, 3)]
+    got = lib.yadif_frame(n[0], n[1], n[2], og.FMT_I420, w, h, 1, tff)
+    assert np.array_equal(got, oracle.yadif_frame(n[0], n[1], n[2], w, h, 1, tff))
+
+
+def test_yadif_frame_16bit(lib, og, oracle):
+    w, h = 130, 74
+    fr = interlaced_sequence(w, h, 3, seed=9, bps=2)
+    got = lib.yadif_frame(fr[0], fr[1], fr[2], og.FMT_I420P10, w, h, 1, 1)
+    assert np.array_equal(got, oracle.yadif_frame(fr[0], fr[1], fr[2], w, h, 1, 1, bps=2))
+
+
+def _oracle_ladder(oracle, frame, w, h, rungs, og):
+    out = []
+    for (dw, dh, fmt) in rungs:
+        i420 = oracle.scale_i420(frame, w, h, dw, dh)
+        out.append(oracle.i420_to_nv12(i420, dw, dh) if fmt == og.FMT_NV12 else i420)
+    return out
+
+
+def test_channel_stream_cfg1_shape(lib, og, oracle):
+    """cfg1 in miniature: interlaced TFF source -> yadif(all) -> {full, 2/3, 1/3} I420 rungs, thumbnails every 3rd frame."""
+    w, h = 192, 108
+    rungs = [(192, 108, og.FMT_I420), (128, 72, og.FMT_I420), (64, 36, og.FMT_I420)]
+    ch = og.Channel(lib, og.make_cfg(w, h, rungs, deint=og.DEINT_ALL, thumb=(44, 36, 3)))
+    frames = interlaced_sequence(w, h, 8, seed=3)
+    ref = oracle.YadifStream(w, h)
+    produced = 0
+    for i, f in enumerate(frames):
+        r = ch.submit(f, interlaced=1, tff=1, pts=1000 + i, dts=900 + i, opaque=0x1000 + i)
+        want = ref.push(f, 1, 1, tag=i)
+        if want is None:
+            assert r is None and i == 0
+            continue
+        produced += 1
+        deint, tag = want
+        assert r["opaque"] == 0x1000 + tag and r["pts"] == 1000 + tag and r["dts"] == 900 + tag
+        for got, exp in zip(r["rungs"], _oracle_ladder(oracle, deint, w, h, rungs, og)):
+            assert np.array_equal(got, exp)
+        if produced % 3 == 0:
+            assert np.array_equal(r["thumbnail"], oracle.scale_i420(deint, w, h, 44, 36))
+        else:
+            assert r["thumbnail"] is None
+    ch.close()
+
+
+def test_channel_reset_and_bff(lib, og, oracle):
+    w, h = 96, 64
+    rungs = [(64, 40, og.FMT_NV12)]                      # no full-size rung: yadif goes through the scratch frame
+    ch = og.Channel(lib, og.make_cfg(w, h, rungs, deint=og.DEINT_ALL))
+    frames = interlaced_sequence(w, h, 6, seed=4, tff=False)
+    ref = oracle.YadifStream(w, h)
+    for i, f in enumerate(frames):
+        if i == 3:                                       # source_discontinuity (transvideo.c:1959-1970)
+            ch.reset()
+            ref.reset()
+        r = ch.submit(f, interlaced=1, tff=0)
+        want = ref.push(f, 1, 0)
+        assert (r is None) == (want is None)
+        if want is not None:
+            assert np.array_equal(r["rungs"][0], _oracle_ladder(oracle, want[0], w, h, rungs, og)[0])
+    ch.close()
+
+
+def test_channel_flagged_only_passes_progressive_through(lib, og, oracle):
+    """cfg2 in miniature: progressive-flagged 60000/1001 => "yadif=0:-1:1": frames pass through one frame late."""
+    w, h = 192, 108
+    rungs = [(192, 108, og.FMT_NV12), (128, 72, og.FMT_NV12), (96, 54, og.FMT_NV12), (64, 36, og.FMT_NV12), (42, 24, og.FMT_NV12)]
+    ch = og.Channel(lib, og.make_cfg(w, h, rungs, deint=og.DEINT_FLAGGED))
+    frames = [natural_i420(w, h, 7, shift=3.0 * i) for i in range(4)]
+    assert ch.submit(frames[0], interlaced=0) is None
+    for i in range(1, 4):
+        r = ch.submit(frames[i], interlaced=0)
+        for got, exp in zip(r["rungs"], _oracle_ladder(oracle, frames[i - 1], w, h, rungs, og)):
+            assert np.array_equal(got, exp)
+    # a flagged frame in the same stream is deinterlaced
+    il = interlaced_sequence(w, h, 3, seed=8)
+    ch.reset()
+    ref = oracle.YadifStream(w, h, deint_flagged_only=True)
+    for f, flag in ((frames[0], 0), (il[1], 1), (il[2], 1), (frames[1], 0)):
+        r = ch.submit(f, interlaced=flag, tff=1)
+        want = ref.push(f, flag, 1)
+        assert (r is None) == (want is None)
+        if want is not None:
+            assert np.array_equal(r["rungs"][1], _oracle_ladder(oracle, want[0], w, h, rungs[1:2], og)[0])
+    ch.close()
+
+
+def test_bypass_is_plain_sws_scale(lib, og, oracle):
+    w, h = 130, 74
+    rungs = [(130, 74, og.FMT_I420), (66, 38, og.FMT_I420)]
+    ch = og.Channel(lib, og.make_cfg(w, h, rungs, deint=og.DEINT_BYPASS, target=og.TARGET_B))
+    for s in range(3):
+        f = noise_i420(w, h, 50 + s)
+        r = ch.submit(f, opaque=s + 1)
+        assert r["opaque"] == s + 1
+        assert np.array_equal(r["rungs"][0], f)
+        assert np.array_equal(r["rungs"][1], oracle.scale_i420(f, w, h, 66, 38, oracle.BICUBIC, oracle.TARGET_B))
+    ch.close()
+
+
+def test_batch_mixed_channels_one_launch(lib, og, oracle):
+    """Several channels with different geometry, depth and deinterlace policy advanced by ONE fused ladder launch."""
+    specs = [
+        dict(w=192, h=108, fmt=og.FMT_I420, rungs=[(192, 108, og.FMT_I420), (128, 72, og.FMT_I420)], deint=og.DEINT_ALL),
+        dict(w=192, h=108, fmt=og.FMT_I420, rungs=[(128, 72, og.FMT_NV12), (64, 36, og.FMT_NV12)], deint=og.DEINT_FLAGGED),
+        dict(w=256, h=144, fmt=og.FMT_P010, rungs=[(256, 144, og.FMT_P010), (128, 72, og.FMT_P010)], deint=og.DEINT_BYPASS),
+        dict(w=130, h=74, fmt=og.FMT_I420, rungs=[(66, 38, og.FMT_I420)], deint=og.DEINT_ALL),
+    ]
+    chans = [og.Channel(lib, og.make_cfg(s["w"], s["h"], s["rungs"], src_fmt=s["fmt"], deint=s["deint"],
+                                         filt=og.FILTER_LANCZOS if s["fmt"] == og.FMT_P010 else og.FILTER_BICUBIC))
+             for s in specs]
+    batch = og.Batch(lib, chans)
+    seqs = [interlaced_sequence(192, 108, 4, seed=1), [natural_i420(192, 108, 7, shift=i) for i in range(4)],
+            [noise_p010(256, 144, 60 + i) for i in range(4)], interlaced_sequence(130, 74, 4, seed=2)]
+    refs = [oracle.YadifStream(192, 108), None, None, oracle.YadifStream(130, 74)]
+    for t in range(4):
+        frames = [seqs[k][t] for k in range(4)]
+        if t == 2:
+            frames[3] = None                              # a channel may sit a step out
+        res = batch.submit(frames, interlaced=1, tff=1)
+        assert batch.last_launches >= 1
+        # channel 0: yadif all
+        want = refs[0].push(frames[0], 1, 1)
+        assert (res[0] is None) == (want is None)
+        if want is not None:
+            assert np.array_equal(res[0]["rungs"][0], want[0])
+            assert np.array_equal(res[0]["rungs"][1], oracle.scale_i420(want[0], 192, 108, 128, 72))
+        # channel 1: flagged-only, but flagged interlaced here => deinterlaced too; compare with stream semantics
+        if t == 0:
+            assert res[1] is None
+        # channel 2: P010 bypass
+        assert np.array_equal(res[2]["rungs"][0], frames[2])
+        assert np.array_equal(res[2]["rungs"][1], oracle.scale_p010(frames[2], 256, 144, 128, 72, oracle.LANCZOS))
+        # channel 3
+        if frames[3] is None:
+            assert res[3] is None
+        else:
+            want = refs[3].push(frames[3], 1, 1)
+            assert (res[3] is None) == (want is None)
+            if want is not None:
+                assert np.array_equal(res[3]["rungs"][0], oracle.scale_i420(want[0], 130, 74, 66, 38))
+    batch.close()
+    for c in chans:
+        c.close()
+
+
+def test_device_resident_frames_and_pools(lib, og, oracle):
+    """Zero-copy mode: source frames and rung surfaces live in device pools (mempool.h discipline); the library
+    reports which inputs it has stopped referencing (memory_return point of transvideo.c:2410)."""
+    w, h = 192, 108
+    rungs = [(192, 108, og.FMT_NV12, 256), (128, 72, og.FMT_NV12, 256)]
+    cfg = og.make_cfg(w, h, rungs, deint=og.DEINT_FLAGGED)
+    ch = og.Channel(lib, cfg)
+    src_pool = og.Pool(lib, 0, og.MEM_DEVICE, 4, lib.frame_bytes(og.FMT_I420, w, h))
+    out_pools = [og.Pool(lib, 0, og.MEM_DEVICE, 2, ch.rung_bytes[r]) for r in range(2)]
+    assert src_pool.unused() == 4
+    frames = [noise_i420(w, h, 70 + i) for i in range(5)]
+    held = []
+    for i, f in enumerate(frames):
+        d = src_pool.take()
+        assert d
+        held.append(d)
+        lib.to_device(d, f)
+        dsts = [p.take() for p in out_pools]
+        r = ch.submit(d, interlaced=0, device_dst=dsts)
+        if r is None:
+            assert i == 0
+        else:
+            exp = frames[i - 1]
+            for k, (dw, dh, fmt, al) in enumerate(rungs):
+                got = lib.from_device(dsts[k], ch.rung_bytes[k])
+                lay = lib.rung_layout(cfg.rung[k])
+                ref = oracle.i420_to_nv12(oracle.scale_i420(exp, w, h, dw, dh), dw, dh)
+                y = got[lay[0][0]: lay[0][0] + lay[0][1] * dh].reshape(dh, lay[0][1])[:, :dw]
+                uv = got[lay[1][0]: lay[1][0] + lay[1][1] * (dh // 2)].reshape(dh // 2, lay[1][1])[:, :dw]
+                assert np.array_equal(y.ravel(), ref[: dw * dh]) and np.array_equal(uv.ravel(), ref[dw * dh:])
+            for p_ in r["released"]:
+                assert p_ in held
+                held.remove(p_)
+                assert src_pool.give_back(p_) == 0
+        for p, d_ in zip(out_pools, dsts):
+            assert p.give_back(d_) == 0
+    assert len(held) <= 3 and src_pool.unused() == 4 - len(held)
+    assert src_pool.give_back(held[0]) == 0 and src_pool.give_back(held[0]) < 0      # double return is refused
+    ch.close()
+    src_pool.close()
+    for p in out_pools:
+        p.close()
+
+
+def test_bad_arguments_are_refused(lib, og):
+    with pytest.raises(og.OttGpuError):
+        og.Channel(lib, og.make_cfg(192, 108, [(128, 72, og.FMT_P010)]))                     # depth mismatch
+    with pytest.raises(og.OttGpuError):
+        og.Channel(lib, og.make_cfg(192, 108, [(128, 72, og.FMT_P010)], src_fmt=og.FMT_P010, deint=og.DEINT_ALL))
+    with pytest.raises(og.OttGpuError):
+        og.Channel(lib, og.make_cfg(192, 108, [(128, 72, og.FMT_I420)] * 9))
+    with pytest.raises(og.OttGpuError):
+        og.Channel(lib, og.make_cfg(192, 108, [(0, 72, og.FMT_I420)]))

@@ -1,0 +1,138 @@
+"""Parity of the ladder scaler (the sws_scale replacement, transvideo.c:1576-1581 / 2169-2174) through the C ABI:
+bit-exact against the CPU oracle (itself pinned to libswscale 8.0.1) and against the committed libswscale fixtures.
+Every test runs on the CPU emulation of the kernel source (tier `emu`) and on the B200 (tier `gpu`)."""
+import hashlib, json, os, re
+import numpy as np
+import pytest
+from conftest import noise_i420, noise_p010, natural_i420, split_i420, chroma_dims
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+SMALL = np.load(os.path.join(G, "swscale_small.npz"))
+DIGESTS = json.load(open(os.path.join(G, "swscale_digests.json")))["digests"]
+KEY = re.compile(r"(i420|p010)_(bicubic|lanczos)_([AB])_(\d+)x(\d+)_(\d+)x(\d+)_s(\d+)")
+
+
+def _run_key(lib, og, key):
+    fmt, kern, tgt, sw, sh, dw, dh, seed = KEY.fullmatch(key).groups()
+    sw, sh, dw, dh, seed = map(int, (sw, sh, dw, dh, seed))
+    filt = og.FILTER_BICUBIC if kern == "bicubic" else og.FILTER_LANCZOS
+    target = og.TARGET_A if tgt == "A" else og.TARGET_B
+    if fmt == "i420":
+        return lib.scale_frame(noise_i420(sw, sh, seed), og.FMT_I420, sw, sh, dw, dh, filt=filt, target=target)
+    return lib.scale_frame(noise_p010(sw, sh, seed), og.FMT_P010, sw, sh, dw, dh, filt=filt, target=target)
+
+
+@pytest.mark.parametrize("key", sorted(SMALL.files))
+def test_matches_libswscale_fixture(lib, og, key):
+    got = _run_key(lib, og, key)
+    assert np.array_equal(got, SMALL[key]), "%s: %d differing samples" % (key, int((got != SMALL[key]).sum()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", sorted(DIGESTS))
+def test_matches_libswscale_digest_full_size(real_lib, og, key):
+    # BASELINE full sizes (1080p noise seed 1234, 2160p P010 seed 99): md5 of the real library's output
+    assert hashlib.md5(_run_key(real_lib, og, key).tobytes()).hexdigest() == DIGESTS[key]
+
+
+CASES = [  # sw, sh, dw, dh : ragged / odd / upscale / one-axis / near-unity
+    (192, 108, 128, 72), (192, 108, 96, 54), (192, 108, 64, 36), (854, 480, 426, 240), (427, 241, 213, 120),
+    (320, 180, 480, 270), (320, 180, 320, 120), (320, 180, 212, 180), (320, 180, 318, 178), (640, 360, 58, 46),
+    (130, 74, 66, 38),
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("filt", ["bicubic", "lanczos"])
+def test_i420_vs_oracle(lib, og, oracle, case, filt):
+    sw, sh, dw, dh = case
+    src = natural_i420(sw, sh, 7) if (sw + dw) % 3 else noise_i420(sw, sh, 21)
+    f, k = (og.FILTER_BICUBIC, oracle.BICUBIC) if filt == "bicubic" else (og.FILTER_LANCZOS, oracle.LANCZOS)
+    for target in (og.TARGET_A, og.TARGET_B):
+        ref = oracle.scale_i420(src, sw, sh, dw, dh, k, target)
+        got = lib.scale_frame(src, og.FMT_I420, sw, sh, dw, dh, filt=f, target=target)
+        assert np.array_equal(got, ref), (case, filt, target, int((got != ref).sum()))
+
+
+@pytest.mark.parametrize("case", [(192, 108, 128, 72), (854, 480, 426, 240), (320, 180, 320, 180), (130, 74, 66, 38)])
+def test_nv12_is_interleaved_target_a_i420(lib, og, oracle, case):
+    # transvideo.c:543-557: the reference's NV12 = byte interleave of the I420 result
+    sw, sh, dw, dh = case
+    src = noise_i420(sw, sh, 33)
+    ref = oracle.i420_to_nv12(oracle.scale_i420(src, sw, sh, dw, dh), dw, dh)
+    got = lib.scale_frame(src, og.FMT_I420, sw, sh, dw, dh, dst_fmt=og.FMT_NV12)
+    assert np.array_equal(got, ref)
+
+
+def test_pitch_aligned_surfaces(lib, og, oracle):
+    sw, sh, dw, dh = 320, 180, 208, 118
+    src = noise_i420(sw, sh, 34)
+    ref = oracle.i420_to_nv12(oracle.scale_i420(src, sw, sh, dw, dh), dw, dh)
+    got = lib.scale_frame(src, og.FMT_I420, sw, sh, dw, dh, dst_fmt=og.FMT_NV12, pitch_align=256)
+    (oy, py), (ouv, puv) = lib.rung_layout(og.RungCfg(dw, dh, og.FMT_NV12, 256))
+    assert py == 256 and puv == 256
+    y = got[oy: oy + py * dh].reshape(dh, py)[:, :dw]
+    uv = got[ouv: ouv + puv * (dh // 2)].reshape(dh // 2, puv)[:, :dw]
+    assert np.array_equal(y.ravel(), ref[: dw * dh]) and np.array_equal(uv.ravel(), ref[dw * dh:])
+
+
+@pytest.mark.parametrize("case", [(256, 144, 128, 72), (256, 144, 170, 96), (256, 144, 86, 48), (128, 72, 256, 144),
+                                  (256, 144, 256, 144), (258, 146, 130, 74)])
+def test_p010_vs_oracle(lib, og, oracle, case):
+    sw, sh, dw, dh = case
+    src = noise_p010(sw, sh, 40)
+    for f, k in ((og.FILTER_LANCZOS, oracle.LANCZOS), (og.FILTER_BICUBIC, oracle.BICUBIC)):
+        for target in (og.TARGET_A, og.TARGET_B):
+            ref = oracle.scale_p010(src, sw, sh, dw, dh, k, target)
+            got = lib.scale_frame(src, og.FMT_P010, sw, sh, dw, dh, filt=f, target=target)
+            assert np.array_equal(got, ref), (case, f, target, int((got != ref).sum()))
+
+
+def test_extreme_values(lib, og, oracle):
+    # checkerboard 0/255, all-0, all-255: exercises the 15-bit clip of the H pass and the 16-bit wraparound of target A
+    sw, sh, dw, dh = 192, 108, 128, 72
+    cw, ch = chroma_dims(sw, sh)
+    yy, xx = np.mgrid[0:sh, 0:sw]
+    checker = (((yy + xx) & 1) * 255).astype(np.uint8)
+    for plane in (checker, np.zeros((sh, sw), np.uint8), np.full((sh, sw), 255, np.uint8), (((yy // 3 + xx // 5) & 1) * 255).astype(np.uint8)):
+        src = np.concatenate([plane.ravel(), plane[:ch, :cw].ravel(), plane[:ch, :cw][::-1].ravel()])
+        for target in (og.TARGET_A, og.TARGET_B):
+            for f, k in ((og.FILTER_BICUBIC, oracle.BICUBIC), (og.FILTER_LANCZOS, oracle.LANCZOS)):
+                ref = oracle.scale_i420(src, sw, sh, dw, dh, k, target)
+                got = lib.scale_frame(src, og.FMT_I420, sw, sh, dw, dh, filt=f, target=target)
+                assert np.array_equal(got, ref)
+
+
+def test_thumbnail_size_filter(lib, og, oracle):
+    # the 176x144 thumbnail from a quarter-size source keeps the long-filter code path (taps > 24) in the CPU tier
+    sw, sh = 960, 540
+    src = noise_i420(sw, sh, 41)
+    ref = oracle.scale_i420(src, sw, sh, 176, 144)
+    got = lib.scale_frame(src, og.FMT_I420, sw, sh, 176, 144)
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", ["cfg1", "cfg2", "cfg3", "thumb"])
+def test_baseline_full_size_ladders(real_lib, og, oracle, cfg):
+    """BASELINE.json configs at full size, every rung against the oracle."""
+    if cfg == "cfg3":
+        sw, sh = 3840, 2160
+        src = noise_p010(sw, sh, 99)
+        rungs = [(3840, 2160), (2560, 1440), (1920, 1080), (1280, 720), (960, 540), (640, 360)]
+        for dw, dh in rungs:
+            ref = oracle.scale_p010(src, sw, sh, dw, dh, oracle.LANCZOS, oracle.TARGET_A)
+            got = real_lib.scale_frame(src, og.FMT_P010, sw, sh, dw, dh, filt=og.FILTER_LANCZOS)
+            assert np.array_equal(got, ref), (dw, dh)
+        return
+    sw, sh = 1920, 1080
+    src = natural_i420(sw, sh, 7)
+    rungs = {"cfg1": [(1920, 1080), (1280, 720), (640, 360)],
+             "cfg2": [(1920, 1080), (1280, 720), (960, 540), (640, 360), (416, 234)], "thumb": [(176, 144)]}[cfg]
+    for dw, dh in rungs:
+        i420 = oracle.scale_i420(src, sw, sh, dw, dh)
+        if cfg == "cfg2":
+            got = real_lib.scale_frame(src, og.FMT_I420, sw, sh, dw, dh, dst_fmt=og.FMT_NV12)
+            assert np.array_equal(got, oracle.i420_to_nv12(i420, dw, dh)), (dw, dh)
+        else:
+            assert np.array_equal(real_lib.scale_frame(src, og.FMT_I420, sw, sh, dw, dh), i420), (dw, dh)
