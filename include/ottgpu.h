@@ -68,6 +68,8 @@ typedef struct ottgpu_cfg {
     int deint;                 /* OTTGPU_DEINT_* */
     int thumb_width, thumb_height; /* THUMBNAIL_WIDTH/HEIGHT 176x144, transvideo.c:157-158; 0 = no thumbnails */
     int thumb_period;          /* 150, transvideo.c:2160-2161 */
+    int thumb_phase;           /* initial value of the thumbnail counter (0 in the reference); lets a multi-channel
+                                  process stagger its channels' thumbnails */
     void *stream;              /* optional cudaStream_t to run on (NULL: the channel creates its own) */
 } ottgpu_cfg;
 
@@ -133,6 +135,10 @@ void ottgpu_batch_destroy(ottgpu_batch *b);
 /* counters for bench.py: kernels launched / work items (CTAs) in the last submit */
 int  ottgpu_batch_last_launches(const ottgpu_batch *b);
 int  ottgpu_batch_last_items(const ottgpu_batch *b);
+/* device-side timing of the ladder launches (CUDA events recorded on the batch's stream around each launch).
+ * enable != 0 starts/reset accumulation; read (after ottgpu_batch_wait) returns the summed milliseconds and count. */
+int  ottgpu_batch_timing(ottgpu_batch *b, int enable);
+int  ottgpu_batch_timing_read(ottgpu_batch *b, double *ms_sum, int *launches);
 
 /* --- pools: the mempool.h discipline (memory_create / memory_take / memory_return / memory_unused,
  *     include/mempool.h:30-35, source/mempool.c:82-265) for device surfaces and pinned host frames ------------------ */

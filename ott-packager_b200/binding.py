@@ -31,7 +31,7 @@ class Cfg(C.Structure):
     _fields_ = [("gpu", C.c_int), ("src_width", C.c_int), ("src_height", C.c_int), ("src_fmt", C.c_int),
                 ("n_rungs", C.c_int), ("rung", RungCfg * MAX_RUNGS), ("filter", C.c_int), ("target", C.c_int),
                 ("deint", C.c_int), ("thumb_width", C.c_int), ("thumb_height", C.c_int), ("thumb_period", C.c_int),
-                ("stream", C.c_void_p)]
+                ("thumb_phase", C.c_int), ("stream", C.c_void_p)]
 
 
 class FrameIn(C.Structure):
@@ -70,6 +70,8 @@ _SIGS = {
     "ottgpu_batch_destroy": (None, [C.c_void_p]),
     "ottgpu_batch_last_launches": (C.c_int, [C.c_void_p]),
     "ottgpu_batch_last_items": (C.c_int, [C.c_void_p]),
+    "ottgpu_batch_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "ottgpu_batch_timing_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "ottgpu_pool_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]),
     "ottgpu_pool_take": (C.c_void_p, [C.c_void_p]),
     "ottgpu_pool_return": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -156,7 +158,7 @@ class Library:
 
 
 def make_cfg(src_w, src_h, rungs, src_fmt=FMT_I420, filt=FILTER_BICUBIC, target=TARGET_A, deint=DEINT_ALL, gpu=0,
-             thumb=(0, 0, 0), stream=None):
+             thumb=(0, 0, 0), stream=None, thumb_phase=0):
     """rungs: list of (w, h, fmt[, pitch_align])"""
     cfg = Cfg()
     cfg.gpu, cfg.src_width, cfg.src_height, cfg.src_fmt = gpu, src_w, src_h, src_fmt
@@ -165,6 +167,7 @@ def make_cfg(src_w, src_h, rungs, src_fmt=FMT_I420, filt=FILTER_BICUBIC, target=
         cfg.rung[i] = RungCfg(r[0], r[1], r[2], r[3] if len(r) > 3 else 0)
     cfg.filter, cfg.target, cfg.deint = filt, target, deint
     cfg.thumb_width, cfg.thumb_height, cfg.thumb_period = thumb
+    cfg.thumb_phase = thumb_phase
     cfg.stream = stream
     return cfg
 
@@ -281,6 +284,14 @@ class Batch:
             bufs.append(c.alloc_out(self.fout[i], None if device_dst is None else device_dst[i]))
         self.submit_raw(SUBMIT_SYNC)
         return [None if b is None else c.collect(self.fout[i], b) for i, (c, b) in enumerate(zip(self.channels, bufs))]
+
+    def timing(self, enable=True):
+        self.lib.check(self.lib.dll.ottgpu_batch_timing(self.handle, int(enable)))
+
+    def timing_read(self):
+        ms, n = C.c_double(), C.c_int()
+        self.lib.check(self.lib.dll.ottgpu_batch_timing_read(self.handle, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     @property
     def last_launches(self):

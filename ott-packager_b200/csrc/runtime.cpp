@@ -109,16 +109,22 @@ struct ottgpu_batch {
     std::vector<ottgpu_channel *> ch;
     int gpu = 0;
     cudaStream_t stream = nullptr;
-    Item *d_items = nullptr, *d_thumb_items = nullptr;
+    Item *d_items = nullptr;
     int n_items = 0, max_thumb_items = 0;
-    std::vector<int> item_begin;                       // per channel range in d_items (unused today, kept for tooling)
     size_t smem_items = 0, smem_thumb = 0;
-    Binding *h_binds = nullptr, *d_binds = nullptr;    // pinned / device
-    YadifJob *h_jobs = nullptr, *d_jobs = nullptr;
-    Item *h_thumb_items = nullptr;
+    // Descriptors are double-buffered so that an ASYNC submit can be prepared while the previous step still runs.
+    struct Set {
+        Binding *h_binds = nullptr, *d_binds = nullptr;    // pinned / device
+        YadifJob *h_jobs = nullptr, *d_jobs = nullptr;
+        Item *h_thumb_items = nullptr, *d_thumb_items = nullptr;
+        cudaEvent_t done = nullptr, k0 = nullptr, k1 = nullptr;
+        bool in_flight = false, timed = false;
+    } set[2];
+    int turn = 0;
     int last_launches = 0, last_items = 0;
-    bool pending = false;
-    struct Thumb { void *host; const uint8_t *dev; size_t bytes; };
+    bool timing = false;
+    double ms_sum = 0.0;
+    int ms_count = 0;
     struct Readback { void *host; const uint8_t *dev; size_t bytes; };
     std::vector<Readback> readbacks;
 };
@@ -240,6 +246,7 @@ int ottgpu_channel_create(const ottgpu_cfg *cfg, ottgpu_channel **out)
     c->plan = plan;
     c->gpu = cfg->gpu;
     c->src_bytes = packed_frame_bytes(cfg->src_fmt, cfg->src_width, cfg->src_height);
+    c->thumb_count = cfg->thumb_period > 0 ? ((cfg->thumb_phase % cfg->thumb_period) + cfg->thumb_period) % cfg->thumb_period : 0;
     if (cfg->stream) {
         c->stream = (cudaStream_t)cfg->stream;
     } else {
@@ -312,7 +319,6 @@ int ottgpu_batch_create(ottgpu_channel **channels, int n, ottgpu_batch **out)
     std::vector<Item> all;
     for (int i = 0; i < n; ++i) {
         const Plan &p = *channels[i]->plan;
-        b->item_begin.push_back((int)all.size());
         for (Item it : p.items) { it.chan = (uint16_t)i; all.push_back(it); }
         b->smem_items = std::max(b->smem_items, p.smem_items);
         b->smem_thumb = std::max(b->smem_thumb, p.smem_thumb);
@@ -321,12 +327,17 @@ int ottgpu_batch_create(ottgpu_channel **channels, int n, ottgpu_batch **out)
     b->n_items = (int)all.size();
     CK(cudaMalloc((void **)&b->d_items, std::max<size_t>(all.size(), 1) * sizeof(Item)));
     if (!all.empty()) CK(cudaMemcpy(b->d_items, all.data(), all.size() * sizeof(Item), cudaMemcpyHostToDevice));
-    CK(cudaMalloc((void **)&b->d_thumb_items, std::max(b->max_thumb_items, 1) * sizeof(Item)));
-    CK(cudaMallocHost((void **)&b->h_thumb_items, std::max(b->max_thumb_items, 1) * sizeof(Item)));
-    CK(cudaMalloc((void **)&b->d_binds, n * sizeof(Binding)));
-    CK(cudaMallocHost((void **)&b->h_binds, n * sizeof(Binding)));
-    CK(cudaMalloc((void **)&b->d_jobs, n * sizeof(YadifJob)));
-    CK(cudaMallocHost((void **)&b->h_jobs, n * sizeof(YadifJob)));
+    for (ottgpu_batch::Set &st : b->set) {
+        CK(cudaMalloc((void **)&st.d_thumb_items, std::max(b->max_thumb_items, 1) * sizeof(Item)));
+        CK(cudaMallocHost((void **)&st.h_thumb_items, std::max(b->max_thumb_items, 1) * sizeof(Item)));
+        CK(cudaMalloc((void **)&st.d_binds, n * sizeof(Binding)));
+        CK(cudaMallocHost((void **)&st.h_binds, n * sizeof(Binding)));
+        CK(cudaMalloc((void **)&st.d_jobs, n * sizeof(YadifJob)));
+        CK(cudaMallocHost((void **)&st.h_jobs, n * sizeof(YadifJob)));
+        CK(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
+        CK(cudaEventCreate(&st.k0));
+        CK(cudaEventCreate(&st.k1));
+    }
     *out = b.release();
     return OTTGPU_OK;
 }
@@ -337,25 +348,73 @@ void ottgpu_batch_destroy(ottgpu_batch *b)
     cudaSetDevice(b->gpu);
     cudaStreamSynchronize(b->stream);
     cudaFree(b->d_items);
-    cudaFree(b->d_thumb_items);
-    cudaFree(b->d_binds);
-    cudaFree(b->d_jobs);
-    cudaFreeHost(b->h_binds);
-    cudaFreeHost(b->h_jobs);
-    cudaFreeHost(b->h_thumb_items);
+    for (ottgpu_batch::Set &st : b->set) {
+        cudaFree(st.d_thumb_items);
+        cudaFree(st.d_binds);
+        cudaFree(st.d_jobs);
+        cudaFreeHost(st.h_binds);
+        cudaFreeHost(st.h_jobs);
+        cudaFreeHost(st.h_thumb_items);
+        if (st.done) cudaEventDestroy(st.done);
+        if (st.k0) cudaEventDestroy(st.k0);
+        if (st.k1) cudaEventDestroy(st.k1);
+    }
     delete b;
 }
 
 int ottgpu_batch_last_launches(const ottgpu_batch *b) { return b ? b->last_launches : 0; }
 int ottgpu_batch_last_items(const ottgpu_batch *b) { return b ? b->last_items : 0; }
 
+}  // extern "C"
+
+namespace {
+// the step that used this descriptor set has finished: harvest its kernel time
+int retire(ottgpu_batch *b, ottgpu_batch::Set &st)
+{
+    if (!st.in_flight) return OTTGPU_OK;
+    CK(cudaEventSynchronize(st.done));
+    if (st.timed) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, st.k0, st.k1));
+        b->ms_sum += ms;
+        b->ms_count++;
+        st.timed = false;
+    }
+    st.in_flight = false;
+    return OTTGPU_OK;
+}
+}  // namespace
+
+extern "C" {
+
 int ottgpu_batch_wait(ottgpu_batch *b)
 {
     if (!b) return fail(OTTGPU_ERR_ARG, "null batch");
-    if (!b->pending) return OTTGPU_OK;
     CK(cudaSetDevice(b->gpu));
     CK(cudaStreamSynchronize(b->stream));
-    b->pending = false;
+    for (ottgpu_batch::Set &st : b->set) {
+        int rc = retire(b, st);
+        if (rc) return rc;
+    }
+    return OTTGPU_OK;
+}
+
+int ottgpu_batch_timing(ottgpu_batch *b, int enable)
+{
+    if (!b) return fail(OTTGPU_ERR_ARG, "null batch");
+    int rc = ottgpu_batch_wait(b);
+    if (rc) return rc;
+    b->timing = enable != 0;
+    b->ms_sum = 0.0;
+    b->ms_count = 0;
+    return OTTGPU_OK;
+}
+
+int ottgpu_batch_timing_read(ottgpu_batch *b, double *ms_sum, int *launches)
+{
+    if (!b || !ms_sum || !launches) return fail(OTTGPU_ERR_ARG, "null argument");
+    *ms_sum = b->ms_sum;
+    *launches = b->ms_count;
     return OTTGPU_OK;
 }
 
@@ -363,8 +422,10 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
 {
     if (!b || !in || !out) return fail(OTTGPU_ERR_ARG, "null argument");
     CK(cudaSetDevice(b->gpu));
-    if (b->pending) {                                   // one step in flight per batch: pinned descriptors are reused
-        int rc = ottgpu_batch_wait(b);
+    ottgpu_batch::Set &st = b->set[b->turn];
+    b->turn ^= 1;
+    {                                                   // at most two steps in flight: this set's previous user must be done
+        int rc = retire(b, st);
         if (rc) return rc;
     }
     const int n = (int)b->ch.size();
@@ -377,8 +438,8 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
         ottgpu_channel *c = b->ch[i];
         const Plan &plan = *c->plan;
         const ottgpu_cfg &cfg = c->cfg;
-        Binding &bind = b->h_binds[i];
-        YadifJob &job = b->h_jobs[i];
+        Binding &bind = st.h_binds[i];
+        YadifJob &job = st.h_jobs[i];
         std::memset(&bind, 0, sizeof(bind));
         std::memset(&job, 0, sizeof(job));
         bind.plan = plan.dev;
@@ -499,7 +560,7 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
             if (!host) return fail(OTTGPU_ERR_NOMEM, "malloc(thumbnail) failed");
             o.thumbnail = host;
             b->readbacks.push_back({host, c->stage[ts], plan.layout[ts].bytes});
-            for (Item it : plan.thumb_items) { it.chan = (uint16_t)i; b->h_thumb_items[n_thumb_items++] = it; }
+            for (Item it : plan.thumb_items) { it.chan = (uint16_t)i; st.h_thumb_items[n_thumb_items++] = it; }
         }
 
         if (cfg.deint == OTTGPU_DEINT_BYPASS) {        // nothing is kept across calls
@@ -510,26 +571,32 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
     }
 
     // ---- 5. enqueue: descriptors, yadif, ladder, thumbnails, read-backs
-    CK(cudaMemcpyAsync(b->d_binds, b->h_binds, n * sizeof(Binding), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(st.d_binds, st.h_binds, n * sizeof(Binding), cudaMemcpyHostToDevice, s));
     if (n_jobs) {
-        CK(cudaMemcpyAsync(b->d_jobs, b->h_jobs, n * sizeof(YadifJob), cudaMemcpyHostToDevice, s));
-        CK(launch_yadif(b->d_jobs, n, max_w, max_h, s));
+        CK(cudaMemcpyAsync(st.d_jobs, st.h_jobs, n * sizeof(YadifJob), cudaMemcpyHostToDevice, s));
+        CK(launch_yadif(st.d_jobs, n, max_w, max_h, s));
         b->last_launches++;
     }
     if (live && b->n_items) {
-        CK(launch_ladder(b->d_items, b->n_items, b->d_binds, b->smem_items, s));
+        if (b->timing) CK(cudaEventRecord(st.k0, s));
+        CK(launch_ladder(b->d_items, b->n_items, st.d_binds, b->smem_items, s));
+        if (b->timing) {
+            CK(cudaEventRecord(st.k1, s));
+            st.timed = true;
+        }
         b->last_launches++;
         b->last_items += b->n_items;
     }
     if (n_thumb_items) {
-        CK(cudaMemcpyAsync(b->d_thumb_items, b->h_thumb_items, n_thumb_items * sizeof(Item), cudaMemcpyHostToDevice, s));
-        CK(launch_ladder(b->d_thumb_items, n_thumb_items, b->d_binds, b->smem_thumb, s));
+        CK(cudaMemcpyAsync(st.d_thumb_items, st.h_thumb_items, n_thumb_items * sizeof(Item), cudaMemcpyHostToDevice, s));
+        CK(launch_ladder(st.d_thumb_items, n_thumb_items, st.d_binds, b->smem_thumb, s));
         b->last_launches++;
         b->last_items += n_thumb_items;
     }
     for (const ottgpu_batch::Readback &r : b->readbacks)
         CK(cudaMemcpyAsync(r.host, r.dev, r.bytes, cudaMemcpyDeviceToHost, s));
-    b->pending = true;
+    CK(cudaEventRecord(st.done, s));
+    st.in_flight = true;
     if (flags & OTTGPU_SUBMIT_ASYNC) return OTTGPU_OK;
     return ottgpu_batch_wait(b);
 }
