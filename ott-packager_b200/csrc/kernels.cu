@@ -10,22 +10,22 @@
 
 namespace ottgpu {
 
-__global__ void __launch_bounds__(kThreads) ladder_kernel(const Item *__restrict__ items, const Binding *__restrict__ binds)
+__global__ void __launch_bounds__(kThreads, 3) ladder_kernel(const Item *__restrict__ items, const Binding *__restrict__ binds)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const Item it = items[blockIdx.x];
     const Binding &b = binds[it.chan];
     const int tid = threadIdx.x;
-    TileCtx c;
-    const int what = item_prepare(it, b, smem, c);
+    TileGeom g;
+    const int what = item_prepare(it, b, g);
     if (what == 0) return;
     if (what == 2) { item_copy(tid, it, b); return; }
-    phase_tables(tid, c);
-    phase_stage(tid, c);
+    phase_tables(tid, g, smem);
+    phase_stage(tid, g, smem);
     __syncthreads();
-    phase_hpass(tid, c);
+    phase_hpass(tid, g, smem);
     __syncthreads();
-    phase_vpass(tid, c);
+    phase_vpass(tid, g, smem);
 }
 
 __global__ void __launch_bounds__(256) yadif_kernel(const YadifJob *__restrict__ jobs)

@@ -1,5 +1,5 @@
-// The ladder scaler's per-CTA work, written as barrier-separated PHASES: phase(tid, ctx) is called by every thread of
-// the CTA (kernel: threadIdx.x, with __syncthreads() between phases).  The same text compiles as plain C++ when
+// The ladder scaler's per-CTA work, written as barrier-separated PHASES: phase(tid, geom, smem) is called by every thread
+// of the CTA (kernel: threadIdx.x, with __syncthreads() between phases).  The same text compiles as plain C++ when
 // OTTGPU_EMULATE is defined, which tests/emu uses to run the CTA logic thread-by-thread on the CPU *as a test* of the
 // kernel source before GPU time is spent; that build is never part of libottgpu.
 //
@@ -9,12 +9,18 @@
 //   V  8-bit x86   : clip_u8(int16((64+8(vs-1))>>4 + sum (t*c12)>>16) >> 3)      (rows < exact_from, target A)
 //   V  10-bit      : clip10((1<<16 + sum t*c12) >> 17)
 //   one vertical tap (axis unscaled): 8-bit clip_u8((t+64)>>7), 10-bit clip10((t+16)>>5)
+//
+// Shared-memory layout of one tile (all sizes from PlaneTables, so planner and kernel agree):
+//   [ staged source : nplanes * sr_max rows * sw_words 32-bit words ]   4 (8-bit) or 2 (16-bit) samples per word
+//   [ H-pass result : nplanes * (sr_max+1) rows * mid_pitch int16   ]   mid_pitch = tw (32|64), rows 16-byte aligned
+//   [ V coefficients: th * vtaps int16 ][ vpos: th int32 ]
 #pragma once
 #include "device_types.h"
 
 #if defined(OTTGPU_EMULATE)
 #include <cstring>
 #define OTT_DEV inline
+#define OTT_UNROLL
 #if !defined(__CUDACC__) && !defined(OTTGPU_EMU_VECTOR_TYPES)
 #define OTTGPU_EMU_VECTOR_TYPES
 struct uint2 { uint32_t x, y; };
@@ -36,6 +42,7 @@ template <typename T> inline T ott_ldg(const T *p) { return *p; }
 }  // namespace ottgpu
 #else
 #define OTT_DEV __device__ __forceinline__
+#define OTT_UNROLL _Pragma("unroll")
 namespace ottgpu {
 OTT_DEV uint32_t ott_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
 OTT_DEV int ott_dp4a_us(uint32_t a, uint32_t b, int c)
@@ -55,178 +62,192 @@ OTT_DEV int ott_min(int a, int b) { return a < b ? a : b; }
 OTT_DEV int ott_max(int a, int b) { return a > b ? a : b; }
 OTT_DEV int ott_clip(int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); }
 
-// Everything one tile needs, resolved once per CTA (thread-uniform).
-struct TileCtx {
+// Everything one tile needs, resolved once per CTA (thread-uniform scalars; no shared-memory pointers are kept in
+// here so that the compiler keeps every shared access in the shared address space).
+struct TileGeom {
     const PlaneTables *T;
     int bps;                 // source/destination bytes per sample
     int nplanes;             // 1 luma, 2 chroma pair
     int x0, y0, tw, th;      // output tile
     int sy0, sr;             // source rows [sy0, sy0+sr)
-    int sx0, nwords;         // source columns start (sample index, word aligned) and 32-bit words per staged row
-    int src_pitch_words;     // smem pitch of the staged source
-    int mid_pitch;           // smem pitch (int16 elements) of the H-pass result, even
+    int sx0;                 // first staged source sample (multiple of 16 bytes)
+    int nvec;                // 16-byte vectors staged per row
+    int spw;                 // smem pitch of the staged source, 32-bit words (multiple of 4)
+    int mid_pitch;           // smem pitch (int16 elements) of the H-pass result: 32 or 64
     int tw_log2;             // T->tw is 32 or 64
     int approx_v;
-    // shared memory carve-up
-    uint32_t *src_s;         // [nplanes*sr][src_pitch_words]
-    int16_t *mid_s;          // [nplanes*sr][mid_pitch]
-    int16_t *vc_s;           // [th][vtaps]
-    int32_t *vpos_s;         // [th]
-    // global operands
-    const uint8_t *src[2];   // plane bases (chroma: U,V or the interleaved UV plane twice)
-    int src_pitch[2];        // bytes
+    int off_mid, off_vc, off_vpos;   // byte offsets of the regions inside the tile's shared memory
+    const uint8_t *src0, *src1;      // plane bases (chroma: U,V or the interleaved UV plane twice)
+    int src_pitch0, src_pitch1;      // bytes
     int src_interleaved;     // chroma samples interleaved in the source (P010)
     int src_shift;           // 6 for P010 (MSB aligned), else 0
-    uint8_t *dst[2];
-    int dst_pitch[2];
+    uint8_t *dst0, *dst1;
+    int dst_pitch0, dst_pitch1;
     int dst_interleaved;     // NV12 / P010 chroma writer
     int dst_shift;           // 6 for P010
 };
 
-OTT_DEV size_t tile_smem_bytes(const PlaneTables &T, int nplanes)
-{
-    const int mid_pitch = (T.tw + 1) & ~1;
-    size_t b = (size_t)nplanes * T.sr_max * T.sw_words * 4;      // staged source
-    b += (size_t)nplanes * T.sr_max * mid_pitch * 2;             // H-pass result
-    b += (size_t)T.th * T.vtaps * 2;                             // vertical coefficients of the tile's rows
-    b = (b + 3) & ~(size_t)3;
-    b += (size_t)T.th * 4;                                       // vpos
-    return b;
-}
-
 // ------------------------------------------------------------------------------------------------ phase 0: tables
-OTT_DEV void phase_tables(int tid, const TileCtx &c)
+OTT_DEV void phase_tables(int tid, const TileGeom &g, unsigned char *smem)
 {
-    const PlaneTables &T = *c.T;
-    for (int i = tid; i < c.th * T.vtaps; i += kThreads) c.vc_s[i] = ott_ldg(T.vc + (size_t)c.y0 * T.vtaps + i);
-    for (int i = tid; i < c.th; i += kThreads) c.vpos_s[i] = ott_ldg(T.vpos + c.y0 + i);
+    const PlaneTables &T = *g.T;
+    int16_t *vc_s = reinterpret_cast<int16_t *>(smem + g.off_vc);
+    int32_t *vpos_s = reinterpret_cast<int32_t *>(smem + g.off_vpos);
+    for (int i = tid; i < g.th * T.vtaps; i += kThreads) vc_s[i] = ott_ldg(T.vc + g.y0 * T.vtaps + i);
+    for (int i = tid; i < g.th; i += kThreads) vpos_s[i] = ott_ldg(T.vpos + g.y0 + i);
 }
 
 // ------------------------------------------------------------------------------------------------ phase 1: staging
-// Copies the tile's source window into shared memory, one 32-bit word (4 or 2 samples) per thread step, rows spread
-// over warps so consecutive lanes read consecutive global words.  Samples right of the plane edge read as zero (they
-// only ever meet zero padding coefficients).
-OTT_DEV uint32_t load_word8(const uint8_t *row, int x, int srcW, bool aligned)
+// Copies the tile's source window into shared memory in 16-byte vectors (LDG.128 -> STS.128) when the plane is 16-byte
+// aligned, else sample by sample.  Samples right of the plane edge read as zero (they only meet zero padding taps).
+OTT_DEV uint4 load_vec_slow(const uint8_t *row, int byte_x, int row_bytes)
 {
-    if (aligned && x + 4 <= srcW) return ott_ldg(reinterpret_cast<const uint32_t *>(row + x));
-    uint32_t v = 0;
-    for (int k = 0; k < 4; ++k)
-        if (x + k < srcW) v |= (uint32_t)ott_ldg(row + x + k) << (8 * k);
+    uint32_t w[4] = {0, 0, 0, 0};
+    OTT_UNROLL
+    for (int i = 0; i < 4; ++i) {
+        OTT_UNROLL
+        for (int k = 0; k < 4; ++k)
+            if (byte_x + 4 * i + k < row_bytes) w[i] |= (uint32_t)ott_ldg(row + byte_x + 4 * i + k) << (8 * k);
+    }
+    uint4 v;
+    v.x = w[0]; v.y = w[1]; v.z = w[2]; v.w = w[3];
     return v;
 }
 
-OTT_DEV uint32_t load_word16(const uint8_t *row, int x, int srcW, bool aligned, int shift)
-{
-    uint32_t v;
-    if (aligned && x + 2 <= srcW) {
-        v = ott_ldg(reinterpret_cast<const uint32_t *>(row + 2 * x));
-    } else {
-        v = 0;
-        for (int k = 0; k < 2; ++k)
-            if (x + k < srcW) v |= (uint32_t)ott_ldg(reinterpret_cast<const uint16_t *>(row + 2 * (x + k))) << (16 * k);
-    }
-    return (v >> shift) & (0xffffu >> shift) * 0x10001u;
-}
+OTT_DEV uint32_t shift_mask16(uint32_t v, int shift) { return (v >> shift) & ((0xffffu >> shift) * 0x10001u); }
 
-// interleaved 16-bit chroma (P010): one 32-bit global word = (V<<16 | U) of one chroma sample
-OTT_DEV void load_uv16(const uint8_t *row, int x, int srcW, int shift, uint32_t &u, uint32_t &v)
+OTT_DEV void phase_stage(int tid, const TileGeom &g, unsigned char *smem)
 {
-    uint32_t a = 0, b = 0;   // samples x and x+1
-    if (x < srcW) a = ott_ldg(reinterpret_cast<const uint32_t *>(row + 4 * x));
-    if (x + 1 < srcW) b = ott_ldg(reinterpret_cast<const uint32_t *>(row + 4 * (x + 1)));
-    const uint32_t m = (0xffffu >> shift) * 0x10001u;
-    a = (a >> shift) & m;
-    b = (b >> shift) & m;
-    u = (a & 0xffffu) | (b << 16);
-    v = (a >> 16) | (b & 0xffff0000u);
-}
-
-OTT_DEV void phase_stage(int tid, const TileCtx &c)
-{
-    const PlaneTables &T = *c.T;
-    const int warp = tid >> 5, lane = tid & 31;
-    const int spw = c.bps == 1 ? 4 : 2;                  // samples per word
-    if (c.src_interleaved) {                             // P010 chroma: de-interleave into the two staged planes
-        const bool ok = (((uintptr_t)c.src[0] | (uintptr_t)c.src_pitch[0]) & 3) == 0;
-        (void)ok;                                        // packed P010 rows are always 4-byte aligned (2*2*cw)
-        for (int r = warp; r < c.sr; r += kThreads / 32) {
-            const uint8_t *row = c.src[0] + (size_t)(c.sy0 + r) * c.src_pitch[0];
-            for (int w = lane; w < c.nwords; w += 32) {
-                uint32_t u, v;
-                load_uv16(row, c.sx0 + 2 * w, T.srcW, c.src_shift, u, v);
-                c.src_s[(size_t)r * c.src_pitch_words + w] = u;
-                c.src_s[(size_t)(c.sr + r) * c.src_pitch_words + w] = v;
+    const PlaneTables &T = *g.T;
+    uint32_t *src_s = reinterpret_cast<uint32_t *>(smem);
+    // lanes per staged row: smallest power of two >= nvec (capped at 32)
+    int lpr_log2 = 0;
+    while ((1 << lpr_log2) < g.nvec && lpr_log2 < 5) ++lpr_log2;
+    const int lpr = 1 << lpr_log2, v0 = tid & (lpr - 1), r0 = tid >> lpr_log2, rstep = kThreads >> lpr_log2;
+    if (g.src_interleaved) {
+        // P010 chroma: one 16-byte vector = 4 (U,V) pairs -> 4 U samples + 4 V samples (8 bytes each plane).
+        // g.sx0 counts chroma samples (multiple of 8); staged vectors hold 8 samples, i.e. two global vectors.
+        const int row_bytes = T.srcW * 4;
+        for (int r = r0; r < g.sr; r += rstep) {
+            const uint8_t *row = g.src0 + (size_t)(g.sy0 + r) * g.src_pitch0;
+            uint32_t *su = src_s + (r * g.spw), *sv = src_s + ((g.sr + r) * g.spw);
+            for (int v = v0; v < g.nvec; v += lpr) {
+                const int bx = (g.sx0 + 8 * v) * 4;
+                uint4 a, b;
+                if ((((uintptr_t)row & 15) == 0) && bx + 32 <= row_bytes) {
+                    a = ott_ldg(reinterpret_cast<const uint4 *>(row + bx));
+                    b = ott_ldg(reinterpret_cast<const uint4 *>(row + bx + 16));
+                } else {
+                    a = load_vec_slow(row, bx, row_bytes);
+                    b = load_vec_slow(row, bx + 16, row_bytes);
+                }
+                const uint32_t in[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                uint32_t u[4], w[4];
+                OTT_UNROLL
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t p = shift_mask16(in[2 * k], g.src_shift), q = shift_mask16(in[2 * k + 1], g.src_shift);
+                    u[k] = (p & 0xffffu) | (q << 16);
+                    w[k] = (p >> 16) | (q & 0xffff0000u);
+                }
+                uint4 ou, ov;
+                ou.x = u[0]; ou.y = u[1]; ou.z = u[2]; ou.w = u[3];
+                ov.x = w[0]; ov.y = w[1]; ov.z = w[2]; ov.w = w[3];
+                reinterpret_cast<uint4 *>(su)[v] = ou;
+                reinterpret_cast<uint4 *>(sv)[v] = ov;
             }
         }
         return;
     }
-    for (int p = 0; p < c.nplanes; ++p) {
-        const bool aligned = (((uintptr_t)c.src[p] | (uintptr_t)c.src_pitch[p]) & 3) == 0;
-        for (int r = warp; r < c.sr; r += kThreads / 32) {
-            const uint8_t *row = c.src[p] + (size_t)(c.sy0 + r) * c.src_pitch[p];
-            uint32_t *srow = c.src_s + (size_t)(p * c.sr + r) * c.src_pitch_words;
-            for (int w = lane; w < c.nwords; w += 32) {
-                const int x = c.sx0 + spw * w;
-                srow[w] = c.bps == 1 ? load_word8(row, x, T.srcW, aligned)
-                                     : load_word16(row, x, T.srcW, aligned, c.src_shift);
+    const int row_bytes = T.srcW * g.bps;
+    const int bx0 = g.sx0 * g.bps;
+    for (int p = 0; p < g.nplanes; ++p) {
+        const uint8_t *base = p ? g.src1 : g.src0;
+        const int pitch = p ? g.src_pitch1 : g.src_pitch0;
+        const bool aligned = (((uintptr_t)base | (uintptr_t)pitch) & 15) == 0;
+        for (int r = r0; r < g.sr; r += rstep) {
+            const uint8_t *row = base + (size_t)(g.sy0 + r) * pitch;
+            uint4 *srow = reinterpret_cast<uint4 *>(src_s + (p * g.sr + r) * g.spw);
+            for (int v = v0; v < g.nvec; v += lpr) {
+                const int bx = bx0 + 16 * v;
+                uint4 q = (aligned && bx + 16 <= row_bytes) ? ott_ldg(reinterpret_cast<const uint4 *>(row + bx))
+                                                            : load_vec_slow(row, bx, row_bytes);
+                if (g.bps == 2 && g.src_shift) {
+                    q.x = shift_mask16(q.x, g.src_shift); q.y = shift_mask16(q.y, g.src_shift);
+                    q.z = shift_mask16(q.z, g.src_shift); q.w = shift_mask16(q.w, g.src_shift);
+                }
+                srow[v] = q;
             }
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------ phase 2: H pass
-// Thread = one output column of the tile (coefficients live in registers), striding over the staged rows.
+// Thread = one output column of the tile (its coefficients live in registers), striding over the staged rows.
 // 8-bit: four taps per dp4a, 14-bit coefficient split into signed high byte and unsigned low byte:
 //        sum p*c = 256*sum p*(c>>8) + sum p*(c&255)   (exact)
 template <int HQ>
-OTT_DEV void hpass8(int tid, const TileCtx &c)
+OTT_DEV int hdot8(const uint32_t *w, uint32_t sh, const uint32_t (&hi)[HQ], const uint32_t (&lo)[HQ])
 {
-    const PlaneTables &T = *c.T;
-    const int col = tid & (T.tw - 1), grp = tid >> c.tw_log2, ngroups = kThreads >> c.tw_log2;
-    if (col >= c.tw) return;
-    const int gx = c.x0 + col;
-    const int off = ott_ldg(T.hpos + gx) - c.sx0;
-    const int wi = off >> 2;
+    uint32_t cur = w[0];
+    int ahi = 0;
+    uint32_t alo = 0;
+    OTT_UNROLL
+    for (int q = 0; q < HQ; ++q) {
+        const uint32_t nxt = w[q + 1];
+        const uint32_t a = ott_funnel_r(cur, nxt, sh);
+        ahi = ott_dp4a_us(a, hi[q], ahi);
+        alo = ott_dp4a_uu(a, lo[q], alo);
+        cur = nxt;
+    }
+    return ott_min((ahi * 256 + (int)alo) >> 7, 32767);
+}
+
+template <int HQ>
+OTT_DEV void hpass8(int tid, const TileGeom &g, unsigned char *smem)
+{
+    const PlaneTables &T = *g.T;
+    const int col = tid & (T.tw - 1), grp = tid >> g.tw_log2, ngroups = kThreads >> g.tw_log2;
+    if (col >= g.tw) return;
+    const int gx = g.x0 + col;
+    const int off = ott_ldg(T.hpos + gx) - g.sx0;
     const uint32_t sh = (uint32_t)(off & 3) * 8;
     uint32_t hi[HQ], lo[HQ];
-#pragma unroll
+    OTT_UNROLL
     for (int q = 0; q < HQ; ++q) {
-        hi[q] = ott_ldg(T.hc_hi + (size_t)gx * HQ + q);
-        lo[q] = ott_ldg(T.hc_lo + (size_t)gx * HQ + q);
+        hi[q] = ott_ldg(T.hc_hi + gx * HQ + q);
+        lo[q] = ott_ldg(T.hc_lo + gx * HQ + q);
     }
-    const int nrows = c.nplanes * c.sr;
-    for (int row = grp; row < nrows; row += ngroups) {
-        const uint32_t *w = c.src_s + (size_t)row * c.src_pitch_words + wi;
-        uint32_t cur = w[0];
-        int ahi = 0;
-        uint32_t alo = 0;
-#pragma unroll
-        for (int q = 0; q < HQ; ++q) {
-            const uint32_t nxt = w[q + 1];
-            const uint32_t a = ott_funnel_r(cur, nxt, sh);
-            ahi = ott_dp4a_us(a, hi[q], ahi);
-            alo = ott_dp4a_uu(a, lo[q], alo);
-            cur = nxt;
-        }
-        const int val = ahi * 2 + (int)(alo >> 7);       // == (256*ahi + alo) >> 7
-        c.mid_s[(size_t)row * c.mid_pitch + col] = (int16_t)ott_min(val, 32767);
+    const int nrows = g.nplanes * g.sr;
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(smem) + (off >> 2) + grp * g.spw;
+    int16_t *m = reinterpret_cast<int16_t *>(smem + g.off_mid) + col + grp * g.mid_pitch;
+    const int wstep = ngroups * g.spw, mstep = ngroups * g.mid_pitch;
+    int row = grp;
+    for (; row + ngroups < nrows; row += 2 * ngroups) {       // two rows in flight per thread
+        const int v0 = hdot8<HQ>(w, sh, hi, lo);
+        const int v1 = hdot8<HQ>(w + wstep, sh, hi, lo);
+        m[0] = (int16_t)v0;
+        m[mstep] = (int16_t)v1;
+        w += 2 * wstep;
+        m += 2 * mstep;
     }
+    if (row < nrows) m[0] = (int16_t)hdot8<HQ>(w, sh, hi, lo);
 }
 
 // any tap count: coefficients re-read per row (L1-resident); used for very long filters (thumbnail, 4K->360p lanczos)
-OTT_DEV void hpass8_any(int tid, const TileCtx &c)
+OTT_DEV void hpass8_any(int tid, const TileGeom &g, unsigned char *smem)
 {
-    const PlaneTables &T = *c.T;
-    const int col = tid & (T.tw - 1), grp = tid >> c.tw_log2, ngroups = kThreads >> c.tw_log2;
-    if (col >= c.tw) return;
-    const int gx = c.x0 + col, hq = T.hq;
-    const int off = ott_ldg(T.hpos + gx) - c.sx0;
-    const int wi = off >> 2;
+    const PlaneTables &T = *g.T;
+    const int col = tid & (T.tw - 1), grp = tid >> g.tw_log2, ngroups = kThreads >> g.tw_log2;
+    if (col >= g.tw) return;
+    const int gx = g.x0 + col, hq = T.hq;
+    const int off = ott_ldg(T.hpos + gx) - g.sx0;
     const uint32_t sh = (uint32_t)(off & 3) * 8;
-    const uint32_t *phi = T.hc_hi + (size_t)gx * hq, *plo = T.hc_lo + (size_t)gx * hq;
-    const int nrows = c.nplanes * c.sr;
+    const uint32_t *phi = T.hc_hi + gx * hq, *plo = T.hc_lo + gx * hq;
+    const int nrows = g.nplanes * g.sr;
+    const uint32_t *src_s = reinterpret_cast<const uint32_t *>(smem) + (off >> 2);
+    int16_t *mid_s = reinterpret_cast<int16_t *>(smem + g.off_mid) + col;
     for (int row = grp; row < nrows; row += ngroups) {
-        const uint32_t *w = c.src_s + (size_t)row * c.src_pitch_words + wi;
+        const uint32_t *w = src_s + row * g.spw;
         uint32_t cur = w[0];
         int ahi = 0;
         uint32_t alo = 0;
@@ -237,54 +258,55 @@ OTT_DEV void hpass8_any(int tid, const TileCtx &c)
             alo = ott_dp4a_uu(a, ott_ldg(plo + q), alo);
             cur = nxt;
         }
-        const int val = ahi * 2 + (int)(alo >> 7);
-        c.mid_s[(size_t)row * c.mid_pitch + col] = (int16_t)ott_min(val, 32767);
+        mid_s[row * g.mid_pitch] = (int16_t)ott_min((ahi * 256 + (int)alo) >> 7, 32767);
     }
 }
 
 // 16-bit samples (10 significant bits, already right-aligned by the staging): two samples per word, plain IMAD.
 template <int HQ>
-OTT_DEV void hpass16(int tid, const TileCtx &c)
+OTT_DEV void hpass16(int tid, const TileGeom &g, unsigned char *smem)
 {
-    const PlaneTables &T = *c.T;
-    const int col = tid & (T.tw - 1), grp = tid >> c.tw_log2, ngroups = kThreads >> c.tw_log2;
-    if (col >= c.tw) return;
-    const int gx = c.x0 + col;
-    const int off = ott_ldg(T.hpos + gx) - c.sx0;
-    const int wi = off >> 1;
+    const PlaneTables &T = *g.T;
+    const int col = tid & (T.tw - 1), grp = tid >> g.tw_log2, ngroups = kThreads >> g.tw_log2;
+    if (col >= g.tw) return;
+    const int gx = g.x0 + col;
+    const int off = ott_ldg(T.hpos + gx) - g.sx0;
     const uint32_t sh = (uint32_t)(off & 1) * 16;
     int cf[4 * HQ];
-#pragma unroll
-    for (int j = 0; j < 4 * HQ; ++j) cf[j] = ott_ldg(T.hc16 + (size_t)gx * (4 * HQ) + j);
-    const int nrows = c.nplanes * c.sr;
+    OTT_UNROLL
+    for (int j = 0; j < 4 * HQ; ++j) cf[j] = ott_ldg(T.hc16 + gx * (4 * HQ) + j);
+    const int nrows = g.nplanes * g.sr;
+    const uint32_t *src_s = reinterpret_cast<const uint32_t *>(smem) + (off >> 1);
+    int16_t *mid_s = reinterpret_cast<int16_t *>(smem + g.off_mid) + col;
     for (int row = grp; row < nrows; row += ngroups) {
-        const uint32_t *w = c.src_s + (size_t)row * c.src_pitch_words + wi;
+        const uint32_t *w = src_s + row * g.spw;
         uint32_t cur = w[0];
         int acc = 0;
-#pragma unroll
+        OTT_UNROLL
         for (int k = 0; k < 2 * HQ; ++k) {
             const uint32_t nxt = w[k + 1];
             const uint32_t a = ott_funnel_r(cur, nxt, sh);
             acc += (int)(a & 0xffffu) * cf[2 * k] + (int)(a >> 16) * cf[2 * k + 1];
             cur = nxt;
         }
-        c.mid_s[(size_t)row * c.mid_pitch + col] = (int16_t)ott_min(acc >> 9, 32767);
+        mid_s[row * g.mid_pitch] = (int16_t)ott_min(acc >> 9, 32767);
     }
 }
 
-OTT_DEV void hpass16_any(int tid, const TileCtx &c)
+OTT_DEV void hpass16_any(int tid, const TileGeom &g, unsigned char *smem)
 {
-    const PlaneTables &T = *c.T;
-    const int col = tid & (T.tw - 1), grp = tid >> c.tw_log2, ngroups = kThreads >> c.tw_log2;
-    if (col >= c.tw) return;
-    const int gx = c.x0 + col, taps = 4 * T.hq;
-    const int off = ott_ldg(T.hpos + gx) - c.sx0;
-    const int wi = off >> 1;
+    const PlaneTables &T = *g.T;
+    const int col = tid & (T.tw - 1), grp = tid >> g.tw_log2, ngroups = kThreads >> g.tw_log2;
+    if (col >= g.tw) return;
+    const int gx = g.x0 + col, taps = 4 * T.hq;
+    const int off = ott_ldg(T.hpos + gx) - g.sx0;
     const uint32_t sh = (uint32_t)(off & 1) * 16;
-    const int16_t *pc = T.hc16 + (size_t)gx * taps;
-    const int nrows = c.nplanes * c.sr;
+    const int16_t *pc = T.hc16 + gx * taps;
+    const int nrows = g.nplanes * g.sr;
+    const uint32_t *src_s = reinterpret_cast<const uint32_t *>(smem) + (off >> 1);
+    int16_t *mid_s = reinterpret_cast<int16_t *>(smem + g.off_mid) + col;
     for (int row = grp; row < nrows; row += ngroups) {
-        const uint32_t *w = c.src_s + (size_t)row * c.src_pitch_words + wi;
+        const uint32_t *w = src_s + row * g.spw;
         uint32_t cur = w[0];
         int acc = 0;
         for (int k = 0; 2 * k < taps; ++k) {
@@ -293,138 +315,241 @@ OTT_DEV void hpass16_any(int tid, const TileCtx &c)
             acc += (int)(a & 0xffffu) * ott_ldg(pc + 2 * k) + (int)(a >> 16) * ott_ldg(pc + 2 * k + 1);
             cur = nxt;
         }
-        c.mid_s[(size_t)row * c.mid_pitch + col] = (int16_t)ott_min(acc >> 9, 32767);
+        mid_s[row * g.mid_pitch] = (int16_t)ott_min(acc >> 9, 32767);
     }
 }
 
-OTT_DEV void phase_hpass(int tid, const TileCtx &c)
+OTT_DEV void phase_hpass(int tid, const TileGeom &g, unsigned char *smem)
 {
-    const int hq = c.T->hq;
-    if (c.bps == 1) {
+    const int hq = g.T->hq;
+    if (g.bps == 1) {
         switch (hq) {
-        case 1: hpass8<1>(tid, c); break;
-        case 2: hpass8<2>(tid, c); break;
-        case 3: hpass8<3>(tid, c); break;
-        case 4: hpass8<4>(tid, c); break;
-        case 5: hpass8<5>(tid, c); break;
-        case 6: hpass8<6>(tid, c); break;
-        default: hpass8_any(tid, c); break;
+        case 1: hpass8<1>(tid, g, smem); break;
+        case 2: hpass8<2>(tid, g, smem); break;
+        case 3: hpass8<3>(tid, g, smem); break;
+        case 4: hpass8<4>(tid, g, smem); break;
+        case 5: hpass8<5>(tid, g, smem); break;
+        case 6: hpass8<6>(tid, g, smem); break;
+        default: hpass8_any(tid, g, smem); break;
         }
     } else {
         switch (hq) {
-        case 1: hpass16<1>(tid, c); break;
-        case 2: hpass16<2>(tid, c); break;
-        case 3: hpass16<3>(tid, c); break;
-        case 4: hpass16<4>(tid, c); break;
-        case 5: hpass16<5>(tid, c); break;
-        case 6: hpass16<6>(tid, c); break;
-        default: hpass16_any(tid, c); break;
+        case 1: hpass16<1>(tid, g, smem); break;
+        case 2: hpass16<2>(tid, g, smem); break;
+        case 3: hpass16<3>(tid, g, smem); break;
+        case 4: hpass16<4>(tid, g, smem); break;
+        case 5: hpass16<5>(tid, g, smem); break;
+        case 6: hpass16<6>(tid, g, smem); break;
+        default: hpass16_any(tid, g, smem); break;
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------ phase 3: V pass + store
-// Thread = two adjacent output columns (one 32-bit shared load per tap gives both), one warp-row at a time.
-// mode: 0 exact 8-bit, 1 x86-truncating 8-bit, 2 10-bit, 3 single tap 8-bit, 4 single tap 10-bit
-OTT_DEV void vcolumn2(const TileCtx &c, const uint32_t *m, int step_words, const int16_t *cf, int vtaps, int mode,
-                      int &o0, int &o1)
+// Thread = CPT adjacent output columns (CPT/2 32-bit shared words per tap) of one output row; a CTA sweep covers
+// 256/(tw/CPT) rows.  VMODE: 0 exact 8-bit, 1 x86-truncating 8-bit, 2 10-bit, 3 single tap 8-bit, 4 single tap 10-bit.
+enum { VM_EXACT8 = 0, VM_APPROX8 = 1, VM_EXACT10 = 2, VM_ONE8 = 3, VM_ONE10 = 4 };
+
+OTT_DEV int sx_lo(uint32_t w) { return (int)(int16_t)(w & 0xffffu); }
+OTT_DEV int sx_hi(uint32_t w) { return (int)w >> 16; }
+
+// NW (2 or 4) consecutive 32-bit words with one 8/16-byte shared load
+template <int NW>
+OTT_DEV void load_words(const uint32_t *p, uint32_t (&w)[NW])
 {
-    if (mode == 3 || mode == 4) {
-        const uint32_t w = m[0];
-        const int t0 = (int)(int16_t)(w & 0xffffu), t1 = (int)w >> 16;
-        if (mode == 3) { o0 = ott_clip((t0 + 64) >> 7, 255); o1 = ott_clip((t1 + 64) >> 7, 255); }
-        else { o0 = ott_clip((t0 + 16) >> 5, 1023); o1 = ott_clip((t1 + 16) >> 5, 1023); }
-        return;
+    if (NW == 4) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(p);
+        w[0] = q.x; w[1] = q.y; w[NW - 2] = q.z; w[NW - 1] = q.w;
+    } else {
+        const uint2 q = *reinterpret_cast<const uint2 *>(p);
+        w[0] = q.x; w[1] = q.y;
     }
-    if (mode == 1) {
-        int a0 = (64 + 8 * (vtaps - 1)) >> 4, a1 = a0;
-        for (int j = 0; j < vtaps; ++j) {
-            const uint32_t w = m[(size_t)j * step_words];
-            const int cj = cf[j];
-            a0 += ((int)(int16_t)(w & 0xffffu) * cj) >> 16;
-            a1 += (((int)w >> 16) * cj) >> 16;
-        }
-        o0 = ott_clip((int)(int16_t)a0 >> 3, 255);         // 16-bit wraparound (paddw) then psraw 3, packuswb
-        o1 = ott_clip((int)(int16_t)a1 >> 3, 255);
-        return;
-    }
-    int a0 = mode == 0 ? 64 << 12 : 1 << 16, a1 = a0;
-    for (int j = 0; j < vtaps; ++j) {
-        const uint32_t w = m[(size_t)j * step_words];
-        const int cj = cf[j];
-        a0 += (int)(int16_t)(w & 0xffffu) * cj;
-        a1 += ((int)w >> 16) * cj;
-    }
-    if (mode == 0) { o0 = ott_clip(a0 >> 19, 255); o1 = ott_clip(a1 >> 19, 255); }
-    else { o0 = ott_clip(a0 >> 17, 1023); o1 = ott_clip(a1 >> 17, 1023); }
 }
 
-template <typename S>
-OTT_DEV void store_run(uint8_t *row, int elem, const int *v, int n, int total)
+// VT > 0: compile-time tap count (fully unrolled); VT == 0: run-time `vtaps` (even), unrolled by two.
+template <int NW, int VT>
+OTT_DEV void vcolumns(const uint32_t *m, int step_words, const int16_t *cf, int vtaps, int mode, int (&o)[2 * NW])
 {
-    // n = 2 (planar) or 4 (interleaved pair) values starting at element index `elem`; `total` = elements in the row
-    S *p = reinterpret_cast<S *>(row) + elem;
-    const int live = ott_min(n, total - elem);
-    constexpr int kVecBytes = (int)sizeof(S);
-    const bool vec = (((uintptr_t)p) & (uintptr_t)(n * kVecBytes - 1)) == 0 && live == n;
-    if (vec) {
-        if (n * kVecBytes == 2) {
-            *reinterpret_cast<uint16_t *>(p) = (uint16_t)(v[0] | (v[1] << 8));
-        } else if (n * kVecBytes == 4) {
-            if (kVecBytes == 1) *reinterpret_cast<uint32_t *>(p) = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
-            else *reinterpret_cast<uint32_t *>(p) = (uint32_t)v[0] | ((uint32_t)v[1] << 16);
-        } else {   // 4 x 16-bit
-            uint2 q;
-            q.x = (uint32_t)v[0] | ((uint32_t)v[1] << 16);
-            q.y = (uint32_t)v[2] | ((uint32_t)v[3] << 16);
-            *reinterpret_cast<uint2 *>(p) = q;
+    if (mode == VM_ONE8 || mode == VM_ONE10) {
+        uint32_t ww[NW];
+        load_words<NW>(m, ww);
+        OTT_UNROLL
+        for (int k = 0; k < NW; ++k) {
+            const uint32_t w = ww[k];
+            if (mode == VM_ONE8) { o[2 * k] = ott_clip((sx_lo(w) + 64) >> 7, 255); o[2 * k + 1] = ott_clip((sx_hi(w) + 64) >> 7, 255); }
+            else { o[2 * k] = ott_clip((sx_lo(w) + 16) >> 5, 1023); o[2 * k + 1] = ott_clip((sx_hi(w) + 16) >> 5, 1023); }
+        }
+        return;
+    }
+    const int n = VT > 0 ? VT : vtaps;
+    int a[2 * NW];
+    if (mode == VM_APPROX8) {
+        const int init = (64 + 8 * (n - 1)) >> 4;
+        OTT_UNROLL
+        for (int k = 0; k < 2 * NW; ++k) a[k] = init;
+        if (VT > 0) {
+            OTT_UNROLL
+            for (int j = 0; j < (VT > 0 ? VT : 1); ++j) {
+                const int cj = cf[j];
+                uint32_t ww[NW];
+                load_words<NW>(m + j * step_words, ww);
+                OTT_UNROLL
+                for (int k = 0; k < NW; ++k) {
+                    a[2 * k] += (sx_lo(ww[k]) * cj) >> 16;
+                    a[2 * k + 1] += (sx_hi(ww[k]) * cj) >> 16;
+                }
+            }
+        } else {
+            for (int j = 0; j < n; ++j) {
+                const int cj = cf[j];
+                uint32_t ww[NW];
+                load_words<NW>(m + j * step_words, ww);
+                OTT_UNROLL
+                for (int k = 0; k < NW; ++k) {
+                    a[2 * k] += (sx_lo(ww[k]) * cj) >> 16;
+                    a[2 * k + 1] += (sx_hi(ww[k]) * cj) >> 16;
+                }
+            }
+        }
+        OTT_UNROLL
+        for (int k = 0; k < 2 * NW; ++k) o[k] = ott_clip((int)(int16_t)a[k] >> 3, 255);   // paddw wraparound, psraw 3, packuswb
+        return;
+    }
+    const int init = mode == VM_EXACT8 ? 64 << 12 : 1 << 16;
+    OTT_UNROLL
+    for (int k = 0; k < 2 * NW; ++k) a[k] = init;
+    if (VT > 0) {
+        OTT_UNROLL
+        for (int j = 0; j < (VT > 0 ? VT : 1); ++j) {
+            const int cj = cf[j];
+            uint32_t ww[NW];
+            load_words<NW>(m + j * step_words, ww);
+            OTT_UNROLL
+            for (int k = 0; k < NW; ++k) {
+                a[2 * k] += sx_lo(ww[k]) * cj;
+                a[2 * k + 1] += sx_hi(ww[k]) * cj;
+            }
         }
     } else {
-        for (int k = 0; k < live; ++k) p[k] = (S)v[k];
-    }
-}
-
-OTT_DEV void phase_vpass(int tid, const TileCtx &c)
-{
-    const PlaneTables &T = *c.T;
-    const int lanes_per_row = T.tw >> 1, lpr_log2 = c.tw_log2 - 1;
-    const int lx = tid & (lanes_per_row - 1), ry = tid >> lpr_log2, rows_per_pass = kThreads >> lpr_log2;
-    const int x = 2 * lx;
-    if (x >= c.tw) return;
-    const int step_words = c.mid_pitch >> 1;
-    const int vtaps = T.vtaps;
-    for (int y = ry; y < c.th; y += rows_per_pass) {
-        const int gy = c.y0 + y;
-        const int r0 = c.vpos_s[y] - c.sy0;
-        const int16_t *cf = c.vc_s + (size_t)y * vtaps;
-        int mode;
-        if (c.bps == 1) mode = vtaps == 1 ? 3 : ((c.approx_v && gy < T.exact_from) ? 1 : 0);
-        else mode = vtaps == 1 ? 4 : 2;
-        int o[4];
-        for (int p = 0; p < c.nplanes; ++p) {
-            const uint32_t *m = reinterpret_cast<const uint32_t *>(c.mid_s + (size_t)(p * c.sr + r0) * c.mid_pitch + x);
-            vcolumn2(c, m, step_words, cf, vtaps, mode, o[2 * p], o[2 * p + 1]);
-        }
-        const int gx = c.x0 + x;
-        if (c.nplanes == 1) {
-            int v[2] = { o[0] << c.dst_shift, o[1] << c.dst_shift };
-            uint8_t *row = c.dst[0] + (size_t)gy * c.dst_pitch[0];
-            if (c.bps == 1) store_run<uint8_t>(row, gx, v, 2, T.dstW);
-            else store_run<uint16_t>(row, gx, v, 2, T.dstW);
-        } else if (c.dst_interleaved) {
-            int v[4] = { o[0] << c.dst_shift, o[2] << c.dst_shift, o[1] << c.dst_shift, o[3] << c.dst_shift };
-            uint8_t *row = c.dst[0] + (size_t)gy * c.dst_pitch[0];
-            if (c.bps == 1) store_run<uint8_t>(row, 2 * gx, v, 4, 2 * T.dstW);
-            else store_run<uint16_t>(row, 2 * gx, v, 4, 2 * T.dstW);
-        } else {
-            for (int p = 0; p < 2; ++p) {
-                int v[2] = { o[2 * p] << c.dst_shift, o[2 * p + 1] << c.dst_shift };
-                uint8_t *row = c.dst[p] + (size_t)gy * c.dst_pitch[p];
-                if (c.bps == 1) store_run<uint8_t>(row, gx, v, 2, T.dstW);
-                else store_run<uint16_t>(row, gx, v, 2, T.dstW);
+        for (int j = 0; j < n; ++j) {
+            const int cj = cf[j];
+            uint32_t ww[NW];
+            load_words<NW>(m + j * step_words, ww);
+            OTT_UNROLL
+            for (int k = 0; k < NW; ++k) {
+                a[2 * k] += sx_lo(ww[k]) * cj;
+                a[2 * k + 1] += sx_hi(ww[k]) * cj;
             }
         }
     }
+    OTT_UNROLL
+    for (int k = 0; k < 2 * NW; ++k) o[k] = mode == VM_EXACT8 ? ott_clip(a[k] >> 19, 255) : ott_clip(a[k] >> 17, 1023);
+}
+
+// n values (n = 4, 8 or 16, a power of two) starting at element `elem` of a row of `total` elements of type S
+template <typename S, int N>
+OTT_DEV void store_run(uint8_t *row, int elem, const int (&v)[N], int total)
+{
+    S *p = reinterpret_cast<S *>(row) + elem;
+    constexpr int kBytes = N * (int)sizeof(S);                 // 4, 8, 16 or 32
+    const bool vec = elem + N <= total && (((uintptr_t)p) & (uintptr_t)((kBytes > 16 ? 16 : kBytes) - 1)) == 0;
+    if (!vec) {
+        OTT_UNROLL
+        for (int k = 0; k < N; ++k)
+            if (elem + k < total) p[k] = (S)v[k];
+        return;
+    }
+    uint32_t w[kBytes / 4];
+    OTT_UNROLL
+    for (int i = 0; i < kBytes / 4; ++i) {
+        if (sizeof(S) == 1) w[i] = (uint32_t)v[4 * i] | ((uint32_t)v[4 * i + 1] << 8) | ((uint32_t)v[4 * i + 2] << 16) | ((uint32_t)v[4 * i + 3] << 24);
+        else w[i] = (uint32_t)v[2 * i] | ((uint32_t)v[2 * i + 1] << 16);
+    }
+    if (kBytes == 4) {
+        *reinterpret_cast<uint32_t *>(p) = w[0];
+    } else if (kBytes == 8) {
+        uint2 q; q.x = w[0]; q.y = w[1];
+        *reinterpret_cast<uint2 *>(p) = q;
+    } else {
+        OTT_UNROLL
+        for (int i = 0; i < kBytes / 16; ++i) {
+            uint4 q; q.x = w[4 * i]; q.y = w[4 * i + 1]; q.z = w[4 * i + 2]; q.w = w[4 * i + 3];
+            reinterpret_cast<uint4 *>(p)[i] = q;
+        }
+    }
+}
+
+template <int CPT, int VT>
+OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
+{
+    constexpr int NW = CPT / 2;
+    const PlaneTables &T = *g.T;
+    const int lpr_log2 = g.tw_log2 - (CPT == 8 ? 3 : 2);        // lanes per output row: tw / CPT
+    const int lx = tid & ((1 << lpr_log2) - 1), ry = tid >> lpr_log2, rows_per_pass = kThreads >> lpr_log2;
+    const int x = CPT * lx;
+    if (x >= g.tw) return;
+    const int step_words = g.mid_pitch >> 1;
+    const int vtaps = T.vtaps;
+    const int16_t *mid_s = reinterpret_cast<const int16_t *>(smem + g.off_mid);
+    const int16_t *vc_s = reinterpret_cast<const int16_t *>(smem + g.off_vc);
+    const int32_t *vpos_s = reinterpret_cast<const int32_t *>(smem + g.off_vpos);
+    const int gx = g.x0 + x;
+    for (int y = ry; y < g.th; y += rows_per_pass) {
+        const int gy = g.y0 + y;
+        const int r0 = vpos_s[y] - g.sy0;
+        const int16_t *cf = vc_s + y * vtaps;
+        int mode;
+        if (g.bps == 1) mode = vtaps == 1 ? VM_ONE8 : ((g.approx_v && gy < T.exact_from) ? VM_APPROX8 : VM_EXACT8);
+        else mode = vtaps == 1 ? VM_ONE10 : VM_EXACT10;
+        int o0[CPT], o1[CPT];
+        vcolumns<NW, VT>(reinterpret_cast<const uint32_t *>(mid_s + r0 * g.mid_pitch + x), step_words, cf, vtaps, mode, o0);
+        if (g.nplanes == 2)
+            vcolumns<NW, VT>(reinterpret_cast<const uint32_t *>(mid_s + (g.sr + r0) * g.mid_pitch + x), step_words, cf, vtaps, mode, o1);
+        if (g.dst_shift) {
+            OTT_UNROLL
+            for (int k = 0; k < CPT; ++k) { o0[k] <<= 6; o1[k] <<= 6; }
+        }
+        if (g.nplanes == 1) {
+            uint8_t *row = g.dst0 + (size_t)gy * g.dst_pitch0;
+            if (g.bps == 1) store_run<uint8_t, CPT>(row, gx, o0, T.dstW);
+            else store_run<uint16_t, CPT>(row, gx, o0, T.dstW);
+        } else if (g.dst_interleaved) {
+            int v[2 * CPT];
+            OTT_UNROLL
+            for (int k = 0; k < CPT; ++k) { v[2 * k] = o0[k]; v[2 * k + 1] = o1[k]; }
+            uint8_t *row = g.dst0 + (size_t)gy * g.dst_pitch0;
+            if (g.bps == 1) store_run<uint8_t, 2 * CPT>(row, 2 * gx, v, 2 * T.dstW);
+            else store_run<uint16_t, 2 * CPT>(row, 2 * gx, v, 2 * T.dstW);
+        } else {
+            uint8_t *rowu = g.dst0 + (size_t)gy * g.dst_pitch0, *rowv = g.dst1 + (size_t)gy * g.dst_pitch1;
+            if (g.bps == 1) { store_run<uint8_t, CPT>(rowu, gx, o0, T.dstW); store_run<uint8_t, CPT>(rowv, gx, o1, T.dstW); }
+            else { store_run<uint16_t, CPT>(rowu, gx, o0, T.dstW); store_run<uint16_t, CPT>(rowv, gx, o1, T.dstW); }
+        }
+    }
+}
+
+template <int CPT>
+OTT_DEV void vpass_dispatch(int tid, const TileGeom &g, unsigned char *smem)
+{
+    switch (g.T->vtaps) {
+    case 2: vpass<CPT, 2>(tid, g, smem); break;
+    case 4: vpass<CPT, 4>(tid, g, smem); break;
+    case 6: vpass<CPT, 6>(tid, g, smem); break;
+    case 8: vpass<CPT, 8>(tid, g, smem); break;
+    case 10: vpass<CPT, 10>(tid, g, smem); break;
+    case 12: vpass<CPT, 12>(tid, g, smem); break;
+    case 14: vpass<CPT, 14>(tid, g, smem); break;
+    case 16: vpass<CPT, 16>(tid, g, smem); break;
+    case 18: vpass<CPT, 18>(tid, g, smem); break;
+    case 20: vpass<CPT, 20>(tid, g, smem); break;
+    default: vpass<CPT, 0>(tid, g, smem); break;
+    }
+}
+
+OTT_DEV void phase_vpass(int tid, const TileGeom &g, unsigned char *smem)
+{
+    if (g.tw_log2 == 6) vpass_dispatch<8>(tid, g, smem);
+    else vpass_dispatch<4>(tid, g, smem);
 }
 
 // ------------------------------------------------------------------------------------------------ copy items
@@ -434,13 +559,18 @@ OTT_DEV void copy_rows(int tid, const uint8_t *src, int spitch, uint8_t *dst, in
     const bool vec = ((((uintptr_t)src | (uintptr_t)dst | (uintptr_t)spitch | (uintptr_t)dpitch) & 15) == 0);
     if (vec) {
         const int nvec = row_bytes >> 4;
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int r = warp; r < rows; r += kThreads / 32) {
+        const int total = rows * nvec;
+        // flat index over (row, vector): consecutive threads copy consecutive 16-byte vectors of a row
+        for (int i = tid; i < total; i += kThreads) {
+            const int r = i / nvec, v = i - r * nvec;
             const uint4 *s = reinterpret_cast<const uint4 *>(src + (size_t)(y0 + r) * spitch);
             uint4 *d = reinterpret_cast<uint4 *>(dst + (size_t)(y0 + r) * dpitch);
-            for (int i = lane; i < nvec; i += 32) d[i] = ott_ldg(s + i);
-            for (int i = (nvec << 4) + lane; i < row_bytes; i += 32)
-                dst[(size_t)(y0 + r) * dpitch + i] = src[(size_t)(y0 + r) * spitch + i];
+            d[v] = ott_ldg(s + v);
+        }
+        const int tail = row_bytes - (nvec << 4);
+        for (int i = tid; i < rows * tail; i += kThreads) {
+            const int r = i / tail, b = (nvec << 4) + (i - r * tail);
+            dst[(size_t)(y0 + r) * dpitch + b] = ott_ldg(src + (size_t)(y0 + r) * spitch + b);
         }
     } else {
         for (int r = 0; r < rows; ++r)
@@ -449,39 +579,39 @@ OTT_DEV void copy_rows(int tid, const uint8_t *src, int spitch, uint8_t *dst, in
     }
 }
 
-// I420 chroma -> NV12 interleaved (byte-wise U,V interleave of transvideo.c:543-557), 4 chroma samples per thread step
+// I420 chroma -> NV12 interleaved (byte-wise U,V interleave of transvideo.c:543-557), 8 chroma samples per thread step
 OTT_DEV void interleave_rows8(int tid, const uint8_t *u, const uint8_t *v, int spitch, uint8_t *dst, int dpitch, int cw,
                               int y0, int rows)
 {
-    const bool vec = ((((uintptr_t)u | (uintptr_t)v | (uintptr_t)spitch) & 3) == 0) &&
-                     ((((uintptr_t)dst | (uintptr_t)dpitch) & 7) == 0);
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int r = warp; r < rows; r += kThreads / 32) {
-        const uint8_t *ur = u + (size_t)(y0 + r) * spitch, *vr = v + (size_t)(y0 + r) * spitch;
+    const bool vec = ((((uintptr_t)u | (uintptr_t)v | (uintptr_t)spitch) & 7) == 0) &&
+                     ((((uintptr_t)dst | (uintptr_t)dpitch) & 15) == 0);
+    const int n8 = vec ? cw >> 3 : 0;
+    if (n8) {
+        const int total = rows * n8;
+        for (int i = tid; i < total; i += kThreads) {
+            const int r = i / n8, k = i - r * n8;
+            const uint2 a = ott_ldg(reinterpret_cast<const uint2 *>(u + (size_t)(y0 + r) * spitch) + k);
+            const uint2 b = ott_ldg(reinterpret_cast<const uint2 *>(v + (size_t)(y0 + r) * spitch) + k);
+            uint4 q;
+            q.x = (a.x & 0xffu) | ((b.x & 0xffu) << 8) | ((a.x & 0xff00u) << 8) | ((b.x & 0xff00u) << 16);
+            q.y = ((a.x >> 16) & 0xffu) | (((b.x >> 16) & 0xffu) << 8) | ((a.x >> 24) << 16) | ((b.x >> 24) << 24);
+            q.z = (a.y & 0xffu) | ((b.y & 0xffu) << 8) | ((a.y & 0xff00u) << 8) | ((b.y & 0xff00u) << 16);
+            q.w = ((a.y >> 16) & 0xffu) | (((b.y >> 16) & 0xffu) << 8) | ((a.y >> 24) << 16) | ((b.y >> 24) << 24);
+            reinterpret_cast<uint4 *>(dst + (size_t)(y0 + r) * dpitch)[k] = q;
+        }
+    }
+    const int done = n8 << 3, tail = cw - done;
+    for (int i = tid; i < rows * tail; i += kThreads) {
+        const int r = i / tail, x = done + (i - r * tail);
         uint8_t *d = dst + (size_t)(y0 + r) * dpitch;
-        int done = 0;
-        if (vec) {
-            const int n4 = cw >> 2;
-            for (int i = lane; i < n4; i += 32) {
-                const uint32_t a = ott_ldg(reinterpret_cast<const uint32_t *>(ur) + i);
-                const uint32_t b = ott_ldg(reinterpret_cast<const uint32_t *>(vr) + i);
-                uint2 q;
-                q.x = (a & 0xffu) | ((b & 0xffu) << 8) | ((a & 0xff00u) << 8) | ((b & 0xff00u) << 16);
-                q.y = ((a >> 16) & 0xffu) | (((b >> 16) & 0xffu) << 8) | ((a >> 24) << 16) | ((b >> 24) << 24);
-                reinterpret_cast<uint2 *>(d)[i] = q;
-            }
-            done = n4 << 2;
-        }
-        for (int i = done + lane; i < cw; i += 32) {
-            d[2 * i] = ott_ldg(ur + i);
-            d[2 * i + 1] = ott_ldg(vr + i);
-        }
+        d[2 * x] = ott_ldg(u + (size_t)(y0 + r) * spitch + x);
+        d[2 * x + 1] = ott_ldg(v + (size_t)(y0 + r) * spitch + x);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ item dispatch
-// Resolves one work item.  Returns 0: nothing to do, 1: scale tile (ctx filled), 2: copy item.
-OTT_DEV int item_prepare(const Item &it, const Binding &b, unsigned char *smem, TileCtx &c)
+// Resolves one work item.  Returns 0: nothing to do, 1: scale tile (geometry filled), 2: copy item.
+OTT_DEV int item_prepare(const Item &it, const Binding &b, TileGeom &g)
 {
     if (!b.active || ((b.skip_mask >> it.slot) & 1u)) return 0;
     const PlanDev &plan = *b.plan;
@@ -491,45 +621,51 @@ OTT_DEV int item_prepare(const Item &it, const Binding &b, unsigned char *smem, 
     const bool luma = it.kind == ITEM_SCALE_LUMA;
     const PlaneTables &T = luma ? R.luma : R.chroma;
     const int src_il = plan.src_fmt == 2 /*P010*/, dst_il = R.fmt == 1 /*NV12*/ || R.fmt == 2 /*P010*/;
-    c.T = &T;
-    c.bps = plan.bps;
-    c.nplanes = luma ? 1 : 2;
-    c.x0 = it.tx * T.tw;
-    c.y0 = it.ty * T.th;
-    c.tw = ott_min(T.tw, T.dstW - c.x0);
-    c.th = ott_min(T.th, T.dstH - c.y0);
-    c.sy0 = ott_ldg(T.vpos + c.y0);
-    c.sr = ott_ldg(T.vpos + c.y0 + c.th - 1) + T.vtaps - c.sy0;
-    const int spw = plan.bps == 1 ? 4 : 2;
-    const int first = ott_ldg(T.hpos + c.x0), last = ott_ldg(T.hpos + c.x0 + c.tw - 1) + 4 * T.hq;
-    c.sx0 = first & ~(spw - 1);
-    c.nwords = (last - c.sx0 + spw - 1) / spw + 1;
-    c.src_pitch_words = T.sw_words;
-    c.mid_pitch = (T.tw + 1) & ~1;
-    c.tw_log2 = T.tw == 64 ? 6 : 5;
-    c.approx_v = R.approx_v;
-    c.src_s = reinterpret_cast<uint32_t *>(smem);
-    c.mid_s = reinterpret_cast<int16_t *>(c.src_s + (size_t)c.nplanes * T.sr_max * T.sw_words);
-    c.vc_s = c.mid_s + (size_t)c.nplanes * T.sr_max * c.mid_pitch;
-    c.vpos_s = reinterpret_cast<int32_t *>((reinterpret_cast<uintptr_t>(c.vc_s + (size_t)T.th * T.vtaps) + 3) & ~(uintptr_t)3);
-    c.src_shift = plan.src_fmt == 2 ? 6 : 0;
-    c.dst_shift = R.fmt == 2 ? 6 : 0;
+    g.T = &T;
+    g.bps = plan.bps;
+    g.nplanes = luma ? 1 : 2;
+    g.x0 = it.tx * T.tw;
+    g.y0 = it.ty * T.th;
+    g.tw = ott_min(T.tw, T.dstW - g.x0);
+    g.th = ott_min(T.th, T.dstH - g.y0);
+    g.sy0 = ott_ldg(T.vpos + g.y0);
+    g.sr = ott_min(ott_ldg(T.vpos + g.y0 + g.th - 1) + T.vtaps, T.srcH) - g.sy0;
+    const int spv = 16 / plan.bps;                                  // samples per 16-byte vector
+    const int first = ott_ldg(T.hpos + g.x0), last = ott_ldg(T.hpos + g.x0 + g.tw - 1) + 4 * T.hq;
+    g.sx0 = first & ~(spv - 1);
+    g.nvec = (last - g.sx0 + 4 / plan.bps + spv - 1) / spv;         // + one word of funnel slack
+    g.spw = T.sw_words;
+    g.mid_pitch = T.tw;
+    g.tw_log2 = T.tw == 64 ? 6 : 5;
+    g.approx_v = R.approx_v;
+    g.off_mid = g.nplanes * T.sr_max * T.sw_words * 4;
+    g.off_vc = g.off_mid + g.nplanes * (T.sr_max + 1) * T.tw * 2;
+    g.off_vpos = (g.off_vc + T.th * T.vtaps * 2 + 3) & ~3;
+    g.src_shift = plan.src_fmt == 2 ? 6 : 0;
+    g.dst_shift = R.fmt == 2 ? 6 : 0;
     if (luma) {
-        c.src[0] = b.src[0]; c.src_pitch[0] = b.src_pitch[0];
-        c.src[1] = nullptr;  c.src_pitch[1] = 0;
-        c.src_interleaved = 0;
-        c.dst[0] = b.dst[it.slot][0]; c.dst_pitch[0] = b.dst_pitch[it.slot][0];
-        c.dst[1] = nullptr; c.dst_pitch[1] = 0;
-        c.dst_interleaved = 0;
+        g.src0 = b.src[0]; g.src_pitch0 = b.src_pitch[0];
+        g.src1 = nullptr;  g.src_pitch1 = 0;
+        g.src_interleaved = 0;
+        g.dst0 = b.dst[it.slot][0]; g.dst_pitch0 = b.dst_pitch[it.slot][0];
+        g.dst1 = nullptr; g.dst_pitch1 = 0;
+        g.dst_interleaved = 0;
     } else {
-        c.src[0] = b.src[1]; c.src_pitch[0] = b.src_pitch[1];
-        c.src[1] = src_il ? b.src[1] : b.src[2]; c.src_pitch[1] = src_il ? b.src_pitch[1] : b.src_pitch[2];
-        c.src_interleaved = src_il;
-        c.dst[0] = b.dst[it.slot][1]; c.dst_pitch[0] = b.dst_pitch[it.slot][1];
-        c.dst[1] = dst_il ? nullptr : b.dst[it.slot][2]; c.dst_pitch[1] = dst_il ? 0 : b.dst_pitch[it.slot][2];
-        c.dst_interleaved = dst_il;
+        g.src0 = b.src[1]; g.src_pitch0 = b.src_pitch[1];
+        g.src1 = src_il ? b.src[1] : b.src[2]; g.src_pitch1 = src_il ? b.src_pitch[1] : b.src_pitch[2];
+        g.src_interleaved = src_il;
+        g.dst0 = b.dst[it.slot][1]; g.dst_pitch0 = b.dst_pitch[it.slot][1];
+        g.dst1 = dst_il ? nullptr : b.dst[it.slot][2]; g.dst_pitch1 = dst_il ? 0 : b.dst_pitch[it.slot][2];
+        g.dst_interleaved = dst_il;
     }
     return 1;
+}
+
+// bytes of shared memory item_prepare()'s layout needs (planner side)
+inline size_t tile_smem_bytes(int nplanes, int sr_max, int sw_words, int tw, int th, int vtaps)
+{
+    size_t b = (size_t)nplanes * sr_max * sw_words * 4 + (size_t)nplanes * (sr_max + 1) * tw * 2 + (size_t)th * vtaps * 2;
+    return ((b + 3) & ~(size_t)3) + (size_t)th * 4 + 16;
 }
 
 OTT_DEV void item_copy(int tid, const Item &it, const Binding &b)

@@ -84,7 +84,8 @@ const T *upload(Plan &plan, const std::vector<T> &v, std::string &err)
 
 size_t tile_bytes(int nplanes, int sr_max, int sw_words, int tw, int th, int vtaps)
 {
-    size_t b = (size_t)nplanes * sr_max * sw_words * 4 + (size_t)nplanes * sr_max * ((tw + 1) & ~1) * 2 + (size_t)th * vtaps * 2;
+    // must match item_prepare() in ladder_core.cuh
+    size_t b = (size_t)nplanes * sr_max * sw_words * 4 + (size_t)nplanes * (sr_max + 1) * tw * 2 + (size_t)th * vtaps * 2;
     return ((b + 3) & ~(size_t)3) + (size_t)th * 4 + 16;
 }
 
@@ -117,14 +118,14 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
     T.tw = dstW >= 128 ? 64 : 32;
     T.tiles_x = (dstW + T.tw - 1) / T.tw;
 
-    const int spw = bps == 1 ? 4 : 2;
-    int sw_words = 0;
+    const int spv = 16 / bps;                                    // samples per 16-byte staging vector
+    int nvec = 0;
     for (int tx = 0; tx < T.tiles_x; ++tx) {
         const int x0 = tx * T.tw, x1 = std::min(x0 + T.tw, dstW) - 1;
-        const int s0 = h.pos[x0] & ~(spw - 1), s1 = h.pos[x1] + taps4;
-        sw_words = std::max(sw_words, (s1 - s0 + spw - 1) / spw + 1);
+        const int s0 = h.pos[x0] & ~(spv - 1), s1 = h.pos[x1] + taps4;
+        nvec = std::max(nvec, (s1 - s0 + 4 / bps + spv - 1) / spv);    // + one word of funnel-shift slack
     }
-    T.sw_words = sw_words | 1;                                   // odd pitch: row groups start in different banks
+    T.sw_words = nvec * 4;
 
     auto rows_needed = [&](int th) {
         int m = 0;
@@ -134,7 +135,7 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
         }
         return m;
     };
-    const int row_quant = T.tw == 64 ? 8 : 16;                   // output rows the V pass covers per sweep
+    const int row_quant = 32;                                    // output rows the V pass covers per sweep
     int th = std::min((dstH + row_quant - 1) / row_quant * row_quant, 256);
     while (th > row_quant && tile_bytes(nplanes, rows_needed(th), T.sw_words, T.tw, th, v.taps) > kSmemBudget) th -= row_quant;
     // rebalance so the last tile row is not a sliver

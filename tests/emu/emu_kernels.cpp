@@ -16,19 +16,20 @@ cudaError_t launch_ladder(const Item *items, int n_items, const Binding *binds, 
     for (int blk = 0; blk < n_items; ++blk) {
         const Item it = items[blk];
         const Binding &b = binds[it.chan];
-        TileCtx c;
-        const int what = item_prepare(it, b, smem.data(), c);
+        TileGeom g;
+        const int what = item_prepare(it, b, g);
         if (what == 0) continue;
         if (what == 2) {
             for (int tid = 0; tid < kThreads; ++tid) item_copy(tid, it, b);
             continue;
         }
         // every byte the phases touch must lie inside the launch's dynamic shared memory
-        if ((unsigned char *)(c.vpos_s + c.th) > smem.data() + smem_bytes) return cudaErrorInvalidValue;
+        if ((size_t)g.off_vpos + (size_t)g.th * 4 > smem_bytes) return cudaErrorInvalidValue;
         std::fill(smem.begin(), smem.end(), 0xA5);       // poison: stale-data reads show up as mismatches
-        for (int tid = 0; tid < kThreads; ++tid) { phase_tables(tid, c); phase_stage(tid, c); }
-        for (int tid = 0; tid < kThreads; ++tid) phase_hpass(tid, c);
-        for (int tid = 0; tid < kThreads; ++tid) phase_vpass(tid, c);
+        unsigned char *sm = smem.data() + ((16 - ((uintptr_t)smem.data() & 15)) & 15);
+        for (int tid = 0; tid < kThreads; ++tid) { phase_tables(tid, g, sm); phase_stage(tid, g, sm); }
+        for (int tid = 0; tid < kThreads; ++tid) phase_hpass(tid, g, sm);
+        for (int tid = 0; tid < kThreads; ++tid) phase_vpass(tid, g, sm);
     }
     return cudaSuccess;
 }
