@@ -12,7 +12,7 @@ cudaError_t launch_ladder(const Item *items, int n_items, const Binding *binds, 
 cudaError_t launch_yadif(const YadifJob *jobs, int n_jobs, int max_w, int max_h, cudaStream_t s);
 
 // upper bound the kernels were configured for (cudaFuncAttributeMaxDynamicSharedMemorySize)
-constexpr size_t kMaxTileSmem = 200 * 1024;
+constexpr size_t kMaxTileSmem = 224 * 1024;
 cudaError_t configure_kernels();
 
 }  // namespace ottgpu

@@ -68,6 +68,7 @@ Plan::~Plan()
 namespace {
 
 constexpr size_t kSmemBudget = 48 * 1024;    // preferred tile footprint (>= 4 CTAs per SM)
+constexpr size_t kSmemHardLimit = 224 * 1024; // == kMaxTileSmem (kernels.h); sm_100 allows 227 KB per CTA
 
 template <typename T>
 const T *upload(Plan &plan, const std::vector<T> &v, std::string &err)
@@ -115,18 +116,8 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
     T.hq = hq;
     T.vtaps = v.taps;
     T.exact_from = exact_from;
-    T.tw = dstW >= 128 ? 64 : 32;
-    T.tiles_x = (dstW + T.tw - 1) / T.tw;
-
     const int spv = 16 / bps;                                    // samples per 16-byte staging vector
-    int nvec = 0;
-    for (int tx = 0; tx < T.tiles_x; ++tx) {
-        const int x0 = tx * T.tw, x1 = std::min(x0 + T.tw, dstW) - 1;
-        const int s0 = h.pos[x0] & ~(spv - 1), s1 = h.pos[x1] + taps4;
-        nvec = std::max(nvec, (s1 - s0 + 4 / bps + spv - 1) / spv);    // + one word of funnel-shift slack
-    }
-    T.sw_words = nvec * 4;
-
+    const int row_quant = 8;                                     // tile heights are multiples of 8 (a V sweep covers 32 rows)
     auto rows_needed = [&](int th) {
         int m = 0;
         for (int y0 = 0; y0 < dstH; y0 += th) {
@@ -135,17 +126,34 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
         }
         return m;
     };
-    const int row_quant = 32;                                    // output rows the V pass covers per sweep
-    int th = std::min((dstH + row_quant - 1) / row_quant * row_quant, 256);
-    while (th > row_quant && tile_bytes(nplanes, rows_needed(th), T.sw_words, T.tw, th, v.taps) > kSmemBudget) th -= row_quant;
-    // rebalance so the last tile row is not a sliver
-    const int nty = (dstH + th - 1) / th;
-    th = ((dstH + nty - 1) / nty + row_quant - 1) / row_quant * row_quant;
-    T.th = th;
-    T.tiles_y = (dstH + th - 1) / th;
-    T.sr_max = rows_needed(th);
-    smem_out = tile_bytes(nplanes, T.sr_max, T.sw_words, T.tw, th, v.taps);
-    if (smem_out > 200 * 1024) { err = "filter too long for one tile (shared memory)"; return false; }
+    auto try_width = [&](int tw) {
+        T.tw = tw;
+        T.tiles_x = (dstW + tw - 1) / tw;
+        int nvec = 0;
+        for (int tx = 0; tx < T.tiles_x; ++tx) {
+            const int x0 = tx * tw, x1 = std::min(x0 + tw, dstW) - 1;
+            const int s0 = h.pos[x0] & ~(spv - 1), s1 = h.pos[x1] + taps4;
+            nvec = std::max(nvec, (s1 - s0 + 4 / bps + spv - 1) / spv);    // + one word of funnel-shift slack
+        }
+        T.sw_words = nvec * 4;
+        int th = std::min((dstH + row_quant - 1) / row_quant * row_quant, 256);
+        while (th > row_quant && tile_bytes(nplanes, rows_needed(th), T.sw_words, tw, th, v.taps) > kSmemBudget) th -= row_quant;
+        if (th == row_quant) {
+            // very long vertical filters (4K -> thumbnail): shrink below the quantum until the tile fits at all
+            while (th > 1 && tile_bytes(nplanes, rows_needed(th), T.sw_words, tw, th, v.taps) > kSmemHardLimit) th /= 2;
+        } else {
+            // rebalance so the last tile row is not a sliver
+            const int nty = (dstH + th - 1) / th;
+            th = ((dstH + nty - 1) / nty + row_quant - 1) / row_quant * row_quant;
+        }
+        T.th = th;
+        T.tiles_y = (dstH + th - 1) / th;
+        T.sr_max = rows_needed(th);
+        return tile_bytes(nplanes, T.sr_max, T.sw_words, tw, th, v.taps);
+    };
+    smem_out = try_width(dstW >= 128 ? 64 : 32);
+    if (smem_out > kSmemBudget && T.tw == 64 && T.th <= row_quant) smem_out = try_width(32);   // extreme ratios: narrower tiles
+    if (smem_out > kSmemHardLimit) { err = "filter too long for one tile (shared memory)"; return false; }
 
     T.hpos = upload(plan, h.pos, err);
     T.hc_hi = upload(plan, hi, err);
@@ -256,12 +264,14 @@ std::shared_ptr<Plan> get_plan(const ottgpu_cfg &cfg_in, std::string &err)
         const int luma_exact = R.approx_v ? std::max(rc.height - 2, 0) : 0;
         const int chroma_exact = R.approx_v ? std::max((rc.height - 2 + 1) / 2, 0) : 0;
         size_t s1 = 0, s2 = 0;
-        if (!build_plane(*plan, R.luma, cfg.src_width, cfg.src_height, rc.width, rc.height, bps, 1, cfg.filter, cfg.target, luma_exact, s1, err)) return nullptr;
-        if (!build_plane(*plan, R.chroma, scw, sch, dcw, dch, bps, 2, cfg.filter, cfg.target, chroma_exact, s2, err)) return nullptr;
+        // the thumbnail scaler is SWS_BICUBIC whatever the ladder uses (transvideo.c:2155-2157)
+        const int filt = s == plan->thumb_slot ? OTTGPU_FILTER_BICUBIC : cfg.filter;
+        if (!build_plane(*plan, R.luma, cfg.src_width, cfg.src_height, rc.width, rc.height, bps, 1, filt, cfg.target, luma_exact, s1, err)) return nullptr;
+        if (!build_plane(*plan, R.chroma, scw, sch, dcw, dch, bps, 2, filt, cfg.target, chroma_exact, s2, err)) return nullptr;
         smem = std::max(smem, std::max(s1, s2));
         // order by the first source row each tile reads, so tiles of different rungs over the same band run together
-        std::vector<int32_t> lv = plan_table(cfg.src_height, rc.height, cfg.filter, cfg.target, true).pos;
-        std::vector<int32_t> cv = plan_table(sch, dch, cfg.filter, cfg.target, true).pos;
+        std::vector<int32_t> lv = plan_table(cfg.src_height, rc.height, filt, cfg.target, true).pos;
+        std::vector<int32_t> cv = plan_table(sch, dch, filt, cfg.target, true).pos;
         for (int ty = 0; ty < R.luma.tiles_y; ++ty)
             for (int tx = 0; tx < R.luma.tiles_x; ++tx) {
                 Sortable so{Item{0, (uint8_t)s, ITEM_SCALE_LUMA, (uint16_t)tx, (uint16_t)ty}, lv[ty * R.luma.th]};

@@ -103,13 +103,25 @@ def test_extreme_values(lib, og, oracle):
                 assert np.array_equal(got, ref)
 
 
-def test_thumbnail_size_filter(lib, og, oracle):
-    # the 176x144 thumbnail from a quarter-size source keeps the long-filter code path (taps > 24) in the CPU tier
-    sw, sh = 960, 540
+@pytest.mark.parametrize("size", [(960, 540), (1920, 1080)])
+def test_thumbnail_size_filter(lib, og, oracle, size):
+    # the 176x144 thumbnail (transvideo.c:2155-2174): long-filter code path (44/30 taps) and the tile-size fallback
+    sw, sh = size
     src = noise_i420(sw, sh, 41)
     ref = oracle.scale_i420(src, sw, sh, 176, 144)
     got = lib.scale_frame(src, og.FMT_I420, sw, sh, 176, 144)
     assert np.array_equal(got, ref)
+
+
+def test_full_size_planning_of_baseline_ladders(lib, og):
+    # every BASELINE.json ladder must plan (tiles fit shared memory) -- channel creation is where that is decided
+    nv = og.FMT_NV12
+    og.Channel(lib, og.make_cfg(1920, 1080, [(1920, 1080, nv), (1280, 720, nv), (960, 540, nv), (640, 360, nv), (416, 234, nv)],
+                                deint=og.DEINT_FLAGGED, thumb=(176, 144, 150))).close()
+    p = og.FMT_P010
+    og.Channel(lib, og.make_cfg(3840, 2160, [(3840, 2160, p), (2560, 1440, p), (1920, 1080, p), (1280, 720, p), (960, 540, p), (640, 360, p)],
+                                src_fmt=p, filt=og.FILTER_LANCZOS, deint=og.DEINT_FLAGGED, thumb=(176, 144, 150))).close()
+    og.Channel(lib, og.make_cfg(3840, 2160, [(3840, 2160, 0), (1920, 1080, 0), (1280, 720, 0), (640, 360, 0)], thumb=(176, 144, 150))).close()
 
 
 @pytest.mark.gpu
