@@ -64,11 +64,28 @@ struct Binding {
     int dst_pitch[kMaxRungSlots][3];
 };
 
+// One work item = one CTA-sized piece of work, with its geometry resolved on the host when the plan is built.
 struct Item {
-    uint16_t chan;
-    uint8_t slot;
-    uint8_t kind;
-    uint16_t tx, ty;
+    uint16_t chan;           // index into the launch's Binding array
+    uint8_t slot;            // rung slot
+    uint8_t kind;            // ItemKind
+    uint16_t x0, y0;         // output tile origin (copy items: y0 = first row)
+    uint16_t tw, th;         // output tile size (copy items: th = rows)
+    uint16_t sy0, sr;        // source rows [sy0, sy0+sr) the tile reads
+    uint16_t sx0, nvec;      // first staged source sample (16-byte aligned) and 16-byte vectors per staged row
+    uint32_t reserved;
+};
+
+// Launch-wide constants of the persistent ladder kernel.
+struct LadderLaunch {
+    const Item *items;
+    const Binding *binds;
+    int n_items;
+    int *counter;            // dynamic tile scheduler (zeroed before every launch)
+    int src_max;             // bytes of ONE staged-source buffer (max over the launch's tiles, multiple of 16)
+    int mid_max;             // bytes of the H-pass result region (multiple of 16)
+    int vc_max;              // bytes of the V coefficient + vpos region
+    int double_buffer;       // 1: two source buffers, next tile's rows are fetched while the current tile computes
 };
 
 // yadif work description, one per channel per launch

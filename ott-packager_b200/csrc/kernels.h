@@ -5,14 +5,18 @@
 
 namespace ottgpu {
 
-// One CTA per work item.  smem_bytes = max tile footprint over the plans referenced by `items`.
-cudaError_t launch_ladder(const Item *items, int n_items, const Binding *binds, size_t smem_bytes, cudaStream_t s);
+// upper bound of dynamic shared memory the ladder kernel is configured for (sm_100 allows 227 KB per CTA)
+constexpr size_t kMaxTileSmem = 224 * 1024;
+
+// shared memory one launch needs for the given region maxima; double_buffer is decided here
+size_t ladder_smem_bytes(int src_max, int mid_max, int vc_max, int *double_buffer);
+
+// Persistent launch: grid = min(n_items, SMs x resident CTAs); CTAs pull work items from L.counter (must be zero).
+cudaError_t launch_ladder(LadderLaunch L, cudaStream_t s);
 
 // yadif: one launch over all jobs (blockIdx.z = job).
 cudaError_t launch_yadif(const YadifJob *jobs, int n_jobs, int max_w, int max_h, cudaStream_t s);
 
-// upper bound the kernels were configured for (cudaFuncAttributeMaxDynamicSharedMemorySize)
-constexpr size_t kMaxTileSmem = 224 * 1024;
 cudaError_t configure_kernels();
 
 }  // namespace ottgpu

@@ -76,7 +76,9 @@ struct TileGeom {
     int mid_pitch;           // smem pitch (int16 elements) of the H-pass result: 32 or 64
     int tw_log2;             // T->tw is 32 or 64
     int approx_v;
-    int off_mid, off_vc, off_vpos;   // byte offsets of the regions inside the tile's shared memory
+    int off_src, off_mid, off_vc, off_vpos;   // byte offsets of the regions inside the CTA's shared memory
+    int bulk_ok;             // source rows can be fetched with 16-byte aligned bulk copies (TMA) into off_src
+    int row_copy_bytes;      // bytes per staged row when bulk_ok
     const uint8_t *src0, *src1;      // plane bases (chroma: U,V or the interleaved UV plane twice)
     int src_pitch0, src_pitch1;      // bytes
     int src_interleaved;     // chroma samples interleaved in the source (P010)
@@ -119,7 +121,7 @@ OTT_DEV uint32_t shift_mask16(uint32_t v, int shift) { return (v >> shift) & ((0
 OTT_DEV void phase_stage(int tid, const TileGeom &g, unsigned char *smem)
 {
     const PlaneTables &T = *g.T;
-    uint32_t *src_s = reinterpret_cast<uint32_t *>(smem);
+    uint32_t *src_s = reinterpret_cast<uint32_t *>(smem + g.off_src);
     // lanes per staged row: smallest power of two >= nvec (capped at 32)
     int lpr_log2 = 0;
     while ((1 << lpr_log2) < g.nvec && lpr_log2 < 5) ++lpr_log2;
@@ -218,7 +220,7 @@ OTT_DEV void hpass8(int tid, const TileGeom &g, unsigned char *smem)
         lo[q] = ott_ldg(T.hc_lo + gx * HQ + q);
     }
     const int nrows = g.nplanes * g.sr;
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(smem) + (off >> 2) + grp * g.spw;
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(smem + g.off_src) + (off >> 2) + grp * g.spw;
     int16_t *m = reinterpret_cast<int16_t *>(smem + g.off_mid) + col + grp * g.mid_pitch;
     const int wstep = ngroups * g.spw, mstep = ngroups * g.mid_pitch;
     int row = grp;
@@ -244,7 +246,7 @@ OTT_DEV void hpass8_any(int tid, const TileGeom &g, unsigned char *smem)
     const uint32_t sh = (uint32_t)(off & 3) * 8;
     const uint32_t *phi = T.hc_hi + gx * hq, *plo = T.hc_lo + gx * hq;
     const int nrows = g.nplanes * g.sr;
-    const uint32_t *src_s = reinterpret_cast<const uint32_t *>(smem) + (off >> 2);
+    const uint32_t *src_s = reinterpret_cast<const uint32_t *>(smem + g.off_src) + (off >> 2);
     int16_t *mid_s = reinterpret_cast<int16_t *>(smem + g.off_mid) + col;
     for (int row = grp; row < nrows; row += ngroups) {
         const uint32_t *w = src_s + row * g.spw;
@@ -276,7 +278,7 @@ OTT_DEV void hpass16(int tid, const TileGeom &g, unsigned char *smem)
     OTT_UNROLL
     for (int j = 0; j < 4 * HQ; ++j) cf[j] = ott_ldg(T.hc16 + gx * (4 * HQ) + j);
     const int nrows = g.nplanes * g.sr;
-    const uint32_t *src_s = reinterpret_cast<const uint32_t *>(smem) + (off >> 1);
+    const uint32_t *src_s = reinterpret_cast<const uint32_t *>(smem + g.off_src) + (off >> 1);
     int16_t *mid_s = reinterpret_cast<int16_t *>(smem + g.off_mid) + col;
     for (int row = grp; row < nrows; row += ngroups) {
         const uint32_t *w = src_s + row * g.spw;
@@ -303,7 +305,7 @@ OTT_DEV void hpass16_any(int tid, const TileGeom &g, unsigned char *smem)
     const uint32_t sh = (uint32_t)(off & 1) * 16;
     const int16_t *pc = T.hc16 + gx * taps;
     const int nrows = g.nplanes * g.sr;
-    const uint32_t *src_s = reinterpret_cast<const uint32_t *>(smem) + (off >> 1);
+    const uint32_t *src_s = reinterpret_cast<const uint32_t *>(smem + g.off_src) + (off >> 1);
     int16_t *mid_s = reinterpret_cast<int16_t *>(smem + g.off_mid) + col;
     for (int row = grp; row < nrows; row += ngroups) {
         const uint32_t *w = src_s + row * g.spw;
@@ -348,6 +350,9 @@ OTT_DEV void phase_hpass(int tid, const TileGeom &g, unsigned char *smem)
 // ------------------------------------------------------------------------------------------------ phase 3: V pass + store
 // Thread = CPT adjacent output columns (CPT/2 32-bit shared words per tap) of one output row; a CTA sweep covers
 // 256/(tw/CPT) rows.  VMODE: 0 exact 8-bit, 1 x86-truncating 8-bit, 2 10-bit, 3 single tap 8-bit, 4 single tap 10-bit.
+template <int BPS> struct StoreT { typedef uint8_t type; };
+template <> struct StoreT<2> { typedef uint16_t type; };
+
 enum { VM_EXACT8 = 0, VM_APPROX8 = 1, VM_EXACT10 = 2, VM_ONE8 = 3, VM_ONE10 = 4 };
 
 OTT_DEV int sx_lo(uint32_t w) { return (int)(int16_t)(w & 0xffffu); }
@@ -366,123 +371,149 @@ OTT_DEV void load_words(const uint32_t *p, uint32_t (&w)[NW])
     }
 }
 
-// VT > 0: compile-time tap count (fully unrolled); VT == 0: run-time `vtaps` (even), unrolled by two.
-template <int NW, int VT>
-OTT_DEV void vcolumns(const uint32_t *m, int step_words, const int16_t *cf, int vtaps, int mode, int (&o)[2 * NW])
+// Packs results as they are produced so that only a few registers stay live: 8-bit -> 4 samples per word,
+// 16-bit -> 2 samples per word (already shifted for P010).
+template <int BPS> OTT_DEV uint32_t pack2(int a, int b, int shift)   // 16-bit: two samples
 {
+    return ((uint32_t)a << shift) | ((uint32_t)b << (16 + shift));
+}
+OTT_DEV uint32_t pack4(int a, int b, int c, int d) { return (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)d << 24); }
+
+// One row of NW*2 adjacent columns.  VT > 0: compile-time tap count (fully unrolled); VT == 0: run-time `vtaps`.
+// Output: 8-bit -> NW/2 packed words, 16-bit -> NW packed words.
+template <int NW, int VT, int BPS>
+OTT_DEV void vcolumns(const uint32_t *m, int step_words, const int16_t *cf, int vtaps, int mode, int shift,
+                      uint32_t (&out)[BPS == 1 ? NW / 2 : NW])
+{
+    int a[2 * NW];
     if (mode == VM_ONE8 || mode == VM_ONE10) {
         uint32_t ww[NW];
         load_words<NW>(m, ww);
         OTT_UNROLL
         for (int k = 0; k < NW; ++k) {
-            const uint32_t w = ww[k];
-            if (mode == VM_ONE8) { o[2 * k] = ott_clip((sx_lo(w) + 64) >> 7, 255); o[2 * k + 1] = ott_clip((sx_hi(w) + 64) >> 7, 255); }
-            else { o[2 * k] = ott_clip((sx_lo(w) + 16) >> 5, 1023); o[2 * k + 1] = ott_clip((sx_hi(w) + 16) >> 5, 1023); }
+            if (mode == VM_ONE8) { a[2 * k] = ott_clip((sx_lo(ww[k]) + 64) >> 7, 255); a[2 * k + 1] = ott_clip((sx_hi(ww[k]) + 64) >> 7, 255); }
+            else { a[2 * k] = ott_clip((sx_lo(ww[k]) + 16) >> 5, 1023); a[2 * k + 1] = ott_clip((sx_hi(ww[k]) + 16) >> 5, 1023); }
         }
-        return;
-    }
-    const int n = VT > 0 ? VT : vtaps;
-    int a[2 * NW];
-    if (mode == VM_APPROX8) {
-        const int init = (64 + 8 * (n - 1)) >> 4;
+    } else {
+        const int n = VT > 0 ? VT : vtaps;
+        const int init = mode == VM_APPROX8 ? (64 + 8 * (n - 1)) >> 4 : (mode == VM_EXACT8 ? 64 << 12 : 1 << 16);
         OTT_UNROLL
         for (int k = 0; k < 2 * NW; ++k) a[k] = init;
-        if (VT > 0) {
-            OTT_UNROLL
-            for (int j = 0; j < (VT > 0 ? VT : 1); ++j) {
-                const int cj = cf[j];
-                uint32_t ww[NW];
-                load_words<NW>(m + j * step_words, ww);
+        if (mode == VM_APPROX8) {
+            if (VT > 0) {
                 OTT_UNROLL
-                for (int k = 0; k < NW; ++k) {
-                    a[2 * k] += (sx_lo(ww[k]) * cj) >> 16;
-                    a[2 * k + 1] += (sx_hi(ww[k]) * cj) >> 16;
+                for (int j = 0; j < (VT > 0 ? VT : 1); ++j) {
+                    const int cj = cf[j];
+                    uint32_t ww[NW];
+                    load_words<NW>(m + j * step_words, ww);
+                    OTT_UNROLL
+                    for (int k = 0; k < NW; ++k) {
+                        a[2 * k] += (sx_lo(ww[k]) * cj) >> 16;
+                        a[2 * k + 1] += (sx_hi(ww[k]) * cj) >> 16;
+                    }
+                }
+            } else {
+                for (int j = 0; j < n; ++j) {
+                    const int cj = cf[j];
+                    uint32_t ww[NW];
+                    load_words<NW>(m + j * step_words, ww);
+                    OTT_UNROLL
+                    for (int k = 0; k < NW; ++k) {
+                        a[2 * k] += (sx_lo(ww[k]) * cj) >> 16;
+                        a[2 * k + 1] += (sx_hi(ww[k]) * cj) >> 16;
+                    }
                 }
             }
+            OTT_UNROLL
+            for (int k = 0; k < 2 * NW; ++k) a[k] = ott_clip((int)(int16_t)a[k] >> 3, 255);   // paddw wraparound, psraw 3, packuswb
         } else {
-            for (int j = 0; j < n; ++j) {
-                const int cj = cf[j];
-                uint32_t ww[NW];
-                load_words<NW>(m + j * step_words, ww);
+            if (VT > 0) {
                 OTT_UNROLL
-                for (int k = 0; k < NW; ++k) {
-                    a[2 * k] += (sx_lo(ww[k]) * cj) >> 16;
-                    a[2 * k + 1] += (sx_hi(ww[k]) * cj) >> 16;
+                for (int j = 0; j < (VT > 0 ? VT : 1); ++j) {
+                    const int cj = cf[j];
+                    uint32_t ww[NW];
+                    load_words<NW>(m + j * step_words, ww);
+                    OTT_UNROLL
+                    for (int k = 0; k < NW; ++k) {
+                        a[2 * k] += sx_lo(ww[k]) * cj;
+                        a[2 * k + 1] += sx_hi(ww[k]) * cj;
+                    }
+                }
+            } else {
+                for (int j = 0; j < n; ++j) {
+                    const int cj = cf[j];
+                    uint32_t ww[NW];
+                    load_words<NW>(m + j * step_words, ww);
+                    OTT_UNROLL
+                    for (int k = 0; k < NW; ++k) {
+                        a[2 * k] += sx_lo(ww[k]) * cj;
+                        a[2 * k + 1] += sx_hi(ww[k]) * cj;
+                    }
                 }
             }
-        }
-        OTT_UNROLL
-        for (int k = 0; k < 2 * NW; ++k) o[k] = ott_clip((int)(int16_t)a[k] >> 3, 255);   // paddw wraparound, psraw 3, packuswb
-        return;
-    }
-    const int init = mode == VM_EXACT8 ? 64 << 12 : 1 << 16;
-    OTT_UNROLL
-    for (int k = 0; k < 2 * NW; ++k) a[k] = init;
-    if (VT > 0) {
-        OTT_UNROLL
-        for (int j = 0; j < (VT > 0 ? VT : 1); ++j) {
-            const int cj = cf[j];
-            uint32_t ww[NW];
-            load_words<NW>(m + j * step_words, ww);
             OTT_UNROLL
-            for (int k = 0; k < NW; ++k) {
-                a[2 * k] += sx_lo(ww[k]) * cj;
-                a[2 * k + 1] += sx_hi(ww[k]) * cj;
-            }
+            for (int k = 0; k < 2 * NW; ++k) a[k] = mode == VM_EXACT8 ? ott_clip(a[k] >> 19, 255) : ott_clip(a[k] >> 17, 1023);
         }
+    }
+    if (BPS == 1) {
+        OTT_UNROLL
+        for (int k = 0; k < NW / 2; ++k) out[k] = pack4(a[4 * k], a[4 * k + 1], a[4 * k + 2], a[4 * k + 3]);
     } else {
-        for (int j = 0; j < n; ++j) {
-            const int cj = cf[j];
-            uint32_t ww[NW];
-            load_words<NW>(m + j * step_words, ww);
-            OTT_UNROLL
-            for (int k = 0; k < NW; ++k) {
-                a[2 * k] += sx_lo(ww[k]) * cj;
-                a[2 * k + 1] += sx_hi(ww[k]) * cj;
-            }
-        }
+        OTT_UNROLL
+        for (int k = 0; k < NW; ++k) out[k] = pack2<2>(a[2 * k], a[2 * k + 1], shift);
     }
-    OTT_UNROLL
-    for (int k = 0; k < 2 * NW; ++k) o[k] = mode == VM_EXACT8 ? ott_clip(a[k] >> 19, 255) : ott_clip(a[k] >> 17, 1023);
 }
 
-// n values (n = 4, 8 or 16, a power of two) starting at element `elem` of a row of `total` elements of type S
-template <typename S, int N>
-OTT_DEV void store_run(uint8_t *row, int elem, const int (&v)[N], int total)
+// NWORDS packed 32-bit words = NWORDS*4/sizeof(S) samples starting at element `elem` of a row of `total` samples
+template <typename S, int NWORDS>
+OTT_DEV void store_words(uint8_t *row, int elem, const uint32_t (&w)[NWORDS], int total)
 {
+    constexpr int N = NWORDS * 4 / (int)sizeof(S);
+    constexpr int kBytes = NWORDS * 4;                         // 4, 8, 16 or 32
     S *p = reinterpret_cast<S *>(row) + elem;
-    constexpr int kBytes = N * (int)sizeof(S);                 // 4, 8, 16 or 32
     const bool vec = elem + N <= total && (((uintptr_t)p) & (uintptr_t)((kBytes > 16 ? 16 : kBytes) - 1)) == 0;
-    if (!vec) {
-        OTT_UNROLL
-        for (int k = 0; k < N; ++k)
-            if (elem + k < total) p[k] = (S)v[k];
+    if (vec) {
+        if (kBytes == 4) {
+            *reinterpret_cast<uint32_t *>(p) = w[0];
+        } else if (kBytes == 8) {
+            uint2 q; q.x = w[0]; q.y = w[NWORDS > 1 ? 1 : 0];
+            *reinterpret_cast<uint2 *>(p) = q;
+        } else {
+            OTT_UNROLL
+            for (int i = 0; i < kBytes / 16; ++i) {
+                uint4 q;
+                q.x = w[(4 * i) % NWORDS]; q.y = w[(4 * i + 1) % NWORDS]; q.z = w[(4 * i + 2) % NWORDS]; q.w = w[(4 * i + 3) % NWORDS];
+                reinterpret_cast<uint4 *>(p)[i] = q;
+            }
+        }
         return;
     }
-    uint32_t w[kBytes / 4];
     OTT_UNROLL
-    for (int i = 0; i < kBytes / 4; ++i) {
-        if (sizeof(S) == 1) w[i] = (uint32_t)v[4 * i] | ((uint32_t)v[4 * i + 1] << 8) | ((uint32_t)v[4 * i + 2] << 16) | ((uint32_t)v[4 * i + 3] << 24);
-        else w[i] = (uint32_t)v[2 * i] | ((uint32_t)v[2 * i + 1] << 16);
-    }
-    if (kBytes == 4) {
-        *reinterpret_cast<uint32_t *>(p) = w[0];
-    } else if (kBytes == 8) {
-        uint2 q; q.x = w[0]; q.y = w[1];
-        *reinterpret_cast<uint2 *>(p) = q;
-    } else {
-        OTT_UNROLL
-        for (int i = 0; i < kBytes / 16; ++i) {
-            uint4 q; q.x = w[4 * i]; q.y = w[4 * i + 1]; q.z = w[4 * i + 2]; q.w = w[4 * i + 3];
-            reinterpret_cast<uint4 *>(p)[i] = q;
-        }
+    for (int k = 0; k < N; ++k) {
+        const uint32_t word = w[(k * (int)sizeof(S)) / 4];
+        const uint32_t v = sizeof(S) == 1 ? (word >> (8 * (k & 3))) & 0xffu : (word >> (16 * (k & 1))) & 0xffffu;
+        if (elem + k < total) p[k] = (S)v;
     }
 }
 
-template <int CPT, int VT>
+// byte / halfword interleave of two packed streams (NV12 / P010 chroma writers)
+OTT_DEV void zip8(uint32_t u, uint32_t v, uint32_t &lo, uint32_t &hi)
+{
+    lo = (u & 0xffu) | ((v & 0xffu) << 8) | ((u & 0xff00u) << 8) | ((v & 0xff00u) << 16);
+    hi = ((u >> 16) & 0xffu) | (((v >> 16) & 0xffu) << 8) | ((u >> 24) << 16) | ((v >> 24) << 24);
+}
+OTT_DEV void zip16(uint32_t u, uint32_t v, uint32_t &lo, uint32_t &hi)
+{
+    lo = (u & 0xffffu) | (v << 16);
+    hi = (u >> 16) | (v & 0xffff0000u);
+}
+
+template <int CPT, int VT, int BPS>
 OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
 {
-    constexpr int NW = CPT / 2;
+    constexpr int NW = CPT / 2;                                 // shared words per tap
+    constexpr int NO = BPS == 1 ? NW / 2 : NW;                  // packed output words per plane
+    typedef typename StoreT<BPS>::type S;
     const PlaneTables &T = *g.T;
     const int lpr_log2 = g.tw_log2 - (CPT == 8 ? 3 : 2);        // lanes per output row: tw / CPT
     const int lx = tid & ((1 << lpr_log2) - 1), ry = tid >> lpr_log2, rows_per_pass = kThreads >> lpr_log2;
@@ -499,57 +530,56 @@ OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
         const int r0 = vpos_s[y] - g.sy0;
         const int16_t *cf = vc_s + y * vtaps;
         int mode;
-        if (g.bps == 1) mode = vtaps == 1 ? VM_ONE8 : ((g.approx_v && gy < T.exact_from) ? VM_APPROX8 : VM_EXACT8);
+        if (BPS == 1) mode = vtaps == 1 ? VM_ONE8 : ((g.approx_v && gy < T.exact_from) ? VM_APPROX8 : VM_EXACT8);
         else mode = vtaps == 1 ? VM_ONE10 : VM_EXACT10;
-        int o0[CPT], o1[CPT];
-        vcolumns<NW, VT>(reinterpret_cast<const uint32_t *>(mid_s + r0 * g.mid_pitch + x), step_words, cf, vtaps, mode, o0);
-        if (g.nplanes == 2)
-            vcolumns<NW, VT>(reinterpret_cast<const uint32_t *>(mid_s + (g.sr + r0) * g.mid_pitch + x), step_words, cf, vtaps, mode, o1);
-        if (g.dst_shift) {
-            OTT_UNROLL
-            for (int k = 0; k < CPT; ++k) { o0[k] <<= 6; o1[k] <<= 6; }
-        }
+        uint32_t o0[NO];
+        vcolumns<NW, VT, BPS>(reinterpret_cast<const uint32_t *>(mid_s + r0 * g.mid_pitch + x), step_words, cf, vtaps, mode, g.dst_shift, o0);
         if (g.nplanes == 1) {
-            uint8_t *row = g.dst0 + (size_t)gy * g.dst_pitch0;
-            if (g.bps == 1) store_run<uint8_t, CPT>(row, gx, o0, T.dstW);
-            else store_run<uint16_t, CPT>(row, gx, o0, T.dstW);
-        } else if (g.dst_interleaved) {
-            int v[2 * CPT];
+            store_words<S, NO>(g.dst0 + (size_t)gy * g.dst_pitch0, gx, o0, T.dstW);
+            continue;
+        }
+        uint32_t o1[NO];
+        vcolumns<NW, VT, BPS>(reinterpret_cast<const uint32_t *>(mid_s + (g.sr + r0) * g.mid_pitch + x), step_words, cf, vtaps, mode, g.dst_shift, o1);
+        if (g.dst_interleaved) {
+            uint32_t z[2 * NO];
             OTT_UNROLL
-            for (int k = 0; k < CPT; ++k) { v[2 * k] = o0[k]; v[2 * k + 1] = o1[k]; }
-            uint8_t *row = g.dst0 + (size_t)gy * g.dst_pitch0;
-            if (g.bps == 1) store_run<uint8_t, 2 * CPT>(row, 2 * gx, v, 2 * T.dstW);
-            else store_run<uint16_t, 2 * CPT>(row, 2 * gx, v, 2 * T.dstW);
+            for (int k = 0; k < NO; ++k) {
+                if (BPS == 1) zip8(o0[k], o1[k], z[2 * k], z[2 * k + 1]);
+                else zip16(o0[k], o1[k], z[2 * k], z[2 * k + 1]);
+            }
+            store_words<S, 2 * NO>(g.dst0 + (size_t)gy * g.dst_pitch0, 2 * gx, z, 2 * T.dstW);
         } else {
-            uint8_t *rowu = g.dst0 + (size_t)gy * g.dst_pitch0, *rowv = g.dst1 + (size_t)gy * g.dst_pitch1;
-            if (g.bps == 1) { store_run<uint8_t, CPT>(rowu, gx, o0, T.dstW); store_run<uint8_t, CPT>(rowv, gx, o1, T.dstW); }
-            else { store_run<uint16_t, CPT>(rowu, gx, o0, T.dstW); store_run<uint16_t, CPT>(rowv, gx, o1, T.dstW); }
+            store_words<S, NO>(g.dst0 + (size_t)gy * g.dst_pitch0, gx, o0, T.dstW);
+            store_words<S, NO>(g.dst1 + (size_t)gy * g.dst_pitch1, gx, o1, T.dstW);
         }
     }
 }
 
-template <int CPT>
+template <int CPT, int BPS>
 OTT_DEV void vpass_dispatch(int tid, const TileGeom &g, unsigned char *smem)
 {
     switch (g.T->vtaps) {
-    case 2: vpass<CPT, 2>(tid, g, smem); break;
-    case 4: vpass<CPT, 4>(tid, g, smem); break;
-    case 6: vpass<CPT, 6>(tid, g, smem); break;
-    case 8: vpass<CPT, 8>(tid, g, smem); break;
-    case 10: vpass<CPT, 10>(tid, g, smem); break;
-    case 12: vpass<CPT, 12>(tid, g, smem); break;
-    case 14: vpass<CPT, 14>(tid, g, smem); break;
-    case 16: vpass<CPT, 16>(tid, g, smem); break;
-    case 18: vpass<CPT, 18>(tid, g, smem); break;
-    case 20: vpass<CPT, 20>(tid, g, smem); break;
-    default: vpass<CPT, 0>(tid, g, smem); break;
+    case 2: vpass<CPT, 2, BPS>(tid, g, smem); break;
+    case 4: vpass<CPT, 4, BPS>(tid, g, smem); break;
+    case 6: vpass<CPT, 6, BPS>(tid, g, smem); break;
+    case 8: vpass<CPT, 8, BPS>(tid, g, smem); break;
+    case 10: vpass<CPT, 10, BPS>(tid, g, smem); break;
+    case 12: vpass<CPT, 12, BPS>(tid, g, smem); break;
+    case 16: vpass<CPT, 16, BPS>(tid, g, smem); break;
+    case 20: vpass<CPT, 20, BPS>(tid, g, smem); break;
+    default: vpass<CPT, 0, BPS>(tid, g, smem); break;
     }
 }
 
 OTT_DEV void phase_vpass(int tid, const TileGeom &g, unsigned char *smem)
 {
-    if (g.tw_log2 == 6) vpass_dispatch<8>(tid, g, smem);
-    else vpass_dispatch<4>(tid, g, smem);
+    if (g.bps == 1) {
+        if (g.tw_log2 == 6) vpass_dispatch<8, 1>(tid, g, smem);
+        else vpass_dispatch<4, 1>(tid, g, smem);
+    } else {
+        if (g.tw_log2 == 6) vpass_dispatch<8, 2>(tid, g, smem);
+        else vpass_dispatch<4, 2>(tid, g, smem);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ copy items
@@ -611,7 +641,8 @@ OTT_DEV void interleave_rows8(int tid, const uint8_t *u, const uint8_t *v, int s
 
 // ------------------------------------------------------------------------------------------------ item dispatch
 // Resolves one work item.  Returns 0: nothing to do, 1: scale tile (geometry filled), 2: copy item.
-OTT_DEV int item_prepare(const Item &it, const Binding &b, TileGeom &g)
+// off_src: byte offset of the source buffer this tile stages into; the other regions follow 2 (or 1) source buffers.
+OTT_DEV int item_prepare(const Item &it, const Binding &b, const LadderLaunch &L, int buf, TileGeom &g)
 {
     if (!b.active || ((b.skip_mask >> it.slot) & 1u)) return 0;
     const PlanDev &plan = *b.plan;
@@ -624,23 +655,16 @@ OTT_DEV int item_prepare(const Item &it, const Binding &b, TileGeom &g)
     g.T = &T;
     g.bps = plan.bps;
     g.nplanes = luma ? 1 : 2;
-    g.x0 = it.tx * T.tw;
-    g.y0 = it.ty * T.th;
-    g.tw = ott_min(T.tw, T.dstW - g.x0);
-    g.th = ott_min(T.th, T.dstH - g.y0);
-    g.sy0 = ott_ldg(T.vpos + g.y0);
-    g.sr = ott_min(ott_ldg(T.vpos + g.y0 + g.th - 1) + T.vtaps, T.srcH) - g.sy0;
-    const int spv = 16 / plan.bps;                                  // samples per 16-byte vector
-    const int first = ott_ldg(T.hpos + g.x0), last = ott_ldg(T.hpos + g.x0 + g.tw - 1) + 4 * T.hq;
-    g.sx0 = first & ~(spv - 1);
-    g.nvec = (last - g.sx0 + 4 / plan.bps + spv - 1) / spv;         // + one word of funnel slack
+    g.x0 = it.x0; g.y0 = it.y0; g.tw = it.tw; g.th = it.th;
+    g.sy0 = it.sy0; g.sr = it.sr; g.sx0 = it.sx0; g.nvec = it.nvec;
     g.spw = T.sw_words;
     g.mid_pitch = T.tw;
     g.tw_log2 = T.tw == 64 ? 6 : 5;
     g.approx_v = R.approx_v;
-    g.off_mid = g.nplanes * T.sr_max * T.sw_words * 4;
-    g.off_vc = g.off_mid + g.nplanes * (T.sr_max + 1) * T.tw * 2;
-    g.off_vpos = (g.off_vc + T.th * T.vtaps * 2 + 3) & ~3;
+    g.off_src = buf * L.src_max;
+    g.off_mid = (L.double_buffer ? 2 : 1) * L.src_max;
+    g.off_vc = g.off_mid + L.mid_max;
+    g.off_vpos = g.off_vc + ((T.th * T.vtaps * 2 + 3) & ~3);
     g.src_shift = plan.src_fmt == 2 ? 6 : 0;
     g.dst_shift = R.fmt == 2 ? 6 : 0;
     if (luma) {
@@ -658,14 +682,13 @@ OTT_DEV int item_prepare(const Item &it, const Binding &b, TileGeom &g)
         g.dst1 = dst_il ? nullptr : b.dst[it.slot][2]; g.dst_pitch1 = dst_il ? 0 : b.dst_pitch[it.slot][2];
         g.dst_interleaved = dst_il;
     }
+    // bulk (TMA) staging: 8-bit planar rows whose base, pitch and width are all multiples of 16 bytes
+    const int row_bytes = T.srcW * plan.bps;
+    const uintptr_t al = (uintptr_t)g.src0 | (uintptr_t)g.src_pitch0 | (uintptr_t)row_bytes |
+                         (g.nplanes == 2 ? ((uintptr_t)g.src1 | (uintptr_t)g.src_pitch1) : 0);
+    g.bulk_ok = plan.bps == 1 && (al & 15) == 0;
+    g.row_copy_bytes = ott_min(g.nvec * 16, row_bytes - g.sx0 * plan.bps);
     return 1;
-}
-
-// bytes of shared memory item_prepare()'s layout needs (planner side)
-inline size_t tile_smem_bytes(int nplanes, int sr_max, int sw_words, int tw, int th, int vtaps)
-{
-    size_t b = (size_t)nplanes * sr_max * sw_words * 4 + (size_t)nplanes * (sr_max + 1) * tw * 2 + (size_t)th * vtaps * 2;
-    return ((b + 3) & ~(size_t)3) + (size_t)th * 4 + 16;
 }
 
 OTT_DEV void item_copy(int tid, const Item &it, const Binding &b)
@@ -675,12 +698,12 @@ OTT_DEV void item_copy(int tid, const Item &it, const Binding &b)
     const int src_il = plan.src_fmt == 2, dst_il = R.fmt == 1 || R.fmt == 2;
     if (it.kind == ITEM_COPY_LUMA) {
         const PlaneTables &T = R.luma;
-        const int y0 = it.ty * T.th, rows = ott_min(T.th, T.dstH - y0);
+        const int y0 = it.y0, rows = it.th;
         copy_rows(tid, b.src[0], b.src_pitch[0], b.dst[it.slot][0], b.dst_pitch[it.slot][0], T.dstW * plan.bps, y0, rows);
         return;
     }
     const PlaneTables &T = R.chroma;
-    const int y0 = it.ty * T.th, rows = ott_min(T.th, T.dstH - y0);
+    const int y0 = it.y0, rows = it.th;
     if (src_il == dst_il) {                 // planar->planar (two planes) or interleaved->interleaved (one plane)
         const int row_bytes = T.dstW * plan.bps * (src_il ? 2 : 1);
         copy_rows(tid, b.src[1], b.src_pitch[1], b.dst[it.slot][1], b.dst_pitch[it.slot][1], row_bytes, y0, rows);

@@ -67,7 +67,7 @@ Plan::~Plan()
 
 namespace {
 
-constexpr size_t kSmemBudget = 48 * 1024;    // preferred tile footprint (>= 4 CTAs per SM)
+constexpr size_t kSmemBudget = 72 * 1024;    // preferred CTA footprint incl. the second source buffer (3 CTAs per SM)
 constexpr size_t kSmemHardLimit = 224 * 1024; // == kMaxTileSmem (kernels.h); sm_100 allows 227 KB per CTA
 
 template <typename T>
@@ -83,16 +83,36 @@ const T *upload(Plan &plan, const std::vector<T> &v, std::string &err)
     return static_cast<const T *>(d);
 }
 
+struct TileRegions { size_t src, mid, vc; };
+
+// must match item_prepare() in ladder_core.cuh
+TileRegions tile_regions(int nplanes, int sr_max, int sw_words, int tw, int th, int vtaps)
+{
+    TileRegions r;
+    r.src = (size_t)nplanes * sr_max * sw_words * 4;                      // multiple of 16 (sw_words % 4 == 0)
+    r.mid = (size_t)nplanes * (sr_max + 1) * tw * 2;                      // tw is 32 or 64 -> multiple of 16
+    r.vc = (((size_t)th * vtaps * 2 + 3) & ~(size_t)3) + (size_t)th * 4;
+    r.vc = (r.vc + 15) & ~(size_t)15;
+    return r;
+}
+
+// footprint used for tile sizing: two source buffers (the next tile is fetched while this one computes)
 size_t tile_bytes(int nplanes, int sr_max, int sw_words, int tw, int th, int vtaps)
 {
-    // must match item_prepare() in ladder_core.cuh
-    size_t b = (size_t)nplanes * sr_max * sw_words * 4 + (size_t)nplanes * (sr_max + 1) * tw * 2 + (size_t)th * vtaps * 2;
-    return ((b + 3) & ~(size_t)3) + (size_t)th * 4 + 16;
+    const TileRegions r = tile_regions(nplanes, sr_max, sw_words, tw, th, vtaps);
+    return 2 * r.src + r.mid + r.vc + 16;
+}
+
+size_t tile_bytes_single(int nplanes, int sr_max, int sw_words, int tw, int th, int vtaps)
+{
+    const TileRegions r = tile_regions(nplanes, sr_max, sw_words, tw, th, vtaps);
+    return r.src + r.mid + r.vc + 16;
 }
 
 // Builds tables + tiling for one plane kind of one rung.  Host vectors are kept in `keep` only long enough to upload.
 bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int dstH, int bps, int nplanes, int filter,
-                 int target, int exact_from, size_t &smem_out, std::string &err)
+                 int target, int exact_from, TileRegions &regions, std::vector<int32_t> &hpos_out,
+                 std::vector<int32_t> &vpos_out, std::string &err)
 {
     const PolyphaseTable h = plan_table(srcW, dstW, filter, target, false);
     const PolyphaseTable v = plan_table(srcH, dstH, filter, target, true);
@@ -140,7 +160,7 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
         while (th > row_quant && tile_bytes(nplanes, rows_needed(th), T.sw_words, tw, th, v.taps) > kSmemBudget) th -= row_quant;
         if (th == row_quant) {
             // very long vertical filters (4K -> thumbnail): shrink below the quantum until the tile fits at all
-            while (th > 1 && tile_bytes(nplanes, rows_needed(th), T.sw_words, tw, th, v.taps) > kSmemHardLimit) th /= 2;
+            while (th > 1 && tile_bytes_single(nplanes, rows_needed(th), T.sw_words, tw, th, v.taps) > kSmemHardLimit) th /= 2;
         } else {
             // rebalance so the last tile row is not a sliver
             const int nty = (dstH + th - 1) / th;
@@ -151,9 +171,13 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
         T.sr_max = rows_needed(th);
         return tile_bytes(nplanes, T.sr_max, T.sw_words, tw, th, v.taps);
     };
-    smem_out = try_width(dstW >= 128 ? 64 : 32);
+    auto single_bytes = [&]() { return tile_bytes_single(nplanes, T.sr_max, T.sw_words, T.tw, T.th, v.taps); };
+    size_t smem_out = try_width(dstW >= 128 ? 64 : 32);
     if (smem_out > kSmemBudget && T.tw == 64 && T.th <= row_quant) smem_out = try_width(32);   // extreme ratios: narrower tiles
-    if (smem_out > kSmemHardLimit) { err = "filter too long for one tile (shared memory)"; return false; }
+    regions = tile_regions(nplanes, T.sr_max, T.sw_words, T.tw, T.th, v.taps);
+    hpos_out = h.pos;
+    vpos_out = v.pos;
+    if (single_bytes() > kSmemHardLimit) { err = "filter too long for one tile (shared memory)"; return false; }
 
     T.hpos = upload(plan, h.pos, err);
     T.hc_hi = upload(plan, hi, err);
@@ -248,40 +272,65 @@ std::shared_ptr<Plan> get_plan(const ottgpu_cfg &cfg_in, std::string &err)
         R.scaled = !same;
         R.approx_v = bps == 1 && cfg.target == OTTGPU_TARGET_A;
         const int dcw = (rc.width + 1) / 2, dch = (rc.height + 1) / 2;
-        std::vector<Item> &sink = s == plan->thumb_slot ? plan->thumb_items : plan->items;
-        size_t &smem = s == plan->thumb_slot ? plan->smem_thumb : plan->smem_items;
+        const int which = s == plan->thumb_slot ? 1 : 0;
+        std::vector<Item> &sink = which ? plan->thumb_items : plan->items;
+        auto copy_item = [&](uint8_t kind, int y0, int rows) {
+            Item it;
+            std::memset(&it, 0, sizeof(it));
+            it.slot = (uint8_t)s;
+            it.kind = kind;
+            it.y0 = (uint16_t)y0;
+            it.th = (uint16_t)rows;
+            return it;
+        };
         if (same) {
             copy_tiling(R.luma, cfg.src_width, cfg.src_height);
             copy_tiling(R.chroma, scw, sch);
-            for (int ty = 0; ty < R.luma.tiles_y; ++ty)
-                ordered.push_back({Item{0, (uint8_t)s, ITEM_COPY_LUMA, 0, (uint16_t)ty}, ty * R.luma.th});
-            for (int ty = 0; ty < R.chroma.tiles_y; ++ty)
-                ordered.push_back({Item{0, (uint8_t)s, ITEM_COPY_CHROMA, 0, (uint16_t)ty}, 2 * ty * R.chroma.th});
+            for (int ty = 0; ty < R.luma.tiles_y; ++ty) {
+                const int y0 = ty * R.luma.th;
+                ordered.push_back({copy_item(ITEM_COPY_LUMA, y0, std::min(R.luma.th, cfg.src_height - y0)), y0});
+            }
+            for (int ty = 0; ty < R.chroma.tiles_y; ++ty) {
+                const int y0 = ty * R.chroma.th;
+                ordered.push_back({copy_item(ITEM_COPY_CHROMA, y0, std::min(R.chroma.th, sch - y0)), 2 * y0});
+            }
             continue;
         }
         // swscale switches to the C vertical functions once dstY >= dstH-2 (luma rows);
         // chroma row uv is emitted while dstY == 2*uv
         const int luma_exact = R.approx_v ? std::max(rc.height - 2, 0) : 0;
         const int chroma_exact = R.approx_v ? std::max((rc.height - 2 + 1) / 2, 0) : 0;
-        size_t s1 = 0, s2 = 0;
         // the thumbnail scaler is SWS_BICUBIC whatever the ladder uses (transvideo.c:2155-2157)
         const int filt = s == plan->thumb_slot ? OTTGPU_FILTER_BICUBIC : cfg.filter;
-        if (!build_plane(*plan, R.luma, cfg.src_width, cfg.src_height, rc.width, rc.height, bps, 1, filt, cfg.target, luma_exact, s1, err)) return nullptr;
-        if (!build_plane(*plan, R.chroma, scw, sch, dcw, dch, bps, 2, filt, cfg.target, chroma_exact, s2, err)) return nullptr;
-        smem = std::max(smem, std::max(s1, s2));
-        // order by the first source row each tile reads, so tiles of different rungs over the same band run together
-        std::vector<int32_t> lv = plan_table(cfg.src_height, rc.height, filt, cfg.target, true).pos;
-        std::vector<int32_t> cv = plan_table(sch, dch, filt, cfg.target, true).pos;
-        for (int ty = 0; ty < R.luma.tiles_y; ++ty)
-            for (int tx = 0; tx < R.luma.tiles_x; ++tx) {
-                Sortable so{Item{0, (uint8_t)s, ITEM_SCALE_LUMA, (uint16_t)tx, (uint16_t)ty}, lv[ty * R.luma.th]};
-                if (s == plan->thumb_slot) sink.push_back(so.it); else ordered.push_back(so);
-            }
-        for (int ty = 0; ty < R.chroma.tiles_y; ++ty)
-            for (int tx = 0; tx < R.chroma.tiles_x; ++tx) {
-                Sortable so{Item{0, (uint8_t)s, ITEM_SCALE_CHROMA, (uint16_t)tx, (uint16_t)ty}, 2 * cv[ty * R.chroma.th]};
-                if (s == plan->thumb_slot) sink.push_back(so.it); else ordered.push_back(so);
-            }
+        TileRegions rl, rc2;
+        std::vector<int32_t> lh, lv, chh, cv;
+        if (!build_plane(*plan, R.luma, cfg.src_width, cfg.src_height, rc.width, rc.height, bps, 1, filt, cfg.target, luma_exact, rl, lh, lv, err)) return nullptr;
+        if (!build_plane(*plan, R.chroma, scw, sch, dcw, dch, bps, 2, filt, cfg.target, chroma_exact, rc2, chh, cv, err)) return nullptr;
+        plan->src_max[which] = std::max(plan->src_max[which], (int)std::max(rl.src, rc2.src));
+        plan->mid_max[which] = std::max(plan->mid_max[which], (int)std::max(rl.mid, rc2.mid));
+        plan->vc_max[which] = std::max(plan->vc_max[which], (int)std::max(rl.vc, rc2.vc));
+        // tile geometry resolved here once (the kernel only loads it); items are ordered by the first source row each
+        // tile reads, so tiles of different rungs over the same band run together and share the source through L2
+        const int spv = 16 / bps;
+        auto scale_items = [&](const PlaneTables &T, const std::vector<int32_t> &hp, const std::vector<int32_t> &vp, uint8_t kind, int band_scale) {
+            for (int ty = 0; ty < T.tiles_y; ++ty)
+                for (int tx = 0; tx < T.tiles_x; ++tx) {
+                    Item it;
+                    std::memset(&it, 0, sizeof(it));
+                    it.slot = (uint8_t)s;
+                    it.kind = kind;
+                    const int x0 = tx * T.tw, y0 = ty * T.th;
+                    const int tw = std::min(T.tw, T.dstW - x0), th = std::min(T.th, T.dstH - y0);
+                    const int sy0 = vp[y0], sr = std::min(vp[y0 + th - 1] + T.vtaps, T.srcH) - sy0;
+                    const int sx0 = hp[x0] & ~(spv - 1), last = hp[x0 + tw - 1] + 4 * T.hq;
+                    it.x0 = (uint16_t)x0; it.y0 = (uint16_t)y0; it.tw = (uint16_t)tw; it.th = (uint16_t)th;
+                    it.sy0 = (uint16_t)sy0; it.sr = (uint16_t)sr; it.sx0 = (uint16_t)sx0;
+                    it.nvec = (uint16_t)((last - sx0 + 4 / bps + spv - 1) / spv);     // + one word of funnel-shift slack
+                    if (which) sink.push_back(it); else ordered.push_back({it, band_scale * sy0});
+                }
+        };
+        scale_items(R.luma, lh, lv, ITEM_SCALE_LUMA, 1);
+        scale_items(R.chroma, chh, cv, ITEM_SCALE_CHROMA, 2);
     }
     std::stable_sort(ordered.begin(), ordered.end(), [](const Sortable &a, const Sortable &b) { return a.band < b.band; });
     for (const Sortable &so : ordered) plan->items.push_back(so.it);

@@ -32,7 +32,8 @@ struct Plan {
     PlanDev *dev = nullptr;
     std::vector<Item> items;                           // chan = 0; rung slots only, ordered by source row band
     std::vector<Item> thumb_items;                     // the thumbnail slot's items (launched only when due)
-    size_t smem_items = 0, smem_thumb = 0;             // dynamic shared memory the two launches need
+    // shared-memory region maxima (bytes) over the tiles of the two launches: [0] rung items, [1] thumbnail items
+    int src_max[2] = {0, 0}, mid_max[2] = {0, 0}, vc_max[2] = {0, 0};
     std::vector<void *> allocations;                   // device memory owned by the plan
     ~Plan();
 };

@@ -111,12 +111,13 @@ struct ottgpu_batch {
     cudaStream_t stream = nullptr;
     Item *d_items = nullptr;
     int n_items = 0, max_thumb_items = 0;
-    size_t smem_items = 0, smem_thumb = 0;
+    int src_max[2] = {0, 0}, mid_max[2] = {0, 0}, vc_max[2] = {0, 0};   // [0] rung launch, [1] thumbnail launch
     // Descriptors are double-buffered so that an ASYNC submit can be prepared while the previous step still runs.
     struct Set {
         Binding *h_binds = nullptr, *d_binds = nullptr;    // pinned / device
         YadifJob *h_jobs = nullptr, *d_jobs = nullptr;
         Item *h_thumb_items = nullptr, *d_thumb_items = nullptr;
+        int *d_counters = nullptr;                          // [0] rung launch, [1] thumbnail launch tile schedulers
         cudaEvent_t done = nullptr, k0 = nullptr, k1 = nullptr;
         bool in_flight = false, timed = false;
     } set[2];
@@ -320,8 +321,11 @@ int ottgpu_batch_create(ottgpu_channel **channels, int n, ottgpu_batch **out)
     for (int i = 0; i < n; ++i) {
         const Plan &p = *channels[i]->plan;
         for (Item it : p.items) { it.chan = (uint16_t)i; all.push_back(it); }
-        b->smem_items = std::max(b->smem_items, p.smem_items);
-        b->smem_thumb = std::max(b->smem_thumb, p.smem_thumb);
+        for (int k = 0; k < 2; ++k) {
+            b->src_max[k] = std::max(b->src_max[k], p.src_max[k]);
+            b->mid_max[k] = std::max(b->mid_max[k], p.mid_max[k]);
+            b->vc_max[k] = std::max(b->vc_max[k], p.vc_max[k]);
+        }
         b->max_thumb_items += (int)p.thumb_items.size();
     }
     b->n_items = (int)all.size();
@@ -334,6 +338,7 @@ int ottgpu_batch_create(ottgpu_channel **channels, int n, ottgpu_batch **out)
         CK(cudaMallocHost((void **)&st.h_binds, n * sizeof(Binding)));
         CK(cudaMalloc((void **)&st.d_jobs, n * sizeof(YadifJob)));
         CK(cudaMallocHost((void **)&st.h_jobs, n * sizeof(YadifJob)));
+        CK(cudaMalloc((void **)&st.d_counters, 2 * sizeof(int)));
         CK(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
         CK(cudaEventCreate(&st.k0));
         CK(cudaEventCreate(&st.k1));
@@ -352,6 +357,7 @@ void ottgpu_batch_destroy(ottgpu_batch *b)
         cudaFree(st.d_thumb_items);
         cudaFree(st.d_binds);
         cudaFree(st.d_jobs);
+        cudaFree(st.d_counters);
         cudaFreeHost(st.h_binds);
         cudaFreeHost(st.h_jobs);
         cudaFreeHost(st.h_thumb_items);
@@ -577,9 +583,22 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
         CK(launch_yadif(st.d_jobs, n, max_w, max_h, s));
         b->last_launches++;
     }
+    auto make_launch = [&](const Item *items, int count, int which) {
+        LadderLaunch L;
+        L.items = items;
+        L.binds = st.d_binds;
+        L.n_items = count;
+        L.counter = st.d_counters + which;
+        L.src_max = b->src_max[which];
+        L.mid_max = b->mid_max[which];
+        L.vc_max = b->vc_max[which];
+        L.double_buffer = 0;                             // decided by launch_ladder from the shared-memory budget
+        return L;
+    };
+    if ((live && b->n_items) || n_thumb_items) CK(cudaMemsetAsync(st.d_counters, 0, 2 * sizeof(int), s));
     if (live && b->n_items) {
         if (b->timing) CK(cudaEventRecord(st.k0, s));
-        CK(launch_ladder(b->d_items, b->n_items, st.d_binds, b->smem_items, s));
+        CK(launch_ladder(make_launch(b->d_items, b->n_items, 0), s));
         if (b->timing) {
             CK(cudaEventRecord(st.k1, s));
             st.timed = true;
@@ -589,7 +608,7 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
     }
     if (n_thumb_items) {
         CK(cudaMemcpyAsync(st.d_thumb_items, st.h_thumb_items, n_thumb_items * sizeof(Item), cudaMemcpyHostToDevice, s));
-        CK(launch_ladder(st.d_thumb_items, n_thumb_items, st.d_binds, b->smem_thumb, s));
+        CK(launch_ladder(make_launch(st.d_thumb_items, n_thumb_items, 1), s));
         b->last_launches++;
         b->last_items += n_thumb_items;
     }

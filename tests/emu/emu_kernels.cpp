@@ -9,15 +9,27 @@ namespace ottgpu {
 
 cudaError_t configure_kernels() { return cudaSuccess; }
 
-cudaError_t launch_ladder(const Item *items, int n_items, const Binding *binds, size_t smem_bytes, cudaStream_t)
+size_t ladder_smem_bytes(int src_max, int mid_max, int vc_max, int *double_buffer)
 {
+    const size_t two = 2 * (size_t)src_max + mid_max + vc_max + 16, one = (size_t)src_max + mid_max + vc_max + 16;
+    const int db = two <= kMaxTileSmem;
+    if (double_buffer) *double_buffer = db;
+    return db ? two : one;
+}
+
+cudaError_t launch_ladder(LadderLaunch L, cudaStream_t)
+{
+    int db = 0;
+    const size_t smem_bytes = ladder_smem_bytes(L.src_max, L.mid_max, L.vc_max, &db);
     if (smem_bytes > kMaxTileSmem) return cudaErrorInvalidValue;
+    L.double_buffer = db;
     std::vector<unsigned char> smem(smem_bytes + 64);
-    for (int blk = 0; blk < n_items; ++blk) {
-        const Item it = items[blk];
-        const Binding &b = binds[it.chan];
+    unsigned char *sm = smem.data() + ((16 - ((uintptr_t)smem.data() & 15)) & 15);
+    for (int blk = 0; blk < L.n_items; ++blk) {
+        const Item it = L.items[blk];
+        const Binding &b = L.binds[it.chan];
         TileGeom g;
-        const int what = item_prepare(it, b, g);
+        const int what = item_prepare(it, b, L, db ? (blk & 1) : 0, g);   // alternate buffers like the kernel does
         if (what == 0) continue;
         if (what == 2) {
             for (int tid = 0; tid < kThreads; ++tid) item_copy(tid, it, b);
@@ -25,8 +37,10 @@ cudaError_t launch_ladder(const Item *items, int n_items, const Binding *binds, 
         }
         // every byte the phases touch must lie inside the launch's dynamic shared memory
         if ((size_t)g.off_vpos + (size_t)g.th * 4 > smem_bytes) return cudaErrorInvalidValue;
+        if ((size_t)g.off_src + (size_t)g.nplanes * g.sr * g.spw * 4 > (size_t)g.off_src + L.src_max) return cudaErrorInvalidValue;
+        if ((size_t)g.nplanes * (g.sr + 1) * g.mid_pitch * 2 > (size_t)L.mid_max) return cudaErrorInvalidValue;
+        if (g.nvec * 4 > g.spw) return cudaErrorInvalidValue;
         std::fill(smem.begin(), smem.end(), 0xA5);       // poison: stale-data reads show up as mismatches
-        unsigned char *sm = smem.data() + ((16 - ((uintptr_t)smem.data() & 15)) & 15);
         for (int tid = 0; tid < kThreads; ++tid) { phase_tables(tid, g, sm); phase_stage(tid, g, sm); }
         for (int tid = 0; tid < kThreads; ++tid) phase_hpass(tid, g, sm);
         for (int tid = 0; tid < kThreads; ++tid) phase_vpass(tid, g, sm);
