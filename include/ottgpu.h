@@ -123,6 +123,9 @@ int  ottgpu_channel_reset(ottgpu_channel *ch);
 /* destroy: avfilter_graph_free / sws_freeContext, transvideo.c:1677, 1963-1966 */
 void ottgpu_channel_destroy(ottgpu_channel *ch);
 int  ottgpu_channel_gpu(const ottgpu_channel *ch);
+/* human-readable plan of the channel (tables, tiling, shared memory, work items per frame) written to buf; returns
+ * the number of bytes that would have been written (snprintf semantics) */
+int  ottgpu_channel_describe(const ottgpu_channel *ch, char *buf, size_t size);
 
 /* --- batch = many channels of one GPU advanced by ONE fused launch per stage (in-process multi-channel daemon) ----- */
 enum { OTTGPU_SUBMIT_SYNC = 0, OTTGPU_SUBMIT_ASYNC = 1 };

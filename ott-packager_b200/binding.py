@@ -64,6 +64,7 @@ _SIGS = {
     "ottgpu_channel_reset": (C.c_int, [C.c_void_p]),
     "ottgpu_channel_destroy": (None, [C.c_void_p]),
     "ottgpu_channel_gpu": (C.c_int, [C.c_void_p]),
+    "ottgpu_channel_describe": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "ottgpu_batch_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]),
     "ottgpu_batch_submit": (C.c_int, [C.c_void_p, C.POINTER(FrameIn), C.POINTER(FrameOut), C.c_int]),
     "ottgpu_batch_wait": (C.c_int, [C.c_void_p]),
@@ -198,6 +199,11 @@ class Channel:
 
     def reset(self):
         self.lib.check(self.lib.dll.ottgpu_channel_reset(self.handle))
+
+    def describe(self):
+        buf = C.create_string_buffer(16384)
+        self.lib.dll.ottgpu_channel_describe(self.handle, buf, len(buf))
+        return buf.value.decode()
 
     def fill_in(self, fin, frame, interlaced, tff, pts, dts, opaque):
         if isinstance(frame, np.ndarray):

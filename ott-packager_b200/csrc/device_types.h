@@ -11,7 +11,7 @@ namespace ottgpu {
 
 constexpr int kMaxRungs = 8;
 constexpr int kMaxRungSlots = kMaxRungs + 1;   // slot 8 = thumbnail (transvideo.c:2155-2174)
-constexpr int kThreads = 256;
+constexpr int kThreads = 256;                  // compute threads of a ladder CTA (8 warps); the kernel adds one producer warp
 
 enum ItemKind : uint8_t {
     ITEM_SCALE_LUMA = 0,     // H+V polyphase of one luma tile

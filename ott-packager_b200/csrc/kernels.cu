@@ -45,78 +45,96 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         : "memory");
 }
 
-// Fetch the tile's source rows into its shared buffer: TMA row copies when the plane allows it, else through registers.
-__device__ __forceinline__ void stage_issue(int tid, const TileGeom &g, unsigned char *smem, uint64_t *bar)
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
-    if (!g.bulk_ok) {
-        phase_stage(tid, g, smem);
-        return;
-    }
-    if (tid < 32) {
-        const int rows = g.nplanes * g.sr;
-        fence_proxy_async();           // the buffer was last read through the generic proxy (H pass of an earlier tile)
-        if (tid == 0) mbar_expect_tx(bar, (uint32_t)(rows * g.row_copy_bytes));
-        __syncwarp();
-        for (int r = tid; r < rows; r += 32) {
-            const int p = r >= g.sr, rr = r - p * g.sr;
-            const uint8_t *src = (p ? g.src1 : g.src0) + (size_t)(g.sy0 + rr) * (p ? g.src_pitch1 : g.src_pitch0) + g.sx0;
-            bulk_g2s(smem + g.off_src + r * g.spw * 4, src, (uint32_t)g.row_copy_bytes, bar);
-        }
-    }
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); }
 
-__global__ void __launch_bounds__(kThreads, 3) ladder_kernel(const LadderLaunch L)
+constexpr int kLadderThreads = kThreads + 32;     // 8 compute warps + 1 producer warp
+
+// Warp-specialised persistent kernel.
+//   producer warp : pulls the next work item from the global counter, resolves its geometry into the shared slot of
+//                   the free buffer, and has the TMA engine copy the tile's source rows (one cp.async.bulk per row)
+//                   into that buffer; completion is signalled on full[buf] (mbarrier, transaction bytes).
+//   compute warps : wait full[buf] -> H pass (staged rows -> int16 intermediates) -> V pass + store -> arrive empty[buf].
+// Two buffers: tile k+1 streams in while tile k computes.
+__global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderLaunch L)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t mbar[2];
-    // Tile descriptors live in shared memory (three rotating slots: previous / current / next) so that no geometry
-    // has to stay in registers across the phases; thread 0 resolves the NEXT tile while the others finish the last one.
-    __shared__ TileGeom s_geom[3];
-    __shared__ int s_idx[3], s_what[3];
+    __shared__ __align__(8) uint64_t full[2], empty[2];
+    __shared__ TileGeom s_geom[2];
+    __shared__ int s_idx[2], s_what[2];
     const int tid = threadIdx.x;
+    const int nbuf = L.double_buffer ? 2 : 1;
     if (tid == 0) {
-        mbar_init(&mbar[0], 1);
-        mbar_init(&mbar[1], 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kThreads); }
         fence_mbar_init();
-        const int first = atomicAdd(L.counter, 1);
-        s_idx[0] = first;
-        s_what[0] = first < L.n_items ? item_prepare(L.items[first], L.binds[L.items[first].chan], L, 0, s_geom[0]) : 0;
     }
     __syncthreads();
-    const int db = L.double_buffer;
-    int buf = 0;
-    uint32_t parity0 = 0, parity1 = 0;
-    if (db && s_what[0] == 1) stage_issue(tid, s_geom[0], smem, &mbar[0]);
-    for (int slot = 0;; slot = slot == 2 ? 0 : slot + 1) {
-        const int cur = s_idx[slot];
-        if (cur >= L.n_items) break;
-        const int nslot = slot == 2 ? 0 : slot + 1;
-        if (tid == 0) {
-            const int nxt = atomicAdd(L.counter, 1);
-            s_idx[nslot] = nxt;
-            s_what[nslot] = nxt < L.n_items ? item_prepare(L.items[nxt], L.binds[L.items[nxt].chan], L, db ? buf ^ 1 : 0, s_geom[nslot]) : 0;
-        }
-        __syncthreads();   // (A) next tile resolved; every thread is past the previous tile's V pass and H pass
-        if (db && s_what[nslot] == 1) stage_issue(tid, s_geom[nslot], smem, &mbar[buf ^ 1]);   // prefetch
-        const int what = s_what[slot];
-        const TileGeom &g = s_geom[slot];
-        if (what == 2) {
-            item_copy(tid, L.items[cur], L.binds[L.items[cur].chan]);
-        } else if (what == 1) {
-            if (!db) {                                     // single buffer (very large tiles): fetch the current tile now
-                stage_issue(tid, g, smem, &mbar[0]);
-                if (!g.bulk_ok) __syncthreads();
+
+    if (tid >= kThreads) {
+        // ------------------------------------------------------------------ producer warp
+        const int lane = tid - kThreads;
+        uint32_t pe0 = 1, pe1 = 1;                 // a fresh mbarrier passes a wait on parity 1
+        for (int buf = 0;; buf = (buf + 1 == nbuf) ? 0 : buf + 1) {
+            int idx = 0;
+            if (lane == 0) idx = atomicAdd(L.counter, 1);
+            idx = __shfl_sync(0xffffffffu, idx, 0);
+            if (buf == 0) { mbar_wait(&empty[0], pe0); pe0 ^= 1; }
+            else { mbar_wait(&empty[1], pe1); pe1 ^= 1; }
+            if (lane == 0) {
+                s_idx[buf] = idx;
+                s_what[buf] = idx < L.n_items ? item_prepare(L.items[idx], L.binds[L.items[idx].chan], L, buf, s_geom[buf]) : 0;
             }
-            if (g.bulk_ok) {
-                if (buf == 0) { mbar_wait(&mbar[0], parity0); parity0 ^= 1; }
-                else { mbar_wait(&mbar[1], parity1); parity1 ^= 1; }
+            __syncwarp();
+            if (idx >= L.n_items) {
+                if (lane == 0) mbar_arrive(&full[buf]);
+                break;
+            }
+            const TileGeom &g = s_geom[buf];
+            if (s_what[buf] == 1 && g.bulk_ok) {
+                const int rows = g.nplanes * g.sr, bytes = g.row_copy_bytes, sr = g.sr;
+                fence_proxy_async();               // the buffer was last read through the generic proxy
+                if (lane == 0) mbar_expect_tx(&full[buf], (uint32_t)(rows * bytes));
+                __syncwarp();
+                unsigned char *dst = smem + g.off_src;
+                const int pitch_s = g.spw * 4;
+                for (int r = lane; r < rows; r += 32) {
+                    const int p = r >= sr, rr = r - p * sr;
+                    const uint8_t *src = (p ? g.src1 : g.src0) + (size_t)(g.sy0 + rr) * (p ? g.src_pitch1 : g.src_pitch0) + g.sx0;
+                    bulk_g2s(dst + r * pitch_s, src, (uint32_t)bytes, &full[buf]);
+                }
+            } else if (lane == 0) {
+                mbar_arrive(&full[buf]);           // nothing to fetch (copy item, skipped item, or compute-warp staging)
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- compute warps
+    uint32_t pf0 = 0, pf1 = 0;
+    for (int buf = 0;; buf = (buf + 1 == nbuf) ? 0 : buf + 1) {
+        if (buf == 0) { mbar_wait(&full[0], pf0); pf0 ^= 1; }
+        else { mbar_wait(&full[1], pf1); pf1 ^= 1; }
+        const int idx = s_idx[buf];
+        if (idx >= L.n_items) break;
+        const int what = s_what[buf];
+        const TileGeom &g = s_geom[buf];
+        if (what == 2) {
+            item_copy(tid, L.items[idx], L.binds[L.items[idx].chan]);
+        } else if (what == 1) {
+            if (!g.bulk_ok) {                      // unaligned / 16-bit sources: staged through registers by the compute warps
+                phase_stage(tid, g, smem);
+                compute_sync();
             }
             phase_tables(tid, g, smem);
             phase_hpass(tid, g, smem);
-            __syncthreads();   // (B) H-pass result and V tables complete
+            compute_sync();                        // H-pass result and V tables complete
             phase_vpass(tid, g, smem);
+            compute_sync();                        // intermediates free for the next tile's H pass
         }
-        buf ^= db;
+        mbar_arrive(&empty[buf]);                  // source buffer + geometry slot may be refilled
     }
 }
 
@@ -150,11 +168,11 @@ cudaError_t launch_ladder(LadderLaunch L, cudaStream_t s)
     int dev = 0, sms = 0, per_sm = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ladder_kernel, kThreads, smem_bytes);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ladder_kernel, kLadderThreads, smem_bytes);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorInvalidValue;
     const int grid = L.n_items < sms * per_sm ? L.n_items : sms * per_sm;     // one wave of resident CTAs
-    ladder_kernel<<<grid, kThreads, smem_bytes, s>>>(L);
+    ladder_kernel<<<grid, kLadderThreads, smem_bytes, s>>>(L);
     return cudaGetLastError();
 }
 

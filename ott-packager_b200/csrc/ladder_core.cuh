@@ -160,22 +160,23 @@ OTT_DEV void phase_stage(int tid, const TileGeom &g, unsigned char *smem)
         }
         return;
     }
-    const int row_bytes = T.srcW * g.bps;
-    const int bx0 = g.sx0 * g.bps;
-    for (int p = 0; p < g.nplanes; ++p) {
+    const int bps = g.bps, sshift = g.src_shift, sr = g.sr, sy0 = g.sy0, spw = g.spw, nvec = g.nvec, nplanes = g.nplanes;
+    const int row_bytes = T.srcW * bps;
+    const int bx0 = g.sx0 * bps;
+    for (int p = 0; p < nplanes; ++p) {
         const uint8_t *base = p ? g.src1 : g.src0;
         const int pitch = p ? g.src_pitch1 : g.src_pitch0;
         const bool aligned = (((uintptr_t)base | (uintptr_t)pitch) & 15) == 0;
-        for (int r = r0; r < g.sr; r += rstep) {
-            const uint8_t *row = base + (size_t)(g.sy0 + r) * pitch;
-            uint4 *srow = reinterpret_cast<uint4 *>(src_s + (p * g.sr + r) * g.spw);
-            for (int v = v0; v < g.nvec; v += lpr) {
+        for (int r = r0; r < sr; r += rstep) {
+            const uint8_t *row = base + (size_t)(sy0 + r) * pitch;
+            uint4 *srow = reinterpret_cast<uint4 *>(src_s + (p * sr + r) * spw);
+            for (int v = v0; v < nvec; v += lpr) {
                 const int bx = bx0 + 16 * v;
                 uint4 q = (aligned && bx + 16 <= row_bytes) ? ott_ldg(reinterpret_cast<const uint4 *>(row + bx))
                                                             : load_vec_slow(row, bx, row_bytes);
-                if (g.bps == 2 && g.src_shift) {
-                    q.x = shift_mask16(q.x, g.src_shift); q.y = shift_mask16(q.y, g.src_shift);
-                    q.z = shift_mask16(q.z, g.src_shift); q.w = shift_mask16(q.w, g.src_shift);
+                if (bps == 2 && sshift) {
+                    q.x = shift_mask16(q.x, sshift); q.y = shift_mask16(q.y, sshift);
+                    q.z = shift_mask16(q.z, sshift); q.w = shift_mask16(q.w, sshift);
                 }
                 srow[v] = q;
             }
@@ -514,43 +515,48 @@ OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
     constexpr int NW = CPT / 2;                                 // shared words per tap
     constexpr int NO = BPS == 1 ? NW / 2 : NW;                  // packed output words per plane
     typedef typename StoreT<BPS>::type S;
+    // the geometry lives in shared memory: copy what the loop needs into registers once
     const PlaneTables &T = *g.T;
-    const int lpr_log2 = g.tw_log2 - (CPT == 8 ? 3 : 2);        // lanes per output row: tw / CPT
+    const int tw_log2 = g.tw_log2, tile_w = g.tw, tile_h = g.th, x0 = g.x0, y0 = g.y0, sy0 = g.sy0, sr = g.sr;
+    const int mid_pitch = g.mid_pitch, approx = g.approx_v, shift = g.dst_shift, nplanes = g.nplanes, il = g.dst_interleaved;
+    const int vtaps = T.vtaps, exact_from = T.exact_from, dstW = T.dstW;
+    uint8_t *const dst0 = g.dst0, *const dst1 = g.dst1;
+    const int dpitch0 = g.dst_pitch0, dpitch1 = g.dst_pitch1;
+    const int lpr_log2 = tw_log2 - (CPT == 8 ? 3 : 2);          // lanes per output row: tw / CPT
     const int lx = tid & ((1 << lpr_log2) - 1), ry = tid >> lpr_log2, rows_per_pass = kThreads >> lpr_log2;
     const int x = CPT * lx;
-    if (x >= g.tw) return;
-    const int step_words = g.mid_pitch >> 1;
-    const int vtaps = T.vtaps;
+    if (x >= tile_w) return;
+    const int step_words = mid_pitch >> 1;
     const int16_t *mid_s = reinterpret_cast<const int16_t *>(smem + g.off_mid);
     const int16_t *vc_s = reinterpret_cast<const int16_t *>(smem + g.off_vc);
     const int32_t *vpos_s = reinterpret_cast<const int32_t *>(smem + g.off_vpos);
-    const int gx = g.x0 + x;
-    for (int y = ry; y < g.th; y += rows_per_pass) {
-        const int gy = g.y0 + y;
-        const int r0 = vpos_s[y] - g.sy0;
+    const int gx = x0 + x;
+    for (int y = ry; y < tile_h; y += rows_per_pass) {
+        const int gy = y0 + y;
+        const int r0 = vpos_s[y] - sy0;
         const int16_t *cf = vc_s + y * vtaps;
         int mode;
-        if (BPS == 1) mode = vtaps == 1 ? VM_ONE8 : ((g.approx_v && gy < T.exact_from) ? VM_APPROX8 : VM_EXACT8);
+        if (BPS == 1) mode = vtaps == 1 ? VM_ONE8 : ((approx && gy < exact_from) ? VM_APPROX8 : VM_EXACT8);
         else mode = vtaps == 1 ? VM_ONE10 : VM_EXACT10;
         uint32_t o0[NO];
-        vcolumns<NW, VT, BPS>(reinterpret_cast<const uint32_t *>(mid_s + r0 * g.mid_pitch + x), step_words, cf, vtaps, mode, g.dst_shift, o0);
-        if (g.nplanes == 1) {
-            store_words<S, NO>(g.dst0 + (size_t)gy * g.dst_pitch0, gx, o0, T.dstW);
+        vcolumns<NW, VT, BPS>(reinterpret_cast<const uint32_t *>(mid_s + r0 * mid_pitch + x), step_words, cf, vtaps, mode, shift, o0);
+        if (nplanes == 1) {
+            store_words<S, NO>(dst0 + (size_t)gy * dpitch0, gx, o0, dstW);
             continue;
         }
         uint32_t o1[NO];
-        vcolumns<NW, VT, BPS>(reinterpret_cast<const uint32_t *>(mid_s + (g.sr + r0) * g.mid_pitch + x), step_words, cf, vtaps, mode, g.dst_shift, o1);
-        if (g.dst_interleaved) {
+        vcolumns<NW, VT, BPS>(reinterpret_cast<const uint32_t *>(mid_s + (sr + r0) * mid_pitch + x), step_words, cf, vtaps, mode, shift, o1);
+        if (il) {
             uint32_t z[2 * NO];
             OTT_UNROLL
             for (int k = 0; k < NO; ++k) {
                 if (BPS == 1) zip8(o0[k], o1[k], z[2 * k], z[2 * k + 1]);
                 else zip16(o0[k], o1[k], z[2 * k], z[2 * k + 1]);
             }
-            store_words<S, 2 * NO>(g.dst0 + (size_t)gy * g.dst_pitch0, 2 * gx, z, 2 * T.dstW);
+            store_words<S, 2 * NO>(dst0 + (size_t)gy * dpitch0, 2 * gx, z, 2 * dstW);
         } else {
-            store_words<S, NO>(g.dst0 + (size_t)gy * g.dst_pitch0, gx, o0, T.dstW);
-            store_words<S, NO>(g.dst1 + (size_t)gy * g.dst_pitch1, gx, o1, T.dstW);
+            store_words<S, NO>(dst0 + (size_t)gy * dpitch0, gx, o0, dstW);
+            store_words<S, NO>(dst1 + (size_t)gy * dpitch1, gx, o1, dstW);
         }
     }
 }

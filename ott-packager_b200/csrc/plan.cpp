@@ -67,7 +67,10 @@ Plan::~Plan()
 
 namespace {
 
-constexpr size_t kSmemBudget = 72 * 1024;    // preferred CTA footprint incl. the second source buffer (3 CTAs per SM)
+// Two CTAs per SM: 2 source buffers + intermediates + tables must stay under ~110 KB per CTA.
+constexpr size_t kSrcCap = 36 * 1024;        // one staged-source buffer
+constexpr size_t kMidCap = 36 * 1024;        // H-pass result region
+constexpr int kMaxTileRows = 128;            // keeps enough tiles per frame for load balance
 constexpr size_t kSmemHardLimit = 224 * 1024; // == kMaxTileSmem (kernels.h); sm_100 allows 227 KB per CTA
 
 template <typename T>
@@ -94,19 +97,6 @@ TileRegions tile_regions(int nplanes, int sr_max, int sw_words, int tw, int th, 
     r.vc = (((size_t)th * vtaps * 2 + 3) & ~(size_t)3) + (size_t)th * 4;
     r.vc = (r.vc + 15) & ~(size_t)15;
     return r;
-}
-
-// footprint used for tile sizing: two source buffers (the next tile is fetched while this one computes)
-size_t tile_bytes(int nplanes, int sr_max, int sw_words, int tw, int th, int vtaps)
-{
-    const TileRegions r = tile_regions(nplanes, sr_max, sw_words, tw, th, vtaps);
-    return 2 * r.src + r.mid + r.vc + 16;
-}
-
-size_t tile_bytes_single(int nplanes, int sr_max, int sw_words, int tw, int th, int vtaps)
-{
-    const TileRegions r = tile_regions(nplanes, sr_max, sw_words, tw, th, vtaps);
-    return r.src + r.mid + r.vc + 16;
 }
 
 // Builds tables + tiling for one plane kind of one rung.  Host vectors are kept in `keep` only long enough to upload.
@@ -146,38 +136,54 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
         }
         return m;
     };
-    auto try_width = [&](int tw) {
-        T.tw = tw;
-        T.tiles_x = (dstW + tw - 1) / tw;
+    // Tile shape: the H pass is recomputed for the vertical halo rows of every tile, so tall tiles are cheap and narrow
+    // ones cost only extra staged bytes.  Pick the tallest tile whose staged source and intermediates fit their caps.
+    struct Shape { int tw, th, sw_words, sr_max; double halo; bool fits; };
+    auto shape_for = [&](int tw) {
+        Shape sh{tw, row_quant, 0, 0, 1e9, false};
+        const int tiles_x = (dstW + tw - 1) / tw;
         int nvec = 0;
-        for (int tx = 0; tx < T.tiles_x; ++tx) {
+        for (int tx = 0; tx < tiles_x; ++tx) {
             const int x0 = tx * tw, x1 = std::min(x0 + tw, dstW) - 1;
             const int s0 = h.pos[x0] & ~(spv - 1), s1 = h.pos[x1] + taps4;
             nvec = std::max(nvec, (s1 - s0 + 4 / bps + spv - 1) / spv);    // + one word of funnel-shift slack
         }
-        T.sw_words = nvec * 4;
-        int th = std::min((dstH + row_quant - 1) / row_quant * row_quant, 256);
-        while (th > row_quant && tile_bytes(nplanes, rows_needed(th), T.sw_words, tw, th, v.taps) > kSmemBudget) th -= row_quant;
-        if (th == row_quant) {
-            // very long vertical filters (4K -> thumbnail): shrink below the quantum until the tile fits at all
-            while (th > 1 && tile_bytes_single(nplanes, rows_needed(th), T.sw_words, tw, th, v.taps) > kSmemHardLimit) th /= 2;
-        } else {
-            // rebalance so the last tile row is not a sliver
-            const int nty = (dstH + th - 1) / th;
+        sh.sw_words = nvec * 4;
+        auto fits = [&](int th, bool hard) {
+            const TileRegions r = tile_regions(nplanes, rows_needed(th), sh.sw_words, tw, th, v.taps);
+            return hard ? r.src + r.mid + r.vc + 16 <= kSmemHardLimit : (r.src <= kSrcCap && r.mid <= kMidCap);
+        };
+        int th = std::min((dstH + row_quant - 1) / row_quant * row_quant, kMaxTileRows);
+        while (th > row_quant && !fits(th, false)) th -= row_quant;
+        if (fits(th, false)) {
+            const int nty = (dstH + th - 1) / th;                // rebalance so the last tile row is not a sliver
             th = ((dstH + nty - 1) / nty + row_quant - 1) / row_quant * row_quant;
+            sh.fits = true;
+        } else {
+            // very long filters (4K -> thumbnail): single-buffered launch, shrink until the tile fits at all
+            while (th > 1 && !fits(th, true)) th /= 2;
+            sh.fits = fits(th, true);
         }
-        T.th = th;
-        T.tiles_y = (dstH + th - 1) / th;
-        T.sr_max = rows_needed(th);
-        return tile_bytes(nplanes, T.sr_max, T.sw_words, tw, th, v.taps);
+        sh.th = th;
+        sh.sr_max = rows_needed(th);
+        sh.halo = (double)sh.sr_max * dstH / ((double)std::min(th, dstH) * srcH);
+        return sh;
     };
-    auto single_bytes = [&]() { return tile_bytes_single(nplanes, T.sr_max, T.sw_words, T.tw, T.th, v.taps); };
-    size_t smem_out = try_width(dstW >= 128 ? 64 : 32);
-    if (smem_out > kSmemBudget && T.tw == 64 && T.th <= row_quant) smem_out = try_width(32);   // extreme ratios: narrower tiles
+    Shape best = shape_for(dstW > 64 ? 64 : 32);
+    if (best.tw == 64) {
+        const Shape narrow = shape_for(32);
+        if (narrow.fits && (!best.fits || narrow.halo < 0.9 * best.halo)) best = narrow;
+    }
+    if (!best.fits) { err = "filter too long for one tile (shared memory)"; return false; }
+    T.tw = best.tw;
+    T.th = best.th;
+    T.sw_words = best.sw_words;
+    T.sr_max = best.sr_max;
+    T.tiles_x = (dstW + T.tw - 1) / T.tw;
+    T.tiles_y = (dstH + T.th - 1) / T.th;
     regions = tile_regions(nplanes, T.sr_max, T.sw_words, T.tw, T.th, v.taps);
     hpos_out = h.pos;
     vpos_out = v.pos;
-    if (single_bytes() > kSmemHardLimit) { err = "filter too long for one tile (shared memory)"; return false; }
 
     T.hpos = upload(plan, h.pos, err);
     T.hc_hi = upload(plan, hi, err);

@@ -273,6 +273,36 @@ int ottgpu_channel_create(const ottgpu_cfg *cfg, ottgpu_channel **out)
 
 int ottgpu_channel_gpu(const ottgpu_channel *ch) { return ch ? ch->gpu : OTTGPU_ERR_ARG; }
 
+int ottgpu_channel_describe(const ottgpu_channel *ch, char *buf, size_t size)
+{
+    if (!ch) return fail(OTTGPU_ERR_ARG, "null channel");
+    const Plan &p = *ch->plan;
+    std::string out;
+    char line[512];
+    int db = 0;
+    const size_t smem = ladder_smem_bytes(p.src_max[0], p.mid_max[0], p.vc_max[0], &db);
+    snprintf(line, sizeof line, "source %dx%d fmt %d, %d rung slot(s), %zu work items/frame (+%zu thumbnail), shared memory %zu B (%s), regions src %d mid %d vc %d\n",
+             p.cfg.src_width, p.cfg.src_height, p.cfg.src_fmt, p.n_slots, p.items.size(), p.thumb_items.size(), smem,
+             db ? "double-buffered" : "single buffer", p.src_max[0], p.mid_max[0], p.vc_max[0]);
+    out += line;
+    for (int s = 0; s < p.n_slots; ++s) {
+        const RungDev &R = p.host_copy.rung[s];
+        for (int k = 0; k < 2; ++k) {
+            const PlaneTables &T = k ? R.chroma : R.luma;
+            snprintf(line, sizeof line, "  slot %d %s %s %dx%d -> %dx%d  taps H %d (x4 quads %d) V %d  tile %dx%d  tiles %dx%d  src rows/tile %d  staged row %d B  exact_from %d\n",
+                     s, s == p.thumb_slot ? "thumb" : "rung", k ? "chroma" : "luma", T.srcW, T.srcH, T.dstW, T.dstH, 4 * T.hq, T.hq,
+                     T.vtaps, T.tw, T.th, T.tiles_x, T.tiles_y, T.sr_max, T.sw_words * 4, T.exact_from);
+            out += R.scaled ? line : std::string("  slot ") + std::to_string(s) + (k ? " chroma" : " luma") + " same size: copy items\n";
+        }
+    }
+    if (buf && size) {
+        const size_t n = std::min(size - 1, out.size());
+        std::memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return (int)out.size();
+}
+
 int ottgpu_channel_reset(ottgpu_channel *ch)
 {
     if (!ch) return fail(OTTGPU_ERR_ARG, "null channel");
