@@ -54,21 +54,26 @@ __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" 
 constexpr int kLadderThreads = kThreads + 32;     // 8 compute warps + 1 producer warp
 
 // Warp-specialised persistent kernel.
-//   producer warp : pulls the next work item from the global counter, resolves its geometry into the shared slot of
-//                   the free buffer, and has the TMA engine copy the tile's source rows (one cp.async.bulk per row)
-//                   into that buffer; completion is signalled on full[buf] (mbarrier, transaction bytes).
-//   compute warps : wait full[buf] -> H pass (staged rows -> int16 intermediates) -> V pass + store -> arrive empty[buf].
-// Two buffers: tile k+1 streams in while tile k computes.
+//   producer warp : pulls work items from the global counter and resolves their geometry into a ring of kGeomSlots
+//                   shared descriptors, running ahead of the compute warps; for tiles whose rows can be bulk-copied it
+//                   waits for a free source buffer and has the TMA engine copy the rows (one cp.async.bulk per row);
+//                   completion (transaction bytes) is signalled on the descriptor's `ready` mbarrier.
+//   compute warps : wait ready[slot] -> H pass (staged rows -> int16 intermediates) -> V pass + store -> release the
+//                   descriptor slot and the source buffer.
+// Two source buffers: tile k+1 streams in while tile k computes.
+constexpr int kGeomSlots = 4;
+
 __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderLaunch L)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t full[2], empty[2];
-    __shared__ TileGeom s_geom[2];
-    __shared__ int s_idx[2], s_what[2];
+    __shared__ __align__(8) uint64_t ready[kGeomSlots], gfree[kGeomSlots], empty[2];
+    __shared__ TileGeom s_geom[kGeomSlots];
+    __shared__ int s_idx[kGeomSlots], s_what[kGeomSlots], s_buf[kGeomSlots];
     const int tid = threadIdx.x;
     const int nbuf = L.double_buffer ? 2 : 1;
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kThreads); }
+        for (int i = 0; i < kGeomSlots; ++i) { mbar_init(&ready[i], 1); mbar_init(&gfree[i], kThreads); }
+        for (int i = 0; i < 2; ++i) mbar_init(&empty[i], kThreads);
         fence_mbar_init();
     }
     __syncthreads();
@@ -76,51 +81,63 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
     if (tid >= kThreads) {
         // ------------------------------------------------------------------ producer warp
         const int lane = tid - kThreads;
-        uint32_t pe0 = 1, pe1 = 1;                 // a fresh mbarrier passes a wait on parity 1
-        for (int buf = 0;; buf = (buf + 1 == nbuf) ? 0 : buf + 1) {
-            int idx = 0;
-            if (lane == 0) idx = atomicAdd(L.counter, 1);
+        uint32_t pg = (1u << kGeomSlots) - 1, pe = 3;    // parity bits; a fresh mbarrier passes a wait on parity 1
+        int buf = 0;
+        int idx = 0;
+        if (lane == 0) idx = atomicAdd(L.counter, 1);
+        for (int slot = 0;; slot = (slot + 1) & (kGeomSlots - 1)) {
             idx = __shfl_sync(0xffffffffu, idx, 0);
-            if (buf == 0) { mbar_wait(&empty[0], pe0); pe0 ^= 1; }
-            else { mbar_wait(&empty[1], pe1); pe1 ^= 1; }
+            int idx_next = 0;
+            if (lane == 0 && idx < L.n_items) idx_next = atomicAdd(L.counter, 1);     // in flight while this tile is set up
+            mbar_wait(&gfree[slot], (pg >> slot) & 1);
+            pg ^= 1u << slot;
             if (lane == 0) {
-                s_idx[buf] = idx;
-                s_what[buf] = idx < L.n_items ? item_prepare(L.items[idx], L.binds[L.items[idx].chan], L, buf, s_geom[buf]) : 0;
+                s_idx[slot] = idx;
+                s_buf[slot] = buf;
+                s_what[slot] = idx < L.n_items ? item_prepare(L.items[idx], L.binds[L.items[idx].chan], L, buf, s_geom[slot]) : 0;
             }
             __syncwarp();
             if (idx >= L.n_items) {
-                if (lane == 0) mbar_arrive(&full[buf]);
+                if (lane == 0) mbar_arrive(&ready[slot]);
                 break;
             }
-            const TileGeom &g = s_geom[buf];
-            if (s_what[buf] == 1 && g.bulk_ok) {
-                const int rows = g.nplanes * g.sr, bytes = g.row_copy_bytes, sr = g.sr;
-                fence_proxy_async();               // the buffer was last read through the generic proxy
-                if (lane == 0) mbar_expect_tx(&full[buf], (uint32_t)(rows * bytes));
-                __syncwarp();
-                unsigned char *dst = smem + g.off_src;
-                const int pitch_s = g.spw * 4;
-                for (int r = lane; r < rows; r += 32) {
-                    const int p = r >= sr, rr = r - p * sr;
-                    const uint8_t *src = (p ? g.src1 : g.src0) + (size_t)(g.sy0 + rr) * (p ? g.src_pitch1 : g.src_pitch0) + g.sx0;
-                    bulk_g2s(dst + r * pitch_s, src, (uint32_t)bytes, &full[buf]);
+            const TileGeom &g = s_geom[slot];
+            if (s_what[slot] == 1) {
+                mbar_wait(&empty[buf], (pe >> buf) & 1);       // the tile that last used this source buffer is done
+                pe ^= 1u << buf;
+                if (g.bulk_ok) {
+                    const int rows = g.nplanes * g.sr, bytes = g.row_copy_bytes, sr = g.sr;
+                    fence_proxy_async();                       // the buffer was last read through the generic proxy
+                    if (lane == 0) mbar_expect_tx(&ready[slot], (uint32_t)(rows * bytes));
+                    __syncwarp();
+                    unsigned char *dst = smem + g.off_src;
+                    const int pitch_s = g.spw * 4;
+                    for (int r = lane; r < rows; r += 32) {
+                        const int p = r >= sr, rr = r - p * sr;
+                        const uint8_t *src = (p ? g.src1 : g.src0) + (size_t)(g.sy0 + rr) * (p ? g.src_pitch1 : g.src_pitch0) + g.sx0;
+                        bulk_g2s(dst + r * pitch_s, src, (uint32_t)bytes, &ready[slot]);
+                    }
+                } else if (lane == 0) {
+                    mbar_arrive(&ready[slot]);                 // compute warps stage this tile through registers
                 }
+                buf = (buf + 1 == nbuf) ? 0 : buf + 1;
             } else if (lane == 0) {
-                mbar_arrive(&full[buf]);           // nothing to fetch (copy item, skipped item, or compute-warp staging)
+                mbar_arrive(&ready[slot]);                     // copy item / skipped item: no source buffer involved
             }
+            idx = idx_next;
         }
         return;
     }
 
     // ---------------------------------------------------------------------- compute warps
-    uint32_t pf0 = 0, pf1 = 0;
-    for (int buf = 0;; buf = (buf + 1 == nbuf) ? 0 : buf + 1) {
-        if (buf == 0) { mbar_wait(&full[0], pf0); pf0 ^= 1; }
-        else { mbar_wait(&full[1], pf1); pf1 ^= 1; }
-        const int idx = s_idx[buf];
+    uint32_t pr = 0;
+    for (int slot = 0;; slot = (slot + 1) & (kGeomSlots - 1)) {
+        mbar_wait(&ready[slot], (pr >> slot) & 1);
+        pr ^= 1u << slot;
+        const int idx = s_idx[slot];
         if (idx >= L.n_items) break;
-        const int what = s_what[buf];
-        const TileGeom &g = s_geom[buf];
+        const int what = s_what[slot];
+        const TileGeom &g = s_geom[slot];
         if (what == 2) {
             item_copy(tid, L.items[idx], L.binds[L.items[idx].chan]);
         } else if (what == 1) {
@@ -130,11 +147,12 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
             }
             phase_tables(tid, g, smem);
             phase_hpass(tid, g, smem);
-            compute_sync();                        // H-pass result and V tables complete
+            compute_sync();                        // H-pass result and V tables complete; the source buffer is free
+            mbar_arrive(&empty[s_buf[slot]]);
             phase_vpass(tid, g, smem);
             compute_sync();                        // intermediates free for the next tile's H pass
         }
-        mbar_arrive(&empty[buf]);                  // source buffer + geometry slot may be refilled
+        mbar_arrive(&gfree[slot]);                 // descriptor slot may be rewritten
     }
 }
 
