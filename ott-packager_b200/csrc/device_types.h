@@ -11,6 +11,7 @@ namespace ottgpu {
 
 constexpr int kMaxRungs = 8;
 constexpr int kMaxRungSlots = kMaxRungs + 1;   // slot 8 = thumbnail (transvideo.c:2155-2174)
+constexpr int kTensorMapBytes = 128;           // sizeof(CUtensorMap)
 constexpr int kThreads = 256;                  // compute threads of a ladder CTA (8 warps); the kernel adds one producer warp
 
 enum ItemKind : uint8_t {
@@ -35,6 +36,7 @@ struct PlaneTables {
     int tiles_x, tiles_y;
     int sw_words;            // shared-memory source row pitch in 32-bit words (max over tiles, + funnel slack)
     int sr_max;              // max source rows any tile needs
+    int tma_ok;              // tiles can be fetched with one 2-D TMA box (sw_words x sr_max u32 elements) per plane
 };
 
 struct RungDev {
@@ -58,6 +60,7 @@ struct Binding {
     int active;              // 0: channel produces nothing this step (yadif priming) -> its items exit at once
     int thumb_active;        // thumbnail slot wanted this step
     uint32_t skip_mask;      // rung slots already produced elsewhere this step (yadif wrote the full-size rung)
+    const unsigned char *tmaps;  // CUtensorMap[kMaxRungSlots][3] (luma, U, V boxes) of this step's source frame, or null
     const uint8_t *src[3];   // Y,U,V  or  Y,UV
     int src_pitch[3];        // bytes
     uint8_t *dst[kMaxRungSlots][3];

@@ -30,6 +30,14 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// one 2-D box (tensor map coordinates: x in 32-bit elements, y in rows) -> shared memory, completion on `bar`
+__device__ __forceinline__ void tma_box_2d(void *dst_smem, const void *tmap, int x, int y, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     asm volatile(
@@ -106,16 +114,12 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
                 mbar_wait(&empty[buf], (pe >> buf) & 1);       // the tile that last used this source buffer is done
                 pe ^= 1u << buf;
                 if (g.bulk_ok) {
-                    const int rows = g.nplanes * g.sr, bytes = g.row_copy_bytes, sr = g.sr;
-                    fence_proxy_async();                       // the buffer was last read through the generic proxy
-                    if (lane == 0) mbar_expect_tx(&ready[slot], (uint32_t)(rows * bytes));
-                    __syncwarp();
-                    unsigned char *dst = smem + g.off_src;
-                    const int pitch_s = g.spw * 4;
-                    for (int r = lane; r < rows; r += 32) {
-                        const int p = r >= sr, rr = r - p * sr;
-                        const uint8_t *src = (p ? g.src1 : g.src0) + (size_t)(g.sy0 + rr) * (p ? g.src_pitch1 : g.src_pitch0) + g.sx0;
-                        bulk_g2s(dst + r * pitch_s, src, (uint32_t)bytes, &ready[slot]);
+                    if (lane == 0) {
+                        fence_proxy_async();                   // the buffer was last read through the generic proxy
+                        mbar_expect_tx(&ready[slot], (uint32_t)(g.nplanes * g.box_bytes));
+                        unsigned char *dst = smem + g.off_src;
+                        tma_box_2d(dst, g.tmap0, g.sx0 >> 2, g.sy0, &ready[slot]);
+                        if (g.nplanes == 2) tma_box_2d(dst + g.plane_stride, g.tmap1, g.sx0 >> 2, g.sy0, &ready[slot]);
                     }
                 } else if (lane == 0) {
                     mbar_arrive(&ready[slot]);                 // compute warps stage this tile through registers

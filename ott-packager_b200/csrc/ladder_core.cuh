@@ -77,8 +77,10 @@ struct TileGeom {
     int tw_log2;             // T->tw is 32 or 64
     int approx_v;
     int off_src, off_mid, off_vc, off_vpos;   // byte offsets of the regions inside the CTA's shared memory
-    int bulk_ok;             // source rows can be fetched with 16-byte aligned bulk copies (TMA) into off_src
-    int row_copy_bytes;      // bytes per staged row when bulk_ok
+    int plane_stride;        // bytes between the two staged chroma planes inside a source buffer (128-byte multiple)
+    int bulk_ok;             // the tile's source window is fetched by the TMA engine (one 2-D box per plane)
+    int box_bytes;           // bytes one TMA box delivers
+    const unsigned char *tmap0, *tmap1;   // tensor maps of the plane(s)
     const uint8_t *src0, *src1;      // plane bases (chroma: U,V or the interleaved UV plane twice)
     int src_pitch0, src_pitch1;      // bytes
     int src_interleaved;     // chroma samples interleaved in the source (P010)
@@ -132,7 +134,7 @@ OTT_DEV void phase_stage(int tid, const TileGeom &g, unsigned char *smem)
         const int row_bytes = T.srcW * 4;
         for (int r = r0; r < g.sr; r += rstep) {
             const uint8_t *row = g.src0 + (size_t)(g.sy0 + r) * g.src_pitch0;
-            uint32_t *su = src_s + (r * g.spw), *sv = src_s + ((g.sr + r) * g.spw);
+            uint32_t *su = src_s + (r * g.spw), *sv = src_s + (g.plane_stride >> 2) + (r * g.spw);
             for (int v = v0; v < g.nvec; v += lpr) {
                 const int bx = (g.sx0 + 8 * v) * 4;
                 uint4 a, b;
@@ -169,7 +171,7 @@ OTT_DEV void phase_stage(int tid, const TileGeom &g, unsigned char *smem)
         const bool aligned = (((uintptr_t)base | (uintptr_t)pitch) & 15) == 0;
         for (int r = r0; r < sr; r += rstep) {
             const uint8_t *row = base + (size_t)(sy0 + r) * pitch;
-            uint4 *srow = reinterpret_cast<uint4 *>(src_s + (p * sr + r) * spw);
+            uint4 *srow = reinterpret_cast<uint4 *>(src_s + p * (g.plane_stride >> 2) + r * spw);
             for (int v = v0; v < nvec; v += lpr) {
                 const int bx = bx0 + 16 * v;
                 uint4 q = (aligned && bx + 16 <= row_bytes) ? ott_ldg(reinterpret_cast<const uint4 *>(row + bx))
@@ -220,20 +222,22 @@ OTT_DEV void hpass8(int tid, const TileGeom &g, unsigned char *smem)
         hi[q] = ott_ldg(T.hc_hi + gx * HQ + q);
         lo[q] = ott_ldg(T.hc_lo + gx * HQ + q);
     }
-    const int nrows = g.nplanes * g.sr;
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(smem + g.off_src) + (off >> 2) + grp * g.spw;
-    int16_t *m = reinterpret_cast<int16_t *>(smem + g.off_mid) + col + grp * g.mid_pitch;
+    const int sr = g.sr, nplanes = g.nplanes, pstride = g.plane_stride >> 2;
     const int wstep = ngroups * g.spw, mstep = ngroups * g.mid_pitch;
-    int row = grp;
-    for (; row + ngroups < nrows; row += 2 * ngroups) {       // two rows in flight per thread
-        const int v0 = hdot8<HQ>(w, sh, hi, lo);
-        const int v1 = hdot8<HQ>(w + wstep, sh, hi, lo);
-        m[0] = (int16_t)v0;
-        m[mstep] = (int16_t)v1;
-        w += 2 * wstep;
-        m += 2 * mstep;
+    for (int p = 0; p < nplanes; ++p) {
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(smem + g.off_src) + p * pstride + (off >> 2) + grp * g.spw;
+        int16_t *m = reinterpret_cast<int16_t *>(smem + g.off_mid) + col + (p * sr + grp) * g.mid_pitch;
+        int row = grp;
+        for (; row + ngroups < sr; row += 2 * ngroups) {      // two rows in flight per thread
+            const int v0 = hdot8<HQ>(w, sh, hi, lo);
+            const int v1 = hdot8<HQ>(w + wstep, sh, hi, lo);
+            m[0] = (int16_t)v0;
+            m[mstep] = (int16_t)v1;
+            w += 2 * wstep;
+            m += 2 * mstep;
+        }
+        if (row < sr) m[0] = (int16_t)hdot8<HQ>(w, sh, hi, lo);
     }
-    if (row < nrows) m[0] = (int16_t)hdot8<HQ>(w, sh, hi, lo);
 }
 
 // any tap count: coefficients re-read per row (L1-resident); used for very long filters (thumbnail, 4K->360p lanczos)
@@ -246,11 +250,12 @@ OTT_DEV void hpass8_any(int tid, const TileGeom &g, unsigned char *smem)
     const int off = ott_ldg(T.hpos + gx) - g.sx0;
     const uint32_t sh = (uint32_t)(off & 3) * 8;
     const uint32_t *phi = T.hc_hi + gx * hq, *plo = T.hc_lo + gx * hq;
-    const int nrows = g.nplanes * g.sr;
+    const int nrows = g.nplanes * g.sr, sr = g.sr, pstride = g.plane_stride >> 2;
     const uint32_t *src_s = reinterpret_cast<const uint32_t *>(smem + g.off_src) + (off >> 2);
     int16_t *mid_s = reinterpret_cast<int16_t *>(smem + g.off_mid) + col;
     for (int row = grp; row < nrows; row += ngroups) {
-        const uint32_t *w = src_s + row * g.spw;
+        const int p = row >= sr;
+        const uint32_t *w = src_s + p * pstride + (row - p * sr) * g.spw;
         uint32_t cur = w[0];
         int ahi = 0;
         uint32_t alo = 0;
@@ -278,11 +283,12 @@ OTT_DEV void hpass16(int tid, const TileGeom &g, unsigned char *smem)
     int cf[4 * HQ];
     OTT_UNROLL
     for (int j = 0; j < 4 * HQ; ++j) cf[j] = ott_ldg(T.hc16 + gx * (4 * HQ) + j);
-    const int nrows = g.nplanes * g.sr;
+    const int nrows = g.nplanes * g.sr, sr = g.sr, pstride = g.plane_stride >> 2;
     const uint32_t *src_s = reinterpret_cast<const uint32_t *>(smem + g.off_src) + (off >> 1);
     int16_t *mid_s = reinterpret_cast<int16_t *>(smem + g.off_mid) + col;
     for (int row = grp; row < nrows; row += ngroups) {
-        const uint32_t *w = src_s + row * g.spw;
+        const int p = row >= sr;
+        const uint32_t *w = src_s + p * pstride + (row - p * sr) * g.spw;
         uint32_t cur = w[0];
         int acc = 0;
         OTT_UNROLL
@@ -305,11 +311,12 @@ OTT_DEV void hpass16_any(int tid, const TileGeom &g, unsigned char *smem)
     const int off = ott_ldg(T.hpos + gx) - g.sx0;
     const uint32_t sh = (uint32_t)(off & 1) * 16;
     const int16_t *pc = T.hc16 + gx * taps;
-    const int nrows = g.nplanes * g.sr;
+    const int nrows = g.nplanes * g.sr, sr = g.sr, pstride = g.plane_stride >> 2;
     const uint32_t *src_s = reinterpret_cast<const uint32_t *>(smem + g.off_src) + (off >> 1);
     int16_t *mid_s = reinterpret_cast<int16_t *>(smem + g.off_mid) + col;
     for (int row = grp; row < nrows; row += ngroups) {
-        const uint32_t *w = src_s + row * g.spw;
+        const int p = row >= sr;
+        const uint32_t *w = src_s + p * pstride + (row - p * sr) * g.spw;
         uint32_t cur = w[0];
         int acc = 0;
         for (int k = 0; 2 * k < taps; ++k) {
@@ -688,12 +695,14 @@ OTT_DEV int item_prepare(const Item &it, const Binding &b, const LadderLaunch &L
         g.dst1 = dst_il ? nullptr : b.dst[it.slot][2]; g.dst_pitch1 = dst_il ? 0 : b.dst_pitch[it.slot][2];
         g.dst_interleaved = dst_il;
     }
-    // bulk (TMA) staging: 8-bit planar rows whose base, pitch and width are all multiples of 16 bytes
-    const int row_bytes = T.srcW * plan.bps;
-    const uintptr_t al = (uintptr_t)g.src0 | (uintptr_t)g.src_pitch0 | (uintptr_t)row_bytes |
-                         (g.nplanes == 2 ? ((uintptr_t)g.src1 | (uintptr_t)g.src_pitch1) : 0);
-    g.bulk_ok = plan.bps == 1 && (al & 15) == 0;
-    g.row_copy_bytes = ott_min(g.nvec * 16, row_bytes - g.sx0 * plan.bps);
+    // one staged plane occupies sr_max rows of spw words, padded to the 128 bytes a TMA destination must be aligned to
+    g.plane_stride = (T.sr_max * T.sw_words * 4 + 127) & ~127;
+    // TMA staging: the host supplied tensor maps for this frame (8-bit planar source, 16-byte aligned planes) and the
+    // tile window fits one box; otherwise the compute warps stage the window through registers
+    g.bulk_ok = T.tma_ok && b.tmaps != nullptr;
+    g.box_bytes = T.sr_max * T.sw_words * 4;
+    g.tmap0 = b.tmaps + (size_t)(it.slot * 3 + (luma ? 0 : 1)) * kTensorMapBytes;
+    g.tmap1 = b.tmaps + (size_t)(it.slot * 3 + 2) * kTensorMapBytes;
     return 1;
 }
 

@@ -92,7 +92,7 @@ struct TileRegions { size_t src, mid, vc; };
 TileRegions tile_regions(int nplanes, int sr_max, int sw_words, int tw, int th, int vtaps)
 {
     TileRegions r;
-    r.src = (size_t)nplanes * sr_max * sw_words * 4;                      // multiple of 16 (sw_words % 4 == 0)
+    r.src = (size_t)nplanes * (((size_t)sr_max * sw_words * 4 + 127) & ~(size_t)127);   // planes 128-byte aligned (TMA)
     r.mid = (size_t)nplanes * (sr_max + 1) * tw * 2;                      // tw is 32 or 64 -> multiple of 16
     r.vc = (((size_t)th * vtaps * 2 + 3) & ~(size_t)3) + (size_t)th * 4;
     r.vc = (r.vc + 15) & ~(size_t)15;
@@ -181,6 +181,8 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
     T.sr_max = best.sr_max;
     T.tiles_x = (dstW + T.tw - 1) / T.tw;
     T.tiles_y = (dstH + T.th - 1) / T.th;
+    // one TMA box per plane: inner dimension <= 256 32-bit elements, <= 256 rows; 8-bit planar sources only
+    T.tma_ok = bps == 1 && T.sw_words <= 256 && T.sr_max <= 256 && srcW % 4 == 0;
     regions = tile_regions(nplanes, T.sr_max, T.sw_words, T.tw, T.th, v.taps);
     hpos_out = h.pos;
     vpos_out = v.pos;

@@ -13,6 +13,9 @@
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
+#if !defined(OTTGPU_EMULATE)
+#include <cuda.h>            // CUtensorMap + cuTensorMapEncodeTiled prototype (resolved through the runtime, no -lcuda)
+#endif
 #include "../../include/ottgpu.h"
 #include "kernels.h"
 #include "plan.h"
@@ -43,6 +46,13 @@ int fail_cuda(cudaError_t e, const char *where)
 std::mutex g_dev_mu;
 bool g_dev_ready[64] = {false};
 
+#if !defined(OTTGPU_EMULATE)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode_tiled = nullptr;
+#endif
+
 int prepare_device(int gpu)
 {
     int n = 0;
@@ -56,6 +66,15 @@ int prepare_device(int gpu)
         CK(cudaGetDeviceProperties(&prop, gpu));
         if (prop.major != 10) return fail(OTTGPU_ERR_CUDA, "libottgpu carries sm_100a code only; device is not compute capability 10.x");
         CK(configure_kernels());
+#if !defined(OTTGPU_EMULATE)
+        if (!g_encode_tiled) {
+            void *fn = nullptr;
+            cudaDriverEntryPointQueryResult st;
+            CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &st));
+            if (st != cudaDriverEntryPointSuccess || !fn) return fail(OTTGPU_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+            g_encode_tiled = (EncodeTiledFn)fn;
+        }
+#endif
         g_dev_ready[gpu] = true;
     }
     return OTTGPU_OK;
@@ -103,6 +122,11 @@ struct ottgpu_channel {
     int thumb_count = 0;
     int direct_rung = -1;                              // rung whose surface is byte-identical to a deinterlaced frame
     ottgpu_batch *solo = nullptr;
+    // tensor maps (one set per distinct source-frame address this channel has seen), least recently used first out
+    struct MapSet { const uint8_t *base = nullptr; unsigned char *dev = nullptr; uint64_t stamp = 0; };
+    std::vector<MapSet> maps;
+    uint64_t map_clock = 0;
+    bool wants_maps = false;
 };
 
 struct ottgpu_batch {
@@ -165,6 +189,76 @@ int ensure_dev(uint8_t **p, size_t bytes)
         cudaGetLastError();
         return fail(OTTGPU_ERR_NOMEM, "cudaMalloc(surface) failed");
     }
+    return OTTGPU_OK;
+}
+
+// Tensor maps for the frame at `base` (device memory, packed planar 8-bit): one box per scaled rung plane.
+// Returns null when TMA cannot be used for this frame (alignment) -- the kernel then stages through registers.
+int frame_tensor_maps(ottgpu_channel *c, const uint8_t *base, cudaStream_t stream, const unsigned char **out)
+{
+    *out = nullptr;
+#if !defined(OTTGPU_EMULATE)
+    if (!c->wants_maps) return OTTGPU_OK;
+    const ottgpu_cfg &cfg = c->cfg;
+    const uint8_t *pl[3];
+    int pitch[3];
+    plane_ptrs(cfg.src_fmt, base, cfg.src_width, cfg.src_height, pl, pitch);
+    for (int k = 0; k < 3; ++k)
+        if (((uintptr_t)pl[k] | (uintptr_t)pitch[k]) & 15) return OTTGPU_OK;
+    for (auto &m : c->maps)
+        if (m.base == base) {
+            m.stamp = ++c->map_clock;
+            *out = m.dev;
+            return OTTGPU_OK;
+        }
+    constexpr size_t kSetBytes = (size_t)kMaxRungSlots * 3 * kTensorMapBytes;
+    constexpr size_t kMaxSets = 24;
+    ottgpu_channel::MapSet *slot = nullptr;
+    if (c->maps.size() < kMaxSets) {
+        c->maps.emplace_back();
+        slot = &c->maps.back();
+        if (cudaMalloc((void **)&slot->dev, kSetBytes) != cudaSuccess) {
+            cudaGetLastError();
+            c->maps.pop_back();
+            return fail(OTTGPU_ERR_NOMEM, "cudaMalloc(tensor maps) failed");
+        }
+    } else {
+        slot = &c->maps[0];
+        for (auto &m : c->maps)
+            if (m.stamp < slot->stamp) slot = &m;
+        CK(cudaStreamSynchronize(stream));             // a launch in flight may still read the evicted set
+    }
+    alignas(64) static thread_local CUtensorMap host[kMaxRungSlots * 3];
+    std::memset(host, 0, sizeof(host));
+    const Plan &plan = *c->plan;
+    const int dims[3][2] = {{cfg.src_width, cfg.src_height},
+                            {(cfg.src_width + 1) / 2, (cfg.src_height + 1) / 2},
+                            {(cfg.src_width + 1) / 2, (cfg.src_height + 1) / 2}};
+    for (int s = 0; s < plan.n_slots; ++s) {
+        const RungDev &R = plan.host_copy.rung[s];
+        if (!R.scaled) continue;
+        for (int k = 0; k < 3; ++k) {
+            const PlaneTables &T = k ? R.chroma : R.luma;
+            if (!T.tma_ok) continue;
+            const cuuint64_t gdim[2] = {(cuuint64_t)(dims[k][0] / 4), (cuuint64_t)dims[k][1]};
+            const cuuint64_t gstride[1] = {(cuuint64_t)pitch[k]};
+            const cuuint32_t box[2] = {(cuuint32_t)T.sw_words, (cuuint32_t)T.sr_max};
+            const cuuint32_t estride[2] = {1, 1};
+            const CUresult r = g_encode_tiled(&host[s * 3 + k], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void *)pl[k], gdim, gstride, box,
+                                              estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(OTTGPU_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+        }
+    }
+    CK(cudaMemcpyAsync(slot->dev, host, kSetBytes, cudaMemcpyHostToDevice, stream));
+    slot->base = base;
+    slot->stamp = ++c->map_clock;
+    *out = slot->dev;
+#else
+    (void)c;
+    (void)base;
+    (void)stream;
+#endif
     return OTTGPU_OK;
 }
 
@@ -261,6 +355,10 @@ int ottgpu_channel_create(const ottgpu_cfg *cfg, ottgpu_channel **out)
             break;
         }
     }
+    for (int sidx = 0; sidx < plan->n_slots; ++sidx) {
+        const RungDev &R = plan->host_copy.rung[sidx];
+        if (R.scaled && (R.luma.tma_ok || R.chroma.tma_ok)) c->wants_maps = true;
+    }
     ottgpu_channel *raw = c.release();
     rc = ottgpu_batch_create(&raw, 1, &raw->solo);
     if (rc) {
@@ -322,6 +420,7 @@ void ottgpu_channel_destroy(ottgpu_channel *ch)
     for (uint8_t *p : ch->slots) cudaFree(p);
     cudaFree(ch->deint);
     for (uint8_t *p : ch->stage) cudaFree(p);
+    for (auto &m : ch->maps) cudaFree(m.dev);
     if (ch->own_stream) cudaStreamDestroy(ch->stream);
     delete ch;
 }
@@ -578,6 +677,10 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
             src_base = ydst;
         }
         plane_ptrs(cfg.src_fmt, src_base, cfg.src_width, cfg.src_height, bind.src, bind.src_pitch);
+        {
+            int rc = frame_tensor_maps(c, src_base, s, &bind.tmaps);
+            if (rc) return rc;
+        }
         bind.active = 1;
         bind.skip_mask = skip;
 

@@ -37,7 +37,7 @@ cudaError_t launch_ladder(LadderLaunch L, cudaStream_t)
         }
         // every byte the phases touch must lie inside the launch's dynamic shared memory
         if ((size_t)g.off_vpos + (size_t)g.th * 4 > smem_bytes) return cudaErrorInvalidValue;
-        if ((size_t)g.off_src + (size_t)g.nplanes * g.sr * g.spw * 4 > (size_t)g.off_src + L.src_max) return cudaErrorInvalidValue;
+        if ((size_t)(g.nplanes - 1) * g.plane_stride + (size_t)g.sr * g.spw * 4 > (size_t)L.src_max) return cudaErrorInvalidValue;
         if ((size_t)g.nplanes * (g.sr + 1) * g.mid_pitch * 2 > (size_t)L.mid_max) return cudaErrorInvalidValue;
         if (g.nvec * 4 > g.spw) return cudaErrorInvalidValue;
         std::fill(smem.begin(), smem.end(), 0xA5);       // poison: stale-data reads show up as mismatches
