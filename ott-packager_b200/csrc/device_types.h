@@ -11,6 +11,7 @@ namespace ottgpu {
 
 constexpr int kMaxRungs = 8;
 constexpr int kMaxRungSlots = kMaxRungs + 1;   // slot 8 = thumbnail (transvideo.c:2155-2174)
+constexpr int kGeomSlots = 4;                  // tile descriptors (and V-table regions) in flight per CTA
 constexpr int kTensorMapBytes = 128;           // sizeof(CUtensorMap)
 constexpr int kThreads = 256;                  // compute threads of a ladder CTA (8 warps); the kernel adds one producer warp
 

@@ -69,8 +69,6 @@ constexpr int kLadderThreads = kThreads + 32;     // 8 compute warps + 1 produce
 //   compute warps : wait ready[slot] -> H pass (staged rows -> int16 intermediates) -> V pass + store -> release the
 //                   descriptor slot and the source buffer.
 // Two source buffers: tile k+1 streams in while tile k computes.
-constexpr int kGeomSlots = 4;
-
 __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderLaunch L)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -102,7 +100,7 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
             if (lane == 0) {
                 s_idx[slot] = idx;
                 s_buf[slot] = buf;
-                s_what[slot] = idx < L.n_items ? item_prepare(L.items[idx], L.binds[L.items[idx].chan], L, buf, s_geom[slot]) : 0;
+                s_what[slot] = idx < L.n_items ? item_prepare(L.items[idx], L.binds[L.items[idx].chan], L, buf, slot, s_geom[slot]) : 0;
             }
             __syncwarp();
             if (idx >= L.n_items) {
@@ -111,6 +109,8 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
             }
             const TileGeom &g = s_geom[slot];
             if (s_what[slot] == 1) {
+                phase_tables(lane, 32, g, smem);               // V coefficients / row positions into this slot's table region
+                __syncwarp();
                 mbar_wait(&empty[buf], (pe >> buf) & 1);       // the tile that last used this source buffer is done
                 pe ^= 1u << buf;
                 if (g.bulk_ok) {
@@ -149,7 +149,6 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
                 phase_stage(tid, g, smem);
                 compute_sync();
             }
-            phase_tables(tid, g, smem);
             phase_hpass(tid, g, smem);
             compute_sync();                        // H-pass result and V tables complete; the source buffer is free
             mbar_arrive(&empty[s_buf[slot]]);
@@ -174,7 +173,8 @@ cudaError_t configure_kernels()
 
 size_t ladder_smem_bytes(int src_max, int mid_max, int vc_max, int *double_buffer)
 {
-    const size_t two = 2 * (size_t)src_max + mid_max + vc_max + 16, one = (size_t)src_max + mid_max + vc_max + 16;
+    const size_t tables = (size_t)kGeomSlots * vc_max;     // one table region per descriptor slot
+    const size_t two = 2 * (size_t)src_max + mid_max + tables + 16, one = (size_t)src_max + mid_max + tables + 16;
     const int db = two <= kMaxTileSmem;
     if (double_buffer) *double_buffer = db;
     return db ? two : one;

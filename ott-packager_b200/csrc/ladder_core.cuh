@@ -92,13 +92,24 @@ struct TileGeom {
 };
 
 // ------------------------------------------------------------------------------------------------ phase 0: tables
-OTT_DEV void phase_tables(int tid, const TileGeom &g, unsigned char *smem)
+// Copies the tile's vertical coefficients and row positions into its table slot; run by `nthreads` cooperating threads
+// (the producer warp in the kernel: the tables are in place before the compute warps are released).
+OTT_DEV void phase_tables(int tid, int nthreads, const TileGeom &g, unsigned char *smem)
 {
     const PlaneTables &T = *g.T;
     int16_t *vc_s = reinterpret_cast<int16_t *>(smem + g.off_vc);
     int32_t *vpos_s = reinterpret_cast<int32_t *>(smem + g.off_vpos);
-    for (int i = tid; i < g.th * T.vtaps; i += kThreads) vc_s[i] = ott_ldg(T.vc + g.y0 * T.vtaps + i);
-    for (int i = tid; i < g.th; i += kThreads) vpos_s[i] = ott_ldg(T.vpos + g.y0 + i);
+    const int n = g.th * T.vtaps, th = g.th;
+    const int16_t *vc = T.vc + g.y0 * T.vtaps;
+    const int32_t *vp = T.vpos + g.y0;
+    if (((n | (g.y0 * T.vtaps)) & 1) == 0) {               // pairs of coefficients per load
+        const uint32_t *s2 = reinterpret_cast<const uint32_t *>(vc);
+        uint32_t *d2 = reinterpret_cast<uint32_t *>(vc_s);
+        for (int i = tid; i < (n >> 1); i += nthreads) d2[i] = ott_ldg(s2 + i);
+    } else {
+        for (int i = tid; i < n; i += nthreads) vc_s[i] = ott_ldg(vc + i);
+    }
+    for (int i = tid; i < th; i += nthreads) vpos_s[i] = ott_ldg(vp + i);
 }
 
 // ------------------------------------------------------------------------------------------------ phase 1: staging
@@ -227,16 +238,24 @@ OTT_DEV void hpass8(int tid, const TileGeom &g, unsigned char *smem)
     for (int p = 0; p < nplanes; ++p) {
         const uint32_t *w = reinterpret_cast<const uint32_t *>(smem + g.off_src) + p * pstride + (off >> 2) + grp * g.spw;
         int16_t *m = reinterpret_cast<int16_t *>(smem + g.off_mid) + col + (p * sr + grp) * g.mid_pitch;
-        int row = grp;
-        for (; row + ngroups < sr; row += 2 * ngroups) {      // two rows in flight per thread
+        int left = (sr - grp + ngroups - 1) / ngroups;         // rows this thread owns in this plane
+        for (; left >= 4; left -= 4) {                         // four rows in flight per thread
             const int v0 = hdot8<HQ>(w, sh, hi, lo);
             const int v1 = hdot8<HQ>(w + wstep, sh, hi, lo);
+            const int v2 = hdot8<HQ>(w + 2 * wstep, sh, hi, lo);
+            const int v3 = hdot8<HQ>(w + 3 * wstep, sh, hi, lo);
             m[0] = (int16_t)v0;
             m[mstep] = (int16_t)v1;
-            w += 2 * wstep;
-            m += 2 * mstep;
+            m[2 * mstep] = (int16_t)v2;
+            m[3 * mstep] = (int16_t)v3;
+            w += 4 * wstep;
+            m += 4 * mstep;
         }
-        if (row < sr) m[0] = (int16_t)hdot8<HQ>(w, sh, hi, lo);
+        for (; left > 0; --left) {
+            m[0] = (int16_t)hdot8<HQ>(w, sh, hi, lo);
+            w += wstep;
+            m += mstep;
+        }
     }
 }
 
@@ -655,7 +674,7 @@ OTT_DEV void interleave_rows8(int tid, const uint8_t *u, const uint8_t *v, int s
 // ------------------------------------------------------------------------------------------------ item dispatch
 // Resolves one work item.  Returns 0: nothing to do, 1: scale tile (geometry filled), 2: copy item.
 // off_src: byte offset of the source buffer this tile stages into; the other regions follow 2 (or 1) source buffers.
-OTT_DEV int item_prepare(const Item &it, const Binding &b, const LadderLaunch &L, int buf, TileGeom &g)
+OTT_DEV int item_prepare(const Item &it, const Binding &b, const LadderLaunch &L, int buf, int table_slot, TileGeom &g)
 {
     if (!b.active || ((b.skip_mask >> it.slot) & 1u)) return 0;
     const PlanDev &plan = *b.plan;
@@ -676,7 +695,7 @@ OTT_DEV int item_prepare(const Item &it, const Binding &b, const LadderLaunch &L
     g.approx_v = R.approx_v;
     g.off_src = buf * L.src_max;
     g.off_mid = (L.double_buffer ? 2 : 1) * L.src_max;
-    g.off_vc = g.off_mid + L.mid_max;
+    g.off_vc = g.off_mid + L.mid_max + table_slot * L.vc_max;
     g.off_vpos = g.off_vc + ((T.th * T.vtaps * 2 + 3) & ~3);
     g.src_shift = plan.src_fmt == 2 ? 6 : 0;
     g.dst_shift = R.fmt == 2 ? 6 : 0;

@@ -11,7 +11,8 @@ cudaError_t configure_kernels() { return cudaSuccess; }
 
 size_t ladder_smem_bytes(int src_max, int mid_max, int vc_max, int *double_buffer)
 {
-    const size_t two = 2 * (size_t)src_max + mid_max + vc_max + 16, one = (size_t)src_max + mid_max + vc_max + 16;
+    const size_t tables = (size_t)kGeomSlots * vc_max;
+    const size_t two = 2 * (size_t)src_max + mid_max + tables + 16, one = (size_t)src_max + mid_max + tables + 16;
     const int db = two <= kMaxTileSmem;
     if (double_buffer) *double_buffer = db;
     return db ? two : one;
@@ -29,7 +30,7 @@ cudaError_t launch_ladder(LadderLaunch L, cudaStream_t)
         const Item it = L.items[blk];
         const Binding &b = L.binds[it.chan];
         TileGeom g;
-        const int what = item_prepare(it, b, L, db ? (blk & 1) : 0, g);   // alternate buffers like the kernel does
+        const int what = item_prepare(it, b, L, db ? (blk & 1) : 0, blk & (kGeomSlots - 1), g);   // alternate buffers like the kernel does
         if (what == 0) continue;
         if (what == 2) {
             for (int tid = 0; tid < kThreads; ++tid) item_copy(tid, it, b);
@@ -41,7 +42,8 @@ cudaError_t launch_ladder(LadderLaunch L, cudaStream_t)
         if ((size_t)g.nplanes * (g.sr + 1) * g.mid_pitch * 2 > (size_t)L.mid_max) return cudaErrorInvalidValue;
         if (g.nvec * 4 > g.spw) return cudaErrorInvalidValue;
         std::fill(smem.begin(), smem.end(), 0xA5);       // poison: stale-data reads show up as mismatches
-        for (int tid = 0; tid < kThreads; ++tid) { phase_tables(tid, g, sm); phase_stage(tid, g, sm); }
+        for (int lane = 0; lane < 32; ++lane) phase_tables(lane, 32, g, sm);
+        for (int tid = 0; tid < kThreads; ++tid) phase_stage(tid, g, sm);
         for (int tid = 0; tid < kThreads; ++tid) phase_hpass(tid, g, sm);
         for (int tid = 0; tid < kThreads; ++tid) phase_vpass(tid, g, sm);
     }
