@@ -406,9 +406,10 @@ template <int BPS> OTT_DEV uint32_t pack2(int a, int b, int shift)   // 16-bit: 
 }
 OTT_DEV uint32_t pack4(int a, int b, int c, int d) { return (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)d << 24); }
 
-// One row of NW*2 adjacent columns.  VT > 0: compile-time tap count (fully unrolled); VT == 0: run-time `vtaps`.
+// One row of NW*2 adjacent columns, `vtaps` taps (run-time count: the tap loop is unrolled by four, which keeps the
+// kernel small enough for the instruction cache -- fully unrolled per-tap-count variants measured slower).
 // Output: 8-bit -> NW/2 packed words, 16-bit -> NW packed words.
-template <int NW, int VT, int BPS>
+template <int NW, int BPS>
 OTT_DEV void vcolumns(const uint32_t *m, int step_words, const int16_t *cf, int vtaps, int mode, int shift,
                       uint32_t (&out)[BPS == 1 ? NW / 2 : NW])
 {
@@ -421,66 +422,66 @@ OTT_DEV void vcolumns(const uint32_t *m, int step_words, const int16_t *cf, int 
             if (mode == VM_ONE8) { a[2 * k] = ott_clip((sx_lo(ww[k]) + 64) >> 7, 255); a[2 * k + 1] = ott_clip((sx_hi(ww[k]) + 64) >> 7, 255); }
             else { a[2 * k] = ott_clip((sx_lo(ww[k]) + 16) >> 5, 1023); a[2 * k + 1] = ott_clip((sx_hi(ww[k]) + 16) >> 5, 1023); }
         }
-    } else {
-        const int n = VT > 0 ? VT : vtaps;
-        const int init = mode == VM_APPROX8 ? (64 + 8 * (n - 1)) >> 4 : (mode == VM_EXACT8 ? 64 << 12 : 1 << 16);
+    } else if (mode == VM_APPROX8) {
+        const int init = (64 + 8 * (vtaps - 1)) >> 4;
         OTT_UNROLL
         for (int k = 0; k < 2 * NW; ++k) a[k] = init;
-        if (mode == VM_APPROX8) {
-            if (VT > 0) {
+        int j = 0;
+        for (; j + 4 <= vtaps; j += 4) {
+            OTT_UNROLL
+            for (int u = 0; u < 4; ++u) {
+                const int cj = cf[j + u];
+                uint32_t ww[NW];
+                load_words<NW>(m + (j + u) * step_words, ww);
                 OTT_UNROLL
-                for (int j = 0; j < (VT > 0 ? VT : 1); ++j) {
-                    const int cj = cf[j];
-                    uint32_t ww[NW];
-                    load_words<NW>(m + j * step_words, ww);
-                    OTT_UNROLL
-                    for (int k = 0; k < NW; ++k) {
-                        a[2 * k] += (sx_lo(ww[k]) * cj) >> 16;
-                        a[2 * k + 1] += (sx_hi(ww[k]) * cj) >> 16;
-                    }
-                }
-            } else {
-                for (int j = 0; j < n; ++j) {
-                    const int cj = cf[j];
-                    uint32_t ww[NW];
-                    load_words<NW>(m + j * step_words, ww);
-                    OTT_UNROLL
-                    for (int k = 0; k < NW; ++k) {
-                        a[2 * k] += (sx_lo(ww[k]) * cj) >> 16;
-                        a[2 * k + 1] += (sx_hi(ww[k]) * cj) >> 16;
-                    }
+                for (int k = 0; k < NW; ++k) {
+                    a[2 * k] += (sx_lo(ww[k]) * cj) >> 16;
+                    a[2 * k + 1] += (sx_hi(ww[k]) * cj) >> 16;
                 }
             }
-            OTT_UNROLL
-            for (int k = 0; k < 2 * NW; ++k) a[k] = ott_clip((int)(int16_t)a[k] >> 3, 255);   // paddw wraparound, psraw 3, packuswb
-        } else {
-            if (VT > 0) {
-                OTT_UNROLL
-                for (int j = 0; j < (VT > 0 ? VT : 1); ++j) {
-                    const int cj = cf[j];
-                    uint32_t ww[NW];
-                    load_words<NW>(m + j * step_words, ww);
-                    OTT_UNROLL
-                    for (int k = 0; k < NW; ++k) {
-                        a[2 * k] += sx_lo(ww[k]) * cj;
-                        a[2 * k + 1] += sx_hi(ww[k]) * cj;
-                    }
-                }
-            } else {
-                for (int j = 0; j < n; ++j) {
-                    const int cj = cf[j];
-                    uint32_t ww[NW];
-                    load_words<NW>(m + j * step_words, ww);
-                    OTT_UNROLL
-                    for (int k = 0; k < NW; ++k) {
-                        a[2 * k] += sx_lo(ww[k]) * cj;
-                        a[2 * k + 1] += sx_hi(ww[k]) * cj;
-                    }
-                }
-            }
-            OTT_UNROLL
-            for (int k = 0; k < 2 * NW; ++k) a[k] = mode == VM_EXACT8 ? ott_clip(a[k] >> 19, 255) : ott_clip(a[k] >> 17, 1023);
         }
+        for (; j < vtaps; ++j) {
+            const int cj = cf[j];
+            uint32_t ww[NW];
+            load_words<NW>(m + j * step_words, ww);
+            OTT_UNROLL
+            for (int k = 0; k < NW; ++k) {
+                a[2 * k] += (sx_lo(ww[k]) * cj) >> 16;
+                a[2 * k + 1] += (sx_hi(ww[k]) * cj) >> 16;
+            }
+        }
+        OTT_UNROLL
+        for (int k = 0; k < 2 * NW; ++k) a[k] = ott_clip((int)(int16_t)a[k] >> 3, 255);   // paddw wraparound, psraw 3, packuswb
+    } else {
+        const int init = mode == VM_EXACT8 ? 64 << 12 : 1 << 16;
+        OTT_UNROLL
+        for (int k = 0; k < 2 * NW; ++k) a[k] = init;
+        int j = 0;
+        for (; j + 4 <= vtaps; j += 4) {
+            OTT_UNROLL
+            for (int u = 0; u < 4; ++u) {
+                const int cj = cf[j + u];
+                uint32_t ww[NW];
+                load_words<NW>(m + (j + u) * step_words, ww);
+                OTT_UNROLL
+                for (int k = 0; k < NW; ++k) {
+                    a[2 * k] += sx_lo(ww[k]) * cj;
+                    a[2 * k + 1] += sx_hi(ww[k]) * cj;
+                }
+            }
+        }
+        for (; j < vtaps; ++j) {
+            const int cj = cf[j];
+            uint32_t ww[NW];
+            load_words<NW>(m + j * step_words, ww);
+            OTT_UNROLL
+            for (int k = 0; k < NW; ++k) {
+                a[2 * k] += sx_lo(ww[k]) * cj;
+                a[2 * k + 1] += sx_hi(ww[k]) * cj;
+            }
+        }
+        OTT_UNROLL
+        for (int k = 0; k < 2 * NW; ++k) a[k] = mode == VM_EXACT8 ? ott_clip(a[k] >> 19, 255) : ott_clip(a[k] >> 17, 1023);
     }
     if (BPS == 1) {
         OTT_UNROLL
@@ -535,7 +536,7 @@ OTT_DEV void zip16(uint32_t u, uint32_t v, uint32_t &lo, uint32_t &hi)
     hi = (u >> 16) | (v & 0xffff0000u);
 }
 
-template <int CPT, int VT, int BPS>
+template <int CPT, int BPS>
 OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
 {
     constexpr int NW = CPT / 2;                                 // shared words per tap
@@ -565,13 +566,13 @@ OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
         if (BPS == 1) mode = vtaps == 1 ? VM_ONE8 : ((approx && gy < exact_from) ? VM_APPROX8 : VM_EXACT8);
         else mode = vtaps == 1 ? VM_ONE10 : VM_EXACT10;
         uint32_t o0[NO];
-        vcolumns<NW, VT, BPS>(reinterpret_cast<const uint32_t *>(mid_s + r0 * mid_pitch + x), step_words, cf, vtaps, mode, shift, o0);
+        vcolumns<NW, BPS>(reinterpret_cast<const uint32_t *>(mid_s + r0 * mid_pitch + x), step_words, cf, vtaps, mode, shift, o0);
         if (nplanes == 1) {
             store_words<S, NO>(dst0 + (size_t)gy * dpitch0, gx, o0, dstW);
             continue;
         }
         uint32_t o1[NO];
-        vcolumns<NW, VT, BPS>(reinterpret_cast<const uint32_t *>(mid_s + (sr + r0) * mid_pitch + x), step_words, cf, vtaps, mode, shift, o1);
+        vcolumns<NW, BPS>(reinterpret_cast<const uint32_t *>(mid_s + (sr + r0) * mid_pitch + x), step_words, cf, vtaps, mode, shift, o1);
         if (il) {
             uint32_t z[2 * NO];
             OTT_UNROLL
@@ -587,30 +588,14 @@ OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
     }
 }
 
-template <int CPT, int BPS>
-OTT_DEV void vpass_dispatch(int tid, const TileGeom &g, unsigned char *smem)
-{
-    switch (g.T->vtaps) {
-    case 2: vpass<CPT, 2, BPS>(tid, g, smem); break;
-    case 4: vpass<CPT, 4, BPS>(tid, g, smem); break;
-    case 6: vpass<CPT, 6, BPS>(tid, g, smem); break;
-    case 8: vpass<CPT, 8, BPS>(tid, g, smem); break;
-    case 10: vpass<CPT, 10, BPS>(tid, g, smem); break;
-    case 12: vpass<CPT, 12, BPS>(tid, g, smem); break;
-    case 16: vpass<CPT, 16, BPS>(tid, g, smem); break;
-    case 20: vpass<CPT, 20, BPS>(tid, g, smem); break;
-    default: vpass<CPT, 0, BPS>(tid, g, smem); break;
-    }
-}
-
 OTT_DEV void phase_vpass(int tid, const TileGeom &g, unsigned char *smem)
 {
     if (g.bps == 1) {
-        if (g.tw_log2 == 6) vpass_dispatch<8, 1>(tid, g, smem);
-        else vpass_dispatch<4, 1>(tid, g, smem);
+        if (g.tw_log2 == 6) vpass<8, 1>(tid, g, smem);
+        else vpass<4, 1>(tid, g, smem);
     } else {
-        if (g.tw_log2 == 6) vpass_dispatch<8, 2>(tid, g, smem);
-        else vpass_dispatch<4, 2>(tid, g, smem);
+        if (g.tw_log2 == 6) vpass<8, 2>(tid, g, smem);
+        else vpass<4, 2>(tid, g, smem);
     }
 }
 
