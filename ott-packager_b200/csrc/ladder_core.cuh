@@ -427,10 +427,11 @@ OTT_DEV void vcolumns(const uint32_t *m, int step_words, const int16_t *cf, int 
         OTT_UNROLL
         for (int k = 0; k < 2 * NW; ++k) a[k] = init;
         int j = 0;
-        for (; j + 4 <= vtaps; j += 4) {
+        for (; j + 2 <= vtaps; j += 2) {                   // x86 tap counts are even (filterAlign 2): no tail in practice
+            const uint32_t c2 = *reinterpret_cast<const uint32_t *>(cf + j);
             OTT_UNROLL
-            for (int u = 0; u < 4; ++u) {
-                const int cj = cf[j + u];
+            for (int u = 0; u < 2; ++u) {
+                const int cj = u ? sx_hi(c2) : sx_lo(c2);
                 uint32_t ww[NW];
                 load_words<NW>(m + (j + u) * step_words, ww);
                 OTT_UNROLL
@@ -457,9 +458,9 @@ OTT_DEV void vcolumns(const uint32_t *m, int step_words, const int16_t *cf, int 
         OTT_UNROLL
         for (int k = 0; k < 2 * NW; ++k) a[k] = init;
         int j = 0;
-        for (; j + 4 <= vtaps; j += 4) {
+        for (; j + 2 <= vtaps; j += 2) {
             OTT_UNROLL
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 2; ++u) {
                 const int cj = cf[j + u];
                 uint32_t ww[NW];
                 load_words<NW>(m + (j + u) * step_words, ww);
@@ -549,7 +550,7 @@ OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
     const int vtaps = T.vtaps, exact_from = T.exact_from, dstW = T.dstW;
     uint8_t *const dst0 = g.dst0, *const dst1 = g.dst1;
     const int dpitch0 = g.dst_pitch0, dpitch1 = g.dst_pitch1;
-    const int lpr_log2 = tw_log2 - (CPT == 8 ? 3 : 2);          // lanes per output row: tw / CPT
+    const int lpr_log2 = tw_log2 - (CPT == 8 ? 3 : 2);          // lanes per output row: tw / CPT (tw 64|32, CPT 8|4)
     const int lx = tid & ((1 << lpr_log2) - 1), ry = tid >> lpr_log2, rows_per_pass = kThreads >> lpr_log2;
     const int x = CPT * lx;
     if (x >= tile_w) return;
@@ -588,13 +589,16 @@ OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
     }
 }
 
+// Columns per thread: as many as keep every thread busy -- a sweep covers 256*CPT/tw output rows, so short tiles
+// (steep downscales, thumbnails) use narrower threads.
 OTT_DEV void phase_vpass(int tid, const TileGeom &g, unsigned char *smem)
 {
+    const bool wide = g.th * g.tw >= (kThreads * 8) / 2 + 1;      // more than half a sweep of 8-column threads
     if (g.bps == 1) {
-        if (g.tw_log2 == 6) vpass<8, 1>(tid, g, smem);
+        if (g.tw_log2 == 6 && wide) vpass<8, 1>(tid, g, smem);
         else vpass<4, 1>(tid, g, smem);
     } else {
-        if (g.tw_log2 == 6) vpass<8, 2>(tid, g, smem);
+        if (g.tw_log2 == 6 && wide) vpass<8, 2>(tid, g, smem);
         else vpass<4, 2>(tid, g, smem);
     }
 }
