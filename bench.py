@@ -329,6 +329,8 @@ def ours_main(args, wl, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize()
 
+    yadif_ms = [0.0, 0]
+
     def timed_region(b, ios, steps, warmup):
         launches = [0]
         with torch.cuda.stream(stream):
@@ -352,11 +354,13 @@ def ours_main(args, wl, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         kms, kn = b.timing_read()
+        yadif_ms[0], yadif_ms[1] = b.timing_read_yadif()
         b.timing(False)
         return ms, launches[0], kms, kn, thumbs
 
     ios = [build_io(p) for p in range(RING)]
     ms, launches, kms, kn, _ = timed_region(batch, ios, args.steps, max(args.warmup, 3))
+    yadif_stat = list(yadif_ms)
     frames_per_step = Cn
     value = world * frames_per_step * args.steps / (ms / 1000.0)
 
@@ -434,6 +438,7 @@ def ours_main(args, wl, rank, world, local_rank):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg, s_in, s_out = algorithmic_bytes(wl)
     k_bytes = ladder_kernel_bytes(wl) * frames_per_step
     k_ms = kms / max(kn, 1)
     achieved = k_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
@@ -445,7 +450,11 @@ def ours_main(args, wl, rank, world, local_rank):
     roofline = {"bound": "hbm", "kernel": "ladder_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
                 "bytes_per_launch": k_bytes, "ms_per_launch": k_ms, "launches_timed": kn}
-    alg, s_in, s_out = algorithmic_bytes(wl)
+    if yadif_stat[1]:
+        y_ms = yadif_stat[0] / yadif_stat[1]
+        y_bytes = 3.5 * s_in * frames_per_step              # yadif reads 2.5*S and writes S per frame
+        roofline["yadif_kernel"] = {"ms_per_launch": y_ms, "bytes_per_launch": y_bytes,
+                                    "achieved": y_bytes / (y_ms * 1e-3) / 1e9, "frac": y_bytes / (y_ms * 1e-3) / 1e9 / peak}
     # ---------------- CPU baseline (rank 0, N=1 only), bounded sample
     cpu = None
     if world == 1 and not args.no_cpu:

@@ -142,6 +142,7 @@ int  ottgpu_batch_last_items(const ottgpu_batch *b);
  * enable != 0 starts/reset accumulation; read (after ottgpu_batch_wait) returns the summed milliseconds and count. */
 int  ottgpu_batch_timing(ottgpu_batch *b, int enable);
 int  ottgpu_batch_timing_read(ottgpu_batch *b, double *ms_sum, int *launches);
+int  ottgpu_batch_timing_read_yadif(ottgpu_batch *b, double *ms_sum, int *launches);   /* same for the yadif launches */
 
 /* --- pools: the mempool.h discipline (memory_create / memory_take / memory_return / memory_unused,
  *     include/mempool.h:30-35, source/mempool.c:82-265) for device surfaces and pinned host frames ------------------ */

@@ -73,6 +73,7 @@ _SIGS = {
     "ottgpu_batch_last_items": (C.c_int, [C.c_void_p]),
     "ottgpu_batch_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "ottgpu_batch_timing_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "ottgpu_batch_timing_read_yadif": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "ottgpu_pool_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]),
     "ottgpu_pool_take": (C.c_void_p, [C.c_void_p]),
     "ottgpu_pool_return": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -297,6 +298,11 @@ class Batch:
     def timing_read(self):
         ms, n = C.c_double(), C.c_int()
         self.lib.check(self.lib.dll.ottgpu_batch_timing_read(self.handle, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def timing_read_yadif(self):
+        ms, n = C.c_double(), C.c_int()
+        self.lib.check(self.lib.dll.ottgpu_batch_timing_read_yadif(self.handle, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
     @property

@@ -163,7 +163,9 @@ __global__ void __launch_bounds__(256) yadif_kernel(const YadifJob *__restrict__
 {
     const YadifJob &j = jobs[blockIdx.z];
     if (!j.active) return;
-    yadif_position(j, blockIdx.x * 32 + (threadIdx.x & 31), blockIdx.y * 8 + (threadIdx.x >> 5));
+    const int gx = blockIdx.x * 32 + (threadIdx.x & 31), gy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (j.fast) yadif_position_fast(j, gx, gy);          // gx counts 4-sample words; rows cover luma then chroma
+    else yadif_position(j, gx, gy);
 }
 
 cudaError_t configure_kernels()
@@ -201,7 +203,8 @@ cudaError_t launch_ladder(LadderLaunch L, cudaStream_t s)
 cudaError_t launch_yadif(const YadifJob *jobs, int n_jobs, int max_w, int max_h, cudaStream_t s)
 {
     if (n_jobs <= 0) return cudaSuccess;
-    dim3 grid((max_w + 31) / 32, (max_h + 7) / 8, n_jobs);
+    // fast jobs need (w/4) x (h + h/2) positions, slow ones w x h: launch the union (extra CTAs exit at once)
+    dim3 grid((max_w + 31) / 32, ((max_h + (max_h + 1) / 2) + 7) / 8, n_jobs);
     yadif_kernel<<<grid, 256, 0, s>>>(jobs);
     return cudaGetLastError();
 }

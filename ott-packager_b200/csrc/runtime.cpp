@@ -142,14 +142,14 @@ struct ottgpu_batch {
         YadifJob *h_jobs = nullptr, *d_jobs = nullptr;
         Item *h_thumb_items = nullptr, *d_thumb_items = nullptr;
         int *d_counters = nullptr;                          // [0] rung launch, [1] thumbnail launch tile schedulers
-        cudaEvent_t done = nullptr, k0 = nullptr, k1 = nullptr;
-        bool in_flight = false, timed = false;
+        cudaEvent_t done = nullptr, k0 = nullptr, k1 = nullptr, y0 = nullptr, y1 = nullptr;
+        bool in_flight = false, timed = false, timed_yadif = false;
     } set[2];
     int turn = 0;
     int last_launches = 0, last_items = 0;
     bool timing = false;
-    double ms_sum = 0.0;
-    int ms_count = 0;
+    double ms_sum = 0.0, yadif_ms_sum = 0.0;
+    int ms_count = 0, yadif_ms_count = 0;
     struct Readback { void *host; const uint8_t *dev; size_t bytes; };
     std::vector<Readback> readbacks;
 };
@@ -471,6 +471,8 @@ int ottgpu_batch_create(ottgpu_channel **channels, int n, ottgpu_batch **out)
         CK(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
         CK(cudaEventCreate(&st.k0));
         CK(cudaEventCreate(&st.k1));
+        CK(cudaEventCreate(&st.y0));
+        CK(cudaEventCreate(&st.y1));
     }
     *out = b.release();
     return OTTGPU_OK;
@@ -493,6 +495,8 @@ void ottgpu_batch_destroy(ottgpu_batch *b)
         if (st.done) cudaEventDestroy(st.done);
         if (st.k0) cudaEventDestroy(st.k0);
         if (st.k1) cudaEventDestroy(st.k1);
+        if (st.y0) cudaEventDestroy(st.y0);
+        if (st.y1) cudaEventDestroy(st.y1);
     }
     delete b;
 }
@@ -514,6 +518,13 @@ int retire(ottgpu_batch *b, ottgpu_batch::Set &st)
         b->ms_sum += ms;
         b->ms_count++;
         st.timed = false;
+    }
+    if (st.timed_yadif) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, st.y0, st.y1));
+        b->yadif_ms_sum += ms;
+        b->yadif_ms_count++;
+        st.timed_yadif = false;
     }
     st.in_flight = false;
     return OTTGPU_OK;
@@ -540,8 +551,8 @@ int ottgpu_batch_timing(ottgpu_batch *b, int enable)
     int rc = ottgpu_batch_wait(b);
     if (rc) return rc;
     b->timing = enable != 0;
-    b->ms_sum = 0.0;
-    b->ms_count = 0;
+    b->ms_sum = b->yadif_ms_sum = 0.0;
+    b->ms_count = b->yadif_ms_count = 0;
     return OTTGPU_OK;
 }
 
@@ -550,6 +561,14 @@ int ottgpu_batch_timing_read(ottgpu_batch *b, double *ms_sum, int *launches)
     if (!b || !ms_sum || !launches) return fail(OTTGPU_ERR_ARG, "null argument");
     *ms_sum = b->ms_sum;
     *launches = b->ms_count;
+    return OTTGPU_OK;
+}
+
+int ottgpu_batch_timing_read_yadif(ottgpu_batch *b, double *ms_sum, int *launches)
+{
+    if (!b || !ms_sum || !launches) return fail(OTTGPU_ERR_ARG, "null argument");
+    *ms_sum = b->yadif_ms_sum;
+    *launches = b->yadif_ms_count;
     return OTTGPU_OK;
 }
 
@@ -671,6 +690,7 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
             job.tff = target.interlaced ? target.tff : 1;
             job.parity = job.tff ^ 1;
             job.active = 1;
+            job.fast = job.bps == 1 && cfg.src_width % 8 == 0 && (((uintptr_t)job.prev | (uintptr_t)job.cur | (uintptr_t)job.next | (uintptr_t)job.dst) & 3) == 0;
             n_jobs++;
             max_w = std::max(max_w, cfg.src_width);
             max_h = std::max(max_h, cfg.src_height);
@@ -713,7 +733,12 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
     CK(cudaMemcpyAsync(st.d_binds, st.h_binds, n * sizeof(Binding), cudaMemcpyHostToDevice, s));
     if (n_jobs) {
         CK(cudaMemcpyAsync(st.d_jobs, st.h_jobs, n * sizeof(YadifJob), cudaMemcpyHostToDevice, s));
+        if (b->timing) CK(cudaEventRecord(st.y0, s));
         CK(launch_yadif(st.d_jobs, n, max_w, max_h, s));
+        if (b->timing) {
+            CK(cudaEventRecord(st.y1, s));
+            st.timed_yadif = true;
+        }
         b->last_launches++;
     }
     auto make_launch = [&](const Item *items, int count, int which) {
@@ -899,6 +924,7 @@ int ottgpu_yadif_frame(int gpu, const void *prev, const void *cur, const void *n
     j.tff = interlaced ? (tff != 0) : 1;
     j.parity = j.tff ^ 1;
     j.active = 1;
+    j.fast = j.bps == 1 && width % 8 == 0;
     cudaError_t e = cudaMemcpy(d, prev, bytes, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d + step, cur, bytes, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d + 2 * step, next, bytes, cudaMemcpyHostToDevice);

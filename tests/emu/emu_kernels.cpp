@@ -54,8 +54,11 @@ cudaError_t launch_yadif(const YadifJob *jobs, int n_jobs, int max_w, int max_h,
 {
     for (int z = 0; z < n_jobs; ++z) {
         if (!jobs[z].active) continue;
-        for (int y = 0; y < (max_h + 7) / 8 * 8; ++y)
-            for (int x = 0; x < (max_w + 31) / 32 * 32; ++x) yadif_position(jobs[z], x, y);
+        for (int y = 0; y < ((max_h + (max_h + 1) / 2) + 7) / 8 * 8; ++y)
+            for (int x = 0; x < (max_w + 31) / 32 * 32; ++x) {
+                if (jobs[z].fast) yadif_position_fast(jobs[z], x, y);
+                else yadif_position(jobs[z], x, y);
+            }
     }
     return cudaSuccess;
 }

@@ -8,7 +8,7 @@ import pytest
 from conftest import noise_i420, noise_p010, natural_i420, interlaced_sequence, split_i420
 
 
-@pytest.mark.parametrize("size", [(64, 48), (130, 74), (854, 480), (36, 22)])
+@pytest.mark.parametrize("size", [(64, 48), (130, 74), (854, 480), (36, 22), (320, 182), (328, 46)])
 @pytest.mark.parametrize("tff", [1, 0])
 def test_yadif_frame_vs_oracle(lib, og, oracle, size, tff):
     w, h = size
@@ -18,6 +18,15 @@ def test_yadif_frame_vs_oracle(lib, og, oracle, size, tff):
     n = [noise_i420(w, h, s) for s in (1, 2, 3)]
     got = lib.yadif_frame(n[0], n[1], n[2], og.FMT_I420, w, h, 1, tff)
     assert np.array_equal(got, oracle.yadif_frame(n[0], n[1], n[2], w, h, 1, tff))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tff", [1, 0])
+def test_yadif_full_size_1080i(real_lib, og, oracle, tff):
+    w, h = 1920, 1080
+    fr = interlaced_sequence(w, h, 3, seed=11, tff=bool(tff))
+    got = real_lib.yadif_frame(fr[0], fr[1], fr[2], og.FMT_I420, w, h, 1, tff)
+    assert np.array_equal(got, oracle.yadif_frame(fr[0], fr[1], fr[2], w, h, 1, tff))
 
 
 def test_yadif_frame_16bit(lib, og, oracle):
