@@ -99,7 +99,7 @@ struct YadifJob {
     int width, height, bps;
     int parity, tff;                    // as resolved by yadif: parity = tff ^ 1 for mode 0
     int active;
-    int fast;                           // 8-bit, width % 8 == 0, 4-byte aligned frames: four samples per thread
+    int fast;                           // 8-bit, width % 16 == 0, 8-byte aligned frames: eight samples per thread
 };
 
 }  // namespace ottgpu

@@ -15,7 +15,8 @@ size_t ladder_smem_bytes(int src_max, int mid_max, int vc_max, int *double_buffe
 cudaError_t launch_ladder(LadderLaunch L, cudaStream_t s);
 
 // yadif: one launch over all jobs (blockIdx.z = job).
-cudaError_t launch_yadif(const YadifJob *jobs, int n_jobs, int max_w, int max_h, cudaStream_t s);
+// all_fast: every job takes the 8-samples-per-thread path, so the grid only spans (w/8) x (h + h/2) positions
+cudaError_t launch_yadif(const YadifJob *jobs, int n_jobs, int max_w, int max_h, bool all_fast, cudaStream_t s);
 
 cudaError_t configure_kernels();
 

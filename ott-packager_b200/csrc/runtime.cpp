@@ -585,6 +585,7 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
     const int n = (int)b->ch.size();
     cudaStream_t s = b->stream;
     int n_jobs = 0, n_thumb_items = 0, max_w = 0, max_h = 0, live = 0;
+    bool all_fast = true;
     b->readbacks.clear();
     b->last_launches = b->last_items = 0;
 
@@ -690,7 +691,10 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
             job.tff = target.interlaced ? target.tff : 1;
             job.parity = job.tff ^ 1;
             job.active = 1;
-            job.fast = job.bps == 1 && cfg.src_width % 8 == 0 && (((uintptr_t)job.prev | (uintptr_t)job.cur | (uintptr_t)job.next | (uintptr_t)job.dst) & 3) == 0;
+            job.fast = job.bps == 1 && cfg.src_width % 16 == 0 && (cfg.src_width * cfg.src_height) % 8 == 0 &&
+                       (((cfg.src_width / 2) * ((cfg.src_height + 1) / 2)) % 8) == 0 &&
+                       (((uintptr_t)job.prev | (uintptr_t)job.cur | (uintptr_t)job.next | (uintptr_t)job.dst) & 7) == 0;
+            all_fast = all_fast && job.fast;
             n_jobs++;
             max_w = std::max(max_w, cfg.src_width);
             max_h = std::max(max_h, cfg.src_height);
@@ -734,7 +738,7 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
     if (n_jobs) {
         CK(cudaMemcpyAsync(st.d_jobs, st.h_jobs, n * sizeof(YadifJob), cudaMemcpyHostToDevice, s));
         if (b->timing) CK(cudaEventRecord(st.y0, s));
-        CK(launch_yadif(st.d_jobs, n, max_w, max_h, s));
+        CK(launch_yadif(st.d_jobs, n, max_w, max_h, all_fast, s));
         if (b->timing) {
             CK(cudaEventRecord(st.y1, s));
             st.timed_yadif = true;
@@ -924,12 +928,12 @@ int ottgpu_yadif_frame(int gpu, const void *prev, const void *cur, const void *n
     j.tff = interlaced ? (tff != 0) : 1;
     j.parity = j.tff ^ 1;
     j.active = 1;
-    j.fast = j.bps == 1 && width % 8 == 0;
+    j.fast = j.bps == 1 && width % 16 == 0 && (width * height) % 8 == 0 && ((width / 2) * ((height + 1) / 2)) % 8 == 0;
     cudaError_t e = cudaMemcpy(d, prev, bytes, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d + step, cur, bytes, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d + 2 * step, next, bytes, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(dj, &j, sizeof(j), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = launch_yadif(dj, 1, width, height, 0);
+    if (e == cudaSuccess) e = launch_yadif(dj, 1, width, height, j.fast != 0, 0);
     if (e == cudaSuccess) e = cudaMemcpy(dst, d + 3 * step, bytes, cudaMemcpyDeviceToHost);
     cudaFree(d);
     cudaFree(dj);

@@ -78,89 +78,101 @@ OTT_DEV void yadif_position(const YadifJob &j, int x, int y)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Fast path (8-bit, plane widths multiples of 4, 4-byte aligned frames): one thread = 4 adjacent samples.  Every
-// neighbour row is fetched as aligned 32-bit words (3 words of `cur` above and below cover the +-3 sample search
-// window of all four samples) instead of ~35 byte loads per sample.
+// Fast path (8-bit, plane widths multiples of 8, 4-byte aligned frames): one thread = 8 adjacent samples (two 32-bit
+// words).  Every neighbour row is fetched as aligned words (4 words of `cur` above and below cover the +-3 sample search
+// window of all eight samples) and the per-sample predictor is branch-free: |a-b|+c is one VABSDIFF, the nested
+// direction search of filter_line_c becomes predicated selects.
 OTT_DEV int ybyte(uint32_t w, int i) { return (int)((w >> (8 * i)) & 0xffu); }
 
-OTT_DEV void yadif_quad8(const YadifJob &j, size_t off, int w, int h, int x4, int y)
+OTT_DEV void yadif_oct8(const YadifJob &j, size_t off, int w, int h, int x8, int y)
 {
     const uint32_t *prev = reinterpret_cast<const uint32_t *>(j.prev + off), *cur = reinterpret_cast<const uint32_t *>(j.cur + off);
     const uint32_t *next = reinterpret_cast<const uint32_t *>(j.next + off);
     uint32_t *dst = reinterpret_cast<uint32_t *>(j.dst + off);
     const int wq = w >> 2;                                 // words per row
-    const int i0 = y * wq + x4;
-    if (!((y ^ j.parity) & 1)) { dst[i0] = ott_ldg(cur + i0); return; }
+    const int i0 = y * wq + 2 * x8;
+    if (!((y ^ j.parity) & 1)) {
+        const uint2 v = ott_ldg(reinterpret_cast<const uint2 *>(cur + i0));
+        *reinterpret_cast<uint2 *>(dst + i0) = v;
+        return;
+    }
     const int dn = y + 1 < h ? wq : -wq, up = y ? -wq : wq;
     const bool first_field = (j.parity ^ j.tff) != 0;
     const uint32_t *p2 = first_field ? prev : cur, *n2 = first_field ? cur : next;
     const bool spatial = !(y == 1 || y + 2 == h);
-    const int xl = x4 > 0 ? -1 : 0, xr = x4 + 1 < wq ? 1 : 0;   // clamped neighbour words (values unused at the edges)
-    const uint32_t cuw[3] = {ott_ldg(cur + i0 + up + xl), ott_ldg(cur + i0 + up), ott_ldg(cur + i0 + up + xr)};
-    const uint32_t cdw[3] = {ott_ldg(cur + i0 + dn + xl), ott_ldg(cur + i0 + dn), ott_ldg(cur + i0 + dn + xr)};
-    const uint32_t pu = ott_ldg(prev + i0 + up), pd = ott_ldg(prev + i0 + dn);
-    const uint32_t nu = ott_ldg(next + i0 + up), nd = ott_ldg(next + i0 + dn);
-    const uint32_t p20 = ott_ldg(p2 + i0), n20 = ott_ldg(n2 + i0);
-    uint32_t p2u = 0, n2u = 0, p2d = 0, n2d = 0;
+    const int xl = x8 > 0 ? -1 : 0, xr = 2 * x8 + 2 < wq ? 2 : 1;   // clamped neighbour words (values unused at the edges)
+    const uint2 cum = ott_ldg(reinterpret_cast<const uint2 *>(cur + i0 + up)), cdm = ott_ldg(reinterpret_cast<const uint2 *>(cur + i0 + dn));
+    const uint32_t cuw[4] = {ott_ldg(cur + i0 + up + xl), cum.x, cum.y, ott_ldg(cur + i0 + up + xr)};
+    const uint32_t cdw[4] = {ott_ldg(cur + i0 + dn + xl), cdm.x, cdm.y, ott_ldg(cur + i0 + dn + xr)};
+    const uint2 pu = ott_ldg(reinterpret_cast<const uint2 *>(prev + i0 + up)), pd = ott_ldg(reinterpret_cast<const uint2 *>(prev + i0 + dn));
+    const uint2 nu = ott_ldg(reinterpret_cast<const uint2 *>(next + i0 + up)), nd = ott_ldg(reinterpret_cast<const uint2 *>(next + i0 + dn));
+    const uint2 p20 = ott_ldg(reinterpret_cast<const uint2 *>(p2 + i0)), n20 = ott_ldg(reinterpret_cast<const uint2 *>(n2 + i0));
+    uint2 p2u, n2u, p2d, n2d;
+    p2u.x = p2u.y = n2u.x = n2u.y = p2d.x = p2d.y = n2d.x = n2d.y = 0;
     if (spatial) {
-        p2u = ott_ldg(p2 + i0 + 2 * up); n2u = ott_ldg(n2 + i0 + 2 * up);
-        p2d = ott_ldg(p2 + i0 + 2 * dn); n2d = ott_ldg(n2 + i0 + 2 * dn);
+        p2u = ott_ldg(reinterpret_cast<const uint2 *>(p2 + i0 + 2 * up)); n2u = ott_ldg(reinterpret_cast<const uint2 *>(n2 + i0 + 2 * up));
+        p2d = ott_ldg(reinterpret_cast<const uint2 *>(p2 + i0 + 2 * dn)); n2d = ott_ldg(reinterpret_cast<const uint2 *>(n2 + i0 + 2 * dn));
     }
-    int cu[12], cd[12];
+    int cu[16], cd[16];                                    // samples 8*x8-4 .. 8*x8+11 of the rows above / below
     OTT_UNROLL
-    for (int k = 0; k < 12; ++k) { cu[k] = ybyte(cuw[k >> 2], k & 3); cd[k] = ybyte(cdw[k >> 2], k & 3); }
-    uint32_t out = 0;
+    for (int k = 0; k < 16; ++k) { cu[k] = ybyte(cuw[k >> 2], k & 3); cd[k] = ybyte(cdw[k >> 2], k & 3); }
+    uint32_t outw[2] = {0, 0};
     OTT_UNROLL
-    for (int i = 0; i < 4; ++i) {
-        const int x = 4 * x4 + i, q = i + 4;               // q indexes cu/cd
+    for (int i = 0; i < 8; ++i) {
+        const int x = 8 * x8 + i, q = i + 4, b4 = i & 3;
         const int c = cu[q], e = cd[q];
-        const int a0 = ybyte(p20, i), b0 = ybyte(n20, i);
+        const int a0 = ybyte(i < 4 ? p20.x : p20.y, b4), b0 = ybyte(i < 4 ? n20.x : n20.y, b4);
         const int d = (a0 + b0) >> 1;
-        const int td0 = ott_abs(a0 - b0);
-        const int td1 = (ott_abs(ybyte(pu, i) - c) + ott_abs(ybyte(pd, i) - e)) >> 1;
-        const int td2 = (ott_abs(ybyte(nu, i) - c) + ott_abs(ybyte(nd, i) - e)) >> 1;
+        const int td0 = ott_sad(a0, b0, 0);
+        const int td1 = ott_sad(ybyte(i < 4 ? pd.x : pd.y, b4), e, ott_sad(ybyte(i < 4 ? pu.x : pu.y, b4), c, 0)) >> 1;
+        const int td2 = ott_sad(ybyte(i < 4 ? nd.x : nd.y, b4), e, ott_sad(ybyte(i < 4 ? nu.x : nu.y, b4), c, 0)) >> 1;
         int diff = ott_max(ott_max(td0 >> 1, td1), td2);
         int pred = (c + e) >> 1;
-        if (x >= 3 && x < w - 3) {
-            int score = ott_abs(cu[q - 1] - cd[q - 1]) + ott_abs(c - e) + ott_abs(cu[q + 1] - cd[q + 1]) - 1;
-            int sc = ott_abs(cu[q - 2] - e) + ott_abs(cu[q - 1] - cd[q + 1]) + ott_abs(c - cd[q + 2]);                  // j = -1
-            if (sc < score) {
-                score = sc; pred = (cu[q - 1] + cd[q + 1]) >> 1;
-                sc = ott_abs(cu[q - 3] - cd[q + 1]) + ott_abs(cu[q - 2] - cd[q + 2]) + ott_abs(cu[q - 1] - cd[q + 3]);  // j = -2
-                if (sc < score) { score = sc; pred = (cu[q - 2] + cd[q + 2]) >> 1; }
-            }
-            sc = ott_abs(c - cd[q - 2]) + ott_abs(cu[q + 1] - cd[q - 1]) + ott_abs(cu[q + 2] - e);                     // j = +1
-            if (sc < score) {
-                score = sc; pred = (cu[q + 1] + cd[q - 1]) >> 1;
-                sc = ott_abs(cu[q + 1] - cd[q - 3]) + ott_abs(cu[q + 2] - cd[q - 2]) + ott_abs(cu[q + 3] - cd[q - 1]);  // j = +2
-                if (sc < score) { score = sc; pred = (cu[q + 2] + cd[q - 2]) >> 1; }
-            }
+        {
+            // edge-directed search; vf_yadif only tries +-2 when +-1 improved the score
+            const bool in = x >= 3 && x < w - 3;
+            int score = ott_sad(cu[q + 1], cd[q + 1], ott_sad(c, e, ott_sad(cu[q - 1], cd[q - 1], -1)));
+            const int s1 = ott_sad(c, cd[q + 2], ott_sad(cu[q - 1], cd[q + 1], ott_sad(cu[q - 2], e, 0)));                   // j = -1
+            const int s2 = ott_sad(cu[q - 1], cd[q + 3], ott_sad(cu[q - 2], cd[q + 2], ott_sad(cu[q - 3], cd[q + 1], 0)));  // j = -2
+            const int s3 = ott_sad(cu[q + 2], e, ott_sad(cu[q + 1], cd[q - 1], ott_sad(c, cd[q - 2], 0)));                  // j = +1
+            const int s4 = ott_sad(cu[q + 3], cd[q - 1], ott_sad(cu[q + 2], cd[q - 2], ott_sad(cu[q + 1], cd[q - 3], 0)));  // j = +2
+            const bool c1 = in && s1 < score;
+            score = c1 ? s1 : score; pred = c1 ? (cu[q - 1] + cd[q + 1]) >> 1 : pred;
+            const bool c2 = c1 && s2 < score;
+            score = c2 ? s2 : score; pred = c2 ? (cu[q - 2] + cd[q + 2]) >> 1 : pred;
+            const bool c3 = in && s3 < score;
+            score = c3 ? s3 : score; pred = c3 ? (cu[q + 1] + cd[q - 1]) >> 1 : pred;
+            const bool c4 = c3 && s4 < score;
+            pred = c4 ? (cu[q + 2] + cd[q - 2]) >> 1 : pred;
         }
         if (spatial) {
-            const int b = (ybyte(p2u, i) + ybyte(n2u, i)) >> 1, f = (ybyte(p2d, i) + ybyte(n2d, i)) >> 1;
+            const int b = (ybyte(i < 4 ? p2u.x : p2u.y, b4) + ybyte(i < 4 ? n2u.x : n2u.y, b4)) >> 1;
+            const int f = (ybyte(i < 4 ? p2d.x : p2d.y, b4) + ybyte(i < 4 ? n2d.x : n2d.y, b4)) >> 1;
             const int mx = ott_max(ott_max(d - e, d - c), ott_min(b - c, f - e));
             const int mn = ott_min(ott_min(d - e, d - c), ott_max(b - c, f - e));
             diff = ott_max(ott_max(diff, mn), -mx);
         }
         const int v = ott_min(ott_max(pred, d - diff), d + diff);
-        out |= (uint32_t)v << (8 * i);
+        outw[i >> 2] |= (uint32_t)v << (8 * b4);
     }
-    dst[i0] = out;
+    uint2 o;
+    o.x = outw[0]; o.y = outw[1];
+    *reinterpret_cast<uint2 *>(dst + i0) = o;
 }
 
-// Fast-path thread position: (x4, r) over a grid of (w/4) x (h + ch) words; rows >= h are chroma rows with the U words
-// in the left half and the V words in the right half.
-OTT_DEV void yadif_position_fast(const YadifJob &j, int x4, int r)
+// Fast-path thread position: (x8, r) over a grid of (w/8) x (h + ch) positions; rows >= h are chroma rows with the U
+// samples in the left half and the V samples in the right half.
+OTT_DEV void yadif_position_fast(const YadifJob &j, int x8, int r)
 {
     const int w = j.width, h = j.height, cw = w >> 1, ch = (h + 1) >> 1;
-    if (x4 >= (w >> 2)) return;
-    if (r < h) { yadif_quad8(j, 0, w, h, x4, r); return; }
+    if (x8 >= (w >> 3)) return;
+    if (r < h) { yadif_oct8(j, 0, w, h, x8, r); return; }
     r -= h;
     if (r >= ch) return;
-    const int cq = cw >> 2;
+    const int co = cw >> 3;
     const size_t uo = (size_t)w * h, vo = uo + (size_t)cw * ch;
-    if (x4 < cq) yadif_quad8(j, uo, cw, ch, x4, r);
-    else yadif_quad8(j, vo, cw, ch, x4 - cq, r);
+    if (x8 < co) yadif_oct8(j, uo, cw, ch, x8, r);
+    else yadif_oct8(j, vo, cw, ch, x8 - co, r);
 }
 
 }  // namespace ottgpu

@@ -50,7 +50,7 @@ cudaError_t launch_ladder(LadderLaunch L, cudaStream_t)
     return cudaSuccess;
 }
 
-cudaError_t launch_yadif(const YadifJob *jobs, int n_jobs, int max_w, int max_h, cudaStream_t)
+cudaError_t launch_yadif(const YadifJob *jobs, int n_jobs, int max_w, int max_h, bool, cudaStream_t)
 {
     for (int z = 0; z < n_jobs; ++z) {
         if (!jobs[z].active) continue;
