@@ -5,3 +5,4 @@ Import with importlib.import_module("ott-packager_b200") (the directory name is 
 """
 from .binding import *  # noqa: F401,F403
 from .binding import Library, Channel, Batch, Pool, make_cfg, OttGpuError, EXPORTS, DEFAULT_LIB  # noqa: F401
+from .sharding import shard_channels, my_channels  # noqa: F401

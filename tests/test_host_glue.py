@@ -1,0 +1,240 @@
+"""Host-side C glue (ott-packager_b200/host/transvideo_gpu.c): the thread body that replaces video_prepare_thread +
+video_scale_thread (source/transvideo.c:1896-2429, 1504-1683), driven through the REFERENCE's own dataqueue.c / mempool.c
+(oracle/_ref/libfillet_rt.so, compiled unmodified from /root/reference) so the queue/pool hand-off is the real one.
+Pixels are checked against the CPU oracle.  Tier `emu` runs the kernel source on the CPU, tier `gpu` on the B200."""
+import ctypes as C
+import os
+import subprocess
+import time
+import numpy as np
+import pytest
+from conftest import ROOT, interlaced_sequence, natural_i420
+
+MAXR = 8
+
+
+class Msg(C.Structure):                       # include/dataqueue.h:32-59
+    _fields_ = [("buffer_type", C.c_int), ("buffer_size", C.c_ulong), ("pts", C.c_int64), ("dts", C.c_int64),
+                ("flags", C.c_uint32), ("source_discontinuity", C.c_int), ("tff", C.c_uint8), ("interlaced", C.c_uint8),
+                ("fps_num", C.c_int), ("fps_den", C.c_int), ("aspect_num", C.c_int), ("aspect_den", C.c_int),
+                ("width", C.c_int), ("height", C.c_int), ("stream_index", C.c_uint8), ("channels", C.c_int),
+                ("sample_rate", C.c_int), ("first_pts", C.c_int64), ("caption_size", C.c_int),
+                ("caption_timestamp", C.c_int64), ("splice_point", C.c_int), ("splice_duration", C.c_int64),
+                ("splice_duration_remaining", C.c_int64), ("smallbuf", C.c_char * 256),
+                ("caption_buffer", C.c_void_p), ("buffer", C.c_void_p)]
+
+
+SIGNAL_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_char_p)
+
+
+class TV(C.Structure):                        # ott-packager_b200/host/transvideo_gpu.h
+    _fields_ = [("prepare_queue", C.c_void_p), ("encode_queue", C.c_void_p * MAXR), ("thumbnail_queue", C.c_void_p),
+                ("raw_video_pool", C.c_void_p), ("msg_pool", C.c_void_p), ("num_outputs", C.c_int),
+                ("out_width", C.c_int * MAXR), ("out_height", C.c_int * MAXR), ("gpu", C.c_int),
+                ("first_timestamp", C.POINTER(C.c_int64)), ("running", C.POINTER(C.c_int)), ("out_fmt", C.c_int),
+                ("device_outputs", C.c_int), ("surface_pool", C.c_void_p * MAXR), ("target", C.c_int),
+                ("signal", SIGNAL_FN), ("direct_error", SIGNAL_FN), ("user", C.c_void_p), ("channel", C.c_void_p),
+                ("chan_width", C.c_int), ("chan_height", C.c_int), ("chan_deint", C.c_int),
+                ("deinterlaced_frame_count", C.c_int64), ("av_sync_compromised", C.c_int), ("frames_in", C.c_int64),
+                ("frames_out", C.c_int64), ("thumbnails_out", C.c_int64)]
+
+
+@pytest.fixture(scope="module")
+def rt():
+    """the reference's dataqueue.c + mempool.c, unmodified"""
+    so = os.path.join(ROOT, "oracle", "_ref", "libfillet_rt.so")
+    if not os.path.exists(so):
+        subprocess.call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libfillet_rt.so not built (reference tree absent)")
+    L = C.CDLL(so, mode=C.RTLD_GLOBAL)
+    L.dataqueue_create.restype = C.c_void_p
+    L.dataqueue_take_back.restype = C.POINTER(Msg)
+    L.dataqueue_take_back.argtypes = [C.c_void_p]
+    L.dataqueue_put_front.argtypes = [C.c_void_p, C.POINTER(Msg)]
+    L.dataqueue_get_size.argtypes = [C.c_void_p]
+    L.memory_create.restype = C.c_void_p
+    L.memory_create.argtypes = [C.c_int, C.c_int]
+    L.memory_take.restype = C.c_void_p
+    L.memory_take.argtypes = [C.c_void_p, C.c_int]
+    L.memory_return.argtypes = [C.c_void_p, C.c_void_p]
+    L.memory_unused.argtypes = [C.c_void_p]
+    return L
+
+
+@pytest.fixture()
+def host(lib, rt):
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "ott-packager_b200", "host")])
+    C.CDLL(lib.path, mode=C.RTLD_GLOBAL)          # libottgpu (emulated or real) provides the ottgpu_* symbols
+    H = C.CDLL(os.path.join(ROOT, "ott-packager_b200", "libottgpu_host.so"))
+    H.ottgpu_transvideo_process.argtypes = [C.POINTER(TV), C.POINTER(Msg)]
+    H.ottgpu_video_prepare_scale_thread.argtypes = [C.c_void_p]
+    H.ottgpu_video_prepare_scale_thread.restype = C.c_void_p
+    H.ottgpu_transvideo_close.argtypes = [C.POINTER(TV)]
+    return H
+
+
+def test_message_struct_matches_reference_header():
+    hdr = "/root/reference/include/dataqueue.h"
+    if not os.path.exists(hdr):
+        pytest.skip("reference tree absent")
+    src = r'''
+#include <stdio.h>
+#include <stddef.h>
+#define P(f) printf("%zu ", offsetof(dataqueue_message_struct, f))
+int main(void){ P(buffer_size);P(pts);P(flags);P(tff);P(interlaced);P(fps_num);P(width);P(stream_index);P(first_pts);P(caption_size);
+ P(splice_point);P(splice_duration_remaining);P(smallbuf);P(caption_buffer);P(buffer); printf("%zu\n", sizeof(dataqueue_message_struct)); return 0; }
+'''
+    outs = []
+    for flags in (["-I/root/reference/include", "-include", "dataqueue.h"],
+                  ["-include", os.path.join(ROOT, "ott-packager_b200", "host", "fillet_abi.h")]):
+        exe = "/tmp/ottgpu_abi_check"
+        subprocess.run(["gcc", "-x", "c", "-o", exe] + flags + ["-"], input=src.encode(), check=True)
+        outs.append(subprocess.check_output([exe]).decode())
+    assert outs[0] == outs[1], outs
+    assert C.sizeof(Msg) == int(outs[0].split()[-1]) == 400
+
+
+def _make_tv(rt, w_h_list, errors, signals, first_ts=None):
+    tv = TV()
+    tv.prepare_queue = rt.dataqueue_create()
+    for i in range(len(w_h_list)):
+        tv.encode_queue[i] = rt.dataqueue_create()
+        tv.out_width[i], tv.out_height[i] = w_h_list[i]
+    tv.thumbnail_queue = rt.dataqueue_create()
+    tv.raw_video_pool = rt.memory_create(512, 0)          # fillet.c:355: size 0 => memory_take mallocs the request
+    tv.msg_pool = rt.memory_create(256, C.sizeof(Msg))    # fillet.c:339 (8192 in production)
+    tv.num_outputs = len(w_h_list)
+    tv.gpu, tv.out_fmt, tv.device_outputs, tv.target = 0, 0, 0, 0
+    tv._running = C.c_int(1)
+    tv.running = C.pointer(tv._running)
+    if first_ts is not None:
+        tv._first = C.c_int64(first_ts)
+        tv.first_timestamp = C.pointer(tv._first)
+    tv._err = SIGNAL_FN(lambda u, code, m: errors.append((code, m)))
+    tv._sig = SIGNAL_FN(lambda u, code, m: signals.append((code, m)))
+    tv.direct_error, tv.signal = tv._err, tv._sig
+    return tv
+
+
+def _push(rt, tv, frame, w, h, pts, interlaced=1, tff=1, fps=(30000, 1001), caption=None, disc=0):
+    buf = rt.memory_take(tv.raw_video_pool, frame.nbytes)
+    C.memmove(buf, frame.ctypes.data, frame.nbytes)
+    m = C.cast(rt.memory_take(tv.msg_pool, C.sizeof(Msg)), C.POINTER(Msg))
+    C.memset(m, 0, C.sizeof(Msg))
+    m.contents.buffer, m.contents.buffer_size = buf, frame.nbytes
+    m.contents.pts, m.contents.dts = pts, pts - 3003
+    m.contents.width, m.contents.height = w, h
+    m.contents.interlaced, m.contents.tff = interlaced, tff
+    m.contents.fps_num, m.contents.fps_den = fps
+    m.contents.aspect_num, m.contents.aspect_den = 16, 9
+    m.contents.source_discontinuity = disc
+    if caption:
+        cb = C.CDLL(None).malloc
+        cb.restype = C.c_void_p
+        p = cb(len(caption))
+        C.memmove(p, caption, len(caption))
+        m.contents.caption_buffer, m.contents.caption_size, m.contents.caption_timestamp = p, len(caption), pts
+    return m
+
+
+def _drain(rt, tv, q, nbytes):
+    out = []
+    while True:
+        m = rt.dataqueue_take_back(q)
+        if not m:
+            break
+        c = m.contents
+        data = np.ctypeslib.as_array(C.cast(c.buffer, C.POINTER(C.c_uint8)), (nbytes,)).copy()
+        cap = C.string_at(c.caption_buffer, c.caption_size) if c.caption_buffer else None
+        out.append(dict(data=data, pts=c.pts, dts=c.dts, w=c.width, h=c.height, idx=c.stream_index, il=c.interlaced,
+                        tff=c.tff, fps=(c.fps_num, c.fps_den), caption=cap, cap_ptr=c.caption_buffer, size=c.buffer_size))
+        rt.memory_return(tv.raw_video_pool, c.buffer)     # what the encoder thread does (transvideo.c:1456-1458)
+        rt.memory_return(tv.msg_pool, m)
+    return out
+
+
+def test_thread_body_semantics(lib, og, oracle, rt, host):
+    w, h = 192, 108
+    outs = [(192, 108), (128, 72), (64, 36)]
+    errors, signals = [], []
+    tv = _make_tv(rt, outs, errors, signals)
+    frames = interlaced_sequence(w, h, 6, seed=21)
+    pool0 = rt.memory_unused(tv.raw_video_pool)
+    ref = oracle.YadifStream(w, h)
+    expected = []
+    for i, f in enumerate(frames):
+        cap = b"CC%02d" % i if i in (1, 3) else None
+        m = _push(rt, tv, f, w, h, 90000 + 3003 * i, caption=cap)
+        assert host.ottgpu_transvideo_process(C.byref(tv), m) == 0
+        r = ref.push(f, 1, 1, tag=i)
+        if r is not None:
+            expected.append(r)
+    assert not errors
+    assert tv.frames_in == 6 and tv.frames_out == 5
+    per_rung = [_drain(rt, tv, tv.encode_queue[k], oracle.i420_size(*outs[k])) for k in range(3)]
+    for k, (dw, dh) in enumerate(outs):
+        assert len(per_rung[k]) == 5
+        for n, got in enumerate(per_rung[k]):
+            deint, tag = expected[n]
+            assert np.array_equal(got["data"], oracle.scale_i420(deint, w, h, dw, dh)), (k, n)
+            assert (got["w"], got["h"], got["idx"], got["il"], got["tff"]) == (dw, dh, k, 0, 1)
+            assert got["pts"] == 90000 + 3003 * tag and got["dts"] == got["pts"] - 3003     # sideband follows the frame
+            assert got["fps"] == (30000, 1001) and got["size"] == oracle.i420_size(dw, dh)
+            assert got["caption"] == (b"CC%02d" % tag if tag in (1, 3) else None)
+    # last rendition owns the original caption buffer, the others got copies (transvideo.c:1649-1657)
+    caps = [[g["cap_ptr"] for g in per_rung[k] if g["cap_ptr"]] for k in range(3)]
+    assert len(set(caps[0]) | set(caps[1]) | set(caps[2])) == 6
+    # every input buffer went back to the pool (transvideo.c:2410) and the outputs were returned by the "encoder"
+    assert rt.memory_unused(tv.raw_video_pool) == pool0
+    host.ottgpu_transvideo_close(C.byref(tv))
+
+
+def test_thread_body_runs_as_pthread_with_discontinuity(lib, og, oracle, rt, host):
+    import threading
+    w, h = 192, 108
+    outs = [(128, 72)]
+    errors, signals = [], []
+    tv = _make_tv(rt, outs, errors, signals)
+    frames = [natural_i420(w, h, 7, shift=2.0 * i) for i in range(8)]
+    t = threading.Thread(target=host.ottgpu_video_prepare_scale_thread, args=(C.addressof(tv),))
+    t.start()
+    for i, f in enumerate(frames):                      # 60000/1001 progressive-flagged => pass-through, one frame late
+        m = _push(rt, tv, f, w, h, 1000 * i, interlaced=0, fps=(60000, 1001), disc=1 if i == 4 else 0)
+        rt.dataqueue_put_front(tv.prepare_queue, m)
+    deadline = time.time() + 30
+    while tv.frames_in < 8 and time.time() < deadline:
+        time.sleep(0.01)
+    time.sleep(0.05)
+    tv._running.value = 0
+    t.join(10)
+    assert not t.is_alive() and not errors
+    got = _drain(rt, tv, tv.encode_queue[0], oracle.i420_size(128, 72))
+    # discontinuity at frame 4 drops the window: frames 0,1,2 come out, then 4,5,6
+    assert [g["pts"] for g in got] == [0, 1000, 2000, 4000, 5000, 6000]
+    for g in got:
+        assert np.array_equal(g["data"], oracle.scale_i420(frames[g["pts"] // 1000], w, h, 128, 72))
+
+
+def test_av_sync_repeat_and_drop(lib, og, oracle, rt, host):
+    # transvideo.c:2233-2382: frames are repeated / dropped when the frame count drifts from what dts implies
+    w, h = 96, 64
+    errors, signals = [], []
+    tv = _make_tv(rt, [(64, 40)], errors, signals, first_ts=0)
+    f = natural_i420(w, h, 7)
+    # dts runs 4 frame-times per frame => the output falls behind => repeats
+    for i in range(5):
+        m = _push(rt, tv, f, w, h, 3003 + 4 * 3003 * i, interlaced=0, fps=(60000, 1001))
+        assert host.ottgpu_transvideo_process(C.byref(tv), m) == 0
+    got = _drain(rt, tv, tv.encode_queue[0], oracle.i420_size(64, 40))
+    assert len(got) > 4 and any(g["pts"] == 0 for g in got) and signals and signals[0][0] == 0x11
+    host.ottgpu_transvideo_close(C.byref(tv))
+    # dts stands still => the output runs ahead => drops
+    errors2, signals2 = [], []
+    tv2 = _make_tv(rt, [(64, 40)], errors2, signals2, first_ts=0)
+    for i in range(8):
+        m = _push(rt, tv2, f, w, h, 3003, interlaced=0, fps=(60000, 1001))
+        assert host.ottgpu_transvideo_process(C.byref(tv2), m) == 0
+    got2 = _drain(rt, tv2, tv2.encode_queue[0], oracle.i420_size(64, 40))
+    assert len(got2) < 7
+    host.ottgpu_transvideo_close(C.byref(tv2))
