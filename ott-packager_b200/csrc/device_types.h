@@ -11,6 +11,15 @@ namespace ottgpu {
 
 constexpr int kMaxRungs = 8;
 constexpr int kMaxRungSlots = kMaxRungs + 1;   // slot 8 = thumbnail (transvideo.c:2155-2174)
+// H-pass intermediates in shared memory: 32-bit (no extraction work in the V pass) or 16-bit (half the footprint)
+#if !defined(OTTGPU_MID_BITS)
+#define OTTGPU_MID_BITS 32
+#endif
+#if OTTGPU_MID_BITS == 32
+typedef int32_t mid_t;
+#else
+typedef int16_t mid_t;
+#endif
 constexpr int kGeomSlots = 4;                  // tile descriptors (and V-table regions) in flight per CTA
 constexpr int kTensorMapBytes = 128;           // sizeof(CUtensorMap)
 constexpr int kThreads = 384;                  // compute threads of a ladder CTA (8 warps); the kernel adds one producer warp

@@ -12,7 +12,7 @@
 //
 // Shared-memory layout of one tile (all sizes from PlaneTables, so planner and kernel agree):
 //   [ staged source : nplanes * sr_max rows * sw_words 32-bit words ]   4 (8-bit) or 2 (16-bit) samples per word
-//   [ H-pass result : nplanes * (sr_max+1) rows * mid_pitch int16   ]   mid_pitch = tw (32|64), rows 16-byte aligned
+//   [ H-pass result : nplanes * (sr_max+1) rows * mid_pitch mid_t   ]   mid_pitch = tw (32|64), rows 16-byte aligned
 //   [ V coefficients: th * vtaps int16 ][ vpos: th int32 ]
 #pragma once
 #include "device_types.h"
@@ -75,7 +75,7 @@ struct TileGeom {
     int sx0;                 // first staged source sample (multiple of 16 bytes)
     int nvec;                // 16-byte vectors staged per row
     int spw;                 // smem pitch of the staged source, 32-bit words (multiple of 4)
-    int mid_pitch;           // smem pitch (int16 elements) of the H-pass result: 32 or 64
+    int mid_pitch;           // smem pitch (mid_t elements) of the H-pass result: 32 or 64
     int tw_log2;             // T->tw is 32 or 64
     int approx_v;
     int off_src, off_mid, off_vc, off_vpos;   // byte offsets of the regions inside the CTA's shared memory
@@ -239,22 +239,22 @@ OTT_DEV void hpass8(int tid, const TileGeom &g, unsigned char *smem)
     const int wstep = ngroups * g.spw, mstep = ngroups * g.mid_pitch;
     for (int p = 0; p < nplanes; ++p) {
         const uint32_t *w = reinterpret_cast<const uint32_t *>(smem + g.off_src) + p * pstride + (off >> 2) + grp * g.spw;
-        int16_t *m = reinterpret_cast<int16_t *>(smem + g.off_mid) + col + (p * sr + grp) * g.mid_pitch;
+        mid_t *m = reinterpret_cast<mid_t *>(smem + g.off_mid) + col + (p * sr + grp) * g.mid_pitch;
         int left = (sr - grp + ngroups - 1) / ngroups;         // rows this thread owns in this plane
         for (; left >= 4; left -= 4) {                         // four rows in flight per thread
             const int v0 = hdot8<HQ>(w, sh, hi, lo);
             const int v1 = hdot8<HQ>(w + wstep, sh, hi, lo);
             const int v2 = hdot8<HQ>(w + 2 * wstep, sh, hi, lo);
             const int v3 = hdot8<HQ>(w + 3 * wstep, sh, hi, lo);
-            m[0] = (int16_t)v0;
-            m[mstep] = (int16_t)v1;
-            m[2 * mstep] = (int16_t)v2;
-            m[3 * mstep] = (int16_t)v3;
+            m[0] = (mid_t)v0;
+            m[mstep] = (mid_t)v1;
+            m[2 * mstep] = (mid_t)v2;
+            m[3 * mstep] = (mid_t)v3;
             w += 4 * wstep;
             m += 4 * mstep;
         }
         for (; left > 0; --left) {
-            m[0] = (int16_t)hdot8<HQ>(w, sh, hi, lo);
+            m[0] = (mid_t)hdot8<HQ>(w, sh, hi, lo);
             w += wstep;
             m += mstep;
         }
@@ -273,7 +273,7 @@ OTT_DEV void hpass8_any(int tid, const TileGeom &g, unsigned char *smem)
     const uint32_t *phi = T.hc_hi + gx * hq, *plo = T.hc_lo + gx * hq;
     const int nrows = g.nplanes * g.sr, sr = g.sr, pstride = g.plane_stride >> 2;
     const uint32_t *src_s = reinterpret_cast<const uint32_t *>(smem + g.off_src) + (off >> 2);
-    int16_t *mid_s = reinterpret_cast<int16_t *>(smem + g.off_mid) + col;
+    mid_t *mid_s = reinterpret_cast<mid_t *>(smem + g.off_mid) + col;
     for (int row = grp; row < nrows; row += ngroups) {
         const int p = row >= sr;
         const uint32_t *w = src_s + p * pstride + (row - p * sr) * g.spw;
@@ -287,7 +287,7 @@ OTT_DEV void hpass8_any(int tid, const TileGeom &g, unsigned char *smem)
             alo = ott_dp4a_uu(a, ott_ldg(plo + q), alo);
             cur = nxt;
         }
-        mid_s[row * g.mid_pitch] = (int16_t)ott_min((ahi * 256 + (int)alo) >> 7, 32767);
+        mid_s[row * g.mid_pitch] = (mid_t)ott_min((ahi * 256 + (int)alo) >> 7, 32767);
     }
 }
 
@@ -306,7 +306,7 @@ OTT_DEV void hpass16(int tid, const TileGeom &g, unsigned char *smem)
     for (int j = 0; j < 4 * HQ; ++j) cf[j] = ott_ldg(T.hc16 + gx * (4 * HQ) + j);
     const int nrows = g.nplanes * g.sr, sr = g.sr, pstride = g.plane_stride >> 2;
     const uint32_t *src_s = reinterpret_cast<const uint32_t *>(smem + g.off_src) + (off >> 1);
-    int16_t *mid_s = reinterpret_cast<int16_t *>(smem + g.off_mid) + col;
+    mid_t *mid_s = reinterpret_cast<mid_t *>(smem + g.off_mid) + col;
     for (int row = grp; row < nrows; row += ngroups) {
         const int p = row >= sr;
         const uint32_t *w = src_s + p * pstride + (row - p * sr) * g.spw;
@@ -319,7 +319,7 @@ OTT_DEV void hpass16(int tid, const TileGeom &g, unsigned char *smem)
             acc += (int)(a & 0xffffu) * cf[2 * k] + (int)(a >> 16) * cf[2 * k + 1];
             cur = nxt;
         }
-        mid_s[row * g.mid_pitch] = (int16_t)ott_min(acc >> 9, 32767);
+        mid_s[row * g.mid_pitch] = (mid_t)ott_min(acc >> 9, 32767);
     }
 }
 
@@ -334,7 +334,7 @@ OTT_DEV void hpass16_any(int tid, const TileGeom &g, unsigned char *smem)
     const int16_t *pc = T.hc16 + gx * taps;
     const int nrows = g.nplanes * g.sr, sr = g.sr, pstride = g.plane_stride >> 2;
     const uint32_t *src_s = reinterpret_cast<const uint32_t *>(smem + g.off_src) + (off >> 1);
-    int16_t *mid_s = reinterpret_cast<int16_t *>(smem + g.off_mid) + col;
+    mid_t *mid_s = reinterpret_cast<mid_t *>(smem + g.off_mid) + col;
     for (int row = grp; row < nrows; row += ngroups) {
         const int p = row >= sr;
         const uint32_t *w = src_s + p * pstride + (row - p * sr) * g.spw;
@@ -346,7 +346,7 @@ OTT_DEV void hpass16_any(int tid, const TileGeom &g, unsigned char *smem)
             acc += (int)(a & 0xffffu) * ott_ldg(pc + 2 * k) + (int)(a >> 16) * ott_ldg(pc + 2 * k + 1);
             cur = nxt;
         }
-        mid_s[row * g.mid_pitch] = (int16_t)ott_min(acc >> 9, 32767);
+        mid_s[row * g.mid_pitch] = (mid_t)ott_min(acc >> 9, 32767);
     }
 }
 
@@ -400,6 +400,26 @@ OTT_DEV void load_words(const uint32_t *p, uint32_t (&w)[NW])
     }
 }
 
+// NV consecutive H-pass results (sign-extended) starting at p (16-byte aligned for NV = 8 with int16, NV = 4 with int32)
+template <int NV>
+OTT_DEV void load_vals(const mid_t *p, int (&t)[NV])
+{
+    if (sizeof(mid_t) == 2) {
+        uint32_t ww[NV / 2];
+        load_words<NV / 2>(reinterpret_cast<const uint32_t *>(p), ww);
+        OTT_UNROLL
+        for (int k = 0; k < NV / 2; ++k) { t[2 * k] = sx_lo(ww[k]); t[2 * k + 1] = sx_hi(ww[k]); }
+    } else {
+        OTT_UNROLL
+        for (int v = 0; v < NV / 4; ++v) {
+            uint32_t ww[4];
+            load_words<4>(reinterpret_cast<const uint32_t *>(p) + 4 * v, ww);
+            OTT_UNROLL
+            for (int k = 0; k < 4; ++k) t[4 * v + k] = (int)ww[k];
+        }
+    }
+}
+
 // Packs results as they are produced so that only a few registers stay live: 8-bit -> 4 samples per word,
 // 16-bit -> 2 samples per word (already shifted for P010).
 template <int BPS> OTT_DEV uint32_t pack2(int a, int b, int shift)   // 16-bit: two samples
@@ -408,90 +428,75 @@ template <int BPS> OTT_DEV uint32_t pack2(int a, int b, int shift)   // 16-bit: 
 }
 OTT_DEV uint32_t pack4(int a, int b, int c, int d) { return (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)d << 24); }
 
-// One row of NW*2 adjacent columns, `vtaps` taps (run-time count: the tap loop is unrolled by four, which keeps the
-// kernel small enough for the instruction cache -- fully unrolled per-tap-count variants measured slower).
-// Output: 8-bit -> NW/2 packed words, 16-bit -> NW packed words.
-template <int NW, int BPS>
-OTT_DEV void vcolumns(const uint32_t *m, int step_words, const int16_t *cf, int vtaps, int mode, int shift,
-                      uint32_t (&out)[BPS == 1 ? NW / 2 : NW])
+// One row of NV adjacent columns, `vtaps` taps (run-time count: the tap loop is unrolled by two, which keeps the kernel
+// small enough for the instruction cache -- fully unrolled per-tap-count variants measured slower).
+// Output: 8-bit -> NV/4 packed words, 16-bit -> NV/2 packed words.
+template <int NV, int BPS>
+OTT_DEV void vcolumns(const mid_t *m, int step, const int16_t *cf, int vtaps, int mode, int shift,
+                      uint32_t (&out)[BPS == 1 ? NV / 4 : NV / 2])
 {
-    int a[2 * NW];
+    int a[NV];
     if (mode == VM_ONE8 || mode == VM_ONE10) {
-        uint32_t ww[NW];
-        load_words<NW>(m, ww);
+        int t[NV];
+        load_vals<NV>(m, t);
         OTT_UNROLL
-        for (int k = 0; k < NW; ++k) {
-            if (mode == VM_ONE8) { a[2 * k] = ott_clip((sx_lo(ww[k]) + 64) >> 7, 255); a[2 * k + 1] = ott_clip((sx_hi(ww[k]) + 64) >> 7, 255); }
-            else { a[2 * k] = ott_clip((sx_lo(ww[k]) + 16) >> 5, 1023); a[2 * k + 1] = ott_clip((sx_hi(ww[k]) + 16) >> 5, 1023); }
-        }
+        for (int k = 0; k < NV; ++k) a[k] = mode == VM_ONE8 ? ott_clip((t[k] + 64) >> 7, 255) : ott_clip((t[k] + 16) >> 5, 1023);
     } else if (mode == VM_APPROX8) {
         const int init = (64 + 8 * (vtaps - 1)) >> 4;
         OTT_UNROLL
-        for (int k = 0; k < 2 * NW; ++k) a[k] = init;
+        for (int k = 0; k < NV; ++k) a[k] = init;
         int j = 0;
         for (; j + 2 <= vtaps; j += 2) {                   // x86 tap counts are even (filterAlign 2): no tail in practice
             const uint32_t c2 = *reinterpret_cast<const uint32_t *>(cf + j);
             OTT_UNROLL
             for (int u = 0; u < 2; ++u) {
                 const int cj = u ? sx_hi(c2) : sx_lo(c2);
-                uint32_t ww[NW];
-                load_words<NW>(m + (j + u) * step_words, ww);
+                int t[NV];
+                load_vals<NV>(m + (j + u) * step, t);
                 OTT_UNROLL
-                for (int k = 0; k < NW; ++k) {
-                    a[2 * k] += (sx_lo(ww[k]) * cj) >> 16;
-                    a[2 * k + 1] += (sx_hi(ww[k]) * cj) >> 16;
-                }
+                for (int k = 0; k < NV; ++k) a[k] += (t[k] * cj) >> 16;
             }
         }
         for (; j < vtaps; ++j) {
             const int cj = cf[j];
-            uint32_t ww[NW];
-            load_words<NW>(m + j * step_words, ww);
+            int t[NV];
+            load_vals<NV>(m + j * step, t);
             OTT_UNROLL
-            for (int k = 0; k < NW; ++k) {
-                a[2 * k] += (sx_lo(ww[k]) * cj) >> 16;
-                a[2 * k + 1] += (sx_hi(ww[k]) * cj) >> 16;
-            }
+            for (int k = 0; k < NV; ++k) a[k] += (t[k] * cj) >> 16;
         }
         OTT_UNROLL
-        for (int k = 0; k < 2 * NW; ++k) a[k] = ott_clip((int)(int16_t)a[k] >> 3, 255);   // paddw wraparound, psraw 3, packuswb
+        for (int k = 0; k < NV; ++k) a[k] = ott_clip((int)(int16_t)a[k] >> 3, 255);   // paddw wraparound, psraw 3, packuswb
     } else {
         const int init = mode == VM_EXACT8 ? 64 << 12 : 1 << 16;
         OTT_UNROLL
-        for (int k = 0; k < 2 * NW; ++k) a[k] = init;
+        for (int k = 0; k < NV; ++k) a[k] = init;
         int j = 0;
         for (; j + 2 <= vtaps; j += 2) {
             OTT_UNROLL
             for (int u = 0; u < 2; ++u) {
                 const int cj = cf[j + u];
-                uint32_t ww[NW];
-                load_words<NW>(m + (j + u) * step_words, ww);
+                int t[NV];
+                load_vals<NV>(m + (j + u) * step, t);
                 OTT_UNROLL
-                for (int k = 0; k < NW; ++k) {
-                    a[2 * k] += sx_lo(ww[k]) * cj;
-                    a[2 * k + 1] += sx_hi(ww[k]) * cj;
-                }
+                for (int k = 0; k < NV; ++k) a[k] += t[k] * cj;
             }
         }
         for (; j < vtaps; ++j) {
             const int cj = cf[j];
-            uint32_t ww[NW];
-            load_words<NW>(m + j * step_words, ww);
+            int t[NV];
+            load_vals<NV>(m + j * step, t);
             OTT_UNROLL
-            for (int k = 0; k < NW; ++k) {
-                a[2 * k] += sx_lo(ww[k]) * cj;
-                a[2 * k + 1] += sx_hi(ww[k]) * cj;
-            }
+            for (int k = 0; k < NV; ++k) a[k] += t[k] * cj;
         }
         OTT_UNROLL
-        for (int k = 0; k < 2 * NW; ++k) a[k] = mode == VM_EXACT8 ? ott_clip(a[k] >> 19, 255) : ott_clip(a[k] >> 17, 1023);
+        for (int k = 0; k < NV; ++k) a[k] = mode == VM_EXACT8 ? ott_clip(a[k] >> 19, 255) : ott_clip(a[k] >> 17, 1023);
     }
     if (BPS == 1) {
         OTT_UNROLL
-        for (int k = 0; k < NW / 2; ++k) out[k] = pack4(a[4 * k], a[4 * k + 1], a[4 * k + 2], a[4 * k + 3]);
+        for (int k = 0; k < NV / 4; ++k) out[k] = pack4(a[4 * k], a[4 * k + 1], a[4 * k + 2], a[4 * k + 3]);
     } else {
         OTT_UNROLL
-        for (int k = 0; k < NW; ++k) out[k] = pack2<2>(a[2 * k], a[2 * k + 1], shift);
+        for (int k = 0; k < NV / 2; ++k) out[k] = pack2<2>(a[2 * k], a[2 * k + 1], shift);
     }
 }
 
@@ -542,8 +547,7 @@ OTT_DEV void zip16(uint32_t u, uint32_t v, uint32_t &lo, uint32_t &hi)
 template <int CPT, int BPS>
 OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
 {
-    constexpr int NW = CPT / 2;                                 // shared words per tap
-    constexpr int NO = BPS == 1 ? NW / 2 : NW;                  // packed output words per plane
+    constexpr int NO = BPS == 1 ? CPT / 4 : CPT / 2;            // packed output words per plane
     typedef typename StoreT<BPS>::type S;
     // the geometry lives in shared memory: copy what the loop needs into registers once
     const PlaneTables &T = *g.T;
@@ -556,8 +560,7 @@ OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
     const int lx = tid & ((1 << lpr_log2) - 1), ry = tid >> lpr_log2, rows_per_pass = kThreads >> lpr_log2;
     const int x = CPT * lx;
     if (x >= tile_w) return;
-    const int step_words = mid_pitch >> 1;
-    const int16_t *mid_s = reinterpret_cast<const int16_t *>(smem + g.off_mid);
+    const mid_t *mid_s = reinterpret_cast<const mid_t *>(smem + g.off_mid);
     const int16_t *vc_s = reinterpret_cast<const int16_t *>(smem + g.off_vc);
     const int32_t *vpos_s = reinterpret_cast<const int32_t *>(smem + g.off_vpos);
     const int gx = x0 + x;
@@ -569,13 +572,13 @@ OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
         if (BPS == 1) mode = vtaps == 1 ? VM_ONE8 : ((approx && gy < exact_from) ? VM_APPROX8 : VM_EXACT8);
         else mode = vtaps == 1 ? VM_ONE10 : VM_EXACT10;
         uint32_t o0[NO];
-        vcolumns<NW, BPS>(reinterpret_cast<const uint32_t *>(mid_s + r0 * mid_pitch + x), step_words, cf, vtaps, mode, shift, o0);
+        vcolumns<CPT, BPS>(mid_s + r0 * mid_pitch + x, mid_pitch, cf, vtaps, mode, shift, o0);
         if (nplanes == 1) {
             store_words<S, NO>(dst0 + (size_t)gy * dpitch0, gx, o0, dstW);
             continue;
         }
         uint32_t o1[NO];
-        vcolumns<NW, BPS>(reinterpret_cast<const uint32_t *>(mid_s + (sr + r0) * mid_pitch + x), step_words, cf, vtaps, mode, shift, o1);
+        vcolumns<CPT, BPS>(mid_s + (sr + r0) * mid_pitch + x, mid_pitch, cf, vtaps, mode, shift, o1);
         if (il) {
             uint32_t z[2 * NO];
             OTT_UNROLL

@@ -68,8 +68,8 @@ Plan::~Plan()
 namespace {
 
 // Two CTAs per SM: 2 source buffers + intermediates + tables must stay under ~110 KB per CTA.
-constexpr size_t kSrcCap = 36 * 1024;        // one staged-source buffer
-constexpr size_t kMidCap = 36 * 1024;        // H-pass result region
+constexpr size_t kSrcCap = (sizeof(mid_t) == 4 ? 24 : 36) * 1024;   // one staged-source buffer
+constexpr size_t kMidCap = (sizeof(mid_t) == 4 ? 52 : 36) * 1024;   // H-pass result region
 constexpr int kMaxTileRows = 128;            // keeps enough tiles per frame for load balance
 constexpr size_t kSmemHardLimit = 224 * 1024; // == kMaxTileSmem (kernels.h); sm_100 allows 227 KB per CTA
 
@@ -93,7 +93,7 @@ TileRegions tile_regions(int nplanes, int sr_max, int sw_words, int tw, int th, 
 {
     TileRegions r;
     r.src = (size_t)nplanes * (((size_t)sr_max * sw_words * 4 + 127) & ~(size_t)127);   // planes 128-byte aligned (TMA)
-    r.mid = (size_t)nplanes * (sr_max + 1) * tw * 2;                      // tw is 32 or 64 -> multiple of 16
+    r.mid = (size_t)nplanes * (sr_max + 1) * tw * sizeof(mid_t);         // tw is 32 or 64 -> multiple of 16
     r.vc = (((size_t)th * vtaps * 2 + 3) & ~(size_t)3) + (size_t)th * 4;
     r.vc = (r.vc + 15) & ~(size_t)15;
     return r;
