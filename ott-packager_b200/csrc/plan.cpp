@@ -68,8 +68,8 @@ Plan::~Plan()
 namespace {
 
 // Two CTAs per SM: 2 source buffers + intermediates + tables must stay under ~110 KB per CTA.
-constexpr size_t kSrcCap = (sizeof(mid_t) == 4 ? 24 : 36) * 1024;   // one staged-source buffer
-constexpr size_t kMidCap = (sizeof(mid_t) == 4 ? 52 : 36) * 1024;   // H-pass result region
+constexpr size_t kSrcCap = (sizeof(mid_t) == 4 ? 22 : 36) * 1024;   // one staged-source buffer
+constexpr size_t kMidCap = (sizeof(mid_t) == 4 ? 54 : 36) * 1024;   // H-pass result region
 constexpr int kMaxTileRows = 128;            // keeps enough tiles per frame for load balance
 constexpr size_t kSmemHardLimit = 224 * 1024; // == kMaxTileSmem (kernels.h); sm_100 allows 227 KB per CTA
 
@@ -138,9 +138,9 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
     };
     // Tile shape: the H pass is recomputed for the vertical halo rows of every tile, so tall tiles are cheap and narrow
     // ones cost only extra staged bytes.  Pick the tallest tile whose staged source and intermediates fit their caps.
-    struct Shape { int tw, th, sw_words, sr_max; double halo; bool fits; };
+    struct Shape { int tw, th, sw_words, sr_max; double halo; bool fits, soft; };
     auto shape_for = [&](int tw) {
-        Shape sh{tw, row_quant, 0, 0, 1e9, false};
+        Shape sh{tw, row_quant, 0, 0, 1e9, false, false};
         const int tiles_x = (dstW + tw - 1) / tw;
         int nvec = 0;
         for (int tx = 0; tx < tiles_x; ++tx) {
@@ -158,7 +158,7 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
         if (fits(th, false)) {
             const int nty = (dstH + th - 1) / th;                // rebalance so the last tile row is not a sliver
             th = ((dstH + nty - 1) / nty + row_quant - 1) / row_quant * row_quant;
-            sh.fits = true;
+            sh.fits = sh.soft = true;
         } else {
             // very long filters (4K -> thumbnail): single-buffered launch, shrink until the tile fits at all
             while (th > 1 && !fits(th, true)) th /= 2;
@@ -172,7 +172,9 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
     Shape best = shape_for(dstW > 64 ? 64 : 32);
     if (best.tw == 64) {
         const Shape narrow = shape_for(32);
-        if (narrow.fits && (!best.fits || narrow.halo < 0.9 * best.halo)) best = narrow;
+        // prefer a shape inside the double-buffered budget; among those the one with less vertical halo
+        if (narrow.soft && (!best.soft || narrow.halo < 0.9 * best.halo)) best = narrow;
+        else if (!best.fits && narrow.fits) best = narrow;
     }
     if (!best.fits) { err = "filter too long for one tile (shared memory)"; return false; }
     T.tw = best.tw;
