@@ -13,7 +13,7 @@ constexpr int kMaxRungs = 8;
 constexpr int kMaxRungSlots = kMaxRungs + 1;   // slot 8 = thumbnail (transvideo.c:2155-2174)
 // H-pass intermediates in shared memory: 32-bit (no extraction work in the V pass) or 16-bit (half the footprint)
 #if !defined(OTTGPU_MID_BITS)
-#define OTTGPU_MID_BITS 32
+#define OTTGPU_MID_BITS 16      /* measured: 32-bit intermediates save V-pass instructions but halve the tile height: slower */
 #endif
 #if OTTGPU_MID_BITS == 32
 typedef int32_t mid_t;

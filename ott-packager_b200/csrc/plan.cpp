@@ -1,5 +1,6 @@
 #include "plan.h"
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -68,9 +69,14 @@ Plan::~Plan()
 namespace {
 
 // Two CTAs per SM: 2 source buffers + intermediates + tables must stay under ~110 KB per CTA.
-constexpr size_t kSrcCap = (sizeof(mid_t) == 4 ? 22 : 36) * 1024;   // one staged-source buffer
-constexpr size_t kMidCap = (sizeof(mid_t) == 4 ? 54 : 36) * 1024;   // H-pass result region
-constexpr int kMaxTileRows = 128;            // keeps enough tiles per frame for load balance
+size_t env_kb(const char *name, size_t dflt_kb)
+{
+    const char *v = std::getenv(name);               // tuning knobs for profiling sessions, not part of the API
+    return (v && std::atoi(v) > 0 ? (size_t)std::atoi(v) : dflt_kb) * 1024;
+}
+const size_t kSrcCap = env_kb("OTTGPU_SRC_CAP_KB", sizeof(mid_t) == 4 ? 22 : 36);   // one staged-source buffer
+const size_t kMidCap = env_kb("OTTGPU_MID_CAP_KB", sizeof(mid_t) == 4 ? 54 : 36);   // H-pass result region
+const int kMaxTileRows = (int)(env_kb("OTTGPU_MAX_TILE_ROWS", 128) / 1024);          // keeps enough tiles per frame for load balance
 constexpr size_t kSmemHardLimit = 224 * 1024; // == kMaxTileSmem (kernels.h); sm_100 allows 227 KB per CTA
 
 template <typename T>
