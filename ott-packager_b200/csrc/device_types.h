@@ -43,6 +43,7 @@ struct PlaneTables {
     int vtaps;
     int exact_from;          // 8-bit target A: first output row computed with the exact vertical formula
     int tw, th;              // tile size in output samples
+    int cpt;                 // V pass: adjacent columns per thread (8 | 4), chosen so the tile's work divides evenly
     int tiles_x, tiles_y;
     int sw_words;            // shared-memory source row pitch in 32-bit words (max over tiles, + funnel slack)
     int sr_max;              // max source rows any tile needs

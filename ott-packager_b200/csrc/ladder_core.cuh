@@ -594,16 +594,16 @@ OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
     }
 }
 
-// Columns per thread: as many as keep every thread busy -- a sweep covers 256*CPT/tw output rows, so short tiles
-// (steep downscales, thumbnails) use narrower threads.
+// Columns per thread (8 or 4) come from the plan: the planner picks the width whose (row, column-group) unit count
+// divides most evenly among the compute threads.
 OTT_DEV void phase_vpass(int tid, const TileGeom &g, unsigned char *smem)
 {
-    const bool wide = g.th * g.tw >= (kThreads * 8) / 2 + 1;      // more than half a sweep of 8-column threads
+    const bool wide = g.T->cpt == 8;
     if (g.bps == 1) {
-        if (g.tw_log2 == 6 && wide) vpass<8, 1>(tid, g, smem);
+        if (wide) vpass<8, 1>(tid, g, smem);
         else vpass<4, 1>(tid, g, smem);
     } else {
-        if (g.tw_log2 == 6 && wide) vpass<8, 2>(tid, g, smem);
+        if (wide) vpass<8, 2>(tid, g, smem);
         else vpass<4, 2>(tid, g, smem);
     }
 }

@@ -142,11 +142,12 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
         }
         return m;
     };
-    // Tile shape: the H pass is recomputed for the vertical halo rows of every tile, so tall tiles are cheap and narrow
-    // ones cost only extra staged bytes.  Pick the tallest tile whose staged source and intermediates fit their caps.
-    struct Shape { int tw, th, sw_words, sr_max; double halo; bool fits, soft; };
-    auto shape_for = [&](int tw) {
-        Shape sh{tw, row_quant, 0, 0, 1e9, false, false};
+    // Tile shape.  The H pass is recomputed for the vertical halo rows of every tile (tall tiles are cheap, narrow ones
+    // only cost staged bytes); the V pass hands out (row, column-group) units to kThreads threads, so a tile whose unit
+    // count is not a multiple of kThreads leaves threads idle at the barrier.  Candidates inside the shared-memory caps
+    // are ranked by an instruction-count model of both passes per useful output sample.
+    struct Shape { int tw, th, cpt, sw_words, sr_max; double cost; bool fits, soft; };
+    auto staged_words = [&](int tw) {
         const int tiles_x = (dstW + tw - 1) / tw;
         int nvec = 0;
         for (int tx = 0; tx < tiles_x; ++tx) {
@@ -154,37 +155,57 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
             const int s0 = h.pos[x0] & ~(spv - 1), s1 = h.pos[x1] + taps4;
             nvec = std::max(nvec, (s1 - s0 + 4 / bps + spv - 1) / spv);    // + one word of funnel-shift slack
         }
-        sh.sw_words = nvec * 4;
+        return nvec * 4;
+    };
+    auto model = [&](int tw, int th, int cpt, int sr) {
+        const int ngroups = kThreads / tw;
+        const double hrows = (double)((nplanes * sr + ngroups - 1) / ngroups) * ngroups;          // rows incl. idle groups
+        const double h_instr = hrows * tw * (9.0 + 4.0 * hq);
+        const int units = th * tw / cpt;
+        const double vunits = (double)((units + kThreads - 1) / kThreads) * kThreads;
+        const double v_instr = vunits * nplanes * cpt * (3.3 * v.taps + 12.0) + vunits * 70.0;
+        const int tiles_y = (dstH + th - 1) / th;
+        const double edge = (double)tiles_y * th / dstH;                                          // partial last tile row
+        const double cols = (double)((dstW + tw - 1) / tw) * tw / dstW;
+        return (h_instr + v_instr) / ((double)nplanes * th * tw) * edge * cols;
+    };
+    auto best_for = [&](int tw) {
+        Shape sh{tw, row_quant, tw == 64 ? 8 : 4, staged_words(tw), 0, 1e30, false, false};
         auto fits = [&](int th, bool hard) {
             const TileRegions r = tile_regions(nplanes, rows_needed(th), sh.sw_words, tw, th, v.taps);
             return hard ? r.src + r.mid + r.vc + 16 <= kSmemHardLimit : (r.src <= kSrcCap && r.mid <= kMidCap);
         };
-        int th = std::min((dstH + row_quant - 1) / row_quant * row_quant, kMaxTileRows);
-        while (th > row_quant && !fits(th, false)) th -= row_quant;
-        if (fits(th, false)) {
-            const int nty = (dstH + th - 1) / th;                // rebalance so the last tile row is not a sliver
-            th = ((dstH + nty - 1) / nty + row_quant - 1) / row_quant * row_quant;
-            sh.fits = sh.soft = true;
-        } else {
+        const int th_max = std::min((dstH + row_quant - 1) / row_quant * row_quant, kMaxTileRows);
+        for (int th = row_quant; th <= th_max; th += row_quant) {
+            if (!fits(th, false)) break;
+            const int sr = rows_needed(th);
+            for (int cpt = 4; cpt <= 8; cpt += 4) {
+                if (tw / cpt < 4) continue;                      // at least 4 lanes per row
+                const double c = model(tw, th, cpt, sr);
+                if (c < sh.cost) { sh.cost = c; sh.th = th; sh.cpt = cpt; sh.sr_max = sr; sh.fits = sh.soft = true; }
+            }
+        }
+        if (!sh.soft) {
             // very long filters (4K -> thumbnail): single-buffered launch, shrink until the tile fits at all
+            int th = row_quant;
             while (th > 1 && !fits(th, true)) th /= 2;
             sh.fits = fits(th, true);
+            sh.th = th;
+            sh.sr_max = rows_needed(th);
+            sh.cost = 1e29;
         }
-        sh.th = th;
-        sh.sr_max = rows_needed(th);
-        sh.halo = (double)sh.sr_max * dstH / ((double)std::min(th, dstH) * srcH);
         return sh;
     };
-    Shape best = shape_for(dstW > 64 ? 64 : 32);
+    Shape best = best_for(dstW > 64 ? 64 : 32);
     if (best.tw == 64) {
-        const Shape narrow = shape_for(32);
-        // prefer a shape inside the double-buffered budget; among those the one with less vertical halo
-        if (narrow.soft && (!best.soft || narrow.halo < 0.9 * best.halo)) best = narrow;
+        const Shape narrow = best_for(32);
+        if (narrow.soft && (!best.soft || narrow.cost < 0.95 * best.cost)) best = narrow;
         else if (!best.fits && narrow.fits) best = narrow;
     }
     if (!best.fits) { err = "filter too long for one tile (shared memory)"; return false; }
     T.tw = best.tw;
     T.th = best.th;
+    T.cpt = best.cpt;
     T.sw_words = best.sw_words;
     T.sr_max = best.sr_max;
     T.tiles_x = (dstW + T.tw - 1) / T.tw;

@@ -387,9 +387,9 @@ int ottgpu_channel_describe(const ottgpu_channel *ch, char *buf, size_t size)
         const RungDev &R = p.host_copy.rung[s];
         for (int k = 0; k < 2; ++k) {
             const PlaneTables &T = k ? R.chroma : R.luma;
-            snprintf(line, sizeof line, "  slot %d %s %s %dx%d -> %dx%d  taps H %d (x4 quads %d) V %d  tile %dx%d  tiles %dx%d  src rows/tile %d  staged row %d B  exact_from %d\n",
+            snprintf(line, sizeof line, "  slot %d %s %s %dx%d -> %dx%d  taps H %d (x4 quads %d) V %d  tile %dx%d cpt %d  tiles %dx%d  src rows/tile %d  staged row %d B  exact_from %d\n",
                      s, s == p.thumb_slot ? "thumb" : "rung", k ? "chroma" : "luma", T.srcW, T.srcH, T.dstW, T.dstH, 4 * T.hq, T.hq,
-                     T.vtaps, T.tw, T.th, T.tiles_x, T.tiles_y, T.sr_max, T.sw_words * 4, T.exact_from);
+                     T.vtaps, T.tw, T.th, T.cpt, T.tiles_x, T.tiles_y, T.sr_max, T.sw_words * 4, T.exact_from);
             out += R.scaled ? line : std::string("  slot ") + std::to_string(s) + (k ? " chroma" : " luma") + " same size: copy items\n";
         }
     }
