@@ -175,14 +175,19 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
             const TileRegions r = tile_regions(nplanes, rows_needed(th), sh.sw_words, tw, th, v.taps);
             return hard ? r.src + r.mid + r.vc + 16 <= kSmemHardLimit : (r.src <= kSrcCap && r.mid <= kMidCap);
         };
-        const int th_max = std::min((dstH + row_quant - 1) / row_quant * row_quant, kMaxTileRows);
-        for (int th = row_quant; th <= th_max; th += row_quant) {
-            if (!fits(th, false)) break;
+        // tallest tile inside the caps (measured better than minimising the modelled cost over all heights: per-tile
+        // overheads the model does not see favour big tiles), rebalanced so the last tile row is not a sliver; then the
+        // V thread width that wastes fewer thread slots
+        int th = std::min((dstH + row_quant - 1) / row_quant * row_quant, kMaxTileRows);
+        while (th > row_quant && !fits(th, false)) th -= row_quant;
+        if (fits(th, false)) {
+            const int nty = (dstH + th - 1) / th;
+            th = ((dstH + nty - 1) / nty + row_quant - 1) / row_quant * row_quant;
             const int sr = rows_needed(th);
-            for (int cpt = 4; cpt <= 8; cpt += 4) {
+            for (int cpt = 8; cpt >= 4; cpt -= 4) {
                 if (tw / cpt < 4) continue;                      // at least 4 lanes per row
                 const double c = model(tw, th, cpt, sr);
-                if (c < sh.cost) { sh.cost = c; sh.th = th; sh.cpt = cpt; sh.sr_max = sr; sh.fits = sh.soft = true; }
+                if (c < sh.cost * (cpt == 4 ? 0.97 : 1.0)) { sh.cost = c; sh.th = th; sh.cpt = cpt; sh.sr_max = sr; sh.fits = sh.soft = true; }
             }
         }
         if (!sh.soft) {
