@@ -40,7 +40,6 @@ inline uint32_t ott_dp4a_uu(uint32_t a, uint32_t b, uint32_t c)
 }
 template <typename T> inline T ott_ldg(const T *p) { return *p; }
 inline int ott_sad(int a, int b, int c) { return (a > b ? a - b : b - a) + c; }
-inline int ott_mulhi(int a, int b) { return (int)(((long long)a * (long long)b) >> 32); }
 }  // namespace ottgpu
 #else
 #define OTT_DEV __device__ __forceinline__
@@ -56,7 +55,6 @@ OTT_DEV int ott_dp4a_us(uint32_t a, uint32_t b, int c)
 OTT_DEV uint32_t ott_dp4a_uu(uint32_t a, uint32_t b, uint32_t c) { return __dp4a(a, b, c); }
 template <typename T> OTT_DEV T ott_ldg(const T *p) { return __ldg(p); }
 OTT_DEV int ott_sad(int a, int b, int c) { return (int)__sad(a, b, (unsigned)c); }   // |a-b|+c in one VABSDIFF
-OTT_DEV int ott_mulhi(int a, int b) { return __mulhi(a, b); }
 }  // namespace ottgpu
 #endif
 
@@ -444,25 +442,19 @@ OTT_DEV void vcolumns(const mid_t *m, int step, const int16_t *cf, int vtaps, in
         OTT_UNROLL
         for (int k = 0; k < NV; ++k) a[k] = mode == VM_ONE8 ? ott_clip((t[k] + 64) >> 7, 255) : ott_clip((t[k] + 16) >> 5, 1023);
     } else if (mode == VM_APPROX8) {
-        // x86 yuv2yuvX: acc += (t*c) >> 16 per tap (pmulhw).  With t held in the upper half of a register,
-        // mulhi(t << 16, c) IS floor(t*c / 65536): the multiply runs on the FMA pipe and leaves the (busier) ALU pipe
-        // only the mask and the adds.
         const int init = (64 + 8 * (vtaps - 1)) >> 4;
         OTT_UNROLL
         for (int k = 0; k < NV; ++k) a[k] = init;
         int j = 0;
-        if (sizeof(mid_t) == 2) {
-            for (; j + 2 <= vtaps; j += 2) {               // x86 tap counts are even (filterAlign 2): no tail in practice
-                const uint32_t c2 = *reinterpret_cast<const uint32_t *>(cf + j);
-                const int c0 = sx_lo(c2), c1 = sx_hi(c2);
-                uint32_t w0[NV / 2], w1[NV / 2];
-                load_words<NV / 2>(reinterpret_cast<const uint32_t *>(m + j * step), w0);
-                load_words<NV / 2>(reinterpret_cast<const uint32_t *>(m + (j + 1) * step), w1);
+        for (; j + 2 <= vtaps; j += 2) {                   // x86 tap counts are even (filterAlign 2): no tail in practice
+            const uint32_t c2 = *reinterpret_cast<const uint32_t *>(cf + j);
+            OTT_UNROLL
+            for (int u = 0; u < 2; ++u) {
+                const int cj = u ? sx_hi(c2) : sx_lo(c2);
+                int t[NV];
+                load_vals<NV>(m + (j + u) * step, t);
                 OTT_UNROLL
-                for (int k = 0; k < NV / 2; ++k) {
-                    a[2 * k] += ott_mulhi((int)(w0[k] << 16), c0) + ott_mulhi((int)(w1[k] << 16), c1);
-                    a[2 * k + 1] += ott_mulhi((int)(w0[k] & 0xffff0000u), c0) + ott_mulhi((int)(w1[k] & 0xffff0000u), c1);
-                }
+                for (int k = 0; k < NV; ++k) a[k] += (t[k] * cj) >> 16;
             }
         }
         for (; j < vtaps; ++j) {
