@@ -114,8 +114,12 @@ struct ottgpu_channel {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     size_t src_bytes = 0;
-    uint8_t *slots[4] = {nullptr, nullptr, nullptr, nullptr};
-    bool slot_used[4] = {false, false, false, false};
+    // upload slots: the yadif window (3) + the frame being uploaded + one step of release delay, so that the upload
+    // of step t+1 (copy stream) never targets a frame the kernels of step t may still read
+    static constexpr int kSlots = 6;
+    uint8_t *slots[kSlots] = {nullptr};
+    bool slot_used[kSlots] = {false};
+    int slot_cooling = -1;                             // released last step, reusable from the next one
     FrameRef prev, cur, next;
     uint8_t *deint = nullptr;                          // yadif output when no rung surface can take it directly
     uint8_t *stage[kMaxRungSlots] = {nullptr};         // device surfaces for host-destined rungs / thumbnail
@@ -133,6 +137,7 @@ struct ottgpu_batch {
     std::vector<ottgpu_channel *> ch;
     int gpu = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;                // host frames are uploaded here while the previous step computes
     Item *d_items = nullptr;
     int n_items = 0, max_thumb_items = 0;
     int src_max[2] = {0, 0}, mid_max[2] = {0, 0}, vc_max[2] = {0, 0};   // [0] rung launch, [1] thumbnail launch
@@ -142,7 +147,7 @@ struct ottgpu_batch {
         YadifJob *h_jobs = nullptr, *d_jobs = nullptr;
         Item *h_thumb_items = nullptr, *d_thumb_items = nullptr;
         int *d_counters = nullptr;                          // [0] rung launch, [1] thumbnail launch tile schedulers
-        cudaEvent_t done = nullptr, k0 = nullptr, k1 = nullptr, y0 = nullptr, y1 = nullptr;
+        cudaEvent_t done = nullptr, uploaded = nullptr, k0 = nullptr, k1 = nullptr, y0 = nullptr, y1 = nullptr;
         bool in_flight = false, timed = false, timed_yadif = false;
     } set[2];
     int turn = 0;
@@ -164,13 +169,16 @@ bool referenced(const ottgpu_channel *c, const uint8_t *dev)
 void release_frame(ottgpu_channel *c, const FrameRef &f, ottgpu_frame_out *out)
 {
     if (!f.valid || referenced(c, f.dev)) return;
-    if (f.slot >= 0) c->slot_used[f.slot] = false;
+    if (f.slot >= 0) {
+        if (c->slot_cooling >= 0) c->slot_used[c->slot_cooling] = false;
+        c->slot_cooling = f.slot;
+    }
     else if (out && out->n_released < 4) out->released[out->n_released++] = f.dev;
 }
 
 int take_slot(ottgpu_channel *c)
 {
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < ottgpu_channel::kSlots; ++i)
         if (!c->slot_used[i]) {
             if (!c->slots[i] && cudaMalloc((void **)&c->slots[i], c->src_bytes + 64) != cudaSuccess) {
                 cudaGetLastError();
@@ -264,7 +272,8 @@ int frame_tensor_maps(ottgpu_channel *c, const uint8_t *base, cudaStream_t strea
 
 void drop_window(ottgpu_channel *c)
 {
-    for (int i = 0; i < 4; ++i) c->slot_used[i] = false;
+    for (int i = 0; i < ottgpu_channel::kSlots; ++i) c->slot_used[i] = false;
+    c->slot_cooling = -1;
     c->prev = c->cur = c->next = FrameRef();
 }
 
@@ -446,6 +455,7 @@ int ottgpu_batch_create(ottgpu_channel **channels, int n, ottgpu_batch **out)
     b->gpu = channels[0]->gpu;
     b->stream = channels[0]->stream;
     CK(cudaSetDevice(b->gpu));
+    CK(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
     std::vector<Item> all;
     for (int i = 0; i < n; ++i) {
         const Plan &p = *channels[i]->plan;
@@ -469,6 +479,7 @@ int ottgpu_batch_create(ottgpu_channel **channels, int n, ottgpu_batch **out)
         CK(cudaMallocHost((void **)&st.h_jobs, n * sizeof(YadifJob)));
         CK(cudaMalloc((void **)&st.d_counters, 2 * sizeof(int)));
         CK(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&st.uploaded, cudaEventDisableTiming));
         CK(cudaEventCreate(&st.k0));
         CK(cudaEventCreate(&st.k1));
         CK(cudaEventCreate(&st.y0));
@@ -483,6 +494,10 @@ void ottgpu_batch_destroy(ottgpu_batch *b)
     if (!b) return;
     cudaSetDevice(b->gpu);
     cudaStreamSynchronize(b->stream);
+    if (b->copy_stream) {
+        cudaStreamSynchronize(b->copy_stream);
+        cudaStreamDestroy(b->copy_stream);
+    }
     cudaFree(b->d_items);
     for (ottgpu_batch::Set &st : b->set) {
         cudaFree(st.d_thumb_items);
@@ -493,6 +508,7 @@ void ottgpu_batch_destroy(ottgpu_batch *b)
         cudaFreeHost(st.h_jobs);
         cudaFreeHost(st.h_thumb_items);
         if (st.done) cudaEventDestroy(st.done);
+        if (st.uploaded) cudaEventDestroy(st.uploaded);
         if (st.k0) cudaEventDestroy(st.k0);
         if (st.k1) cudaEventDestroy(st.k1);
         if (st.y0) cudaEventDestroy(st.y0);
@@ -584,6 +600,9 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
     }
     const int n = (int)b->ch.size();
     cudaStream_t s = b->stream;
+    // uploads of this step may overwrite slots last read two steps ago: order the copy stream after that step only
+    // (this set's previous use was retired above; the other set = the previous step may still be running)
+    bool uploads = false;
     int n_jobs = 0, n_thumb_items = 0, max_w = 0, max_h = 0, live = 0;
     bool all_fast = true;
     b->readbacks.clear();
@@ -620,7 +639,8 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
             f.slot = take_slot(c);
             if (f.slot < 0) return fail(OTTGPU_ERR_NOMEM, "no device slot for the incoming frame");
             f.dev = c->slots[f.slot];
-            CK(cudaMemcpyAsync(c->slots[f.slot], in[i].data, c->src_bytes, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(c->slots[f.slot], in[i].data, c->src_bytes, cudaMemcpyHostToDevice, b->copy_stream));
+            uploads = true;
         } else if (in[i].mem == OTTGPU_MEM_DEVICE) {
             f.dev = static_cast<const uint8_t *>(in[i].data);
         } else {
@@ -734,6 +754,10 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
     }
 
     // ---- 5. enqueue: descriptors, yadif, ladder, thumbnails, read-backs
+    if (uploads) {
+        CK(cudaEventRecord(st.uploaded, b->copy_stream));
+        CK(cudaStreamWaitEvent(s, st.uploaded, 0));
+    }
     CK(cudaMemcpyAsync(st.d_binds, st.h_binds, n * sizeof(Binding), cudaMemcpyHostToDevice, s));
     if (n_jobs) {
         CK(cudaMemcpyAsync(st.d_jobs, st.h_jobs, n * sizeof(YadifJob), cudaMemcpyHostToDevice, s));
