@@ -455,6 +455,19 @@ int ottgpu_batch_create(ottgpu_channel **channels, int n, ottgpu_batch **out)
     b->gpu = channels[0]->gpu;
     b->stream = channels[0]->stream;
     CK(cudaSetDevice(b->gpu));
+    // One stream per batch.  Channels that created their own stream adopt the batch's (their own is retired); a stream
+    // shared this way is deliberately never destroyed, so no channel or batch can be left with a dangling handle.
+    for (int i = 1; i < n; ++i) {
+        ottgpu_channel *c = channels[i];
+        if (c->stream == b->stream) continue;
+        if (!c->own_stream) return fail(OTTGPU_ERR_ARG, "channels of one batch must use the same cudaStream_t");
+        CK(cudaStreamSynchronize(c->stream));
+        cudaStreamDestroy(c->stream);
+        c->stream = b->stream;
+        c->own_stream = false;
+        if (c->solo) c->solo->stream = b->stream;
+    }
+    if (n > 1) channels[0]->own_stream = false;
     CK(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
     std::vector<Item> all;
     for (int i = 0; i < n; ++i) {
