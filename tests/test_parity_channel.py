@@ -224,3 +224,54 @@ def test_bad_arguments_are_refused(lib, og):
         og.Channel(lib, og.make_cfg(192, 108, [(128, 72, og.FMT_I420)] * 9))
     with pytest.raises(og.OttGpuError):
         og.Channel(lib, og.make_cfg(192, 108, [(0, 72, og.FMT_I420)]))
+
+
+def test_eight_rungs_and_odd_geometry(lib, og, oracle):
+    """MAX_TRANS_OUTPUTS = 8 renditions (include/fillet.h:57) incl. ragged sizes, one launch."""
+    w, h = 322, 182
+    rungs = [(322, 182, og.FMT_I420), (214, 120, og.FMT_I420), (160, 90, og.FMT_I420), (107, 61, og.FMT_I420),
+             (86, 48, og.FMT_I420), (64, 36, og.FMT_I420), (50, 28, og.FMT_I420), (42, 24, og.FMT_I420)]
+    ch = og.Channel(lib, og.make_cfg(w, h, rungs, deint=og.DEINT_BYPASS))
+    f = noise_i420(w, h, 77)
+    r = ch.submit(f)
+    for got, (dw, dh, _) in zip(r["rungs"], rungs):
+        assert np.array_equal(got, oracle.scale_i420(f, w, h, dw, dh)), (dw, dh)
+    ch.close()
+
+
+@pytest.mark.gpu
+def test_cfg5_4k_channel_with_thumbnail_full_size(real_lib, og, oracle):
+    """BASELINE config 5's 4K channel: 2160p 8-bit -> {2160p,1080p,720p,360p} + 176x144 thumbnail (the thumbnail's
+    88/60-tap filters take the single-buffered launch)."""
+    w, h = 3840, 2160
+    rungs = [(3840, 2160, og.FMT_I420), (1920, 1080, og.FMT_I420), (1280, 720, og.FMT_I420), (640, 360, og.FMT_I420)]
+    ch = og.Channel(real_lib, og.make_cfg(w, h, rungs, deint=og.DEINT_FLAGGED, thumb=(176, 144, 1)))
+    f0, f1 = noise_i420(w, h, 5), natural_i420(w, h, 7)
+    assert ch.submit(f0, interlaced=0) is None
+    r = ch.submit(f1, interlaced=0)
+    for got, (dw, dh, _) in zip(r["rungs"], rungs):
+        assert np.array_equal(got, oracle.scale_i420(f0, w, h, dw, dh)), (dw, dh)
+    assert np.array_equal(r["thumbnail"], oracle.scale_i420(f0, w, h, 176, 144))
+    ch.close()
+
+
+@pytest.mark.gpu
+def test_cfg4_many_channels_one_batch_full_size(real_lib, og, oracle):
+    """BASELINE config 4's per-GPU slice: 8 concurrent 1080i channels, yadif + 4 rungs, one launch per stage."""
+    w, h = 1920, 1080
+    rungs = [(1920, 1080, og.FMT_I420), (1280, 720, og.FMT_I420), (960, 540, og.FMT_I420), (640, 360, og.FMT_I420)]
+    chans = [og.Channel(real_lib, og.make_cfg(w, h, rungs, deint=og.DEINT_ALL)) for _ in range(8)]
+    batch = og.Batch(real_lib, chans)
+    seq = interlaced_sequence(w, h, 3, seed=31)
+    for t in range(3):
+        res = batch.submit([np.roll(seq[t], 1000 * c) for c in range(8)], interlaced=1, tff=1)
+    assert batch.last_launches == 2                          # one yadif launch + one ladder launch for all 8 channels
+    for c in (0, 5):
+        fr = [np.roll(seq[t], 1000 * c) for t in range(3)]
+        deint = oracle.yadif_frame(fr[0], fr[1], fr[2], w, h, 1, 1)
+        assert np.array_equal(res[c]["rungs"][0], deint)
+        for k in (1, 3):
+            assert np.array_equal(res[c]["rungs"][k], oracle.scale_i420(deint, w, h, rungs[k][0], rungs[k][1]))
+    batch.close()
+    for c in chans:
+        c.close()
