@@ -500,6 +500,43 @@ OTT_DEV void vcolumns(const mid_t *m, int step, const int16_t *cf, int vtaps, in
     }
 }
 
+// Fast path of the common case (8-bit, x86-truncating rows, even tap count).  The accumulator is kept shifted left by
+// 16: A = (A & 0xffff0000) + t*c adds floor(t*c / 65536) to the upper half (its low half is the product's remainder,
+// masked away before the next tap), the 16-bit wraparound of paddw is the upper half's natural overflow, and the final
+// (int16(acc) >> 3) is A >> 19.  First tap pair peeled so no accumulator initialisation moves are needed.
+template <int NV>
+OTT_DEV void vrow_approx8(const mid_t *m, int step, const int16_t *cf, int vtaps, uint32_t (&out)[NV / 4])
+{
+    const int init = ((64 + 8 * (vtaps - 1)) >> 4) << 16;
+    int a[NV];
+    {
+        const uint32_t c2 = *reinterpret_cast<const uint32_t *>(cf);
+        const int c0 = sx_lo(c2), c1 = sx_hi(c2);
+        int t0[NV], t1[NV];
+        load_vals<NV>(m, t0);
+        load_vals<NV>(m + step, t1);
+        OTT_UNROLL
+        for (int k = 0; k < NV; ++k) a[k] = t0[k] * c0 + init;
+        OTT_UNROLL
+        for (int k = 0; k < NV; ++k) a[k] = (int)((uint32_t)a[k] & 0xffff0000u) + t1[k] * c1;
+    }
+    for (int j = 2; j < vtaps; j += 2) {
+        const uint32_t c2 = *reinterpret_cast<const uint32_t *>(cf + j);
+        const int c0 = sx_lo(c2), c1 = sx_hi(c2);
+        int t0[NV], t1[NV];
+        load_vals<NV>(m + j * step, t0);
+        load_vals<NV>(m + (j + 1) * step, t1);
+        OTT_UNROLL
+        for (int k = 0; k < NV; ++k) a[k] = (int)((uint32_t)a[k] & 0xffff0000u) + t0[k] * c0;
+        OTT_UNROLL
+        for (int k = 0; k < NV; ++k) a[k] = (int)((uint32_t)a[k] & 0xffff0000u) + t1[k] * c1;
+    }
+    OTT_UNROLL
+    for (int k = 0; k < NV / 4; ++k)
+        out[k] = pack4(ott_clip(a[4 * k] >> 19, 255), ott_clip(a[4 * k + 1] >> 19, 255), ott_clip(a[4 * k + 2] >> 19, 255),
+                       ott_clip(a[4 * k + 3] >> 19, 255));
+}
+
 // NWORDS packed 32-bit words = NWORDS*4/sizeof(S) samples starting at element `elem` of a row of `total` samples
 template <typename S, int NWORDS>
 OTT_DEV void store_words(uint8_t *row, int elem, const uint32_t (&w)[NWORDS], int total)
@@ -544,6 +581,18 @@ OTT_DEV void zip16(uint32_t u, uint32_t v, uint32_t &lo, uint32_t &hi)
     hi = (u >> 16) | (v & 0xffff0000u);
 }
 
+template <int CPT, int BPS> struct VRowFast {
+    static OTT_DEV void run(const mid_t *, int, const int16_t *, int, uint32_t (&)[BPS == 1 ? CPT / 4 : CPT / 2]) {}
+};
+template <int CPT> struct VRowFast<CPT, 1> {
+    static OTT_DEV void run(const mid_t *m, int step, const int16_t *cf, int vtaps, uint32_t (&out)[CPT / 4]) { vrow_approx8<CPT>(m, step, cf, vtaps, out); }
+};
+template <int CPT, int BPS>
+OTT_DEV void vrow_fast(const mid_t *m, int step, const int16_t *cf, int vtaps, uint32_t (&out)[BPS == 1 ? CPT / 4 : CPT / 2])
+{
+    VRowFast<CPT, BPS>::run(m, step, cf, vtaps, out);
+}
+
 template <int CPT, int BPS>
 OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
 {
@@ -571,14 +620,17 @@ OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
         int mode;
         if (BPS == 1) mode = vtaps == 1 ? VM_ONE8 : ((approx && gy < exact_from) ? VM_APPROX8 : VM_EXACT8);
         else mode = vtaps == 1 ? VM_ONE10 : VM_EXACT10;
+        const bool fast = BPS == 1 && mode == VM_APPROX8 && !(vtaps & 1);
         uint32_t o0[NO];
-        vcolumns<CPT, BPS>(mid_s + r0 * mid_pitch + x, mid_pitch, cf, vtaps, mode, shift, o0);
+        if (fast) vrow_fast<CPT, BPS>(mid_s + r0 * mid_pitch + x, mid_pitch, cf, vtaps, o0);
+        else vcolumns<CPT, BPS>(mid_s + r0 * mid_pitch + x, mid_pitch, cf, vtaps, mode, shift, o0);
         if (nplanes == 1) {
             store_words<S, NO>(dst0 + (size_t)gy * dpitch0, gx, o0, dstW);
             continue;
         }
         uint32_t o1[NO];
-        vcolumns<CPT, BPS>(mid_s + (sr + r0) * mid_pitch + x, mid_pitch, cf, vtaps, mode, shift, o1);
+        if (fast) vrow_fast<CPT, BPS>(mid_s + (sr + r0) * mid_pitch + x, mid_pitch, cf, vtaps, o1);
+        else vcolumns<CPT, BPS>(mid_s + (sr + r0) * mid_pitch + x, mid_pitch, cf, vtaps, mode, shift, o1);
         if (il) {
             uint32_t z[2 * NO];
             OTT_UNROLL
