@@ -40,6 +40,7 @@ inline uint32_t ott_dp4a_uu(uint32_t a, uint32_t b, uint32_t c)
 }
 template <typename T> inline T ott_ldg(const T *p) { return *p; }
 inline int ott_sad(int a, int b, int c) { return (a > b ? a - b : b - a) + c; }
+inline int ott_byte(uint32_t w, int i) { return (int)((w >> (8 * i)) & 0xffu); }
 }  // namespace ottgpu
 #else
 #define OTT_DEV __device__ __forceinline__
@@ -55,6 +56,7 @@ OTT_DEV int ott_dp4a_us(uint32_t a, uint32_t b, int c)
 OTT_DEV uint32_t ott_dp4a_uu(uint32_t a, uint32_t b, uint32_t c) { return __dp4a(a, b, c); }
 template <typename T> OTT_DEV T ott_ldg(const T *p) { return __ldg(p); }
 OTT_DEV int ott_sad(int a, int b, int c) { return (int)__sad(a, b, (unsigned)c); }   // |a-b|+c in one VABSDIFF
+OTT_DEV int ott_byte(uint32_t w, int i) { return (int)__byte_perm(w, 0, 0x4440 | i); }   // one PRMT instead of shift+mask
 }  // namespace ottgpu
 #endif
 

@@ -82,7 +82,7 @@ OTT_DEV void yadif_position(const YadifJob &j, int x, int y)
 // words).  Every neighbour row is fetched as aligned words (4 words of `cur` above and below cover the +-3 sample search
 // window of all eight samples) and the per-sample predictor is branch-free: |a-b|+c is one VABSDIFF, the nested
 // direction search of filter_line_c becomes predicated selects.
-OTT_DEV int ybyte(uint32_t w, int i) { return (int)((w >> (8 * i)) & 0xffu); }
+OTT_DEV int ybyte(uint32_t w, int i) { return ott_byte(w, i); }
 
 OTT_DEV void yadif_oct8(const YadifJob &j, size_t off, int w, int h, int x8, int y)
 {
