@@ -28,7 +28,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-I420, NV12 = 0, 1
+I420, NV12, P010 = 0, 1, 2
 WORKLOADS = {
     # BASELINE.json configs[1]: 1080p60 progressive 8-bit -> 5-rung NV12 ladder, zero-copy surfaces for NVENC
     "cfg2": dict(desc="cfg2: 1080p60 progressive I420 8-bit -> 5-rung NV12 ladder 1080p/720p/540p/360p/416x234, "
@@ -44,6 +44,11 @@ WORKLOADS = {
     "cfg4": dict(desc="cfg4: 1080i channels -> yadif(all) + 4-rung I420 ladder 1080p/720p/540p/360p, bicubic target A",
                  w=1920, h=1080, rungs=[(1920, 1080), (1280, 720), (960, 540), (640, 360)], out_fmt=I420, deint=0,
                  interlaced=1, pitch_align=0),
+    # BASELINE.json configs[2]: 2160p60 10-bit P010 -> 6-rung lanczos ladder (P010 rungs)
+    "cfg3": dict(desc="cfg3: 2160p60 P010 10-bit progressive -> 6-rung P010 lanczos ladder 2160p/1440p/1080p/720p/540p/360p, "
+                      "target A tables, yadif=0:-1:1 pass-through, 176x144 thumbnail every 150 frames",
+                 w=3840, h=2160, rungs=[(3840, 2160), (2560, 1440), (1920, 1080), (1280, 720), (960, 540), (640, 360)],
+                 out_fmt=P010, src_fmt=P010, bps=2, lanczos=1, deint=1, interlaced=0, pitch_align=0),
 }
 THUMB = (176, 144, 150)
 
@@ -54,21 +59,28 @@ def frame_bytes(w, h):
 
 def algorithmic_bytes(wl):
     """fused read (2.5*S with yadif, S without) + sum of rung bytes, per source frame."""
-    s = frame_bytes(wl["w"], wl["h"])
-    out = sum(frame_bytes(w, h) for w, h in wl["rungs"])
+    bps = wl.get("bps", 1)
+    s = frame_bytes(wl["w"], wl["h"]) * bps
+    out = sum(frame_bytes(w, h) for w, h in wl["rungs"]) * bps
     return (2.5 * s if wl["deint"] == 0 else s) + out, s, out
 
 
 def ladder_kernel_bytes(wl):
     """bytes the ladder kernel itself moves per frame: read S, write the rungs it produces (with yadif the full-size rung
     is written by the yadif kernel instead)."""
+    bps = wl.get("bps", 1)
     s = frame_bytes(wl["w"], wl["h"])
     out = sum(frame_bytes(w, h) for w, h in wl["rungs"] if not (wl["deint"] == 0 and (w, h) == (wl["w"], wl["h"])))
-    return s + out
+    return (s + out) * bps
 
 
-def synth_frames(w, h, n, interlaced):
-    """n distinct natural-like frames (sin/cos + checker + noise); woven fields when interlaced."""
+def synth_frames(w, h, n, interlaced, p010=False):
+    """n distinct natural-like frames (sin/cos + checker + noise); woven fields when interlaced.
+    p010: 10-bit noise MSB-aligned in 16 bits, Y plane then interleaved UV (seed 99)."""
+    if p010:
+        rng = np.random.default_rng(99)
+        n_s = frame_bytes(w, h)
+        return [((rng.integers(0, 1024, n_s, dtype=np.uint16)) << 6).astype(np.uint16).view(np.uint8) for _ in range(n)]
     rng = np.random.default_rng(7)
     cw, ch = (w + 1) // 2, (h + 1) // 2
     out = []
@@ -143,7 +155,15 @@ class CpuReference:
         self.w, self.h = wl["w"], wl["h"]
         self.count = 0
         self.prev = None
-        if self.kind == "reference":
+        self.p010 = wl.get("src_fmt") == P010
+        if self.kind == "reference" and self.p010:
+            S.load()
+            self.S = S
+            self.ctx = [S.Scaler(self.w, self.h, "p010le", dw, dh, "p010le", S.SWS_LANCZOS) for dw, dh in wl["rungs"]]
+            self.thumb = S.Scaler(self.w, self.h, "p010le", THUMB[0], THUMB[1], "yuv420p10le", S.SWS_BICUBIC)
+            self.out = [S._alloc_planes("p010le", dw, dh) for dw, dh in wl["rungs"]]
+            self.tout = S._alloc_planes("yuv420p10le", THUMB[0], THUMB[1])
+        elif self.kind == "reference":
             S.load()
             self.S = S
             self.ctx = [S.Scaler(self.w, self.h, "yuv420p", dw, dh, "yuv420p", S.SWS_BICUBIC) for dw, dh in wl["rungs"]]
@@ -155,6 +175,9 @@ class CpuReference:
     def planes(self, f):
         w, h = self.w, self.h
         cw, ch = (w + 1) // 2, (h + 1) // 2
+        if self.p010:
+            f16 = f.view(np.uint16)
+            return [f16[: w * h].reshape(h, w), f16[w * h:].reshape(ch, 2 * cw)]
         return [f[: w * h].reshape(h, w), f[w * h: w * h + cw * ch].reshape(ch, cw), f[w * h + cw * ch:].reshape(ch, cw)]
 
     def frame(self, f, nxt):
@@ -172,6 +195,9 @@ class CpuReference:
                     O.lib().ora_i420_to_nv12(packed.ctypes.data, dw, dh, nv.ctypes.data)
             if self.count % THUMB[2] == 0:
                 self.thumb.scale_planes(src, self.tout)
+        elif self.p010:
+            for (dw, dh) in wl["rungs"]:
+                O.scale_p010(f.view(np.uint16), self.w, self.h, dw, dh, O.LANCZOS)
         else:
             for (dw, dh), nv in zip(wl["rungs"], self.nv12):
                 o = O.scale_i420(f, self.w, self.h, dw, dh)
@@ -229,7 +255,7 @@ def reference_main(args, wl, rank, world):
     if rank != 0:
         return
     threads = host_cores()
-    frames = synth_frames(wl["w"], wl["h"], 4, wl["interlaced"])
+    frames = synth_frames(wl["w"], wl["h"], 4, wl["interlaced"], wl.get("src_fmt") == P010)
     total_rounds = args.warmup + args.steps
     _, _, kind, per_round = run_cpu_rounds(wl, frames, threads, rounds=total_rounds)
     timed = per_round[args.warmup:]
@@ -262,16 +288,17 @@ def ours_main(args, wl, rank, world, local_rank):
     w, h, Cn = wl["w"], wl["h"], args.channels
     fmt = wl["out_fmt"]
     rungs = [(dw, dh, fmt, wl["pitch_align"]) for dw, dh in wl["rungs"]]
-    src_bytes = frame_bytes(w, h)
+    bps, src_fmt = wl.get("bps", 1), wl.get("src_fmt", I420)
+    src_bytes = frame_bytes(w, h) * bps
 
     def make_channels():
-        return [og.Channel(lib, og.make_cfg(w, h, rungs, deint=wl["deint"], gpu=local_rank, thumb=THUMB,
+        return [og.Channel(lib, og.make_cfg(w, h, rungs, src_fmt=src_fmt, filt=wl.get("lanczos", 0), deint=wl["deint"], gpu=local_rank, thumb=THUMB,
                                             stream=stream.cuda_stream, thumb_phase=(i * THUMB[2]) // Cn))
                 for i in range(Cn)]
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    base_frames = synth_frames(w, h, 4, wl["interlaced"])
+    base_frames = synth_frames(w, h, 4, wl["interlaced"], src_fmt == P010)
     RING = 4
     # ---------------- device-resident arm
     chans = make_channels()
@@ -366,7 +393,18 @@ def ours_main(args, wl, rank, world, local_rank):
 
     # parity spot check (channel 0, the frame produced by the last step) against the CPU oracle
     parity = None
-    if rank == 0 and args.steps >= 3:
+    if rank == 0 and args.steps >= 3 and src_fmt == P010:
+        from oracle import oracle as O
+        last_phase = (args.steps - 1) % RING
+        exp_src = base_frames[((args.steps - 2) % RING) % 4].view(np.uint16)
+        ok = True
+        for r, (dw, dh) in enumerate(wl["rungs"]):
+            if (dw, dh) not in ((3840, 2160), (640, 360)):
+                continue                                     # the 4K lanczos oracle is slow: check the first and last rung
+            got = lib.from_device(dst_dev[0][last_phase % 2][r], rung_bytes[r], gpu=local_rank).view(np.uint16)
+            ok = ok and np.array_equal(got, O.scale_p010(exp_src, w, h, dw, dh, O.LANCZOS))
+        parity = "bit-exact vs oracle (channel 0, rungs 2160p + 360p)" if ok else "MISMATCH"
+    elif rank == 0 and args.steps >= 3:
         from oracle import oracle as O
         # timed step k used ios[k % RING]; the last step's output is the frame submitted one step earlier (yadif latency)
         last_phase = (args.steps - 1) % RING
@@ -397,7 +435,7 @@ def ours_main(args, wl, rank, world, local_rank):
     for c in range(Cn):
         for r in range(2):
             f = np.roll(base_frames[(c + r) % 4], 64 * c)
-            C.memmove(host_src[c][r], f.ctypes.data, src_bytes)
+            C.memmove(host_src[c][r], np.ascontiguousarray(f).ctypes.data, src_bytes)
     e2e_steps = max(4, min(args.steps, 60))
     chans = make_channels()
     batch = og.Batch(lib, chans)
@@ -405,7 +443,7 @@ def ours_main(args, wl, rank, world, local_rank):
     e2e_warm = max(args.warmup, 8)        # the channels allocate their upload slots / tensor maps lazily: settle first
     ems, elaunch, _, _, thumbs = timed_region(batch, ios, e2e_steps, e2e_warm)
     e2e_value = world * Cn * e2e_steps / (ems / 1000.0)
-    thumb_bytes = frame_bytes(THUMB[0], THUMB[1])
+    thumb_bytes = frame_bytes(THUMB[0], THUMB[1]) * bps
     e2e = {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": Cn * src_bytes + Cn * 424,
            "d2h_bytes_per_step": thumbs * thumb_bytes / float(e2e_steps), "ms_per_step": ems / e2e_steps,
            "outputs": "device surfaces (NVENC-style zero-copy hand-off); thumbnails to host"}
@@ -475,7 +513,7 @@ def ours_main(args, wl, rank, world, local_rank):
                          % (done, done // threads, threads, el)}
     line = {"metric": "ladder_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "vs_baseline": None, "dtype": "u8" if bps == 1 else "u16 (10 significant bits)", "data": "synthetic",
             "config": {"workload": wl["desc"], "channels_per_gpu": Cn, "frames_per_step": world * Cn,
                        "algorithmic_bytes_per_frame": alg, "l2": "inputs+outputs per step exceed L2 (%.0f MB in, %.0f MB out per GPU per step)"
                        % (Cn * s_in / 1e6, Cn * s_out / 1e6), "parity": parity,
