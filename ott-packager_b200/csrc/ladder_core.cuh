@@ -38,6 +38,16 @@ inline uint32_t ott_dp4a_uu(uint32_t a, uint32_t b, uint32_t c)
     for (int k = 0; k < 4; ++k) c += ((a >> (8 * k)) & 255) * ((b >> (8 * k)) & 255);
     return c;
 }
+inline int ott_dp2a_us(uint32_t a, uint32_t b, int c, int hi)      // two u16 of a x two s8 of b (bytes 0,1 or 2,3)
+{
+    const uint32_t bb = hi ? b >> 16 : b;
+    return c + (int)(a & 0xffffu) * (int)(int8_t)(bb & 255) + (int)(a >> 16) * (int)(int8_t)((bb >> 8) & 255);
+}
+inline uint32_t ott_dp2a_uu(uint32_t a, uint32_t b, uint32_t c, int hi)
+{
+    const uint32_t bb = hi ? b >> 16 : b;
+    return c + (a & 0xffffu) * (bb & 255) + (a >> 16) * ((bb >> 8) & 255);
+}
 template <typename T> inline T ott_ldg(const T *p) { return *p; }
 inline int ott_sad(int a, int b, int c) { return (a > b ? a - b : b - a) + c; }
 inline int ott_byte(uint32_t w, int i) { return (int)((w >> (8 * i)) & 0xffu); }
@@ -54,6 +64,20 @@ OTT_DEV int ott_dp4a_us(uint32_t a, uint32_t b, int c)
     return d;
 }
 OTT_DEV uint32_t ott_dp4a_uu(uint32_t a, uint32_t b, uint32_t c) { return __dp4a(a, b, c); }
+OTT_DEV int ott_dp2a_us(uint32_t a, uint32_t b, int c, int hi)
+{
+    int d;
+    if (hi) asm("dp2a.hi.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    else asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+OTT_DEV uint32_t ott_dp2a_uu(uint32_t a, uint32_t b, uint32_t c, int hi)
+{
+    uint32_t d;
+    if (hi) asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    else asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 template <typename T> OTT_DEV T ott_ldg(const T *p) { return __ldg(p); }
 OTT_DEV int ott_sad(int a, int b, int c) { return (int)__sad(a, b, (unsigned)c); }   // |a-b|+c in one VABSDIFF
 OTT_DEV int ott_byte(uint32_t w, int i) { return (int)__byte_perm(w, 0, 0x4440 | i); }   // one PRMT instead of shift+mask
@@ -293,7 +317,27 @@ OTT_DEV void hpass8_any(int tid, const TileGeom &g, unsigned char *smem)
     }
 }
 
-// 16-bit samples (10 significant bits, already right-aligned by the staging): two samples per word, plain IMAD.
+// 16-bit samples (10 significant bits, already right-aligned by the staging): two samples per word.  Same coefficient
+// split as the 8-bit path, two taps per dp2a: sum v*c = 256*sum v*(c>>8) + sum v*(c&255)   (exact).
+template <int HQ>
+OTT_DEV int hdot16(const uint32_t *w, uint32_t sh, const uint32_t (&hi)[HQ], const uint32_t (&lo)[HQ])
+{
+    uint32_t cur = w[0];
+    int ahi = 0;
+    uint32_t alo = 0;
+    OTT_UNROLL
+    for (int q = 0; q < HQ; ++q) {
+        const uint32_t w1 = w[2 * q + 1], w2 = w[2 * q + 2];
+        const uint32_t a0 = ott_funnel_r(cur, w1, sh), a1 = ott_funnel_r(w1, w2, sh);
+        ahi = ott_dp2a_us(a0, hi[q], ahi, 0);
+        ahi = ott_dp2a_us(a1, hi[q], ahi, 1);
+        alo = ott_dp2a_uu(a0, lo[q], alo, 0);
+        alo = ott_dp2a_uu(a1, lo[q], alo, 1);
+        cur = w2;
+    }
+    return ott_min((ahi * 256 + (int)alo) >> 9, 32767);
+}
+
 template <int HQ>
 OTT_DEV void hpass16(int tid, const TileGeom &g, unsigned char *smem)
 {
@@ -303,25 +347,27 @@ OTT_DEV void hpass16(int tid, const TileGeom &g, unsigned char *smem)
     const int gx = g.x0 + col;
     const int off = ott_ldg(T.hpos + gx) - g.sx0;
     const uint32_t sh = (uint32_t)(off & 1) * 16;
-    int cf[4 * HQ];
+    uint32_t hi[HQ], lo[HQ];
     OTT_UNROLL
-    for (int j = 0; j < 4 * HQ; ++j) cf[j] = ott_ldg(T.hc16 + gx * (4 * HQ) + j);
-    const int nrows = g.nplanes * g.sr, sr = g.sr, pstride = g.plane_stride >> 2;
-    const uint32_t *src_s = reinterpret_cast<const uint32_t *>(smem + g.off_src) + (off >> 1);
-    mid_t *mid_s = reinterpret_cast<mid_t *>(smem + g.off_mid) + col;
-    for (int row = grp; row < nrows; row += ngroups) {
-        const int p = row >= sr;
-        const uint32_t *w = src_s + p * pstride + (row - p * sr) * g.spw;
-        uint32_t cur = w[0];
-        int acc = 0;
-        OTT_UNROLL
-        for (int k = 0; k < 2 * HQ; ++k) {
-            const uint32_t nxt = w[k + 1];
-            const uint32_t a = ott_funnel_r(cur, nxt, sh);
-            acc += (int)(a & 0xffffu) * cf[2 * k] + (int)(a >> 16) * cf[2 * k + 1];
-            cur = nxt;
+    for (int q = 0; q < HQ; ++q) {
+        hi[q] = ott_ldg(T.hc_hi + gx * HQ + q);
+        lo[q] = ott_ldg(T.hc_lo + gx * HQ + q);
+    }
+    const int sr = g.sr, nplanes = g.nplanes, pstride = g.plane_stride >> 2;
+    const int wstep = ngroups * g.spw, mstep = ngroups * g.mid_pitch;
+    for (int p = 0; p < nplanes; ++p) {
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(smem + g.off_src) + p * pstride + (off >> 1) + grp * g.spw;
+        mid_t *m = reinterpret_cast<mid_t *>(smem + g.off_mid) + col + (p * sr + grp) * g.mid_pitch;
+        int left = (sr - grp + ngroups - 1) / ngroups;
+        for (; left >= 2; left -= 2) {                         // two rows in flight per thread
+            const int v0 = hdot16<HQ>(w, sh, hi, lo);
+            const int v1 = hdot16<HQ>(w + wstep, sh, hi, lo);
+            m[0] = (mid_t)v0;
+            m[mstep] = (mid_t)v1;
+            w += 2 * wstep;
+            m += 2 * mstep;
         }
-        mid_s[row * g.mid_pitch] = (mid_t)ott_min(acc >> 9, 32767);
+        if (left > 0) m[0] = (mid_t)hdot16<HQ>(w, sh, hi, lo);
     }
 }
 
@@ -373,6 +419,9 @@ OTT_DEV void phase_hpass(int tid, const TileGeom &g, unsigned char *smem)
         case 4: hpass16<4>(tid, g, smem); break;
         case 5: hpass16<5>(tid, g, smem); break;
         case 6: hpass16<6>(tid, g, smem); break;
+        case 7: hpass16<7>(tid, g, smem); break;
+        case 8: hpass16<8>(tid, g, smem); break;
+        case 9: hpass16<9>(tid, g, smem); break;
         default: hpass16_any(tid, g, smem); break;
         }
     }
