@@ -107,7 +107,7 @@ TileRegions tile_regions(int nplanes, int sr_max, int sw_words, int tw, int th, 
 
 // Builds tables + tiling for one plane kind of one rung.  Host vectors are kept in `keep` only long enough to upload.
 bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int dstH, int bps, int nplanes, int filter,
-                 int target, int exact_from, TileRegions &regions, std::vector<int32_t> &hpos_out,
+                 int target, int exact_from, TileRegions &regions, bool &soft_out, std::vector<int32_t> &hpos_out,
                  std::vector<int32_t> &vpos_out, std::string &err)
 {
     const PolyphaseTable h = plan_table(srcW, dstW, filter, target, false);
@@ -190,6 +190,10 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
                 if (c < sh.cost * (cpt == 4 ? 0.97 : 1.0)) { sh.cost = c; sh.th = th; sh.cpt = cpt; sh.sr_max = sr; sh.fits = sh.soft = true; }
             }
         }
+        for (int th = row_quant / 2; !sh.soft && th >= 1; th /= 2) {      // steep filters: shorter than the quantum, still inside the caps
+            if (!fits(th, false)) continue;
+            sh.th = th; sh.cpt = 4; sh.sr_max = rows_needed(th); sh.cost = model(tw, th, 4, sh.sr_max); sh.fits = sh.soft = true;
+        }
         if (!sh.soft) {
             // very long filters (4K -> thumbnail): single-buffered launch, shrink until the tile fits at all
             int th = row_quant;
@@ -208,6 +212,7 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
         else if (!best.fits && narrow.fits) best = narrow;
     }
     if (!best.fits) { err = "filter too long for one tile (shared memory)"; return false; }
+    soft_out = best.soft;
     T.tw = best.tw;
     T.th = best.th;
     T.cpt = best.cpt;
@@ -314,8 +319,7 @@ std::shared_ptr<Plan> get_plan(const ottgpu_cfg &cfg_in, std::string &err)
         R.scaled = !same;
         R.approx_v = bps == 1 && cfg.target == OTTGPU_TARGET_A;
         const int dcw = (rc.width + 1) / 2, dch = (rc.height + 1) / 2;
-        const int which = s == plan->thumb_slot ? 1 : 0;
-        std::vector<Item> &sink = which ? plan->thumb_items : plan->items;
+        const bool is_thumb = s == plan->thumb_slot;
         auto copy_item = [&](uint8_t kind, int y0, int rows) {
             Item it;
             std::memset(&it, 0, sizeof(it));
@@ -345,16 +349,23 @@ std::shared_ptr<Plan> get_plan(const ottgpu_cfg &cfg_in, std::string &err)
         // the thumbnail scaler is SWS_BICUBIC whatever the ladder uses (transvideo.c:2155-2157)
         const int filt = s == plan->thumb_slot ? OTTGPU_FILTER_BICUBIC : cfg.filter;
         TileRegions rl, rc2;
+        bool soft_l = true, soft_c = true;
         std::vector<int32_t> lh, lv, chh, cv;
-        if (!build_plane(*plan, R.luma, cfg.src_width, cfg.src_height, rc.width, rc.height, bps, 1, filt, cfg.target, luma_exact, rl, lh, lv, err)) return nullptr;
-        if (!build_plane(*plan, R.chroma, scw, sch, dcw, dch, bps, 2, filt, cfg.target, chroma_exact, rc2, chh, cv, err)) return nullptr;
-        plan->src_max[which] = std::max(plan->src_max[which], (int)std::max(rl.src, rc2.src));
-        plan->mid_max[which] = std::max(plan->mid_max[which], (int)std::max(rl.mid, rc2.mid));
-        plan->vc_max[which] = std::max(plan->vc_max[which], (int)std::max(rl.vc, rc2.vc));
+        if (!build_plane(*plan, R.luma, cfg.src_width, cfg.src_height, rc.width, rc.height, bps, 1, filt, cfg.target, luma_exact, rl, soft_l, lh, lv, err)) return nullptr;
+        if (!build_plane(*plan, R.chroma, scw, sch, dcw, dch, bps, 2, filt, cfg.target, chroma_exact, rc2, soft_c, chh, cv, err)) return nullptr;
+        // launch class per plane kind: 0 = inside the double-buffer budget, 1 = big tiles, 2 = thumbnail
+        const int class_l = is_thumb ? 2 : (soft_l ? 0 : 1), class_c = is_thumb ? 2 : (soft_c ? 0 : 1);
+        auto account = [&](int cls, const TileRegions &r) {
+            plan->src_max[cls] = std::max(plan->src_max[cls], (int)r.src);
+            plan->mid_max[cls] = std::max(plan->mid_max[cls], (int)r.mid);
+            plan->vc_max[cls] = std::max(plan->vc_max[cls], (int)r.vc);
+        };
+        account(class_l, rl);
+        account(class_c, rc2);
         // tile geometry resolved here once (the kernel only loads it); items are ordered by the first source row each
         // tile reads, so tiles of different rungs over the same band run together and share the source through L2
         const int spv = 16 / bps;
-        auto scale_items = [&](const PlaneTables &T, const std::vector<int32_t> &hp, const std::vector<int32_t> &vp, uint8_t kind, int band_scale) {
+        auto scale_items = [&](const PlaneTables &T, const std::vector<int32_t> &hp, const std::vector<int32_t> &vp, uint8_t kind, int band_scale, int cls) {
             for (int ty = 0; ty < T.tiles_y; ++ty)
                 for (int tx = 0; tx < T.tiles_x; ++tx) {
                     Item it;
@@ -368,11 +379,13 @@ std::shared_ptr<Plan> get_plan(const ottgpu_cfg &cfg_in, std::string &err)
                     it.x0 = (uint16_t)x0; it.y0 = (uint16_t)y0; it.tw = (uint16_t)tw; it.th = (uint16_t)th;
                     it.sy0 = (uint16_t)sy0; it.sr = (uint16_t)sr; it.sx0 = (uint16_t)sx0;
                     it.nvec = (uint16_t)((last - sx0 + 4 / bps + spv - 1) / spv);     // + one word of funnel-shift slack
-                    if (which) sink.push_back(it); else ordered.push_back({it, band_scale * sy0});
+                    if (cls == 2) plan->thumb_items.push_back(it);
+                    else if (cls == 1) plan->big_items.push_back(it);
+                    else ordered.push_back({it, band_scale * sy0});
                 }
         };
-        scale_items(R.luma, lh, lv, ITEM_SCALE_LUMA, 1);
-        scale_items(R.chroma, chh, cv, ITEM_SCALE_CHROMA, 2);
+        scale_items(R.luma, lh, lv, ITEM_SCALE_LUMA, 1, class_l);
+        scale_items(R.chroma, chh, cv, ITEM_SCALE_CHROMA, 2, class_c);
     }
     std::stable_sort(ordered.begin(), ordered.end(), [](const Sortable &a, const Sortable &b) { return a.band < b.band; });
     for (const Sortable &so : ordered) plan->items.push_back(so.it);

@@ -30,10 +30,11 @@ struct Plan {
     RungLayout layout[kMaxRungSlots];
     PlanDev host_copy{};                               // what was uploaded (device pointers inside)
     PlanDev *dev = nullptr;
-    std::vector<Item> items;                           // chan = 0; rung slots only, ordered by source row band
+    std::vector<Item> items;                           // chan = 0; rung tiles inside the double-buffer budget, ordered by source row band
+    std::vector<Item> big_items;                       // rung tiles of very steep / long filters: own (larger) launch
     std::vector<Item> thumb_items;                     // the thumbnail slot's items (launched only when due)
-    // shared-memory region maxima (bytes) over the tiles of the two launches: [0] rung items, [1] thumbnail items
-    int src_max[2] = {0, 0}, mid_max[2] = {0, 0}, vc_max[2] = {0, 0};
+    // shared-memory region maxima (bytes) over the tiles of the launch classes: [0] items, [1] big_items, [2] thumbnail
+    int src_max[3] = {0, 0, 0}, mid_max[3] = {0, 0, 0}, vc_max[3] = {0, 0, 0};
     std::vector<void *> allocations;                   // device memory owned by the plan
     ~Plan();
 };

@@ -138,15 +138,15 @@ struct ottgpu_batch {
     int gpu = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;                // host frames are uploaded here while the previous step computes
-    Item *d_items = nullptr;
-    int n_items = 0, max_thumb_items = 0;
-    int src_max[2] = {0, 0}, mid_max[2] = {0, 0}, vc_max[2] = {0, 0};   // [0] rung launch, [1] thumbnail launch
+    Item *d_items = nullptr, *d_big_items = nullptr;   // static per batch: every channel's plan items, chan filled in
+    int n_items = 0, n_big_items = 0, max_thumb_items = 0;
+    int src_max[3] = {0, 0, 0}, mid_max[3] = {0, 0, 0}, vc_max[3] = {0, 0, 0};   // launch classes: rung, big-tile rung, thumbnail
     // Descriptors are double-buffered so that an ASYNC submit can be prepared while the previous step still runs.
     struct Set {
         Binding *h_binds = nullptr, *d_binds = nullptr;    // pinned / device
         YadifJob *h_jobs = nullptr, *d_jobs = nullptr;
         Item *h_thumb_items = nullptr, *d_thumb_items = nullptr;
-        int *d_counters = nullptr;                          // [0] rung launch, [1] thumbnail launch tile schedulers
+        int *d_counters = nullptr;                          // tile schedulers of the three launch classes
         cudaEvent_t done = nullptr, uploaded = nullptr, k0 = nullptr, k1 = nullptr, y0 = nullptr, y1 = nullptr;
         bool in_flight = false, timed = false, timed_yadif = false;
     } set[2];
@@ -388,8 +388,8 @@ int ottgpu_channel_describe(const ottgpu_channel *ch, char *buf, size_t size)
     char line[512];
     int db = 0;
     const size_t smem = ladder_smem_bytes(p.src_max[0], p.mid_max[0], p.vc_max[0], &db);
-    snprintf(line, sizeof line, "source %dx%d fmt %d, %d rung slot(s), %zu work items/frame (+%zu thumbnail), shared memory %zu B (%s), regions src %d mid %d vc %d\n",
-             p.cfg.src_width, p.cfg.src_height, p.cfg.src_fmt, p.n_slots, p.items.size(), p.thumb_items.size(), smem,
+    snprintf(line, sizeof line, "source %dx%d fmt %d, %d rung slot(s), %zu work items/frame (+%zu big-tile, +%zu thumbnail), shared memory %zu B (%s), regions src %d mid %d vc %d\n",
+             p.cfg.src_width, p.cfg.src_height, p.cfg.src_fmt, p.n_slots, p.items.size(), p.big_items.size(), p.thumb_items.size(), smem,
              db ? "double-buffered" : "single buffer", p.src_max[0], p.mid_max[0], p.vc_max[0]);
     out += line;
     for (int s = 0; s < p.n_slots; ++s) {
@@ -469,11 +469,12 @@ int ottgpu_batch_create(ottgpu_channel **channels, int n, ottgpu_batch **out)
     }
     if (n > 1) channels[0]->own_stream = false;
     CK(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
-    std::vector<Item> all;
+    std::vector<Item> all, big;
     for (int i = 0; i < n; ++i) {
         const Plan &p = *channels[i]->plan;
         for (Item it : p.items) { it.chan = (uint16_t)i; all.push_back(it); }
-        for (int k = 0; k < 2; ++k) {
+        for (Item it : p.big_items) { it.chan = (uint16_t)i; big.push_back(it); }
+        for (int k = 0; k < 3; ++k) {
             b->src_max[k] = std::max(b->src_max[k], p.src_max[k]);
             b->mid_max[k] = std::max(b->mid_max[k], p.mid_max[k]);
             b->vc_max[k] = std::max(b->vc_max[k], p.vc_max[k]);
@@ -483,6 +484,9 @@ int ottgpu_batch_create(ottgpu_channel **channels, int n, ottgpu_batch **out)
     b->n_items = (int)all.size();
     CK(cudaMalloc((void **)&b->d_items, std::max<size_t>(all.size(), 1) * sizeof(Item)));
     if (!all.empty()) CK(cudaMemcpy(b->d_items, all.data(), all.size() * sizeof(Item), cudaMemcpyHostToDevice));
+    b->n_big_items = (int)big.size();
+    CK(cudaMalloc((void **)&b->d_big_items, std::max<size_t>(big.size(), 1) * sizeof(Item)));
+    if (!big.empty()) CK(cudaMemcpy(b->d_big_items, big.data(), big.size() * sizeof(Item), cudaMemcpyHostToDevice));
     for (ottgpu_batch::Set &st : b->set) {
         CK(cudaMalloc((void **)&st.d_thumb_items, std::max(b->max_thumb_items, 1) * sizeof(Item)));
         CK(cudaMallocHost((void **)&st.h_thumb_items, std::max(b->max_thumb_items, 1) * sizeof(Item)));
@@ -490,7 +494,7 @@ int ottgpu_batch_create(ottgpu_channel **channels, int n, ottgpu_batch **out)
         CK(cudaMallocHost((void **)&st.h_binds, n * sizeof(Binding)));
         CK(cudaMalloc((void **)&st.d_jobs, n * sizeof(YadifJob)));
         CK(cudaMallocHost((void **)&st.h_jobs, n * sizeof(YadifJob)));
-        CK(cudaMalloc((void **)&st.d_counters, 2 * sizeof(int)));
+        CK(cudaMalloc((void **)&st.d_counters, 3 * sizeof(int)));
         CK(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&st.uploaded, cudaEventDisableTiming));
         CK(cudaEventCreate(&st.k0));
@@ -512,6 +516,7 @@ void ottgpu_batch_destroy(ottgpu_batch *b)
         cudaStreamDestroy(b->copy_stream);
     }
     cudaFree(b->d_items);
+    cudaFree(b->d_big_items);
     for (ottgpu_batch::Set &st : b->set) {
         cudaFree(st.d_thumb_items);
         cudaFree(st.d_binds);
@@ -794,7 +799,7 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
         L.double_buffer = 0;                             // decided by launch_ladder from the shared-memory budget
         return L;
     };
-    if ((live && b->n_items) || n_thumb_items) CK(cudaMemsetAsync(st.d_counters, 0, 2 * sizeof(int), s));
+    if ((live && (b->n_items || b->n_big_items)) || n_thumb_items) CK(cudaMemsetAsync(st.d_counters, 0, 3 * sizeof(int), s));
     if (live && b->n_items) {
         if (b->timing) CK(cudaEventRecord(st.k0, s));
         CK(launch_ladder(make_launch(b->d_items, b->n_items, 0), s));
@@ -805,9 +810,14 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
         b->last_launches++;
         b->last_items += b->n_items;
     }
+    if (live && b->n_big_items) {
+        CK(launch_ladder(make_launch(b->d_big_items, b->n_big_items, 1), s));
+        b->last_launches++;
+        b->last_items += b->n_big_items;
+    }
     if (n_thumb_items) {
         CK(cudaMemcpyAsync(st.d_thumb_items, st.h_thumb_items, n_thumb_items * sizeof(Item), cudaMemcpyHostToDevice, s));
-        CK(launch_ladder(make_launch(st.d_thumb_items, n_thumb_items, 1), s));
+        CK(launch_ladder(make_launch(st.d_thumb_items, n_thumb_items, 2), s));
         b->last_launches++;
         b->last_items += n_thumb_items;
     }
