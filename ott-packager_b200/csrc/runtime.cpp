@@ -234,7 +234,7 @@ int frame_tensor_maps(ottgpu_channel *c, const uint8_t *base, cudaStream_t strea
         slot = &c->maps[0];
         for (auto &m : c->maps)
             if (m.stamp < slot->stamp) slot = &m;
-        CK(cudaStreamSynchronize(stream));             // a launch in flight may still read the evicted set
+        CK(cudaDeviceSynchronize());                   // rare: a launch in flight (any stream) may still read the evicted set
     }
     alignas(64) static thread_local CUtensorMap host[kMaxRungSlots * 3];
     std::memset(host, 0, sizeof(host));
@@ -740,7 +740,7 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
         }
         plane_ptrs(cfg.src_fmt, src_base, cfg.src_width, cfg.src_height, bind.src, bind.src_pitch);
         {
-            int rc = frame_tensor_maps(c, src_base, s, &bind.tmaps);
+            int rc = frame_tensor_maps(c, src_base, in[i].mem == OTTGPU_MEM_HOST ? b->copy_stream : s, &bind.tmaps);
             if (rc) return rc;
         }
         bind.active = 1;
@@ -772,13 +772,17 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
     }
 
     // ---- 5. enqueue: descriptors, yadif, ladder, thumbnails, read-backs
+    // With host frames in flight the small descriptor copies ride on the copy stream behind this step's uploads:
+    // on the compute stream they would queue behind the NEXT step's bulk uploads in the H2D copy engine.
+    cudaStream_t ds = uploads ? b->copy_stream : s;
+    CK(cudaMemcpyAsync(st.d_binds, st.h_binds, n * sizeof(Binding), cudaMemcpyHostToDevice, ds));
+    if (n_jobs) CK(cudaMemcpyAsync(st.d_jobs, st.h_jobs, n * sizeof(YadifJob), cudaMemcpyHostToDevice, ds));
+    if (n_thumb_items) CK(cudaMemcpyAsync(st.d_thumb_items, st.h_thumb_items, n_thumb_items * sizeof(Item), cudaMemcpyHostToDevice, ds));
     if (uploads) {
         CK(cudaEventRecord(st.uploaded, b->copy_stream));
         CK(cudaStreamWaitEvent(s, st.uploaded, 0));
     }
-    CK(cudaMemcpyAsync(st.d_binds, st.h_binds, n * sizeof(Binding), cudaMemcpyHostToDevice, s));
     if (n_jobs) {
-        CK(cudaMemcpyAsync(st.d_jobs, st.h_jobs, n * sizeof(YadifJob), cudaMemcpyHostToDevice, s));
         if (b->timing) CK(cudaEventRecord(st.y0, s));
         CK(launch_yadif(st.d_jobs, n, max_w, max_h, all_fast, s));
         if (b->timing) {
@@ -816,7 +820,6 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
         b->last_items += b->n_big_items;
     }
     if (n_thumb_items) {
-        CK(cudaMemcpyAsync(st.d_thumb_items, st.h_thumb_items, n_thumb_items * sizeof(Item), cudaMemcpyHostToDevice, s));
         CK(launch_ladder(make_launch(st.d_thumb_items, n_thumb_items, 2), s));
         b->last_launches++;
         b->last_items += n_thumb_items;
