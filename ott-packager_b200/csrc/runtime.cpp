@@ -122,7 +122,8 @@ struct ottgpu_channel {
     int slot_cooling = -1;                             // released last step, reusable from the next one
     FrameRef prev, cur, next;
     uint8_t *deint = nullptr;                          // yadif output when no rung surface can take it directly
-    uint8_t *stage[kMaxRungSlots] = {nullptr};         // device surfaces for host-destined rungs / thumbnail
+    uint8_t *stage[2][kMaxRungSlots] = {{nullptr}, {nullptr}};   // device surfaces for host-destined rungs / thumbnail,
+                                                                 // one set per descriptor set (read-back of step t overlaps step t+1)
     int thumb_count = 0;
     int direct_rung = -1;                              // rung whose surface is byte-identical to a deinterlaced frame
     ottgpu_batch *solo = nullptr;
@@ -138,6 +139,7 @@ struct ottgpu_batch {
     int gpu = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;                // host frames are uploaded here while the previous step computes
+    cudaStream_t readback_stream = nullptr;            // results for host destinations are copied back here
     Item *d_items = nullptr, *d_big_items = nullptr;   // static per batch: every channel's plan items, chan filled in
     int n_items = 0, n_big_items = 0, max_thumb_items = 0;
     int src_max[3] = {0, 0, 0}, mid_max[3] = {0, 0, 0}, vc_max[3] = {0, 0, 0};   // launch classes: rung, big-tile rung, thumbnail
@@ -147,8 +149,8 @@ struct ottgpu_batch {
         YadifJob *h_jobs = nullptr, *d_jobs = nullptr;
         Item *h_thumb_items = nullptr, *d_thumb_items = nullptr;
         int *d_counters = nullptr;                          // tile schedulers of the three launch classes
-        cudaEvent_t done = nullptr, uploaded = nullptr, k0 = nullptr, k1 = nullptr, y0 = nullptr, y1 = nullptr;
-        bool in_flight = false, timed = false, timed_yadif = false;
+        cudaEvent_t done = nullptr, uploaded = nullptr, computed = nullptr, read_back = nullptr, k0 = nullptr, k1 = nullptr, y0 = nullptr, y1 = nullptr;
+        bool in_flight = false, timed = false, timed_yadif = false, has_readback = false;
     } set[2];
     int turn = 0;
     int last_launches = 0, last_items = 0;
@@ -428,7 +430,8 @@ void ottgpu_channel_destroy(ottgpu_channel *ch)
     if (ch->solo) ottgpu_batch_destroy(ch->solo);
     for (uint8_t *p : ch->slots) cudaFree(p);
     cudaFree(ch->deint);
-    for (uint8_t *p : ch->stage) cudaFree(p);
+    for (auto &set : ch->stage)
+        for (uint8_t *p : set) cudaFree(p);
     for (auto &m : ch->maps) cudaFree(m.dev);
     if (ch->own_stream) cudaStreamDestroy(ch->stream);
     delete ch;
@@ -469,6 +472,7 @@ int ottgpu_batch_create(ottgpu_channel **channels, int n, ottgpu_batch **out)
     }
     if (n > 1) channels[0]->own_stream = false;
     CK(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&b->readback_stream, cudaStreamNonBlocking));
     std::vector<Item> all, big;
     for (int i = 0; i < n; ++i) {
         const Plan &p = *channels[i]->plan;
@@ -497,6 +501,8 @@ int ottgpu_batch_create(ottgpu_channel **channels, int n, ottgpu_batch **out)
         CK(cudaMalloc((void **)&st.d_counters, 3 * sizeof(int)));
         CK(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&st.uploaded, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&st.computed, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&st.read_back, cudaEventDisableTiming));
         CK(cudaEventCreate(&st.k0));
         CK(cudaEventCreate(&st.k1));
         CK(cudaEventCreate(&st.y0));
@@ -515,6 +521,10 @@ void ottgpu_batch_destroy(ottgpu_batch *b)
         cudaStreamSynchronize(b->copy_stream);
         cudaStreamDestroy(b->copy_stream);
     }
+    if (b->readback_stream) {
+        cudaStreamSynchronize(b->readback_stream);
+        cudaStreamDestroy(b->readback_stream);
+    }
     cudaFree(b->d_items);
     cudaFree(b->d_big_items);
     for (ottgpu_batch::Set &st : b->set) {
@@ -527,6 +537,8 @@ void ottgpu_batch_destroy(ottgpu_batch *b)
         cudaFreeHost(st.h_thumb_items);
         if (st.done) cudaEventDestroy(st.done);
         if (st.uploaded) cudaEventDestroy(st.uploaded);
+        if (st.computed) cudaEventDestroy(st.computed);
+        if (st.read_back) cudaEventDestroy(st.read_back);
         if (st.k0) cudaEventDestroy(st.k0);
         if (st.k1) cudaEventDestroy(st.k1);
         if (st.y0) cudaEventDestroy(st.y0);
@@ -546,6 +558,8 @@ int retire(ottgpu_batch *b, ottgpu_batch::Set &st)
 {
     if (!st.in_flight) return OTTGPU_OK;
     CK(cudaEventSynchronize(st.done));
+    if (st.has_readback) CK(cudaEventSynchronize(st.read_back));
+    st.has_readback = false;
     if (st.timed) {
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, st.k0, st.k1));
@@ -572,6 +586,7 @@ int ottgpu_batch_wait(ottgpu_batch *b)
     if (!b) return fail(OTTGPU_ERR_ARG, "null batch");
     CK(cudaSetDevice(b->gpu));
     CK(cudaStreamSynchronize(b->stream));
+    CK(cudaStreamSynchronize(b->readback_stream));
     for (ottgpu_batch::Set &st : b->set) {
         int rc = retire(b, st);
         if (rc) return rc;
@@ -610,7 +625,8 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
 {
     if (!b || !in || !out) return fail(OTTGPU_ERR_ARG, "null argument");
     CK(cudaSetDevice(b->gpu));
-    ottgpu_batch::Set &st = b->set[b->turn];
+    const int turn = b->turn;
+    ottgpu_batch::Set &st = b->set[turn];
     b->turn ^= 1;
     {                                                   // at most two steps in flight: this set's previous user must be done
         int rc = retire(b, st);
@@ -697,9 +713,9 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
             if (o.dst_mem[r] == OTTGPU_MEM_DEVICE) {
                 base = static_cast<uint8_t *>(o.dst[r]);
             } else {
-                int rc = ensure_dev(&c->stage[r], plan.layout[r].bytes);
+                int rc = ensure_dev(&c->stage[turn][r], plan.layout[r].bytes);
                 if (rc) return rc;
-                base = c->stage[r];
+                base = c->stage[turn][r];
                 b->readbacks.push_back({o.dst[r], base, plan.layout[r].bytes});
             }
             if (!base || (o.dst_mem[r] != OTTGPU_MEM_DEVICE && !o.dst[r])) return fail(OTTGPU_ERR_ARG, "missing destination buffer");
@@ -750,17 +766,17 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
         if (plan.thumb_slot >= 0 && ++c->thumb_count == cfg.thumb_period) {
             c->thumb_count = 0;
             const int ts = plan.thumb_slot;
-            int rc = ensure_dev(&c->stage[ts], plan.layout[ts].bytes);
+            int rc = ensure_dev(&c->stage[turn][ts], plan.layout[ts].bytes);
             if (rc) return rc;
             for (int p = 0; p < plan.layout[ts].planes; ++p) {
-                bind.dst[ts][p] = c->stage[ts] + plan.layout[ts].offset[p];
+                bind.dst[ts][p] = c->stage[turn][ts] + plan.layout[ts].offset[p];
                 bind.dst_pitch[ts][p] = plan.layout[ts].pitch[p];
             }
             bind.thumb_active = 1;
             void *host = std::malloc(plan.layout[ts].bytes);
             if (!host) return fail(OTTGPU_ERR_NOMEM, "malloc(thumbnail) failed");
             o.thumbnail = host;
-            b->readbacks.push_back({host, c->stage[ts], plan.layout[ts].bytes});
+            b->readbacks.push_back({host, c->stage[turn][ts], plan.layout[ts].bytes});
             for (Item it : plan.thumb_items) { it.chan = (uint16_t)i; st.h_thumb_items[n_thumb_items++] = it; }
         }
 
@@ -824,9 +840,16 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
         b->last_launches++;
         b->last_items += n_thumb_items;
     }
-    for (const ottgpu_batch::Readback &r : b->readbacks)
-        CK(cudaMemcpyAsync(r.host, r.dev, r.bytes, cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(st.done, s));
+    if (!b->readbacks.empty()) {
+        // results for host destinations leave on their own stream: the next step's kernels do not wait for them
+        CK(cudaEventRecord(st.computed, s));
+        CK(cudaStreamWaitEvent(b->readback_stream, st.computed, 0));
+        for (const ottgpu_batch::Readback &r : b->readbacks)
+            CK(cudaMemcpyAsync(r.host, r.dev, r.bytes, cudaMemcpyDeviceToHost, b->readback_stream));
+        CK(cudaEventRecord(st.read_back, b->readback_stream));
+        st.has_readback = true;
+    }
     st.in_flight = true;
     if (flags & OTTGPU_SUBMIT_ASYNC) return OTTGPU_OK;
     return ottgpu_batch_wait(b);
