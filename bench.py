@@ -508,9 +508,12 @@ def ours_main(args, wl, rank, world, local_rank):
     if world == 1 and not args.no_cpu:
         threads = host_cores()
         done, el, kind, _ = run_cpu_rounds(wl, base_frames, threads, seconds=args.cpu_seconds)
+        one_done, one_el, _, _ = run_cpu_rounds(wl, base_frames, 1, seconds=min(3.0, args.cpu_seconds))
         cpu = {"value": done / el, "unit": "frames/s", "cores": threads, "kind": kind,
                "sample": "%d frames of the same workload (%d rounds x %d host threads, one frame per thread per round, ~%.0f s)"
-                         % (done, done // threads, threads, el)}
+                         % (done, done // threads, threads, el),
+               "single_thread": {"value": one_done / one_el, "unit": "frames/s",
+                                 "note": "one thread = how the reference runs one channel's scaler (transvideo.c:1504)"}}
     line = {"metric": "ladder_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8" if bps == 1 else "u16 (10 significant bits)", "data": "synthetic",
