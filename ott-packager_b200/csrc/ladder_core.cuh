@@ -571,20 +571,7 @@ OTT_DEV void vrow_approx8(const mid_t *m, int step, const int16_t *cf, int vtaps
         OTT_UNROLL
         for (int k = 0; k < NV; ++k) a[k] = (int)((uint32_t)a[k] & 0xffff0000u) + t1[k] * c1;
     }
-    int j = 2;
-    for (; j + 4 <= vtaps; j += 4) {                       // four taps per trip: half the loop overhead
-        const uint32_t ca = *reinterpret_cast<const uint32_t *>(cf + j), cb = *reinterpret_cast<const uint32_t *>(cf + j + 2);
-        OTT_UNROLL
-        for (int u = 0; u < 4; ++u) {
-            const uint32_t cc = u < 2 ? ca : cb;
-            const int cj = (u & 1) ? sx_hi(cc) : sx_lo(cc);
-            int t[NV];
-            load_vals<NV>(m + (j + u) * step, t);
-            OTT_UNROLL
-            for (int k = 0; k < NV; ++k) a[k] = (int)((uint32_t)a[k] & 0xffff0000u) + t[k] * cj;
-        }
-    }
-    for (; j < vtaps; j += 2) {
+    for (int j = 2; j < vtaps; j += 2) {
         const uint32_t c2 = *reinterpret_cast<const uint32_t *>(cf + j);
         const int c0 = sx_lo(c2), c1 = sx_hi(c2);
         int t0[NV], t1[NV];
