@@ -275,3 +275,16 @@ def test_cfg4_many_channels_one_batch_full_size(real_lib, og, oracle):
     batch.close()
     for c in chans:
         c.close()
+
+
+@pytest.mark.gpu
+def test_1080p_thumbnail_slot_full_size(real_lib, og, oracle):
+    """The thumbnail launch class at the reference's real geometry (1080p -> 176x144, transvideo.c:2155-2174): its tiles do
+    not fit the double-buffered budget, so this runs the single-buffer TMA path of the kernel."""
+    w, h = 1920, 1080
+    ch = og.Channel(real_lib, og.make_cfg(w, h, [(1280, 720, og.FMT_NV12, 256)], deint=og.DEINT_BYPASS, thumb=(176, 144, 1)))
+    for seed in (3, 4):
+        f = natural_i420(w, h, 7, shift=seed) if seed == 3 else noise_i420(w, h, seed)
+        r = ch.submit(f)
+        assert np.array_equal(r["thumbnail"], oracle.scale_i420(f, w, h, 176, 144))
+    ch.close()
