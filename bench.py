@@ -281,6 +281,9 @@ def ours_main(args, wl, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        # keep stdout to the single JSON line: NCCL prints its version banner there at VERSION/INFO level
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = og.Library()
