@@ -116,10 +116,10 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
                 if (g.bulk_ok) {
                     if (lane == 0) {
                         fence_proxy_async();                   // the buffer was last read through the generic proxy
-                        mbar_expect_tx(&ready[slot], (uint32_t)(g.nplanes * g.box_bytes));
+                        mbar_expect_tx(&ready[slot], (uint32_t)(g.staged_planes * g.box_bytes));
                         unsigned char *dst = smem + g.off_src;
-                        tma_box_2d(dst, g.tmap0, g.sx0 >> 2, g.sy0, &ready[slot]);
-                        if (g.nplanes == 2) tma_box_2d(dst + g.plane_stride, g.tmap1, g.sx0 >> 2, g.sy0, &ready[slot]);
+                        tma_box_2d(dst, g.tmap0, g.tma_x, g.sy0, &ready[slot]);
+                        if (g.staged_planes == 2) tma_box_2d(dst + g.plane_stride, g.tmap1, g.tma_x, g.sy0, &ready[slot]);
                     }
                 } else if (lane == 0) {
                     mbar_arrive(&ready[slot]);                 // compute warps stage this tile through registers
@@ -145,8 +145,12 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
         if (what == 2) {
             item_copy(tid, L.items[idx], L.binds[L.items[idx].chan]);
         } else if (what == 1) {
-            if (!g.bulk_ok) {                      // unaligned / 16-bit sources: staged through registers by the compute warps
+            if (!g.bulk_ok) {                      // unaligned planes: staged through registers by the compute warps
                 phase_stage(tid, g, smem);
+                compute_sync();
+            }
+            if (g.src_shift) {                     // P010: right-align the 10 significant bits in place
+                phase_fixup16(tid, g, smem);
                 compute_sync();
             }
             phase_hpass(tid, g, smem);

@@ -51,6 +51,8 @@ inline uint32_t ott_dp2a_uu(uint32_t a, uint32_t b, uint32_t c, int hi)
 template <typename T> inline T ott_ldg(const T *p) { return *p; }
 inline int ott_sad(int a, int b, int c) { return (a > b ? a - b : b - a) + c; }
 inline int ott_byte(uint32_t w, int i) { return (int)((w >> (8 * i)) & 0xffu); }
+inline uint32_t ott_lo16x2(uint32_t a, uint32_t b) { return (a & 0xffffu) | (b << 16); }          // (a.lo, b.lo)
+inline uint32_t ott_hi16x2(uint32_t a, uint32_t b) { return (a >> 16) | (b & 0xffff0000u); }     // (a.hi, b.hi)
 }  // namespace ottgpu
 #else
 #define OTT_DEV __device__ __forceinline__
@@ -81,6 +83,8 @@ OTT_DEV uint32_t ott_dp2a_uu(uint32_t a, uint32_t b, uint32_t c, int hi)
 template <typename T> OTT_DEV T ott_ldg(const T *p) { return __ldg(p); }
 OTT_DEV int ott_sad(int a, int b, int c) { return (int)__sad(a, b, (unsigned)c); }   // |a-b|+c in one VABSDIFF
 OTT_DEV int ott_byte(uint32_t w, int i) { return (int)__byte_perm(w, 0, 0x4440 | i); }   // one PRMT instead of shift+mask
+OTT_DEV uint32_t ott_lo16x2(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x5410); }
+OTT_DEV uint32_t ott_hi16x2(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x7632); }
 }  // namespace ottgpu
 #endif
 
@@ -111,7 +115,10 @@ struct TileGeom {
     const unsigned char *tmap0, *tmap1;   // tensor maps of the plane(s)
     const uint8_t *src0, *src1;      // plane bases (chroma: U,V or the interleaved UV plane twice)
     int src_pitch0, src_pitch1;      // bytes
-    int src_interleaved;     // chroma samples interleaved in the source (P010)
+    int src_interleaved;     // chroma samples interleaved in the source (P010): staged as ONE plane of (U,V) words
+    int staged_planes;       // planes in the staged window (1 for luma and for interleaved chroma, else 2)
+    int px_bytes;            // bytes per staged sample position: 1 (8-bit), 2 (16-bit), 4 (interleaved 16-bit pair)
+    int tma_x;               // TMA box x coordinate in 32-bit elements
     int src_shift;           // 6 for P010 (MSB aligned), else 0
     uint8_t *dst0, *dst1;
     int dst_pitch0, dst_pitch1;
@@ -161,50 +168,18 @@ OTT_DEV uint32_t shift_mask16(uint32_t v, int shift) { return (v >> shift) & ((0
 
 OTT_DEV void phase_stage(int tid, const TileGeom &g, unsigned char *smem)
 {
+    // Register path (planes that are not 16-byte aligned): RAW bytes, same layout the TMA box produces; P010's >>6 is
+    // applied afterwards by phase_fixup16 on both paths.
     const PlaneTables &T = *g.T;
     uint32_t *src_s = reinterpret_cast<uint32_t *>(smem + g.off_src);
     // lanes per staged row: smallest power of two >= nvec (capped at 32)
     int lpr_log2 = 0;
     while ((1 << lpr_log2) < g.nvec && lpr_log2 < 5) ++lpr_log2;
     const int lpr = 1 << lpr_log2, v0 = tid & (lpr - 1), r0 = tid >> lpr_log2, rstep = kThreads >> lpr_log2;
-    if (g.src_interleaved) {
-        // P010 chroma: one 16-byte vector = 4 (U,V) pairs -> 4 U samples + 4 V samples (8 bytes each plane).
-        // g.sx0 counts chroma samples (multiple of 8); staged vectors hold 8 samples, i.e. two global vectors.
-        const int row_bytes = T.srcW * 4;
-        for (int r = r0; r < g.sr; r += rstep) {
-            const uint8_t *row = g.src0 + (size_t)(g.sy0 + r) * g.src_pitch0;
-            uint32_t *su = src_s + (r * g.spw), *sv = src_s + (g.plane_stride >> 2) + (r * g.spw);
-            for (int v = v0; v < g.nvec; v += lpr) {
-                const int bx = (g.sx0 + 8 * v) * 4;
-                uint4 a, b;
-                if ((((uintptr_t)row & 15) == 0) && bx + 32 <= row_bytes) {
-                    a = ott_ldg(reinterpret_cast<const uint4 *>(row + bx));
-                    b = ott_ldg(reinterpret_cast<const uint4 *>(row + bx + 16));
-                } else {
-                    a = load_vec_slow(row, bx, row_bytes);
-                    b = load_vec_slow(row, bx + 16, row_bytes);
-                }
-                const uint32_t in[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-                uint32_t u[4], w[4];
-                OTT_UNROLL
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t p = shift_mask16(in[2 * k], g.src_shift), q = shift_mask16(in[2 * k + 1], g.src_shift);
-                    u[k] = (p & 0xffffu) | (q << 16);
-                    w[k] = (p >> 16) | (q & 0xffff0000u);
-                }
-                uint4 ou, ov;
-                ou.x = u[0]; ou.y = u[1]; ou.z = u[2]; ou.w = u[3];
-                ov.x = w[0]; ov.y = w[1]; ov.z = w[2]; ov.w = w[3];
-                reinterpret_cast<uint4 *>(su)[v] = ou;
-                reinterpret_cast<uint4 *>(sv)[v] = ov;
-            }
-        }
-        return;
-    }
-    const int bps = g.bps, sshift = g.src_shift, sr = g.sr, sy0 = g.sy0, spw = g.spw, nvec = g.nvec, nplanes = g.nplanes;
-    const int row_bytes = T.srcW * bps;
-    const int bx0 = g.sx0 * bps;
-    for (int p = 0; p < nplanes; ++p) {
+    const int sr = g.sr, sy0 = g.sy0, spw = g.spw, nvec = g.nvec, planes = g.staged_planes;
+    const int row_bytes = T.srcW * g.px_bytes;
+    const int bx0 = g.sx0 * g.px_bytes;
+    for (int p = 0; p < planes; ++p) {
         const uint8_t *base = p ? g.src1 : g.src0;
         const int pitch = p ? g.src_pitch1 : g.src_pitch0;
         const bool aligned = (((uintptr_t)base | (uintptr_t)pitch) & 15) == 0;
@@ -213,16 +188,34 @@ OTT_DEV void phase_stage(int tid, const TileGeom &g, unsigned char *smem)
             uint4 *srow = reinterpret_cast<uint4 *>(src_s + p * (g.plane_stride >> 2) + r * spw);
             for (int v = v0; v < nvec; v += lpr) {
                 const int bx = bx0 + 16 * v;
-                uint4 q = (aligned && bx + 16 <= row_bytes) ? ott_ldg(reinterpret_cast<const uint4 *>(row + bx))
+                srow[v] = (aligned && bx + 16 <= row_bytes) ? ott_ldg(reinterpret_cast<const uint4 *>(row + bx))
                                                             : load_vec_slow(row, bx, row_bytes);
-                if (bps == 2 && sshift) {
-                    q.x = shift_mask16(q.x, sshift); q.y = shift_mask16(q.y, sshift);
-                    q.z = shift_mask16(q.z, sshift); q.w = shift_mask16(q.w, sshift);
-                }
-                srow[v] = q;
             }
         }
     }
+}
+
+// P010 keeps its 10 significant bits in the upper part of each 16-bit sample: right-align them in place (both halves of
+// every staged word, i.e. two luma samples or one (U,V) pair) before the H pass reads the window.
+OTT_DEV void phase_fixup16(int tid, const TileGeom &g, unsigned char *smem)
+{
+    const int shift = g.src_shift;
+    if (!shift) return;
+    uint32_t *src_s = reinterpret_cast<uint32_t *>(smem + g.off_src);
+    int lpr_log2 = 0;
+    while ((1 << lpr_log2) < g.nvec && lpr_log2 < 5) ++lpr_log2;
+    const int lpr = 1 << lpr_log2, v0 = tid & (lpr - 1), r0 = tid >> lpr_log2, rstep = kThreads >> lpr_log2;
+    const int sr = g.sr, spw = g.spw, nvec = g.nvec;
+    for (int p = 0; p < g.staged_planes; ++p)
+        for (int r = r0; r < sr; r += rstep) {
+            uint4 *srow = reinterpret_cast<uint4 *>(src_s + p * (g.plane_stride >> 2) + r * spw);
+            for (int v = v0; v < nvec; v += lpr) {
+                uint4 q = srow[v];
+                q.x = shift_mask16(q.x, shift); q.y = shift_mask16(q.y, shift);
+                q.z = shift_mask16(q.z, shift); q.w = shift_mask16(q.w, shift);
+                srow[v] = q;
+            }
+        }
 }
 
 // ------------------------------------------------------------------------------------------------ phase 2: H pass
@@ -371,6 +364,72 @@ OTT_DEV void hpass16(int tid, const TileGeom &g, unsigned char *smem)
     }
 }
 
+// Interleaved 16-bit chroma (P010): every staged word is one (U,V) pair, so both planes read the same rows and the pair
+// of samples a dp2a needs is one PRMT of two neighbouring words (low halves = U, high halves = V); no alignment shift.
+template <int HQ>
+OTT_DEV int hdot16il(const uint32_t *w, int plane, const uint32_t (&hi)[HQ], const uint32_t (&lo)[HQ])
+{
+    int ahi = 0;
+    uint32_t alo = 0;
+    OTT_UNROLL
+    for (int q = 0; q < HQ; ++q) {
+        const uint32_t w0 = w[4 * q], w1 = w[4 * q + 1], w2 = w[4 * q + 2], w3 = w[4 * q + 3];
+        const uint32_t a0 = plane ? ott_hi16x2(w0, w1) : ott_lo16x2(w0, w1);
+        const uint32_t a1 = plane ? ott_hi16x2(w2, w3) : ott_lo16x2(w2, w3);
+        ahi = ott_dp2a_us(a0, hi[q], ahi, 0);
+        ahi = ott_dp2a_us(a1, hi[q], ahi, 1);
+        alo = ott_dp2a_uu(a0, lo[q], alo, 0);
+        alo = ott_dp2a_uu(a1, lo[q], alo, 1);
+    }
+    return ott_min((ahi * 256 + (int)alo) >> 9, 32767);
+}
+
+template <int HQ>
+OTT_DEV void hpass16il(int tid, const TileGeom &g, unsigned char *smem)
+{
+    const PlaneTables &T = *g.T;
+    const int col = tid & (T.tw - 1), grp = tid >> g.tw_log2, ngroups = kThreads >> g.tw_log2;
+    if (col >= g.tw) return;
+    const int gx = g.x0 + col;
+    const int off = ott_ldg(T.hpos + gx) - g.sx0;            // in samples = staged words
+    uint32_t hi[HQ], lo[HQ];
+    OTT_UNROLL
+    for (int q = 0; q < HQ; ++q) {
+        hi[q] = ott_ldg(T.hc_hi + gx * HQ + q);
+        lo[q] = ott_ldg(T.hc_lo + gx * HQ + q);
+    }
+    const int sr = g.sr, spw = g.spw, mp = g.mid_pitch;
+    const uint32_t *src_s = reinterpret_cast<const uint32_t *>(smem + g.off_src) + off;
+    mid_t *mid_s = reinterpret_cast<mid_t *>(smem + g.off_mid) + col;
+    for (int row = grp; row < 2 * sr; row += ngroups) {      // rows 0..sr-1 -> U, sr..2sr-1 -> V
+        const int p = row >= sr, r = row - p * sr;
+        mid_s[row * mp] = (mid_t)hdot16il<HQ>(src_s + r * spw, p, hi, lo);
+    }
+}
+
+OTT_DEV void hpass16il_any(int tid, const TileGeom &g, unsigned char *smem)
+{
+    const PlaneTables &T = *g.T;
+    const int col = tid & (T.tw - 1), grp = tid >> g.tw_log2, ngroups = kThreads >> g.tw_log2;
+    if (col >= g.tw) return;
+    const int gx = g.x0 + col, taps = 4 * T.hq;
+    const int off = ott_ldg(T.hpos + gx) - g.sx0;
+    const int16_t *pc = T.hc16 + gx * taps;
+    const int sr = g.sr, spw = g.spw, mp = g.mid_pitch;
+    const uint32_t *src_s = reinterpret_cast<const uint32_t *>(smem + g.off_src) + off;
+    mid_t *mid_s = reinterpret_cast<mid_t *>(smem + g.off_mid) + col;
+    for (int row = grp; row < 2 * sr; row += ngroups) {
+        const int p = row >= sr, r = row - p * sr;
+        const uint32_t *w = src_s + r * spw;
+        int acc = 0;
+        for (int k = 0; k < taps; ++k) {
+            const uint32_t v = w[k];
+            acc += (int)(p ? v >> 16 : v & 0xffffu) * ott_ldg(pc + k);
+        }
+        mid_s[row * mp] = (mid_t)ott_min(acc >> 9, 32767);
+    }
+}
+
 OTT_DEV void hpass16_any(int tid, const TileGeom &g, unsigned char *smem)
 {
     const PlaneTables &T = *g.T;
@@ -410,6 +469,19 @@ OTT_DEV void phase_hpass(int tid, const TileGeom &g, unsigned char *smem)
         case 5: hpass8<5>(tid, g, smem); break;
         case 6: hpass8<6>(tid, g, smem); break;
         default: hpass8_any(tid, g, smem); break;
+        }
+    } else if (g.src_interleaved) {
+        switch (hq) {
+        case 1: hpass16il<1>(tid, g, smem); break;
+        case 2: hpass16il<2>(tid, g, smem); break;
+        case 3: hpass16il<3>(tid, g, smem); break;
+        case 4: hpass16il<4>(tid, g, smem); break;
+        case 5: hpass16il<5>(tid, g, smem); break;
+        case 6: hpass16il<6>(tid, g, smem); break;
+        case 7: hpass16il<7>(tid, g, smem); break;
+        case 8: hpass16il<8>(tid, g, smem); break;
+        case 9: hpass16il<9>(tid, g, smem); break;
+        default: hpass16il_any(tid, g, smem); break;
         }
     } else {
         switch (hq) {
@@ -811,10 +883,13 @@ OTT_DEV int item_prepare(const Item &it, const Binding &b, const LadderLaunch &L
         g.dst1 = dst_il ? nullptr : b.dst[it.slot][2]; g.dst_pitch1 = dst_il ? 0 : b.dst_pitch[it.slot][2];
         g.dst_interleaved = dst_il;
     }
+    g.staged_planes = (luma || src_il) ? 1 : 2;
+    g.px_bytes = (!luma && src_il) ? 4 : plan.bps;
+    g.tma_x = g.sx0 * g.px_bytes / 4;
     // one staged plane occupies sr_max rows of spw words, padded to the 128 bytes a TMA destination must be aligned to
     g.plane_stride = (T.sr_max * T.sw_words * 4 + 127) & ~127;
-    // TMA staging: the host supplied tensor maps for this frame (8-bit planar source, 16-byte aligned planes) and the
-    // tile window fits one box; otherwise the compute warps stage the window through registers
+    // TMA staging: the host supplied tensor maps for this frame (16-byte aligned planes) and the tile window fits one
+    // box; otherwise the compute warps stage the window through registers
     g.bulk_ok = T.tma_ok && b.tmaps != nullptr;
     g.box_bytes = T.sr_max * T.sw_words * 4;
     g.tmap0 = b.tmaps + (size_t)(it.slot * 3 + (luma ? 0 : 1)) * kTensorMapBytes;

@@ -95,10 +95,10 @@ const T *upload(Plan &plan, const std::vector<T> &v, std::string &err)
 struct TileRegions { size_t src, mid, vc; };
 
 // must match item_prepare() in ladder_core.cuh
-TileRegions tile_regions(int nplanes, int sr_max, int sw_words, int tw, int th, int vtaps)
+TileRegions tile_regions(int nplanes, int staged_planes, int sr_max, int sw_words, int tw, int th, int vtaps)
 {
     TileRegions r;
-    r.src = (size_t)nplanes * (((size_t)sr_max * sw_words * 4 + 127) & ~(size_t)127);   // planes 128-byte aligned (TMA)
+    r.src = (size_t)staged_planes * (((size_t)sr_max * sw_words * 4 + 127) & ~(size_t)127);   // planes 128-byte aligned (TMA)
     r.mid = (size_t)nplanes * (sr_max + 1) * tw * sizeof(mid_t);         // tw is 32 or 64 -> multiple of 16
     r.vc = (((size_t)th * vtaps * 2 + 3) & ~(size_t)3) + (size_t)th * 4;
     r.vc = (r.vc + 15) & ~(size_t)15;
@@ -106,7 +106,7 @@ TileRegions tile_regions(int nplanes, int sr_max, int sw_words, int tw, int th, 
 }
 
 // Builds tables + tiling for one plane kind of one rung.  Host vectors are kept in `keep` only long enough to upload.
-bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int dstH, int bps, int nplanes, int filter,
+bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int dstH, int bps, int px_bytes, int nplanes, int filter,
                  int target, int exact_from, TileRegions &regions, bool &soft_out, std::vector<int32_t> &hpos_out,
                  std::vector<int32_t> &vpos_out, std::string &err)
 {
@@ -132,7 +132,11 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
     T.hq = hq;
     T.vtaps = v.taps;
     T.exact_from = exact_from;
-    const int spv = 16 / bps;                                    // samples per 16-byte staging vector
+    // px_bytes = bytes per staged sample position: bps for planar samples, 4 for P010's interleaved (U,V) pairs, which are
+    // staged as ONE plane of 32-bit words
+    const int spv = 16 / px_bytes;                               // sample positions per 16-byte staging vector
+    const int slack = 4 / px_bytes > 0 ? 4 / px_bytes : 1;       // one 32-bit word of read-ahead for the funnel shift
+    const int staged_planes = px_bytes == 4 ? 1 : nplanes;
     const int row_quant = 8;                                     // tile heights are multiples of 8 (a V sweep covers 32 rows)
     auto rows_needed = [&](int th) {
         int m = 0;
@@ -153,7 +157,7 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
         for (int tx = 0; tx < tiles_x; ++tx) {
             const int x0 = tx * tw, x1 = std::min(x0 + tw, dstW) - 1;
             const int s0 = h.pos[x0] & ~(spv - 1), s1 = h.pos[x1] + taps4;
-            nvec = std::max(nvec, (s1 - s0 + 4 / bps + spv - 1) / spv);    // + one word of funnel-shift slack
+            nvec = std::max(nvec, (s1 - s0 + slack + spv - 1) / spv);
         }
         return nvec * 4;
     };
@@ -172,7 +176,7 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
     auto best_for = [&](int tw) {
         Shape sh{tw, row_quant, tw == 64 ? 8 : 4, staged_words(tw), 0, 1e30, false, false};
         auto fits = [&](int th, bool hard) {
-            const TileRegions r = tile_regions(nplanes, rows_needed(th), sh.sw_words, tw, th, v.taps);
+            const TileRegions r = tile_regions(nplanes, staged_planes, rows_needed(th), sh.sw_words, tw, th, v.taps);
             return hard ? r.src + r.mid + r.vc + 16 <= kSmemHardLimit : (r.src <= kSrcCap && r.mid <= kMidCap);
         };
         // tallest tile inside the caps (measured better than minimising the modelled cost over all heights: per-tile
@@ -220,9 +224,9 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
     T.sr_max = best.sr_max;
     T.tiles_x = (dstW + T.tw - 1) / T.tw;
     T.tiles_y = (dstH + T.th - 1) / T.th;
-    // one TMA box per plane: inner dimension <= 256 32-bit elements, <= 256 rows; 8-bit planar sources only
-    T.tma_ok = bps == 1 && T.sw_words <= 256 && T.sr_max <= 256 && srcW % 4 == 0;
-    regions = tile_regions(nplanes, T.sr_max, T.sw_words, T.tw, T.th, v.taps);
+    // one TMA box per staged plane: inner dimension <= 256 32-bit elements, <= 256 rows, rows a whole number of words
+    T.tma_ok = T.sw_words <= 256 && T.sr_max <= 256 && (srcW * px_bytes) % 4 == 0;
+    regions = tile_regions(nplanes, staged_planes, T.sr_max, T.sw_words, T.tw, T.th, v.taps);
     hpos_out = h.pos;
     vpos_out = v.pos;
 
@@ -351,8 +355,8 @@ std::shared_ptr<Plan> get_plan(const ottgpu_cfg &cfg_in, std::string &err)
         TileRegions rl, rc2;
         bool soft_l = true, soft_c = true;
         std::vector<int32_t> lh, lv, chh, cv;
-        if (!build_plane(*plan, R.luma, cfg.src_width, cfg.src_height, rc.width, rc.height, bps, 1, filt, cfg.target, luma_exact, rl, soft_l, lh, lv, err)) return nullptr;
-        if (!build_plane(*plan, R.chroma, scw, sch, dcw, dch, bps, 2, filt, cfg.target, chroma_exact, rc2, soft_c, chh, cv, err)) return nullptr;
+        if (!build_plane(*plan, R.luma, cfg.src_width, cfg.src_height, rc.width, rc.height, bps, bps, 1, filt, cfg.target, luma_exact, rl, soft_l, lh, lv, err)) return nullptr;
+        if (!build_plane(*plan, R.chroma, scw, sch, dcw, dch, bps, cfg.src_fmt == OTTGPU_FMT_P010 ? 4 : bps, 2, filt, cfg.target, chroma_exact, rc2, soft_c, chh, cv, err)) return nullptr;
         // launch class per plane kind: 0 = inside the double-buffer budget, 1 = big tiles, 2 = thumbnail
         const int class_l = is_thumb ? 2 : (soft_l ? 0 : 1), class_c = is_thumb ? 2 : (soft_c ? 0 : 1);
         auto account = [&](int cls, const TileRegions &r) {
@@ -364,8 +368,9 @@ std::shared_ptr<Plan> get_plan(const ottgpu_cfg &cfg_in, std::string &err)
         account(class_c, rc2);
         // tile geometry resolved here once (the kernel only loads it); items are ordered by the first source row each
         // tile reads, so tiles of different rungs over the same band run together and share the source through L2
-        const int spv = 16 / bps;
         auto scale_items = [&](const PlaneTables &T, const std::vector<int32_t> &hp, const std::vector<int32_t> &vp, uint8_t kind, int band_scale, int cls) {
+            const int pxb = (kind == ITEM_SCALE_CHROMA && cfg.src_fmt == OTTGPU_FMT_P010) ? 4 : bps;
+            const int spv = 16 / pxb, slack = 4 / pxb > 0 ? 4 / pxb : 1;
             for (int ty = 0; ty < T.tiles_y; ++ty)
                 for (int tx = 0; tx < T.tiles_x; ++tx) {
                     Item it;
@@ -378,7 +383,7 @@ std::shared_ptr<Plan> get_plan(const ottgpu_cfg &cfg_in, std::string &err)
                     const int sx0 = hp[x0] & ~(spv - 1), last = hp[x0 + tw - 1] + 4 * T.hq;
                     it.x0 = (uint16_t)x0; it.y0 = (uint16_t)y0; it.tw = (uint16_t)tw; it.th = (uint16_t)th;
                     it.sy0 = (uint16_t)sy0; it.sr = (uint16_t)sr; it.sx0 = (uint16_t)sx0;
-                    it.nvec = (uint16_t)((last - sx0 + 4 / bps + spv - 1) / spv);     // + one word of funnel-shift slack
+                    it.nvec = (uint16_t)((last - sx0 + slack + spv - 1) / spv);       // + one word of funnel-shift slack
                     if (cls == 2) plan->thumb_items.push_back(it);
                     else if (cls == 1) plan->big_items.push_back(it);
                     else ordered.push_back({it, band_scale * sy0});

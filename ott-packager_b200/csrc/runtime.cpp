@@ -213,7 +213,7 @@ int frame_tensor_maps(ottgpu_channel *c, const uint8_t *base, cudaStream_t strea
     const uint8_t *pl[3];
     int pitch[3];
     plane_ptrs(cfg.src_fmt, base, cfg.src_width, cfg.src_height, pl, pitch);
-    for (int k = 0; k < 3; ++k)
+    for (int k = 0; k < (cfg.src_fmt == OTTGPU_FMT_P010 ? 2 : 3); ++k)
         if (((uintptr_t)pl[k] | (uintptr_t)pitch[k]) & 15) return OTTGPU_OK;
     for (auto &m : c->maps)
         if (m.base == base) {
@@ -241,16 +241,19 @@ int frame_tensor_maps(ottgpu_channel *c, const uint8_t *base, cudaStream_t strea
     alignas(64) static thread_local CUtensorMap host[kMaxRungSlots * 3];
     std::memset(host, 0, sizeof(host));
     const Plan &plan = *c->plan;
-    const int dims[3][2] = {{cfg.src_width, cfg.src_height},
-                            {(cfg.src_width + 1) / 2, (cfg.src_height + 1) / 2},
-                            {(cfg.src_width + 1) / 2, (cfg.src_height + 1) / 2}};
+    // planes as 2-D arrays of 32-bit elements: {elements per row, rows}; P010 has Y and the interleaved UV plane
+    const int cw = (cfg.src_width + 1) / 2, chh = (cfg.src_height + 1) / 2, bps = fmt_bps(cfg.src_fmt);
+    const bool semi = cfg.src_fmt == OTTGPU_FMT_P010;
+    const int nmaps = semi ? 2 : 3;
+    const int row_bytes[3] = {cfg.src_width * bps, semi ? 2 * cw * bps : cw * bps, cw * bps};
+    const int rows[3] = {cfg.src_height, chh, chh};
     for (int s = 0; s < plan.n_slots; ++s) {
         const RungDev &R = plan.host_copy.rung[s];
         if (!R.scaled) continue;
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < nmaps; ++k) {
             const PlaneTables &T = k ? R.chroma : R.luma;
             if (!T.tma_ok) continue;
-            const cuuint64_t gdim[2] = {(cuuint64_t)(dims[k][0] / 4), (cuuint64_t)dims[k][1]};
+            const cuuint64_t gdim[2] = {(cuuint64_t)(row_bytes[k] / 4), (cuuint64_t)rows[k]};
             const cuuint64_t gstride[1] = {(cuuint64_t)pitch[k]};
             const cuuint32_t box[2] = {(cuuint32_t)T.sw_words, (cuuint32_t)T.sr_max};
             const cuuint32_t estride[2] = {1, 1};
