@@ -53,6 +53,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         : "memory");
 }
 
+// producer-side wait: the producer is usually far ahead, so it backs off between probes instead of competing with the
+// compute warps of its scheduler for issue slots
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity)
+{
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+        __nanosleep(256);
+    }
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -95,7 +114,7 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
             idx = __shfl_sync(0xffffffffu, idx, 0);
             int idx_next = 0;
             if (lane == 0 && idx < L.n_items) idx_next = atomicAdd(L.counter, 1);     // in flight while this tile is set up
-            mbar_wait(&gfree[slot], (pg >> slot) & 1);
+            mbar_wait_backoff(&gfree[slot], (pg >> slot) & 1);
             pg ^= 1u << slot;
             if (lane == 0) {
                 s_idx[slot] = idx;
@@ -111,7 +130,7 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
             if (s_what[slot] == 1) {
                 phase_tables(lane, 32, g, smem);               // V coefficients / row positions into this slot's table region
                 __syncwarp();
-                mbar_wait(&empty[buf], (pe >> buf) & 1);       // the tile that last used this source buffer is done
+                mbar_wait_backoff(&empty[buf], (pe >> buf) & 1);   // the tile that last used this source buffer is done
                 pe ^= 1u << buf;
                 if (g.bulk_ok) {
                     if (lane == 0) {

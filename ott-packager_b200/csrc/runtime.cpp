@@ -448,6 +448,8 @@ int ottgpu_channel_submit(ottgpu_channel *ch, const ottgpu_frame_in *in, ottgpu_
 }
 
 /* ---------------------------------------------------------------------------------------------------- batch */
+static int batch_build(ottgpu_batch *b, ottgpu_channel **channels, int n);
+
 int ottgpu_batch_create(ottgpu_channel **channels, int n, ottgpu_batch **out)
 {
     if (!channels || n < 1 || n > 65535 || !out) return fail(OTTGPU_ERR_ARG, "bad batch arguments");
@@ -456,7 +458,20 @@ int ottgpu_batch_create(ottgpu_channel **channels, int n, ottgpu_batch **out)
         if (!channels[i]) return fail(OTTGPU_ERR_ARG, "null channel in batch");
         if (channels[i]->gpu != channels[0]->gpu) return fail(OTTGPU_ERR_ARG, "channels of one batch must share a GPU");
     }
-    std::unique_ptr<ottgpu_batch> b(new ottgpu_batch);
+    ottgpu_batch *b = new ottgpu_batch;
+    const int rc = batch_build(b, channels, n);
+    if (rc != OTTGPU_OK) {
+        const std::string why = t_err;                 // destroy() must not clobber the reason
+        ottgpu_batch_destroy(b);
+        t_err = why;
+        return rc;
+    }
+    *out = b;
+    return OTTGPU_OK;
+}
+
+static int batch_build(ottgpu_batch *b, ottgpu_channel **channels, int n)
+{
     b->ch.assign(channels, channels + n);
     b->gpu = channels[0]->gpu;
     b->stream = channels[0]->stream;
@@ -511,7 +526,6 @@ int ottgpu_batch_create(ottgpu_channel **channels, int n, ottgpu_batch **out)
         CK(cudaEventCreate(&st.y0));
         CK(cudaEventCreate(&st.y1));
     }
-    *out = b.release();
     return OTTGPU_OK;
 }
 
@@ -519,7 +533,7 @@ void ottgpu_batch_destroy(ottgpu_batch *b)
 {
     if (!b) return;
     cudaSetDevice(b->gpu);
-    cudaStreamSynchronize(b->stream);
+    if (b->stream) cudaStreamSynchronize(b->stream);
     if (b->copy_stream) {
         cudaStreamSynchronize(b->copy_stream);
         cudaStreamDestroy(b->copy_stream);
