@@ -10,7 +10,7 @@ byop, smp, st = collections.Counter(), collections.Counter(), collections.Counte
 for r in data:
     try:
         n = int(r[ia])
-    except ValueError:
+    except (ValueError, IndexError):
         continue
     sp = r[isrc].split()
     op = (sp[1] if sp[0].startswith('@') else sp[0]).split('.')[0]
@@ -24,12 +24,14 @@ for op, n in byop.most_common(int(sys.argv[2]) if len(sys.argv) > 2 else 16):
 print("stalls:", ", ".join("%s %.1f%%" % (h[6:], 100.0 * v / max(ts, 1)) for h, v in st.most_common(8)))
 blk = []
 for i in range(0, len(data), 64):
-    seg = data[i:i + 64]
+    seg = [r for r in data[i:i + 64] if len(r) > max(ia, ismp)]
     blk.append((sum(int(r[ia] or 0) for r in seg), sum(int(r[ismp] or 0) for r in seg), i))
 print("hottest 64-instruction regions (index, %instr, %samples, top ops):")
 for n, s, i in sorted(blk, key=lambda b: -b[1])[:12]:
     ops = collections.Counter()
     for r in data[i:i + 64]:
+        if len(r) <= isrc or not r[isrc].split():
+            continue
         sp = r[isrc].split()
         ops[(sp[1] if sp[0].startswith('@') else sp[0]).split('.')[0]] += 1
     print("  %6d %5.1f%% %5.1f%%  %s" % (i, 100.0 * n / tot, 100.0 * s / max(ts, 1), ops.most_common(5)))

@@ -288,3 +288,56 @@ def test_1080p_thumbnail_slot_full_size(real_lib, og, oracle):
         r = ch.submit(f)
         assert np.array_equal(r["thumbnail"], oracle.scale_i420(f, w, h, 176, 144))
     ch.close()
+
+
+def test_channels_driven_from_concurrent_threads(lib, og, oracle):
+    """The reference runs one prepare/scale thread pair per channel (transvideo.c:3044-3099); a process hosting several
+    channels drives each ottgpu_channel from its own thread.  ctypes drops the GIL during the calls, so the submits below
+    really overlap; every channel must still produce exactly what the oracle says."""
+    import threading
+    specs = [(192, 108, [(128, 72, og.FMT_I420), (64, 36, og.FMT_NV12)], og.DEINT_ALL),
+             (130, 74, [(130, 74, og.FMT_I420), (66, 38, og.FMT_I420)], og.DEINT_BYPASS),
+             (96, 64, [(64, 40, og.FMT_NV12)], og.DEINT_ALL),
+             (192, 108, [(128, 72, og.FMT_I420), (64, 36, og.FMT_NV12)], og.DEINT_FLAGGED)]   # same plan as channel 0
+    n_frames = 5
+    inputs, results, errors = [], [None] * len(specs), []
+    for k, (w, h, rungs, deint) in enumerate(specs):
+        inputs.append(interlaced_sequence(w, h, n_frames, seed=20 + k) if deint != og.DEINT_BYPASS
+                      else [noise_i420(w, h, 70 + k + i) for i in range(n_frames)])
+    start = threading.Barrier(len(specs))
+
+    def drive(k):
+        try:
+            w, h, rungs, deint = specs[k]
+            ch = og.Channel(lib, og.make_cfg(w, h, rungs, deint=deint))
+            start.wait()
+            out = []
+            for i, f in enumerate(inputs[k]):
+                r = ch.submit(f, interlaced=1, tff=1, opaque=1000 + 100 * k + i)
+                out.append(None if r is None else (r["opaque"], [np.array(x) for x in r["rungs"]]))
+            ch.close()
+            results[k] = out
+        except Exception as e:                                   # surfaced in the main thread
+            errors.append((k, repr(e)))
+            try:
+                start.abort()
+            except Exception:
+                pass
+
+    threads = [threading.Thread(target=drive, args=(k,)) for k in range(len(specs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+    assert not errors, errors
+    for k, (w, h, rungs, deint) in enumerate(specs):
+        ref = None if deint == og.DEINT_BYPASS else oracle.YadifStream(w, h, deint_flagged_only=deint == og.DEINT_FLAGGED)
+        for i, f in enumerate(inputs[k]):
+            want = (f, i) if ref is None else ref.push(f, 1, 1, tag=i)
+            got = results[k][i]
+            assert (got is None) == (want is None)
+            if want is None:
+                continue
+            assert got[0] == 1000 + 100 * k + want[1]
+            for a, b in zip(got[1], _oracle_ladder(oracle, want[0], w, h, rungs, og)):
+                assert np.array_equal(a, b)

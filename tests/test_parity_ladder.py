@@ -148,3 +148,72 @@ def test_baseline_full_size_ladders(real_lib, og, oracle, cfg):
             assert np.array_equal(got, oracle.i420_to_nv12(i420, dw, dh)), (dw, dh)
         else:
             assert np.array_equal(real_lib.scale_frame(src, og.FMT_I420, sw, sh, dw, dh), i420), (dw, dh)
+
+
+# ------------------------------------------------------------------------------------- size-independent properties
+def _const_i420(w, h, y, u, v):
+    cw, ch = (w + 1) // 2, (h + 1) // 2
+    return np.concatenate([np.full(w * h, y, np.uint8), np.full(cw * ch, u, np.uint8), np.full(cw * ch, v, np.uint8)])
+
+
+@pytest.mark.parametrize("levels", [(16, 128, 128), (235, 16, 240), (0, 0, 0), (255, 255, 255), (81, 90, 240)])
+def test_flat_frame_stays_flat_small(lib, og, oracle, levels):
+    """A flat frame scales to a flat frame whose level does not depend on the frame size: the small case is checked
+    against the oracle here and gives the expected level for the full-size run below."""
+    src = _const_i420(192, 108, *levels)
+    got = lib.scale_frame(src, og.FMT_I420, 192, 108, 128, 72)
+    assert np.array_equal(got, oracle.scale_i420(src, 192, 108, 128, 72))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("levels", [(16, 128, 128), (235, 16, 240), (255, 255, 255), (81, 90, 240)])
+def test_flat_frame_stays_flat_full_size(real_lib, og, oracle, levels):
+    """BASELINE.json cfg2 ladder at full size on a flat frame: every rung is flat, and its level is the one the oracle
+    produces for the same scale ratio on a frame 1/10th the size (the polyphase phases repeat, so the level is the same)."""
+    sw, sh = 1920, 1080
+    src = _const_i420(sw, sh, *levels)
+    for dw, dh in [(1280, 720), (960, 540), (640, 360)]:
+        got = real_lib.scale_frame(src, og.FMT_I420, sw, sh, dw, dh)
+        small = oracle.scale_i420(_const_i420(sw // 10, sh // 10, *levels), sw // 10, sh // 10, dw // 10, dh // 10)
+        y, u, v = split_i420(got, dw, dh)
+        ys, us, vs = split_i420(small, dw // 10, dh // 10)
+        for plane, ref in ((y, ys), (u, us), (v, vs)):
+            # interior rows/columns (the last two luma rows / last chroma row take libswscale's exact vertical path)
+            assert np.unique(plane[4:-4, 4:-4]).tolist() == np.unique(ref[4:-4, 4:-4]).tolist(), (dw, dh)
+            assert np.array_equal(plane[-4:, 8:16], np.broadcast_to(ref[-4:, 8:9], (4, 8)))
+
+
+@pytest.mark.gpu
+def test_full_size_crop_independence(real_lib, og, oracle):
+    """Tile seams must not show: the top-left region of a full-size 2:1 downscale equals the oracle's result on the
+    matching top-left crop of the source (outputs only see a finite window of source rows/columns)."""
+    sw, sh = 1920, 1080
+    src = natural_i420(sw, sh, 31)
+    got = real_lib.scale_frame(src, og.FMT_I420, sw, sh, 960, 540)
+    y, u, v = split_i420(src, sw, sh)
+    cw, chh = 512, 288                                     # crop of the source, same 2:1 ratio -> 256x144 output
+    crop = np.concatenate([y[:chh, :cw].ravel(), u[:chh // 2, :cw // 2].ravel(), v[:chh // 2, :cw // 2].ravel()])
+    ref = oracle.scale_i420(crop, cw, chh, cw // 2, chh // 2)
+    gy, gu, gv = split_i420(got, 960, 540)
+    ry, ru, rv = split_i420(ref, cw // 2, chh // 2)
+    m = 8                                                  # keep clear of the crop's right/bottom border handling
+    assert np.array_equal(gy[:chh // 2 - m, :cw // 2 - m], ry[:-m, :-m])
+    assert np.array_equal(gu[:chh // 4 - m, :cw // 4 - m], ru[:-m, :-m])
+    assert np.array_equal(gv[:chh // 4 - m, :cw // 4 - m], rv[:-m, :-m])
+
+
+@pytest.mark.gpu
+def test_full_size_runs_are_deterministic(real_lib, og):
+    """The dynamic tile scheduler hands tiles to CTAs in a different order every launch; the bytes must not depend on it."""
+    import hashlib
+    sw, sh = 1920, 1080
+    nv = og.FMT_NV12
+    rungs = [(1920, 1080, nv), (1280, 720, nv), (960, 540, nv), (640, 360, nv), (416, 234, nv)]
+    src = natural_i420(sw, sh, 5)
+    digests = set()
+    for _ in range(4):
+        ch = og.Channel(real_lib, og.make_cfg(sw, sh, rungs, deint=og.DEINT_BYPASS))
+        r = ch.submit(src)
+        digests.add(hashlib.md5(b"".join(np.ascontiguousarray(x).tobytes() for x in r["rungs"])).hexdigest())
+        ch.close()
+    assert len(digests) == 1
