@@ -148,9 +148,14 @@ class CpuReference:
     transvideo.c:1563-1581), NV12 repack when the workload asks for NV12 (transvideo.c:543-557), yadif via the C port
     (no libavfilter in the image), thumbnail every 150th frame (transvideo.c:2159-2174).  One instance per thread."""
 
-    def __init__(self, wl):
+    def __init__(self, wl, copies=False):
         from oracle import oracle as O, swscale_so as S
         self.O, self.wl = O, wl
+        # copies=True adds the full-frame memcpys the reference makes around the arithmetic (SURVEY 3B): #3 into the filter
+        # frame (transvideo.c:1476-1502, 2130), #4 out of it (2217-2231), #5 per rendition into the pool buffer (1610-1624)
+        self.copies = copies
+        self.stage_in = np.empty(frame_bytes(wl["w"], wl["h"]) * (2 if wl.get("src_fmt") == P010 else 1), np.uint8)
+        self.stage_out = np.empty_like(self.stage_in)
         self.kind = "reference" if S.available() else "port"
         self.w, self.h = wl["w"], wl["h"]
         self.count = 0
@@ -182,16 +187,21 @@ class CpuReference:
 
     def frame(self, f, nxt):
         O, wl = self.O, self.wl
+        if self.copies:
+            np.copyto(self.stage_in, f.view(np.uint8))            # copy #3 (the filter graph's input frame)
         if wl["deint"] == 0:                                  # yadif on every frame
             f = O.yadif_frame(self.prev if self.prev is not None else f, f, nxt, self.w, self.h, 1, 1)
         self.prev = f
         self.count += 1
+        if self.copies:
+            np.copyto(self.stage_out, f.view(np.uint8))           # copy #4 (deinterlaced frame -> pool buffer)
         if self.kind == "reference":
             src = self.planes(f)
             for sc, out, (dw, dh), nv in zip(self.ctx, self.out, wl["rungs"], self.nv12):
                 sc.scale_planes(src, out)
+                if wl["out_fmt"] == NV12 or self.copies:
+                    packed = np.concatenate([p.ravel() for p in out])     # copy #5: planes -> contiguous pool buffer
                 if wl["out_fmt"] == NV12:
-                    packed = np.concatenate([p.ravel() for p in out])
                     O.lib().ora_i420_to_nv12(packed.ctypes.data, dw, dh, nv.ctypes.data)
             if self.count % THUMB[2] == 0:
                 self.thumb.scale_planes(src, self.tout)
@@ -214,10 +224,10 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def run_cpu_rounds(wl, frames, threads, rounds=None, seconds=None):
+def run_cpu_rounds(wl, frames, threads, rounds=None, seconds=None, copies=False):
     """Each round = every worker thread processes ONE source frame (ctypes releases the GIL inside libswscale / the C
     oracle).  Returns (frames_done, elapsed_s, kind, per-round seconds)."""
-    workers = [CpuReference(wl) for _ in range(threads)]
+    workers = [CpuReference(wl, copies) for _ in range(threads)]
     kind = workers[0].kind
     barrier = threading.Barrier(threads + 1)
     state = {"go": True}
@@ -512,9 +522,13 @@ def ours_main(args, wl, rank, world, local_rank):
         threads = host_cores()
         done, el, kind, _ = run_cpu_rounds(wl, base_frames, threads, seconds=args.cpu_seconds)
         one_done, one_el, _, _ = run_cpu_rounds(wl, base_frames, 1, seconds=min(3.0, args.cpu_seconds))
+        cp_done, cp_el, _, _ = run_cpu_rounds(wl, base_frames, threads, seconds=min(4.0, args.cpu_seconds), copies=True)
         cpu = {"value": done / el, "unit": "frames/s", "cores": threads, "kind": kind,
                "sample": "%d frames of the same workload (%d rounds x %d host threads, one frame per thread per round, ~%.0f s)"
                          % (done, done // threads, threads, el),
+               "with_reference_copies": {"value": cp_done / cp_el, "unit": "frames/s",
+                                         "note": "same, plus the reference's full-frame memcpys #3, #4 and #5 per rendition "
+                                                 "(transvideo.c:1476-1502, 2217-2231, 1610-1624); `value` leaves them out"},
                "single_thread": {"value": one_done / one_el, "unit": "frames/s",
                                  "note": "one thread = how the reference runs one channel's scaler (transvideo.c:1504)"}}
     line = {"metric": "ladder_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
