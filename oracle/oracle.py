@@ -37,6 +37,8 @@ def lib():
         L.ora_scale_i420.argtypes = [vp, ci, ci, vp, ci, ci, ci, ci]
         L.ora_i420_to_nv12.argtypes = [vp, ci, ci, vp]
         L.ora_scale_p010.argtypes = [vp, ci, ci, vp, ci, ci, ci, ci]
+        L.ora_convert_to_i420.argtypes = [vp, vp, ci, ci, ci, vp, ci]
+        L.ora_convert_to_i420.restype = ci
         L.ora_yadif_plane.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci]
         L.ora_yadif_frame_420.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci]
         for f in ("ora_scale_plane_u8", "ora_scale_plane_u10", "ora_scale_i420", "ora_i420_to_nv12",
@@ -82,6 +84,20 @@ def scale_p010(src, sw, sh, dw, dh, kernel=LANCZOS, target=TARGET_A):
     dst = np.empty(i420_size(dw, dh), np.uint16)
     lib().ora_scale_p010(src.ctypes.data, sw, sh, dst.ctypes.data, dw, dh, kernel, target)
     return dst
+
+
+PIX_YUV420P, PIX_YUV422P, PIX_YUV420P10, PIX_YUV422P10 = 0, 1, 2, 3
+
+
+def convert_to_i420(planes, fmt, w, h, target=TARGET_A):
+    """planes: three 2-D numpy arrays as a decoder hands them over (uint8 or uint16, any row stride) -> packed I420."""
+    L = lib()
+    pp = (ctypes.c_void_p * 3)(*[p.ctypes.data for p in planes])
+    ss = (ctypes.c_int * 3)(*[p.strides[0] for p in planes])
+    out = np.empty(i420_size(w, h), np.uint8)
+    if L.ora_convert_to_i420(pp, ss, fmt, w, h, out.ctypes.data, target) != 0:
+        raise ValueError("unknown pixel format %r" % (fmt,))
+    return out
 
 
 def yadif_frame(prev, cur, nxt, w, h, interlaced=1, tff=1, bps=1):

@@ -36,6 +36,28 @@ def noise_p010(w, h, seed=99):
     return np.concatenate([y.ravel(), uv.ravel()])
 
 
+DECODED_FORMATS = {"yuv420p": (np.uint8, 256, False), "yuv422p": (np.uint8, 256, True),
+                   "yuv420p10le": (np.uint16, 1024, False), "yuv422p10le": (np.uint16, 1024, True)}
+
+
+def decoded_planes(fmt, w, h, seed=1, kind="noise", pad=0):
+    """Three planes as a decoder hands them over (transvideo.c:2788-2795): Y, U, V with `pad` extra samples per row
+    (linesize > width).  kind: noise | extreme (0 / max checker noise) | ramp."""
+    dt, mx, is422 = DECODED_FORMATS[fmt]
+    cw, ch = (w + 1) // 2, (h if is422 else (h + 1) // 2)
+    rng = np.random.default_rng(seed)
+    out = []
+    for pw, ph in ((w, h), (cw, ch), (cw, ch)):
+        if kind == "noise":
+            a = rng.integers(0, mx, (ph, pw + pad))
+        elif kind == "extreme":
+            a = rng.integers(0, 2, (ph, pw + pad)) * (mx - 1)
+        else:
+            a = (np.arange(pw + pad)[None, :] * 3 + np.arange(ph)[:, None] * 5) % mx
+        out.append(np.ascontiguousarray(a.astype(dt))[:, :pw])
+    return out
+
+
 def natural_i420(w, h, seed=7, shift=0.0):
     cw, ch = chroma_dims(w, h)
     rng = np.random.default_rng(seed)
