@@ -156,6 +156,36 @@ void   ottgpu_pool_destroy(ottgpu_pool *p);
  * i.e. what replaces the memcpy of transvideo.c:1330-1338 when the rung lives in HBM) */
 int    ottgpu_memcpy(int gpu, void *dst, int dst_mem, const void *src, int src_mem, size_t bytes);
 
+/* --- decode-side converter ------------------------------------------------------------------------------------------
+ * Replaces the decode thread's `decode_converter` (transvideo.c:2797-2808: sws_getContext(w,h,source_format -> w,h,
+ * AV_PIX_FMT_YUV420P, SWS_BICUBIC) + sws_scale) together with the three row-copy loops that pack the planes into the
+ * contiguous w*h*3/2 frame handed to the prepare thread (transvideo.c:2823-2840).  The result is byte-identical to
+ * libswscale's for the same flags (`target` as in ottgpu_cfg).  With dst_mem = OTTGPU_MEM_DEVICE the packed frame stays
+ * on the GPU and is fed to ottgpu_channel_submit / ottgpu_batch_submit as an OTTGPU_MEM_DEVICE input. */
+enum {
+    OTTGPU_PIX_YUV420P   = 0,   /* AV_PIX_FMT_YUV420P: no arithmetic, rows re-packed                                */
+    OTTGPU_PIX_YUV422P   = 1,   /* AV_PIX_FMT_YUV422P                                                               */
+    OTTGPU_PIX_YUV420P10 = 2,   /* AV_PIX_FMT_YUV420P10LE (samples 0..1023 in 16-bit words)                         */
+    OTTGPU_PIX_YUV422P10 = 3    /* AV_PIX_FMT_YUV422P10LE                                                           */
+};
+
+typedef struct ottgpu_picture {
+    const void *plane[3];       /* Y, U, V as the decoder hands them over (AVFrame.data, transvideo.c:2788-2791)    */
+    int         stride[3];      /* bytes per row (AVFrame.linesize, transvideo.c:2792-2795); >= the row's bytes     */
+    int         mem;            /* OTTGPU_MEM_HOST or OTTGPU_MEM_DEVICE                                             */
+} ottgpu_picture;
+
+typedef struct ottgpu_converter ottgpu_converter;
+
+/* stream: the caller's cudaStream_t (work is ordered on it) or NULL for a private stream */
+int  ottgpu_converter_create(int gpu, int pix_fmt, int width, int height, int target, void *stream, ottgpu_converter **out);
+/* dst: packed I420 frame, ottgpu_frame_bytes(OTTGPU_FMT_I420, width, height) bytes, in dst_mem.
+ * flags: 0 = the frame is complete on return; OTTGPU_SUBMIT_ASYNC = enqueued on the stream (host pictures must stay
+ * valid until ottgpu_converter_wait / a stream synchronisation) */
+int  ottgpu_converter_convert(ottgpu_converter *cv, const ottgpu_picture *in, void *dst, int dst_mem, int flags);
+int  ottgpu_converter_wait(ottgpu_converter *cv);
+void ottgpu_converter_destroy(ottgpu_converter *cv);
+
 /* --- stateless single-shot helpers (unit tests, golden comparisons; same kernels) --------------------------------- */
 /* sws_getContext + sws_scale on one packed host frame: src (fmt,w,h) -> dst rung; dst is ottgpu_rung_bytes() large   */
 int ottgpu_scale_frame(int gpu, const void *src, int src_fmt, int src_w, int src_h,

@@ -18,6 +18,7 @@ TARGET_A, TARGET_B = 0, 1
 DEINT_ALL, DEINT_FLAGGED, DEINT_BYPASS = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
 SUBMIT_SYNC, SUBMIT_ASYNC = 0, 1
+PIX_YUV420P, PIX_YUV422P, PIX_YUV420P10, PIX_YUV422P10 = 0, 1, 2, 3
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.path.join(HERE, "libottgpu.so")
@@ -43,6 +44,10 @@ class FrameOut(C.Structure):
     _fields_ = [("dst", C.c_void_p * MAX_RUNGS), ("dst_mem", C.c_int * MAX_RUNGS), ("produced", C.c_int),
                 ("opaque", C.c_void_p), ("pts", C.c_int64), ("dts", C.c_int64), ("interlaced", C.c_int),
                 ("tff", C.c_int), ("thumbnail", C.c_void_p), ("n_released", C.c_int), ("released", C.c_void_p * 4)]
+
+
+class Picture(C.Structure):
+    _fields_ = [("plane", C.c_void_p * 3), ("stride", C.c_int * 3), ("mem", C.c_int)]
 
 
 class OttGpuError(RuntimeError):
@@ -80,6 +85,10 @@ _SIGS = {
     "ottgpu_pool_unused": (C.c_int, [C.c_void_p]),
     "ottgpu_pool_destroy": (None, [C.c_void_p]),
     "ottgpu_memcpy": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_size_t]),
+    "ottgpu_converter_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ottgpu_converter_convert": (C.c_int, [C.c_void_p, C.POINTER(Picture), C.c_void_p, C.c_int, C.c_int]),
+    "ottgpu_converter_wait": (C.c_int, [C.c_void_p]),
+    "ottgpu_converter_destroy": (None, [C.c_void_p]),
     "ottgpu_scale_frame": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(RungCfg),
                                      C.c_int, C.c_int]),
     "ottgpu_yadif_frame": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
@@ -248,6 +257,53 @@ class Channel:
         bufs = self.alloc_out(fout, device_dst)
         self.lib.check(self.lib.dll.ottgpu_channel_submit(self.handle, C.byref(fin), C.byref(fout)))
         return self.collect(fout, bufs)
+
+
+class Converter:
+    """The decode thread's `decode_converter` + packing loops (transvideo.c:2797-2840): decoder planes -> packed I420."""
+
+    def __init__(self, lib, pix_fmt, w, h, target=TARGET_A, gpu=0, stream=None):
+        self.lib, self.pix_fmt, self.w, self.h, self.gpu = lib, pix_fmt, w, h, gpu
+        h_ = C.c_void_p()
+        lib.check(lib.dll.ottgpu_converter_create(gpu, pix_fmt, w, h, target, stream, C.byref(h_)))
+        self.handle = h_
+        self.out_bytes = lib.frame_bytes(FMT_I420, w, h)
+
+    def close(self):
+        if self.handle:
+            self.lib.dll.ottgpu_converter_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def picture(self, planes, mem=MEM_HOST, strides=None):
+        """planes: numpy arrays (host) or integer device addresses with `strides` in bytes."""
+        pic = Picture()
+        pic.mem = mem
+        for i, p in enumerate(planes):
+            if mem == MEM_HOST:
+                pic.plane[i], pic.stride[i] = p.ctypes.data, p.strides[0]
+            else:
+                pic.plane[i], pic.stride[i] = p, strides[i]
+        return pic
+
+    def convert(self, planes, device_dst=None, flags=SUBMIT_SYNC, mem=MEM_HOST, strides=None):
+        """-> packed I420 numpy array, or None when the frame is written to `device_dst`."""
+        pic = self.picture(planes, mem, strides)
+        self._keep = (planes, pic)
+        if device_dst is not None:
+            self.lib.check(self.lib.dll.ottgpu_converter_convert(self.handle, C.byref(pic), device_dst, MEM_DEVICE, flags))
+            return None
+        out = np.empty(self.out_bytes, np.uint8)
+        self.lib.check(self.lib.dll.ottgpu_converter_convert(self.handle, C.byref(pic), out.ctypes.data, MEM_HOST, SUBMIT_SYNC))
+        return out
+
+    def wait(self):
+        self.lib.check(self.lib.dll.ottgpu_converter_wait(self.handle))
 
 
 class Batch:

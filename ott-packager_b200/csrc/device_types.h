@@ -112,4 +112,33 @@ struct YadifJob {
     int fast;                           // 8-bit, width % 16 == 0, 8-byte aligned frames: eight samples per thread
 };
 
+// decode-side converter (transvideo.c:2797-2840): one plane of one picture
+enum ConvertMode : int {
+    CONV_COPY8 = 0,      // 8-bit plane, rows re-packed
+    CONV_REDUCE10 = 1,   // 10-bit plane -> 8 bit, 2x2 ordered dither (== the Bayer row >> 5 of the generic 1-tap path)
+    CONV_VFILT8 = 2,     // 4:2:2 chroma, 8-bit: vertical 2:1 polyphase
+    CONV_VFILT10 = 3,    // 4:2:2 chroma, 10-bit: vertical 2:1 polyphase with the 8x8 Bayer dither
+};
+
+struct ConvertPlane {
+    const uint8_t *src;
+    int src_pitch;           // bytes
+    uint8_t *dst;
+    int dst_pitch;           // bytes (packed I420: the plane width)
+    int w, h;                // destination plane size in samples
+    int mode;
+    int dither_offset;       // column offset into the Bayer row (0: Y/U, 3: V)
+    int fast;                // rows can be moved as aligned 16-sample vectors
+};
+
+struct ConvertJob {
+    ConvertPlane plane[3];
+    const int32_t *vpos;     // [chroma rows] first source row of each output row
+    const int16_t *vc;       // [chroma rows * vtaps] 12-bit coefficients
+    int vtaps;
+    int exact_from;          // first chroma row that takes the exact vertical path under target A
+    int approx;              // 1: target A (x86 default flags), 0: target B
+    uint8_t bayer[64];       // ff_dither_8x8_128
+};
+
 }  // namespace ottgpu

@@ -5,10 +5,12 @@
 //                   while the previous tile is still computing.  The source frame is read from HBM once and shared by
 //                   the rungs through L2 (items are ordered by source row band), see DESIGN.md.
 //   yadif_kernel  : yadif mode 0 first-field deinterlacer on planar 8/16-bit frames.
+//   convert_kernel: decode-side 4:2:2 / 10-bit -> packed 8-bit 4:2:0 converter.
 // The per-thread work lives in ladder_core.cuh / yadif_core.cuh.
 #include "kernels.h"
 #include "ladder_core.cuh"
 #include "yadif_core.cuh"
+#include "convert_core.cuh"
 
 namespace ottgpu {
 
@@ -191,6 +193,12 @@ __global__ void __launch_bounds__(256) yadif_kernel(const YadifJob *__restrict__
     else yadif_position(j, gx, gy);
 }
 
+// decode-side converter: the job (three plane descriptors + the Bayer table) travels as a kernel parameter
+__global__ void __launch_bounds__(256) convert_kernel(const ConvertJob j)
+{
+    convert_position(j, blockIdx.x * 32 + (threadIdx.x & 31), blockIdx.y * 8 + (threadIdx.x >> 5));
+}
+
 cudaError_t configure_kernels()
 {
     return cudaFuncSetAttribute(ladder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTileSmem);
@@ -230,6 +238,16 @@ cudaError_t launch_yadif(const YadifJob *jobs, int n_jobs, int max_w, int max_h,
     const int cols = all_fast ? (max_w / 8 + 31) / 32 : (max_w + 31) / 32;
     dim3 grid(cols, ((max_h + (max_h + 1) / 2) + 7) / 8, n_jobs);
     yadif_kernel<<<grid, 256, 0, s>>>(jobs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_convert(const ConvertJob &job, cudaStream_t s)
+{
+    const int rows = job.plane[0].h + job.plane[1].h + job.plane[2].h;
+    const int groups = (job.plane[0].w + kConvertGroup - 1) / kConvertGroup;
+    if (rows <= 0 || groups <= 0) return cudaSuccess;
+    dim3 grid((groups + 31) / 32, (rows + 7) / 8, 1);
+    convert_kernel<<<grid, 256, 0, s>>>(job);
     return cudaGetLastError();
 }
 

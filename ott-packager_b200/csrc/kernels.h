@@ -18,6 +18,9 @@ cudaError_t launch_ladder(LadderLaunch L, cudaStream_t s);
 // all_fast: every job takes the 8-samples-per-thread path, so the grid only spans (w/8) x (h + h/2) positions
 cudaError_t launch_yadif(const YadifJob *jobs, int n_jobs, int max_w, int max_h, bool all_fast, cudaStream_t s);
 
+// decode-side converter: one launch per picture
+cudaError_t launch_convert(const ConvertJob &job, cudaStream_t s);
+
 cudaError_t configure_kernels();
 
 }  // namespace ottgpu

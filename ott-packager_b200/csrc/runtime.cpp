@@ -1032,3 +1032,176 @@ int ottgpu_yadif_frame(int gpu, const void *prev, const void *cur, const void *n
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------- decode-side converter
+struct ottgpu_converter {
+    int gpu = 0, pix_fmt = 0, w = 0, h = 0, target = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int32_t *d_vpos = nullptr;
+    int16_t *d_vc = nullptr;
+    int vtaps = 1, exact_from = 0;
+    // per plane: source rows / bytes per row, destination size
+    int src_rows[3] = {0, 0, 0}, row_bytes[3] = {0, 0, 0}, dw[3] = {0, 0, 0}, dh[3] = {0, 0, 0}, mode[3] = {0, 0, 0};
+    size_t stage_pitch[3] = {0, 0, 0};
+    static constexpr int kSets = 2;                 // a host picture is uploaded while the previous one converts
+    uint8_t *stage[kSets][3] = {{nullptr}, {nullptr}};
+    uint8_t *out_stage[kSets] = {nullptr, nullptr}; // packed result on the device when the caller wants it in host memory
+    cudaEvent_t done[kSets] = {nullptr, nullptr};
+    int phase = 0;
+    size_t out_bytes = 0;
+};
+
+namespace {
+
+const uint8_t kBayer8x8[64] = {36, 68, 60, 92, 34, 66, 58, 90, 100, 4,  124, 28, 98,  2,  122, 26, 52, 84, 44, 76, 50, 82,
+                               42, 74, 116, 20, 108, 12, 114, 18, 106, 10, 32, 64, 56,  88, 38,  70, 62, 94, 96, 0,  120, 24,
+                               102, 6,  126, 30, 48, 80, 40, 72, 54, 86, 46,  78, 112, 16, 104, 8,  118, 22, 110, 14};
+
+void converter_free(ottgpu_converter *cv)
+{
+    if (!cv) return;
+    cudaSetDevice(cv->gpu);
+    if (cv->stream) cudaStreamSynchronize(cv->stream);
+    for (int s = 0; s < ottgpu_converter::kSets; ++s) {
+        for (int p = 0; p < 3; ++p) cudaFree(cv->stage[s][p]);
+        cudaFree(cv->out_stage[s]);
+        if (cv->done[s]) cudaEventDestroy(cv->done[s]);
+    }
+    cudaFree(cv->d_vpos);
+    cudaFree(cv->d_vc);
+    if (cv->own_stream && cv->stream) cudaStreamDestroy(cv->stream);
+    delete cv;
+}
+
+int converter_build(ottgpu_converter *cv, void *stream)
+{
+    const int w = cv->w, h = cv->h, cw = (w + 1) / 2, ch = (h + 1) / 2;
+    const bool is422 = cv->pix_fmt == OTTGPU_PIX_YUV422P || cv->pix_fmt == OTTGPU_PIX_YUV422P10;
+    const int bps = (cv->pix_fmt == OTTGPU_PIX_YUV420P10 || cv->pix_fmt == OTTGPU_PIX_YUV422P10) ? 2 : 1;
+    cv->dw[0] = w; cv->dh[0] = h;
+    cv->dw[1] = cv->dw[2] = cw; cv->dh[1] = cv->dh[2] = ch;
+    cv->src_rows[0] = h;
+    cv->src_rows[1] = cv->src_rows[2] = is422 ? h : ch;
+    cv->row_bytes[0] = w * bps;
+    cv->row_bytes[1] = cv->row_bytes[2] = cw * bps;
+    cv->mode[0] = bps == 2 ? CONV_REDUCE10 : CONV_COPY8;
+    cv->mode[1] = cv->mode[2] = is422 ? (bps == 2 ? CONV_VFILT10 : CONV_VFILT8) : cv->mode[0];
+    cv->out_bytes = (size_t)w * h + 2 * (size_t)cw * ch;
+    if (stream) cv->stream = (cudaStream_t)stream;
+    else {
+        CK(cudaStreamCreateWithFlags(&cv->stream, cudaStreamNonBlocking));
+        cv->own_stream = true;
+    }
+    if (is422) {
+        // the vertical chroma filter sws_getContext builds for h -> ceil(h/2) rows (chrSrcVSubSample 0 -> 1)
+        const PolyphaseTable t = plan_table(h, ch, OTTGPU_FILTER_BICUBIC, cv->target, true);
+        if (t.taps > 64) return fail(OTTGPU_ERR_ARG, "vertical chroma filter too long");
+        cv->vtaps = t.taps;
+        int uv = (h - 2 + 1) / 2;                          // chroma row uv is produced while dstY == 2*uv (swscale.c)
+        cv->exact_from = uv < 0 ? 0 : uv;
+        CK(cudaMalloc((void **)&cv->d_vpos, std::max<size_t>(t.pos.size() * sizeof(int32_t), 16)));
+        CK(cudaMalloc((void **)&cv->d_vc, std::max<size_t>(t.coef.size() * sizeof(int16_t), 16)));
+        CK(cudaMemcpy(cv->d_vpos, t.pos.data(), t.pos.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(cv->d_vc, t.coef.data(), t.coef.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
+    }
+    for (int p = 0; p < 3; ++p) cv->stage_pitch[p] = ((size_t)cv->row_bytes[p] + 15) & ~(size_t)15;
+    for (int s = 0; s < ottgpu_converter::kSets; ++s) CK(cudaEventCreateWithFlags(&cv->done[s], cudaEventDisableTiming));
+    return OTTGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ottgpu_converter_create(int gpu, int pix_fmt, int width, int height, int target, void *stream, ottgpu_converter **out)
+{
+    if (!out) return fail(OTTGPU_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (pix_fmt < OTTGPU_PIX_YUV420P || pix_fmt > OTTGPU_PIX_YUV422P10) return fail(OTTGPU_ERR_ARG, "unknown decoder pixel format");
+    if (target != OTTGPU_TARGET_A && target != OTTGPU_TARGET_B) return fail(OTTGPU_ERR_ARG, "unknown parity target");
+    if (width < 8 || height < 4 || width > 16384 || height > 16384) return fail(OTTGPU_ERR_ARG, "picture size out of range");
+    int rc = prepare_device(gpu);
+    if (rc) return rc;
+    ottgpu_converter *cv = new ottgpu_converter();
+    cv->gpu = gpu; cv->pix_fmt = pix_fmt; cv->w = width; cv->h = height; cv->target = target;
+    rc = converter_build(cv, stream);
+    if (rc) {
+        const std::string why = t_err;
+        converter_free(cv);
+        t_err = why;
+        return rc;
+    }
+    *out = cv;
+    return OTTGPU_OK;
+}
+
+int ottgpu_converter_convert(ottgpu_converter *cv, const ottgpu_picture *in, void *dst, int dst_mem, int flags)
+{
+    if (!cv || !in || !dst) return fail(OTTGPU_ERR_ARG, "null argument");
+    if ((in->mem != OTTGPU_MEM_HOST && in->mem != OTTGPU_MEM_DEVICE) || (dst_mem != OTTGPU_MEM_HOST && dst_mem != OTTGPU_MEM_DEVICE))
+        return fail(OTTGPU_ERR_ARG, "unknown memory kind");
+    for (int p = 0; p < 3; ++p) {
+        if (!in->plane[p]) return fail(OTTGPU_ERR_ARG, "null plane");
+        if (in->stride[p] < cv->row_bytes[p]) return fail(OTTGPU_ERR_ARG, "stride smaller than the row");
+    }
+    CK(cudaSetDevice(cv->gpu));
+    const int set = cv->phase;
+    cv->phase ^= 1;
+    CK(cudaEventSynchronize(cv->done[set]));                 // the conversion that last used this set has finished
+    ConvertJob j;
+    std::memset(&j, 0, sizeof(j));
+    for (int p = 0; p < 3; ++p) {
+        ConvertPlane &P = j.plane[p];
+        if (in->mem == OTTGPU_MEM_HOST) {
+            if (!cv->stage[set][p]) CK(cudaMalloc((void **)&cv->stage[set][p], cv->stage_pitch[p] * cv->src_rows[p] + 16));
+            CK(cudaMemcpy2DAsync(cv->stage[set][p], cv->stage_pitch[p], in->plane[p], (size_t)in->stride[p], (size_t)cv->row_bytes[p],
+                                 (size_t)cv->src_rows[p], cudaMemcpyHostToDevice, cv->stream));
+            P.src = cv->stage[set][p];
+            P.src_pitch = (int)cv->stage_pitch[p];
+        } else {
+            P.src = static_cast<const uint8_t *>(in->plane[p]);
+            P.src_pitch = in->stride[p];
+        }
+        P.w = cv->dw[p]; P.h = cv->dh[p];
+        P.dst_pitch = cv->dw[p];
+        P.mode = cv->mode[p];
+        P.dither_offset = p == 2 ? 3 : 0;
+    }
+    uint8_t *d = static_cast<uint8_t *>(dst);
+    if (dst_mem == OTTGPU_MEM_HOST) {
+        if (!cv->out_stage[set]) CK(cudaMalloc((void **)&cv->out_stage[set], cv->out_bytes + 16));
+        d = cv->out_stage[set];
+    }
+    j.plane[0].dst = d;
+    j.plane[1].dst = d + (size_t)cv->w * cv->h;
+    j.plane[2].dst = j.plane[1].dst + (size_t)cv->dw[1] * cv->dh[1];
+    for (int p = 0; p < 3; ++p) {
+        ConvertPlane &P = j.plane[p];
+        // vector path: 16 samples per thread (8 on vertically filtered planes) moved as 8/16-byte words
+        const bool vf = cv->mode[p] == CONV_VFILT8 || cv->mode[p] == CONV_VFILT10;
+        const int group = vf ? 8 : 16;
+        P.fast = P.w % group == 0 && ((uintptr_t)P.src % 16) == 0 && P.src_pitch % 16 == 0 && ((uintptr_t)P.dst % group) == 0;
+    }
+    j.vpos = cv->d_vpos; j.vc = cv->d_vc;
+    j.vtaps = cv->vtaps; j.exact_from = cv->exact_from;
+    j.approx = cv->target == OTTGPU_TARGET_A;
+    std::memcpy(j.bayer, kBayer8x8, sizeof(j.bayer));
+    CK(launch_convert(j, cv->stream));
+    if (dst_mem == OTTGPU_MEM_HOST) CK(cudaMemcpyAsync(dst, d, cv->out_bytes, cudaMemcpyDeviceToHost, cv->stream));
+    CK(cudaEventRecord(cv->done[set], cv->stream));
+    if (!(flags & OTTGPU_SUBMIT_ASYNC)) CK(cudaStreamSynchronize(cv->stream));
+    return OTTGPU_OK;
+}
+
+int ottgpu_converter_wait(ottgpu_converter *cv)
+{
+    if (!cv) return fail(OTTGPU_ERR_ARG, "null converter");
+    CK(cudaSetDevice(cv->gpu));
+    CK(cudaStreamSynchronize(cv->stream));
+    return OTTGPU_OK;
+}
+
+void ottgpu_converter_destroy(ottgpu_converter *cv) { converter_free(cv); }
+
+}  // extern "C"

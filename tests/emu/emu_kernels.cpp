@@ -4,6 +4,7 @@
 #include "kernels.h"
 #include "ladder_core.cuh"
 #include "yadif_core.cuh"
+#include "convert_core.cuh"
 
 namespace ottgpu {
 
@@ -61,6 +62,15 @@ cudaError_t launch_yadif(const YadifJob *jobs, int n_jobs, int max_w, int max_h,
                 else yadif_position(jobs[z], x, y);
             }
     }
+    return cudaSuccess;
+}
+
+cudaError_t launch_convert(const ConvertJob &job, cudaStream_t)
+{
+    const int rows = job.plane[0].h + job.plane[1].h + job.plane[2].h;
+    const int groups = (job.plane[0].w + kConvertGroup - 1) / kConvertGroup;
+    for (int r = 0; r < (rows + 7) / 8 * 8; ++r)
+        for (int x = 0; x < (groups + 31) / 32 * 32; ++x) convert_position(job, x, r);
     return cudaSuccess;
 }
 
