@@ -23,12 +23,40 @@ static void tv_fatal(ottgpu_transvideo *tv, int code, const char *msg)
     if (tv->direct_error) tv->direct_error(tv->user, code, msg);
 }
 
-static void tv_return_input(ottgpu_transvideo *tv, dataqueue_message_struct *msg)
+/* submitted: the channel has been handed the frame.  Host frames were copied during that call; device frames stay
+ * referenced by the deinterlacer window and come back through ottgpu_frame_out.released[] (tv_settle_inputs). */
+static void tv_return_input(ottgpu_transvideo *tv, dataqueue_message_struct *msg, int submitted)
 {
     /* transvideo.c:2410-2413 */
-    memory_return(tv->raw_video_pool, msg->buffer);
+    if (msg->flags & OTTGPU_MSG_FLAG_DEVICE) {
+        if (!submitted && msg->buffer) ottgpu_pool_return(tv->input_pool, msg->buffer);
+    } else {
+        memory_return(tv->raw_video_pool, msg->buffer);
+    }
     msg->buffer = NULL;
     memory_return(tv->msg_pool, msg);
+}
+
+static void tv_release_held(ottgpu_transvideo *tv)
+{
+    int i;
+    for (i = 0; i < tv->n_held; ++i) ottgpu_pool_return(tv->input_pool, tv->held_inputs[i]);
+    tv->n_held = 0;
+}
+
+/* after a submit: remember the device frame just handed over, give back the ones the channel let go of */
+static void tv_settle_inputs(ottgpu_transvideo *tv, void *submitted_device_frame, const ottgpu_frame_out *out)
+{
+    int r, i;
+    if (submitted_device_frame && tv->n_held < (int)(sizeof(tv->held_inputs) / sizeof(tv->held_inputs[0])))
+        tv->held_inputs[tv->n_held++] = submitted_device_frame;
+    for (r = 0; r < out->n_released; ++r)
+        for (i = 0; i < tv->n_held; ++i)
+            if (tv->held_inputs[i] == out->released[r]) {
+                ottgpu_pool_return(tv->input_pool, tv->held_inputs[i]);
+                tv->held_inputs[i] = tv->held_inputs[--tv->n_held];
+                break;
+            }
 }
 
 static int tv_open_channel(ottgpu_transvideo *tv, const dataqueue_message_struct *msg)
@@ -39,6 +67,7 @@ static int tv_open_channel(ottgpu_transvideo *tv, const dataqueue_message_struct
     if (tv->channel && tv->chan_width == msg->width && tv->chan_height == msg->height && tv->chan_deint == deint) return 0;
     if (tv->channel) ottgpu_channel_destroy(tv->channel);   /* the reference never re-keys its scalers (latent bug) */
     tv->channel = NULL;
+    tv_release_held(tv);
     memset(&cfg, 0, sizeof(cfg));
     cfg.gpu = tv->gpu;
     cfg.src_width = msg->width;
@@ -127,16 +156,17 @@ int ottgpu_transvideo_process(ottgpu_transvideo *tv, dataqueue_message_struct *m
     tv->frames_in++;
     if (tv_open_channel(tv, msg) != 0) {
         tv_fatal(tv, OTTGPU_SIGNAL_DIRECT_ERROR_RAWPOOL, ottgpu_last_error());
-        tv_return_input(tv, msg);
+        tv_return_input(tv, msg, 0);
         return -1;
     }
     if (msg->source_discontinuity) {                         /* transvideo.c:1959-1970 */
         ottgpu_channel_reset(tv->channel);
+        tv_release_held(tv);
         msg->source_discontinuity = 0;
     }
     /* sideband for this frame (transvideo.c:2103-2128); it comes back with the frame it belongs to */
     sb = (tv_sideband *)calloc(1, sizeof(*sb));
-    if (!sb) { tv_return_input(tv, msg); return -1; }
+    if (!sb) { tv_return_input(tv, msg, 0); return -1; }
     if (msg->caption_buffer) {
         sb->caption_buffer = msg->caption_buffer;
         sb->caption_size = msg->caption_size;
@@ -153,7 +183,7 @@ int ottgpu_transvideo_process(ottgpu_transvideo *tv, dataqueue_message_struct *m
     memset(&in, 0, sizeof(in));
     memset(&out, 0, sizeof(out));
     in.data = msg->buffer;
-    in.mem = OTTGPU_MEM_HOST;
+    in.mem = (msg->flags & OTTGPU_MSG_FLAG_DEVICE) ? OTTGPU_MEM_DEVICE : OTTGPU_MEM_HOST;
     in.interlaced = msg->interlaced;                         /* transvideo.c:2100-2101 */
     in.tff = msg->tff;
     in.pts = msg->pts;
@@ -170,18 +200,19 @@ int ottgpu_transvideo_process(ottgpu_transvideo *tv, dataqueue_message_struct *m
             tv_fatal(tv, OTTGPU_SIGNAL_DIRECT_ERROR_RAWPOOL, "Out of Uncompressed Video Buffers (SCALE) - Restarting Service");
             for (k = 0; k < i; ++k) tv_return_rung(tv, k, out.dst[k]);
             free(sb);
-            tv_return_input(tv, msg);
+            tv_return_input(tv, msg, 0);
             return -1;
         }
     }
     rc = ottgpu_channel_submit(tv->channel, &in, &out);
+    if (rc == OTTGPU_OK) tv_settle_inputs(tv, in.mem == OTTGPU_MEM_DEVICE ? msg->buffer : NULL, &out);
     if (rc != OTTGPU_OK || !out.produced) {
         for (i = 0; i < tv->num_outputs; ++i) tv_return_rung(tv, i, out.dst[i]);
         if (rc != OTTGPU_OK) {
             tv_fatal(tv, OTTGPU_SIGNAL_DIRECT_ERROR_RAWPOOL, ottgpu_last_error());
             free(sb);
         }
-        tv_return_input(tv, msg);                            /* the host copy of the frame is no longer needed */
+        tv_return_input(tv, msg, rc == OTTGPU_OK);           /* the host copy of the frame is no longer needed */
         return rc == OTTGPU_OK ? 0 : -1;
     }
 
@@ -224,7 +255,7 @@ int ottgpu_transvideo_process(ottgpu_transvideo *tv, dataqueue_message_struct *m
                     for (i = 0; i < tv->num_outputs; ++i) tv_return_rung(tv, i, out.dst[i]);
                     free(osb->caption_buffer);
                     free(osb);
-                    tv_return_input(tv, msg);
+                    tv_return_input(tv, msg, 1);
                     return -1;
                 }
             } else {
@@ -275,7 +306,7 @@ int ottgpu_transvideo_process(ottgpu_transvideo *tv, dataqueue_message_struct *m
         }
         free(osb);
     }
-    tv_return_input(tv, msg);
+    tv_return_input(tv, msg, 1);
     return 0;
 }
 
@@ -290,7 +321,7 @@ void *ottgpu_video_prepare_scale_thread(void *context)
         }
         if (!*tv->running) {                                 /* drain, transvideo.c:1940-1952 */
             while (msg) {
-                tv_return_input(tv, msg);
+                tv_return_input(tv, msg, 0);
                 msg = dataqueue_take_back(tv->prepare_queue);
             }
             break;
@@ -305,4 +336,5 @@ void ottgpu_transvideo_close(ottgpu_transvideo *tv)
 {
     if (tv->channel) ottgpu_channel_destroy(tv->channel);    /* avfilter_graph_free / sws_freeContext, 2416-2427 */
     tv->channel = NULL;
+    tv_release_held(tv);
 }

@@ -51,6 +51,11 @@ typedef struct ottgpu_transvideo {
     int64_t deinterlaced_frame_count;
     int   av_sync_compromised;
     int64_t frames_in, frames_out, thumbnails_out;
+    /* ---- device-resident input frames (decode stage ran ottgpu_converter_convert with OTTGPU_MEM_DEVICE and tagged the
+     *      message OTTGPU_MSG_FLAG_DEVICE): the pool they go back to once the deinterlacer window has moved past them ---- */
+    ottgpu_pool *input_pool;
+    void *held_inputs[8];
+    int   n_held;
 } ottgpu_transvideo;
 
 /* pthread body: replaces video_prepare_thread + video_scale_thread.  context = ottgpu_transvideo*.

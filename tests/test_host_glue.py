@@ -36,7 +36,8 @@ class TV(C.Structure):                        # ott-packager_b200/host/transvide
                 ("signal", SIGNAL_FN), ("direct_error", SIGNAL_FN), ("user", C.c_void_p), ("channel", C.c_void_p),
                 ("chan_width", C.c_int), ("chan_height", C.c_int), ("chan_deint", C.c_int),
                 ("deinterlaced_frame_count", C.c_int64), ("av_sync_compromised", C.c_int), ("frames_in", C.c_int64),
-                ("frames_out", C.c_int64), ("thumbnails_out", C.c_int64)]
+                ("frames_out", C.c_int64), ("thumbnails_out", C.c_int64), ("input_pool", C.c_void_p),
+                ("held_inputs", C.c_void_p * 8), ("n_held", C.c_int)]
 
 
 @pytest.fixture(scope="module")
@@ -238,3 +239,50 @@ def test_av_sync_repeat_and_drop(lib, og, oracle, rt, host):
     got2 = _drain(rt, tv2, tv2.encode_queue[0], oracle.i420_size(64, 40))
     assert len(got2) < 7
     host.ottgpu_transvideo_close(C.byref(tv2))
+
+
+def test_device_resident_inputs_from_the_converter(lib, og, oracle, rt, host):
+    """Decode stage converts a 4:2:2 10-bit picture on the GPU and leaves the packed frame there
+    (ottgpu_converter_convert, OTTGPU_MEM_DEVICE); the message is tagged OTTGPU_MSG_FLAG_DEVICE and the thread body feeds
+    the frame to the channel without a host round trip, returning it to its pool when the yadif window lets go of it."""
+    from conftest import decoded_planes
+    w, h = 192, 108
+    outs = [(192, 108), (96, 54)]
+    errors, signals = [], []
+    tv = _make_tv(rt, outs, errors, signals)
+    in_pool = og.Pool(lib, 0, og.MEM_DEVICE, 5, lib.frame_bytes(og.FMT_I420, w, h))
+    tv.input_pool = in_pool.handle
+    cv = og.Converter(lib, og.PIX_YUV422P10, w, h)
+    ref = oracle.YadifStream(w, h)
+    expected = []
+    for i in range(7):
+        planes = decoded_planes("yuv422p10le", w, h, 400 + i, "noise", pad=4)
+        frame = oracle.convert_to_i420(planes, oracle.PIX_YUV422P10, w, h)
+        buf = in_pool.take()
+        assert buf, "input pool ran dry: released frames are not coming back"
+        cv.convert(planes, device_dst=buf)
+        m = C.cast(rt.memory_take(tv.msg_pool, C.sizeof(Msg)), C.POINTER(Msg))
+        C.memset(m, 0, C.sizeof(Msg))
+        m.contents.buffer, m.contents.buffer_size, m.contents.flags = buf, frame.nbytes, 0x4f540001
+        m.contents.pts, m.contents.dts = 9000 * i, 9000 * i - 3003
+        m.contents.width, m.contents.height = w, h
+        m.contents.interlaced, m.contents.tff = 1, 1
+        m.contents.fps_num, m.contents.fps_den = 30000, 1001
+        m.contents.source_discontinuity = 1 if i == 4 else 0
+        assert host.ottgpu_transvideo_process(C.byref(tv), m) == 0
+        if i == 4:
+            ref.reset()
+        r = ref.push(frame, 1, 1, tag=i)
+        if r is not None:
+            expected.append(r)
+    assert not errors
+    for k, (dw, dh) in enumerate(outs):
+        got = _drain(rt, tv, tv.encode_queue[k], oracle.i420_size(dw, dh))
+        assert [g["pts"] for g in got] == [9000 * tag for _, tag in expected]
+        for g, (deint, tag) in zip(got, expected):
+            assert np.array_equal(g["data"], oracle.scale_i420(deint, w, h, dw, dh)), (k, tag)
+    assert 0 < tv.n_held <= 3                               # the window still references the newest frames ...
+    host.ottgpu_transvideo_close(C.byref(tv))
+    assert tv.n_held == 0 and in_pool.unused() == 5         # ... and closing hands every one of them back
+    cv.close()
+    in_pool.close()
