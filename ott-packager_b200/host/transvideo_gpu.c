@@ -265,8 +265,9 @@ int ottgpu_transvideo_process(ottgpu_transvideo *tv, dataqueue_message_struct *m
             drop = sync_diff > 1 && (osb->splice_point == 0 || osb->splice_duration_remaining == 0);   /* 2366-2382 */
         }
 
-        if (repeat && !tv->device_outputs) {
-            /* repeat the frame to maintain A/V sync (transvideo.c:2271-2316): same pictures, pts/dts 0, no captions */
+        if (repeat) {
+            /* repeat the frame to maintain A/V sync (transvideo.c:2271-2316): same pictures, pts/dts 0, no captions.
+             * Device surfaces are duplicated on the device (no host round trip). */
             tv_sideband rsb = *osb;
             rsb.pts = rsb.dts = 0;
             rsb.caption_buffer = NULL;
@@ -274,13 +275,14 @@ int ottgpu_transvideo_process(ottgpu_transvideo *tv, dataqueue_message_struct *m
             rsb.caption_timestamp = 0;
             if (tv->signal) tv->signal(tv->user, OTTGPU_SIGNAL_FRAME_REPEAT, "Repeating Video Frame To Maintain A/V Sync");
             for (i = 0; i < tv->num_outputs; ++i) {
-                void *copy = memory_take(tv->raw_video_pool, (int)bytes[i]);
+                void *copy = tv_take_rung(tv, i, bytes[i]);
                 if (!copy) {
                     tv_fatal(tv, OTTGPU_SIGNAL_DIRECT_ERROR_RAWPOOL, "Out of Uncompressed Video Buffers (SYNC) - Restarting Service");
                     break;
                 }
-                memcpy(copy, out.dst[i], bytes[i]);
-                if (tv_emit(tv, i, copy, bytes[i], &rsb, 0) != 0) { memory_return(tv->raw_video_pool, copy); break; }
+                if (tv->device_outputs) ottgpu_memcpy(tv->gpu, copy, OTTGPU_MEM_DEVICE, out.dst[i], OTTGPU_MEM_DEVICE, bytes[i]);
+                else memcpy(copy, out.dst[i], bytes[i]);
+                if (tv_emit(tv, i, copy, bytes[i], &rsb, 0) != 0) { tv_return_rung(tv, i, copy); break; }
             }
             tv->deinterlaced_frame_count++;
         }

@@ -286,3 +286,38 @@ def test_device_resident_inputs_from_the_converter(lib, og, oracle, rt, host):
     assert tv.n_held == 0 and in_pool.unused() == 5         # ... and closing hands every one of them back
     cv.close()
     in_pool.close()
+
+
+def test_av_sync_repeat_with_device_surfaces(lib, og, oracle, rt, host):
+    """NVENC mode (device_outputs=1): a repeated frame is a second device surface with the same pixels, duplicated on
+    the device (transvideo.c:2271-2316 copies on the host)."""
+    w, h = 96, 64
+    dw, dh = 64, 40
+    errors, signals = [], []
+    tv = _make_tv(rt, [(dw, dh)], errors, signals, first_ts=0)
+    tv.device_outputs, tv.out_fmt = 1, og.FMT_NV12
+    rung = og.RungCfg(dw, dh, og.FMT_NV12, 0)
+    nbytes = lib.rung_bytes(rung)
+    pool = og.Pool(lib, 0, og.MEM_DEVICE, 16, nbytes)
+    tv.surface_pool[0] = pool.handle
+    f = natural_i420(w, h, 7)
+    for i in range(4):                                   # dts runs 4 frame-times per frame => repeats
+        m = _push(rt, tv, f, w, h, 3003 + 4 * 3003 * i, interlaced=0, fps=(60000, 1001))
+        assert host.ottgpu_transvideo_process(C.byref(tv), m) == 0
+    want = oracle.i420_to_nv12(oracle.scale_i420(f, w, h, dw, dh), dw, dh)
+    seen, repeats = set(), 0
+    while True:
+        m = rt.dataqueue_take_back(tv.encode_queue[0])
+        if not m:
+            break
+        c = m.contents
+        assert c.flags & 0xffff00ff == 0x4f540001 and c.buffer not in seen
+        seen.add(c.buffer)
+        repeats += c.pts == 0
+        assert np.array_equal(lib.from_device(c.buffer, nbytes), want)
+        pool.give_back(c.buffer)
+        rt.memory_return(tv.msg_pool, m)
+    assert repeats >= 1 and len(seen) > 3 and not errors
+    host.ottgpu_transvideo_close(C.byref(tv))
+    assert pool.unused() == 16
+    pool.close()
