@@ -36,6 +36,8 @@ struct PlaneTables {
     const uint32_t *hc_hi;   // [dstW][hq] 8-bit path: per tap quad, high bytes  (coef >> 8, signed)   packed s8x4
     const uint32_t *hc_lo;   // [dstW][hq]                          low bytes   (coef & 255, unsigned) packed u8x4
     const int16_t *hc16;     // [dstW][4*hq] plain 14-bit coefficients (16-bit sample path)
+    const uint32_t *hc_pair; // [dstW][hq+1][2] 8-bit path: s16x2 coefficient pairs laid out against the source WORDS the
+                             //   window starts in (taps shifted by hpos&3 bytes, zero padded): {bytes 0,1}, {bytes 2,3}
     const int32_t *vpos;     // [dstH]   first source row of each output row
     const int16_t *vc;       // [dstH][vtaps] 12-bit coefficients
     int srcW, srcH, dstW, dstH;

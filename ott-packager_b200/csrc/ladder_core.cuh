@@ -48,6 +48,11 @@ inline uint32_t ott_dp2a_uu(uint32_t a, uint32_t b, uint32_t c, int hi)
     const uint32_t bb = hi ? b >> 16 : b;
     return c + (a & 0xffffu) * (bb & 255) + (a >> 16) * ((bb >> 8) & 255);
 }
+inline int ott_dp2a_su(uint32_t a, uint32_t b, int c, int hi)      // two s16 of a x two u8 of b (bytes 0,1 or 2,3)
+{
+    const uint32_t bb = hi ? b >> 16 : b;
+    return c + (int)(int16_t)(a & 0xffffu) * (int)(bb & 255) + (int)(int16_t)(a >> 16) * (int)((bb >> 8) & 255);
+}
 template <typename T> inline T ott_ldg(const T *p) { return *p; }
 inline int ott_sad(int a, int b, int c) { return (a > b ? a - b : b - a) + c; }
 inline int ott_byte(uint32_t w, int i) { return (int)((w >> (8 * i)) & 0xffu); }
@@ -71,6 +76,13 @@ OTT_DEV int ott_dp2a_us(uint32_t a, uint32_t b, int c, int hi)
     int d;
     if (hi) asm("dp2a.hi.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     else asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+OTT_DEV int ott_dp2a_su(uint32_t a, uint32_t b, int c, int hi)
+{
+    int d;
+    if (hi) asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    else asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
 OTT_DEV uint32_t ott_dp2a_uu(uint32_t a, uint32_t b, uint32_t c, int hi)
@@ -222,21 +234,19 @@ OTT_DEV void phase_fixup16(int tid, const TileGeom &g, unsigned char *smem)
 // Thread = one output column of the tile (its coefficients live in registers), striding over the staged rows.
 // 8-bit: four taps per dp4a, 14-bit coefficient split into signed high byte and unsigned low byte:
 //        sum p*c = 256*sum p*(c>>8) + sum p*(c&255)   (exact)
+// Fixed-length filters: the 14-bit coefficients are used whole, as s16 pairs against two source bytes each (dp2a),
+// positioned at table-build time against the aligned source words the window starts in - no shift, no hi/lo recombination.
 template <int HQ>
-OTT_DEV int hdot8(const uint32_t *w, uint32_t sh, const uint32_t (&hi)[HQ], const uint32_t (&lo)[HQ])
+OTT_DEV int hdot8(const uint32_t *w, const uint32_t (&c01)[HQ + 1], const uint32_t (&c23)[HQ + 1])
 {
-    uint32_t cur = w[0];
-    int ahi = 0;
-    uint32_t alo = 0;
+    int a = 0;
     OTT_UNROLL
-    for (int q = 0; q < HQ; ++q) {
-        const uint32_t nxt = w[q + 1];
-        const uint32_t a = ott_funnel_r(cur, nxt, sh);
-        ahi = ott_dp4a_us(a, hi[q], ahi);
-        alo = ott_dp4a_uu(a, lo[q], alo);
-        cur = nxt;
+    for (int q = 0; q <= HQ; ++q) {
+        const uint32_t s = w[q];
+        a = ott_dp2a_su(c01[q], s, a, 0);
+        a = ott_dp2a_su(c23[q], s, a, 1);
     }
-    return ott_min((ahi * 256 + (int)alo) >> 7, 32767);
+    return ott_min(a >> 7, 32767);
 }
 
 template <int HQ>
@@ -247,12 +257,12 @@ OTT_DEV void hpass8(int tid, const TileGeom &g, unsigned char *smem)
     if (col >= g.tw) return;
     const int gx = g.x0 + col;
     const int off = ott_ldg(T.hpos + gx) - g.sx0;
-    const uint32_t sh = (uint32_t)(off & 3) * 8;
-    uint32_t hi[HQ], lo[HQ];
+    uint32_t c01[HQ + 1], c23[HQ + 1];
     OTT_UNROLL
-    for (int q = 0; q < HQ; ++q) {
-        hi[q] = ott_ldg(T.hc_hi + gx * HQ + q);
-        lo[q] = ott_ldg(T.hc_lo + gx * HQ + q);
+    for (int q = 0; q <= HQ; ++q) {
+        const uint2 c = ott_ldg(reinterpret_cast<const uint2 *>(T.hc_pair) + gx * (HQ + 1) + q);
+        c01[q] = c.x;
+        c23[q] = c.y;
     }
     const int sr = g.sr, nplanes = g.nplanes, pstride = g.plane_stride >> 2;
     const int wstep = ngroups * g.spw, mstep = ngroups * g.mid_pitch;
@@ -261,10 +271,10 @@ OTT_DEV void hpass8(int tid, const TileGeom &g, unsigned char *smem)
         mid_t *m = reinterpret_cast<mid_t *>(smem + g.off_mid) + col + (p * sr + grp) * g.mid_pitch;
         int left = (sr - grp + ngroups - 1) / ngroups;         // rows this thread owns in this plane
         for (; left >= 4; left -= 4) {                         // four rows in flight per thread
-            const int v0 = hdot8<HQ>(w, sh, hi, lo);
-            const int v1 = hdot8<HQ>(w + wstep, sh, hi, lo);
-            const int v2 = hdot8<HQ>(w + 2 * wstep, sh, hi, lo);
-            const int v3 = hdot8<HQ>(w + 3 * wstep, sh, hi, lo);
+            const int v0 = hdot8<HQ>(w, c01, c23);
+            const int v1 = hdot8<HQ>(w + wstep, c01, c23);
+            const int v2 = hdot8<HQ>(w + 2 * wstep, c01, c23);
+            const int v3 = hdot8<HQ>(w + 3 * wstep, c01, c23);
             m[0] = (mid_t)v0;
             m[mstep] = (mid_t)v1;
             m[2 * mstep] = (mid_t)v2;
@@ -273,7 +283,7 @@ OTT_DEV void hpass8(int tid, const TileGeom &g, unsigned char *smem)
             m += 4 * mstep;
         }
         for (; left > 0; --left) {
-            m[0] = (mid_t)hdot8<HQ>(w, sh, hi, lo);
+            m[0] = (mid_t)hdot8<HQ>(w, c01, c23);
             w += wstep;
             m += mstep;
         }

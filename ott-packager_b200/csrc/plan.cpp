@@ -76,7 +76,8 @@ size_t env_kb(const char *name, size_t dflt_kb)
 }
 const size_t kSrcCap = env_kb("OTTGPU_SRC_CAP_KB", sizeof(mid_t) == 4 ? 22 : 36);   // one staged-source buffer
 const size_t kMidCap = env_kb("OTTGPU_MID_CAP_KB", sizeof(mid_t) == 4 ? 54 : 36);   // H-pass result region
-const int kMaxTileRows = (int)(env_kb("OTTGPU_MAX_TILE_ROWS", 128) / 1024);          // keeps enough tiles per frame for load balance
+const int kMaxTileRows = (int)(env_kb("OTTGPU_MAX_TILE_ROWS", 128) / 1024);
+const int kTileRounds = [] { const char *v = std::getenv("OTTGPU_TILE_ROUNDS"); return v ? std::atoi(v) : 1; }();   // 1: also try tile heights that fill whole V rounds          // keeps enough tiles per frame for load balance
 constexpr size_t kSmemHardLimit = 224 * 1024; // == kMaxTileSmem (kernels.h); sm_100 allows 227 KB per CTA
 
 template <typename T>
@@ -128,6 +129,20 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
             hi[(size_t)x * hq + q] = a;
             lo[(size_t)x * hq + q] = b;
         }
+    // 8-bit fixed-length path: coefficient pairs positioned against the aligned source words, so the kernel needs no
+    // funnel shift and no hi/lo split (tile origins are multiples of 16 samples, so hpos & 3 is the byte offset in every tile)
+    std::vector<uint32_t> pairs;
+    if (bps == 1 && px_bytes == 1) {
+        pairs.assign((size_t)dstW * 2 * (hq + 1), 0);
+        for (int x = 0; x < dstW; ++x) {
+            const int sh = h.pos[x] & 3;
+            for (int b = 0; b < 4 * (hq + 1); ++b) {
+                const int j = b - sh;
+                const uint32_t c = (j >= 0 && j < h.taps) ? (uint16_t)h.coef[(size_t)x * h.taps + j] : 0u;
+                pairs[((size_t)x * (hq + 1) + (b >> 2)) * 2 + ((b >> 1) & 1)] |= c << (16 * (b & 1));
+            }
+        }
+    }
     T.srcW = srcW; T.srcH = srcH; T.dstW = dstW; T.dstH = dstH;
     T.hq = hq;
     T.vtaps = v.taps;
@@ -164,7 +179,7 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
     auto model = [&](int tw, int th, int cpt, int sr) {
         const int ngroups = kThreads / tw;
         const double hrows = (double)((nplanes * sr + ngroups - 1) / ngroups) * ngroups;          // rows incl. idle groups
-        const double h_instr = hrows * tw * (9.0 + 4.0 * hq);
+        const double h_instr = hrows * tw * (6.0 + 3.0 * hq);
         const int units = th * tw / cpt;
         const double vunits = (double)((units + kThreads - 1) / kThreads) * kThreads;
         const double v_instr = vunits * nplanes * cpt * (3.3 * v.taps + 12.0) + vunits * 70.0;
@@ -234,9 +249,10 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
     T.hc_hi = upload(plan, hi, err);
     T.hc_lo = upload(plan, lo, err);
     T.hc16 = upload(plan, c16, err);
+    T.hc_pair = upload(plan, pairs, err);
     T.vpos = upload(plan, v.pos, err);
     T.vc = upload(plan, v.coef, err);
-    return T.hpos && T.hc_hi && T.hc_lo && T.hc16 && T.vpos && T.vc;
+    return T.hpos && T.hc_hi && T.hc_lo && T.hc16 && T.hc_pair && T.vpos && T.vc;
 }
 
 void copy_tiling(PlaneTables &T, int w, int h)
