@@ -279,7 +279,7 @@ def reference_main(args, wl, rank, world):
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -292,8 +292,7 @@ def ours_main(args, wl, rank, world, local_rank):
     dist = None
     if world > 1:
         # keep stdout to the single JSON line: NCCL prints its version banner there at VERSION/INFO level
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL logs (version banner included) off stdout
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = og.Library()
@@ -542,9 +541,28 @@ def ours_main(args, wl, rank, world, local_rank):
             "clocks": sampler.result()}
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
+
+
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """The driver reads ONE JSON line from stdout.  Libraries print there too (NCCL's version banner, for one), so the
+    real stdout is set aside for emit() and everything else written to fd 1 from here on goes to stderr."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, data)
 
 
 def main():
@@ -558,6 +576,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

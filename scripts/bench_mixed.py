@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=8)
     args = ap.parse_args()
+    B.claim_stdout()
     import torch
     og = importlib.import_module("ott-packager_b200")
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -39,8 +40,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = og.Library()
@@ -135,14 +135,14 @@ def main():
         # real-time factor: one step must not take longer than the fastest channel's frame period (4K60: 16.68 ms)
         rt = (1000.0 / (60000 / 1001.0)) / (ms / args.steps)
         ert = (1000.0 / (60000 / 1001.0)) / (ems / args.steps)
-        print(json.dumps({"metric": "ladder_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        B.emit({"metric": "ladder_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
                           "dtype": "u8", "data": "synthetic",
                           "config": {"workload": "cfg5: 16 x 2160p60 (4 rungs) + 48 x 1080i (yadif + 4 rungs), 176x144 thumbnails /150, "
                                                  "channel-sharded, stepped in lock-step (the 1080i channels are advanced at the 4K rate)",
                                      "channels": total, "channels_rank0": n, "realtime_factor": rt},
                           "e2e": {"value": efps, "unit": "frames/s", "ms_per_step": ems / args.steps, "realtime_factor": ert},
-                          "gpu_launches": launches}))
+                          "gpu_launches": launches})
     if dist is not None:
         dist.destroy_process_group()
 
