@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(256) yadif_kernel(const YadifJob *__restrict__
     const YadifJob &j = jobs[blockIdx.z];
     if (!j.active) return;
     const int gx = blockIdx.x * 32 + (threadIdx.x & 31), gy = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (j.fast) yadif_position_fast(j, gx, gy);          // gx counts 8-sample groups; rows cover luma then chroma
+    if (j.fast) yadif_position_fast(j, gx, gy);          // gx counts 8-sample groups, gy row pairs (luma then chroma)
     else yadif_position(j, gx, gy);
 }
 
@@ -234,9 +234,11 @@ cudaError_t launch_ladder(LadderLaunch L, cudaStream_t s)
 cudaError_t launch_yadif(const YadifJob *jobs, int n_jobs, int max_w, int max_h, bool all_fast, cudaStream_t s)
 {
     if (n_jobs <= 0) return cudaSuccess;
-    // fast jobs need (w/4) x (h + h/2) positions, slow ones w x h: launch the union (extra CTAs exit at once)
+    // fast jobs need (w/8) x (row pairs of luma and chroma) positions, slow ones w x h: launch the union (extra CTAs
+    // exit at once)
     const int cols = all_fast ? (max_w / 8 + 31) / 32 : (max_w + 31) / 32;
-    dim3 grid(cols, ((max_h + (max_h + 1) / 2) + 7) / 8, n_jobs);
+    const int rows = all_fast ? (max_h + 1) / 2 + ((max_h + 1) / 2 + 1) / 2 : max_h + (max_h + 1) / 2;
+    dim3 grid(cols, (rows + 7) / 8, n_jobs);
     yadif_kernel<<<grid, 256, 0, s>>>(jobs);
     return cudaGetLastError();
 }

@@ -84,6 +84,15 @@ OTT_DEV void yadif_position(const YadifJob &j, int x, int y)
 // direction search of filter_line_c becomes predicated selects.
 OTT_DEV int ybyte(uint32_t w, int i) { return ott_byte(w, i); }
 
+// kept-field row: 8 samples copied
+OTT_DEV void yadif_keep8(const YadifJob &j, size_t off, int w, int x8, int y)
+{
+    const int i0 = y * (w >> 2) + 2 * x8;
+    *reinterpret_cast<uint2 *>(reinterpret_cast<uint32_t *>(j.dst + off) + i0) =
+        ott_ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const uint32_t *>(j.cur + off) + i0));
+}
+
+// interpolated row: 8 samples predicted
 OTT_DEV void yadif_oct8(const YadifJob &j, size_t off, int w, int h, int x8, int y)
 {
     const uint32_t *prev = reinterpret_cast<const uint32_t *>(j.prev + off), *cur = reinterpret_cast<const uint32_t *>(j.cur + off);
@@ -91,11 +100,6 @@ OTT_DEV void yadif_oct8(const YadifJob &j, size_t off, int w, int h, int x8, int
     uint32_t *dst = reinterpret_cast<uint32_t *>(j.dst + off);
     const int wq = w >> 2;                                 // words per row
     const int i0 = y * wq + 2 * x8;
-    if (!((y ^ j.parity) & 1)) {
-        const uint2 v = ott_ldg(reinterpret_cast<const uint2 *>(cur + i0));
-        *reinterpret_cast<uint2 *>(dst + i0) = v;
-        return;
-    }
     const int dn = y + 1 < h ? wq : -wq, up = y ? -wq : wq;
     const bool first_field = (j.parity ^ j.tff) != 0;
     const uint32_t *p2 = first_field ? prev : cur, *n2 = first_field ? cur : next;
@@ -160,19 +164,31 @@ OTT_DEV void yadif_oct8(const YadifJob &j, size_t off, int w, int h, int x8, int
     *reinterpret_cast<uint2 *>(dst + i0) = o;
 }
 
-// Fast-path thread position: (x8, r) over a grid of (w/8) x (h + ch) positions; rows >= h are chroma rows with the U
-// samples in the left half and the V samples in the right half.
-OTT_DEV void yadif_position_fast(const YadifJob &j, int x8, int r)
+// Fast-path thread position: (x8, rp) over a grid of (w/8) x (row pairs of luma + row pairs of chroma) positions; a
+// thread produces the kept row AND the interpolated row of its pair, so every warp of a block carries the same load
+// (with one row per thread half of the warps would only copy and leave their slots idle until the block retires).
+// Chroma row pairs hold the U samples in the left half and the V samples in the right half.
+OTT_DEV void yadif_pair8(const YadifJob &j, size_t off, int w, int h, int x8, int rp)
+{
+    const int kept = 2 * rp + (j.parity & 1), other = 2 * rp + 1 - (j.parity & 1);      // rows with (y ^ parity) & 1 == 0 are kept
+    if (kept < h) yadif_keep8(j, off, w, x8, kept);
+    if (other < h) yadif_oct8(j, off, w, h, x8, other);
+}
+
+OTT_DEV int yadif_fast_rows(int h) { return ((h + 1) >> 1) + ((((h + 1) >> 1) + 1) >> 1); }   // row pairs: luma + chroma
+
+OTT_DEV void yadif_position_fast(const YadifJob &j, int x8, int rp)
 {
     const int w = j.width, h = j.height, cw = w >> 1, ch = (h + 1) >> 1;
     if (x8 >= (w >> 3)) return;
-    if (r < h) { yadif_oct8(j, 0, w, h, x8, r); return; }
-    r -= h;
-    if (r >= ch) return;
+    const int lp = (h + 1) >> 1;
+    if (rp < lp) { yadif_pair8(j, 0, w, h, x8, rp); return; }
+    rp -= lp;
+    if (rp >= ((ch + 1) >> 1)) return;
     const int co = cw >> 3;
     const size_t uo = (size_t)w * h, vo = uo + (size_t)cw * ch;
-    if (x8 < co) yadif_oct8(j, uo, cw, ch, x8, r);
-    else yadif_oct8(j, vo, cw, ch, x8 - co, r);
+    if (x8 < co) yadif_pair8(j, uo, cw, ch, x8, rp);
+    else yadif_pair8(j, vo, cw, ch, x8 - co, rp);
 }
 
 }  // namespace ottgpu
