@@ -1,7 +1,7 @@
 // sm_100a kernels of libottgpu.
 //   ladder_kernel : persistent fused H+V polyphase scaler / format writer.  Each CTA pulls output tiles (work items:
 //                   all rungs of all channels of a batch) from a global counter; the tile's source rows are fetched by
-//                   the TMA engine (cp.async.bulk global->shared, mbarrier completion) into one of two shared buffers
+//                   the TMA engine (one 2-D tensor-map box per plane, mbarrier completion) into one of two shared buffers
 //                   while the previous tile is still computing.  The source frame is read from HBM once and shared by
 //                   the rungs through L2 (items are ordered by source row band), see DESIGN.md.
 //   yadif_kernel  : yadif mode 0 first-field deinterlacer on planar 8/16-bit frames.
@@ -25,12 +25,6 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
 }
 // one 2-D box (tensor map coordinates: x in 32-bit elements, y in rows) -> shared memory, completion on `bar`
 __device__ __forceinline__ void tma_box_2d(void *dst_smem, const void *tmap, int x, int y, uint64_t *bar)
@@ -80,13 +74,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 }
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); }
 
-constexpr int kLadderThreads = kThreads + 32;     // 8 compute warps + 1 producer warp
+constexpr int kLadderThreads = kThreads + 32;     // 12 compute warps + 1 producer warp
 
 // Warp-specialised persistent kernel.
 //   producer warp : pulls work items from the global counter and resolves their geometry into a ring of kGeomSlots
-//                   shared descriptors, running ahead of the compute warps; for tiles whose rows can be bulk-copied it
-//                   waits for a free source buffer and has the TMA engine copy the rows (one cp.async.bulk per row);
-//                   completion (transaction bytes) is signalled on the descriptor's `ready` mbarrier.
+//                   shared descriptors, running ahead of the compute warps; it copies the tile's V tables into the
+//                   descriptor's table region, waits for a free source buffer and has the TMA engine fetch the tile's
+//                   source window (one 2-D tensor-map box per staged plane); completion (transaction bytes) is
+//                   signalled on the descriptor's `ready` mbarrier.
 //   compute warps : wait ready[slot] -> H pass (staged rows -> int16 intermediates) -> V pass + store -> release the
 //                   descriptor slot and the source buffer.
 // Two source buffers: tile k+1 streams in while tile k computes.
