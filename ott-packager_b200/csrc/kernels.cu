@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
     }
 }
 
-__global__ void __launch_bounds__(256) yadif_kernel(const YadifJob *__restrict__ jobs)
+__global__ void __launch_bounds__(256, 4) yadif_kernel(const YadifJob *__restrict__ jobs)
 {
     const YadifJob &j = jobs[blockIdx.z];
     if (!j.active) return;

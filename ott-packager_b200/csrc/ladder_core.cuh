@@ -53,6 +53,35 @@ inline int ott_dp2a_su(uint32_t a, uint32_t b, int c, int hi)      // two s16 of
     const uint32_t bb = hi ? b >> 16 : b;
     return c + (int)(int16_t)(a & 0xffffu) * (int)(bb & 255) + (int)(int16_t)(a >> 16) * (int)((bb >> 8) & 255);
 }
+inline uint32_t ott_prmt(uint32_t a, uint32_t b, uint32_t sel)     // byte permute, selector nibbles 0-7 (no sign replication)
+{
+    const uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int k = 0; k < 4; ++k) r |= (uint32_t)((v >> (8 * ((sel >> (4 * k)) & 7))) & 0xffu) << (8 * k);
+    return r;
+}
+inline uint32_t ott_vabsdiff4(uint32_t a, uint32_t b)              // per-byte |a-b|
+{
+    uint32_t r = 0;
+    for (int k = 0; k < 4; ++k) {
+        const int x = (int)((a >> (8 * k)) & 255) - (int)((b >> (8 * k)) & 255);
+        r |= (uint32_t)(x < 0 ? -x : x) << (8 * k);
+    }
+    return r;
+}
+inline uint32_t ott_lanes16(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+inline int ott_lane_lo(uint32_t v) { return (int)(int16_t)(v & 0xffffu); }
+inline int ott_lane_hi(uint32_t v) { return (int)(int16_t)(v >> 16); }
+inline uint32_t ott_vmax_s16x2(uint32_t a, uint32_t b)
+{
+    return ott_lanes16(ott_lane_lo(a) > ott_lane_lo(b) ? ott_lane_lo(a) : ott_lane_lo(b), ott_lane_hi(a) > ott_lane_hi(b) ? ott_lane_hi(a) : ott_lane_hi(b));
+}
+inline uint32_t ott_vmin_s16x2(uint32_t a, uint32_t b)
+{
+    return ott_lanes16(ott_lane_lo(a) < ott_lane_lo(b) ? ott_lane_lo(a) : ott_lane_lo(b), ott_lane_hi(a) < ott_lane_hi(b) ? ott_lane_hi(a) : ott_lane_hi(b));
+}
+inline uint32_t ott_vmax3_s16x2(uint32_t a, uint32_t b, uint32_t c) { return ott_vmax_s16x2(ott_vmax_s16x2(a, b), c); }
+inline uint32_t ott_vmin3_s16x2(uint32_t a, uint32_t b, uint32_t c) { return ott_vmin_s16x2(ott_vmin_s16x2(a, b), c); }
 template <typename T> inline T ott_ldg(const T *p) { return *p; }
 inline int ott_sad(int a, int b, int c) { return (a > b ? a - b : b - a) + c; }
 inline int ott_byte(uint32_t w, int i) { return (int)((w >> (8 * i)) & 0xffu); }
@@ -92,6 +121,12 @@ OTT_DEV uint32_t ott_dp2a_uu(uint32_t a, uint32_t b, uint32_t c, int hi)
     else asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
+OTT_DEV uint32_t ott_prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+OTT_DEV uint32_t ott_vabsdiff4(uint32_t a, uint32_t b) { return __vabsdiffu4(a, b); }                 // VABSDIFF4.U8
+OTT_DEV uint32_t ott_vmax_s16x2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }                    // VIMNMX.S16x2
+OTT_DEV uint32_t ott_vmin_s16x2(uint32_t a, uint32_t b) { return __vmins2(a, b); }
+OTT_DEV uint32_t ott_vmax3_s16x2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }   // VIMNMX3.S16x2
+OTT_DEV uint32_t ott_vmin3_s16x2(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_s16x2(a, b, c); }
 template <typename T> OTT_DEV T ott_ldg(const T *p) { return __ldg(p); }
 OTT_DEV int ott_sad(int a, int b, int c) { return (int)__sad(a, b, (unsigned)c); }   // |a-b|+c in one VABSDIFF
 OTT_DEV int ott_byte(uint32_t w, int i) { return (int)__byte_perm(w, 0, 0x4440 | i); }   // one PRMT instead of shift+mask

@@ -92,9 +92,20 @@ OTT_DEV void yadif_keep8(const YadifJob &j, size_t off, int w, int x8, int y)
         ott_ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const uint32_t *>(j.cur + off) + i0));
 }
 
-// interpolated row: 8 samples predicted
+// per-byte floor((a+b)/2) of two words of four unsigned bytes
+OTT_DEV uint32_t yavg4(uint32_t a, uint32_t b) { return (a & b) + (((a ^ b) & 0xfefefefeu) >> 1); }
+// bytes (b0,b1) / (b2,b3) of a word as two 16-bit lanes
+OTT_DEV uint32_t ylanes_lo(uint32_t w) { return ott_prmt(w, 0u, 0x4140u); }
+OTT_DEV uint32_t ylanes_hi(uint32_t w) { return ott_prmt(w, 0u, 0x4342u); }
+
+// interpolated row: 8 samples predicted.
+// The edge-directed search (scores, the nested +-1/+-2 selection) runs per sample on scalars; everything that is
+// "vertical" - temporal differences, the averages d/b/f, the spatial clamp of diff and the final clamp of the predictor -
+// runs SIMD-in-register: four samples per VABSDIFF4 / byte average, then two samples per 16-bit-lane min/max/add.
+// Lanes that can go negative carry a +256 bias (kBias) so plain 32-bit adds/subtracts never borrow across lanes.
 OTT_DEV void yadif_oct8(const YadifJob &j, size_t off, int w, int h, int x8, int y)
 {
+    const uint32_t kBias = 0x01000100u;
     const uint32_t *prev = reinterpret_cast<const uint32_t *>(j.prev + off), *cur = reinterpret_cast<const uint32_t *>(j.cur + off);
     const uint32_t *next = reinterpret_cast<const uint32_t *>(j.next + off);
     uint32_t *dst = reinterpret_cast<uint32_t *>(j.dst + off);
@@ -117,48 +128,73 @@ OTT_DEV void yadif_oct8(const YadifJob &j, size_t off, int w, int h, int x8, int
         p2u = ott_ldg(reinterpret_cast<const uint2 *>(p2 + i0 + 2 * up)); n2u = ott_ldg(reinterpret_cast<const uint2 *>(n2 + i0 + 2 * up));
         p2d = ott_ldg(reinterpret_cast<const uint2 *>(p2 + i0 + 2 * dn)); n2d = ott_ldg(reinterpret_cast<const uint2 *>(n2 + i0 + 2 * dn));
     }
+    // ---- temporal difference and spatial check first (their inputs die here): clamp bounds d-diff / d+diff, two samples
+    //      per register, lanes biased by +256.  Word hw covers samples 4hw .. 4hw+3.
+    uint32_t lo[4], hi[4];
+    OTT_UNROLL
+    for (int hw = 0; hw < 2; ++hw) {
+        const uint32_t cw4 = cuw[1 + hw], ew4 = cdw[1 + hw];
+        const uint32_t a4 = hw ? p20.y : p20.x, b4 = hw ? n20.y : n20.x;
+        const uint32_t td0h = (ott_vabsdiff4(a4, b4) >> 1) & 0x7f7f7f7fu;                                        // |p2-n2| >> 1
+        const uint32_t td1 = yavg4(ott_vabsdiff4(hw ? pu.y : pu.x, cw4), ott_vabsdiff4(hw ? pd.y : pd.x, ew4));  // (|pu-c|+|pd-e|) >> 1
+        const uint32_t td2 = yavg4(ott_vabsdiff4(hw ? nu.y : nu.x, cw4), ott_vabsdiff4(hw ? nd.y : nd.x, ew4));
+        const uint32_t d4 = yavg4(a4, b4);
+        uint32_t bq = 0, fq = 0;
+        if (spatial) {
+            bq = yavg4(hw ? p2u.y : p2u.x, hw ? n2u.y : n2u.x);
+            fq = yavg4(hw ? p2d.y : p2d.x, hw ? n2d.y : n2d.x);
+        }
+        OTT_UNROLL
+        for (int half = 0; half < 2; ++half) {             // two samples per 16-bit-lane register
+            const uint32_t d = half ? ylanes_hi(d4) : ylanes_lo(d4);
+            uint32_t diff = ott_vmax3_s16x2(half ? ylanes_hi(td0h) : ylanes_lo(td0h), half ? ylanes_hi(td1) : ylanes_lo(td1),
+                                            half ? ylanes_hi(td2) : ylanes_lo(td2));
+            if (spatial) {
+                const uint32_t c = half ? ylanes_hi(cw4) : ylanes_lo(cw4), e = half ? ylanes_hi(ew4) : ylanes_lo(ew4);
+                const uint32_t b = half ? ylanes_hi(bq) : ylanes_lo(bq), f = half ? ylanes_hi(fq) : ylanes_lo(fq);
+                const uint32_t de = d + kBias - e, dc = d + kBias - c, bc = b + kBias - c, fe = f + kBias - e;   // each lane value + 256
+                const uint32_t mx = ott_vmax3_s16x2(de, dc, ott_vmin_s16x2(bc, fe));
+                const uint32_t mn = ott_vmin3_s16x2(de, dc, ott_vmax_s16x2(bc, fe));
+                diff = ott_vmax3_s16x2(diff + kBias, mn, 2u * kBias - mx) - kBias;                               // max(diff, mn, -mx)
+            }
+            lo[2 * hw + half] = d + kBias - diff;
+            hi[2 * hw + half] = d + kBias + diff;
+        }
+    }
+    // ---- direction search, per sample: pred = (c+e)>>1 or the average along the best of the +-1 / +-2 diagonals,
+    //      clamped two samples at a time
     int cu[16], cd[16];                                    // samples 8*x8-4 .. 8*x8+11 of the rows above / below
     OTT_UNROLL
     for (int k = 0; k < 16; ++k) { cu[k] = ybyte(cuw[k >> 2], k & 3); cd[k] = ybyte(cdw[k >> 2], k & 3); }
-    uint32_t outw[2] = {0, 0};
+    uint32_t o16[4];
     OTT_UNROLL
     for (int i = 0; i < 8; ++i) {
-        const int x = 8 * x8 + i, q = i + 4, b4 = i & 3;
+        const int x = 8 * x8 + i, q = i + 4;
         const int c = cu[q], e = cd[q];
-        const int a0 = ybyte(i < 4 ? p20.x : p20.y, b4), b0 = ybyte(i < 4 ? n20.x : n20.y, b4);
-        const int d = (a0 + b0) >> 1;
-        const int td0 = ott_sad(a0, b0, 0);
-        const int td1 = ott_sad(ybyte(i < 4 ? pd.x : pd.y, b4), e, ott_sad(ybyte(i < 4 ? pu.x : pu.y, b4), c, 0)) >> 1;
-        const int td2 = ott_sad(ybyte(i < 4 ? nd.x : nd.y, b4), e, ott_sad(ybyte(i < 4 ? nu.x : nu.y, b4), c, 0)) >> 1;
-        int diff = ott_max(ott_max(td0 >> 1, td1), td2);
-        int pred = (c + e) >> 1;
-        {
-            // edge-directed search; vf_yadif only tries +-2 when +-1 improved the score
-            const bool in = x >= 3 && x < w - 3;
-            int score = ott_sad(cu[q + 1], cd[q + 1], ott_sad(c, e, ott_sad(cu[q - 1], cd[q - 1], -1)));
-            const int s1 = ott_sad(c, cd[q + 2], ott_sad(cu[q - 1], cd[q + 1], ott_sad(cu[q - 2], e, 0)));                   // j = -1
-            const int s2 = ott_sad(cu[q - 1], cd[q + 3], ott_sad(cu[q - 2], cd[q + 2], ott_sad(cu[q - 3], cd[q + 1], 0)));  // j = -2
-            const int s3 = ott_sad(cu[q + 2], e, ott_sad(cu[q + 1], cd[q - 1], ott_sad(c, cd[q - 2], 0)));                  // j = +1
-            const int s4 = ott_sad(cu[q + 3], cd[q - 1], ott_sad(cu[q + 2], cd[q - 2], ott_sad(cu[q + 1], cd[q - 3], 0)));  // j = +2
-            const bool c1 = in && s1 < score;
-            score = c1 ? s1 : score; pred = c1 ? (cu[q - 1] + cd[q + 1]) >> 1 : pred;
-            const bool c2 = c1 && s2 < score;
-            score = c2 ? s2 : score; pred = c2 ? (cu[q - 2] + cd[q + 2]) >> 1 : pred;
-            const bool c3 = in && s3 < score;
-            score = c3 ? s3 : score; pred = c3 ? (cu[q + 1] + cd[q - 1]) >> 1 : pred;
-            const bool c4 = c3 && s4 < score;
-            pred = c4 ? (cu[q + 2] + cd[q - 2]) >> 1 : pred;
+        int p = (c + e) >> 1;
+        // vf_yadif only tries +-2 when +-1 improved the score
+        const bool in = x >= 3 && x < w - 3;
+        int score = ott_sad(cu[q + 1], cd[q + 1], ott_sad(c, e, ott_sad(cu[q - 1], cd[q - 1], -1)));
+        const int s1 = ott_sad(c, cd[q + 2], ott_sad(cu[q - 1], cd[q + 1], ott_sad(cu[q - 2], e, 0)));                   // j = -1
+        const int s2 = ott_sad(cu[q - 1], cd[q + 3], ott_sad(cu[q - 2], cd[q + 2], ott_sad(cu[q - 3], cd[q + 1], 0)));  // j = -2
+        const int s3 = ott_sad(cu[q + 2], e, ott_sad(cu[q + 1], cd[q - 1], ott_sad(c, cd[q - 2], 0)));                  // j = +1
+        const int s4 = ott_sad(cu[q + 3], cd[q - 1], ott_sad(cu[q + 2], cd[q - 2], ott_sad(cu[q + 1], cd[q - 3], 0)));  // j = +2
+        const bool c1 = in && s1 < score;
+        score = c1 ? s1 : score; p = c1 ? (cu[q - 1] + cd[q + 1]) >> 1 : p;
+        const bool c2 = c1 && s2 < score;
+        score = c2 ? s2 : score; p = c2 ? (cu[q - 2] + cd[q + 2]) >> 1 : p;
+        const bool c3 = in && s3 < score;
+        score = c3 ? s3 : score; p = c3 ? (cu[q + 1] + cd[q - 1]) >> 1 : p;
+        const bool c4 = c3 && s4 < score;
+        p = c4 ? (cu[q + 2] + cd[q - 2]) >> 1 : p;
+        if (i & 1) {
+            const uint32_t pp = o16[i >> 1] + ((uint32_t)p << 16);                                              // (pred[i-1], pred[i]) + bias
+            o16[i >> 1] = ott_vmin_s16x2(ott_vmax_s16x2(pp, lo[i >> 1]), hi[i >> 1]) - kBias;                   // 0..255 per lane
+        } else {
+            o16[i >> 1] = (uint32_t)p + kBias;
         }
-        if (spatial) {
-            const int b = (ybyte(i < 4 ? p2u.x : p2u.y, b4) + ybyte(i < 4 ? n2u.x : n2u.y, b4)) >> 1;
-            const int f = (ybyte(i < 4 ? p2d.x : p2d.y, b4) + ybyte(i < 4 ? n2d.x : n2d.y, b4)) >> 1;
-            const int mx = ott_max(ott_max(d - e, d - c), ott_min(b - c, f - e));
-            const int mn = ott_min(ott_min(d - e, d - c), ott_max(b - c, f - e));
-            diff = ott_max(ott_max(diff, mn), -mx);
-        }
-        const int v = ott_min(ott_max(pred, d - diff), d + diff);
-        outw[i >> 2] |= (uint32_t)v << (8 * b4);
     }
+    const uint32_t outw[2] = {ott_prmt(o16[0], o16[1], 0x6420u), ott_prmt(o16[2], o16[3], 0x6420u)};
     uint2 o;
     o.x = outw[0]; o.y = outw[1];
     *reinterpret_cast<uint2 *>(dst + i0) = o;

@@ -20,6 +20,26 @@ def test_yadif_frame_vs_oracle(lib, og, oracle, size, tff):
     assert np.array_equal(got, oracle.yadif_frame(n[0], n[1], n[2], w, h, 1, tff))
 
 
+@pytest.mark.parametrize("size", [(64, 48), (130, 74), (192, 108)])
+def test_yadif_extreme_values(lib, og, oracle, size):
+    """0 / 255 checker noise drives every |a-b| to 0 or 255 and every clamp to its limits (the packed 16-bit lanes of the
+    fast path must never borrow or carry into their neighbours); flat frames exercise the all-equal paths."""
+    w, h = size
+    rng = np.random.default_rng(w)
+    n = oracle.i420_size(w, h)
+    for tff in (1, 0):
+        fr = [(rng.integers(0, 2, n) * 255).astype(np.uint8) for _ in range(3)]
+        got = lib.yadif_frame(fr[0], fr[1], fr[2], og.FMT_I420, w, h, 1, tff)
+        assert np.array_equal(got, oracle.yadif_frame(fr[0], fr[1], fr[2], w, h, 1, tff))
+        # two-level frames with long runs: large spatial-check terms next to zero temporal differences
+        fr = [np.repeat((rng.integers(0, 2, (n + 15) // 16) * 255).astype(np.uint8), 16)[:n] for _ in range(3)]
+        got = lib.yadif_frame(fr[0], fr[1], fr[1], og.FMT_I420, w, h, 1, tff)
+        assert np.array_equal(got, oracle.yadif_frame(fr[0], fr[1], fr[1], w, h, 1, tff))
+    for level in (0, 255, 128):
+        flat = np.full(n, level, np.uint8)
+        assert np.array_equal(lib.yadif_frame(flat, flat, flat, og.FMT_I420, w, h, 1, 1), flat)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("tff", [1, 0])
 def test_yadif_full_size_1080i(real_lib, og, oracle, tff):
