@@ -217,6 +217,12 @@ class CpuReference:
                 O.scale_i420(f, self.w, self.h, THUMB[0], THUMB[1])
 
 
+CPU_KIND_NOTE = ("kind=reference: the scaler is the real libswscale 8.0.1 in this image (the library the reference calls through "
+                 "sws_getContext/sws_scale, x86 SIMD enabled), one single-threaded context per rendition per worker exactly as "
+                 "transvideo.c:1563-1581; yadif and the NV12 repack run through the C port in oracle/ (no libavfilter in the image). "
+                 "kind=port: everything through oracle/ (bundled libswscale missing)")
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -276,7 +282,7 @@ def reference_main(args, wl, rank, world):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * elapsed / len(timed),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": wl["desc"], "frames_per_step": threads},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind, "sample": sample},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind, "sample": sample, "note": CPU_KIND_NOTE},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -522,7 +528,7 @@ def ours_main(args, wl, rank, world, local_rank):
         done, el, kind, _ = run_cpu_rounds(wl, base_frames, threads, seconds=args.cpu_seconds)
         one_done, one_el, _, _ = run_cpu_rounds(wl, base_frames, 1, seconds=min(3.0, args.cpu_seconds))
         cp_done, cp_el, _, _ = run_cpu_rounds(wl, base_frames, threads, seconds=min(4.0, args.cpu_seconds), copies=True)
-        cpu = {"value": done / el, "unit": "frames/s", "cores": threads, "kind": kind,
+        cpu = {"value": done / el, "unit": "frames/s", "cores": threads, "kind": kind, "note": CPU_KIND_NOTE,
                "sample": "%d frames of the same workload (%d rounds x %d host threads, one frame per thread per round, ~%.0f s)"
                          % (done, done // threads, threads, el),
                "with_reference_copies": {"value": cp_done / cp_el, "unit": "frames/s",
