@@ -217,3 +217,30 @@ def test_full_size_runs_are_deterministic(real_lib, og):
         digests.add(hashlib.md5(b"".join(np.ascontiguousarray(x).tobytes() for x in r["rungs"])).hexdigest())
         ch.close()
     assert len(digests) == 1
+
+
+# ------------------------------------------------------------------------------------- randomised geometry sweep
+def _random_cases(n, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < n:
+        sw, sh = int(rng.integers(8, 120)) * 2, int(rng.integers(6, 80)) * 2
+        ratio_w, ratio_h = rng.uniform(0.2, 2.2), rng.uniform(0.2, 2.2)
+        dw, dh = max(8, int(sw * ratio_w)) & ~1, max(8, int(sh * ratio_h)) & ~1
+        out.append((sw, sh, dw, dh, int(rng.integers(0, 2)), int(rng.integers(0, 2)), int(rng.integers(0, 2))))
+    return out
+
+
+@pytest.mark.parametrize("case", _random_cases(48, 2024))
+def test_random_geometry_vs_oracle(lib, og, oracle, case):
+    """Seeded random source/destination sizes (down- and up-scaling, independent ratios per axis), both filters, both
+    targets, I420 and NV12 writers: planner corner cases (narrow last tiles, 1-tap axes, long filters) against the oracle."""
+    sw, sh, dw, dh, lanczos, target_b, nv12 = case
+    src = noise_i420(sw, sh, sw * 7 + dh)
+    f, k = (og.FILTER_LANCZOS, oracle.LANCZOS) if lanczos else (og.FILTER_BICUBIC, oracle.BICUBIC)
+    t, kt = (og.TARGET_B, oracle.TARGET_B) if target_b else (og.TARGET_A, oracle.TARGET_A)
+    ref = oracle.scale_i420(src, sw, sh, dw, dh, k, kt)
+    if nv12:
+        ref = oracle.i420_to_nv12(ref, dw, dh)
+    got = lib.scale_frame(src, og.FMT_I420, sw, sh, dw, dh, dst_fmt=og.FMT_NV12 if nv12 else og.FMT_I420, filt=f, target=t)
+    assert np.array_equal(got, ref), (case, int((got != ref).sum()))
