@@ -84,7 +84,7 @@ constexpr int kLadderThreads = kThreads + 32;     // 12 compute warps + 1 produc
 //                   signalled on the descriptor's `ready` mbarrier.
 //   compute warps : wait ready[slot] -> H pass (staged rows -> int16 intermediates) -> V pass + store -> release the
 //                   descriptor slot and the source buffer.
-// Two source buffers: tile k+1 streams in while tile k computes.
+// One source buffer: it is released after the H pass, tile k+1 streams in while tile k's V pass runs.
 __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderLaunch L)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
         // ------------------------------------------------------------------ producer warp
         const int lane = tid - kThreads;
         uint32_t pg = (1u << kGeomSlots) - 1, pe = 3;    // parity bits; a fresh mbarrier passes a wait on parity 1
-        int buf = 0;
+        int buf = 0, mid = 0;
         int idx = 0;
         if (lane == 0) idx = atomicAdd(L.counter, 1);
         for (int slot = 0;; slot = (slot + 1) & (kGeomSlots - 1)) {
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
             if (lane == 0) {
                 s_idx[slot] = idx;
                 s_buf[slot] = buf;
-                s_what[slot] = idx < L.n_items ? item_prepare(L.items[idx], L.binds[L.items[idx].chan], L, buf, slot, s_geom[slot]) : 0;
+                s_what[slot] = idx < L.n_items ? item_prepare(L.items[idx], L.binds[L.items[idx].chan], L, buf, mid, slot, s_geom[slot]) : 0;
             }
             __syncwarp();
             if (idx >= L.n_items) {
@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
                     mbar_arrive(&ready[slot]);                 // compute warps stage this tile through registers
                 }
                 buf = (buf + 1 == nbuf) ? 0 : buf + 1;
+                mid = (mid + 1 == L.mid_buffers) ? 0 : mid + 1;
             } else if (lane == 0) {
                 mbar_arrive(&ready[slot]);                     // copy item / skipped item: no source buffer involved
             }
@@ -173,7 +174,10 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
             compute_sync();                        // H-pass result and V tables complete; the source buffer is free
             mbar_arrive(&empty[s_buf[slot]]);
             phase_vpass(tid, g, smem);
-            compute_sync();                        // intermediates free for the next tile's H pass
+            // one intermediate region: everybody must be done reading it before the next tile's H pass writes it.  Two
+            // regions: the next H pass writes the other one, and the region it will overwrite after that was last read
+            // before the barrier above - no wait here, a warp that is done starts the next tile at once
+            if (L.mid_buffers == 1) compute_sync();
         }
         mbar_arrive(&gfree[slot]);                 // descriptor slot may be rewritten
     }
@@ -199,22 +203,28 @@ cudaError_t configure_kernels()
     return cudaFuncSetAttribute(ladder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTileSmem);
 }
 
-size_t ladder_smem_bytes(int src_max, int mid_max, int vc_max, int *double_buffer)
+// Shared memory layout of one CTA: [source buffer(s)] [intermediate region(s)] [kGeomSlots table regions].
+// Preferred: one source buffer + two intermediate regions (the next tile's window is fetched during the V pass, which
+// is far longer than the copy, and the V -> next-H hand-over needs no barrier).  Launches whose tiles are too big for
+// that (very long filters) run with one of each.
+size_t ladder_smem_bytes(int src_max, int mid_max, int vc_max, int *double_buffer, int *mid_buffers)
 {
     const size_t tables = (size_t)kGeomSlots * vc_max;     // one table region per descriptor slot
-    const size_t two = 2 * (size_t)src_max + mid_max + tables + 16, one = (size_t)src_max + mid_max + tables + 16;
-    const int db = two <= kMaxTileSmem;
-    if (double_buffer) *double_buffer = db;
-    return db ? two : one;
+    const size_t two_mid = (size_t)src_max + 2 * (size_t)mid_max + tables + 16, one = (size_t)src_max + mid_max + tables + 16;
+    const int mb = two_mid <= kMaxTileSmem ? 2 : 1;
+    if (double_buffer) *double_buffer = 0;
+    if (mid_buffers) *mid_buffers = mb;
+    return mb == 2 ? two_mid : one;
 }
 
 cudaError_t launch_ladder(LadderLaunch L, cudaStream_t s)
 {
     if (L.n_items <= 0) return cudaSuccess;
-    int db = 0;
-    const size_t smem_bytes = ladder_smem_bytes(L.src_max, L.mid_max, L.vc_max, &db);
+    int db = 0, mb = 1;
+    const size_t smem_bytes = ladder_smem_bytes(L.src_max, L.mid_max, L.vc_max, &db, &mb);
     if (smem_bytes > kMaxTileSmem) return cudaErrorInvalidValue;
     L.double_buffer = db;
+    L.mid_buffers = mb;
     int dev = 0, sms = 0, per_sm = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

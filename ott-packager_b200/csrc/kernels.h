@@ -8,8 +8,8 @@ namespace ottgpu {
 // upper bound of dynamic shared memory the ladder kernel is configured for (sm_100 allows 227 KB per CTA)
 constexpr size_t kMaxTileSmem = 224 * 1024;
 
-// shared memory one launch needs for the given region maxima; double_buffer is decided here
-size_t ladder_smem_bytes(int src_max, int mid_max, int vc_max, int *double_buffer);
+// shared memory one launch needs for the given region maxima; the number of source / intermediate buffers is decided here
+size_t ladder_smem_bytes(int src_max, int mid_max, int vc_max, int *double_buffer, int *mid_buffers = nullptr);
 
 // Persistent launch: grid = min(n_items, SMs x resident CTAs); CTAs pull work items from L.counter (must be zero).
 cudaError_t launch_ladder(LadderLaunch L, cudaStream_t s);

@@ -887,8 +887,9 @@ OTT_DEV void interleave_rows8(int tid, const uint8_t *u, const uint8_t *v, int s
 
 // ------------------------------------------------------------------------------------------------ item dispatch
 // Resolves one work item.  Returns 0: nothing to do, 1: scale tile (geometry filled), 2: copy item.
-// off_src: byte offset of the source buffer this tile stages into; the other regions follow 2 (or 1) source buffers.
-OTT_DEV int item_prepare(const Item &it, const Binding &b, const LadderLaunch &L, int buf, int table_slot, TileGeom &g)
+// off_src: byte offset of the source buffer this tile stages into; the intermediate region(s) and the per-slot tables
+// follow the source buffer(s).
+OTT_DEV int item_prepare(const Item &it, const Binding &b, const LadderLaunch &L, int buf, int mid_buf, int table_slot, TileGeom &g)
 {
     if (!b.active || ((b.skip_mask >> it.slot) & 1u)) return 0;
     const PlanDev &plan = *b.plan;
@@ -908,8 +909,9 @@ OTT_DEV int item_prepare(const Item &it, const Binding &b, const LadderLaunch &L
     g.tw_log2 = T.tw == 64 ? 6 : 5;
     g.approx_v = R.approx_v;
     g.off_src = buf * L.src_max;
-    g.off_mid = (L.double_buffer ? 2 : 1) * L.src_max;
-    g.off_vc = g.off_mid + L.mid_max + table_slot * L.vc_max;
+    const int mid_base = (L.double_buffer ? 2 : 1) * L.src_max;
+    g.off_mid = mid_base + mid_buf * L.mid_max;
+    g.off_vc = mid_base + L.mid_buffers * L.mid_max + table_slot * L.vc_max;
     g.off_vpos = g.off_vc + ((T.th * T.vtaps * 2 + 3) & ~3);
     g.src_shift = plan.src_fmt == 2 ? 6 : 0;
     g.dst_shift = R.fmt == 2 ? 6 : 0;

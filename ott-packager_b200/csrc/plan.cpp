@@ -68,14 +68,15 @@ Plan::~Plan()
 
 namespace {
 
-// Two CTAs per SM: 2 source buffers + intermediates + tables must stay under ~110 KB per CTA.
+// Two CTAs per SM: 1 source buffer + 2 intermediate regions + tables must stay under ~112 KB per CTA.
 size_t env_kb(const char *name, size_t dflt_kb)
 {
     const char *v = std::getenv(name);               // tuning knobs for profiling sessions, not part of the API
     return (v && std::atoi(v) > 0 ? (size_t)std::atoi(v) : dflt_kb) * 1024;
 }
-const size_t kSrcCap = env_kb("OTTGPU_SRC_CAP_KB", sizeof(mid_t) == 4 ? 22 : 36);   // one staged-source buffer
-const size_t kMidCap = env_kb("OTTGPU_MID_CAP_KB", sizeof(mid_t) == 4 ? 54 : 36);   // H-pass result region
+// (48 + 2 x 27 + ~9 KB of tables; measured best of the sweep in DESIGN.md 4.1)
+const size_t kSrcCap = env_kb("OTTGPU_SRC_CAP_KB", sizeof(mid_t) == 4 ? 22 : 48);   // the staged-source buffer
+const size_t kMidCap = env_kb("OTTGPU_MID_CAP_KB", sizeof(mid_t) == 4 ? 54 : 27);   // one H-pass result region (there are two)
 const int kMaxTileRows = (int)(env_kb("OTTGPU_MAX_TILE_ROWS", 128) / 1024);
 const int kTileRounds = [] { const char *v = std::getenv("OTTGPU_TILE_ROUNDS"); return v ? std::atoi(v) : 1; }();   // 1: also try tile heights that fill whole V rounds          // keeps enough tiles per frame for load balance
 constexpr size_t kSmemHardLimit = 224 * 1024; // == kMaxTileSmem (kernels.h); sm_100 allows 227 KB per CTA

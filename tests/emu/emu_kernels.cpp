@@ -10,28 +10,30 @@ namespace ottgpu {
 
 cudaError_t configure_kernels() { return cudaSuccess; }
 
-size_t ladder_smem_bytes(int src_max, int mid_max, int vc_max, int *double_buffer)
+size_t ladder_smem_bytes(int src_max, int mid_max, int vc_max, int *double_buffer, int *mid_buffers)
 {
     const size_t tables = (size_t)kGeomSlots * vc_max;
-    const size_t two = 2 * (size_t)src_max + mid_max + tables + 16, one = (size_t)src_max + mid_max + tables + 16;
-    const int db = two <= kMaxTileSmem;
-    if (double_buffer) *double_buffer = db;
-    return db ? two : one;
+    const size_t two_mid = (size_t)src_max + 2 * (size_t)mid_max + tables + 16, one = (size_t)src_max + mid_max + tables + 16;
+    const int mb = two_mid <= kMaxTileSmem ? 2 : 1;
+    if (double_buffer) *double_buffer = 0;
+    if (mid_buffers) *mid_buffers = mb;
+    return mb == 2 ? two_mid : one;
 }
 
 cudaError_t launch_ladder(LadderLaunch L, cudaStream_t)
 {
-    int db = 0;
-    const size_t smem_bytes = ladder_smem_bytes(L.src_max, L.mid_max, L.vc_max, &db);
+    int db = 0, mb = 1;
+    const size_t smem_bytes = ladder_smem_bytes(L.src_max, L.mid_max, L.vc_max, &db, &mb);
     if (smem_bytes > kMaxTileSmem) return cudaErrorInvalidValue;
     L.double_buffer = db;
+    L.mid_buffers = mb;
     std::vector<unsigned char> smem(smem_bytes + 64);
     unsigned char *sm = smem.data() + ((16 - ((uintptr_t)smem.data() & 15)) & 15);
     for (int blk = 0; blk < L.n_items; ++blk) {
         const Item it = L.items[blk];
         const Binding &b = L.binds[it.chan];
         TileGeom g;
-        const int what = item_prepare(it, b, L, db ? (blk & 1) : 0, blk & (kGeomSlots - 1), g);   // alternate buffers like the kernel does
+        const int what = item_prepare(it, b, L, db ? (blk & 1) : 0, mb == 2 ? (blk & 1) : 0, blk & (kGeomSlots - 1), g);   // alternate buffers like the kernel does
         if (what == 0) continue;
         if (what == 2) {
             for (int tid = 0; tid < kThreads; ++tid) item_copy(tid, it, b);
@@ -41,6 +43,7 @@ cudaError_t launch_ladder(LadderLaunch L, cudaStream_t)
         if ((size_t)g.off_vpos + (size_t)g.th * 4 > smem_bytes) return cudaErrorInvalidValue;
         if ((size_t)(g.staged_planes - 1) * g.plane_stride + (size_t)g.sr * g.spw * 4 > (size_t)L.src_max) return cudaErrorInvalidValue;
         if ((size_t)g.nplanes * (g.sr + 1) * g.mid_pitch * 2 > (size_t)L.mid_max) return cudaErrorInvalidValue;
+        if ((size_t)g.off_mid + L.mid_max > (size_t)g.off_vc) return cudaErrorInvalidValue;
         if (g.nvec * 4 > g.spw) return cudaErrorInvalidValue;
         std::fill(smem.begin(), smem.end(), 0xA5);       // poison: stale-data reads show up as mismatches
         for (int lane = 0; lane < 32; ++lane) phase_tables(lane, 32, g, sm);
