@@ -217,6 +217,17 @@ size_t ladder_smem_bytes(int src_max, int mid_max, int vc_max, int *double_buffe
     return mb == 2 ? two_mid : one;
 }
 
+int ladder_ctas_per_sm(size_t smem_bytes)
+{
+    int per_sm = 0;
+    if (smem_bytes > kMaxTileSmem) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ladder_kernel, kLadderThreads, smem_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return per_sm;
+}
+
 cudaError_t launch_ladder(LadderLaunch L, cudaStream_t s)
 {
     if (L.n_items <= 0) return cudaSuccess;

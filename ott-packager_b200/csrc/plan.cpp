@@ -1,4 +1,5 @@
 #include "plan.h"
+#include "kernels.h"
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -74,9 +75,15 @@ size_t env_kb(const char *name, size_t dflt_kb)
     const char *v = std::getenv(name);               // tuning knobs for profiling sessions, not part of the API
     return (v && std::atoi(v) > 0 ? (size_t)std::atoi(v) : dflt_kb) * 1024;
 }
-// (48 + 2 x 27 + ~9 KB of tables; measured best of the sweep in DESIGN.md 4.1)
-const size_t kSrcCap = env_kb("OTTGPU_SRC_CAP_KB", sizeof(mid_t) == 4 ? 22 : 48);   // the staged-source buffer
-const size_t kMidCap = env_kb("OTTGPU_MID_CAP_KB", sizeof(mid_t) == 4 ? 54 : 27);   // one H-pass result region (there are two)
+// The caps are tried from the most generous pair downwards until the launch really gets two resident CTAs per SM (the
+// table regions grow with the filter length, so a fixed pair can fall off that cliff: 2160p lanczos did).  Set by get_plan()
+// under its lock.  Orders measured on the B200: 8-bit sources like a 48 KB window, 16-bit ones (twice the
+// bytes per staged sample) a bigger window and smaller intermediate regions.
+size_t kSrcCap = 48 * 1024;                                 // the staged-source buffer
+size_t kMidCap = 27 * 1024;                                 // one H-pass result region (there are two)
+struct CapPair { int src_kb, mid_kb; };
+const CapPair kCaps8[] = {{48, 27}, {44, 27}, {40, 26}, {36, 26}, {32, 24}, {28, 22}, {24, 20}, {20, 16}};
+const CapPair kCaps16[] = {{68, 18}, {64, 20}, {60, 20}, {56, 20}, {48, 20}, {40, 18}, {32, 16}, {24, 14}};
 const int kMaxTileRows = (int)(env_kb("OTTGPU_MAX_TILE_ROWS", 128) / 1024);
 const int kTileRounds = [] { const char *v = std::getenv("OTTGPU_TILE_ROUNDS"); return v ? std::atoi(v) : 1; }();   // 1: also try tile heights that fill whole V rounds          // keeps enough tiles per frame for load balance
 constexpr size_t kSmemHardLimit = 224 * 1024; // == kMaxTileSmem (kernels.h); sm_100 allows 227 KB per CTA
@@ -274,6 +281,8 @@ struct Key {
 std::mutex g_mu;
 std::map<Key, std::weak_ptr<Plan>> g_cache;
 
+std::shared_ptr<Plan> build_plan(const ottgpu_cfg &cfg, std::string &err);
+
 bool compatible(int src_fmt, int dst_fmt, bool same_size)
 {
     if (fmt_bps(src_fmt) != fmt_bps(dst_fmt) || !fmt_bps(src_fmt)) return false;
@@ -309,6 +318,30 @@ std::shared_ptr<Plan> get_plan(const ottgpu_cfg &cfg_in, std::string &err)
         if (auto p = found->second.lock()) return p;
 
     if (cudaSetDevice(cfg.gpu) != cudaSuccess) { err = "cudaSetDevice failed"; return nullptr; }
+    // tile budgets: an explicit pair from the environment (profiling sessions), else the first pair of the list that
+    // keeps two CTAs of the main launch resident per SM
+    const char *env_src = std::getenv("OTTGPU_SRC_CAP_KB"), *env_mid = std::getenv("OTTGPU_MID_CAP_KB");
+    std::vector<CapPair> tries;
+    if (env_src && env_mid && std::atoi(env_src) > 0 && std::atoi(env_mid) > 0) tries.push_back({std::atoi(env_src), std::atoi(env_mid)});
+    else if (fmt_bps(cfg.src_fmt) == 1) tries.assign(std::begin(kCaps8), std::end(kCaps8));
+    else tries.assign(std::begin(kCaps16), std::end(kCaps16));
+    std::shared_ptr<Plan> plan;
+    for (size_t k = 0; k < tries.size(); ++k) {
+        kSrcCap = (size_t)tries[k].src_kb * 1024;
+        kMidCap = (size_t)tries[k].mid_kb * 1024;
+        plan = build_plan(cfg, err);
+        if (!plan) return nullptr;
+        if (plan->items.empty() || k + 1 == tries.size()) break;
+        if (ladder_ctas_per_sm(ladder_smem_bytes(plan->src_max[0], plan->mid_max[0], plan->vc_max[0], nullptr, nullptr)) >= 2) break;
+    }
+    g_cache[key] = plan;
+    return plan;
+}
+
+namespace {
+
+std::shared_ptr<Plan> build_plan(const ottgpu_cfg &cfg, std::string &err)
+{
     auto plan = std::make_shared<Plan>();
     plan->gpu = cfg.gpu;
     plan->cfg = cfg;
@@ -417,8 +450,9 @@ std::shared_ptr<Plan> get_plan(const ottgpu_cfg &cfg_in, std::string &err)
     plan->allocations.push_back(d);
     if (cudaMemcpy(d, &P, sizeof(PlanDev), cudaMemcpyHostToDevice) != cudaSuccess) { err = "cudaMemcpy(plan) failed"; return nullptr; }
     plan->dev = static_cast<PlanDev *>(d);
-    g_cache[key] = plan;
     return plan;
 }
+
+}  // namespace
 
 }  // namespace ottgpu

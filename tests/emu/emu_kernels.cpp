@@ -20,6 +20,9 @@ size_t ladder_smem_bytes(int src_max, int mid_max, int vc_max, int *double_buffe
     return mb == 2 ? two_mid : one;
 }
 
+// the B200 figure: 228 KB per SM, 1 KB reserved + ~1 KB static per CTA
+int ladder_ctas_per_sm(size_t smem_bytes) { return smem_bytes > kMaxTileSmem ? 0 : (smem_bytes <= 114816 ? 2 : 1); }
+
 cudaError_t launch_ladder(LadderLaunch L, cudaStream_t)
 {
     int db = 0, mb = 1;
