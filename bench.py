@@ -424,25 +424,28 @@ def ours_main(args, wl, rank, world, local_rank):
         parity = "bit-exact vs oracle (channel 0, rungs 2160p + 360p)" if ok else "MISMATCH"
     elif rank == 0 and args.steps >= 3:
         from oracle import oracle as O
-        # timed step k used ios[k % RING]; the last step's output is the frame submitted one step earlier (yadif latency)
+        # timed step k used ios[k % RING]; the last step's output is the frame submitted one step earlier (yadif latency).
+        # First, middle and last channel of the launch (their tiles are spread over different CTAs and waves).
         last_phase = (args.steps - 1) % RING
-        src_of = lambda k: base_frames[((args.steps - 1 + k) % RING) % 4]          # channel 0: roll 0
-        exp_src = src_of(0) if wl["deint"] == 2 else src_of(-1)
-        if wl["deint"] == 0:
-            exp_src = O.yadif_frame(src_of(-2), src_of(-1), src_of(0), w, h, 1, 1)
+        checked = sorted({0, Cn // 2, Cn - 1})
         ok = True
-        for r, (dw, dh) in enumerate(wl["rungs"]):
-            got = lib.from_device(dst_dev[0][last_phase % 2][r], rung_bytes[r], gpu=local_rank)
-            ref = O.scale_i420(exp_src, w, h, dw, dh)
-            if fmt == NV12:
-                ref = O.i420_to_nv12(ref, dw, dh)
-            lay = lib.rung_layout(og.RungCfg(dw, dh, fmt, wl["pitch_align"]))
-            ch_h = (dh + 1) // 2
-            rows = [dh, ch_h] if fmt == NV12 else [dh, ch_h, ch_h]
-            widths = [dw, 2 * ((dw + 1) // 2)] if fmt == NV12 else [dw, (dw + 1) // 2, (dw + 1) // 2]
-            flat = np.concatenate([got[o: o + pch * n].reshape(n, pch)[:, :wd].ravel() for (o, pch), n, wd in zip(lay, rows, widths)])
-            ok = ok and np.array_equal(flat, ref)
-        parity = "bit-exact vs oracle (channel 0, %d rungs)" % len(rungs) if ok else "MISMATCH"
+        for c in checked:
+            src_of = lambda k: np.roll(base_frames[(c + ((args.steps - 1 + k) % RING)) % 4], 64 * c)
+            exp_src = src_of(0) if wl["deint"] == 2 else src_of(-1)
+            if wl["deint"] == 0:
+                exp_src = O.yadif_frame(src_of(-2), src_of(-1), src_of(0), w, h, 1, 1)
+            for r, (dw, dh) in enumerate(wl["rungs"]):
+                got = lib.from_device(dst_dev[c][last_phase % 2][r], rung_bytes[r], gpu=local_rank)
+                ref = O.scale_i420(exp_src, w, h, dw, dh)
+                if fmt == NV12:
+                    ref = O.i420_to_nv12(ref, dw, dh)
+                lay = lib.rung_layout(og.RungCfg(dw, dh, fmt, wl["pitch_align"]))
+                ch_h = (dh + 1) // 2
+                rows = [dh, ch_h] if fmt == NV12 else [dh, ch_h, ch_h]
+                widths = [dw, 2 * ((dw + 1) // 2)] if fmt == NV12 else [dw, (dw + 1) // 2, (dw + 1) // 2]
+                flat = np.concatenate([got[o: o + pch * n].reshape(n, pch)[:, :wd].ravel() for (o, pch), n, wd in zip(lay, rows, widths)])
+                ok = ok and np.array_equal(flat, ref)
+        parity = "bit-exact vs oracle (channels %s, %d rungs each)" % (",".join(str(c) for c in checked), len(rungs)) if ok else "MISMATCH"
 
     # ---------------- end-to-end arms (host pinned source frames through the C ABI)
     batch.close()
