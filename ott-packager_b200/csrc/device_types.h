@@ -22,7 +22,7 @@ typedef int16_t mid_t;
 #endif
 constexpr int kGeomSlots = 4;                  // tile descriptors (and V-table regions) in flight per CTA
 constexpr int kTensorMapBytes = 128;           // sizeof(CUtensorMap)
-constexpr int kThreads = 384;                  // compute threads of a ladder CTA (8 warps); the kernel adds one producer warp
+constexpr int kThreads = 384;                  // compute threads of a ladder CTA (12 warps); the kernel adds one producer warp
 
 enum ItemKind : uint8_t {
     ITEM_SCALE_LUMA = 0,     // H+V polyphase of one luma tile
