@@ -11,6 +11,10 @@
  * SWS_ACCURATE_RND / non-x86.
  *
  * There is NO CPU fallback: every call fails with OTTGPU_ERR_CUDA when no CUDA device / kernel image is usable.
+ *
+ * Threading (the reference runs one prepare/scale thread pair per channel, transvideo.c:3044-3099): any number of threads
+ * may use the library at once; one object (channel, batch, converter) is driven by one thread at a time; pools are
+ * internally locked and may be shared between threads (producer takes, consumer returns, like mempool.c).
  */
 #ifndef OTTGPU_H_
 #define OTTGPU_H_
