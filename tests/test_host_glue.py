@@ -321,3 +321,38 @@ def test_av_sync_repeat_with_device_surfaces(lib, og, oracle, rt, host):
     host.ottgpu_transvideo_close(C.byref(tv))
     assert pool.unused() == 16
     pool.close()
+
+
+def test_pool_exhaustion_reports_like_the_reference(lib, og, oracle, rt, host):
+    """transvideo.c:1596-1600, 2203-2207: when raw_video_pool has no buffer left the reference calls
+    send_direct_error(SIGNAL_DIRECT_ERROR_RAWPOOL, "Out of Uncompressed Video Buffers ...") and exits; the thread body
+    reports through the same hook (the hook decides about exit), returns every buffer it holds and fails the message."""
+    w, h = 96, 64
+    errors, signals = [], []
+    tv = _make_tv(rt, [(64, 40), (48, 32)], errors, signals)
+    rt.memory_unused.restype = C.c_int
+    f = natural_i420(w, h, 7)
+    m0 = _push(rt, tv, f, w, h, 1000, interlaced=0, fps=(60000, 1001))
+    assert host.ottgpu_transvideo_process(C.byref(tv), m0) == 0          # primes the window
+    m1 = _push(rt, tv, f, w, h, 2000, interlaced=0, fps=(60000, 1001))
+    # drain the pool: the next memory_take for a rendition buffer returns NULL
+    hoard = []
+    while True:
+        p = rt.memory_take(tv.raw_video_pool, 64)
+        if not p:
+            break
+        hoard.append(p)
+    msgs_before = rt.memory_unused(tv.msg_pool)
+    assert host.ottgpu_transvideo_process(C.byref(tv), m1) == -1
+    assert errors and b"Out of Uncompressed Video Buffers" in errors[0][1]
+    assert rt.memory_unused(tv.msg_pool) == msgs_before + 1             # the input message went back to its pool
+    assert not rt.dataqueue_take_back(tv.encode_queue[0])               # nothing was emitted for the failed message
+    for p in hoard:
+        rt.memory_return(tv.raw_video_pool, p)
+    # the channel is still usable afterwards
+    m2 = _push(rt, tv, f, w, h, 3000, interlaced=0, fps=(60000, 1001))
+    assert host.ottgpu_transvideo_process(C.byref(tv), m2) == 0
+    got = _drain(rt, tv, tv.encode_queue[0], oracle.i420_size(64, 40))
+    assert len(got) == 1 and np.array_equal(got[0]["data"], oracle.scale_i420(f, w, h, 64, 40))
+    _drain(rt, tv, tv.encode_queue[1], oracle.i420_size(48, 32))
+    host.ottgpu_transvideo_close(C.byref(tv))
