@@ -18,33 +18,16 @@
 
 #define MAX_SMALLBUF_SIZE 256
 
+/* same members, order and types as include/dataqueue.h:32-59; byte offsets on LP64 in the right-hand column */
 typedef struct _dataqueue_message_struct_ {
-    int             buffer_type;
-    unsigned long   buffer_size;
-    int64_t         pts;
-    int64_t         dts;
-    uint32_t        flags;
-    int             source_discontinuity;
-    uint8_t         tff;
-    uint8_t         interlaced;
-    int             fps_num;
-    int             fps_den;
-    int             aspect_num;
-    int             aspect_den;
-    int             width;
-    int             height;
-    uint8_t         stream_index;
-    int             channels;
-    int             sample_rate;
-    int64_t         first_pts;
-    int             caption_size;
-    int64_t         caption_timestamp;
-    int             splice_point;
-    int64_t         splice_duration;
-    int64_t         splice_duration_remaining;
-    char            smallbuf[MAX_SMALLBUF_SIZE];
-    uint8_t         *caption_buffer;
-    void            *buffer;
+    int buffer_type;  unsigned long buffer_size;                                         /*   0    8          */
+    int64_t pts, dts;                                                                    /*  16   24          */
+    uint32_t flags;  int source_discontinuity;  uint8_t tff, interlaced;                 /*  32   36   40  41 */
+    int fps_num, fps_den, aspect_num, aspect_den, width, height;                         /*  44 .. 64         */
+    uint8_t stream_index;  int channels, sample_rate;                                    /*  68   72   76     */
+    int64_t first_pts;  int caption_size;  int64_t caption_timestamp;                    /*  80   88   96     */
+    int splice_point;  int64_t splice_duration, splice_duration_remaining;               /* 104  112  120     */
+    char smallbuf[MAX_SMALLBUF_SIZE];  uint8_t *caption_buffer;  void *buffer;           /* 128  384  392     */
 } dataqueue_message_struct;
 
 #if defined(__cplusplus)
