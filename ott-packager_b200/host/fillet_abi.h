@@ -30,6 +30,13 @@ typedef struct _dataqueue_message_struct_ {
     char smallbuf[MAX_SMALLBUF_SIZE];  uint8_t *caption_buffer;  void *buffer;           /* 128  384  392     */
 } dataqueue_message_struct;
 
+#if defined(__LP64__) && defined(__STDC_VERSION__) && __STDC_VERSION__ >= 201112L
+_Static_assert(sizeof(dataqueue_message_struct) == 400, "dataqueue_message_struct must stay 400 bytes (include/dataqueue.h)");
+_Static_assert(offsetof(dataqueue_message_struct, flags) == 32 && offsetof(dataqueue_message_struct, width) == 60 &&
+               offsetof(dataqueue_message_struct, smallbuf) == 128 && offsetof(dataqueue_message_struct, buffer) == 392,
+               "dataqueue_message_struct layout drifted from include/dataqueue.h");
+#endif
+
 #if defined(__cplusplus)
 extern "C" {
 #endif
