@@ -15,6 +15,7 @@ C channels per GPU, channel-sharded, no collective on the data path -- SURVEY.md
 Nothing here reads /root/reference.  oracle/ is used only by the cpu_baseline / reference legs and the parity spot check.
 """
 import argparse
+import gc
 import ctypes as C
 import importlib
 import json
@@ -359,6 +360,8 @@ def ours_main(args, wl, rank, world, local_rank):
     libc = C.CDLL(None)
     submit = lib.dll.ottgpu_batch_submit
 
+    step_events = [] if os.environ.get("OTT_STEP_EVENTS") else None       # debugging aid: one CUDA event per step
+
     def run_steps(b, ios, n, launches):
         thumbs = 0
         for k in range(n):
@@ -366,6 +369,10 @@ def ours_main(args, wl, rank, world, local_rank):
             thumbs += free_thumbs(fout)                      # thumbnails of this set's previous use (step k-4: complete)
             lib.check(submit(b.handle, fin, fout, og.SUBMIT_ASYNC))
             launches[0] += b.last_launches
+            if step_events is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(stream)
+                step_events.append(ev)
         return thumbs
 
     def barrier():
@@ -386,15 +393,24 @@ def ours_main(args, wl, rank, world, local_rank):
             b.timing(True)
             sampler.busy = True
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            gc.collect()
+            gc.disable()                                     # a collector pause inside the loop would show up as GPU idle time
             e0.record(stream)
             h0 = time.perf_counter()
             thumbs = run_steps(b, ios, steps, launches)
             host_ms[0] = (time.perf_counter() - h0) * 1000.0 / max(steps, 1)      # wall time of the submission loop per step (includes waiting for a free descriptor set)
             e1.record(stream)
+            gc.enable()
             b.wait()
             torch.cuda.synchronize()
             sampler.busy = False
             ms = e0.elapsed_time(e1)
+            if step_events:
+                tail = step_events[-steps:]
+                d = [tail[i].elapsed_time(tail[i + 1]) for i in range(len(tail) - 1)]
+                worst = sorted(range(len(d)), key=lambda i: -d[i])[:6]
+                sys.stderr.write("step deltas ms: median %.4f, worst %s\n" % (sorted(d)[len(d) // 2], [(i, round(d[i], 3)) for i in worst]))
+                del step_events[:]
             for fin, fout in ios:
                 thumbs += free_thumbs(fout)
         if dist is not None:

@@ -130,6 +130,7 @@ struct ottgpu_channel {
     // tensor maps (one set per distinct source-frame address this channel has seen), least recently used first out
     struct MapSet { const uint8_t *base = nullptr; unsigned char *dev = nullptr; uint64_t stamp = 0; };
     std::vector<MapSet> maps;
+    unsigned char *maps_pool = nullptr;                // all sets in one allocation made at creation (no cudaMalloc mid-stream)
     uint64_t map_clock = 0;
     bool wants_maps = false;
 };
@@ -225,13 +226,13 @@ int frame_tensor_maps(ottgpu_channel *c, const uint8_t *base, cudaStream_t strea
     constexpr size_t kMaxSets = 24;
     ottgpu_channel::MapSet *slot = nullptr;
     if (c->maps.size() < kMaxSets) {
-        c->maps.emplace_back();
-        slot = &c->maps.back();
-        if (cudaMalloc((void **)&slot->dev, kSetBytes) != cudaSuccess) {
+        if (!c->maps_pool && cudaMalloc((void **)&c->maps_pool, kMaxSets * kSetBytes) != cudaSuccess) {
             cudaGetLastError();
-            c->maps.pop_back();
             return fail(OTTGPU_ERR_NOMEM, "cudaMalloc(tensor maps) failed");
         }
+        c->maps.emplace_back();
+        slot = &c->maps.back();
+        slot->dev = c->maps_pool + (c->maps.size() - 1) * kSetBytes;
     } else {
         slot = &c->maps[0];
         for (auto &m : c->maps)
@@ -373,6 +374,17 @@ int ottgpu_channel_create(const ottgpu_cfg *cfg, ottgpu_channel **out)
         const RungDev &R = plan->host_copy.rung[sidx];
         if (R.scaled && (R.luma.tma_ok || R.chroma.tma_ok)) c->wants_maps = true;
     }
+    // the thumbnail's device staging (one per descriptor set) is allocated now: a cudaMalloc in the middle of a running
+    // stream can stall it for milliseconds (measured: a one-off 3-136 ms gap at the first thumbnail of one channel)
+    if (plan->thumb_slot >= 0)
+        for (auto &set : c->stage) {
+            rc = ensure_dev(&set[plan->thumb_slot], plan->layout[plan->thumb_slot].bytes);
+            if (rc) {
+                for (auto &other : c->stage) cudaFree(other[plan->thumb_slot]);
+                if (c->own_stream) cudaStreamDestroy(c->stream);
+                return rc;
+            }
+        }
     ottgpu_channel *raw = c.release();
     rc = ottgpu_batch_create(&raw, 1, &raw->solo);
     if (rc) {
@@ -435,7 +447,7 @@ void ottgpu_channel_destroy(ottgpu_channel *ch)
     cudaFree(ch->deint);
     for (auto &set : ch->stage)
         for (uint8_t *p : set) cudaFree(p);
-    for (auto &m : ch->maps) cudaFree(m.dev);
+    cudaFree(ch->maps_pool);
     if (ch->own_stream) cudaStreamDestroy(ch->stream);
     delete ch;
 }
