@@ -150,9 +150,14 @@ struct ottgpu_batch {
         YadifJob *h_jobs = nullptr, *d_jobs = nullptr;
         Item *h_thumb_items = nullptr, *d_thumb_items = nullptr;
         int *d_counters = nullptr;                          // tile schedulers of the three launch classes
+        uint8_t *h_thumbs = nullptr;                        // pinned landing area for this step's thumbnails (all channels)
+        struct PendingThumb { void *dst; const uint8_t *src; size_t bytes; };
+        std::vector<PendingThumb> pending_thumbs;           // pinned -> the caller's malloc'ed buffer, done when the step retires
         cudaEvent_t done = nullptr, uploaded = nullptr, computed = nullptr, read_back = nullptr, k0 = nullptr, k1 = nullptr, y0 = nullptr, y1 = nullptr;
         bool in_flight = false, timed = false, timed_yadif = false, has_readback = false;
     } set[2];
+    std::vector<size_t> thumb_offset;                      // per channel, into Set::h_thumbs
+    size_t thumb_stage_bytes = 0;
     int turn = 0;
     int last_launches = 0, last_items = 0;
     bool timing = false;
@@ -514,6 +519,8 @@ static int batch_build(ottgpu_batch *b, ottgpu_channel **channels, int n)
             b->vc_max[k] = std::max(b->vc_max[k], p.vc_max[k]);
         }
         b->max_thumb_items += (int)p.thumb_items.size();
+        b->thumb_offset.push_back(b->thumb_stage_bytes);
+        if (p.thumb_slot >= 0) b->thumb_stage_bytes += (p.layout[p.thumb_slot].bytes + 63) & ~(size_t)63;
     }
     b->n_items = (int)all.size();
     CK(cudaMalloc((void **)&b->d_items, std::max<size_t>(all.size(), 1) * sizeof(Item)));
@@ -529,6 +536,7 @@ static int batch_build(ottgpu_batch *b, ottgpu_channel **channels, int n)
         CK(cudaMalloc((void **)&st.d_jobs, n * sizeof(YadifJob)));
         CK(cudaMallocHost((void **)&st.h_jobs, n * sizeof(YadifJob)));
         CK(cudaMalloc((void **)&st.d_counters, 3 * sizeof(int)));
+        CK(cudaMallocHost((void **)&st.h_thumbs, std::max<size_t>(b->thumb_stage_bytes, 64)));
         CK(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&st.uploaded, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&st.computed, cudaEventDisableTiming));
@@ -564,6 +572,7 @@ void ottgpu_batch_destroy(ottgpu_batch *b)
         cudaFreeHost(st.h_binds);
         cudaFreeHost(st.h_jobs);
         cudaFreeHost(st.h_thumb_items);
+        cudaFreeHost(st.h_thumbs);
         if (st.done) cudaEventDestroy(st.done);
         if (st.uploaded) cudaEventDestroy(st.uploaded);
         if (st.computed) cudaEventDestroy(st.computed);
@@ -589,6 +598,8 @@ int retire(ottgpu_batch *b, ottgpu_batch::Set &st)
     CK(cudaEventSynchronize(st.done));
     if (st.has_readback) CK(cudaEventSynchronize(st.read_back));
     st.has_readback = false;
+    for (const ottgpu_batch::Set::PendingThumb &t : st.pending_thumbs) std::memcpy(t.dst, t.src, t.bytes);
+    st.pending_thumbs.clear();
     if (st.timed) {
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, st.k0, st.k1));
@@ -660,6 +671,7 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
     {                                                   // at most two steps in flight: this set's previous user must be done
         int rc = retire(b, st);
         if (rc) return rc;
+        st.pending_thumbs.clear();                      // (left over only if a previous submit failed half way)
     }
     const int n = (int)b->ch.size();
     cudaStream_t s = b->stream;
@@ -802,10 +814,15 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
                 bind.dst_pitch[ts][p] = plan.layout[ts].pitch[p];
             }
             bind.thumb_active = 1;
+            // the consumer frees the thumbnail with free() (transvideo.c:254-255), so it is malloc'ed; the device-to-host copy
+            // lands in pinned memory (a copy into pageable memory would block this thread behind every queued read-back)
+            // and is moved into the malloc'ed buffer when the step retires
             void *host = std::malloc(plan.layout[ts].bytes);
             if (!host) return fail(OTTGPU_ERR_NOMEM, "malloc(thumbnail) failed");
             o.thumbnail = host;
-            b->readbacks.push_back({host, c->stage[turn][ts], plan.layout[ts].bytes});
+            uint8_t *landing = st.h_thumbs + b->thumb_offset[i];
+            b->readbacks.push_back({landing, c->stage[turn][ts], plan.layout[ts].bytes});
+            st.pending_thumbs.push_back({host, landing, plan.layout[ts].bytes});
             for (Item it : plan.thumb_items) { it.chan = (uint16_t)i; st.h_thumb_items[n_thumb_items++] = it; }
         }
 
