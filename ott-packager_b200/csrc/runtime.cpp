@@ -677,7 +677,6 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
     cudaStream_t s = b->stream;
     // uploads of this step may overwrite slots last read two steps ago: order the copy stream after that step only
     // (this set's previous use was retired above; the other set = the previous step may still be running)
-    bool uploads = false;
     int n_jobs = 0, n_thumb_items = 0, max_w = 0, max_h = 0, live = 0;
     bool all_fast = true;
     b->readbacks.clear();
@@ -715,7 +714,6 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
             if (f.slot < 0) return fail(OTTGPU_ERR_NOMEM, "no device slot for the incoming frame");
             f.dev = c->slots[f.slot];
             CK(cudaMemcpyAsync(c->slots[f.slot], in[i].data, c->src_bytes, cudaMemcpyHostToDevice, b->copy_stream));
-            uploads = true;
         } else if (in[i].mem == OTTGPU_MEM_DEVICE) {
             f.dev = static_cast<const uint8_t *>(in[i].data);
         } else {
@@ -834,16 +832,18 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
     }
 
     // ---- 5. enqueue: descriptors, yadif, ladder, thumbnails, read-backs
-    // With host frames in flight the small descriptor copies ride on the copy stream behind this step's uploads:
-    // on the compute stream they would queue behind the NEXT step's bulk uploads in the H2D copy engine.
-    cudaStream_t ds = uploads ? b->copy_stream : s;
+    // The small descriptor copies and the reset of the tile schedulers always ride on the copy stream: they belong to this
+    // step's own descriptor set (its previous user was retired above), so they overlap the previous step's kernels instead
+    // of sitting between two launches on the compute stream; with host frames in flight they also stay behind this step's
+    // uploads instead of queueing behind the NEXT step's bulk uploads in the H2D copy engine.
+    cudaStream_t ds = b->copy_stream;
     CK(cudaMemcpyAsync(st.d_binds, st.h_binds, n * sizeof(Binding), cudaMemcpyHostToDevice, ds));
     if (n_jobs) CK(cudaMemcpyAsync(st.d_jobs, st.h_jobs, n * sizeof(YadifJob), cudaMemcpyHostToDevice, ds));
     if (n_thumb_items) CK(cudaMemcpyAsync(st.d_thumb_items, st.h_thumb_items, n_thumb_items * sizeof(Item), cudaMemcpyHostToDevice, ds));
-    if (uploads) {
-        CK(cudaEventRecord(st.uploaded, b->copy_stream));
-        CK(cudaStreamWaitEvent(s, st.uploaded, 0));
-    }
+    const bool any_ladder = (live && (b->n_items || b->n_big_items)) || n_thumb_items;
+    if (any_ladder) CK(cudaMemsetAsync(st.d_counters, 0, 3 * sizeof(int), ds));
+    CK(cudaEventRecord(st.uploaded, ds));
+    CK(cudaStreamWaitEvent(s, st.uploaded, 0));
     if (n_jobs) {
         if (b->timing) CK(cudaEventRecord(st.y0, s));
         CK(launch_yadif(st.d_jobs, n, max_w, max_h, all_fast, s));
@@ -865,7 +865,6 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
         L.double_buffer = 0;                             // decided by launch_ladder from the shared-memory budget
         return L;
     };
-    if ((live && (b->n_items || b->n_big_items)) || n_thumb_items) CK(cudaMemsetAsync(st.d_counters, 0, 3 * sizeof(int), s));
     if (live && b->n_items) {
         if (b->timing) CK(cudaEventRecord(st.k0, s));
         CK(launch_ladder(make_launch(b->d_items, b->n_items, 0), s));
