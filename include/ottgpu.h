@@ -134,8 +134,10 @@ int  ottgpu_channel_describe(const ottgpu_channel *ch, char *buf, size_t size);
 /* --- batch = many channels of one GPU advanced by ONE fused launch per stage (in-process multi-channel daemon) ----- */
 enum { OTTGPU_SUBMIT_SYNC = 0, OTTGPU_SUBMIT_ASYNC = 1 };
 int  ottgpu_batch_create(ottgpu_channel **channels, int n, ottgpu_batch **out);    /* channels must share gpu + stream */
-/* in[n] / out[n]; in[i].data == NULL skips channel i this step.  ASYNC: returns after enqueueing; host-memory results
- * and out[] fields are valid after ottgpu_batch_wait().                                                                */
+/* in[n] / out[n]; in[i].data == NULL skips channel i this step.  ASYNC: returns after enqueueing; at most two steps are
+ * in flight (a third submit first waits for the oldest).  Host-memory results, out[] fields and the CONTENT of
+ * out[i].thumbnail are valid once the step has completed: after ottgpu_batch_wait(), or when the second-next submit of
+ * the same batch has returned.  A thumbnail buffer must not be free()d before that.                                   */
 int  ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame_out *out, int flags);
 int  ottgpu_batch_wait(ottgpu_batch *b);
 void ottgpu_batch_destroy(ottgpu_batch *b);
