@@ -601,7 +601,7 @@ def main():
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--channels", type=int, default=32, help="concurrent channels per GPU (one frame each per step)")
+    ap.add_argument("--channels", type=int, default=64, help="concurrent channels per GPU (one frame each per step)")
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
