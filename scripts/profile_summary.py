@@ -9,9 +9,16 @@ rep = os.path.join(ROOT, "gpurun_out", tag + "_ladder.ncu-rep")
 raw = subprocess.check_output(["ncu", "-i", rep, "--page", "raw", "--csv"], stderr=subprocess.DEVNULL).decode()
 rows = list(csv.reader(io.StringIO(raw)))
 h = rows[0]
+# the capture may hold launches of different classes (main ladder launch, thumbnail launch): keep the biggest grid with the
+# longest duration = the main launch of a step, never an average over unlike launches
+ig, it = h.index("launch__grid_size"), h.index("gpu__time_duration.sum")
+gmax = max(float(r[ig].replace(",", "")) for r in rows[2:])
+main = [r for r in rows[2:] if float(r[ig].replace(",", "")) == gmax]
+tmax = max(float(r[it].replace(",", "")) for r in main)
+main = [r for r in main if float(r[it].replace(",", "")) >= 0.8 * tmax]
 def col(name):
     i = h.index(name)
-    vals = [float(r[i].replace(",", "")) for r in rows[2:]]
+    vals = [float(r[i].replace(",", "")) for r in main]
     return sum(vals) / len(vals), rows[1][i]
 keys = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "smsp__inst_executed.sum",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
