@@ -189,6 +189,9 @@ int  ottgpu_converter_create(int gpu, int pix_fmt, int width, int height, int ta
  * flags: 0 = the frame is complete on return; OTTGPU_SUBMIT_ASYNC = enqueued on the stream (host pictures must stay
  * valid until ottgpu_converter_wait / a stream synchronisation) */
 int  ottgpu_converter_convert(ottgpu_converter *cv, const ottgpu_picture *in, void *dst, int dst_mem, int flags);
+/* n pictures of n converters (one per channel, same gpu) in ONE launch, ordered on cv[0]'s stream: a 1080p conversion is
+ * launch-bound, a multi-channel process converts all of a step's pictures together.  in[i] / dst[i] belong to cv[i]. */
+int  ottgpu_converter_convert_batch(ottgpu_converter *const *cv, const ottgpu_picture *in, void *const *dst, int n, int dst_mem, int flags);
 int  ottgpu_converter_wait(ottgpu_converter *cv);
 void ottgpu_converter_destroy(ottgpu_converter *cv);
 

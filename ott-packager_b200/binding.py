@@ -87,6 +87,7 @@ _SIGS = {
     "ottgpu_memcpy": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_size_t]),
     "ottgpu_converter_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "ottgpu_converter_convert": (C.c_int, [C.c_void_p, C.POINTER(Picture), C.c_void_p, C.c_int, C.c_int]),
+    "ottgpu_converter_convert_batch": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(Picture), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]),
     "ottgpu_converter_wait": (C.c_int, [C.c_void_p]),
     "ottgpu_converter_destroy": (None, [C.c_void_p]),
     "ottgpu_scale_frame": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(RungCfg),
@@ -304,6 +305,28 @@ class Converter:
 
     def wait(self):
         self.lib.check(self.lib.dll.ottgpu_converter_wait(self.handle))
+
+
+def convert_batch(lib, converters, planes_list, device_dsts=None, flags=SUBMIT_SYNC, mem=MEM_HOST, strides_list=None):
+    """One launch for the pictures of several converters (one per channel).  Returns the packed frames (host) or None."""
+    n = len(converters)
+    cvs = (C.c_void_p * n)(*[c.handle for c in converters])
+    pics = (Picture * n)()
+    keep = []
+    for i, (c, planes) in enumerate(zip(converters, planes_list)):
+        p = c.picture(planes, mem, None if strides_list is None else strides_list[i])
+        pics[i].mem = p.mem
+        for k in range(3):
+            pics[i].plane[k], pics[i].stride[k] = p.plane[k], p.stride[k]
+        keep.append(planes)
+    if device_dsts is not None:
+        dsts = (C.c_void_p * n)(*device_dsts)
+        lib.check(lib.dll.ottgpu_converter_convert_batch(cvs, pics, dsts, n, MEM_DEVICE, flags))
+        return None
+    outs = [np.empty(c.out_bytes, np.uint8) for c in converters]
+    dsts = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+    lib.check(lib.dll.ottgpu_converter_convert_batch(cvs, pics, dsts, n, MEM_HOST, SUBMIT_SYNC))
+    return outs
 
 
 class Batch:

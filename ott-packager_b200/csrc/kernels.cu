@@ -198,6 +198,12 @@ __global__ void __launch_bounds__(256) convert_kernel(const ConvertJob j)
     convert_position(j, blockIdx.x * 32 + (threadIdx.x & 31), blockIdx.y * 8 + (threadIdx.x >> 5));
 }
 
+// many pictures (different converters) in one launch: blockIdx.z = job
+__global__ void __launch_bounds__(256) convert_batch_kernel(const ConvertJob *__restrict__ jobs)
+{
+    convert_position(jobs[blockIdx.z], blockIdx.x * 32 + (threadIdx.x & 31), blockIdx.y * 8 + (threadIdx.x >> 5));
+}
+
 cudaError_t configure_kernels()
 {
     return cudaFuncSetAttribute(ladder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTileSmem);
@@ -266,6 +272,15 @@ cudaError_t launch_convert(const ConvertJob &job, cudaStream_t s)
     if (rows <= 0 || groups <= 0) return cudaSuccess;
     dim3 grid((groups + 31) / 32, (rows + 7) / 8, 1);
     convert_kernel<<<grid, 256, 0, s>>>(job);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_convert_batch(const ConvertJob *jobs, int n_jobs, int max_w, int max_rows, cudaStream_t s)
+{
+    if (n_jobs <= 0 || max_w <= 0 || max_rows <= 0) return cudaSuccess;
+    // luma: 16-sample groups over max_w; chroma planes are half as wide, their 8-sample groups fit the same range
+    dim3 grid(((max_w + kConvertGroup - 1) / kConvertGroup + 31) / 32, (max_rows + 7) / 8, n_jobs);
+    convert_batch_kernel<<<grid, 256, 0, s>>>(jobs);
     return cudaGetLastError();
 }
 

@@ -23,6 +23,8 @@ cudaError_t launch_yadif(const YadifJob *jobs, int n_jobs, int max_w, int max_h,
 
 // decode-side converter: one launch per picture
 cudaError_t launch_convert(const ConvertJob &job, cudaStream_t s);
+// many pictures in one launch; jobs live in device memory; max_w / max_rows bound the grid (rows = Y + U + V rows)
+cudaError_t launch_convert_batch(const ConvertJob *jobs, int n_jobs, int max_w, int max_rows, cudaStream_t s);
 
 cudaError_t configure_kernels();
 

@@ -1078,6 +1078,8 @@ struct ottgpu_converter {
     cudaEvent_t done[kSets] = {nullptr, nullptr};
     int phase = 0;
     size_t out_bytes = 0;
+    ConvertJob *h_jobs[kSets] = {nullptr, nullptr}, *d_jobs[kSets] = {nullptr, nullptr};   // batch calls led by this converter
+    int job_capacity = 0;
 };
 
 namespace {
@@ -1094,6 +1096,8 @@ void converter_free(ottgpu_converter *cv)
     for (int s = 0; s < ottgpu_converter::kSets; ++s) {
         for (int p = 0; p < 3; ++p) cudaFree(cv->stage[s][p]);
         cudaFree(cv->out_stage[s]);
+        cudaFreeHost(cv->h_jobs[s]);
+        cudaFree(cv->d_jobs[s]);
         if (cv->done[s]) cudaEventDestroy(cv->done[s]);
     }
     cudaFree(cv->d_vpos);
@@ -1164,7 +1168,12 @@ int ottgpu_converter_create(int gpu, int pix_fmt, int width, int height, int tar
     return OTTGPU_OK;
 }
 
-int ottgpu_converter_convert(ottgpu_converter *cv, const ottgpu_picture *in, void *dst, int dst_mem, int flags)
+}  // extern "C"
+
+namespace {
+
+// Validates one picture, uploads host planes into the converter's staging set and fills the kernel's job.
+int converter_prepare(ottgpu_converter *cv, const ottgpu_picture *in, void *dst, int dst_mem, int set, cudaStream_t stream, ConvertJob &j)
 {
     if (!cv || !in || !dst) return fail(OTTGPU_ERR_ARG, "null argument");
     if ((in->mem != OTTGPU_MEM_HOST && in->mem != OTTGPU_MEM_DEVICE) || (dst_mem != OTTGPU_MEM_HOST && dst_mem != OTTGPU_MEM_DEVICE))
@@ -1173,18 +1182,13 @@ int ottgpu_converter_convert(ottgpu_converter *cv, const ottgpu_picture *in, voi
         if (!in->plane[p]) return fail(OTTGPU_ERR_ARG, "null plane");
         if (in->stride[p] < cv->row_bytes[p]) return fail(OTTGPU_ERR_ARG, "stride smaller than the row");
     }
-    CK(cudaSetDevice(cv->gpu));
-    const int set = cv->phase;
-    cv->phase ^= 1;
-    CK(cudaEventSynchronize(cv->done[set]));                 // the conversion that last used this set has finished
-    ConvertJob j;
     std::memset(&j, 0, sizeof(j));
     for (int p = 0; p < 3; ++p) {
         ConvertPlane &P = j.plane[p];
         if (in->mem == OTTGPU_MEM_HOST) {
             if (!cv->stage[set][p]) CK(cudaMalloc((void **)&cv->stage[set][p], cv->stage_pitch[p] * cv->src_rows[p] + 16));
             CK(cudaMemcpy2DAsync(cv->stage[set][p], cv->stage_pitch[p], in->plane[p], (size_t)in->stride[p], (size_t)cv->row_bytes[p],
-                                 (size_t)cv->src_rows[p], cudaMemcpyHostToDevice, cv->stream));
+                                 (size_t)cv->src_rows[p], cudaMemcpyHostToDevice, stream));
             P.src = cv->stage[set][p];
             P.src_pitch = (int)cv->stage_pitch[p];
         } else {
@@ -1215,10 +1219,73 @@ int ottgpu_converter_convert(ottgpu_converter *cv, const ottgpu_picture *in, voi
     j.vtaps = cv->vtaps; j.exact_from = cv->exact_from;
     j.approx = cv->target == OTTGPU_TARGET_A;
     std::memcpy(j.bayer, kBayer8x8, sizeof(j.bayer));
+    return OTTGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ottgpu_converter_convert(ottgpu_converter *cv, const ottgpu_picture *in, void *dst, int dst_mem, int flags)
+{
+    if (!cv) return fail(OTTGPU_ERR_ARG, "null argument");
+    CK(cudaSetDevice(cv->gpu));
+    const int set = cv->phase;
+    CK(cudaEventSynchronize(cv->done[set]));                 // the conversion that last used this set has finished
+    ConvertJob j;
+    int rc = converter_prepare(cv, in, dst, dst_mem, set, cv->stream, j);
+    if (rc) return rc;
+    cv->phase ^= 1;
     CK(launch_convert(j, cv->stream));
-    if (dst_mem == OTTGPU_MEM_HOST) CK(cudaMemcpyAsync(dst, d, cv->out_bytes, cudaMemcpyDeviceToHost, cv->stream));
+    if (dst_mem == OTTGPU_MEM_HOST) CK(cudaMemcpyAsync(dst, cv->out_stage[set], cv->out_bytes, cudaMemcpyDeviceToHost, cv->stream));
     CK(cudaEventRecord(cv->done[set], cv->stream));
     if (!(flags & OTTGPU_SUBMIT_ASYNC)) CK(cudaStreamSynchronize(cv->stream));
+    return OTTGPU_OK;
+}
+
+int ottgpu_converter_convert_batch(ottgpu_converter *const *cv, const ottgpu_picture *in, void *const *dst, int n, int dst_mem, int flags)
+{
+    if (!cv || !in || !dst || n < 1) return fail(OTTGPU_ERR_ARG, "null argument");
+    ottgpu_converter *lead = cv[0];
+    if (!lead) return fail(OTTGPU_ERR_ARG, "null converter");
+    for (int i = 0; i < n; ++i) {
+        if (!cv[i]) return fail(OTTGPU_ERR_ARG, "null converter");
+        if (cv[i]->gpu != lead->gpu) return fail(OTTGPU_ERR_ARG, "converters of one batch must be on the same gpu");
+        for (int k = 0; k < i; ++k)
+            if (cv[k] == cv[i]) return fail(OTTGPU_ERR_ARG, "a converter may appear once per batch");
+    }
+    CK(cudaSetDevice(lead->gpu));
+    cudaStream_t s = lead->stream;                            // the whole batch is ordered on the first converter's stream
+    const int set = lead->phase;
+    for (int i = 0; i < n; ++i) {
+        if (cv[i]->phase != set) return fail(OTTGPU_ERR_STATE, "converters of one batch must have been used the same number of times");
+        CK(cudaEventSynchronize(cv[i]->done[set]));
+    }
+    if (lead->job_capacity < n) {                             // job lists (pinned + device, one pair per set) sized on first use
+        for (int k = 0; k < ottgpu_converter::kSets; ++k) {
+            cudaFreeHost(lead->h_jobs[k]);
+            cudaFree(lead->d_jobs[k]);
+            lead->h_jobs[k] = nullptr; lead->d_jobs[k] = nullptr;
+            CK(cudaMallocHost((void **)&lead->h_jobs[k], (size_t)n * sizeof(ConvertJob)));
+            CK(cudaMalloc((void **)&lead->d_jobs[k], (size_t)n * sizeof(ConvertJob)));
+        }
+        lead->job_capacity = n;
+    }
+    int max_w = 0, max_rows = 0;
+    for (int i = 0; i < n; ++i) {
+        int rc = converter_prepare(cv[i], &in[i], dst[i], dst_mem, set, s, lead->h_jobs[set][i]);
+        if (rc) return rc;
+        max_w = std::max(max_w, cv[i]->w);
+        max_rows = std::max(max_rows, cv[i]->dh[0] + cv[i]->dh[1] + cv[i]->dh[2]);
+    }
+    CK(cudaMemcpyAsync(lead->d_jobs[set], lead->h_jobs[set], (size_t)n * sizeof(ConvertJob), cudaMemcpyHostToDevice, s));
+    CK(launch_convert_batch(lead->d_jobs[set], n, max_w, max_rows, s));
+    for (int i = 0; i < n; ++i) {
+        if (dst_mem == OTTGPU_MEM_HOST) CK(cudaMemcpyAsync(dst[i], cv[i]->out_stage[set], cv[i]->out_bytes, cudaMemcpyDeviceToHost, s));
+        cv[i]->phase ^= 1;
+        CK(cudaEventRecord(cv[i]->done[set], s));
+    }
+    if (!(flags & OTTGPU_SUBMIT_ASYNC)) CK(cudaStreamSynchronize(s));
     return OTTGPU_OK;
 }
 

@@ -71,6 +71,14 @@ cudaError_t launch_yadif(const YadifJob *jobs, int n_jobs, int max_w, int max_h,
     return cudaSuccess;
 }
 
+cudaError_t launch_convert_batch(const ConvertJob *jobs, int n_jobs, int max_w, int max_rows, cudaStream_t)
+{
+    for (int z = 0; z < n_jobs; ++z)
+        for (int r = 0; r < (max_rows + 7) / 8 * 8; ++r)
+            for (int x = 0; x < ((max_w + kConvertGroup - 1) / kConvertGroup + 31) / 32 * 32; ++x) convert_position(jobs[z], x, r);
+    return cudaSuccess;
+}
+
 cudaError_t launch_convert(const ConvertJob &job, cudaStream_t)
 {
     const int rows = job.plane[0].h + job.plane[1].h + job.plane[2].h;

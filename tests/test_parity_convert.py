@@ -134,3 +134,20 @@ def test_full_size_1080_422p10_device_picture(real_lib, og, oracle):
     cv.close()
     for p in pools + [out_pool]:
         p.close()
+
+
+def test_batched_conversion_one_launch(lib, og, oracle):
+    """Several channels' pictures (different formats and sizes) converted by ONE launch; twice, so both staging sets of
+    every converter are used; results identical to the per-picture path."""
+    specs = [("yuv422p10le", 192, 108), ("yuv420p10le", 130, 74), ("yuv422p", 96, 64), ("yuv420p", 66, 38), ("yuv422p10le", 64, 48)]
+    cvs = [og.Converter(lib, pix(og, f), w, h) for f, w, h in specs]
+    for rnd in range(3):
+        planes = [decoded_planes(f, w, h, 700 + 10 * rnd + k, "noise" if (k + rnd) % 2 else "extreme", pad=8 * (k % 3)) for k, (f, w, h) in enumerate(specs)]
+        outs = og.convert_batch(lib, cvs, planes)
+        for (f, w, h), p, got in zip(specs, planes, outs):
+            assert np.array_equal(got, oracle.convert_to_i420(p, pix(oracle, f), w, h)), (f, w, h, rnd)
+    # a converter may not appear twice in one batch
+    with pytest.raises(og.OttGpuError):
+        og.convert_batch(lib, [cvs[0], cvs[0]], [planes[0], planes[0]])
+    for c in cvs:
+        c.close()
