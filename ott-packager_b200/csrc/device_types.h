@@ -101,7 +101,7 @@ struct LadderLaunch {
     int src_max;             // bytes of ONE staged-source buffer (max over the launch's tiles, multiple of 16)
     int mid_max;             // bytes of the H-pass result region (multiple of 16)
     int vc_max;              // bytes of the V coefficient + vpos region
-    int double_buffer;       // 1: two source buffers (tile k+1 may be fetched before tile k's H pass has finished)
+    int double_buffer;       // 1: two source buffers (kept for experiments; the launcher always uses one: the V pass hides the copy)
     int mid_buffers;         // 2: H-pass results alternate between two regions, so a warp that finishes its share of
                              //    the V pass starts the next tile's H pass without waiting for the others
 };

@@ -1,8 +1,8 @@
 // sm_100a kernels of libottgpu.
 //   ladder_kernel : persistent fused H+V polyphase scaler / format writer.  Each CTA pulls output tiles (work items:
 //                   all rungs of all channels of a batch) from a global counter; the tile's source rows are fetched by
-//                   the TMA engine (one 2-D tensor-map box per plane, mbarrier completion) into one of two shared buffers
-//                   while the previous tile is still computing.  The source frame is read from HBM once and shared by
+//                   the TMA engine (one 2-D tensor-map box per plane, mbarrier completion) into the shared source buffer
+//                   while the previous tile's V pass is still running.  The source frame is read from HBM once and shared by
 //                   the rungs through L2 (items are ordered by source row band), see DESIGN.md.
 //   yadif_kernel  : yadif mode 0 first-field deinterlacer on planar 8/16-bit frames.
 //   convert_kernel: decode-side 4:2:2 / 10-bit -> packed 8-bit 4:2:0 converter.

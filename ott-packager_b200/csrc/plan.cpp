@@ -407,7 +407,7 @@ std::shared_ptr<Plan> build_plan(const ottgpu_cfg &cfg, std::string &err)
         std::vector<int32_t> lh, lv, chh, cv;
         if (!build_plane(*plan, R.luma, cfg.src_width, cfg.src_height, rc.width, rc.height, bps, bps, 1, filt, cfg.target, luma_exact, rl, soft_l, lh, lv, err)) return nullptr;
         if (!build_plane(*plan, R.chroma, scw, sch, dcw, dch, bps, cfg.src_fmt == OTTGPU_FMT_P010 ? 4 : bps, 2, filt, cfg.target, chroma_exact, rc2, soft_c, chh, cv, err)) return nullptr;
-        // launch class per plane kind: 0 = inside the double-buffer budget, 1 = big tiles, 2 = thumbnail
+        // launch class per plane kind: 0 = inside the two-CTAs-per-SM budget, 1 = big tiles, 2 = thumbnail
         const int class_l = is_thumb ? 2 : (soft_l ? 0 : 1), class_c = is_thumb ? 2 : (soft_c ? 0 : 1);
         auto account = [&](int cls, const TileRegions &r) {
             plan->src_max[cls] = std::max(plan->src_max[cls], (int)r.src);

@@ -30,7 +30,7 @@ struct Plan {
     RungLayout layout[kMaxRungSlots];
     PlanDev host_copy{};                               // what was uploaded (device pointers inside)
     PlanDev *dev = nullptr;
-    std::vector<Item> items;                           // chan = 0; rung tiles inside the double-buffer budget, ordered by source row band
+    std::vector<Item> items;                           // chan = 0; rung tiles inside the two-CTAs-per-SM budget, ordered by source row band
     std::vector<Item> big_items;                       // rung tiles of very steep / long filters: own (larger) launch
     std::vector<Item> thumb_items;                     // the thumbnail slot's items (launched only when due)
     // shared-memory region maxima (bytes) over the tiles of the launch classes: [0] items, [1] big_items, [2] thumbnail
