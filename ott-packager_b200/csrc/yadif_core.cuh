@@ -166,14 +166,17 @@ OTT_DEV void yadif_oct8(const YadifJob &j, size_t off, int w, int h, int x8, int
     int cu[16], cd[16];                                    // samples 8*x8-4 .. 8*x8+11 of the rows above / below
     OTT_UNROLL
     for (int k = 0; k < 16; ++k) { cu[k] = ybyte(cuw[k >> 2], k & 3); cd[k] = ybyte(cdw[k >> 2], k & 3); }
+    const bool first_group = x8 == 0, last_group = 8 * x8 + 8 >= w;
     uint32_t o16[4];
     OTT_UNROLL
     for (int i = 0; i < 8; ++i) {
-        const int x = 8 * x8 + i, q = i + 4;
+        const int q = i + 4;
         const int c = cu[q], e = cd[q];
         int p = (c + e) >> 1;
+        // the search is skipped on the first and last three samples of a row (filter_edges): with w a multiple of 8 those
+        // are samples 0-2 of the first group and 5-7 of the last one, a per-thread flag instead of two compares per sample.
         // vf_yadif only tries +-2 when +-1 improved the score
-        const bool in = x >= 3 && x < w - 3;
+        const bool in = i < 3 ? !first_group : (i >= 5 ? !last_group : true);
         int score = ott_sad(cu[q + 1], cd[q + 1], ott_sad(c, e, ott_sad(cu[q - 1], cd[q - 1], -1)));
         const int s1 = ott_sad(c, cd[q + 2], ott_sad(cu[q - 1], cd[q + 1], ott_sad(cu[q - 2], e, 0)));                   // j = -1
         const int s2 = ott_sad(cu[q - 1], cd[q + 3], ott_sad(cu[q - 2], cd[q + 2], ott_sad(cu[q - 3], cd[q + 1], 0)));  // j = -2
