@@ -21,7 +21,7 @@ SUBMIT_SYNC, SUBMIT_ASYNC = 0, 1
 PIX_YUV420P, PIX_YUV422P, PIX_YUV420P10, PIX_YUV422P10 = 0, 1, 2, 3
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_LIB = os.path.join(HERE, "libottgpu.so")
+DEFAULT_LIB = os.environ.get("OTTGPU_LIB") or os.path.join(HERE, "libottgpu.so")     # OTTGPU_LIB: A/B builds in profiling sessions
 
 
 class RungCfg(C.Structure):
