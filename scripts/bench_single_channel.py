@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """One channel driven the way ONE fillet process drives it (the reference runs one process per channel): synchronous
 ottgpu_channel_submit per frame, pinned host frame in, rungs to host memory (x264/x265 mode) or left in device surfaces
-(NVENC mode).  Prints per-frame latency; the CPU figure beside it is one libswscale thread doing the same ladder
-(how the reference's video_scale_thread works, transvideo.c:1504-1683)."""
+(NVENC mode).  Prints per-frame latency.  The CPU figure to hold beside it is bench.py's cpu_baseline.single_thread (one
+libswscale thread doing the same ladder, how the reference's video_scale_thread works, transvideo.c:1504-1683)."""
 import argparse, importlib, json, os, sys, time
 import numpy as np
 
@@ -53,9 +53,7 @@ def main():
         ch.close()
         lat.sort()
         out[mode] = {"ms_median": lat[len(lat) // 2], "ms_p99": lat[int(len(lat) * 0.99)], "frames_per_sec": 1000.0 / (sum(lat) / len(lat))}
-    done, el, kind, _ = B.run_cpu_rounds(wl, frames, 1, seconds=4.0)
-    B.emit({"metric": "single_channel_frame_latency", "workload": wl["desc"], "gpu": out,
-            "cpu_one_thread": {"ms_per_frame": 1000.0 * el / done, "frames_per_sec": done / el, "kind": kind}})
+    B.emit({"metric": "single_channel_frame_latency", "workload": wl["desc"], "gpu": out})
 
 
 if __name__ == "__main__":

@@ -1,15 +1,15 @@
 #!/usr/bin/env python
 """TEST INFRASTRUCTURE: seeded random differential check of the kernel source (CPU emulation build, tests/emu) against the
-oracle - ladder geometry (I420/NV12, P010), yadif frame sizes, decode-side converter.  Not part of the pytest tiers
+oracle - ladder geometry (I420/NV12, P010), yadif frame sizes, decode-side converter.  Lives in tests/ (it uses the oracle) but is not collected by pytest
 (minutes, not seconds); run it after touching the planner or a kernel core:
 
-    python scripts/fuzz_emu.py [--cases 600] [--seed 77] [--lib path/to/libottgpu(.so|_emu.so)]"""
+    python tests/fuzz_emu.py [--cases 600] [--seed 77] [--lib path/to/libottgpu(.so|_emu.so)]"""
 import argparse, importlib, os, subprocess, sys
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from conftest import noise_i420, noise_p010, decoded_planes, DECODED_FORMATS  # noqa: E402
 from oracle import oracle  # noqa: E402
 
