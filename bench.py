@@ -12,7 +12,8 @@ C channels per GPU, channel-sharded, no collective on the data path -- SURVEY.md
   roofline   : ladder_kernel algorithmic bytes / its CUDA-event launch time vs MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline / --impl reference: the reference's CPU path (real libswscale 8.0.1 via oracle/swscale_so.py when the
                bundled .so is present, else the C oracle port) on the box's host cores.
-Nothing here reads /root/reference.  oracle/ is used only by the cpu_baseline / reference legs and the parity spot check.
+Nothing here reads /root/reference.  oracle/ is executed only by the cpu_baseline leg (which also checks the last step's GPU
+output against the CPU result) and by --impl reference.
 """
 import argparse
 import gc
@@ -429,9 +430,12 @@ def ours_main(args, wl, rank, world, local_rank):
     frames_per_step = Cn
     value = world * frames_per_step * args.steps / (ms / 1000.0)
 
-    # parity spot check (channel 0, the frame produced by the last step) against the CPU oracle
+    # First half of the cpu_baseline leg (rank 0, N=1, not with --no-cpu): the frames the last timed step produced are
+    # compared with what the CPU path computes for the same inputs.  oracle/ is only ever executed by this leg and by
+    # --impl reference, as the checker / the baseline - never on the measured path.
     parity = None
-    if rank == 0 and args.steps >= 3 and src_fmt == P010:
+    cpu_leg = rank == 0 and world == 1 and not args.no_cpu
+    if cpu_leg and args.steps >= 3 and src_fmt == P010:
         from oracle import oracle as O
         last_phase = (args.steps - 1) % RING
         exp_src = base_frames[((args.steps - 2) % RING) % 4].view(np.uint16)
@@ -442,7 +446,7 @@ def ours_main(args, wl, rank, world, local_rank):
             got = lib.from_device(dst_dev[0][last_phase % 2][r], rung_bytes[r], gpu=local_rank).view(np.uint16)
             ok = ok and np.array_equal(got, O.scale_p010(exp_src, w, h, dw, dh, O.LANCZOS))
         parity = "bit-exact vs oracle (channel 0, rungs 2160p + 360p)" if ok else "MISMATCH"
-    elif rank == 0 and args.steps >= 3:
+    elif cpu_leg and args.steps >= 3:
         from oracle import oracle as O
         # timed step k used ios[k % RING]; the last step's output is the frame submitted one step earlier (yadif latency).
         # First, middle and last channel of the launch (their tiles are spread over different CTAs and waves).
@@ -546,7 +550,7 @@ def ours_main(args, wl, rank, world, local_rank):
                                     "achieved": y_bytes / (y_ms * 1e-3) / 1e9, "frac": y_bytes / (y_ms * 1e-3) / 1e9 / peak}
     # ---------------- CPU baseline (rank 0, N=1 only), bounded sample
     cpu = None
-    if world == 1 and not args.no_cpu:
+    if cpu_leg:
         threads = host_cores()
         done, el, kind, _ = run_cpu_rounds(wl, base_frames, threads, seconds=args.cpu_seconds)
         one_done, one_el, _, _ = run_cpu_rounds(wl, base_frames, 1, seconds=min(3.0, args.cpu_seconds))

@@ -14,7 +14,7 @@ tail -5 $OUT/${TAG}_pytest.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke exit $?" | tee -a $OUT/${TAG}_smoke.log
 timeout 600 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench exit $?"
 cat $OUT/${TAG}_bench.json; tail -3 $OUT/${TAG}_bench.err
-timeout 300 python bench.py --workload cfg1 --no-cpu --steps 100 > $OUT/${TAG}_bench_cfg1.json 2> $OUT/${TAG}_bench_cfg1.err; cat $OUT/${TAG}_bench_cfg1.json
+timeout 300 python bench.py --workload cfg1 --cpu-seconds 0.5 --steps 100 > $OUT/${TAG}_bench_cfg1.json 2> $OUT/${TAG}_bench_cfg1.err; cat $OUT/${TAG}_bench_cfg1.json
 BENCH_SMALL="python bench.py --steps 4 --warmup 3 --no-cpu"
 timeout 300 $BENCH_SMALL > $OUT/${TAG}_plain.log 2>&1 && \
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/${TAG}_launches.csv $BENCH_SMALL > $OUT/${TAG}_ncu1.log 2>&1

@@ -10,7 +10,7 @@ else
   timeout 600 python -m pytest tests/test_parity_ladder.py tests/test_parity_channel.py -x -q -m gpu -k "not digest" > $OUT/${TAG}_pytest.log 2>&1; echo "pytest exit $?"
 fi
 tail -3 $OUT/${TAG}_pytest.log
-timeout 600 python bench.py --no-cpu --steps 300 ${BENCH_ARGS:-} > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench exit $?"
+timeout 600 python bench.py --cpu-seconds 0.5 --steps 300 ${BENCH_ARGS:-} > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench exit $?"
 python - <<PY
 import json
 try:

@@ -4,10 +4,10 @@
 # step-down list; keep src + 2*mid + ~9 KB of tables under 112 KB or the launch drops to one CTA per SM)
 WL=${1:-cfg2}; CH=${2:-32}
 OUT=gpurun_out; mkdir -p $OUT
-run() { env "$@" python bench.py --workload $WL --channels $CH --no-cpu --steps 200 > $OUT/sweep.json 2>$OUT/sweep.err; python - "$*" <<'PY'
+run() { env "$@" python bench.py --workload $WL --channels $CH --cpu-seconds 0.5 --steps 200 > $OUT/sweep.json 2>$OUT/sweep.err; python - "$*" <<'PY'
 import json,sys
 try:
-    d=json.load(open("gpurun_out/sweep.json")); print("%-70s kernel %.4f ms  value %.0f  parity %s" % (sys.argv[1], d["roofline"]["ms_per_launch"], d["value"], d["config"]["parity"][:9]))
+    d=json.load(open("gpurun_out/sweep.json")); print("%-70s kernel %.4f ms  value %.0f  parity %s" % (sys.argv[1], d["roofline"]["ms_per_launch"], d["value"], str(d["config"]["parity"])[:9]))
 except Exception as e: print(sys.argv[1], "FAILED", e, open("gpurun_out/sweep.err").read()[-300:])
 PY
 }
