@@ -38,11 +38,21 @@ struct PlaneTables {
     const int16_t *hc16;     // [dstW][4*hq] plain 14-bit coefficients (16-bit sample path)
     const uint32_t *hc_pair; // [dstW][hq+1][2] 8-bit path: s16x2 coefficient pairs laid out against the source WORDS the
                              //   window starts in (taps shifted by hpos&3 bytes, zero padded): {bytes 0,1}, {bytes 2,3}
+    const uint32_t *hmma;    // 8-bit path: [ceil(dstW/8)][hks][32 lanes][4] IMMA.16832 B fragments of each group of 8 output
+                             //   columns: {hi.b0, hi.b1, lo.b0, lo.b1}, coefficient = hi << hsplit | lo, laid out against
+                             //   the source bytes hkbase[group] + 32*kstep + k
+    const int32_t *hkbase;   // [ceil(dstW/8)] first source byte of the group's K window (multiple of 4)
     const int32_t *vpos;     // [dstH]   first source row of each output row
     const int16_t *vc;       // [dstH][vtaps] 12-bit coefficients
     int srcW, srcH, dstW, dstH;
     int hq;                  // horizontal taps / 4 (tables zero-padded to a multiple of four taps)
+    int hks;                 // 8-bit path: K steps (32 source bytes each) of the H-pass contraction
+    int hsplit;              // 8-bit path: 7 (c = 128*hi + lo, lo < 256) or 8 (c = 256*hi + lo)
+    int mid_pitch;           // H-pass result row pitch in shared memory (mid_t elements): tw + 8, so that the fragment
+                             //   stores of the H pass and the 16-byte loads of the V pass are both bank-conflict free
     int vtaps;
+    int vbias;               // 8-bit target A fast path: per-product bias (max|c| >> 1) + 1 of the V pass, 0 = not usable
+                             //   (odd tap count, or taps * (max|c| + 2) would overflow a 16-bit lane)
     int exact_from;          // 8-bit target A: first output row computed with the exact vertical formula
     int tw, th;              // tile size in output samples
     int cpt;                 // V pass: adjacent columns per thread (8 | 4), chosen so the tile's work divides evenly
@@ -97,6 +107,7 @@ struct LadderLaunch {
     const Item *items;
     const Binding *binds;
     int n_items;
+    int bps;                 // bytes per sample of every item's channel (1 | 2): selects the kernel instance
     int *counter;            // dynamic tile scheduler (zeroed before every launch)
     int src_max;             // bytes of ONE staged-source buffer (max over the launch's tiles, multiple of 16)
     int mid_max;             // bytes of the H-pass result region (multiple of 16)
@@ -140,6 +151,8 @@ struct ConvertJob {
     const int32_t *vpos;     // [chroma rows] first source row of each output row
     const int16_t *vc;       // [chroma rows * vtaps] 12-bit coefficients
     int vtaps;
+    int vbias;               // 8-bit target A fast path: per-product bias (max|c| >> 1) + 1 of the V pass, 0 = not usable
+                             //   (odd tap count, or taps * (max|c| + 2) would overflow a 16-bit lane)
     int exact_from;          // first chroma row that takes the exact vertical path under target A
     int approx;              // 1: target A (x86 default flags), 0: target B
     uint8_t bayer[64];       // ff_dither_8x8_128

@@ -85,6 +85,7 @@ constexpr int kLadderThreads = kThreads + 32;     // 12 compute warps + 1 produc
 //   compute warps : wait ready[slot] -> H pass (staged rows -> int16 intermediates) -> V pass + store -> release the
 //                   descriptor slot and the source buffer.
 // One source buffer: it is released after the H pass, tile k+1 streams in while tile k's V pass runs.
+template <int BPS>
 __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderLaunch L)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -166,14 +167,14 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
                 phase_stage(tid, g, smem);
                 compute_sync();
             }
-            if (g.src_shift) {                     // P010: right-align the 10 significant bits in place
+            if (BPS == 2 && g.src_shift) {         // P010: right-align the 10 significant bits in place
                 phase_fixup16(tid, g, smem);
                 compute_sync();
             }
-            phase_hpass(tid, g, smem);
+            phase_hpass<BPS>(tid, g, smem);
             compute_sync();                        // H-pass result and V tables complete; the source buffer is free
             mbar_arrive(&empty[s_buf[slot]]);
-            phase_vpass(tid, g, smem);
+            phase_vpass<BPS>(tid, g, smem);
             // one intermediate region: everybody must be done reading it before the next tile's H pass writes it.  Two
             // regions: the next H pass writes the other one, and the region it will overwrite after that was last read
             // before the barrier above - no wait here, a warp that is done starts the next tile at once
@@ -206,7 +207,9 @@ __global__ void __launch_bounds__(256) convert_batch_kernel(const ConvertJob *__
 
 cudaError_t configure_kernels()
 {
-    return cudaFuncSetAttribute(ladder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTileSmem);
+    cudaError_t e = cudaFuncSetAttribute(ladder_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTileSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ladder_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTileSmem);
+    return e;
 }
 
 // Shared memory layout of one CTA: [source buffer(s)] [intermediate region(s)] [kGeomSlots table regions].
@@ -227,7 +230,8 @@ int ladder_ctas_per_sm(size_t smem_bytes)
 {
     int per_sm = 0;
     if (smem_bytes > kMaxTileSmem) return 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ladder_kernel, kLadderThreads, smem_bytes) != cudaSuccess) {
+    // both instances are built with the same launch bounds; the 8-bit one stands for the pair
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ladder_kernel<1>, kLadderThreads, smem_bytes) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
@@ -245,11 +249,14 @@ cudaError_t launch_ladder(LadderLaunch L, cudaStream_t s)
     int dev = 0, sms = 0, per_sm = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ladder_kernel, kLadderThreads, smem_bytes);
+    if (e == cudaSuccess)
+        e = L.bps == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ladder_kernel<2>, kLadderThreads, smem_bytes)
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ladder_kernel<1>, kLadderThreads, smem_bytes);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorInvalidValue;
     const int grid = L.n_items < sms * per_sm ? L.n_items : sms * per_sm;     // one wave of resident CTAs
-    ladder_kernel<<<grid, kLadderThreads, smem_bytes, s>>>(L);
+    if (L.bps == 2) ladder_kernel<2><<<grid, kLadderThreads, smem_bytes, s>>>(L);
+    else ladder_kernel<1><<<grid, kLadderThreads, smem_bytes, s>>>(L);
     return cudaGetLastError();
 }
 

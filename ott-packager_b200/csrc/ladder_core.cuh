@@ -20,6 +20,8 @@
 #if defined(OTTGPU_EMULATE)
 #include <cstring>
 #define OTT_DEV inline
+#define OTT_COLD inline
+#define OTT_NOUNROLL
 #define OTT_UNROLL
 #if !defined(__CUDACC__) && !defined(OTTGPU_EMU_VECTOR_TYPES)
 #define OTTGPU_EMU_VECTOR_TYPES
@@ -87,9 +89,14 @@ inline int ott_sad(int a, int b, int c) { return (a > b ? a - b : b - a) + c; }
 inline int ott_byte(uint32_t w, int i) { return (int)((w >> (8 * i)) & 0xffu); }
 inline uint32_t ott_lo16x2(uint32_t a, uint32_t b) { return (a & 0xffffu) | (b << 16); }          // (a.lo, b.lo)
 inline uint32_t ott_hi16x2(uint32_t a, uint32_t b) { return (a >> 16) | (b & 0xffff0000u); }     // (a.hi, b.hi)
+inline int ott_sat(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+inline uint32_t ott_pack_s16(int hi, int lo) { return ((uint32_t)ott_sat(hi, -32768, 32767) << 16) | ((uint32_t)ott_sat(lo, -32768, 32767) & 0xffffu); }
+inline uint32_t ott_pack_u8(int b1, int b0, uint32_t upper) { return (upper << 16) | ((uint32_t)ott_sat(b1, 0, 255) << 8) | (uint32_t)ott_sat(b0, 0, 255); }
 }  // namespace ottgpu
 #else
 #define OTT_DEV __device__ __forceinline__
+#define OTT_COLD __device__ __forceinline__        /* rarely taken paths (out-of-line copies measured wrong on sm_100a: kept inline, behind a branch) */
+#define OTT_NOUNROLL _Pragma("unroll 1")
 #define OTT_UNROLL _Pragma("unroll")
 namespace ottgpu {
 OTT_DEV uint32_t ott_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
@@ -132,6 +139,33 @@ OTT_DEV int ott_sad(int a, int b, int c) { return (int)__sad(a, b, (unsigned)c);
 OTT_DEV int ott_byte(uint32_t w, int i) { return (int)__byte_perm(w, 0, 0x4440 | i); }   // one PRMT instead of shift+mask
 OTT_DEV uint32_t ott_lo16x2(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x5410); }
 OTT_DEV uint32_t ott_hi16x2(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x7632); }
+// two s32 -> saturated s16 pair (hi: upper half) in one I2IP
+OTT_DEV uint32_t ott_pack_s16(int hi, int lo)
+{
+    uint32_t d;
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(d) : "r"(hi), "r"(lo));
+    return d;
+}
+// two s32 -> saturated u8 pair in bytes 1,0; the low half of `upper` moves to bytes 3,2 (one I2IP)
+OTT_DEV uint32_t ott_pack_u8(int b1, int b0, uint32_t upper)
+{
+    uint32_t d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(b1), "r"(b0), "r"(upper));
+    return d;
+}
+// m16n8k32 int8 MMA, A = u8 source bytes (rows), B = coefficient bytes (columns); accumulates into d
+OTT_DEV void ott_mma_u8s8(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+OTT_DEV void ott_mma_u8u8(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 }  // namespace ottgpu
 #endif
 
@@ -152,7 +186,8 @@ struct TileGeom {
     int sx0;                 // first staged source sample (multiple of 16 bytes)
     int nvec;                // 16-byte vectors staged per row
     int spw;                 // smem pitch of the staged source, 32-bit words (multiple of 4)
-    int mid_pitch;           // smem pitch (mid_t elements) of the H-pass result: 32 or 64
+    int mid_pitch;           // smem pitch (mid_t elements) of the H-pass result: tw + 8
+    int mid_rows;            // rows per plane in the H-pass result (sr rounded up to the H pass's 16-row groups)
     int tw_log2;             // T->tw is 32 or 64
     int approx_v;
     int off_src, off_mid, off_vc, off_vpos;   // byte offsets of the regions inside the CTA's shared memory
@@ -179,15 +214,21 @@ struct TileGeom {
 OTT_DEV void phase_tables(int tid, int nthreads, const TileGeom &g, unsigned char *smem)
 {
     const PlaneTables &T = *g.T;
-    int16_t *vc_s = reinterpret_cast<int16_t *>(smem + g.off_vc);
+    int32_t *vc_s = reinterpret_cast<int32_t *>(smem + g.off_vc);     // widened to 32 bits: the V pass multiplies them as they are
     int32_t *vpos_s = reinterpret_cast<int32_t *>(smem + g.off_vpos);
     const int n = g.th * T.vtaps, th = g.th;
     const int16_t *vc = T.vc + g.y0 * T.vtaps;
     const int32_t *vp = T.vpos + g.y0;
     if (((n | (g.y0 * T.vtaps)) & 1) == 0) {               // pairs of coefficients per load
         const uint32_t *s2 = reinterpret_cast<const uint32_t *>(vc);
-        uint32_t *d2 = reinterpret_cast<uint32_t *>(vc_s);
-        for (int i = tid; i < (n >> 1); i += nthreads) d2[i] = ott_ldg(s2 + i);
+        uint2 *d2 = reinterpret_cast<uint2 *>(vc_s);
+        for (int i = tid; i < (n >> 1); i += nthreads) {
+            const uint32_t c2 = ott_ldg(s2 + i);
+            uint2 q;
+            q.x = (uint32_t)(int)(int16_t)(c2 & 0xffffu);
+            q.y = (uint32_t)((int)c2 >> 16);
+            d2[i] = q;
+        }
     } else {
         for (int i = tid; i < n; i += nthreads) vc_s[i] = ott_ldg(vc + i);
     }
@@ -213,7 +254,7 @@ OTT_DEV uint4 load_vec_slow(const uint8_t *row, int byte_x, int row_bytes)
 
 OTT_DEV uint32_t shift_mask16(uint32_t v, int shift) { return (v >> shift) & ((0xffffu >> shift) * 0x10001u); }
 
-OTT_DEV void phase_stage(int tid, const TileGeom &g, unsigned char *smem)
+OTT_COLD void phase_stage(int tid, const TileGeom &g, unsigned char *smem)
 {
     // Register path (planes that are not 16-byte aligned): RAW bytes, same layout the TMA box produces; P010's >>6 is
     // applied afterwards by phase_fixup16 on both paths.
@@ -266,92 +307,114 @@ OTT_DEV void phase_fixup16(int tid, const TileGeom &g, unsigned char *smem)
 }
 
 // ------------------------------------------------------------------------------------------------ phase 2: H pass
-// Thread = one output column of the tile (its coefficients live in registers), striding over the staged rows.
-// 8-bit: four taps per dp4a, 14-bit coefficient split into signed high byte and unsigned low byte:
-//        sum p*c = 256*sum p*(c>>8) + sum p*(c&255)   (exact)
-// Fixed-length filters: the 14-bit coefficients are used whole, as s16 pairs against two source bytes each (dp2a),
-// positioned at table-build time against the aligned source words the window starts in - no shift, no hi/lo recombination.
-template <int HQ>
-OTT_DEV int hdot8(const uint32_t *w, const uint32_t (&c01)[HQ + 1], const uint32_t (&c23)[HQ + 1])
+// 8-bit sources: the H pass is an exact banded contraction  t[row][x] = min((sum_k src[row][k] * c[x][k]) >> 7, 32767)  of
+// u8 samples with s15 coefficients.  It runs on the tensor cores as int8 MMAs (IMMA.16832): M = 16 staged source rows,
+// N = 8 adjacent output columns, K = 32 source bytes per step starting at the group's 4-byte aligned window base, with
+// the coefficient split into two bytes, c = (hi << split) + lo, hi signed, lo unsigned:
+//     sum src*c = (H << split) + L,   H = sum src*hi  (u8 x s8 MMA),   L = sum src*lo >= 0  (u8 x u8 MMA)
+//     (sum >> 7) = (H << (split-7)) + (L >> 7)      exactly, because (H << split) is a multiple of 128 and L >= 0.
+// The B fragments come ready-made from the plan (PlaneTables::hmma); a warp keeps them in registers while it walks down
+// the rows of its column group.  A fragments are four 32-bit shared loads per K step (rows g / g+8, bytes 4t.. and
+// 16+4t..; the staged row pitch is an odd multiple of 16 bytes, so a warp's 8 rows x 16 bytes hit 32 distinct banks).
+// Results leave as saturated s16 pairs (the lower clamp is never reached: the plan rejects filters that could get there).
+#if defined(OTTGPU_EMULATE)
+// the MMA of one lane, evaluated from the shared rows and the whole fragment table (emulation runs lane by lane)
+inline void hmma_lane(const uint32_t *row_g, const uint32_t *row_g8, const uint32_t *frag32x4, int lane, int (&H)[4], int (&L)[4])
 {
-    int a = 0;
-    OTT_UNROLL
-    for (int q = 0; q <= HQ; ++q) {
-        const uint32_t s = w[q];
-        a = ott_dp2a_su(c01[q], s, a, 0);
-        a = ott_dp2a_su(c23[q], s, a, 1);
-    }
-    return ott_min(a >> 7, 32767);
-}
-
-template <int HQ>
-OTT_DEV void hpass8(int tid, const TileGeom &g, unsigned char *smem)
-{
-    const PlaneTables &T = *g.T;
-    const int col = tid & (T.tw - 1), grp = tid >> g.tw_log2, ngroups = kThreads >> g.tw_log2;
-    if (col >= g.tw) return;
-    const int gx = g.x0 + col;
-    const int off = ott_ldg(T.hpos + gx) - g.sx0;
-    uint32_t c01[HQ + 1], c23[HQ + 1];
-    OTT_UNROLL
-    for (int q = 0; q <= HQ; ++q) {
-        const uint2 c = ott_ldg(reinterpret_cast<const uint2 *>(T.hc_pair) + gx * (HQ + 1) + q);
-        c01[q] = c.x;
-        c23[q] = c.y;
-    }
-    const int sr = g.sr, nplanes = g.nplanes, pstride = g.plane_stride >> 2;
-    const int wstep = ngroups * g.spw, mstep = ngroups * g.mid_pitch;
-    for (int p = 0; p < nplanes; ++p) {
-        const uint32_t *w = reinterpret_cast<const uint32_t *>(smem + g.off_src) + p * pstride + (off >> 2) + grp * g.spw;
-        mid_t *m = reinterpret_cast<mid_t *>(smem + g.off_mid) + col + (p * sr + grp) * g.mid_pitch;
-        int left = (sr - grp + ngroups - 1) / ngroups;         // rows this thread owns in this plane
-        for (; left >= 4; left -= 4) {                         // four rows in flight per thread
-            const int v0 = hdot8<HQ>(w, c01, c23);
-            const int v1 = hdot8<HQ>(w + wstep, c01, c23);
-            const int v2 = hdot8<HQ>(w + 2 * wstep, c01, c23);
-            const int v3 = hdot8<HQ>(w + 3 * wstep, c01, c23);
-            m[0] = (mid_t)v0;
-            m[mstep] = (mid_t)v1;
-            m[2 * mstep] = (mid_t)v2;
-            m[3 * mstep] = (mid_t)v3;
-            w += 4 * wstep;
-            m += 4 * mstep;
-        }
-        for (; left > 0; --left) {
-            m[0] = (mid_t)hdot8<HQ>(w, c01, c23);
-            w += wstep;
-            m += mstep;
+    const int t = lane & 3;
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t *row = (i & 2) ? row_g8 : row_g;          // rows are passed already offset by +t words
+        const int n = 2 * t + (i & 1);
+        for (int k = 0; k < 32; ++k) {
+            const int src = (int)((row[(k >> 2) - t] >> (8 * (k & 3))) & 255u);
+            const uint32_t *f = frag32x4 + (size_t)(4 * n + ((k & 15) >> 2)) * 4;
+            const int r = k >> 4, b = k & 3;
+            H[i] += src * (int)(int8_t)((f[r] >> (8 * b)) & 255u);
+            L[i] += src * (int)((f[2 + r] >> (8 * b)) & 255u);
         }
     }
 }
+#endif
 
-// any tap count: coefficients re-read per row (L1-resident); used for very long filters (thumbnail, 4K->360p lanczos)
-OTT_DEV void hpass8_any(int tid, const TileGeom &g, unsigned char *smem)
+template <int KS, int SPLIT>
+OTT_DEV void hpass8_mma(int tid, const TileGeom &g, unsigned char *smem)
 {
     const PlaneTables &T = *g.T;
-    const int col = tid & (T.tw - 1), grp = tid >> g.tw_log2, ngroups = kThreads >> g.tw_log2;
-    if (col >= g.tw) return;
-    const int gx = g.x0 + col, hq = T.hq;
-    const int off = ott_ldg(T.hpos + gx) - g.sx0;
-    const uint32_t sh = (uint32_t)(off & 3) * 8;
-    const uint32_t *phi = T.hc_hi + gx * hq, *plo = T.hc_lo + gx * hq;
-    const int nrows = g.nplanes * g.sr, sr = g.sr, pstride = g.plane_stride >> 2;
-    const uint32_t *src_s = reinterpret_cast<const uint32_t *>(smem + g.off_src) + (off >> 2);
-    mid_t *mid_s = reinterpret_cast<mid_t *>(smem + g.off_mid) + col;
-    for (int row = grp; row < nrows; row += ngroups) {
-        const int p = row >= sr;
-        const uint32_t *w = src_s + p * pstride + (row - p * sr) * g.spw;
-        uint32_t cur = w[0];
-        int ahi = 0;
-        uint32_t alo = 0;
-        for (int q = 0; q < hq; ++q) {
-            const uint32_t nxt = w[q + 1];
-            const uint32_t a = ott_funnel_r(cur, nxt, sh);
-            ahi = ott_dp4a_us(a, ott_ldg(phi + q), ahi);
-            alo = ott_dp4a_uu(a, ott_ldg(plo + q), alo);
-            cur = nxt;
+    constexpr int kWarps = kThreads / 32;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int ks_n = KS ? KS : T.hks;
+    const int groups = (g.tw + 7) >> 3;                         // 8-column groups of this tile
+    const int mt_plane = (g.sr + 15) >> 4, mt_total = g.nplanes * mt_plane;
+    // (column group, 16-row group) pairs, column-group major, dealt out in contiguous runs so that a warp re-reads its
+    // B fragments at most twice
+    const int total = groups * mt_total, per = (total + kWarps - 1) / kWarps;
+    int f = warp * per;
+    const int fend = ott_min(f + per, total);
+    if (f >= fend) return;
+    const int spw = g.spw, pitch = g.mid_pitch;
+    const int lane_src = (lane >> 2) * spw + (lane & 3), lane_mid = (lane >> 2) * pitch + 2 * (lane & 3);
+    const uint32_t *src_s = reinterpret_cast<const uint32_t *>(smem + g.off_src) + lane_src;
+    mid_t *mid_s = reinterpret_cast<mid_t *>(smem + g.off_mid) + lane_mid;
+    int nt = f / mt_total, mt = f - nt * mt_total;
+    int left = fend - f;
+    while (left > 0) {
+        const int gnt = (g.x0 >> 3) + nt;
+        const int kw = (ott_ldg(T.hkbase + gnt) - g.sx0) >> 2;    // window base as a word offset into the staged rows
+        const uint32_t *frag = T.hmma + (size_t)gnt * ks_n * 128;
+#if !defined(OTTGPU_EMULATE)
+        uint4 B[KS ? KS : 1];
+        if (KS) {
+            OTT_UNROLL
+            for (int ks = 0; ks < KS; ++ks) B[ks] = ott_ldg(reinterpret_cast<const uint4 *>(frag) + ks * 32 + lane);
         }
-        mid_s[row * g.mid_pitch] = (mid_t)ott_min((ahi * 256 + (int)alo) >> 7, 32767);
+#endif
+        int run = ott_min(left, mt_total - mt);                   // row groups of this column group (both planes)
+        left -= run;
+        while (run > 0) {
+            const int p = mt >= mt_plane, m0 = mt - p * mt_plane;
+            int cnt = ott_min(run, mt_plane - m0);                // ... inside one plane
+            run -= cnt;
+            mt += cnt;
+            const uint32_t *rg = src_s + p * (g.plane_stride >> 2) + (m0 << 4) * spw + kw;
+            const uint32_t *rg8 = rg + 8 * spw;
+            uint32_t *o = reinterpret_cast<uint32_t *>(mid_s + (p * g.mid_rows + (m0 << 4)) * pitch + 8 * nt);
+            uint32_t *o8 = o + 4 * pitch;                          // 8 rows down: 8 * pitch elements = 4 * pitch words
+            OTT_NOUNROLL
+            for (; cnt > 0; --cnt, rg += 16 * spw, rg8 += 16 * spw, o += 8 * pitch, o8 += 8 * pitch) {
+                int H[4] = {0, 0, 0, 0}, L[4] = {0, 0, 0, 0};
+                if (KS) {
+                    OTT_UNROLL
+                    for (int ks = 0; ks < (KS ? KS : 1); ++ks) {
+#if defined(OTTGPU_EMULATE)
+                        hmma_lane(rg + 8 * ks, rg8 + 8 * ks, frag + (size_t)ks * 128, lane, H, L);
+#else
+                        const uint32_t a[4] = {rg[8 * ks], rg8[8 * ks], rg[8 * ks + 4], rg8[8 * ks + 4]};
+                        ott_mma_u8s8(H, a, B[ks].x, B[ks].y);
+                        ott_mma_u8u8(L, a, B[ks].z, B[ks].w);
+#endif
+                    }
+                } else {
+                    for (int ks = 0; ks < ks_n; ++ks) {         // long filters: fragments re-read per step (L1-resident)
+#if defined(OTTGPU_EMULATE)
+                        hmma_lane(rg + 8 * ks, rg8 + 8 * ks, frag + (size_t)ks * 128, lane, H, L);
+#else
+                        const uint4 b = ott_ldg(reinterpret_cast<const uint4 *>(frag) + ks * 32 + lane);
+                        const uint32_t a[4] = {rg[8 * ks], rg8[8 * ks], rg[8 * ks + 4], rg8[8 * ks + 4]};
+                        ott_mma_u8s8(H, a, b.x, b.y);
+                        ott_mma_u8u8(L, a, b.z, b.w);
+#endif
+                    }
+                }
+                // D fragment: lane (g,t) holds rows g and g+8, columns 2t and 2t+1; (sum >> 7) = (H << (split-7)) + (L >> 7)
+                int v[4];
+                OTT_UNROLL
+                for (int i = 0; i < 4; ++i) v[i] = (SPLIT == 7 ? H[i] : 2 * H[i]) + (int)((uint32_t)L[i] >> 7);
+                o[0] = ott_pack_s16(v[1], v[0]);
+                o8[0] = ott_pack_s16(v[3], v[2]);
+            }
+        }
+        mt = 0;
+        ++nt;
     }
 }
 
@@ -395,7 +458,7 @@ OTT_DEV void hpass16(int tid, const TileGeom &g, unsigned char *smem)
     const int wstep = ngroups * g.spw, mstep = ngroups * g.mid_pitch;
     for (int p = 0; p < nplanes; ++p) {
         const uint32_t *w = reinterpret_cast<const uint32_t *>(smem + g.off_src) + p * pstride + (off >> 1) + grp * g.spw;
-        mid_t *m = reinterpret_cast<mid_t *>(smem + g.off_mid) + col + (p * sr + grp) * g.mid_pitch;
+        mid_t *m = reinterpret_cast<mid_t *>(smem + g.off_mid) + col + (p * g.mid_rows + grp) * g.mid_pitch;
         int left = (sr - grp + ngroups - 1) / ngroups;
         for (; left >= 2; left -= 2) {                         // two rows in flight per thread
             const int v0 = hdot16<HQ>(w, sh, hi, lo);
@@ -448,7 +511,7 @@ OTT_DEV void hpass16il(int tid, const TileGeom &g, unsigned char *smem)
     mid_t *mid_s = reinterpret_cast<mid_t *>(smem + g.off_mid) + col;
     for (int row = grp; row < 2 * sr; row += ngroups) {      // rows 0..sr-1 -> U, sr..2sr-1 -> V
         const int p = row >= sr, r = row - p * sr;
-        mid_s[row * mp] = (mid_t)hdot16il<HQ>(src_s + r * spw, p, hi, lo);
+        mid_s[(p * g.mid_rows + r) * mp] = (mid_t)hdot16il<HQ>(src_s + r * spw, p, hi, lo);
     }
 }
 
@@ -471,7 +534,7 @@ OTT_DEV void hpass16il_any(int tid, const TileGeom &g, unsigned char *smem)
             const uint32_t v = w[k];
             acc += (int)(p ? v >> 16 : v & 0xffffu) * ott_ldg(pc + k);
         }
-        mid_s[row * mp] = (mid_t)ott_min(acc >> 9, 32767);
+        mid_s[(p * g.mid_rows + r) * mp] = (mid_t)ott_min(acc >> 9, 32767);
     }
 }
 
@@ -498,23 +561,22 @@ OTT_DEV void hpass16_any(int tid, const TileGeom &g, unsigned char *smem)
             acc += (int)(a & 0xffffu) * ott_ldg(pc + 2 * k) + (int)(a >> 16) * ott_ldg(pc + 2 * k + 1);
             cur = nxt;
         }
-        mid_s[row * g.mid_pitch] = (mid_t)ott_min(acc >> 9, 32767);
+        mid_s[(p * g.mid_rows + row - p * sr) * g.mid_pitch] = (mid_t)ott_min(acc >> 9, 32767);
     }
 }
 
+// BPS = bytes per sample of the launch (1 | 2): the kernel is instantiated once per sample size so that each image only
+// carries its own paths (the hot loops are sensitive to instruction-cache pressure).
+template <int BPS>
 OTT_DEV void phase_hpass(int tid, const TileGeom &g, unsigned char *smem)
 {
     const int hq = g.T->hq;
-    if (g.bps == 1) {
-        switch (hq) {
-        case 1: hpass8<1>(tid, g, smem); break;
-        case 2: hpass8<2>(tid, g, smem); break;
-        case 3: hpass8<3>(tid, g, smem); break;
-        case 4: hpass8<4>(tid, g, smem); break;
-        case 5: hpass8<5>(tid, g, smem); break;
-        case 6: hpass8<6>(tid, g, smem); break;
-        default: hpass8_any(tid, g, smem); break;
-        }
+    if (BPS == 1) {
+        const int hks = g.T->hks;
+        if (g.T->hsplit != 7) hpass8_mma<0, 8>(tid, g, smem);       // a coefficient beyond 127*128+255 (border-folded taps): rare
+        else if (hks == 1) hpass8_mma<1, 7>(tid, g, smem);
+        else if (hks == 2) hpass8_mma<2, 7>(tid, g, smem);
+        else hpass8_mma<0, 7>(tid, g, smem);
     } else if (g.src_interleaved) {
         switch (hq) {
         case 1: hpass16il<1>(tid, g, smem); break;
@@ -600,7 +662,7 @@ OTT_DEV uint32_t pack4(int a, int b, int c, int d) { return (uint32_t)a | ((uint
 // small enough for the instruction cache -- fully unrolled per-tap-count variants measured slower).
 // Output: 8-bit -> NV/4 packed words, 16-bit -> NV/2 packed words.
 template <int NV, int BPS>
-OTT_DEV void vcolumns(const mid_t *m, int step, const int16_t *cf, int vtaps, int mode, int shift,
+OTT_DEV void vcolumns(const mid_t *m, int step, const int32_t *cf, int vtaps, int mode, int shift,
                       uint32_t (&out)[BPS == 1 ? NV / 4 : NV / 2])
 {
     int a[NV];
@@ -615,10 +677,9 @@ OTT_DEV void vcolumns(const mid_t *m, int step, const int16_t *cf, int vtaps, in
         for (int k = 0; k < NV; ++k) a[k] = init;
         int j = 0;
         for (; j + 2 <= vtaps; j += 2) {                   // x86 tap counts are even (filterAlign 2): no tail in practice
-            const uint32_t c2 = *reinterpret_cast<const uint32_t *>(cf + j);
             OTT_UNROLL
             for (int u = 0; u < 2; ++u) {
-                const int cj = u ? sx_hi(c2) : sx_lo(c2);
+                const int cj = cf[j + u];
                 int t[NV];
                 load_vals<NV>(m + (j + u) * step, t);
                 OTT_UNROLL
@@ -668,41 +729,46 @@ OTT_DEV void vcolumns(const mid_t *m, int step, const int16_t *cf, int vtaps, in
     }
 }
 
-// Fast path of the common case (8-bit, x86-truncating rows, even tap count).  The accumulator is kept shifted left by
-// 16: A = (A & 0xffff0000) + t*c adds floor(t*c / 65536) to the upper half (its low half is the product's remainder,
-// masked away before the next tap), the 16-bit wraparound of paddw is the upper half's natural overflow, and the final
-// (int16(acc) >> 3) is A >> 19.  First tap pair peeled so no accumulator initialisation moves are needed.
+// Fast path of the common case (8-bit, x86-truncating rows, even tap count):
+//     out = clip_u8(int16(init + sum_j floor(t_j*c_j / 65536)) >> 3)            (pmulhw / paddw / psraw / packuswb)
+// The per-tap floor cannot be contracted, so every tap-sample costs one multiply; what can be saved is the bookkeeping.
+// Each product gets a bias that makes its upper half non-negative:  p = t*c + (b << 16),  b = (max|c| >> 1) + 1, so
+// upper16(p) = floor(t*c / 65536) + b  lies in [0, max|c| + 1].  The upper halves of two neighbouring columns' products are
+// packed into one register (one PRMT) and summed over the taps as independent 16-bit lanes of an ordinary 32-bit add -
+// no lane can overflow because taps * (max|c| + 1) < 65536 (checked by the plan, PlaneTables::vbias).  The multiplies no
+// longer depend on the accumulator (no serial chain), there is no masking, and the adds are three-input.  At the end the
+// lanes hold sum + taps*b;  (lane - K) with K = taps*b - init, taken modulo 2^16 and shifted, is the paddw/psraw result.
 template <int NV>
-OTT_DEV void vrow_approx8(const mid_t *m, int step, const int16_t *cf, int vtaps, uint32_t (&out)[NV / 4])
+OTT_DEV void vrow_bias8(const mid_t *m, int step, const int32_t *cf, int vtaps, int bias16, int k16, uint32_t (&out)[NV / 4])
 {
-    const int init = ((64 + 8 * (vtaps - 1)) >> 4) << 16;
-    int a[NV];
-    {
-        const uint32_t c2 = *reinterpret_cast<const uint32_t *>(cf);
-        const int c0 = sx_lo(c2), c1 = sx_hi(c2);
-        int t0[NV], t1[NV];
-        load_vals<NV>(m, t0);
-        load_vals<NV>(m + step, t1);
+    constexpr int NW = NV / 2;
+    uint32_t acc[NW];
+    OTT_UNROLL
+    for (int k = 0; k < NW; ++k) acc[k] = 0;
+    for (int j = 0; j < vtaps; j += 2) {
+        const int c0 = cf[j], c1 = cf[j + 1];
+        uint32_t w0[NW], w1[NW];
+        load_words<NW>(reinterpret_cast<const uint32_t *>(m), w0);
+        load_words<NW>(reinterpret_cast<const uint32_t *>(m + step), w1);
+        m += 2 * step;
         OTT_UNROLL
-        for (int k = 0; k < NV; ++k) a[k] = t0[k] * c0 + init;
-        OTT_UNROLL
-        for (int k = 0; k < NV; ++k) a[k] = (int)((uint32_t)a[k] & 0xffff0000u) + t1[k] * c1;
+        for (int k = 0; k < NW; ++k) {
+            const uint32_t q0 = ott_hi16x2((uint32_t)(sx_lo(w0[k]) * c0 + bias16), (uint32_t)(sx_hi(w0[k]) * c0 + bias16));
+            const uint32_t q1 = ott_hi16x2((uint32_t)(sx_lo(w1[k]) * c1 + bias16), (uint32_t)(sx_hi(w1[k]) * c1 + bias16));
+            acc[k] = acc[k] + q0 + q1;
+        }
     }
-    for (int j = 2; j < vtaps; j += 2) {
-        const uint32_t c2 = *reinterpret_cast<const uint32_t *>(cf + j);
-        const int c0 = sx_lo(c2), c1 = sx_hi(c2);
-        int t0[NV], t1[NV];
-        load_vals<NV>(m + j * step, t0);
-        load_vals<NV>(m + (j + 1) * step, t1);
-        OTT_UNROLL
-        for (int k = 0; k < NV; ++k) a[k] = (int)((uint32_t)a[k] & 0xffff0000u) + t0[k] * c0;
-        OTT_UNROLL
-        for (int k = 0; k < NV; ++k) a[k] = (int)((uint32_t)a[k] & 0xffff0000u) + t1[k] * c1;
+    int lo[NW], hi[NW];
+    OTT_UNROLL
+    for (int k = 0; k < NW; ++k) {
+        lo[k] = (int)(acc[k] * 65536u - (uint32_t)k16) >> 19;      // low lane moved up, corrected, int16 >> 3
+        hi[k] = (int)(acc[k] - (uint32_t)k16) >> 19;               // the low lane's bits fall off the shift
     }
     OTT_UNROLL
-    for (int k = 0; k < NV / 4; ++k)
-        out[k] = pack4(ott_clip(a[4 * k] >> 19, 255), ott_clip(a[4 * k + 1] >> 19, 255), ott_clip(a[4 * k + 2] >> 19, 255),
-                       ott_clip(a[4 * k + 3] >> 19, 255));
+    for (int k = 0; k < NV / 4; ++k) {
+        const uint32_t upper = ott_pack_u8(hi[2 * k + 1], lo[2 * k + 1], 0u);     // samples 4k+3, 4k+2
+        out[k] = ott_pack_u8(hi[2 * k], lo[2 * k], upper);                        // samples 4k+1, 4k
+    }
 }
 
 // NWORDS packed 32-bit words = NWORDS*4/sizeof(S) samples starting at element `elem` of a row of `total` samples
@@ -749,57 +815,63 @@ OTT_DEV void zip16(uint32_t u, uint32_t v, uint32_t &lo, uint32_t &hi)
     hi = (u >> 16) | (v & 0xffff0000u);
 }
 
-template <int CPT, int BPS> struct VRowFast {
-    static OTT_DEV void run(const mid_t *, int, const int16_t *, int, uint32_t (&)[BPS == 1 ? CPT / 4 : CPT / 2]) {}
-};
-template <int CPT> struct VRowFast<CPT, 1> {
-    static OTT_DEV void run(const mid_t *m, int step, const int16_t *cf, int vtaps, uint32_t (&out)[CPT / 4]) { vrow_approx8<CPT>(m, step, cf, vtaps, out); }
-};
-template <int CPT, int BPS>
-OTT_DEV void vrow_fast(const mid_t *m, int step, const int16_t *cf, int vtaps, uint32_t (&out)[BPS == 1 ? CPT / 4 : CPT / 2])
+// 8-bit rows outside the fast path (exact rows at the bottom of a plane, target B, odd tap counts)
+OTT_COLD void vcolumns8_cold(const mid_t *m, int step, const int32_t *cf, int vtaps, int mode, uint32_t (&out)[2])
 {
-    VRowFast<CPT, BPS>::run(m, step, cf, vtaps, out);
+    vcolumns<8, 1>(m, step, cf, vtaps, mode, 0, out);
 }
 
-template <int CPT, int BPS>
+// Thread = 8 adjacent output columns of one output row (one 16-byte shared load per tap); a CTA sweep covers
+// kThreads / (tw / 8) rows.  Chroma tiles run the row function once per plane (a real loop: one copy of the code).
+template <int BPS>
 OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
 {
-    constexpr int NO = BPS == 1 ? CPT / 4 : CPT / 2;            // packed output words per plane
+    constexpr int CPT = 8, NO = BPS == 1 ? CPT / 4 : CPT / 2;   // packed output words per plane
     typedef typename StoreT<BPS>::type S;
     // the geometry lives in shared memory: copy what the loop needs into registers once
     const PlaneTables &T = *g.T;
-    const int tw_log2 = g.tw_log2, tile_w = g.tw, tile_h = g.th, x0 = g.x0, y0 = g.y0, sy0 = g.sy0, sr = g.sr;
-    const int mid_pitch = g.mid_pitch, approx = g.approx_v, shift = g.dst_shift, nplanes = g.nplanes, il = g.dst_interleaved;
+    const int tile_w = g.tw, tile_h = g.th, x0 = g.x0, y0 = g.y0, sy0 = g.sy0;
+    const int mid_pitch = g.mid_pitch, mid_rows = g.mid_rows, approx = g.approx_v, shift = g.dst_shift, nplanes = g.nplanes, il = g.dst_interleaved;
     const int vtaps = T.vtaps, exact_from = T.exact_from, dstW = T.dstW;
+    const int bias16 = T.vbias << 16, k16 = (vtaps * T.vbias - ((64 + 8 * (vtaps - 1)) >> 4)) << 16;
+    const bool fast_ok = BPS == 1 && approx && T.vbias > 0;
     uint8_t *const dst0 = g.dst0, *const dst1 = g.dst1;
     const int dpitch0 = g.dst_pitch0, dpitch1 = g.dst_pitch1;
-    const int lpr_log2 = tw_log2 - (CPT == 8 ? 3 : 2);          // lanes per output row: tw / CPT (tw 64|32, CPT 8|4)
+    const int lpr_log2 = g.tw_log2 - 3;                          // lanes per output row: tw / 8
     const int lx = tid & ((1 << lpr_log2) - 1), ry = tid >> lpr_log2, rows_per_pass = kThreads >> lpr_log2;
     const int x = CPT * lx;
     if (x >= tile_w) return;
-    const mid_t *mid_s = reinterpret_cast<const mid_t *>(smem + g.off_mid);
-    const int16_t *vc_s = reinterpret_cast<const int16_t *>(smem + g.off_vc);
+    const mid_t *mid_s = reinterpret_cast<const mid_t *>(smem + g.off_mid) + x;
+    const int32_t *vc_s = reinterpret_cast<const int32_t *>(smem + g.off_vc);
     const int32_t *vpos_s = reinterpret_cast<const int32_t *>(smem + g.off_vpos);
     const int gx = x0 + x;
     for (int y = ry; y < tile_h; y += rows_per_pass) {
         const int gy = y0 + y;
-        const int r0 = vpos_s[y] - sy0;
-        const int16_t *cf = vc_s + y * vtaps;
+        const int32_t *cf = vc_s + y * vtaps;
         int mode;
         if (BPS == 1) mode = vtaps == 1 ? VM_ONE8 : ((approx && gy < exact_from) ? VM_APPROX8 : VM_EXACT8);
         else mode = vtaps == 1 ? VM_ONE10 : VM_EXACT10;
-        const bool fast = BPS == 1 && mode == VM_APPROX8 && !(vtaps & 1);
-        uint32_t o0[NO];
-        if (fast) vrow_fast<CPT, BPS>(mid_s + r0 * mid_pitch + x, mid_pitch, cf, vtaps, o0);
-        else vcolumns<CPT, BPS>(mid_s + r0 * mid_pitch + x, mid_pitch, cf, vtaps, mode, shift, o0);
+        const bool fast = fast_ok && gy < exact_from;
+        const mid_t *m = mid_s + (vpos_s[y] - sy0) * mid_pitch;
+        uint32_t o0[NO], o1[NO];
+        OTT_NOUNROLL
+        for (int p = 0; p < nplanes; ++p, m += mid_rows * mid_pitch) {
+            uint32_t t[NO];
+            if (BPS == 1) {
+                if (fast) vrow_bias8<CPT>(m, mid_pitch, cf, vtaps, bias16, k16, reinterpret_cast<uint32_t (&)[CPT / 4]>(t));
+                else vcolumns8_cold(m, mid_pitch, cf, vtaps, mode, reinterpret_cast<uint32_t (&)[2]>(t));
+            } else {
+                vcolumns<CPT, BPS>(m, mid_pitch, cf, vtaps, mode, shift, t);
+            }
+            OTT_UNROLL
+            for (int k = 0; k < NO; ++k) {
+                if (p == 0) o0[k] = t[k];
+                else o1[k] = t[k];
+            }
+        }
         if (nplanes == 1) {
             store_words<S, NO>(dst0 + (size_t)gy * dpitch0, gx, o0, dstW);
-            continue;
-        }
-        uint32_t o1[NO];
-        if (fast) vrow_fast<CPT, BPS>(mid_s + (sr + r0) * mid_pitch + x, mid_pitch, cf, vtaps, o1);
-        else vcolumns<CPT, BPS>(mid_s + (sr + r0) * mid_pitch + x, mid_pitch, cf, vtaps, mode, shift, o1);
-        if (il) {
+        } else if (il) {
             uint32_t z[2 * NO];
             OTT_UNROLL
             for (int k = 0; k < NO; ++k) {
@@ -814,18 +886,10 @@ OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
     }
 }
 
-// Columns per thread (8 or 4) come from the plan: the planner picks the width whose (row, column-group) unit count
-// divides most evenly among the compute threads.
+template <int BPS>
 OTT_DEV void phase_vpass(int tid, const TileGeom &g, unsigned char *smem)
 {
-    const bool wide = g.T->cpt == 8;
-    if (g.bps == 1) {
-        if (wide) vpass<8, 1>(tid, g, smem);
-        else vpass<4, 1>(tid, g, smem);
-    } else {
-        if (wide) vpass<8, 2>(tid, g, smem);
-        else vpass<4, 2>(tid, g, smem);
-    }
+    vpass<BPS>(tid, g, smem);
 }
 
 // ------------------------------------------------------------------------------------------------ copy items
@@ -905,14 +969,15 @@ OTT_DEV int item_prepare(const Item &it, const Binding &b, const LadderLaunch &L
     g.x0 = it.x0; g.y0 = it.y0; g.tw = it.tw; g.th = it.th;
     g.sy0 = it.sy0; g.sr = it.sr; g.sx0 = it.sx0; g.nvec = it.nvec;
     g.spw = T.sw_words;
-    g.mid_pitch = T.tw;
+    g.mid_pitch = T.mid_pitch;
+    g.mid_rows = (it.sr + 15) & ~15;
     g.tw_log2 = T.tw == 64 ? 6 : 5;
     g.approx_v = R.approx_v;
     g.off_src = buf * L.src_max;
     const int mid_base = (L.double_buffer ? 2 : 1) * L.src_max;
     g.off_mid = mid_base + mid_buf * L.mid_max;
     g.off_vc = mid_base + L.mid_buffers * L.mid_max + table_slot * L.vc_max;
-    g.off_vpos = g.off_vc + ((T.th * T.vtaps * 2 + 3) & ~3);
+    g.off_vpos = g.off_vc + T.th * T.vtaps * 4;
     g.src_shift = plan.src_fmt == 2 ? 6 : 0;
     g.dst_shift = R.fmt == 2 ? 6 : 0;
     if (luma) {

@@ -108,8 +108,9 @@ TileRegions tile_regions(int nplanes, int staged_planes, int sr_max, int sw_word
 {
     TileRegions r;
     r.src = (size_t)staged_planes * (((size_t)sr_max * sw_words * 4 + 127) & ~(size_t)127);   // planes 128-byte aligned (TMA)
-    r.mid = (size_t)nplanes * (sr_max + 1) * tw * sizeof(mid_t);         // tw is 32 or 64 -> multiple of 16
-    r.vc = (((size_t)th * vtaps * 2 + 3) & ~(size_t)3) + (size_t)th * 4;
+    // rows per plane rounded up to the 16-row groups of the H pass, row pitch tw + 8 (bank-conflict free, 16-byte multiple)
+    r.mid = (size_t)nplanes * ((sr_max + 15) & ~15) * (tw + 8) * sizeof(mid_t);
+    r.vc = (size_t)th * vtaps * 4 + (size_t)th * 4;                  // 32-bit coefficients + row positions
     r.vc = (r.vc + 15) & ~(size_t)15;
     return r;
 }
@@ -117,7 +118,7 @@ TileRegions tile_regions(int nplanes, int staged_planes, int sr_max, int sw_word
 // Builds tables + tiling for one plane kind of one rung.  Host vectors are kept in `keep` only long enough to upload.
 bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int dstH, int bps, int px_bytes, int nplanes, int filter,
                  int target, int exact_from, TileRegions &regions, bool &soft_out, std::vector<int32_t> &hpos_out,
-                 std::vector<int32_t> &vpos_out, std::string &err)
+                 std::vector<int32_t> &vpos_out, std::vector<int32_t> &kbase_out, std::string &err)
 {
     const PolyphaseTable h = plan_table(srcW, dstW, filter, target, false);
     const PolyphaseTable v = plan_table(srcH, dstH, filter, target, true);
@@ -137,23 +138,66 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
             hi[(size_t)x * hq + q] = a;
             lo[(size_t)x * hq + q] = b;
         }
-    // 8-bit fixed-length path: coefficient pairs positioned against the aligned source words, so the kernel needs no
-    // funnel shift and no hi/lo split (tile origins are multiples of 16 samples, so hpos & 3 is the byte offset in every tile)
-    std::vector<uint32_t> pairs;
-    if (bps == 1 && px_bytes == 1) {
-        pairs.assign((size_t)dstW * 2 * (hq + 1), 0);
-        for (int x = 0; x < dstW; ++x) {
-            const int sh = h.pos[x] & 3;
-            for (int b = 0; b < 4 * (hq + 1); ++b) {
-                const int j = b - sh;
-                const uint32_t c = (j >= 0 && j < h.taps) ? (uint16_t)h.coef[(size_t)x * h.taps + j] : 0u;
-                pairs[((size_t)x * (hq + 1) + (b >> 2)) * 2 + ((b >> 1) & 1)] |= c << (16 * (b & 1));
+    // 8-bit path: the H pass is an exact u8 x s15 banded contraction, run on the tensor cores as two int8 MMAs
+    // (m16n8k32, rows = 16 source rows, columns = 8 output columns, K = 32 source bytes per step) with the coefficient
+    // split c = (hi << hsplit) + lo.  Per group of 8 output columns: the K window starts at the 4-byte aligned source
+    // byte hkbase[group]; the B fragments are stored exactly as the 32 lanes hold them (lane = 4*column + k/4).
+    std::vector<uint32_t> frags;
+    std::vector<int32_t> kbase;
+    int hks = 1, hsplit = 7;
+    const bool mma8 = bps == 1 && px_bytes == 1;
+    if (mma8) {
+        const int groups = (dstW + 7) / 8;
+        kbase.resize(groups);
+        for (int gi = 0; gi < groups; ++gi) {
+            int lo_pos = 1 << 30, hi_pos = 0;
+            for (int x = 8 * gi; x < std::min(8 * gi + 8, dstW); ++x) {
+                lo_pos = std::min(lo_pos, h.pos[x]);
+                hi_pos = std::max(hi_pos, h.pos[x] + h.taps);
             }
+            kbase[gi] = lo_pos & ~3;
+            hks = std::max(hks, (hi_pos - kbase[gi] + 31) / 32);
         }
+        long long worst_low = 0;
+        for (int x = 0; x < dstW; ++x) {
+            long long neg = 0;
+            for (int j = 0; j < h.taps; ++j) {
+                const int c = h.coef[(size_t)x * h.taps + j];
+                if (c < -16384 || c > 127 * 128 + 255) hsplit = 8;
+                if (c < 0) neg += c;
+            }
+            worst_low = std::min(worst_low, (255 * neg) >> 7);
+        }
+        if (worst_low < -32768) { err = "horizontal filter overshoots the 16-bit intermediate range"; return false; }
+        frags.assign((size_t)groups * hks * 32 * 4, 0);
+        for (int gi = 0; gi < groups; ++gi)
+            for (int ks = 0; ks < hks; ++ks)
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int x = 8 * gi + (lane >> 2), t = lane & 3;
+                    uint32_t *f = &frags[(((size_t)gi * hks + ks) * 32 + lane) * 4];
+                    if (x >= dstW) continue;
+                    for (int r = 0; r < 2; ++r)
+                        for (int b = 0; b < 4; ++b) {
+                            const int j = kbase[gi] + 32 * ks + 16 * r + 4 * t + b - h.pos[x];
+                            const int c = (j >= 0 && j < h.taps) ? h.coef[(size_t)x * h.taps + j] : 0;
+                            int chi, clo;
+                            if (hsplit == 7) { chi = std::min(c >> 7, 127); clo = c - 128 * chi; }
+                            else { chi = c >> 8; clo = c & 255; }
+                            f[r] |= (uint32_t)(chi & 255) << (8 * b);
+                            f[2 + r] |= (uint32_t)(clo & 255) << (8 * b);
+                        }
+                }
     }
     T.srcW = srcW; T.srcH = srcH; T.dstW = dstW; T.dstH = dstH;
     T.hq = hq;
+    T.hks = hks;
+    T.hsplit = hsplit;
     T.vtaps = v.taps;
+    {
+        int cmax = 0;
+        for (int16_t c : v.coef) cmax = std::max(cmax, std::abs((int)c));
+        T.vbias = (v.taps % 2 == 0 && (long long)v.taps * (cmax + 2) < 65536) ? (cmax >> 1) + 1 : 0;
+    }
     T.exact_from = exact_from;
     // px_bytes = bytes per staged sample position: bps for planar samples, 4 for P010's interleaved (U,V) pairs, which are
     // staged as ONE plane of 32-bit words
@@ -179,9 +223,19 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
         int nvec = 0;
         for (int tx = 0; tx < tiles_x; ++tx) {
             const int x0 = tx * tw, x1 = std::min(x0 + tw, dstW) - 1;
-            const int s0 = h.pos[x0] & ~(spv - 1), s1 = h.pos[x1] + taps4;
-            nvec = std::max(nvec, (s1 - s0 + slack + spv - 1) / spv);
+            int s0 = h.pos[x0] & ~(spv - 1), s1 = h.pos[x1] + taps4 + slack;
+            if (mma8) {                                          // every column group reads its whole K window
+                s0 = 1 << 30;
+                s1 = 0;
+                for (int gi = x0 / 8; gi <= x1 / 8; ++gi) {
+                    s0 = std::min(s0, kbase[gi] & ~15);
+                    s1 = std::max(s1, kbase[gi] + 32 * hks);
+                }
+            }
+            nvec = std::max(nvec, (s1 - s0 + spv - 1) / spv);
         }
+        if (mma8) nvec |= 1;                                     // row pitch = odd multiple of 16 bytes: the fragment loads
+                                                                 // (8 rows x 16 bytes) then hit 32 distinct banks
         return nvec * 4;
     };
     auto model = [&](int tw, int th, int cpt, int sr) {
@@ -211,21 +265,16 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
             const int nty = (dstH + th - 1) / th;
             th = ((dstH + nty - 1) / nty + row_quant - 1) / row_quant * row_quant;
             const int sr = rows_needed(th);
-            // V thread width: 8 columns per thread whenever a row still has 4 lanes (measured: 3-5 % faster than choosing
-            // the width that leaves fewer threads idle in the last round - with no barrier after the V pass an idle
-            // thread simply starts the next tile, while 4-column units pay their per-unit overhead twice as often).
-            // OTTGPU_FORCE_CPT=4 forces the narrow units for experiments.
-            static const int force_cpt = [] { const char *v = std::getenv("OTTGPU_FORCE_CPT"); return v ? std::atoi(v) : 8; }();
-            for (int cpt = 8; cpt >= 4; cpt -= 4) {
+            // V thread width: 8 columns per thread (the kernel carries that unit only; tw is 32 or 64, so a row has 4 or 8 lanes)
+            for (int cpt = 8; cpt >= 8; cpt -= 4) {               // the kernel carries the 8-column unit only
                 if (tw / cpt < 4) continue;                      // at least 4 lanes per row
-                if (cpt != force_cpt && tw / force_cpt >= 4) continue;
                 const double c = model(tw, th, cpt, sr);
                 if (c < sh.cost * (cpt == 4 ? 0.97 : 1.0)) { sh.cost = c; sh.th = th; sh.cpt = cpt; sh.sr_max = sr; sh.fits = sh.soft = true; }
             }
         }
         for (int th = row_quant / 2; !sh.soft && th >= 1; th /= 2) {      // steep filters: shorter than the quantum, still inside the caps
             if (!fits(th, false)) continue;
-            sh.th = th; sh.cpt = 4; sh.sr_max = rows_needed(th); sh.cost = model(tw, th, 4, sh.sr_max); sh.fits = sh.soft = true;
+            sh.th = th; sh.cpt = 8; sh.sr_max = rows_needed(th); sh.cost = model(tw, th, 8, sh.sr_max); sh.fits = sh.soft = true;
         }
         if (!sh.soft) {
             // very long filters (4K -> thumbnail): single-buffered launch, shrink until the tile fits at all
@@ -247,6 +296,7 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
     if (!best.fits) { err = "filter too long for one tile (shared memory)"; return false; }
     soft_out = best.soft;
     T.tw = best.tw;
+    T.mid_pitch = best.tw + 8;
     T.th = best.th;
     T.cpt = best.cpt;
     T.sw_words = best.sw_words;
@@ -258,15 +308,18 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
     regions = tile_regions(nplanes, staged_planes, T.sr_max, T.sw_words, T.tw, T.th, v.taps);
     hpos_out = h.pos;
     vpos_out = v.pos;
+    kbase_out = kbase;
 
+    if (mma8) { hi.clear(); lo.clear(); c16.clear(); }           // the 8-bit path reads only the fragment tables
     T.hpos = upload(plan, h.pos, err);
     T.hc_hi = upload(plan, hi, err);
     T.hc_lo = upload(plan, lo, err);
     T.hc16 = upload(plan, c16, err);
-    T.hc_pair = upload(plan, pairs, err);
+    T.hmma = upload(plan, frags, err);
+    T.hkbase = upload(plan, kbase, err);
     T.vpos = upload(plan, v.pos, err);
     T.vc = upload(plan, v.coef, err);
-    return T.hpos && T.hc_hi && T.hc_lo && T.hc16 && T.hc_pair && T.vpos && T.vc;
+    return T.hpos && T.hc_hi && T.hc_lo && T.hc16 && T.hmma && T.hkbase && T.vpos && T.vc;
 }
 
 void copy_tiling(PlaneTables &T, int w, int h)
@@ -410,9 +463,9 @@ std::shared_ptr<Plan> build_plan(const ottgpu_cfg &cfg, std::string &err)
         const int filt = s == plan->thumb_slot ? OTTGPU_FILTER_BICUBIC : cfg.filter;
         TileRegions rl, rc2;
         bool soft_l = true, soft_c = true;
-        std::vector<int32_t> lh, lv, chh, cv;
-        if (!build_plane(*plan, R.luma, cfg.src_width, cfg.src_height, rc.width, rc.height, bps, bps, 1, filt, cfg.target, luma_exact, rl, soft_l, lh, lv, err)) return nullptr;
-        if (!build_plane(*plan, R.chroma, scw, sch, dcw, dch, bps, cfg.src_fmt == OTTGPU_FMT_P010 ? 4 : bps, 2, filt, cfg.target, chroma_exact, rc2, soft_c, chh, cv, err)) return nullptr;
+        std::vector<int32_t> lh, lv, chh, cv, lk, ck;
+        if (!build_plane(*plan, R.luma, cfg.src_width, cfg.src_height, rc.width, rc.height, bps, bps, 1, filt, cfg.target, luma_exact, rl, soft_l, lh, lv, lk, err)) return nullptr;
+        if (!build_plane(*plan, R.chroma, scw, sch, dcw, dch, bps, cfg.src_fmt == OTTGPU_FMT_P010 ? 4 : bps, 2, filt, cfg.target, chroma_exact, rc2, soft_c, chh, cv, ck, err)) return nullptr;
         // launch class per plane kind: 0 = inside the two-CTAs-per-SM budget, 1 = big tiles, 2 = thumbnail
         const int class_l = is_thumb ? 2 : (soft_l ? 0 : 1), class_c = is_thumb ? 2 : (soft_c ? 0 : 1);
         auto account = [&](int cls, const TileRegions &r) {
@@ -424,7 +477,7 @@ std::shared_ptr<Plan> build_plan(const ottgpu_cfg &cfg, std::string &err)
         account(class_c, rc2);
         // tile geometry resolved here once (the kernel only loads it); items are ordered by the first source row each
         // tile reads, so tiles of different rungs over the same band run together and share the source through L2
-        auto scale_items = [&](const PlaneTables &T, const std::vector<int32_t> &hp, const std::vector<int32_t> &vp, uint8_t kind, int band_scale, int cls) {
+        auto scale_items = [&](const PlaneTables &T, const std::vector<int32_t> &hp, const std::vector<int32_t> &vp, const std::vector<int32_t> &kb, uint8_t kind, int band_scale, int cls) {
             const int pxb = (kind == ITEM_SCALE_CHROMA && cfg.src_fmt == OTTGPU_FMT_P010) ? 4 : bps;
             const int spv = 16 / pxb, slack = 4 / pxb > 0 ? 4 / pxb : 1;
             for (int ty = 0; ty < T.tiles_y; ++ty)
@@ -436,17 +489,25 @@ std::shared_ptr<Plan> build_plan(const ottgpu_cfg &cfg, std::string &err)
                     const int x0 = tx * T.tw, y0 = ty * T.th;
                     const int tw = std::min(T.tw, T.dstW - x0), th = std::min(T.th, T.dstH - y0);
                     const int sy0 = vp[y0], sr = std::min(vp[y0 + th - 1] + T.vtaps, T.srcH) - sy0;
-                    const int sx0 = hp[x0] & ~(spv - 1), last = hp[x0 + tw - 1] + 4 * T.hq;
+                    int sx0 = hp[x0] & ~(spv - 1), last = hp[x0 + tw - 1] + 4 * T.hq + slack;   // + one word of funnel-shift slack
+                    if (!kb.empty()) {                           // 8-bit: the K windows of the tile's column groups
+                        sx0 = 1 << 30;
+                        last = 0;
+                        for (int gi = x0 / 8; gi <= (x0 + tw - 1) / 8; ++gi) {
+                            sx0 = std::min(sx0, kb[gi] & ~15);
+                            last = std::max(last, kb[gi] + 32 * T.hks);
+                        }
+                    }
                     it.x0 = (uint16_t)x0; it.y0 = (uint16_t)y0; it.tw = (uint16_t)tw; it.th = (uint16_t)th;
                     it.sy0 = (uint16_t)sy0; it.sr = (uint16_t)sr; it.sx0 = (uint16_t)sx0;
-                    it.nvec = (uint16_t)((last - sx0 + slack + spv - 1) / spv);       // + one word of funnel-shift slack
+                    it.nvec = (uint16_t)((last - sx0 + spv - 1) / spv);
                     if (cls == 2) plan->thumb_items.push_back(it);
                     else if (cls == 1) plan->big_items.push_back(it);
                     else ordered.push_back({it, band_scale * sy0});
                 }
         };
-        scale_items(R.luma, lh, lv, ITEM_SCALE_LUMA, 1, class_l);
-        scale_items(R.chroma, chh, cv, ITEM_SCALE_CHROMA, 2, class_c);
+        scale_items(R.luma, lh, lv, lk, ITEM_SCALE_LUMA, 1, class_l);
+        scale_items(R.chroma, chh, cv, ck, ITEM_SCALE_CHROMA, 2, class_c);
     }
     std::stable_sort(ordered.begin(), ordered.end(), [](const Sortable &a, const Sortable &b) { return a.band < b.band; });
     for (const Sortable &so : ordered) plan->items.push_back(so.it);

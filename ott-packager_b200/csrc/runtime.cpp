@@ -141,15 +141,18 @@ struct ottgpu_batch {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;                // host frames are uploaded here while the previous step computes
     cudaStream_t readback_stream = nullptr;            // results for host destinations are copied back here
-    Item *d_items = nullptr, *d_big_items = nullptr;   // static per batch: every channel's plan items, chan filled in
+    Item *d_items = nullptr, *d_big_items = nullptr;   // static per batch: every channel's plan items, chan filled in;
+                                                       // 8-bit channels' items first, then the 16-bit ones (one kernel
+                                                       // instance per sample size)
     int n_items = 0, n_big_items = 0, max_thumb_items = 0;
+    int n_items_bps[2] = {0, 0}, n_big_items_bps[2] = {0, 0};
     int src_max[3] = {0, 0, 0}, mid_max[3] = {0, 0, 0}, vc_max[3] = {0, 0, 0};   // launch classes: rung, big-tile rung, thumbnail
     // Descriptors are double-buffered so that an ASYNC submit can be prepared while the previous step still runs.
     struct Set {
         Binding *h_binds = nullptr, *d_binds = nullptr;    // pinned / device
         YadifJob *h_jobs = nullptr, *d_jobs = nullptr;
         Item *h_thumb_items = nullptr, *d_thumb_items = nullptr;
-        int *d_counters = nullptr;                          // tile schedulers of the three launch classes
+        int *d_counters = nullptr;                          // tile schedulers: three launch classes x two sample sizes
         uint8_t *h_thumbs = nullptr;                        // pinned landing area for this step's thumbnails (all channels)
         struct PendingThumb { void *dst; const uint8_t *src; size_t bytes; };
         std::vector<PendingThumb> pending_thumbs;           // pinned -> the caller's malloc'ed buffer, done when the step retires
@@ -509,10 +512,15 @@ static int batch_build(ottgpu_batch *b, ottgpu_channel **channels, int n)
     CK(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&b->readback_stream, cudaStreamNonBlocking));
     std::vector<Item> all, big;
+    for (int bps = 1; bps <= 2; ++bps)
+        for (int i = 0; i < n; ++i) {
+            const Plan &p = *channels[i]->plan;
+            if (p.host_copy.bps != bps) continue;
+            for (Item it : p.items) { it.chan = (uint16_t)i; all.push_back(it); b->n_items_bps[bps - 1]++; }
+            for (Item it : p.big_items) { it.chan = (uint16_t)i; big.push_back(it); b->n_big_items_bps[bps - 1]++; }
+        }
     for (int i = 0; i < n; ++i) {
         const Plan &p = *channels[i]->plan;
-        for (Item it : p.items) { it.chan = (uint16_t)i; all.push_back(it); }
-        for (Item it : p.big_items) { it.chan = (uint16_t)i; big.push_back(it); }
         for (int k = 0; k < 3; ++k) {
             b->src_max[k] = std::max(b->src_max[k], p.src_max[k]);
             b->mid_max[k] = std::max(b->mid_max[k], p.mid_max[k]);
@@ -535,7 +543,7 @@ static int batch_build(ottgpu_batch *b, ottgpu_channel **channels, int n)
         CK(cudaMallocHost((void **)&st.h_binds, n * sizeof(Binding)));
         CK(cudaMalloc((void **)&st.d_jobs, n * sizeof(YadifJob)));
         CK(cudaMallocHost((void **)&st.h_jobs, n * sizeof(YadifJob)));
-        CK(cudaMalloc((void **)&st.d_counters, 3 * sizeof(int)));
+        CK(cudaMalloc((void **)&st.d_counters, 6 * sizeof(int)));
         CK(cudaMallocHost((void **)&st.h_thumbs, std::max<size_t>(b->thumb_stage_bytes, 64)));
         CK(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&st.uploaded, cudaEventDisableTiming));
@@ -677,7 +685,7 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
     cudaStream_t s = b->stream;
     // uploads of this step may overwrite slots last read two steps ago: order the copy stream after that step only
     // (this set's previous use was retired above; the other set = the previous step may still be running)
-    int n_jobs = 0, n_thumb_items = 0, max_w = 0, max_h = 0, live = 0;
+    int n_jobs = 0, n_thumb_items = 0, n_thumb_items16 = 0, max_w = 0, max_h = 0, live = 0;
     bool all_fast = true;
     b->readbacks.clear();
     b->last_launches = b->last_items = 0;
@@ -821,7 +829,12 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
             uint8_t *landing = st.h_thumbs + b->thumb_offset[i];
             b->readbacks.push_back({landing, c->stage[turn][ts], plan.layout[ts].bytes});
             st.pending_thumbs.push_back({host, landing, plan.layout[ts].bytes});
-            for (Item it : plan.thumb_items) { it.chan = (uint16_t)i; st.h_thumb_items[n_thumb_items++] = it; }
+            // 8-bit channels' items fill the list from the front, 16-bit ones from the back
+            for (Item it : plan.thumb_items) {
+                it.chan = (uint16_t)i;
+                if (plan.host_copy.bps == 2) st.h_thumb_items[b->max_thumb_items - ++n_thumb_items16] = it;
+                else st.h_thumb_items[n_thumb_items++] = it;
+            }
         }
 
         if (cfg.deint == OTTGPU_DEINT_BYPASS) {        // nothing is kept across calls
@@ -840,8 +853,11 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
     CK(cudaMemcpyAsync(st.d_binds, st.h_binds, n * sizeof(Binding), cudaMemcpyHostToDevice, ds));
     if (n_jobs) CK(cudaMemcpyAsync(st.d_jobs, st.h_jobs, n * sizeof(YadifJob), cudaMemcpyHostToDevice, ds));
     if (n_thumb_items) CK(cudaMemcpyAsync(st.d_thumb_items, st.h_thumb_items, n_thumb_items * sizeof(Item), cudaMemcpyHostToDevice, ds));
-    const bool any_ladder = (live && (b->n_items || b->n_big_items)) || n_thumb_items;
-    if (any_ladder) CK(cudaMemsetAsync(st.d_counters, 0, 3 * sizeof(int), ds));
+    if (n_thumb_items16)
+        CK(cudaMemcpyAsync(st.d_thumb_items + (b->max_thumb_items - n_thumb_items16), st.h_thumb_items + (b->max_thumb_items - n_thumb_items16),
+                           n_thumb_items16 * sizeof(Item), cudaMemcpyHostToDevice, ds));
+    const bool any_ladder = (live && (b->n_items || b->n_big_items)) || n_thumb_items || n_thumb_items16;
+    if (any_ladder) CK(cudaMemsetAsync(st.d_counters, 0, 6 * sizeof(int), ds));
     CK(cudaEventRecord(st.uploaded, ds));
     CK(cudaStreamWaitEvent(s, st.uploaded, 0));
     if (n_jobs) {
@@ -853,12 +869,13 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
         }
         b->last_launches++;
     }
-    auto make_launch = [&](const Item *items, int count, int which) {
+    auto make_launch = [&](const Item *items, int count, int which, int bps) {
         LadderLaunch L;
         L.items = items;
         L.binds = st.d_binds;
         L.n_items = count;
-        L.counter = st.d_counters + which;
+        L.bps = bps;
+        L.counter = st.d_counters + 2 * which + (bps - 1);
         L.src_max = b->src_max[which];
         L.mid_max = b->mid_max[which];
         L.vc_max = b->vc_max[which];
@@ -867,23 +884,34 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
     };
     if (live && b->n_items) {
         if (b->timing) CK(cudaEventRecord(st.k0, s));
-        CK(launch_ladder(make_launch(b->d_items, b->n_items, 0), s));
+        for (int k = 0, at = 0; k < 2; at += b->n_items_bps[k], ++k)
+            if (b->n_items_bps[k]) {
+                CK(launch_ladder(make_launch(b->d_items + at, b->n_items_bps[k], 0, k + 1), s));
+                b->last_launches++;
+            }
         if (b->timing) {
             CK(cudaEventRecord(st.k1, s));
             st.timed = true;
         }
-        b->last_launches++;
         b->last_items += b->n_items;
     }
     if (live && b->n_big_items) {
-        CK(launch_ladder(make_launch(b->d_big_items, b->n_big_items, 1), s));
-        b->last_launches++;
+        for (int k = 0, at = 0; k < 2; at += b->n_big_items_bps[k], ++k)
+            if (b->n_big_items_bps[k]) {
+                CK(launch_ladder(make_launch(b->d_big_items + at, b->n_big_items_bps[k], 1, k + 1), s));
+                b->last_launches++;
+            }
         b->last_items += b->n_big_items;
     }
     if (n_thumb_items) {
-        CK(launch_ladder(make_launch(st.d_thumb_items, n_thumb_items, 2), s));
+        CK(launch_ladder(make_launch(st.d_thumb_items, n_thumb_items, 2, 1), s));
         b->last_launches++;
         b->last_items += n_thumb_items;
+    }
+    if (n_thumb_items16) {
+        CK(launch_ladder(make_launch(st.d_thumb_items + (b->max_thumb_items - n_thumb_items16), n_thumb_items16, 2, 2), s));
+        b->last_launches++;
+        b->last_items += n_thumb_items16;
     }
     CK(cudaEventRecord(st.done, s));
     if (!b->readbacks.empty()) {

@@ -45,15 +45,21 @@ cudaError_t launch_ladder(LadderLaunch L, cudaStream_t)
         // every byte the phases touch must lie inside the launch's dynamic shared memory
         if ((size_t)g.off_vpos + (size_t)g.th * 4 > smem_bytes) return cudaErrorInvalidValue;
         if ((size_t)(g.staged_planes - 1) * g.plane_stride + (size_t)g.sr * g.spw * 4 > (size_t)L.src_max) return cudaErrorInvalidValue;
-        if ((size_t)g.nplanes * (g.sr + 1) * g.mid_pitch * 2 > (size_t)L.mid_max) return cudaErrorInvalidValue;
+        if ((size_t)g.nplanes * g.mid_rows * g.mid_pitch * 2 > (size_t)L.mid_max) return cudaErrorInvalidValue;
         if ((size_t)g.off_mid + L.mid_max > (size_t)g.off_vc) return cudaErrorInvalidValue;
         if (g.nvec * 4 > g.spw) return cudaErrorInvalidValue;
         std::fill(smem.begin(), smem.end(), 0xA5);       // poison: stale-data reads show up as mismatches
         for (int lane = 0; lane < 32; ++lane) phase_tables(lane, 32, g, sm);
         for (int tid = 0; tid < kThreads; ++tid) phase_stage(tid, g, sm);
         for (int tid = 0; tid < kThreads; ++tid) phase_fixup16(tid, g, sm);
-        for (int tid = 0; tid < kThreads; ++tid) phase_hpass(tid, g, sm);
-        for (int tid = 0; tid < kThreads; ++tid) phase_vpass(tid, g, sm);
+        if (g.bps != L.bps) return cudaErrorInvalidValue;   // the launcher partitions items by sample size
+        if (L.bps == 2) {
+            for (int tid = 0; tid < kThreads; ++tid) phase_hpass<2>(tid, g, sm);
+            for (int tid = 0; tid < kThreads; ++tid) phase_vpass<2>(tid, g, sm);
+        } else {
+            for (int tid = 0; tid < kThreads; ++tid) phase_hpass<1>(tid, g, sm);
+            for (int tid = 0; tid < kThreads; ++tid) phase_vpass<1>(tid, g, sm);
+        }
     }
     return cudaSuccess;
 }
