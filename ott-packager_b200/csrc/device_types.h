@@ -43,7 +43,7 @@ struct PlaneTables {
                              //   the source bytes hkbase[group] + 32*kstep + k
     const int32_t *hkbase;   // [ceil(dstW/8)] first source byte of the group's K window (multiple of 4)
     const int32_t *vpos;     // [dstH]   first source row of each output row
-    const int16_t *vc;       // [dstH][vtaps] 12-bit coefficients
+    const int32_t *vc;       // [dstH][vtaps] 12-bit coefficients, widened to 32 bits (the V pass multiplies them as they are)
     int srcW, srcH, dstW, dstH;
     int hq;                  // horizontal taps / 4 (tables zero-padded to a multiple of four taps)
     int hks;                 // 8-bit path: K steps (32 source bytes each) of the H-pass contraction
@@ -90,8 +90,14 @@ struct Binding {
     int dst_pitch[kMaxRungSlots][3];
 };
 
-// One work item = one CTA-sized piece of work, with its geometry resolved on the host when the plan is built.
+// One work item = one CTA-sized piece of work.  Everything that does not depend on where the channel's frame lives is
+// resolved on the host when the plan is built, so that the kernel's producer warp only copies this block into shared
+// memory and patches the frame / surface pointers of the step in: the producer's per-tile latency bounds the tile rate
+// of a CTA (measured: with the geometry derived on the device a tile cost ~3 us whatever its size).
 struct Item {
+    const PlaneTables *T;    // the tables of this plane kind of this rung (device pointer into the plan)
+    const int32_t *vc_src;   // this tile's slice of the V coefficient table ...
+    const int32_t *vpos_src; // ... and of the row positions
     uint16_t chan;           // index into the launch's Binding array
     uint8_t slot;            // rung slot
     uint8_t kind;            // ItemKind
@@ -99,8 +105,40 @@ struct Item {
     uint16_t tw, th;         // output tile size (copy items: th = rows)
     uint16_t sy0, sr;        // source rows [sy0, sy0+sr) the tile reads
     uint16_t sx0, nvec;      // first staged source sample (16-byte aligned) and 16-byte vectors per staged row
-    uint32_t reserved;
+    uint16_t spw;            // smem pitch of the staged source, 32-bit words
+    uint16_t mid_pitch;      // smem pitch (mid_t elements) of the H-pass result
+    uint16_t mid_rows;       // rows per plane in the H-pass result (sr rounded up to the H pass's 16-row groups)
+    uint16_t tma_x;          // TMA box x coordinate in 32-bit elements
+    int32_t plane_stride;    // bytes between the two staged chroma planes inside a source buffer (128-byte multiple)
+    int32_t box_bytes;       // bytes one TMA box delivers
+    uint16_t vc_bytes;       // V coefficient slice as a bulk copy (16-byte multiple), 0: copied by the producer's lanes
+    uint16_t vpos_bytes;     // row position slice as a bulk copy
+    uint16_t vpos_off;       // offset of the row positions inside the table region (= T->th * vtaps * 4)
+    uint8_t bps;             // source/destination bytes per sample
+    uint8_t nplanes;         // 1 luma, 2 chroma pair
+    uint8_t tw_log2;         // T->tw is 32 or 64
+    uint8_t approx_v;
+    uint8_t src_interleaved; // chroma samples interleaved in the source (P010): staged as ONE plane of (U,V) words
+    uint8_t dst_interleaved; // NV12 / P010 chroma writer
+    uint8_t staged_planes;   // planes in the staged window (1 for luma and for interleaved chroma, else 2)
+    uint8_t px_bytes;        // bytes per staged sample position: 1 (8-bit), 2 (16-bit), 4 (interleaved 16-bit pair)
+    uint8_t src_shift;       // 6 for P010 (MSB aligned), else 0
+    uint8_t dst_shift;       // 6 for P010
+    uint8_t tma_ok;          // the source window fits one 2-D TMA box per plane
+    uint8_t thumb;           // item of the thumbnail slot: runs only on the steps the thumbnail is due
+    uint16_t pad1;
+    // 8-bit H pass: the (column group, 16-row group) pairs dealt to each compute warp as one contiguous run:
+    // bits 0-7 first column group, 8-19 first row group, 20-31 number of pairs
+    uint32_t hrun[kThreads / 32];
+    // copies of the table fields the hot loops need, so that no thread waits on a chain of global loads through T
+    // at the start of a tile (measured: ~1.1 us of fixed cost per tile per CTA went there)
+    const uint32_t *hmma;    // 8-bit: B fragments of the tile's first column group
+    uint16_t kw[8];          // 8-bit: K-window base of each of the tile's column groups, in 32-bit words from sx0
+    uint16_t vtaps, vbias, exact_from, dstW;
+    uint8_t hks, hsplit, hq, pad2;
+    uint32_t pad3[3];
 };
+static_assert(sizeof(Item) == 176, "Item is copied into shared memory as eleven 16-byte vectors");
 
 // Launch-wide constants of the persistent ladder kernel.
 struct LadderLaunch {
@@ -109,6 +147,7 @@ struct LadderLaunch {
     int n_items;
     int bps;                 // bytes per sample of every item's channel (1 | 2): selects the kernel instance
     int *counter;            // dynamic tile scheduler (zeroed before every launch)
+    int claim;               // work items a CTA claims per atomic on the counter (1, 2 or 4; set by the launcher)
     int src_max;             // bytes of ONE staged-source buffer (max over the launch's tiles, multiple of 16)
     int mid_max;             // bytes of the H-pass result region (multiple of 16)
     int vc_max;              // bytes of the V coefficient + vpos region

@@ -8,6 +8,7 @@
 //   convert_kernel: decode-side 4:2:2 / 10-bit -> packed 8-bit 4:2:0 converter.
 // The per-thread work lives in ladder_core.cuh / yadif_core.cuh.
 #include "kernels.h"
+#include <cstdlib>
 #include "ladder_core.cuh"
 #include "yadif_core.cuh"
 #include "convert_core.cuh"
@@ -49,8 +50,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         : "memory");
 }
 
-// producer-side wait: the producer is usually far ahead, so it backs off between probes instead of competing with the
-// compute warps of its scheduler for issue slots
+// producer-side wait: try_wait suspends the warp in hardware up to the time hint, so a waiting producer takes no issue
+// slots from the compute warps and wakes as soon as the phase completes (a nanosleep poll added up to 0.25 us per wait)
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity)
 {
     for (;;) {
@@ -58,15 +59,26 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity
         asm volatile(
             "{\n"
             ".reg .pred P1;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
             "selp.u32 %0, 1, 0, P1;\n"
             "}"
             : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(4000u)
             : "memory");
         if (ok) return;
-        __nanosleep(256);
     }
+}
+// adds to the pending transaction bytes of the current phase without arriving
+__device__ __forceinline__ void mbar_add_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared (16-byte aligned addresses and size), completion on `bar`
+__device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
@@ -90,7 +102,7 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t ready[kGeomSlots], gfree[kGeomSlots], empty[2];
-    __shared__ TileGeom s_geom[kGeomSlots];
+    __shared__ __align__(16) TileGeom s_geom[kGeomSlots];
     __shared__ int s_idx[kGeomSlots], s_what[kGeomSlots], s_buf[kGeomSlots];
     const int tid = threadIdx.x;
     const int nbuf = L.double_buffer ? 2 : 1;
@@ -106,32 +118,71 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
         const int lane = tid - kThreads;
         uint32_t pg = (1u << kGeomSlots) - 1, pe = 3;    // parity bits; a fresh mbarrier passes a wait on parity 1
         int buf = 0, mid = 0;
-        int idx = 0;
-        if (lane == 0) idx = atomicAdd(L.counter, 1);
+        // Work items are claimed kClaim at a time: one atomic on the launch-wide counter per tile (296 CTAs on one address)
+        // bounded the whole launch at ~5 ns per tile.  The next claim is issued while the current one is being worked
+        // off, so its latency stays hidden.  Consecutive items share source rows, so a CTA's run of tiles also helps L2.
+        const int kClaim = L.claim;
+        int cur = 0, cur_end = 0, nxt = 0;                   // lane 0: current run [cur, cur_end), start of the prefetched run
+        if (lane == 0) {
+            cur = atomicAdd(L.counter, kClaim);
+            cur_end = cur + kClaim;
+            nxt = atomicAdd(L.counter, kClaim);
+        }
         for (int slot = 0;; slot = (slot + 1) & (kGeomSlots - 1)) {
+            int idx = 0;
+            if (lane == 0) {
+                if (cur == cur_end) {
+                    cur = nxt;
+                    cur_end = cur + kClaim;
+                    if (cur < L.n_items) nxt = atomicAdd(L.counter, kClaim);
+                }
+                idx = cur++;
+            }
             idx = __shfl_sync(0xffffffffu, idx, 0);
-            int idx_next = 0;
-            if (lane == 0 && idx < L.n_items) idx_next = atomicAdd(L.counter, 1);     // in flight while this tile is set up
             mbar_wait_backoff(&gfree[slot], (pg >> slot) & 1);
             pg ^= 1u << slot;
+            if (idx >= L.n_items) {
+                if (lane == 0) {
+                    s_idx[slot] = idx;
+                    mbar_arrive(&ready[slot]);
+                }
+                break;
+            }
+            // the item's static block: eight lanes, one 16-byte vector each, straight into the descriptor slot
+            TileGeom &g = s_geom[slot];
+            if (lane < (int)(sizeof(Item) / 16))
+                reinterpret_cast<uint4 *>(&g)[lane] = __ldg(reinterpret_cast<const uint4 *>(L.items + idx) + lane);
+            __syncwarp();
+            int what = 0;
             if (lane == 0) {
                 s_idx[slot] = idx;
                 s_buf[slot] = buf;
-                s_what[slot] = idx < L.n_items ? item_prepare(L.items[idx], L.binds[L.items[idx].chan], L, buf, mid, slot, s_geom[slot]) : 0;
+                what = item_prepare(L.binds[g.chan], L, buf, mid, slot, g);     // frame / surface pointers of this step
+                s_what[slot] = what;
             }
+            what = __shfl_sync(0xffffffffu, what, 0);
             __syncwarp();
-            if (idx >= L.n_items) {
-                if (lane == 0) mbar_arrive(&ready[slot]);
-                break;
-            }
-            const TileGeom &g = s_geom[slot];
-            if (s_what[slot] == 1) {
-                phase_tables(lane, 32, g, smem);               // V coefficients / row positions into this slot's table region
-                __syncwarp();
+            if (what == 1) {
+                if (g.vc_bytes) {                              // V coefficients / row positions: two bulk copies
+                    if (lane == 0) {
+                        fence_proxy_async();                   // the table region was last read through the generic proxy
+                        mbar_add_tx(&ready[slot], (uint32_t)g.vc_bytes + g.vpos_bytes);
+                        bulk_copy_g2s(smem + g.off_vc, g.vc_src, g.vc_bytes, &ready[slot]);
+                        bulk_copy_g2s(smem + g.off_vpos, g.vpos_src, g.vpos_bytes, &ready[slot]);
+                    }
+                } else {
+                    phase_tables(lane, 32, g, smem);
+                    __syncwarp();
+                }
                 mbar_wait_backoff(&empty[buf], (pe >> buf) & 1);   // the tile that last used this source buffer is done
                 pe ^= 1u << buf;
+#if defined(OTTGPU_DEBUG_NO_TMA)
+                if (false) {
+                    if (lane == 0) {
+#else
                 if (g.bulk_ok) {
                     if (lane == 0) {
+#endif
                         fence_proxy_async();                   // the buffer was last read through the generic proxy
                         mbar_expect_tx(&ready[slot], (uint32_t)(g.staged_planes * g.box_bytes));
                         unsigned char *dst = smem + g.off_src;
@@ -146,7 +197,6 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
             } else if (lane == 0) {
                 mbar_arrive(&ready[slot]);                     // copy item / skipped item: no source buffer involved
             }
-            idx = idx_next;
         }
         return;
     }
@@ -161,9 +211,13 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
         const int what = s_what[slot];
         const TileGeom &g = s_geom[slot];
         if (what == 2) {
-            item_copy(tid, L.items[idx], L.binds[L.items[idx].chan]);
+            item_copy(tid, g, L.binds[g.chan]);
         } else if (what == 1) {
+#if defined(OTTGPU_DEBUG_NO_TMA)
+            if (false) {
+#else
             if (!g.bulk_ok) {                      // unaligned planes: staged through registers by the compute warps
+#endif
                 phase_stage(tid, g, smem);
                 compute_sync();
             }
@@ -171,10 +225,14 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
                 phase_fixup16(tid, g, smem);
                 compute_sync();
             }
+#if !defined(OTTGPU_DEBUG_SKIP_H)
             phase_hpass<BPS>(tid, g, smem);
+#endif
             compute_sync();                        // H-pass result and V tables complete; the source buffer is free
             mbar_arrive(&empty[s_buf[slot]]);
+#if !defined(OTTGPU_DEBUG_SKIP_V)
             phase_vpass<BPS>(tid, g, smem);
+#endif
             // one intermediate region: everybody must be done reading it before the next tile's H pass writes it.  Two
             // regions: the next H pass writes the other one, and the region it will overwrite after that was last read
             // before the barrier above - no wait here, a warp that is done starts the next tile at once
@@ -219,9 +277,11 @@ cudaError_t configure_kernels()
 size_t ladder_smem_bytes(int src_max, int mid_max, int vc_max, int *double_buffer, int *mid_buffers)
 {
     const size_t tables = (size_t)kGeomSlots * vc_max;     // one table region per descriptor slot
-    const size_t two_mid = (size_t)src_max + 2 * (size_t)mid_max + tables + 16, one = (size_t)src_max + mid_max + tables + 16;
+    static const int want_two_src = [] { const char *v = std::getenv("OTTGPU_DOUBLE_SRC"); return v ? std::atoi(v) : 0; }();
+    const size_t nsrc = want_two_src && 2 * (size_t)src_max + 2 * (size_t)mid_max + tables + 16 <= kMaxTileSmem ? 2 : 1;
+    const size_t two_mid = nsrc * src_max + 2 * (size_t)mid_max + tables + 16, one = (size_t)src_max + mid_max + tables + 16;
     const int mb = two_mid <= kMaxTileSmem ? 2 : 1;
-    if (double_buffer) *double_buffer = 0;
+    if (double_buffer) *double_buffer = mb == 2 && nsrc == 2;
     if (mid_buffers) *mid_buffers = mb;
     return mb == 2 ? two_mid : one;
 }
@@ -255,6 +315,7 @@ cudaError_t launch_ladder(LadderLaunch L, cudaStream_t s)
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorInvalidValue;
     const int grid = L.n_items < sms * per_sm ? L.n_items : sms * per_sm;     // one wave of resident CTAs
+    L.claim = L.n_items / (grid * 4) >= 4 ? 4 : (L.n_items / (grid * 4) >= 2 ? 2 : 1);   // small launches keep every CTA busy
     if (L.bps == 2) ladder_kernel<2><<<grid, kLadderThreads, smem_bytes, s>>>(L);
     else ladder_kernel<1><<<grid, kLadderThreads, smem_bytes, s>>>(L);
     return cudaGetLastError();

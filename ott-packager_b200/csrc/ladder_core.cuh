@@ -175,37 +175,28 @@ OTT_DEV int ott_min(int a, int b) { return a < b ? a : b; }
 OTT_DEV int ott_max(int a, int b) { return a > b ? a : b; }
 OTT_DEV int ott_clip(int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); }
 
-// Everything one tile needs, resolved once per CTA (thread-uniform scalars; no shared-memory pointers are kept in
-// here so that the compiler keeps every shared access in the shared address space).
-struct TileGeom {
-    const PlaneTables *T;
-    int bps;                 // source/destination bytes per sample
-    int nplanes;             // 1 luma, 2 chroma pair
-    int x0, y0, tw, th;      // output tile
-    int sy0, sr;             // source rows [sy0, sy0+sr)
-    int sx0;                 // first staged source sample (multiple of 16 bytes)
-    int nvec;                // 16-byte vectors staged per row
-    int spw;                 // smem pitch of the staged source, 32-bit words (multiple of 4)
-    int mid_pitch;           // smem pitch (mid_t elements) of the H-pass result: tw + 8
-    int mid_rows;            // rows per plane in the H-pass result (sr rounded up to the H pass's 16-row groups)
-    int tw_log2;             // T->tw is 32 or 64
-    int approx_v;
+// byte / halfword interleave of two packed streams (NV12 / P010 chroma writers)
+OTT_DEV void zip8(uint32_t u, uint32_t v, uint32_t &lo, uint32_t &hi)
+{
+    lo = ott_prmt(u, v, 0x5140);      // u0 v0 u1 v1
+    hi = ott_prmt(u, v, 0x7362);      // u2 v2 u3 v3
+}
+OTT_DEV void zip16(uint32_t u, uint32_t v, uint32_t &lo, uint32_t &hi)
+{
+    lo = (u & 0xffffu) | (v << 16);
+    hi = (u >> 16) | (v & 0xffff0000u);
+}
+
+// Everything one tile needs: the item's static block plus what depends on the step (thread-uniform scalars; no
+// shared-memory pointers are kept in here so that the compiler keeps every shared access in the shared address space).
+struct alignas(16) TileGeom : Item {
     int off_src, off_mid, off_vc, off_vpos;   // byte offsets of the regions inside the CTA's shared memory
-    int plane_stride;        // bytes between the two staged chroma planes inside a source buffer (128-byte multiple)
     int bulk_ok;             // the tile's source window is fetched by the TMA engine (one 2-D box per plane)
-    int box_bytes;           // bytes one TMA box delivers
     const unsigned char *tmap0, *tmap1;   // tensor maps of the plane(s)
     const uint8_t *src0, *src1;      // plane bases (chroma: U,V or the interleaved UV plane twice)
     int src_pitch0, src_pitch1;      // bytes
-    int src_interleaved;     // chroma samples interleaved in the source (P010): staged as ONE plane of (U,V) words
-    int staged_planes;       // planes in the staged window (1 for luma and for interleaved chroma, else 2)
-    int px_bytes;            // bytes per staged sample position: 1 (8-bit), 2 (16-bit), 4 (interleaved 16-bit pair)
-    int tma_x;               // TMA box x coordinate in 32-bit elements
-    int src_shift;           // 6 for P010 (MSB aligned), else 0
     uint8_t *dst0, *dst1;
     int dst_pitch0, dst_pitch1;
-    int dst_interleaved;     // NV12 / P010 chroma writer
-    int dst_shift;           // 6 for P010
 };
 
 // ------------------------------------------------------------------------------------------------ phase 0: tables
@@ -213,26 +204,11 @@ struct TileGeom {
 // (the producer warp in the kernel: the tables are in place before the compute warps are released).
 OTT_DEV void phase_tables(int tid, int nthreads, const TileGeom &g, unsigned char *smem)
 {
-    const PlaneTables &T = *g.T;
-    int32_t *vc_s = reinterpret_cast<int32_t *>(smem + g.off_vc);     // widened to 32 bits: the V pass multiplies them as they are
+    int32_t *vc_s = reinterpret_cast<int32_t *>(smem + g.off_vc);
     int32_t *vpos_s = reinterpret_cast<int32_t *>(smem + g.off_vpos);
-    const int n = g.th * T.vtaps, th = g.th;
-    const int16_t *vc = T.vc + g.y0 * T.vtaps;
-    const int32_t *vp = T.vpos + g.y0;
-    if (((n | (g.y0 * T.vtaps)) & 1) == 0) {               // pairs of coefficients per load
-        const uint32_t *s2 = reinterpret_cast<const uint32_t *>(vc);
-        uint2 *d2 = reinterpret_cast<uint2 *>(vc_s);
-        for (int i = tid; i < (n >> 1); i += nthreads) {
-            const uint32_t c2 = ott_ldg(s2 + i);
-            uint2 q;
-            q.x = (uint32_t)(int)(int16_t)(c2 & 0xffffu);
-            q.y = (uint32_t)((int)c2 >> 16);
-            d2[i] = q;
-        }
-    } else {
-        for (int i = tid; i < n; i += nthreads) vc_s[i] = ott_ldg(vc + i);
-    }
-    for (int i = tid; i < th; i += nthreads) vpos_s[i] = ott_ldg(vp + i);
+    const int n = g.th * g.vtaps, th = g.th;
+    for (int i = tid; i < n; i += nthreads) vc_s[i] = ott_ldg(g.vc_src + i);
+    for (int i = tid; i < th; i += nthreads) vpos_s[i] = ott_ldg(g.vpos_src + i);
 }
 
 // ------------------------------------------------------------------------------------------------ phase 1: staging
@@ -339,28 +315,22 @@ inline void hmma_lane(const uint32_t *row_g, const uint32_t *row_g8, const uint3
 template <int KS, int SPLIT>
 OTT_DEV void hpass8_mma(int tid, const TileGeom &g, unsigned char *smem)
 {
-    const PlaneTables &T = *g.T;
-    constexpr int kWarps = kThreads / 32;
     const int warp = tid >> 5, lane = tid & 31;
-    const int ks_n = KS ? KS : T.hks;
-    const int groups = (g.tw + 7) >> 3;                         // 8-column groups of this tile
+    const int ks_n = KS ? KS : g.hks;
     const int mt_plane = (g.sr + 15) >> 4, mt_total = g.nplanes * mt_plane;
     // (column group, 16-row group) pairs, column-group major, dealt out in contiguous runs so that a warp re-reads its
-    // B fragments at most twice
-    const int total = groups * mt_total, per = (total + kWarps - 1) / kWarps;
-    int f = warp * per;
-    const int fend = ott_min(f + per, total);
-    if (f >= fend) return;
+    // B fragments at most twice; the runs were cut by the producer (item_hruns)
+    const uint32_t hr = g.hrun[warp];
+    int left = (int)(hr >> 20);
+    if (left == 0) return;
     const int spw = g.spw, pitch = g.mid_pitch;
     const int lane_src = (lane >> 2) * spw + (lane & 3), lane_mid = (lane >> 2) * pitch + 2 * (lane & 3);
     const uint32_t *src_s = reinterpret_cast<const uint32_t *>(smem + g.off_src) + lane_src;
     mid_t *mid_s = reinterpret_cast<mid_t *>(smem + g.off_mid) + lane_mid;
-    int nt = f / mt_total, mt = f - nt * mt_total;
-    int left = fend - f;
+    int nt = (int)(hr & 255u), mt = (int)((hr >> 8) & 4095u);
     while (left > 0) {
-        const int gnt = (g.x0 >> 3) + nt;
-        const int kw = (ott_ldg(T.hkbase + gnt) - g.sx0) >> 2;    // window base as a word offset into the staged rows
-        const uint32_t *frag = T.hmma + (size_t)gnt * ks_n * 128;
+        const int kw = g.kw[nt];                                  // window base as a word offset into the staged rows
+        const uint32_t *frag = g.hmma + (size_t)nt * ks_n * 128;
 #if !defined(OTTGPU_EMULATE)
         uint4 B[KS ? KS : 1];
         if (KS) {
@@ -570,10 +540,10 @@ OTT_DEV void hpass16_any(int tid, const TileGeom &g, unsigned char *smem)
 template <int BPS>
 OTT_DEV void phase_hpass(int tid, const TileGeom &g, unsigned char *smem)
 {
-    const int hq = g.T->hq;
+    const int hq = g.hq;
     if (BPS == 1) {
-        const int hks = g.T->hks;
-        if (g.T->hsplit != 7) hpass8_mma<0, 8>(tid, g, smem);       // a coefficient beyond 127*128+255 (border-folded taps): rare
+        const int hks = g.hks;
+        if (g.hsplit != 7) hpass8_mma<0, 8>(tid, g, smem);       // a coefficient beyond 127*128+255 (border-folded taps): rare
         else if (hks == 1) hpass8_mma<1, 7>(tid, g, smem);
         else if (hks == 2) hpass8_mma<2, 7>(tid, g, smem);
         else hpass8_mma<0, 7>(tid, g, smem);
@@ -745,12 +715,16 @@ OTT_DEV void vrow_bias8(const mid_t *m, int step, const int32_t *cf, int vtaps, 
     uint32_t acc[NW];
     OTT_UNROLL
     for (int k = 0; k < NW; ++k) acc[k] = 0;
-    for (int j = 0; j < vtaps; j += 2) {
-        const int c0 = cf[j], c1 = cf[j + 1];
+    // two taps per trip (the tap count is even on this path), plain pointer bumps: the loop stays small
+    const uint32_t *m0 = reinterpret_cast<const uint32_t *>(m), *m1 = reinterpret_cast<const uint32_t *>(m + step);
+    const uint2 *c2 = reinterpret_cast<const uint2 *>(cf);       // rows of an even number of 32-bit coefficients: 8-byte aligned
+    OTT_NOUNROLL
+    for (int j = vtaps; j > 0; j -= 2, m0 += step, m1 += step, ++c2) {     // step elements = two rows of step/2 words
+        const uint2 cc = *c2;
+        const int c0 = (int)cc.x, c1 = (int)cc.y;
         uint32_t w0[NW], w1[NW];
-        load_words<NW>(reinterpret_cast<const uint32_t *>(m), w0);
-        load_words<NW>(reinterpret_cast<const uint32_t *>(m + step), w1);
-        m += 2 * step;
+        load_words<NW>(m0, w0);
+        load_words<NW>(m1, w1);
         OTT_UNROLL
         for (int k = 0; k < NW; ++k) {
             const uint32_t q0 = ott_hi16x2((uint32_t)(sx_lo(w0[k]) * c0 + bias16), (uint32_t)(sx_hi(w0[k]) * c0 + bias16));
@@ -803,38 +777,50 @@ OTT_DEV void store_words(uint8_t *row, int elem, const uint32_t (&w)[NWORDS], in
     }
 }
 
-// byte / halfword interleave of two packed streams (NV12 / P010 chroma writers)
-OTT_DEV void zip8(uint32_t u, uint32_t v, uint32_t &lo, uint32_t &hi)
-{
-    lo = (u & 0xffu) | ((v & 0xffu) << 8) | ((u & 0xff00u) << 8) | ((v & 0xff00u) << 16);
-    hi = ((u >> 16) & 0xffu) | (((v >> 16) & 0xffu) << 8) | ((u >> 24) << 16) | ((v >> 24) << 24);
-}
-OTT_DEV void zip16(uint32_t u, uint32_t v, uint32_t &lo, uint32_t &hi)
-{
-    lo = (u & 0xffffu) | (v << 16);
-    hi = (u >> 16) | (v & 0xffff0000u);
-}
-
-// 8-bit rows outside the fast path (exact rows at the bottom of a plane, target B, odd tap counts)
-OTT_COLD void vcolumns8_cold(const mid_t *m, int step, const int32_t *cf, int vtaps, int mode, uint32_t (&out)[2])
-{
-    vcolumns<8, 1>(m, step, cf, vtaps, mode, 0, out);
-}
-
 // Thread = 8 adjacent output columns of one output row (one 16-byte shared load per tap); a CTA sweep covers
 // kThreads / (tw / 8) rows.  Chroma tiles run the row function once per plane (a real loop: one copy of the code).
+// The rows of the fast path (8-bit target A, all but the bottom rows of a plane) come first in a loop of their own, so
+// that loop carries no per-row mode decision; what is left (exact rows, target B, 16-bit) goes through vcolumns.
+template <int BPS>
+OTT_DEV void vpass_store(uint8_t *dst0, uint8_t *dst1, int dpitch0, int dpitch1, int gy, int gx, int dstW, int nplanes, int il,
+                         bool vec_ok, const uint32_t (&o0)[BPS == 1 ? 2 : 4], const uint32_t (&o1)[BPS == 1 ? 2 : 4])
+{
+    constexpr int NO = BPS == 1 ? 2 : 4;
+    typedef typename StoreT<BPS>::type S;
+    if (nplanes == 1) {
+        if (BPS == 1 && vec_ok) {
+            uint2 q; q.x = o0[0]; q.y = o0[1];
+            *reinterpret_cast<uint2 *>(dst0 + (size_t)gy * dpitch0 + gx) = q;
+        } else {
+            store_words<S, NO>(dst0 + (size_t)gy * dpitch0, gx, o0, dstW);
+        }
+    } else if (il) {
+        uint32_t z[2 * NO];
+        OTT_UNROLL
+        for (int k = 0; k < NO; ++k) {
+            if (BPS == 1) zip8(o0[k], o1[k], z[2 * k], z[2 * k + 1]);
+            else zip16(o0[k], o1[k], z[2 * k], z[2 * k + 1]);
+        }
+        if (BPS == 1 && vec_ok) {
+            uint4 q; q.x = z[0]; q.y = z[1]; q.z = z[2]; q.w = z[3];
+            *reinterpret_cast<uint4 *>(dst0 + (size_t)gy * dpitch0 + 2 * gx) = q;
+        } else {
+            store_words<S, 2 * NO>(dst0 + (size_t)gy * dpitch0, 2 * gx, z, 2 * dstW);
+        }
+    } else {
+        store_words<S, NO>(dst0 + (size_t)gy * dpitch0, gx, o0, dstW);
+        store_words<S, NO>(dst1 + (size_t)gy * dpitch1, gx, o1, dstW);
+    }
+}
+
 template <int BPS>
 OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
 {
     constexpr int CPT = 8, NO = BPS == 1 ? CPT / 4 : CPT / 2;   // packed output words per plane
-    typedef typename StoreT<BPS>::type S;
     // the geometry lives in shared memory: copy what the loop needs into registers once
-    const PlaneTables &T = *g.T;
-    const int tile_w = g.tw, tile_h = g.th, x0 = g.x0, y0 = g.y0, sy0 = g.sy0;
-    const int mid_pitch = g.mid_pitch, mid_rows = g.mid_rows, approx = g.approx_v, shift = g.dst_shift, nplanes = g.nplanes, il = g.dst_interleaved;
-    const int vtaps = T.vtaps, exact_from = T.exact_from, dstW = T.dstW;
-    const int bias16 = T.vbias << 16, k16 = (vtaps * T.vbias - ((64 + 8 * (vtaps - 1)) >> 4)) << 16;
-    const bool fast_ok = BPS == 1 && approx && T.vbias > 0;
+    const int tile_w = g.tw, tile_h = g.th, y0 = g.y0, sy0 = g.sy0;
+    const int mid_pitch = g.mid_pitch, plane_step = g.mid_rows * g.mid_pitch, approx = g.approx_v, shift = g.dst_shift, nplanes = g.nplanes, il = g.dst_interleaved;
+    const int vtaps = g.vtaps, exact_from = g.exact_from, dstW = g.dstW;
     uint8_t *const dst0 = g.dst0, *const dst1 = g.dst1;
     const int dpitch0 = g.dst_pitch0, dpitch1 = g.dst_pitch1;
     const int lpr_log2 = g.tw_log2 - 3;                          // lanes per output row: tw / 8
@@ -844,45 +830,50 @@ OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
     const mid_t *mid_s = reinterpret_cast<const mid_t *>(smem + g.off_mid) + x;
     const int32_t *vc_s = reinterpret_cast<const int32_t *>(smem + g.off_vc);
     const int32_t *vpos_s = reinterpret_cast<const int32_t *>(smem + g.off_vpos);
-    const int gx = x0 + x;
-    for (int y = ry; y < tile_h; y += rows_per_pass) {
+    const int gx = g.x0 + x;
+    int y = ry;
+    if (BPS == 1 && approx && g.vbias > 0) {
+        const int bias16 = g.vbias << 16, k16 = (vtaps * g.vbias - ((64 + 8 * (vtaps - 1)) >> 4)) << 16;
+        const int fast_rows = ott_min(tile_h, exact_from - y0);
+        // whole 8 / 16-byte stores when the unit lies inside the plane and the surface rows are aligned
+        const bool vec_ok = gx + CPT <= dstW && (il ? ((((uintptr_t)dst0 | (uintptr_t)dpitch0) & 15) == 0)
+                                                    : (nplanes == 1 && (((uintptr_t)dst0 | (uintptr_t)dpitch0) & 7) == 0));
+        for (; y < fast_rows; y += rows_per_pass) {
+            const int32_t *cf = vc_s + y * vtaps;
+            const mid_t *m = mid_s + (vpos_s[y] - sy0) * mid_pitch;
+            uint32_t o0[NO], o1[NO];
+            OTT_NOUNROLL
+            for (int p = 0; p < nplanes; ++p, m += plane_step) {
+                uint32_t t[CPT / 4];
+                vrow_bias8<CPT>(m, mid_pitch, cf, vtaps, bias16, k16, t);
+                OTT_UNROLL
+                for (int k = 0; k < CPT / 4; ++k) {
+                    if (p == 0) o0[k] = t[k];
+                    else o1[k] = t[k];
+                }
+            }
+            vpass_store<BPS>(dst0, dst1, dpitch0, dpitch1, y0 + y, gx, dstW, nplanes, il, vec_ok, o0, o1);
+        }
+    }
+    for (; y < tile_h; y += rows_per_pass) {
         const int gy = y0 + y;
         const int32_t *cf = vc_s + y * vtaps;
         int mode;
         if (BPS == 1) mode = vtaps == 1 ? VM_ONE8 : ((approx && gy < exact_from) ? VM_APPROX8 : VM_EXACT8);
         else mode = vtaps == 1 ? VM_ONE10 : VM_EXACT10;
-        const bool fast = fast_ok && gy < exact_from;
         const mid_t *m = mid_s + (vpos_s[y] - sy0) * mid_pitch;
         uint32_t o0[NO], o1[NO];
         OTT_NOUNROLL
-        for (int p = 0; p < nplanes; ++p, m += mid_rows * mid_pitch) {
+        for (int p = 0; p < nplanes; ++p, m += plane_step) {
             uint32_t t[NO];
-            if (BPS == 1) {
-                if (fast) vrow_bias8<CPT>(m, mid_pitch, cf, vtaps, bias16, k16, reinterpret_cast<uint32_t (&)[CPT / 4]>(t));
-                else vcolumns8_cold(m, mid_pitch, cf, vtaps, mode, reinterpret_cast<uint32_t (&)[2]>(t));
-            } else {
-                vcolumns<CPT, BPS>(m, mid_pitch, cf, vtaps, mode, shift, t);
-            }
+            vcolumns<CPT, BPS>(m, mid_pitch, cf, vtaps, mode, shift, t);
             OTT_UNROLL
             for (int k = 0; k < NO; ++k) {
                 if (p == 0) o0[k] = t[k];
                 else o1[k] = t[k];
             }
         }
-        if (nplanes == 1) {
-            store_words<S, NO>(dst0 + (size_t)gy * dpitch0, gx, o0, dstW);
-        } else if (il) {
-            uint32_t z[2 * NO];
-            OTT_UNROLL
-            for (int k = 0; k < NO; ++k) {
-                if (BPS == 1) zip8(o0[k], o1[k], z[2 * k], z[2 * k + 1]);
-                else zip16(o0[k], o1[k], z[2 * k], z[2 * k + 1]);
-            }
-            store_words<S, 2 * NO>(dst0 + (size_t)gy * dpitch0, 2 * gx, z, 2 * dstW);
-        } else {
-            store_words<S, NO>(dst0 + (size_t)gy * dpitch0, gx, o0, dstW);
-            store_words<S, NO>(dst1 + (size_t)gy * dpitch1, gx, o1, dstW);
-        }
+        vpass_store<BPS>(dst0, dst1, dpitch0, dpitch1, gy, gx, dstW, nplanes, il, false, o0, o1);
     }
 }
 
@@ -897,25 +888,21 @@ OTT_DEV void phase_vpass(int tid, const TileGeom &g, unsigned char *smem)
 OTT_DEV void copy_rows(int tid, const uint8_t *src, int spitch, uint8_t *dst, int dpitch, int row_bytes, int y0, int rows)
 {
     const bool vec = ((((uintptr_t)src | (uintptr_t)dst | (uintptr_t)spitch | (uintptr_t)dpitch) & 15) == 0);
-    if (vec) {
-        const int nvec = row_bytes >> 4;
-        const int total = rows * nvec;
-        // flat index over (row, vector): consecutive threads copy consecutive 16-byte vectors of a row
-        for (int i = tid; i < total; i += kThreads) {
-            const int r = i / nvec, v = i - r * nvec;
-            const uint4 *s = reinterpret_cast<const uint4 *>(src + (size_t)(y0 + r) * spitch);
-            uint4 *d = reinterpret_cast<uint4 *>(dst + (size_t)(y0 + r) * dpitch);
-            d[v] = ott_ldg(s + v);
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr int kWarps = kThreads / 32;
+    const int nvec = vec ? row_bytes >> 4 : 0;
+    // a warp takes a row, its lanes stride over the row's 16-byte vectors (two in flight per lane)
+    for (int r = warp; r < rows; r += kWarps) {
+        const uint8_t *s = src + (size_t)(y0 + r) * spitch;
+        uint8_t *d = dst + (size_t)(y0 + r) * dpitch;
+        int v = lane;
+        for (; v + 32 < nvec; v += 64) {
+            const uint4 a = ott_ldg(reinterpret_cast<const uint4 *>(s) + v), b = ott_ldg(reinterpret_cast<const uint4 *>(s) + v + 32);
+            reinterpret_cast<uint4 *>(d)[v] = a;
+            reinterpret_cast<uint4 *>(d)[v + 32] = b;
         }
-        const int tail = row_bytes - (nvec << 4);
-        for (int i = tid; i < rows * tail; i += kThreads) {
-            const int r = i / tail, b = (nvec << 4) + (i - r * tail);
-            dst[(size_t)(y0 + r) * dpitch + b] = ott_ldg(src + (size_t)(y0 + r) * spitch + b);
-        }
-    } else {
-        for (int r = 0; r < rows; ++r)
-            for (int i = tid; i < row_bytes; i += kThreads)
-                dst[(size_t)(y0 + r) * dpitch + i] = ott_ldg(src + (size_t)(y0 + r) * spitch + i);
+        for (; v < nvec; v += 32) reinterpret_cast<uint4 *>(d)[v] = ott_ldg(reinterpret_cast<const uint4 *>(s) + v);
+        for (int i = (nvec << 4) + lane; i < row_bytes; i += 32) d[i] = ott_ldg(s + i);
     }
 }
 
@@ -926,26 +913,23 @@ OTT_DEV void interleave_rows8(int tid, const uint8_t *u, const uint8_t *v, int s
     const bool vec = ((((uintptr_t)u | (uintptr_t)v | (uintptr_t)spitch) & 7) == 0) &&
                      ((((uintptr_t)dst | (uintptr_t)dpitch) & 15) == 0);
     const int n8 = vec ? cw >> 3 : 0;
-    if (n8) {
-        const int total = rows * n8;
-        for (int i = tid; i < total; i += kThreads) {
-            const int r = i / n8, k = i - r * n8;
-            const uint2 a = ott_ldg(reinterpret_cast<const uint2 *>(u + (size_t)(y0 + r) * spitch) + k);
-            const uint2 b = ott_ldg(reinterpret_cast<const uint2 *>(v + (size_t)(y0 + r) * spitch) + k);
-            uint4 q;
-            q.x = (a.x & 0xffu) | ((b.x & 0xffu) << 8) | ((a.x & 0xff00u) << 8) | ((b.x & 0xff00u) << 16);
-            q.y = ((a.x >> 16) & 0xffu) | (((b.x >> 16) & 0xffu) << 8) | ((a.x >> 24) << 16) | ((b.x >> 24) << 24);
-            q.z = (a.y & 0xffu) | ((b.y & 0xffu) << 8) | ((a.y & 0xff00u) << 8) | ((b.y & 0xff00u) << 16);
-            q.w = ((a.y >> 16) & 0xffu) | (((b.y >> 16) & 0xffu) << 8) | ((a.y >> 24) << 16) | ((b.y >> 24) << 24);
-            reinterpret_cast<uint4 *>(dst + (size_t)(y0 + r) * dpitch)[k] = q;
-        }
-    }
-    const int done = n8 << 3, tail = cw - done;
-    for (int i = tid; i < rows * tail; i += kThreads) {
-        const int r = i / tail, x = done + (i - r * tail);
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr int kWarps = kThreads / 32;
+    for (int r = warp; r < rows; r += kWarps) {
+        const uint8_t *su = u + (size_t)(y0 + r) * spitch, *sv = v + (size_t)(y0 + r) * spitch;
         uint8_t *d = dst + (size_t)(y0 + r) * dpitch;
-        d[2 * x] = ott_ldg(u + (size_t)(y0 + r) * spitch + x);
-        d[2 * x + 1] = ott_ldg(v + (size_t)(y0 + r) * spitch + x);
+        for (int k = lane; k < n8; k += 32) {
+            const uint2 a = ott_ldg(reinterpret_cast<const uint2 *>(su) + k);
+            const uint2 b = ott_ldg(reinterpret_cast<const uint2 *>(sv) + k);
+            uint4 q;
+            zip8(a.x, b.x, q.x, q.y);
+            zip8(a.y, b.y, q.z, q.w);
+            reinterpret_cast<uint4 *>(d)[k] = q;
+        }
+        for (int x = (n8 << 3) + lane; x < cw; x += 32) {
+            d[2 * x] = ott_ldg(su + x);
+            d[2 * x + 1] = ott_ldg(sv + x);
+        }
     }
 }
 
@@ -953,59 +937,36 @@ OTT_DEV void interleave_rows8(int tid, const uint8_t *u, const uint8_t *v, int s
 // Resolves one work item.  Returns 0: nothing to do, 1: scale tile (geometry filled), 2: copy item.
 // off_src: byte offset of the source buffer this tile stages into; the intermediate region(s) and the per-slot tables
 // follow the source buffer(s).
-OTT_DEV int item_prepare(const Item &it, const Binding &b, const LadderLaunch &L, int buf, int mid_buf, int table_slot, TileGeom &g)
+// g's static block (the Item) is already in place; this adds what depends on the step.
+OTT_DEV int item_prepare(const Binding &b, const LadderLaunch &L, int buf, int mid_buf, int table_slot, TileGeom &g)
 {
-    if (!b.active || ((b.skip_mask >> it.slot) & 1u)) return 0;
-    const PlanDev &plan = *b.plan;
-    if (it.slot == plan.thumb_slot && !b.thumb_active) return 0;
-    if (it.kind == ITEM_COPY_LUMA || it.kind == ITEM_COPY_CHROMA) return 2;
-    const RungDev &R = plan.rung[it.slot];
-    const bool luma = it.kind == ITEM_SCALE_LUMA;
-    const PlaneTables &T = luma ? R.luma : R.chroma;
-    const int src_il = plan.src_fmt == 2 /*P010*/, dst_il = R.fmt == 1 /*NV12*/ || R.fmt == 2 /*P010*/;
-    g.T = &T;
-    g.bps = plan.bps;
-    g.nplanes = luma ? 1 : 2;
-    g.x0 = it.x0; g.y0 = it.y0; g.tw = it.tw; g.th = it.th;
-    g.sy0 = it.sy0; g.sr = it.sr; g.sx0 = it.sx0; g.nvec = it.nvec;
-    g.spw = T.sw_words;
-    g.mid_pitch = T.mid_pitch;
-    g.mid_rows = (it.sr + 15) & ~15;
-    g.tw_log2 = T.tw == 64 ? 6 : 5;
-    g.approx_v = R.approx_v;
+    const int slot = g.slot;
+    if (!b.active || ((b.skip_mask >> slot) & 1u)) return 0;
+    if (g.kind == ITEM_COPY_LUMA || g.kind == ITEM_COPY_CHROMA) return (g.thumb && !b.thumb_active) ? 0 : 2;
+    if (g.thumb && !b.thumb_active) return 0;
+    const bool luma = g.kind == ITEM_SCALE_LUMA;
     g.off_src = buf * L.src_max;
     const int mid_base = (L.double_buffer ? 2 : 1) * L.src_max;
     g.off_mid = mid_base + mid_buf * L.mid_max;
     g.off_vc = mid_base + L.mid_buffers * L.mid_max + table_slot * L.vc_max;
-    g.off_vpos = g.off_vc + T.th * T.vtaps * 4;
-    g.src_shift = plan.src_fmt == 2 ? 6 : 0;
-    g.dst_shift = R.fmt == 2 ? 6 : 0;
+    g.off_vpos = g.off_vc + g.vpos_off;
     if (luma) {
         g.src0 = b.src[0]; g.src_pitch0 = b.src_pitch[0];
         g.src1 = nullptr;  g.src_pitch1 = 0;
-        g.src_interleaved = 0;
-        g.dst0 = b.dst[it.slot][0]; g.dst_pitch0 = b.dst_pitch[it.slot][0];
+        g.dst0 = b.dst[slot][0]; g.dst_pitch0 = b.dst_pitch[slot][0];
         g.dst1 = nullptr; g.dst_pitch1 = 0;
-        g.dst_interleaved = 0;
     } else {
+        const int src_il = g.src_interleaved, dst_il = g.dst_interleaved;
         g.src0 = b.src[1]; g.src_pitch0 = b.src_pitch[1];
         g.src1 = src_il ? b.src[1] : b.src[2]; g.src_pitch1 = src_il ? b.src_pitch[1] : b.src_pitch[2];
-        g.src_interleaved = src_il;
-        g.dst0 = b.dst[it.slot][1]; g.dst_pitch0 = b.dst_pitch[it.slot][1];
-        g.dst1 = dst_il ? nullptr : b.dst[it.slot][2]; g.dst_pitch1 = dst_il ? 0 : b.dst_pitch[it.slot][2];
-        g.dst_interleaved = dst_il;
+        g.dst0 = b.dst[slot][1]; g.dst_pitch0 = b.dst_pitch[slot][1];
+        g.dst1 = dst_il ? nullptr : b.dst[slot][2]; g.dst_pitch1 = dst_il ? 0 : b.dst_pitch[slot][2];
     }
-    g.staged_planes = (luma || src_il) ? 1 : 2;
-    g.px_bytes = (!luma && src_il) ? 4 : plan.bps;
-    g.tma_x = g.sx0 * g.px_bytes / 4;
-    // one staged plane occupies sr_max rows of spw words, padded to the 128 bytes a TMA destination must be aligned to
-    g.plane_stride = (T.sr_max * T.sw_words * 4 + 127) & ~127;
     // TMA staging: the host supplied tensor maps for this frame (16-byte aligned planes) and the tile window fits one
     // box; otherwise the compute warps stage the window through registers
-    g.bulk_ok = T.tma_ok && b.tmaps != nullptr;
-    g.box_bytes = T.sr_max * T.sw_words * 4;
-    g.tmap0 = b.tmaps + (size_t)(it.slot * 3 + (luma ? 0 : 1)) * kTensorMapBytes;
-    g.tmap1 = b.tmaps + (size_t)(it.slot * 3 + 2) * kTensorMapBytes;
+    g.bulk_ok = g.tma_ok && b.tmaps != nullptr;
+    g.tmap0 = b.tmaps + (size_t)(slot * 3 + (luma ? 0 : 1)) * kTensorMapBytes;
+    g.tmap1 = b.tmaps + (size_t)(slot * 3 + 2) * kTensorMapBytes;
     return 1;
 }
 

@@ -92,7 +92,7 @@ template <typename T>
 const T *upload(Plan &plan, const std::vector<T> &v, std::string &err)
 {
     void *d = nullptr;
-    if (cudaMalloc(&d, std::max<size_t>(v.size() * sizeof(T), 16)) != cudaSuccess) { err = "cudaMalloc(tables) failed"; return nullptr; }
+    if (cudaMalloc(&d, v.size() * sizeof(T) + 64) != cudaSuccess) { err = "cudaMalloc(tables) failed"; return nullptr; }   // + slack: table slices are bulk-copied in 16-byte units
     plan.allocations.push_back(d);
     if (!v.empty() && cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) {
         err = "cudaMemcpy(tables) failed";
@@ -318,7 +318,7 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
     T.hmma = upload(plan, frags, err);
     T.hkbase = upload(plan, kbase, err);
     T.vpos = upload(plan, v.pos, err);
-    T.vc = upload(plan, v.coef, err);
+    T.vc = upload(plan, std::vector<int32_t>(v.coef.begin(), v.coef.end()), err);
     return T.hpos && T.hc_hi && T.hc_lo && T.hc16 && T.hmma && T.hkbase && T.vpos && T.vc;
 }
 
@@ -417,6 +417,12 @@ std::shared_ptr<Plan> build_plan(const ottgpu_cfg &cfg, std::string &err)
     P.n_slots = plan->n_slots;
     P.thumb_slot = plan->thumb_slot;
 
+    {
+        void *d = nullptr;
+        if (cudaMalloc(&d, sizeof(PlanDev)) != cudaSuccess) { err = "cudaMalloc(plan) failed"; return nullptr; }
+        plan->allocations.push_back(d);
+        plan->dev = static_cast<PlanDev *>(d);
+    }
     struct Sortable { Item it; int band; };
     std::vector<Sortable> ordered;
     for (int s = 0; s < plan->n_slots; ++s) {
@@ -440,6 +446,8 @@ std::shared_ptr<Plan> build_plan(const ottgpu_cfg &cfg, std::string &err)
             it.kind = kind;
             it.y0 = (uint16_t)y0;
             it.th = (uint16_t)rows;
+            it.bps = (uint8_t)bps;
+            it.thumb = is_thumb;
             return it;
         };
         if (same) {
@@ -477,8 +485,12 @@ std::shared_ptr<Plan> build_plan(const ottgpu_cfg &cfg, std::string &err)
         account(class_c, rc2);
         // tile geometry resolved here once (the kernel only loads it); items are ordered by the first source row each
         // tile reads, so tiles of different rungs over the same band run together and share the source through L2
-        auto scale_items = [&](const PlaneTables &T, const std::vector<int32_t> &hp, const std::vector<int32_t> &vp, const std::vector<int32_t> &kb, uint8_t kind, int band_scale, int cls) {
-            const int pxb = (kind == ITEM_SCALE_CHROMA && cfg.src_fmt == OTTGPU_FMT_P010) ? 4 : bps;
+        bool bad_item = false;
+        auto scale_items = [&](const PlaneTables &T, const PlaneTables *T_dev, const std::vector<int32_t> &hp, const std::vector<int32_t> &vp,
+                               const std::vector<int32_t> &kb, uint8_t kind, int band_scale, int cls) {
+            const bool luma = kind == ITEM_SCALE_LUMA, src_il = cfg.src_fmt == OTTGPU_FMT_P010;
+            const bool dst_il = R.fmt == OTTGPU_FMT_NV12 || R.fmt == OTTGPU_FMT_P010;
+            const int pxb = (!luma && src_il) ? 4 : bps;
             const int spv = 16 / pxb, slack = 4 / pxb > 0 ? 4 / pxb : 1;
             for (int ty = 0; ty < T.tiles_y; ++ty)
                 for (int tx = 0; tx < T.tiles_x; ++tx) {
@@ -486,6 +498,7 @@ std::shared_ptr<Plan> build_plan(const ottgpu_cfg &cfg, std::string &err)
                     std::memset(&it, 0, sizeof(it));
                     it.slot = (uint8_t)s;
                     it.kind = kind;
+                    it.thumb = is_thumb;
                     const int x0 = tx * T.tw, y0 = ty * T.th;
                     const int tw = std::min(T.tw, T.dstW - x0), th = std::min(T.th, T.dstH - y0);
                     const int sy0 = vp[y0], sr = std::min(vp[y0 + th - 1] + T.vtaps, T.srcH) - sy0;
@@ -498,25 +511,73 @@ std::shared_ptr<Plan> build_plan(const ottgpu_cfg &cfg, std::string &err)
                             last = std::max(last, kb[gi] + 32 * T.hks);
                         }
                     }
+                    it.T = T_dev;
                     it.x0 = (uint16_t)x0; it.y0 = (uint16_t)y0; it.tw = (uint16_t)tw; it.th = (uint16_t)th;
                     it.sy0 = (uint16_t)sy0; it.sr = (uint16_t)sr; it.sx0 = (uint16_t)sx0;
                     it.nvec = (uint16_t)((last - sx0 + spv - 1) / spv);
+                    it.spw = (uint16_t)T.sw_words;
+                    it.mid_pitch = (uint16_t)T.mid_pitch;
+                    it.mid_rows = (uint16_t)((sr + 15) & ~15);
+                    it.tma_x = (uint16_t)(sx0 * pxb / 4);
+                    // one staged plane occupies sr_max rows of spw words, padded to the 128 bytes a TMA destination must be aligned to
+                    it.plane_stride = (T.sr_max * T.sw_words * 4 + 127) & ~127;
+                    it.box_bytes = T.sr_max * T.sw_words * 4;
+                    it.bps = (uint8_t)bps;
+                    it.nplanes = luma ? 1 : 2;
+                    it.tw_log2 = T.tw == 64 ? 6 : 5;
+                    it.approx_v = (uint8_t)R.approx_v;
+                    it.src_interleaved = !luma && src_il;
+                    it.dst_interleaved = !luma && dst_il;
+                    it.staged_planes = (luma || src_il) ? 1 : 2;
+                    it.px_bytes = (uint8_t)pxb;
+                    it.src_shift = src_il ? 6 : 0;
+                    it.dst_shift = R.fmt == OTTGPU_FMT_P010 ? 6 : 0;
+                    it.tma_ok = (uint8_t)T.tma_ok;
+                    // the tile's slices of the V tables (device pointers); fetched by two bulk copies when 16-byte aligned
+                    it.vc_src = T.vc + (size_t)y0 * T.vtaps;
+                    it.vpos_src = T.vpos + y0;
+                    it.vpos_off = (uint16_t)(T.th * T.vtaps * 4);
+                    const size_t vcb = ((size_t)th * T.vtaps * 4 + 15) & ~(size_t)15, vpb = ((size_t)th * 4 + 15) & ~(size_t)15;
+                    const bool bulk = ((size_t)y0 * T.vtaps * 4) % 16 == 0 && ((size_t)y0 * 4) % 16 == 0 && it.vpos_off % 16 == 0 &&
+                                      vcb <= (size_t)it.vpos_off && vcb < 65536;
+                    it.vc_bytes = bulk ? (uint16_t)vcb : 0;
+                    it.vpos_bytes = bulk ? (uint16_t)vpb : 0;
+                    it.vtaps = (uint16_t)T.vtaps; it.vbias = (uint16_t)T.vbias; it.exact_from = (uint16_t)T.exact_from; it.dstW = (uint16_t)T.dstW;
+                    it.hks = (uint8_t)std::min(T.hks, 255); it.hsplit = (uint8_t)T.hsplit; it.hq = (uint8_t)std::min(T.hq, 255);
+                    if (!kb.empty()) {
+                        it.hmma = T.hmma + (size_t)(x0 / 8) * T.hks * 128;
+                        for (int gi = x0 / 8; gi <= (x0 + tw - 1) / 8; ++gi) {
+                            if (((kb[gi] - sx0) >> 2) > 65535) { err = "source window of one tile too wide"; bad_item = true; }
+                            it.kw[gi - x0 / 8] = (uint16_t)((kb[gi] - sx0) >> 2);
+                        }
+                    }
+                    if (bps == 1) {                              // H-pass runs of the compute warps
+                        constexpr int kWarps = kThreads / 32;
+                        const int groups = (tw + 7) >> 3, mt_total = it.nplanes * ((sr + 15) >> 4);
+                        const int total = groups * mt_total, per = (total + kWarps - 1) / kWarps;
+                        int nt = 0, mt = 0;
+                        for (int w = 0, f = 0; w < kWarps; ++w) {
+                            const int n = std::max(0, std::min(per, total - f));
+                            it.hrun[w] = (uint32_t)nt | ((uint32_t)mt << 8) | ((uint32_t)n << 20);
+                            f += n;
+                            mt += n;
+                            while (mt_total > 0 && mt >= mt_total) { mt -= mt_total; ++nt; }
+                        }
+                    }
                     if (cls == 2) plan->thumb_items.push_back(it);
                     else if (cls == 1) plan->big_items.push_back(it);
                     else ordered.push_back({it, band_scale * sy0});
                 }
         };
-        scale_items(R.luma, lh, lv, lk, ITEM_SCALE_LUMA, 1, class_l);
-        scale_items(R.chroma, chh, cv, ck, ITEM_SCALE_CHROMA, 2, class_c);
+        const PlaneTables *dev_luma = &plan->dev->rung[s].luma, *dev_chroma = &plan->dev->rung[s].chroma;   // addresses only
+        scale_items(R.luma, dev_luma, lh, lv, lk, ITEM_SCALE_LUMA, 1, class_l);
+        scale_items(R.chroma, dev_chroma, chh, cv, ck, ITEM_SCALE_CHROMA, 2, class_c);
+        if (bad_item) return nullptr;
     }
     std::stable_sort(ordered.begin(), ordered.end(), [](const Sortable &a, const Sortable &b) { return a.band < b.band; });
     for (const Sortable &so : ordered) plan->items.push_back(so.it);
 
-    void *d = nullptr;
-    if (cudaMalloc(&d, sizeof(PlanDev)) != cudaSuccess) { err = "cudaMalloc(plan) failed"; return nullptr; }
-    plan->allocations.push_back(d);
-    if (cudaMemcpy(d, &P, sizeof(PlanDev), cudaMemcpyHostToDevice) != cudaSuccess) { err = "cudaMemcpy(plan) failed"; return nullptr; }
-    plan->dev = static_cast<PlanDev *>(d);
+    if (cudaMemcpy(plan->dev, &P, sizeof(PlanDev), cudaMemcpyHostToDevice) != cudaSuccess) { err = "cudaMemcpy(plan) failed"; return nullptr; }
     return plan;
 }
 

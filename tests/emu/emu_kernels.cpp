@@ -36,7 +36,8 @@ cudaError_t launch_ladder(LadderLaunch L, cudaStream_t)
         const Item it = L.items[blk];
         const Binding &b = L.binds[it.chan];
         TileGeom g;
-        const int what = item_prepare(it, b, L, db ? (blk & 1) : 0, mb == 2 ? (blk & 1) : 0, blk & (kGeomSlots - 1), g);   // alternate buffers like the kernel does
+        static_cast<Item &>(g) = it;                          // the producer copies the static block, then patches the step's pointers in
+        const int what = item_prepare(b, L, db ? (blk & 1) : 0, mb == 2 ? (blk & 1) : 0, blk & (kGeomSlots - 1), g);   // alternate buffers like the kernel does
         if (what == 0) continue;
         if (what == 2) {
             for (int tid = 0; tid < kThreads; ++tid) item_copy(tid, it, b);
