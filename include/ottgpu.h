@@ -79,7 +79,10 @@ typedef struct ottgpu_cfg {
 
 typedef struct ottgpu_frame_in {
     const void *data;          /* msg->buffer: packed frame, Y then U then V (or Y then UV) */
-    int mem;                   /* OTTGPU_MEM_HOST (copied during the call) | OTTGPU_MEM_DEVICE (referenced, see released[]) */
+    int mem;                   /* OTTGPU_MEM_HOST: uploaded by the call - complete on return for SYNC submits; with
+                                  OTTGPU_SUBMIT_ASYNC the buffer must stay untouched until the step has retired
+                                  (ottgpu_batch_wait, or the second-next submit of the batch has returned).
+                                  OTTGPU_MEM_DEVICE: referenced in place, see released[] */
     int interlaced, tff;       /* msg->interlaced / msg->tff -> AVFrame flags, transvideo.c:2100-2101 */
     int64_t pts, dts;
     void *opaque;              /* rides with the frame through the 1-frame latency (AVFrame.opaque, transvideo.c:2103-2152) */
@@ -122,8 +125,13 @@ int  ottgpu_channel_create(const ottgpu_cfg *cfg, ottgpu_channel **out);
 /* submit: av_buffersrc_add_frame_flags + av_buffersink_get_frame (2132-2141) + sws_scale x n (1576) + thumbnail
  * sws_scale (2169) + the packed-buffer copies (1610-1624, 2217-2231) + NV12 repack (543-557).  Synchronous.            */
 int  ottgpu_channel_submit(ottgpu_channel *ch, const ottgpu_frame_in *in, ottgpu_frame_out *out);
-/* reset: source_discontinuity handling, transvideo.c:1959-1970 (drops the yadif window and the thumbnail counter)     */
+/* reset: source_discontinuity handling, transvideo.c:1959-1970: drops the yadif window (the frame submitted last is
+ * never produced; fetch its opaque with ottgpu_channel_pending_opaque() first).  The thumbnail counter keeps running,
+ * like the reference's thumbnail_count, which the discontinuity block does not touch.                                 */
 int  ottgpu_channel_reset(ottgpu_channel *ch);
+/* opaque of the frame held back by yadif's one-frame latency (submitted, not yet produced), or NULL.  Call it before
+ * reset / destroy to release what rides with that frame (the reference leaks its opaque_struct there).               */
+void *ottgpu_channel_pending_opaque(const ottgpu_channel *ch);
 /* destroy: avfilter_graph_free / sws_freeContext, transvideo.c:1677, 1963-1966 */
 void ottgpu_channel_destroy(ottgpu_channel *ch);
 int  ottgpu_channel_gpu(const ottgpu_channel *ch);
@@ -137,7 +145,9 @@ int  ottgpu_batch_create(ottgpu_channel **channels, int n, ottgpu_batch **out); 
 /* in[n] / out[n]; in[i].data == NULL skips channel i this step.  ASYNC: returns after enqueueing; at most two steps are
  * in flight (a third submit first waits for the oldest).  Host-memory results, out[] fields and the CONTENT of
  * out[i].thumbnail are valid once the step has completed: after ottgpu_batch_wait(), or when the second-next submit of
- * the same batch has returned.  A thumbnail buffer must not be free()d before that.                                   */
+ * the same batch has returned.  A thumbnail buffer must not be free()d before that; host INPUT frames must not be
+ * overwritten before that either (their upload is asynchronous).  A failed submit leaves the batch and its channels
+ * exactly as they were before the call (windows, slots, thumbnail counters), out[].thumbnail NULL, nothing leaked.    */
 int  ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame_out *out, int flags);
 int  ottgpu_batch_wait(ottgpu_batch *b);
 void ottgpu_batch_destroy(ottgpu_batch *b);

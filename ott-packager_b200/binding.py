@@ -18,6 +18,7 @@ TARGET_A, TARGET_B = 0, 1
 DEINT_ALL, DEINT_FLAGGED, DEINT_BYPASS = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
 SUBMIT_SYNC, SUBMIT_ASYNC = 0, 1
+OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_STATE = 0, -1, -2, -3, -4
 PIX_YUV420P, PIX_YUV422P, PIX_YUV420P10, PIX_YUV422P10 = 0, 1, 2, 3
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -70,6 +71,7 @@ _SIGS = {
     "ottgpu_channel_destroy": (None, [C.c_void_p]),
     "ottgpu_channel_gpu": (C.c_int, [C.c_void_p]),
     "ottgpu_channel_describe": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
+    "ottgpu_channel_pending_opaque": (C.c_void_p, [C.c_void_p]),
     "ottgpu_batch_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]),
     "ottgpu_batch_submit": (C.c_int, [C.c_void_p, C.POINTER(FrameIn), C.POINTER(FrameOut), C.c_int]),
     "ottgpu_batch_wait": (C.c_int, [C.c_void_p]),

@@ -339,6 +339,7 @@ int ottgpu_filter_table(int src_n, int dst_n, int filter, int target, int vertic
 {
     if (src_n < 4 || dst_n < 1 || !pos || !coef) return fail(OTTGPU_ERR_ARG, "bad table request");
     const PolyphaseTable t = plan_table(src_n, dst_n, filter, target, vertical != 0);
+    if (t.taps > 256) return fail(OTTGPU_ERR_ARG, "filter longer than 256 taps: the caller's coef buffer holds dst_n*256 entries");
     std::memcpy(pos, t.pos.data(), sizeof(int32_t) * t.pos.size());
     std::memcpy(coef, t.coef.data(), sizeof(int16_t) * t.coef.size());
     return t.taps;
@@ -358,7 +359,9 @@ int ottgpu_channel_create(const ottgpu_cfg *cfg, ottgpu_channel **out)
     if (rc) return rc;
     std::string err;
     std::shared_ptr<Plan> plan = get_plan(*cfg, err);
-    if (!plan) return fail(err.find("cuda") != std::string::npos ? OTTGPU_ERR_CUDA : OTTGPU_ERR_ARG, err);
+    if (!plan)
+        return fail(err.find("cudaMalloc") != std::string::npos ? OTTGPU_ERR_NOMEM
+                                                                : (err.find("cuda") != std::string::npos ? OTTGPU_ERR_CUDA : OTTGPU_ERR_ARG), err);
     std::unique_ptr<ottgpu_channel> c(new ottgpu_channel);
     c->cfg = *cfg;
     c->plan = plan;
@@ -441,8 +444,16 @@ int ottgpu_channel_reset(ottgpu_channel *ch)
     cudaSetDevice(ch->gpu);
     cudaStreamSynchronize(ch->stream);
     drop_window(ch);
-    ch->thumb_count = 0;       // the reference rebuilds the graph; its thumbnail_count keeps running (transvideo.c:1959-1970)
+    // thumb_count is NOT touched: the reference's thumbnail_count is a local of the thread loop that the discontinuity
+    // block (transvideo.c:1959-1970) leaves alone, so the 150-frame cadence runs straight through a signal loss
     return OTTGPU_OK;
+}
+
+void *ottgpu_channel_pending_opaque(const ottgpu_channel *ch)
+{
+    // the frame submitted last has not been produced yet (yadif's one-frame latency); BYPASS keeps nothing
+    if (!ch || ch->cfg.deint == OTTGPU_DEINT_BYPASS || !ch->next.valid) return nullptr;
+    return ch->next.opaque;
 }
 
 void ottgpu_channel_destroy(ottgpu_channel *ch)
@@ -669,10 +680,72 @@ int ottgpu_batch_timing_read_yadif(ottgpu_batch *b, double *ms_sum, int *launche
     return OTTGPU_OK;
 }
 
+}  // extern "C"
+
+namespace {
+int batch_submit_body(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame_out *out, int flags);
+
+// what a failed submit must put back so that the batch and its channels look as if the call had never been made
+struct ChannelState {
+    FrameRef prev, cur, next;
+    bool slot_used[ottgpu_channel::kSlots];
+    int slot_cooling, thumb_count;
+};
+}  // namespace
+
+extern "C" {
+
 int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame_out *out, int flags)
 {
     if (!b || !in || !out) return fail(OTTGPU_ERR_ARG, "null argument");
     CK(cudaSetDevice(b->gpu));
+    const int n = (int)b->ch.size(), turn = b->turn;
+    std::vector<ChannelState> saved(n);
+    for (int i = 0; i < n; ++i) {
+        const ottgpu_channel *c = b->ch[i];
+        saved[i].prev = c->prev; saved[i].cur = c->cur; saved[i].next = c->next;
+        std::memcpy(saved[i].slot_used, c->slot_used, sizeof(c->slot_used));
+        saved[i].slot_cooling = c->slot_cooling;
+        saved[i].thumb_count = c->thumb_count;
+        out[i].thumbnail = nullptr;                     // so that a failure half way through frees only what this call allocated
+    }
+    const int rc = batch_submit_body(b, in, out, flags);
+    if (rc == OTTGPU_OK) return rc;
+    // Roll back: yadif windows, upload slots and thumbnail counters as before the call, the thumbnails this call
+    // malloc()ed released, the descriptor set handed back.  Uploads already queued on the copy stream only touch slots
+    // that are free again after the roll-back; a later upload into the same slot is ordered behind them on that stream.
+    const std::string why = t_err;
+    for (int i = 0; i < n; ++i) {
+        ottgpu_channel *c = b->ch[i];
+        c->prev = saved[i].prev; c->cur = saved[i].cur; c->next = saved[i].next;
+        std::memcpy(c->slot_used, saved[i].slot_used, sizeof(c->slot_used));
+        c->slot_cooling = saved[i].slot_cooling;
+        c->thumb_count = saved[i].thumb_count;
+        if (out[i].thumbnail) std::free(out[i].thumbnail);
+        out[i].thumbnail = nullptr;
+        out[i].produced = 0;
+        out[i].opaque = nullptr;
+        out[i].n_released = 0;
+    }
+    ottgpu_batch::Set &st = b->set[turn];
+    cudaStreamSynchronize(b->copy_stream);              // whatever part of the step was enqueued no longer reads the descriptors
+    cudaStreamSynchronize(b->stream);
+    cudaGetLastError();
+    if (!st.in_flight) {                                // failed before the step was enqueued as a whole
+        st.pending_thumbs.clear();
+        st.has_readback = false;
+        b->turn = turn;
+    }
+    t_err = why;
+    return rc;
+}
+
+}  // extern "C"
+
+namespace {
+
+int batch_submit_body(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame_out *out, int flags)
+{
     const int turn = b->turn;
     ottgpu_batch::Set &st = b->set[turn];
     b->turn ^= 1;
@@ -928,8 +1001,9 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
     return ottgpu_batch_wait(b);
 }
 
+}  // namespace
+
 /* ---------------------------------------------------------------------------------------------------- pools */
-}  // extern "C"
 
 struct ottgpu_pool {
     int gpu = 0, mem = 0;

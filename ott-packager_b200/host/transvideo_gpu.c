@@ -37,6 +37,18 @@ static void tv_return_input(ottgpu_transvideo *tv, dataqueue_message_struct *msg
     memory_return(tv->msg_pool, msg);
 }
 
+/* the frame yadif still holds back never comes out after a reset / re-key / close: free what rides with it */
+static void tv_drop_pending(ottgpu_transvideo *tv)
+{
+    tv_sideband *sb;
+    if (!tv->channel) return;
+    sb = (tv_sideband *)ottgpu_channel_pending_opaque(tv->channel);
+    if (sb) {
+        free(sb->caption_buffer);
+        free(sb);
+    }
+}
+
 static void tv_release_held(ottgpu_transvideo *tv)
 {
     int i;
@@ -65,6 +77,7 @@ static int tv_open_channel(ottgpu_transvideo *tv, const dataqueue_message_struct
     /* "yadif=0:-1:1" only for 50/60 fps sources, else blanket deinterlace (transvideo.c:2036-2052) */
     const int deint = (msg->fps_num == 60000 || msg->fps_num == 50000) ? OTTGPU_DEINT_FLAGGED : OTTGPU_DEINT_ALL;
     if (tv->channel && tv->chan_width == msg->width && tv->chan_height == msg->height && tv->chan_deint == deint) return 0;
+    tv_drop_pending(tv);
     if (tv->channel) ottgpu_channel_destroy(tv->channel);   /* the reference never re-keys its scalers (latent bug) */
     tv->channel = NULL;
     tv_release_held(tv);
@@ -160,6 +173,7 @@ int ottgpu_transvideo_process(ottgpu_transvideo *tv, dataqueue_message_struct *m
         return -1;
     }
     if (msg->source_discontinuity) {                         /* transvideo.c:1959-1970 */
+        tv_drop_pending(tv);
         ottgpu_channel_reset(tv->channel);
         tv_release_held(tv);
         msg->source_discontinuity = 0;
@@ -209,7 +223,10 @@ int ottgpu_transvideo_process(ottgpu_transvideo *tv, dataqueue_message_struct *m
     if (rc != OTTGPU_OK || !out.produced) {
         for (i = 0; i < tv->num_outputs; ++i) tv_return_rung(tv, i, out.dst[i]);
         if (rc != OTTGPU_OK) {
+            /* a failed submit leaves the channel as it was (the frame was not taken into the window), so this frame's
+             * sideband is ours to free; the reference exit(0)s here, the hook decides */
             tv_fatal(tv, OTTGPU_SIGNAL_DIRECT_ERROR_RAWPOOL, ottgpu_last_error());
+            free(sb->caption_buffer);
             free(sb);
         }
         tv_return_input(tv, msg, rc == OTTGPU_OK);           /* the host copy of the frame is no longer needed */
@@ -336,6 +353,7 @@ void *ottgpu_video_prepare_scale_thread(void *context)
 
 void ottgpu_transvideo_close(ottgpu_transvideo *tv)
 {
+    tv_drop_pending(tv);
     if (tv->channel) ottgpu_channel_destroy(tv->channel);    /* avfilter_graph_free / sws_freeContext, 2416-2427 */
     tv->channel = NULL;
     tv_release_held(tv);

@@ -361,3 +361,68 @@ def test_channels_driven_from_concurrent_threads(lib, og, oracle):
             assert got[0] == 1000 + 100 * k + want[1]
             for a, b in zip(got[1], _oracle_ladder(oracle, want[0], w, h, rungs, og)):
                 assert np.array_equal(a, b)
+
+
+def test_thumbnail_cadence_runs_through_a_discontinuity(lib, og, oracle):
+    """The reference's thumbnail_count is a local of the prepare thread that the source_discontinuity block leaves alone
+    (transvideo.c:1925, 1959-1970, 2160-2185): the Nth PRODUCED frame gets the thumbnail, resets or not."""
+    w, h = 96, 64
+    ch = og.Channel(lib, og.make_cfg(w, h, [(64, 40, og.FMT_I420)], deint=og.DEINT_ALL, thumb=(44, 36, 4)))
+    frames = interlaced_sequence(w, h, 12, seed=9)
+    produced, with_thumb = 0, []
+    for i, f in enumerate(frames):
+        if i == 3 or i == 7:
+            ch.reset()
+        r = ch.submit(f, interlaced=1, tff=1)
+        if r is None:
+            continue
+        produced += 1
+        if r["thumbnail"] is not None:
+            with_thumb.append(produced)
+    assert produced == 12 - 3                            # one priming frame at the start and after each reset
+    assert with_thumb == [4, 8]                          # every 4th produced frame, counted across the resets
+    ch.close()
+
+
+def test_failed_submit_changes_nothing(lib, og, oracle):
+    """ottgpu_batch_submit is transactional: a call that fails (here: a rung without a destination) leaves the yadif
+    window, the upload slots and the thumbnail counter as they were, and the stream continues bit-exactly."""
+    import ctypes as C
+    w, h = 96, 64
+    rungs = [(96, 64, og.FMT_I420), (64, 40, og.FMT_I420)]
+    ch = og.Channel(lib, og.make_cfg(w, h, rungs, deint=og.DEINT_ALL, thumb=(44, 36, 2)))
+    frames = interlaced_sequence(w, h, 7, seed=11)
+    ref = oracle.YadifStream(w, h)
+    produced = 0
+    for i, f in enumerate(frames):
+        if i in (2, 4):                                  # a broken call in between: second rung has no buffer
+            fin, fout = og.FrameIn(), og.FrameOut()
+            ch.fill_in(fin, frames[(i + 3) % 7], 1, 1, 0, 0, 0x77)
+            bufs = ch.alloc_out(fout)
+            fout.dst[1] = None
+            rc = lib.dll.ottgpu_channel_submit(ch.handle, C.byref(fin), C.byref(fout))
+            assert rc == og.ERR_ARG and not fout.thumbnail and not fout.produced
+            assert lib.dll.ottgpu_channel_pending_opaque(ch.handle) == (0x1000 + i - 1)
+        r = ch.submit(f, interlaced=1, tff=1, opaque=0x1000 + i)
+        want = ref.push(f, 1, 1, tag=i)
+        assert (r is None) == (want is None)
+        assert lib.dll.ottgpu_channel_pending_opaque(ch.handle) == 0x1000 + i
+        if want is None:
+            continue
+        produced += 1
+        deint, tag = want
+        assert r["opaque"] == 0x1000 + tag
+        for got, exp in zip(r["rungs"], _oracle_ladder(oracle, deint, w, h, rungs, og)):
+            assert np.array_equal(got, exp)
+        assert (r["thumbnail"] is not None) == (produced % 2 == 0)
+    ch.reset()
+    assert not lib.dll.ottgpu_channel_pending_opaque(ch.handle)
+    ch.close()
+
+
+def test_filter_table_refuses_more_taps_than_the_callers_buffer_holds(real_lib, og):
+    import ctypes as C
+    pos = (C.c_int32 * 144)()
+    coef = (C.c_int16 * (144 * 256))()
+    assert real_lib.dll.ottgpu_filter_table(16384, 144, og.FILTER_BICUBIC, og.TARGET_A, 0, pos, coef) == og.ERR_ARG
+    assert real_lib.dll.ottgpu_filter_table(1080, 144, og.FILTER_BICUBIC, og.TARGET_A, 1, pos, coef) == 30
