@@ -1,22 +1,30 @@
 #!/usr/bin/env python
 """bench.py -- ladder frames/s of the transvideo preprocessing hot path on B200 (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--channels C] [--workload cfg2|cfg1|cfg4]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--channels C] [--workload cfg4|cfg2|cfg1|cfg3]
+                  [--repeats R] [--no-cpu] [--no-extra]
 
 A *step* = one pass of the hot path over one batch: ONE frame of each of C concurrent channels per GPU (weak scaling:
 C channels per GPU, channel-sharded, no collective on the data path -- SURVEY.md 8(e)).
-  value      : source frames/s fully processed to all rungs, inputs and outputs resident in HBM, CUDA-event timed.
-  e2e        : the same through the C ABI with HOST (pinned) source frames: H2D of every frame inside the timed region,
-               rungs written to device surfaces (the workload's NVENC zero-copy hand-off), thumbnails read back to host.
-  e2e_host_out: additionally every rung copied back to pinned host memory (the x264/x265 consumer layout).
-  roofline   : ladder_kernel algorithmic bytes / its CUDA-event launch time vs MEASURED_PEAKS.json hbm_gbs.
+The headline workload is cfg4 (BASELINE.json configs[3], the "1080i channels/box" half of the metric: yadif + 4 rungs,
+64 channels per GPU); the other configs run in the same process with a shorter budget and are reported under `workloads`.
+  value      : source frames/s fully processed to all rungs, inputs and outputs resident in HBM, CUDA-event timed; the
+               timed region of exactly K steps is repeated R times (default 5), `value` is the median region.
+  e2e        : the same through the C ABI with HOST (pinned) source frames: H2D of every frame inside the timed region.
+               Where the rungs land follows the workload's consumer: x264/x265 (cfg1, cfg4, cfg3) = every rung copied
+               back to pinned host memory in the contiguous layout transvideo.c:1330-1338 / 960-967 read; NVENC (cfg2) =
+               pitch-aligned device surfaces, thumbnails to host.  Both variants are always reported (e2e_device_out,
+               e2e_host_out).
+  roofline   : the dominant kernel's algorithmic bytes / its CUDA-event launch time vs MEASURED_PEAKS.json hbm_gbs;
+               roofline.kernels has ladder_kernel and yadif_kernel side by side.
   cpu_baseline / --impl reference: the reference's CPU path (real libswscale 8.0.1 via oracle/swscale_so.py when the
-               bundled .so is present, else the C oracle port) on the box's host cores.
+               bundled .so is present, else the C oracle port) on the box's host cores, free-running workers.
 Nothing here reads /root/reference.  oracle/ is executed only by the cpu_baseline leg (which also checks the last step's GPU
 output against the CPU result) and by --impl reference.
 """
 import argparse
 import gc
+import hashlib
 import ctypes as C
 import importlib
 import json
@@ -36,21 +44,21 @@ WORKLOADS = {
     "cfg2": dict(desc="cfg2: 1080p60 progressive I420 8-bit -> 5-rung NV12 ladder 1080p/720p/540p/360p/416x234, "
                       "bicubic target A, yadif=0:-1:1 pass-through, 176x144 thumbnail every 150 frames",
                  w=1920, h=1080, rungs=[(1920, 1080), (1280, 720), (960, 540), (640, 360), (416, 234)], out_fmt=NV12,
-                 deint=1, interlaced=0, pitch_align=256),
+                 deint=1, interlaced=0, pitch_align=256, consumer="nvenc (device surfaces)"),
     # BASELINE.json configs[0]: 1080i -> yadif + 3 rungs I420
     "cfg1": dict(desc="cfg1: 1080i29.97 TFF I420 8-bit -> yadif(all) + 3-rung I420 ladder 1080p/720p/360p, bicubic "
                       "target A, 176x144 thumbnail every 150 frames",
                  w=1920, h=1080, rungs=[(1920, 1080), (1280, 720), (640, 360)], out_fmt=I420, deint=0, interlaced=1,
-                 pitch_align=0),
+                 pitch_align=0, consumer="x264 (packed host buffers)"),
     # BASELINE.json configs[3] per-GPU slice: 1080i -> yadif + 4 rungs
     "cfg4": dict(desc="cfg4: 1080i channels -> yadif(all) + 4-rung I420 ladder 1080p/720p/540p/360p, bicubic target A",
                  w=1920, h=1080, rungs=[(1920, 1080), (1280, 720), (960, 540), (640, 360)], out_fmt=I420, deint=0,
-                 interlaced=1, pitch_align=0),
+                 interlaced=1, pitch_align=0, consumer="x264 (packed host buffers)"),
     # BASELINE.json configs[2]: 2160p60 10-bit P010 -> 6-rung lanczos ladder (P010 rungs)
     "cfg3": dict(desc="cfg3: 2160p60 P010 10-bit progressive -> 6-rung P010 lanczos ladder 2160p/1440p/1080p/720p/540p/360p, "
                       "target A tables, yadif=0:-1:1 pass-through, 176x144 thumbnail every 150 frames",
                  w=3840, h=2160, rungs=[(3840, 2160), (2560, 1440), (1920, 1080), (1280, 720), (960, 540), (640, 360)],
-                 out_fmt=P010, src_fmt=P010, bps=2, lanczos=1, deint=1, interlaced=0, pitch_align=0),
+                 out_fmt=P010, src_fmt=P010, bps=2, lanczos=1, deint=1, interlaced=0, pitch_align=0, consumer="x265 (packed host buffers)"),
 }
 THUMB = (176, 144, 150)
 
@@ -225,6 +233,7 @@ CPU_KIND_NOTE = ("kind=reference: the scaler is the real libswscale 8.0.1 in thi
                  "kind=port: everything through oracle/ (bundled libswscale missing)")
 
 
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -232,41 +241,50 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def run_cpu_rounds(wl, frames, threads, rounds=None, seconds=None, copies=False):
-    """Each round = every worker thread processes ONE source frame (ctypes releases the GIL inside libswscale / the C
-    oracle).  Returns (frames_done, elapsed_s, kind, per-round seconds)."""
-    workers = [CpuReference(wl, copies) for _ in range(threads)]
-    kind = workers[0].kind
-    barrier = threading.Barrier(threads + 1)
-    state = {"go": True}
+class CpuPool:
+    """Free-running CPU workers: every thread owns its scaler contexts (like one fillet process per channel) and pulls
+    the next frame index from a shared counter until the region's frame budget is used up - no per-round barrier, so a
+    slow frame on one thread never idles the others (ctypes releases the GIL inside libswscale / the C oracle)."""
 
-    def loop(k):
-        i = k
-        while True:
-            barrier.wait()
-            if not state["go"]:
-                return
-            workers[k].frame(frames[i % len(frames)], frames[(i + 1) % len(frames)])
-            i += 1
-            barrier.wait()
+    def __init__(self, wl, frames, threads, copies=False):
+        self.workers = [CpuReference(wl, copies) for _ in range(threads)]
+        self.kind = self.workers[0].kind
+        self.frames, self.threads = frames, threads
 
-    ts = [threading.Thread(target=loop, args=(k,), daemon=True) for k in range(threads)]
-    for t in ts:
-        t.start()
-    per_round, done, t_start = [], 0, time.perf_counter()
-    while True:
+    def run(self, n_frames=None, seconds=None):
+        """Process n_frames (or as many as fit in `seconds`) -> (frames_done, elapsed_s)."""
+        lock = threading.Lock()
+        state = {"next": 0, "done": 0}
+        t_end = None if seconds is None else time.perf_counter() + seconds
+
+        def loop(k):
+            w, fr = self.workers[k], self.frames
+            while True:
+                with lock:
+                    i = state["next"]
+                    if (n_frames is not None and i >= n_frames) or (t_end is not None and time.perf_counter() >= t_end):
+                        return
+                    state["next"] = i + 1
+                w.frame(fr[i % len(fr)], fr[(i + 1) % len(fr)])
+                with lock:
+                    state["done"] += 1
+
+        ts = [threading.Thread(target=loop, args=(k,), daemon=True) for k in range(self.threads)]
         t0 = time.perf_counter()
-        barrier.wait()
-        barrier.wait()
-        per_round.append(time.perf_counter() - t0)
-        done += threads
-        if rounds is not None and len(per_round) >= rounds:
-            break
-        if seconds is not None and time.perf_counter() - t_start >= seconds:
-            break
-    state["go"] = False
-    barrier.wait()
-    return done, sum(per_round), kind, per_round
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        return state["done"], time.perf_counter() - t0
+
+
+def static_config(wl, channels, world):
+    """The part of `config` both arms print verbatim (the driver compares it)."""
+    alg, s_in, s_out = algorithmic_bytes(wl)
+    return {"workload": wl["desc"], "channels_per_gpu": channels, "frames_per_step": world * channels,
+            "algorithmic_bytes_per_frame": alg,
+            "l2": "inputs+outputs per step exceed L2 (%.0f MB in, %.0f MB out per GPU per step)" % (channels * s_in / 1e6, channels * s_out / 1e6),
+            "consumer": wl["consumer"]}
 
 
 def reference_main(args, wl, rank, world):
@@ -274,53 +292,55 @@ def reference_main(args, wl, rank, world):
         return
     threads = host_cores()
     frames = synth_frames(wl["w"], wl["h"], 4, wl["interlaced"], wl.get("src_fmt") == P010)
-    total_rounds = args.warmup + args.steps
-    _, _, kind, per_round = run_cpu_rounds(wl, frames, threads, rounds=total_rounds)
-    timed = per_round[args.warmup:]
-    elapsed = sum(timed)
-    fps = threads * len(timed) / elapsed
-    sample = "%d rounds x %d threads x 1 frame (one frame per host thread per step)" % (len(timed), threads)
+    per_step = world * args.channels                         # the same step as our arm: one frame of every channel
+    pool = CpuPool(wl, frames, threads)
+    if args.warmup > 0:
+        pool.run(n_frames=args.warmup * per_step)
+    done, elapsed = pool.run(n_frames=args.steps * per_step)
+    fps = done / elapsed
+    sample = "%d steps x %d frames (one frame of each of the %d channels per step), %d free-running host threads, %.1f s" % (
+        args.steps, per_step, per_step, threads, elapsed)
     line = {"impl": "reference", "metric": "ladder_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * elapsed / len(timed),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": wl["desc"], "frames_per_step": threads},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind, "sample": sample, "note": CPU_KIND_NOTE},
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * elapsed / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8" if wl.get("bps", 1) == 1 else "u16 (10 significant bits)",
+            "data": "synthetic", "config": static_config(wl, args.channels, world),
+            "run": {"host_threads": threads, "yadif_parity": "unpinned (C port of vf_yadif; no libavfilter in the image)" if wl["deint"] == 0 else "n/a"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": pool.kind, "sample": sample, "note": CPU_KIND_NOTE},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
-def ours_main(args, wl, rank, world, local_rank):
-    import torch
-    og = importlib.import_module("ott-packager_b200")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; libottgpu has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        # keep stdout to the single JSON line: NCCL prints its version banner there at VERSION/INFO level
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL logs (version banner included) off stdout
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    lib = og.Library()
-    stream = torch.cuda.Stream()
-    w, h, Cn = wl["w"], wl["h"], args.channels
+class Ctx:
+    pass
+
+
+def median(v):
+    v = sorted(v)
+    return v[len(v) // 2] if len(v) % 2 else 0.5 * (v[len(v) // 2 - 1] + v[len(v) // 2])
+
+
+def run_workload(cx, name, Cn, steps, warmup, repeats, do_e2e, do_parity):
+    """One workload on this rank's GPU: device-resident region (value, kernel times), optional in-run parity check against
+    the CPU path, optional end-to-end regions.  Every rank of a multi-GPU run executes the same sequence."""
+    og, lib, torch, dist, stream, local_rank, world = cx.og, cx.lib, cx.torch, cx.dist, cx.stream, cx.local_rank, cx.world
+    wl = WORKLOADS[name]
+    w, h = wl["w"], wl["h"]
     fmt = wl["out_fmt"]
     rungs = [(dw, dh, fmt, wl["pitch_align"]) for dw, dh in wl["rungs"]]
     bps, src_fmt = wl.get("bps", 1), wl.get("src_fmt", I420)
     src_bytes = frame_bytes(w, h) * bps
+    libc = C.CDLL(None)
+    submit = lib.dll.ottgpu_batch_submit
 
     def make_channels():
         return [og.Channel(lib, og.make_cfg(w, h, rungs, src_fmt=src_fmt, filt=wl.get("lanczos", 0), deint=wl["deint"], gpu=local_rank, thumb=THUMB,
                                             stream=stream.cuda_stream, thumb_phase=(i * THUMB[2]) // Cn))
                 for i in range(Cn)]
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     base_frames = synth_frames(w, h, 4, wl["interlaced"], src_fmt == P010)
     RING = 4
-    # ---------------- device-resident arm
     chans = make_channels()
     batch = og.Batch(lib, chans)
     rung_bytes = chans[0].rung_bytes
@@ -330,8 +350,7 @@ def ours_main(args, wl, rank, world, local_rank):
     dst_dev = [[[p.take() for p in dst_pools] for _ in range(2)] for _ in range(Cn)]
     for c in range(Cn):
         for r in range(RING):
-            f = np.roll(base_frames[(c + r) % 4], 64 * c)
-            lib.to_device(src_dev[c][r], f, gpu=local_rank)
+            lib.to_device(src_dev[c][r], np.roll(base_frames[(c + r) % 4], 64 * c), gpu=local_rank)
 
     def build_io(phase, host_src=None, host_dst=None):
         fin = (og.FrameIn * Cn)()
@@ -358,22 +377,13 @@ def ours_main(args, wl, rank, world, local_rank):
                 n += 1
         return n
 
-    libc = C.CDLL(None)
-    submit = lib.dll.ottgpu_batch_submit
-
-    step_events = [] if os.environ.get("OTT_STEP_EVENTS") else None       # debugging aid: one CUDA event per step
-
-    def run_steps(b, ios, n, launches):
+    def run_steps(b, ios, first, n, launches):
         thumbs = 0
-        for k in range(n):
+        for k in range(first, first + n):
             fin, fout = ios[k % len(ios)]
             thumbs += free_thumbs(fout)                      # thumbnails of this set's previous use (step k-4: complete)
             lib.check(submit(b.handle, fin, fout, og.SUBMIT_ASYNC))
             launches[0] += b.last_launches
-            if step_events is not None:
-                ev = torch.cuda.Event(enable_timing=True)
-                ev.record(stream)
-                step_events.append(ev)
         return thumbs
 
     def barrier():
@@ -382,84 +392,91 @@ def ours_main(args, wl, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize()
 
-    yadif_ms = [0.0, 0]
-    host_ms = [0.0]
-
-    def timed_region(b, ios, steps, warmup):
-        launches = [0]
+    def timed_regions(b, ios, steps, warmup, repeats):
+        """W warm-up steps, then `repeats` regions of exactly `steps` steps each, every region bracketed by a barrier +
+        synchronize on both sides and timed with CUDA events on the batch's stream; max over ranks per region."""
+        out = []
         with torch.cuda.stream(stream):
-            run_steps(b, ios, warmup, [0])
+            k = 0
+            run_steps(b, ios, k, warmup, [0])
+            k += warmup
             b.wait()
-            barrier()
-            b.timing(True)
-            sampler.busy = True
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            gc.collect()
-            gc.disable()                                     # a collector pause inside the loop would show up as GPU idle time
-            e0.record(stream)
-            h0 = time.perf_counter()
-            thumbs = run_steps(b, ios, steps, launches)
-            host_ms[0] = (time.perf_counter() - h0) * 1000.0 / max(steps, 1)      # wall time of the submission loop per step (includes waiting for a free descriptor set)
-            e1.record(stream)
-            gc.enable()
-            b.wait()
-            torch.cuda.synchronize()
-            sampler.busy = False
-            ms = e0.elapsed_time(e1)
-            if step_events:
-                tail = step_events[-steps:]
-                d = [tail[i].elapsed_time(tail[i + 1]) for i in range(len(tail) - 1)]
-                worst = sorted(range(len(d)), key=lambda i: -d[i])[:6]
-                sys.stderr.write("step deltas ms: median %.4f, worst %s\n" % (sorted(d)[len(d) // 2], [(i, round(d[i], 3)) for i in worst]))
-                del step_events[:]
+            for _ in range(repeats):
+                barrier()
+                b.timing(True)
+                cx.sampler.busy = True
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                gc.collect()
+                gc.disable()                                 # a collector pause inside the loop would show up as GPU idle time
+                launches = [0]
+                e0.record(stream)
+                h0 = time.perf_counter()
+                thumbs = run_steps(b, ios, k, steps, launches)
+                host_ms = (time.perf_counter() - h0) * 1000.0 / max(steps, 1)
+                e1.record(stream)
+                gc.enable()
+                b.wait()
+                barrier()
+                cx.sampler.busy = False
+                ms = e0.elapsed_time(e1)
+                k += steps
+                if dist is not None:
+                    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    ms = float(t.item())
+                kms, kn = b.timing_read()
+                yms, yn = b.timing_read_yadif()
+                b.timing(False)
+                out.append({"ms": ms, "launches": launches[0], "ladder_ms": kms / max(kn, 1), "ladder_n": kn,
+                            "yadif_ms": yms / max(yn, 1) if yn else None, "thumbs": thumbs, "host_ms": host_ms, "last_step": k - 1})
             for fin, fout in ios:
-                thumbs += free_thumbs(fout)
-        if dist is not None:
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        kms, kn = b.timing_read()
-        yadif_ms[0], yadif_ms[1] = b.timing_read_yadif()
-        b.timing(False)
-        return ms, launches[0], kms, kn, thumbs
+                free_thumbs(fout)
+        return out
 
+    def pick(regs):
+        """the median region (by time) and the spread"""
+        order = sorted(range(len(regs)), key=lambda i: regs[i]["ms"])
+        med = regs[order[len(order) // 2]]
+        spread = {"n": len(regs), "ms_per_step": [r["ms"] / steps for r in regs],
+                  "median": med["ms"] / steps, "min": regs[order[0]]["ms"] / steps, "max": regs[order[-1]]["ms"] / steps}
+        return med, spread
+
+    res = {"name": name, "channels": Cn, "steps": steps}
     ios = [build_io(p) for p in range(RING)]
-    ms, launches, kms, kn, _ = timed_region(batch, ios, args.steps, max(args.warmup, 3))
-    yadif_stat = list(yadif_ms)
-    host_submit_ms = host_ms[0]
-    frames_per_step = Cn
-    value = world * frames_per_step * args.steps / (ms / 1000.0)
+    regs = timed_regions(batch, ios, steps, warmup, repeats)
+    med, spread = pick(regs)
+    res.update(ms_per_step=med["ms"] / steps, value=world * Cn * steps / (med["ms"] / 1000.0), repeats=spread,
+               launches=med["launches"], host_loop_ms_per_step=med["host_ms"],
+               ladder_ms=median([r["ladder_ms"] for r in regs]), ladder_launches_timed=sum(r["ladder_n"] for r in regs),
+               yadif_ms=median([r["yadif_ms"] for r in regs]) if regs[0]["yadif_ms"] is not None else None)
 
-    # First half of the cpu_baseline leg (rank 0, N=1, not with --no-cpu): the frames the last timed step produced are
-    # compared with what the CPU path computes for the same inputs.  oracle/ is only ever executed by this leg and by
-    # --impl reference, as the checker / the baseline - never on the measured path.
+    # in-run parity (first half of the cpu_baseline leg: rank 0, N=1, not with --no-cpu): the frames the LAST step of the
+    # last region produced are compared with what the CPU path computes for the same inputs
     parity = None
-    cpu_leg = rank == 0 and world == 1 and not args.no_cpu
-    if cpu_leg and args.steps >= 3 and src_fmt == P010:
+    last_k = regs[-1]["last_step"]
+    if do_parity and last_k >= 3 and src_fmt == P010:
         from oracle import oracle as O
-        last_phase = (args.steps - 1) % RING
-        exp_src = base_frames[((args.steps - 2) % RING) % 4].view(np.uint16)
+        exp_src = base_frames[(((last_k - 1) % RING)) % 4].view(np.uint16)
         ok = True
         for r, (dw, dh) in enumerate(wl["rungs"]):
             if (dw, dh) not in ((3840, 2160), (640, 360)):
                 continue                                     # the 4K lanczos oracle is slow: check the first and last rung
-            got = lib.from_device(dst_dev[0][last_phase % 2][r], rung_bytes[r], gpu=local_rank).view(np.uint16)
+            got = lib.from_device(dst_dev[0][last_k % 2][r], rung_bytes[r], gpu=local_rank).view(np.uint16)
             ok = ok and np.array_equal(got, O.scale_p010(exp_src, w, h, dw, dh, O.LANCZOS))
         parity = "bit-exact vs oracle (channel 0, rungs 2160p + 360p)" if ok else "MISMATCH"
-    elif cpu_leg and args.steps >= 3:
+    elif do_parity and last_k >= 3:
         from oracle import oracle as O
-        # timed step k used ios[k % RING]; the last step's output is the frame submitted one step earlier (yadif latency).
+        # step k used ios[k % RING]; its output is the frame submitted one step earlier (yadif latency).
         # First, middle and last channel of the launch (their tiles are spread over different CTAs and waves).
-        last_phase = (args.steps - 1) % RING
         checked = sorted({0, Cn // 2, Cn - 1})
         ok = True
         for c in checked:
-            src_of = lambda k: np.roll(base_frames[(c + ((args.steps - 1 + k) % RING)) % 4], 64 * c)
+            src_of = lambda d: np.roll(base_frames[(c + ((last_k + d) % RING)) % 4], 64 * c)
             exp_src = src_of(0) if wl["deint"] == 2 else src_of(-1)
             if wl["deint"] == 0:
                 exp_src = O.yadif_frame(src_of(-2), src_of(-1), src_of(0), w, h, 1, 1)
             for r, (dw, dh) in enumerate(wl["rungs"]):
-                got = lib.from_device(dst_dev[c][last_phase % 2][r], rung_bytes[r], gpu=local_rank)
+                got = lib.from_device(dst_dev[c][last_k % 2][r], rung_bytes[r], gpu=local_rank)
                 ref = O.scale_i420(exp_src, w, h, dw, dh)
                 if fmt == NV12:
                     ref = O.i420_to_nv12(ref, dw, dh)
@@ -469,110 +486,181 @@ def ours_main(args, wl, rank, world, local_rank):
                 widths = [dw, 2 * ((dw + 1) // 2)] if fmt == NV12 else [dw, (dw + 1) // 2, (dw + 1) // 2]
                 flat = np.concatenate([got[o: o + pch * n].reshape(n, pch)[:, :wd].ravel() for (o, pch), n, wd in zip(lay, rows, widths)])
                 ok = ok and np.array_equal(flat, ref)
-        parity = "bit-exact vs oracle (channels %s, %d rungs each)" % (",".join(str(c) for c in checked), len(rungs)) if ok else "MISMATCH"
+        parity = ("bit-exact vs CPU path (channels %s, %d rungs each%s)" % (",".join(str(c) for c in checked), len(rungs),
+                  "; yadif vs the C port of vf_yadif - FFmpeg parity unpinned" if wl["deint"] == 0 else "")) if ok else "MISMATCH"
+    res["parity"] = parity
+    batch.close()
+    for c in chans:
+        c.close()
 
     # ---------------- end-to-end arms (host pinned source frames through the C ABI)
-    batch.close()
-    for c in chans:
-        c.close()
-    host_pool = og.Pool(lib, local_rank, og.MEM_HOST, Cn * 2, src_bytes)
-    host_src = [[host_pool.take() for _ in range(2)] for _ in range(Cn)]
-    for c in range(Cn):
-        for r in range(2):
-            f = np.roll(base_frames[(c + r) % 4], 64 * c)
-            C.memmove(host_src[c][r], np.ascontiguousarray(f).ctypes.data, src_bytes)
-    e2e_steps = max(4, min(args.steps, 400))          # same K as the device-resident region (a short region is hostage to one hiccup)
-    chans = make_channels()
-    batch = og.Batch(lib, chans)
-    ios = [build_io(p, host_src=host_src) for p in range(RING)]
-    e2e_warm = max(args.warmup, 8)        # the channels allocate their upload slots / tensor maps lazily: settle first
-    ems, elaunch, _, _, thumbs = timed_region(batch, ios, e2e_steps, e2e_warm)
-    e2e_value = world * Cn * e2e_steps / (ems / 1000.0)
-    thumb_bytes = frame_bytes(THUMB[0], THUMB[1]) * bps
-    e2e = {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": Cn * src_bytes + Cn * 424,
-           "d2h_bytes_per_step": thumbs * thumb_bytes / float(e2e_steps), "ms_per_step": ems / e2e_steps,
-           "outputs": "device surfaces (NVENC-style zero-copy hand-off); thumbnails to host"}
-    batch.close()
-    for c in chans:
-        c.close()
-    # every rung back to pinned host memory (CPU-encoder consumers)
-    out_pools = [og.Pool(lib, local_rank, og.MEM_HOST, Cn, rb) for rb in rung_bytes]
-    host_dst = [[p.take() for p in out_pools] for _ in range(Cn)]
-    chans = make_channels()
-    batch = og.Batch(lib, chans)
-    ios = [build_io(p, host_src=host_src, host_dst=host_dst) for p in range(RING)]
-    hms, _, _, _, thumbs2 = timed_region(batch, ios, e2e_steps, e2e_warm)
-    e2e_host = {"value": world * Cn * e2e_steps / (hms / 1000.0), "unit": "frames/s",
-                "h2d_bytes_per_step": Cn * src_bytes + Cn * 424,
-                "d2h_bytes_per_step": Cn * sum(rung_bytes) + thumbs2 * thumb_bytes / float(e2e_steps),
-                "ms_per_step": hms / e2e_steps, "outputs": "all rungs copied to pinned host memory"}
-    batch.close()
-    for c in chans:
-        c.close()
-    sampler.stop_flag = True
+    if do_e2e:
+        host_pool = og.Pool(lib, local_rank, og.MEM_HOST, Cn * 2, src_bytes)
+        host_src = [[None, None] for _ in range(Cn)]
+        for r in range(2):                                   # one phase's frames of all channels are contiguous in pinned memory
+            for c in range(Cn):
+                host_src[c][r] = host_pool.take()
+        for c in range(Cn):
+            for r in range(2):
+                f = np.roll(base_frames[(c + r) % 4], 64 * c)
+                C.memmove(host_src[c][r], np.ascontiguousarray(f).ctypes.data, src_bytes)
+        e2e_warm = max(warmup, 8)         # the channels allocate their upload slots / tensor maps lazily: settle first
+        thumb_bytes = frame_bytes(THUMB[0], THUMB[1]) * bps
+        chans = make_channels()
+        batch = og.Batch(lib, chans)
+        ios = [build_io(p, host_src=host_src) for p in range(RING)]
+        med, spread = pick(timed_regions(batch, ios, steps, e2e_warm, max(3, repeats)))
+        res["e2e_device_out"] = {"value": world * Cn * steps / (med["ms"] / 1000.0), "unit": "frames/s",
+                                 "h2d_bytes_per_step": Cn * src_bytes + Cn * 424,
+                                 "d2h_bytes_per_step": med["thumbs"] * thumb_bytes / float(steps), "ms_per_step": med["ms"] / steps,
+                                 "repeats": spread, "outputs": "device surfaces (NVENC-style zero-copy hand-off); thumbnails to host"}
+        batch.close()
+        for c in chans:
+            c.close()
+        out_pools = [og.Pool(lib, local_rank, og.MEM_HOST, Cn, rb) for rb in rung_bytes]
+        host_dst = [[p.take() for p in out_pools] for _ in range(Cn)]
+        chans = make_channels()
+        batch = og.Batch(lib, chans)
+        ios = [build_io(p, host_src=host_src, host_dst=host_dst) for p in range(RING)]
+        med, spread = pick(timed_regions(batch, ios, steps, e2e_warm, max(3, repeats)))
+        res["e2e_host_out"] = {"value": world * Cn * steps / (med["ms"] / 1000.0), "unit": "frames/s",
+                               "h2d_bytes_per_step": Cn * src_bytes + Cn * 424,
+                               "d2h_bytes_per_step": Cn * sum(rung_bytes) + med["thumbs"] * thumb_bytes / float(steps),
+                               "ms_per_step": med["ms"] / steps, "repeats": spread,
+                               "outputs": "every rung copied to pinned host memory in the packed layout the x264/x265 threads read (transvideo.c:1330-1338, 960-967)"}
+        batch.close()
+        for c in chans:
+            c.close()
+        for p in out_pools:
+            p.close()
+        host_pool.close()
+    for p in dst_pools:
+        p.close()
+    src_pool.close()
+    res["base_frames"] = base_frames
+    return res
 
+
+def kernel_rooflines(wl, res, peak):
+    """ladder_kernel / yadif_kernel: algorithmic bytes per launch (SURVEY 8(d) per-frame figures x frames per launch) over
+    the CUDA-event launch time the library measured on its stream."""
+    Cn = res["channels"]
+    _, s_in, _ = algorithmic_bytes(wl)
+    out = {}
+    if res["ladder_ms"]:
+        b = ladder_kernel_bytes(wl) * Cn
+        a = b / (res["ladder_ms"] * 1e-3) / 1e9
+        out["ladder_kernel"] = {"ms_per_launch": res["ladder_ms"], "bytes_per_launch": b, "achieved": a, "frac": a / peak}
+    if res["yadif_ms"]:
+        b = 3.5 * s_in * Cn                                  # SURVEY 8(d): yadif reads 2.5*S and writes S per frame
+        a = b / (res["yadif_ms"] * 1e-3) / 1e9
+        out["yadif_kernel"] = {"ms_per_launch": res["yadif_ms"], "bytes_per_launch": b, "achieved": a, "frac": a / peak}
+    return out
+
+
+def ours_main(args, wl, rank, world, local_rank):
+    import torch
+    og = importlib.import_module("ott-packager_b200")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libottgpu has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        # keep stdout to the single JSON line: NCCL prints its version banner there at VERSION/INFO level
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL logs (version banner included) off stdout
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = og.Library()
+    info = (lib.dll.ottgpu_build_info() or b"").decode()
+    if "sm_100a" not in info:
+        raise SystemExit("bench.py: %s is not the sm_100a product build (%s); refusing to measure it" % (lib.path, info))
+    cx = Ctx()
+    cx.og, cx.lib, cx.torch, cx.dist, cx.local_rank, cx.world = og, lib, torch, dist, local_rank, world
+    cx.stream = torch.cuda.Stream()
+    cx.sampler = ClockSampler(local_rank)
+    cx.sampler.start()
+    cpu_leg = rank == 0 and world == 1 and not args.no_cpu
+    warm = max(args.warmup, 3)
+    res = run_workload(cx, args.workload, args.channels, args.steps, warm, args.repeats, True, cpu_leg)
+    extra = {}
+    if not args.no_extra:
+        for name in ("cfg2", "cfg1", "cfg3", "cfg4"):
+            if name == args.workload:
+                continue
+            ch = min(args.channels, 16) if name == "cfg3" else args.channels
+            r = run_workload(cx, name, ch, min(args.steps, 30), warm, 3, False, cpu_leg and name != "cfg3")
+            extra[name] = r
+    cx.sampler.stop_flag = True
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
-    # ---------------- roofline of the dominant kernel
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    alg, s_in, s_out = algorithmic_bytes(wl)
-    k_bytes = ladder_kernel_bytes(wl) * frames_per_step
-    k_ms = kms / max(kn, 1)
-    achieved = k_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-    # DRAM bytes of the same kernel from the committed `ncu --set full` capture (profiles/), scaled from the capture's
-    # frames per launch to this run's; null for workloads that were not captured
+    kr = kernel_rooflines(wl, res, peak)
+    dom = max(kr, key=lambda k: kr[k]["ms_per_launch"]) if kr else None
+    # DRAM bytes of the dominant kernel from the committed `ncu --set full` capture of this workload (profiles/), scaled
+    # from the capture's frames per launch to this run's; null when no capture of that kernel/workload is committed
     traffic, traffic_note = None, None
     try:
-        import glob
-        caps = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ladder_traffic.json")))
-        if caps and args.workload == "cfg2":
-            cap = json.load(open(caps[-1]))
-            traffic = cap["traffic_bytes_per_frame"] * frames_per_step
-            traffic_note = "%s: %d-frame capture scaled per frame; rung writes still resident in L2 at kernel end are not counted by dram__bytes_write" % (
-                os.path.basename(caps[-1]), cap["channels"])
+        cap_file = os.path.join(ROOT, "profiles", "r2_%s_%s_traffic.json" % (args.workload, dom))
+        if dom and os.path.exists(cap_file):
+            cap = json.load(open(cap_file))
+            traffic = cap["traffic_bytes_per_frame"] * res["channels"]
+            traffic_note = "%s: %d-frame capture scaled per frame; writes still resident in L2 at kernel end are not counted by dram__bytes_write" % (
+                os.path.basename(cap_file), cap["channels"])
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "ladder_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kr[dom]["achieved"] if dom else None, "peak": peak, "unit": "GB/s",
+                "frac": kr[dom]["frac"] if dom else None, "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": "measured" if peaks else "fallback",
-                "bytes_per_launch": k_bytes, "ms_per_launch": k_ms, "launches_timed": kn}
-    if yadif_stat[1]:
-        y_ms = yadif_stat[0] / yadif_stat[1]
-        y_bytes = 3.5 * s_in * frames_per_step              # yadif reads 2.5*S and writes S per frame
-        roofline["yadif_kernel"] = {"ms_per_launch": y_ms, "bytes_per_launch": y_bytes,
-                                    "achieved": y_bytes / (y_ms * 1e-3) / 1e9, "frac": y_bytes / (y_ms * 1e-3) / 1e9 / peak}
+                "bytes_per_launch": kr[dom]["bytes_per_launch"] if dom else None, "ms_per_launch": kr[dom]["ms_per_launch"] if dom else None,
+                "kernels": kr,
+                "note": "per-kernel: algorithmic bytes / CUDA-event launch time on the library's stream; the step runs yadif_kernel then ladder_kernel back to back"}
     # ---------------- CPU baseline (rank 0, N=1 only), bounded sample
     cpu = None
     if cpu_leg:
         threads = host_cores()
-        done, el, kind, _ = run_cpu_rounds(wl, base_frames, threads, seconds=args.cpu_seconds)
-        one_done, one_el, _, _ = run_cpu_rounds(wl, base_frames, 1, seconds=min(3.0, args.cpu_seconds))
-        cp_done, cp_el, _, _ = run_cpu_rounds(wl, base_frames, threads, seconds=min(4.0, args.cpu_seconds), copies=True)
-        cpu = {"value": done / el, "unit": "frames/s", "cores": threads, "kind": kind, "note": CPU_KIND_NOTE,
-               "sample": "%d frames of the same workload (%d rounds x %d host threads, one frame per thread per round, ~%.0f s)"
-                         % (done, done // threads, threads, el),
+        frames = res["base_frames"]
+        pool = CpuPool(wl, frames, threads)
+        pool.run(n_frames=2 * threads)
+        done, el = pool.run(seconds=args.cpu_seconds)
+        one = CpuPool(wl, frames, 1)
+        one_done, one_el = one.run(seconds=min(3.0, args.cpu_seconds))
+        cp = CpuPool(wl, frames, threads, copies=True)
+        cp_done, cp_el = cp.run(seconds=min(4.0, args.cpu_seconds))
+        cpu = {"value": done / el, "unit": "frames/s", "cores": threads, "kind": pool.kind, "note": CPU_KIND_NOTE,
+               "sample": "%d frames of the same workload, %d free-running host threads, %.1f s" % (done, threads, el),
                "with_reference_copies": {"value": cp_done / cp_el, "unit": "frames/s",
                                          "note": "same, plus the reference's full-frame memcpys #3, #4 and #5 per rendition "
                                                  "(transvideo.c:1476-1502, 2217-2231, 1610-1624); `value` leaves them out"},
                "single_thread": {"value": one_done / one_el, "unit": "frames/s",
                                  "note": "one thread = how the reference runs one channel's scaler (transvideo.c:1504)"}}
-    line = {"metric": "ladder_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8" if bps == 1 else "u16 (10 significant bits)", "data": "synthetic",
-            "config": {"workload": wl["desc"], "channels_per_gpu": Cn, "frames_per_step": world * Cn,
-                       "algorithmic_bytes_per_frame": alg, "l2": "inputs+outputs per step exceed L2 (%.0f MB in, %.0f MB out per GPU per step)"
-                       % (Cn * s_in / 1e6, Cn * s_out / 1e6), "parity": parity,
-                       "host_loop_ms_per_step": host_submit_ms,
-                       "realtime_channels_equiv": value / (60000.0 / 1001.0 if wl["interlaced"] == 0 else 30000.0 / 1001.0)},
-            "e2e": e2e, "e2e_host_out": e2e_host, "gpu_launches": launches, "roofline": roofline,
-            "clocks": sampler.result()}
+    e2e_key = "e2e_host_out" if wl["consumer"].startswith("x26") else "e2e_device_out"
+    sha = hashlib.sha256(open(lib.path, "rb").read()).hexdigest()[:16]
+    line = {"metric": "ladder_frames_per_sec", "value": res["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8" if wl.get("bps", 1) == 1 else "u16 (10 significant bits)", "data": "synthetic",
+            "config": static_config(wl, args.channels, world),
+            "run": {"parity": res["parity"], "host_loop_ms_per_step": res["host_loop_ms_per_step"], "host_threads": host_cores(),
+                    "realtime_channels_equiv": res["value"] / (60000.0 / 1001.0 if wl["interlaced"] == 0 else 30000.0 / 1001.0),
+                    "library": {"path": os.path.relpath(lib.path, ROOT), "sha256_16": sha, "build": info},
+                    "yadif_parity": "unpinned (GPU == C port of vf_yadif bit-exact; no libavfilter in the image to pin the port)" if wl["deint"] == 0 else "n/a"},
+            "repeats": res["repeats"],
+            "e2e": dict(res[e2e_key], variant=e2e_key), "e2e_device_out": res["e2e_device_out"], "e2e_host_out": res["e2e_host_out"],
+            "gpu_launches": res["launches"], "roofline": roofline, "clocks": cx.sampler.result()}
+    if extra:
+        wls = {}
+        for name, r in extra.items():
+            k2 = kernel_rooflines(WORKLOADS[name], r, peak)
+            wls[name] = {"workload": WORKLOADS[name]["desc"], "channels_per_gpu": r["channels"], "steps": r["steps"],
+                         "value": r["value"], "unit": "frames/s", "ms_per_step": r["ms_per_step"], "repeats": r["repeats"],
+                         "kernels": k2, "parity": r["parity"], "gpu_launches": r["launches"]}
+        line["workloads"] = wls
     if cpu is not None:
         line["cpu_baseline"] = cpu
     emit(line)
@@ -602,13 +690,15 @@ def emit(line):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--channels", type=int, default=64, help="concurrent channels per GPU (one frame each per step)")
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
+    ap.add_argument("--repeats", type=int, default=5, help="timed regions of exactly --steps steps; value = the median region")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the `workloads` block (the other BASELINE configs)")
     args = ap.parse_args()
     claim_stdout()
     wl = WORKLOADS[args.workload]

@@ -109,6 +109,7 @@ typedef struct ottgpu_batch ottgpu_batch;
 
 /* --- library -------------------------------------------------------------------------------------------------- */
 int         ottgpu_abi_version(void);
+const char *ottgpu_build_info(void);                    /* "libottgpu sm_100a ..." for the product build          */
 int         ottgpu_device_count(void);                  /* <0 on error (no driver / no device)                   */
 const char *ottgpu_strerror(int code);
 const char *ottgpu_last_error(void);                    /* thread-local detail string of the last failure          */

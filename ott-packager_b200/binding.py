@@ -59,6 +59,7 @@ class OttGpuError(RuntimeError):
 
 _SIGS = {
     "ottgpu_abi_version": (C.c_int, []),
+    "ottgpu_build_info": (C.c_char_p, []),
     "ottgpu_device_count": (C.c_int, []),
     "ottgpu_strerror": (C.c_char_p, [C.c_int]),
     "ottgpu_last_error": (C.c_char_p, []),

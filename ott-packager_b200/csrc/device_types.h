@@ -20,7 +20,10 @@ typedef int32_t mid_t;
 #else
 typedef int16_t mid_t;
 #endif
-constexpr int kGeomSlots = 4;                  // tile descriptors (and V-table regions) in flight per CTA
+#if !defined(OTTGPU_GEOM_SLOTS)
+#define OTTGPU_GEOM_SLOTS 4
+#endif
+constexpr int kGeomSlots = OTTGPU_GEOM_SLOTS;  // tile descriptors (and V-table regions) in flight per CTA (power of two)
 constexpr int kTensorMapBytes = 128;           // sizeof(CUtensorMap)
 constexpr int kThreads = 384;                  // compute threads of a ladder CTA (12 warps); the kernel adds one producer warp
 

@@ -297,6 +297,15 @@ extern "C" {
 
 int ottgpu_abi_version(void) { return OTTGPU_ABI_VERSION; }
 
+const char *ottgpu_build_info(void)
+{
+#if defined(OTTGPU_EMULATE)
+    return "libottgpu EMULATION (tests/emu: kernel source compiled for the CPU; test infrastructure, not a product build)";
+#else
+    return "libottgpu sm_100a (hand-written CUDA kernels: ladder_kernel<1|2>, yadif_kernel, convert_kernel; no CPU fallback)";
+#endif
+}
+
 int ottgpu_device_count(void)
 {
     int n = 0;

@@ -15,7 +15,7 @@ python - <<PY
 import json
 try:
     d=json.load(open("$OUT/${TAG}_bench.json"))
-    print("value %.0f fps  ms/step %.3f  kernel %.3f ms  roofline %.1f GB/s (%.3f)  e2e %.0f  e2e_host %.0f  parity %s clocks %s" % (d["value"], d["ms_per_step"], d["roofline"]["ms_per_launch"], d["roofline"]["achieved"], d["roofline"]["frac"], d["e2e"]["value"], d["e2e_host_out"]["value"], d["config"]["parity"], d["clocks"]))
+    print("value %.0f fps  ms/step %.3f  kernel %.3f ms  roofline %.1f GB/s (%.3f)  e2e %.0f  e2e_host %.0f  parity %s clocks %s" % (d["value"], d["ms_per_step"], d["roofline"]["ms_per_launch"], d["roofline"]["achieved"], d["roofline"]["frac"], d["e2e"]["value"], d["e2e_host_out"]["value"], d["run"]["parity"], d["clocks"]))
 except Exception as e:
     print("bench parse failed", e); print(open("$OUT/${TAG}_bench.err").read()[-2000:])
 PY

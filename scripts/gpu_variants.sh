@@ -11,7 +11,7 @@ import json
 try:
     d=json.load(open("$OUT/${TAG}_$v.json"))
     r=d["roofline"]
-    print("$v: value %.0f fps  kernel %.4f ms  frac %.3f  %s" % (d["value"], r["ms_per_launch"], r["frac"], d["config"].get("parity")))
+    print("$v: value %.0f fps  kernel %.4f ms  frac %.3f  %s" % (d["value"], r["ms_per_launch"], r["frac"], d["run"].get("parity")))
 except Exception as e:
     print("$v: failed", e); print(open("$OUT/${TAG}_$v.err").read()[-1500:])
 PY
