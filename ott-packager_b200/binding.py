@@ -113,7 +113,12 @@ class Library:
                                   "(there is no CPU fallback)" % self.path)
         self.dll = C.CDLL(self.path)
         for name, (res, args) in _SIGS.items():
-            fn = getattr(self.dll, name)
+            try:
+                fn = getattr(self.dll, name)
+            except AttributeError:
+                if name in ("ottgpu_build_info", "ottgpu_channel_pending_opaque"):     # absent from older A/B builds
+                    continue
+                raise
             fn.restype, fn.argtypes = res, args
 
     def check(self, rc):

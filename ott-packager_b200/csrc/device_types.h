@@ -20,10 +20,11 @@ typedef int32_t mid_t;
 #else
 typedef int16_t mid_t;
 #endif
-#if !defined(OTTGPU_GEOM_SLOTS)
-#define OTTGPU_GEOM_SLOTS 4
-#endif
-constexpr int kGeomSlots = OTTGPU_GEOM_SLOTS;  // tile descriptors (and V-table regions) in flight per CTA (power of two)
+// tile descriptors (and V-table regions) in flight per CTA (powers of two).  16-bit ladders run long lanczos filters whose
+// V tables are large (tile rows x taps x 4 bytes): two regions instead of four leave the shared memory to the tiles
+// (measured on cfg3: 167 -> 146 us per frame); the 8-bit ladders are 1 % faster with four.
+constexpr int kGeomSlots8 = 4, kGeomSlots16 = 2;
+constexpr int geom_slots(int bps) { return bps == 2 ? kGeomSlots16 : kGeomSlots8; }
 constexpr int kTensorMapBytes = 128;           // sizeof(CUtensorMap)
 constexpr int kThreads = 384;                  // compute threads of a ladder CTA (12 warps); the kernel adds one producer warp
 

@@ -101,6 +101,7 @@ template <int BPS>
 __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderLaunch L)
 {
     extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int kGeomSlots = BPS == 2 ? kGeomSlots16 : kGeomSlots8;
     __shared__ __align__(8) uint64_t ready[kGeomSlots], gfree[kGeomSlots], empty[2];
     __shared__ __align__(16) TileGeom s_geom[kGeomSlots];
     __shared__ int s_idx[kGeomSlots], s_what[kGeomSlots], s_buf[kGeomSlots];
@@ -274,9 +275,9 @@ cudaError_t configure_kernels()
 // Preferred: one source buffer + two intermediate regions (the next tile's window is fetched during the V pass, which
 // is far longer than the copy, and the V -> next-H hand-over needs no barrier).  Launches whose tiles are too big for
 // that (very long filters) run with one of each.
-size_t ladder_smem_bytes(int src_max, int mid_max, int vc_max, int *double_buffer, int *mid_buffers)
+size_t ladder_smem_bytes(int bps, int src_max, int mid_max, int vc_max, int *double_buffer, int *mid_buffers)
 {
-    const size_t tables = (size_t)kGeomSlots * vc_max;     // one table region per descriptor slot
+    const size_t tables = (size_t)geom_slots(bps) * vc_max;     // one table region per descriptor slot
     static const int want_two_src = [] { const char *v = std::getenv("OTTGPU_DOUBLE_SRC"); return v ? std::atoi(v) : 0; }();
     const size_t nsrc = want_two_src && 2 * (size_t)src_max + 2 * (size_t)mid_max + tables + 16 <= kMaxTileSmem ? 2 : 1;
     const size_t two_mid = nsrc * src_max + 2 * (size_t)mid_max + tables + 16, one = (size_t)src_max + mid_max + tables + 16;
@@ -302,7 +303,7 @@ cudaError_t launch_ladder(LadderLaunch L, cudaStream_t s)
 {
     if (L.n_items <= 0) return cudaSuccess;
     int db = 0, mb = 1;
-    const size_t smem_bytes = ladder_smem_bytes(L.src_max, L.mid_max, L.vc_max, &db, &mb);
+    const size_t smem_bytes = ladder_smem_bytes(L.bps, L.src_max, L.mid_max, L.vc_max, &db, &mb);
     if (smem_bytes > kMaxTileSmem) return cudaErrorInvalidValue;
     L.double_buffer = db;
     L.mid_buffers = mb;

@@ -9,7 +9,7 @@ namespace ottgpu {
 constexpr size_t kMaxTileSmem = 224 * 1024;
 
 // shared memory one launch needs for the given region maxima; the number of source / intermediate buffers is decided here
-size_t ladder_smem_bytes(int src_max, int mid_max, int vc_max, int *double_buffer, int *mid_buffers = nullptr);
+size_t ladder_smem_bytes(int bps, int src_max, int mid_max, int vc_max, int *double_buffer, int *mid_buffers = nullptr);
 
 // resident CTAs of the ladder kernel per SM for a launch that needs `smem_bytes` of dynamic shared memory (0 on error)
 int ladder_ctas_per_sm(size_t smem_bytes);

@@ -391,7 +391,7 @@ std::shared_ptr<Plan> get_plan(const ottgpu_cfg &cfg_in, std::string &err)
         plan = build_plan(cfg, err);
         if (!plan) return nullptr;
         if (plan->items.empty() || k + 1 == tries.size()) break;
-        if (ladder_ctas_per_sm(ladder_smem_bytes(plan->src_max[0], plan->mid_max[0], plan->vc_max[0], nullptr, nullptr)) >= 2) break;
+        if (ladder_ctas_per_sm(ladder_smem_bytes(fmt_bps(cfg.src_fmt), plan->src_max[0], plan->mid_max[0], plan->vc_max[0], nullptr, nullptr)) >= 2) break;
     }
     g_cache[key] = plan;
     return plan;

@@ -424,7 +424,7 @@ int ottgpu_channel_describe(const ottgpu_channel *ch, char *buf, size_t size)
     std::string out;
     char line[512];
     int db = 0, mb = 1;
-    const size_t smem = ladder_smem_bytes(p.src_max[0], p.mid_max[0], p.vc_max[0], &db, &mb);
+    const size_t smem = ladder_smem_bytes(p.host_copy.bps, p.src_max[0], p.mid_max[0], p.vc_max[0], &db, &mb);
     snprintf(line, sizeof line, "source %dx%d fmt %d, %d rung slot(s), %zu work items/frame (+%zu big-tile, +%zu thumbnail), shared memory %zu B (%s), regions src %d mid %d vc %d\n",
              p.cfg.src_width, p.cfg.src_height, p.cfg.src_fmt, p.n_slots, p.items.size(), p.big_items.size(), p.thumb_items.size(), smem,
              mb == 2 ? "1 source buffer + 2 intermediate regions" : "1 source buffer + 1 intermediate region", p.src_max[0], p.mid_max[0], p.vc_max[0]);

@@ -11,23 +11,27 @@ ap.add_argument("--channels", type=int, default=64)
 ap.add_argument("--steps", type=int, default=60)
 ap.add_argument("--src", default="1920x1080")
 ap.add_argument("--fmt", default="nv12")
+ap.add_argument("--p010", action="store_true", help="P010 source and rungs, lanczos (cfg3 style)")
 ap.add_argument("sets", nargs="+")
 a = ap.parse_args()
 lib = og.Library()
 w, h = map(int, a.src.split("x"))
-fmt = og.FMT_NV12 if a.fmt == "nv12" else og.FMT_I420
-src_bytes = lib.frame_bytes(og.FMT_I420, w, h)
+fmt = og.FMT_P010 if a.p010 else (og.FMT_NV12 if a.fmt == "nv12" else og.FMT_I420)
+src_fmt = og.FMT_P010 if a.p010 else og.FMT_I420
+src_bytes = lib.frame_bytes(src_fmt, w, h)
 rng = np.random.default_rng(3)
-frame = rng.integers(16, 236, src_bytes, dtype=np.uint8)
+frame = ((rng.integers(0, 1024, src_bytes // 2, dtype=np.uint16) << 6).astype(np.uint16).view(np.uint8) if a.p010
+         else rng.integers(16, 236, src_bytes, dtype=np.uint8))
 Cn = a.channels
 src_pool = og.Pool(lib, 0, og.MEM_DEVICE, 2 * Cn, src_bytes)
 srcs = [[src_pool.take() for _ in range(2)] for _ in range(Cn)]
 for c in range(Cn):
     for k in range(2):
-        lib.to_device(srcs[c][k], np.roll(frame, 97 * (2 * c + k)))
+        lib.to_device(srcs[c][k], np.roll(frame, 98 * (2 * c + k)))
 for spec in a.sets:
     rungs = [tuple(map(int, r.split("x"))) + (fmt, 256 if fmt == og.FMT_NV12 else 0) for r in spec.split(",")]
-    chans = [og.Channel(lib, og.make_cfg(w, h, rungs, deint=og.DEINT_BYPASS)) for _ in range(Cn)]
+    chans = [og.Channel(lib, og.make_cfg(w, h, rungs, src_fmt=src_fmt, filt=og.FILTER_LANCZOS if a.p010 else og.FILTER_BICUBIC,
+                                         deint=og.DEINT_BYPASS)) for _ in range(Cn)]
     batch = og.Batch(lib, chans)
     pools = [og.Pool(lib, 0, og.MEM_DEVICE, Cn, rb) for rb in chans[0].rung_bytes]
     dst = [[p.take() for p in pools] for _ in range(Cn)]

@@ -10,9 +10,9 @@ namespace ottgpu {
 
 cudaError_t configure_kernels() { return cudaSuccess; }
 
-size_t ladder_smem_bytes(int src_max, int mid_max, int vc_max, int *double_buffer, int *mid_buffers)
+size_t ladder_smem_bytes(int bps, int src_max, int mid_max, int vc_max, int *double_buffer, int *mid_buffers)
 {
-    const size_t tables = (size_t)kGeomSlots * vc_max;
+    const size_t tables = (size_t)geom_slots(bps) * vc_max;
     const size_t two_mid = (size_t)src_max + 2 * (size_t)mid_max + tables + 16, one = (size_t)src_max + mid_max + tables + 16;
     const int mb = two_mid <= kMaxTileSmem ? 2 : 1;
     if (double_buffer) *double_buffer = 0;
@@ -26,7 +26,7 @@ int ladder_ctas_per_sm(size_t smem_bytes) { return smem_bytes > kMaxTileSmem ? 0
 cudaError_t launch_ladder(LadderLaunch L, cudaStream_t)
 {
     int db = 0, mb = 1;
-    const size_t smem_bytes = ladder_smem_bytes(L.src_max, L.mid_max, L.vc_max, &db, &mb);
+    const size_t smem_bytes = ladder_smem_bytes(L.bps, L.src_max, L.mid_max, L.vc_max, &db, &mb);
     if (smem_bytes > kMaxTileSmem) return cudaErrorInvalidValue;
     L.double_buffer = db;
     L.mid_buffers = mb;
@@ -37,7 +37,7 @@ cudaError_t launch_ladder(LadderLaunch L, cudaStream_t)
         const Binding &b = L.binds[it.chan];
         TileGeom g;
         static_cast<Item &>(g) = it;                          // the producer copies the static block, then patches the step's pointers in
-        const int what = item_prepare(b, L, db ? (blk & 1) : 0, mb == 2 ? (blk & 1) : 0, blk & (kGeomSlots - 1), g);   // alternate buffers like the kernel does
+        const int what = item_prepare(b, L, db ? (blk & 1) : 0, mb == 2 ? (blk & 1) : 0, blk & (geom_slots(L.bps) - 1), g);   // alternate buffers like the kernel does
         if (what == 0) continue;
         if (what == 2) {
             for (int tid = 0; tid < kThreads; ++tid) item_copy(tid, it, b);
