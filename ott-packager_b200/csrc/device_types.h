@@ -45,13 +45,14 @@ struct PlaneTables {
     const uint32_t *hmma;    // 8-bit path: [ceil(dstW/8)][hks][32 lanes][4] IMMA.16832 B fragments of each group of 8 output
                              //   columns: {hi.b0, hi.b1, lo.b0, lo.b1}, coefficient = hi << hsplit | lo, laid out against
                              //   the source bytes hkbase[group] + 32*kstep + k
+    const uint32_t *hmma2;   // 16-bit path, interleaved chroma: the V plane's fragments (hmma holds U's)
     const int32_t *hkbase;   // [ceil(dstW/8)] first source byte of the group's K window (multiple of 4)
     const int32_t *vpos;     // [dstH]   first source row of each output row
     const int32_t *vc;       // [dstH][vtaps] 12-bit coefficients, widened to 32 bits (the V pass multiplies them as they are)
     int srcW, srcH, dstW, dstH;
     int hq;                  // horizontal taps / 4 (tables zero-padded to a multiple of four taps)
     int hks;                 // 8-bit path: K steps (32 source bytes each) of the H-pass contraction
-    int hsplit;              // 8-bit path: 7 (c = 128*hi + lo, lo < 256) or 8 (c = 256*hi + lo)
+    int hsplit;              // 8-bit path: 7 (c = 128*hi + lo, lo < 256) or 8 (c = 256*hi + lo); 16: the 16-bit MMA path
     int mid_pitch;           // H-pass result row pitch in shared memory (mid_t elements): tw + 8, so that the fragment
                              //   stores of the H pass and the 16-byte loads of the V pass are both bank-conflict free
     int vtaps;
@@ -140,9 +141,11 @@ struct Item {
     uint16_t kw[8];          // 8-bit: K-window base of each of the tile's column groups, in 32-bit words from sx0
     uint16_t vtaps, vbias, exact_from, dstW;
     uint8_t hks, hsplit, hq, pad2;
-    uint32_t pad3[3];
+    uint32_t pad3;
+    const uint32_t *hmma2;   // 16-bit interleaved chroma: fragments of the second (V) plane, else = hmma
+    uint32_t pad4[4];
 };
-static_assert(sizeof(Item) == 176, "Item is copied into shared memory as eleven 16-byte vectors");
+static_assert(sizeof(Item) == 192, "Item is copied into shared memory as twelve 16-byte vectors");
 
 // Launch-wide constants of the persistent ladder kernel.
 struct LadderLaunch {

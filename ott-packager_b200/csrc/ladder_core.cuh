@@ -261,10 +261,16 @@ OTT_COLD void phase_stage(int tid, const TileGeom &g, unsigned char *smem)
 
 // P010 keeps its 10 significant bits in the upper part of each 16-bit sample: right-align them in place (both halves of
 // every staged word, i.e. two luma samples or one (U,V) pair) before the H pass reads the window.
+OTT_DEV uint32_t split_bytes16(uint32_t v10x2)         // two right-aligned 10-bit samples -> (s0, s1) byte pairs: s0 = v & 127, s1 = v >> 7
+{
+    return (v10x2 & 0x007f007fu) | ((v10x2 << 1) & 0x0f000f00u);
+}
+
 OTT_DEV void phase_fixup16(int tid, const TileGeom &g, unsigned char *smem)
 {
     const int shift = g.src_shift;
-    if (!shift) return;
+    const bool split = g.hsplit == 16;                    // the MMA path reads every sample as two bytes (s0, s1)
+    if (!shift && !split) return;
     uint32_t *src_s = reinterpret_cast<uint32_t *>(smem + g.off_src);
     int lpr_log2 = 0;
     while ((1 << lpr_log2) < g.nvec && lpr_log2 < 5) ++lpr_log2;
@@ -277,6 +283,7 @@ OTT_DEV void phase_fixup16(int tid, const TileGeom &g, unsigned char *smem)
                 uint4 q = srow[v];
                 q.x = shift_mask16(q.x, shift); q.y = shift_mask16(q.y, shift);
                 q.z = shift_mask16(q.z, shift); q.w = shift_mask16(q.w, shift);
+                if (split) { q.x = split_bytes16(q.x); q.y = split_bytes16(q.y); q.z = split_bytes16(q.z); q.w = split_bytes16(q.w); }
                 srow[v] = q;
             }
         }
@@ -535,6 +542,112 @@ OTT_DEV void hpass16_any(int tid, const TileGeom &g, unsigned char *smem)
     }
 }
 
+// 16-bit sources on the tensor cores: three int8 MMAs per K step over the byte-split staged rows (see plan.cpp):
+//     P0 = sum s0*c0    P1 = sum (s0*c1 + s1*c0)    P2 = sum s1*c1      sum v*c = 16384*P2 + 128*P1 + P0
+//     (sum >> 9) = 32*P2 + ((P1 + (P0 >> 7)) >> 2)          exactly (P0 >= 0, the other terms are multiples of 128)
+// Same work distribution as the 8-bit pass; interleaved P010 chroma reads the same staged rows for both planes with a
+// fragment table per plane.
+#if defined(OTTGPU_EMULATE)
+inline void hmma16_lane(const uint32_t *row_g, const uint32_t *row_g8, const uint32_t *frag32x8, int lane, int (&P0)[4], int (&P1)[4], int (&P2)[4])
+{
+    const int t = lane & 3;
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t *row = (i & 2) ? row_g8 : row_g;          // rows are passed already offset by +t words
+        const int n = 2 * t + (i & 1);
+        for (int k = 0; k < 32; ++k) {
+            const int src = (int)((row[(k >> 2) - t] >> (8 * (k & 3))) & 255u);
+            const uint32_t *f = frag32x8 + (size_t)(4 * n + ((k & 15) >> 2)) * 8;
+            const int r = k >> 4, b = k & 3;
+            P0[i] += src * (int)(int8_t)((f[r] >> (8 * b)) & 255u);
+            P1[i] += src * (int)(int8_t)((f[2 + r] >> (8 * b)) & 255u);
+            P2[i] += src * (int)(int8_t)((f[4 + r] >> (8 * b)) & 255u);
+        }
+    }
+}
+#endif
+
+template <int KS>
+OTT_DEV void hpass16_mma(int tid, const TileGeom &g, unsigned char *smem)
+{
+    const int warp = tid >> 5, lane = tid & 31;
+    const int ks_n = KS ? KS : g.hks;
+    const int mt_plane = (g.sr + 15) >> 4, mt_total = g.nplanes * mt_plane;
+    const uint32_t hr = g.hrun[warp];
+    int left = (int)(hr >> 20);
+    if (left == 0) return;
+    const int spw = g.spw, pitch = g.mid_pitch;
+    const int lane_src = (lane >> 2) * spw + (lane & 3), lane_mid = (lane >> 2) * pitch + 2 * (lane & 3);
+    const uint32_t *src_s = reinterpret_cast<const uint32_t *>(smem + g.off_src) + lane_src;
+    mid_t *mid_s = reinterpret_cast<mid_t *>(smem + g.off_mid) + lane_mid;
+    int nt = (int)(hr & 255u), mt = (int)((hr >> 8) & 4095u);
+    // interleaved chroma: both planes read the one staged plane of (U,V) words
+    const int src_plane_words = g.src_interleaved ? 0 : (g.plane_stride >> 2);
+    while (left > 0) {
+        const int kw = g.kw[nt];
+        int run = ott_min(left, mt_total - mt);
+        left -= run;
+        while (run > 0) {
+            const int p = mt >= mt_plane, m0 = mt - p * mt_plane;
+            int cnt = ott_min(run, mt_plane - m0);
+            run -= cnt;
+            mt += cnt;
+            const uint32_t *frag = (p ? g.hmma2 : g.hmma) + (size_t)nt * ks_n * 256;
+#if !defined(OTTGPU_EMULATE)
+            uint4 Ba[KS ? KS : 1];
+            uint2 Bc[KS ? KS : 1];
+            if (KS) {
+                OTT_UNROLL
+                for (int ks = 0; ks < KS; ++ks) {
+                    Ba[ks] = ott_ldg(reinterpret_cast<const uint4 *>(frag) + (ks * 32 + lane) * 2);
+                    Bc[ks] = ott_ldg(reinterpret_cast<const uint2 *>(frag) + (ks * 32 + lane) * 4 + 2);
+                }
+            }
+#endif
+            const uint32_t *rg = src_s + p * src_plane_words + (m0 << 4) * spw + kw;
+            const uint32_t *rg8 = rg + 8 * spw;
+            uint32_t *o = reinterpret_cast<uint32_t *>(mid_s + (p * g.mid_rows + (m0 << 4)) * pitch + 8 * nt);
+            uint32_t *o8 = o + 4 * pitch;
+            OTT_NOUNROLL
+            for (; cnt > 0; --cnt, rg += 16 * spw, rg8 += 16 * spw, o += 8 * pitch, o8 += 8 * pitch) {
+                int P0[4] = {0, 0, 0, 0}, P1[4] = {0, 0, 0, 0}, P2[4] = {0, 0, 0, 0};
+                if (KS) {
+                    OTT_UNROLL
+                    for (int ks = 0; ks < (KS ? KS : 1); ++ks) {
+#if defined(OTTGPU_EMULATE)
+                        hmma16_lane(rg + 8 * ks, rg8 + 8 * ks, frag + (size_t)ks * 256, lane, P0, P1, P2);
+#else
+                        const uint32_t a[4] = {rg[8 * ks], rg8[8 * ks], rg[8 * ks + 4], rg8[8 * ks + 4]};
+                        ott_mma_u8s8(P0, a, Ba[ks].x, Ba[ks].y);
+                        ott_mma_u8s8(P1, a, Ba[ks].z, Ba[ks].w);
+                        ott_mma_u8s8(P2, a, Bc[ks].x, Bc[ks].y);
+#endif
+                    }
+                } else {
+                    for (int ks = 0; ks < ks_n; ++ks) {
+#if defined(OTTGPU_EMULATE)
+                        hmma16_lane(rg + 8 * ks, rg8 + 8 * ks, frag + (size_t)ks * 256, lane, P0, P1, P2);
+#else
+                        const uint4 ba = ott_ldg(reinterpret_cast<const uint4 *>(frag) + (ks * 32 + lane) * 2);
+                        const uint2 bc = ott_ldg(reinterpret_cast<const uint2 *>(frag) + (ks * 32 + lane) * 4 + 2);
+                        const uint32_t a[4] = {rg[8 * ks], rg8[8 * ks], rg[8 * ks + 4], rg8[8 * ks + 4]};
+                        ott_mma_u8s8(P0, a, ba.x, ba.y);
+                        ott_mma_u8s8(P1, a, ba.z, ba.w);
+                        ott_mma_u8s8(P2, a, bc.x, bc.y);
+#endif
+                    }
+                }
+                int v[4];
+                OTT_UNROLL
+                for (int i = 0; i < 4; ++i) v[i] = 32 * P2[i] + ((P1[i] + (int)((uint32_t)P0[i] >> 7)) >> 2);
+                o[0] = ott_pack_s16(v[1], v[0]);
+                o8[0] = ott_pack_s16(v[3], v[2]);
+            }
+        }
+        mt = 0;
+        ++nt;
+    }
+}
+
 // BPS = bytes per sample of the launch (1 | 2): the kernel is instantiated once per sample size so that each image only
 // carries its own paths (the hot loops are sensitive to instruction-cache pressure).
 template <int BPS>
@@ -547,6 +660,12 @@ OTT_DEV void phase_hpass(int tid, const TileGeom &g, unsigned char *smem)
         else if (hks == 1) hpass8_mma<1, 7>(tid, g, smem);
         else if (hks == 2) hpass8_mma<2, 7>(tid, g, smem);
         else hpass8_mma<0, 7>(tid, g, smem);
+    } else if (g.hsplit == 16) {
+        const int hks = g.hks;
+        if (hks == 1) hpass16_mma<1>(tid, g, smem);
+        else if (hks == 2) hpass16_mma<2>(tid, g, smem);
+        else if (hks == 3) hpass16_mma<3>(tid, g, smem);
+        else hpass16_mma<0>(tid, g, smem);
     } else if (g.src_interleaved) {
         switch (hq) {
         case 1: hpass16il<1>(tid, g, smem); break;

@@ -188,6 +188,57 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
                         }
                 }
     }
+    // 16-bit path (10 significant bits): samples and coefficients are both split at bit 7, v = 128*s1 + s0 and
+    // c = 128*c1 + c0 (s0, c0 < 128; s1 < 8; c1 signed), and the contraction becomes three int8 MMAs over the staged BYTES
+    // (every sample position holds s0 then s1 after the staging fix-up; P010 chroma holds U.s0 U.s1 V.s0 V.s1):
+    //     P0 = sum s0*c0     P1 = sum (s0*c1 + s1*c0)     P2 = sum s1*c1        sum v*c = 16384*P2 + 128*P1 + P0
+    // Fragments per (column group, K step, lane): {A.r0, A.r1, B.r0, B.r1, C.r0, C.r1, 0, 0}; interleaved chroma gets one
+    // table per plane (the non-zero byte positions differ).  hsplit = 16 marks the plane as running this path.
+    std::vector<uint32_t> frags_v;
+    bool mma16 = false;
+    if (bps == 2) {
+        mma16 = true;
+        for (int16_t c : h.coef)
+            if (c < -16384 || c > 16383) mma16 = false;          // c1 must fit a signed byte: else the dp2a path
+    }
+    if (mma16) {
+        const int groups = (dstW + 7) / 8, planes = px_bytes == 4 ? 2 : 1;
+        kbase.resize(groups);
+        for (int gi = 0; gi < groups; ++gi) {
+            int lo_pos = 1 << 30, hi_pos = 0;
+            for (int x = 8 * gi; x < std::min(8 * gi + 8, dstW); ++x) {
+                lo_pos = std::min(lo_pos, h.pos[x]);
+                hi_pos = std::max(hi_pos, h.pos[x] + h.taps);
+            }
+            kbase[gi] = (lo_pos * px_bytes) & ~3;                // BYTES from the start of the staged row's plane
+            hks = std::max(hks, (hi_pos * px_bytes - kbase[gi] + 31) / 32);
+        }
+        hsplit = 16;
+        for (int pl = 0; pl < planes; ++pl) {
+            std::vector<uint32_t> &out = pl ? frags_v : frags;
+            out.assign((size_t)groups * hks * 32 * 8, 0);
+            for (int gi = 0; gi < groups; ++gi)
+                for (int ks = 0; ks < hks; ++ks)
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int x = 8 * gi + (lane >> 2), t = lane & 3;
+                        uint32_t *f = &out[(((size_t)gi * hks + ks) * 32 + lane) * 8];
+                        if (x >= dstW) continue;
+                        for (int r = 0; r < 2; ++r)
+                            for (int b = 0; b < 4; ++b) {
+                                const int pos = kbase[gi] + 32 * ks + 16 * r + 4 * t + b;      // byte in the staged row
+                                const int xs = pos / px_bytes, w = pos % px_bytes;
+                                const int lo_byte = px_bytes == 4 ? 2 * pl : 0;                // where this plane's s0 sits
+                                const bool is_s0 = w == lo_byte, is_s1 = w == lo_byte + 1;
+                                const int j = xs - h.pos[x];
+                                const int c = (j >= 0 && j < h.taps) ? h.coef[(size_t)x * h.taps + j] : 0;
+                                const int c0 = c & 127, c1 = c >> 7;
+                                f[r] |= (uint32_t)((is_s0 ? c0 : 0) & 255) << (8 * b);
+                                f[2 + r] |= (uint32_t)((is_s0 ? c1 : (is_s1 ? c0 : 0)) & 255) << (8 * b);
+                                f[4 + r] |= (uint32_t)((is_s1 ? c1 : 0) & 255) << (8 * b);
+                            }
+                    }
+        }
+    }
     T.srcW = srcW; T.srcH = srcH; T.dstW = dstW; T.dstH = dstH;
     T.hq = hq;
     T.hks = hks;
@@ -224,17 +275,18 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
         for (int tx = 0; tx < tiles_x; ++tx) {
             const int x0 = tx * tw, x1 = std::min(x0 + tw, dstW) - 1;
             int s0 = h.pos[x0] & ~(spv - 1), s1 = h.pos[x1] + taps4 + slack;
-            if (mma8) {                                          // every column group reads its whole K window
-                s0 = 1 << 30;
-                s1 = 0;
+            if (mma8 || mma16) {                                 // every column group reads its whole K window (kbase in bytes)
+                int b0 = 1 << 30, b1 = 0;
                 for (int gi = x0 / 8; gi <= x1 / 8; ++gi) {
-                    s0 = std::min(s0, kbase[gi] & ~15);
-                    s1 = std::max(s1, kbase[gi] + 32 * hks);
+                    b0 = std::min(b0, kbase[gi] & ~15);
+                    b1 = std::max(b1, kbase[gi] + 32 * hks);
                 }
+                s0 = b0 / px_bytes;
+                s1 = (b1 + px_bytes - 1) / px_bytes;
             }
             nvec = std::max(nvec, (s1 - s0 + spv - 1) / spv);
         }
-        if (mma8) nvec |= 1;                                     // row pitch = odd multiple of 16 bytes: the fragment loads
+        if (mma8 || mma16) nvec |= 1;                                     // row pitch = odd multiple of 16 bytes: the fragment loads
                                                                  // (8 rows x 16 bytes) then hit 32 distinct banks
         return nvec * 4;
     };
@@ -310,16 +362,17 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
     vpos_out = v.pos;
     kbase_out = kbase;
 
-    if (mma8) { hi.clear(); lo.clear(); c16.clear(); }           // the 8-bit path reads only the fragment tables
+    if (mma8 || mma16) { hi.clear(); lo.clear(); c16.clear(); }  // the MMA paths read only the fragment tables
     T.hpos = upload(plan, h.pos, err);
     T.hc_hi = upload(plan, hi, err);
     T.hc_lo = upload(plan, lo, err);
     T.hc16 = upload(plan, c16, err);
     T.hmma = upload(plan, frags, err);
+    T.hmma2 = upload(plan, frags_v, err);
     T.hkbase = upload(plan, kbase, err);
     T.vpos = upload(plan, v.pos, err);
     T.vc = upload(plan, std::vector<int32_t>(v.coef.begin(), v.coef.end()), err);
-    return T.hpos && T.hc_hi && T.hc_lo && T.hc16 && T.hmma && T.hkbase && T.vpos && T.vc;
+    return T.hpos && T.hc_hi && T.hc_lo && T.hc16 && T.hmma && T.hmma2 && T.hkbase && T.vpos && T.vc;
 }
 
 void copy_tiling(PlaneTables &T, int w, int h)
@@ -503,13 +556,14 @@ std::shared_ptr<Plan> build_plan(const ottgpu_cfg &cfg, std::string &err)
                     const int tw = std::min(T.tw, T.dstW - x0), th = std::min(T.th, T.dstH - y0);
                     const int sy0 = vp[y0], sr = std::min(vp[y0 + th - 1] + T.vtaps, T.srcH) - sy0;
                     int sx0 = hp[x0] & ~(spv - 1), last = hp[x0 + tw - 1] + 4 * T.hq + slack;   // + one word of funnel-shift slack
-                    if (!kb.empty()) {                           // 8-bit: the K windows of the tile's column groups
-                        sx0 = 1 << 30;
-                        last = 0;
+                    if (!kb.empty()) {                           // MMA paths: the K windows (bytes) of the tile's column groups
+                        int b0 = 1 << 30, b1 = 0;
                         for (int gi = x0 / 8; gi <= (x0 + tw - 1) / 8; ++gi) {
-                            sx0 = std::min(sx0, kb[gi] & ~15);
-                            last = std::max(last, kb[gi] + 32 * T.hks);
+                            b0 = std::min(b0, kb[gi] & ~15);
+                            b1 = std::max(b1, kb[gi] + 32 * T.hks);
                         }
+                        sx0 = b0 / pxb;
+                        last = (b1 + pxb - 1) / pxb;
                     }
                     it.T = T_dev;
                     it.x0 = (uint16_t)x0; it.y0 = (uint16_t)y0; it.tw = (uint16_t)tw; it.th = (uint16_t)th;
@@ -545,13 +599,16 @@ std::shared_ptr<Plan> build_plan(const ottgpu_cfg &cfg, std::string &err)
                     it.vtaps = (uint16_t)T.vtaps; it.vbias = (uint16_t)T.vbias; it.exact_from = (uint16_t)T.exact_from; it.dstW = (uint16_t)T.dstW;
                     it.hks = (uint8_t)std::min(T.hks, 255); it.hsplit = (uint8_t)T.hsplit; it.hq = (uint8_t)std::min(T.hq, 255);
                     if (!kb.empty()) {
-                        it.hmma = T.hmma + (size_t)(x0 / 8) * T.hks * 128;
+                        const int frag_words = bps == 1 ? 128 : 256;                       // per column group and K step
+                        it.hmma = T.hmma + (size_t)(x0 / 8) * T.hks * frag_words;
+                        it.hmma2 = (!luma && src_il) ? T.hmma2 + (size_t)(x0 / 8) * T.hks * frag_words : it.hmma;
                         for (int gi = x0 / 8; gi <= (x0 + tw - 1) / 8; ++gi) {
-                            if (((kb[gi] - sx0) >> 2) > 65535) { err = "source window of one tile too wide"; bad_item = true; }
-                            it.kw[gi - x0 / 8] = (uint16_t)((kb[gi] - sx0) >> 2);
+                            const int kwv = (kb[gi] - sx0 * pxb) >> 2;
+                            if (kwv > 65535 || kwv < 0) { err = "source window of one tile too wide"; bad_item = true; }
+                            it.kw[gi - x0 / 8] = (uint16_t)kwv;
                         }
                     }
-                    if (bps == 1) {                              // H-pass runs of the compute warps
+                    if (!kb.empty()) {                           // H-pass runs of the compute warps (MMA paths)
                         constexpr int kWarps = kThreads / 32;
                         const int groups = (tw + 7) >> 3, mt_total = it.nplanes * ((sr + 15) >> 4);
                         const int total = groups * mt_total, per = (total + kWarps - 1) / kWarps;

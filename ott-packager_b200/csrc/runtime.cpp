@@ -433,9 +433,11 @@ int ottgpu_channel_describe(const ottgpu_channel *ch, char *buf, size_t size)
         const RungDev &R = p.host_copy.rung[s];
         for (int k = 0; k < 2; ++k) {
             const PlaneTables &T = k ? R.chroma : R.luma;
-            snprintf(line, sizeof line, "  slot %d %s %s %dx%d -> %dx%d  taps H %d (x4 quads %d) V %d  tile %dx%d cpt %d  tiles %dx%d  src rows/tile %d  staged row %d B  exact_from %d\n",
-                     s, s == p.thumb_slot ? "thumb" : "rung", k ? "chroma" : "luma", T.srcW, T.srcH, T.dstW, T.dstH, 4 * T.hq, T.hq,
-                     T.vtaps, T.tw, T.th, T.cpt, T.tiles_x, T.tiles_y, T.sr_max, T.sw_words * 4, T.exact_from);
+            const char *hpath = p.host_copy.bps == 1 ? (T.hsplit == 7 ? "IMMA u8 (7-bit split)" : "IMMA u8 (8-bit split)")
+                                                     : (T.hsplit == 16 ? "IMMA 10-bit (3 products)" : "dp2a");
+            snprintf(line, sizeof line, "  slot %d %s %s %dx%d -> %dx%d  taps H %d V %d  H pass %s, %d K step(s)  tile %dx%d  tiles %dx%d  src rows/tile %d  staged row %d B  exact_from %d  V bias %d\n",
+                     s, s == p.thumb_slot ? "thumb" : "rung", k ? "chroma" : "luma", T.srcW, T.srcH, T.dstW, T.dstH, 4 * T.hq,
+                     T.vtaps, hpath, T.hks, T.tw, T.th, T.tiles_x, T.tiles_y, T.sr_max, T.sw_words * 4, T.exact_from, T.vbias);
             out += R.scaled ? line : std::string("  slot ") + std::to_string(s) + (k ? " chroma" : " luma") + " same size: copy items\n";
         }
     }
