@@ -172,6 +172,7 @@ OTT_DEV void ott_mma_u8u8(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint
 namespace ottgpu {
 
 OTT_DEV int ott_min(int a, int b) { return a < b ? a : b; }
+OTT_DEV int ott_select(bool c, int a, int b) { return c ? a : b; }
 OTT_DEV int ott_max(int a, int b) { return a > b ? a : b; }
 OTT_DEV int ott_clip(int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); }
 

@@ -161,40 +161,84 @@ OTT_DEV void yadif_oct8(const YadifJob &j, size_t off, int w, int h, int x8, int
             hi[2 * hw + half] = d + kBias + diff;
         }
     }
-    // ---- direction search, per sample: pred = (c+e)>>1 or the average along the best of the +-1 / +-2 diagonals,
-    //      clamped two samples at a time
-    int cu[16], cd[16];                                    // samples 8*x8-4 .. 8*x8+11 of the rows above / below
+    // ---- direction search.  For direction j the score of sample x is A_j[x-1] + A_j[x] + A_j[x+1] with
+    //      A_j[x] = |u[x+j] - d[x-j]|  (u / d = the rows above / below in cur).  A_j is built four samples at a time: the
+    //      rows are byte-shifted against each other with funnel shifts and differenced with one VABSDIFF4 per word.
+    //      The three-term sums are dot products of the difference words with byte masks (IDP.4A, on the multiply pipe,
+    //      which this kernel otherwise leaves idle); the mask value 8 and the addend turn the sum into the key
+    //      8*score + rank (rank = the order vf_yadif tries the directions in: 0, -1, -2, +1, +2), so that "take the
+    //      candidate only if strictly better" becomes a plain minimum over keys.
+    //      Local byte L of the 16-byte windows cuw / cdw is sample x0 - 4 + L; the thread's samples are L = 4..11.
+    uint32_t A[5][4], P[5][2];                                 // [direction rank][word]: |u-d| words 0..3, averages of words 1..2
     OTT_UNROLL
-    for (int k = 0; k < 16; ++k) { cu[k] = ybyte(cuw[k >> 2], k & 3); cd[k] = ybyte(cdw[k >> 2], k & 3); }
+    for (int r = 0; r < 5; ++r) {
+        const int j = r == 0 ? 0 : (r == 1 ? -1 : (r == 2 ? -2 : (r == 3 ? 1 : 2)));
+        OTT_UNROLL
+        for (int m = 0; m < 4; ++m) {
+            uint32_t uw, dw;
+            if (j == 0) {
+                uw = cuw[m]; dw = cdw[m];
+            } else if (j > 0) {                                 // u shifted up by j bytes, d down by j bytes
+                uw = ott_funnel_r(cuw[m], cuw[m < 3 ? m + 1 : 3], 8u * j);
+                dw = ott_funnel_r(cdw[m > 0 ? m - 1 : 0], cdw[m], 32u - 8u * j);
+            } else {
+                uw = ott_funnel_r(cuw[m > 0 ? m - 1 : 0], cuw[m], 32u + 8 * j);
+                dw = ott_funnel_r(cdw[m], cdw[m < 3 ? m + 1 : 3], (uint32_t)(-8 * j));
+            }
+            A[r][m] = ott_vabsdiff4(uw, dw);
+            if (m == 1 || m == 2) P[r][m - 1] = yavg4(uw, dw);  // candidate predictions (u[x+j] + d[x-j]) >> 1, four per word
+        }
+    }
     const bool first_group = x8 == 0, last_group = 8 * x8 + 8 >= w;
+    // candidate bytes transposed per sample (byte r of q = candidate of rank r, rank 4 in byte 0 of r4): the winner is then
+    // one byte permute with the rank as the selector - no branches, no per-candidate selects
+    uint32_t q[8], r4[8];
+    OTT_UNROLL
+    for (int wsel = 0; wsel < 2; ++wsel) {
+        const uint32_t ab_lo = ott_prmt(P[0][wsel], P[1][wsel], 0x5140u), ab_hi = ott_prmt(P[0][wsel], P[1][wsel], 0x7362u);
+        const uint32_t cd_lo = ott_prmt(P[2][wsel], P[3][wsel], 0x5140u), cd_hi = ott_prmt(P[2][wsel], P[3][wsel], 0x7362u);
+        q[4 * wsel + 0] = ott_prmt(ab_lo, cd_lo, 0x5410u);
+        q[4 * wsel + 1] = ott_prmt(ab_lo, cd_lo, 0x7632u);
+        q[4 * wsel + 2] = ott_prmt(ab_hi, cd_hi, 0x5410u);
+        q[4 * wsel + 3] = ott_prmt(ab_hi, cd_hi, 0x7632u);
+        OTT_UNROLL
+        for (int bsel = 0; bsel < 4; ++bsel) r4[4 * wsel + bsel] = ott_prmt(P[4][wsel], 0u, 0x4440u | (uint32_t)bsel);
+    }
     uint32_t o16[4];
     OTT_UNROLL
     for (int i = 0; i < 8; ++i) {
-        const int q = i + 4;
-        const int c = cu[q], e = cd[q];
-        int p = (c + e) >> 1;
+        // bytes L-1, L, L+1 of A with L = 4 + i: one or two dot products against masks of 8s
+        int key[5];
+        OTT_UNROLL
+        for (int r = 0; r < 5; ++r) {
+            const uint32_t c0 = r == 0 ? 0xfffffff8u : (uint32_t)r;          // j = 0 carries the "- 1" of vf_yadif: 8*(s-1)
+            uint32_t k;
+            switch (i) {
+            case 0: k = ott_dp4a_uu(A[r][1], 0x00000808u, ott_dp4a_uu(A[r][0], 0x08000000u, c0)); break;
+            case 1: k = ott_dp4a_uu(A[r][1], 0x00080808u, c0); break;
+            case 2: k = ott_dp4a_uu(A[r][1], 0x08080800u, c0); break;
+            case 3: k = ott_dp4a_uu(A[r][2], 0x00000008u, ott_dp4a_uu(A[r][1], 0x08080000u, c0)); break;
+            case 4: k = ott_dp4a_uu(A[r][2], 0x00000808u, ott_dp4a_uu(A[r][1], 0x08000000u, c0)); break;
+            case 5: k = ott_dp4a_uu(A[r][2], 0x00080808u, c0); break;
+            case 6: k = ott_dp4a_uu(A[r][2], 0x08080800u, c0); break;
+            default: k = ott_dp4a_uu(A[r][3], 0x00000008u, ott_dp4a_uu(A[r][2], 0x08080000u, c0)); break;
+            }
+            key[r] = (int)k;
+        }
+        // vf_yadif only tries +-2 when +-1 improved the score; ties keep the earlier candidate (the rank in the low bits)
+        const int k2 = ott_select(key[1] < key[0], key[2], 0x7fffffff);
+        const int kl = ott_min(ott_min(key[0], key[1]), k2);
+        const int best = ott_select(key[3] < kl, ott_min(key[3], key[4]), kl);
         // the search is skipped on the first and last three samples of a row (filter_edges): with w a multiple of 8 those
-        // are samples 0-2 of the first group and 5-7 of the last one, a per-thread flag instead of two compares per sample.
-        // vf_yadif only tries +-2 when +-1 improved the score
+        // are samples 0-2 of the first group and 5-7 of the last one
         const bool in = i < 3 ? !first_group : (i >= 5 ? !last_group : true);
-        int score = ott_sad(cu[q + 1], cd[q + 1], ott_sad(c, e, ott_sad(cu[q - 1], cd[q - 1], -1)));
-        const int s1 = ott_sad(c, cd[q + 2], ott_sad(cu[q - 1], cd[q + 1], ott_sad(cu[q - 2], e, 0)));                   // j = -1
-        const int s2 = ott_sad(cu[q - 1], cd[q + 3], ott_sad(cu[q - 2], cd[q + 2], ott_sad(cu[q - 3], cd[q + 1], 0)));  // j = -2
-        const int s3 = ott_sad(cu[q + 2], e, ott_sad(cu[q + 1], cd[q - 1], ott_sad(c, cd[q - 2], 0)));                  // j = +1
-        const int s4 = ott_sad(cu[q + 3], cd[q - 1], ott_sad(cu[q + 2], cd[q - 2], ott_sad(cu[q + 1], cd[q - 3], 0)));  // j = +2
-        const bool c1 = in && s1 < score;
-        score = c1 ? s1 : score; p = c1 ? (cu[q - 1] + cd[q + 1]) >> 1 : p;
-        const bool c2 = c1 && s2 < score;
-        score = c2 ? s2 : score; p = c2 ? (cu[q - 2] + cd[q + 2]) >> 1 : p;
-        const bool c3 = in && s3 < score;
-        score = c3 ? s3 : score; p = c3 ? (cu[q + 1] + cd[q - 1]) >> 1 : p;
-        const bool c4 = c3 && s4 < score;
-        p = c4 ? (cu[q + 2] + cd[q - 2]) >> 1 : p;
+        const uint32_t sel = (uint32_t)ott_select(in, (best & 7) | 0x5550, 0x5550);      // bytes 1-3 of the result: zero (r4 byte 1)
+        const uint32_t p = ott_prmt(q[i], r4[i], sel);
         if (i & 1) {
-            const uint32_t pp = o16[i >> 1] + ((uint32_t)p << 16);                                              // (pred[i-1], pred[i]) + bias
+            const uint32_t pp = o16[i >> 1] + (p << 16);                                                         // (pred[i-1], pred[i]) + bias
             o16[i >> 1] = ott_vmin_s16x2(ott_vmax_s16x2(pp, lo[i >> 1]), hi[i >> 1]) - kBias;                   // 0..255 per lane
         } else {
-            o16[i >> 1] = (uint32_t)p + kBias;
+            o16[i >> 1] = p + kBias;
         }
     }
     const uint32_t outw[2] = {ott_prmt(o16[0], o16[1], 0x6420u), ott_prmt(o16[2], o16[3], 0x6420u)};

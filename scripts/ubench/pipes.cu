@@ -46,6 +46,38 @@ __device__ __forceinline__ void body(uint32_t (&a)[8], uint32_t b, uint32_t c)
             asm volatile("" : "+r"(x));
             asm volatile("mad.hi.s32 %0, %1, %2, %0;" : "+r"(a[k]) : "r"(x), "r"(c));
         }
+        if (OP == 16) { // IDP + LOP3 pair
+            asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(b), "r"(c));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(a[(k + 4) & 7]) : "r"(b), "r"(c));
+        }
+        if (OP == 17) { // IDP + IMAD pair
+            asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(b), "r"(c));
+            asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(a[(k + 4) & 7]) : "r"(b), "r"(c));
+        }
+        if (OP == 18) { // VABSDIFF4 + LOP3 pair
+            asm volatile("vabsdiff4.u32.u32.u32.add %0, %0, %1, %2;" : "+r"(a[k]) : "r"(b), "r"(c));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(a[(k + 4) & 7]) : "r"(b), "r"(c));
+        }
+        if (OP == 19) { // VABSDIFF4 + IMAD pair
+            asm volatile("vabsdiff4.u32.u32.u32.add %0, %0, %1, %2;" : "+r"(a[k]) : "r"(b), "r"(c));
+            asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(a[(k + 4) & 7]) : "r"(b), "r"(c));
+        }
+        if (OP == 20) { // scalar sad (VABSDIFF) + LOP3
+            asm volatile("sad.u32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(b), "r"(c));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(a[(k + 4) & 7]) : "r"(b), "r"(c));
+        }
+        if (OP == 21) { // scalar sad + IMAD
+            asm volatile("sad.u32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(b), "r"(c));
+            asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(a[(k + 4) & 7]) : "r"(b), "r"(c));
+        }
+        if (OP == 22) { // PRMT + IMAD
+            asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(b), "r"(c));
+            asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(a[(k + 4) & 7]) : "r"(b), "r"(c));
+        }
+        if (OP == 23) { // SHF + LOP3 (both alu?)
+            asm volatile("shf.r.clamp.b32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(b), "r"(c & 31));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(a[(k + 4) & 7]) : "r"(b), "r"(c));
+        }
         if (OP == 15) { // vimnmx s16x2
             asm volatile("max.s16x2 %0, %0, %1;" : "+r"(a[k]) : "r"(b));
         }
@@ -169,7 +201,7 @@ int main()
     cudaMalloc(&d_out, 148 * 1024 * 4);
     cudaMalloc(&d_cyc, 148 * 8);
     uint32_t b = 0x01020304u, c = 0x00030001u;
-    for (int T : {128, 512, 1024}) {
+    for (int T : {512}) {
         RUN_ALU(0, "IMAD (mad.lo)", T);
         RUN_ALU(1, "IMAD.HI (mad.hi)", T);
         RUN_ALU(2, "LOP3", T);
@@ -186,6 +218,14 @@ int main()
         RUN_ALU(13, "mul.wide + add", T);
         RUN_ALU(14, "LOP3 + IMAD.HI", T);
         RUN_ALU(15, "VIMNMX.S16x2", T);
+        RUN_ALU(16, "pair IDP+LOP3 (x2 instr)", T);
+        RUN_ALU(17, "pair IDP+IMAD", T);
+        RUN_ALU(18, "pair VABSDIFF4+LOP3", T);
+        RUN_ALU(19, "pair VABSDIFF4+IMAD", T);
+        RUN_ALU(20, "pair SAD+LOP3", T);
+        RUN_ALU(21, "pair SAD+IMAD", T);
+        RUN_ALU(22, "pair PRMT+IMAD", T);
+        RUN_ALU(23, "pair SHF+LOP3", T);
         report("IMMA.16832 u8.s8 x4acc", T, 4, [&] { k_mma<4, 0><<<148, T>>>(d_out, b, d_cyc); });
         report("IMMA.16832 u8.s8 x8acc", T, 8, [&] { k_mma<8, 0><<<148, T>>>(d_out, b, d_cyc); });
         report("IMMA.16816 u8.s8 x8acc", T, 8, [&] { k_mma<8, 1><<<148, T>>>(d_out, b, d_cyc); });
