@@ -356,3 +356,223 @@ def test_pool_exhaustion_reports_like_the_reference(lib, og, oracle, rt, host):
     assert len(got) == 1 and np.array_equal(got[0]["data"], oracle.scale_i420(f, w, h, 64, 40))
     _drain(rt, tv, tv.encode_queue[1], oracle.i420_size(48, 32))
     host.ottgpu_transvideo_close(C.byref(tv))
+
+
+# ------------------------------------------------------------------------------------------------ N3: signal-loss filler
+class MON(C.Structure):                       # ott-packager_b200/host/monitor_gpu.h
+    _fields_ = [("monitor_queue", C.c_void_p), ("prepare_queue", C.c_void_p), ("raw_video_pool", C.c_void_p),
+                ("msg_pool", C.c_void_p), ("device_pool", C.c_void_p), ("gpu", C.c_int), ("running", C.POINTER(C.c_int)),
+                ("reinitialize_decoder", C.POINTER(C.c_int)), ("signal", SIGNAL_FN), ("direct_error", SIGNAL_FN),
+                ("user", C.c_void_p), ("monitor_ready", C.c_int), ("monitor_width", C.c_int), ("monitor_height", C.c_int),
+                ("monitor_num", C.c_int), ("monitor_den", C.c_int), ("monitor_tff", C.c_int), ("monitor_interlaced", C.c_int),
+                ("monitor_aspect_num", C.c_int), ("monitor_aspect_den", C.c_int), ("monitor_anchor_dts", C.c_int64),
+                ("monitor_anchor_pts", C.c_int64), ("total_dead_frames", C.c_int64),
+                ("total_video_monitor_dead_time", C.c_int64), ("expected_dead_frames", C.c_double),
+                ("dead_frames_triggered", C.c_int), ("saved_video_frame", C.c_void_p), ("saved_is_device", C.c_int),
+                ("saved_bytes", C.c_size_t), ("frames_passed", C.c_int64), ("filler_frames", C.c_int64)]
+
+
+def _make_mon(rt, tv, errors, signals):
+    mon = MON()
+    mon.monitor_queue = rt.dataqueue_create()
+    mon.prepare_queue = tv.prepare_queue
+    mon.raw_video_pool, mon.msg_pool, mon.gpu = tv.raw_video_pool, tv.msg_pool, 0
+    mon._running = C.c_int(1)
+    mon.running = C.pointer(mon._running)
+    mon._reinit = C.c_int(0)
+    mon.reinitialize_decoder = C.pointer(mon._reinit)
+    mon._err = SIGNAL_FN(lambda u, code, m: errors.append((code, m)))
+    mon._sig = SIGNAL_FN(lambda u, code, m: signals.append((code, m)))
+    mon.direct_error, mon.signal = mon._err, mon._sig
+    return mon
+
+
+def test_monitor_filler_frames_follow_the_reference(lib, og, oracle, rt, host):
+    """transvideo.c:1726-1812 / 1839-1884: after one second without input the saved frame is repeated at the stream's frame
+    rate with pts/dts extrapolated from the last real frame; the next real frame carries source_discontinuity."""
+    host.ottgpu_monitor_frame.argtypes = [C.POINTER(MON), C.POINTER(Msg)]
+    host.ottgpu_monitor_dead_time.argtypes = [C.POINTER(MON)]
+    host.ottgpu_monitor_close.argtypes = [C.POINTER(MON)]
+    w, h = 96, 64
+    errors, signals = [], []
+    tv = _make_tv(rt, [(64, 40)], errors, signals)
+    mon = _make_mon(rt, tv, errors, signals)
+    frames = [natural_i420(w, h, 7, shift=3.0 * i) for i in range(3)]
+    m = _push(rt, tv, frames[0], w, h, 900000, interlaced=0, fps=(30000, 1001))
+    assert host.ottgpu_monitor_frame(C.byref(mon), m) == 0
+    assert host.ottgpu_monitor_dead_time(C.byref(mon)) == 29          # int(29.97) + 0 drift correction
+    assert host.ottgpu_monitor_dead_time(C.byref(mon)) == 29          # expected 29.97 vs 29 queued: drift 0.97 < 1, no correction yet
+    m2 = _push(rt, tv, frames[1], w, h, 900000 + 3003 * 70, interlaced=0, fps=(30000, 1001))
+    assert host.ottgpu_monitor_frame(C.byref(mon), m2) == 0
+    m3 = _push(rt, tv, frames[2], w, h, 900000 + 3003 * 71, interlaced=0, fps=(30000, 1001))
+    assert host.ottgpu_monitor_frame(C.byref(mon), m3) == 0
+    assert mon._reinit.value == 1 and signals and signals[0][0] == 0x18 and b"Filler Video Frames" in signals[0][1]
+    got = []
+    while True:
+        q = rt.dataqueue_take_back(tv.prepare_queue)
+        if not q:
+            break
+        c = q.contents
+        got.append((c.pts, c.dts, c.source_discontinuity, np.ctypeslib.as_array(C.cast(c.buffer, C.POINTER(C.c_uint8)), (frames[0].nbytes,)).copy()))
+        rt.memory_return(tv.raw_video_pool, c.buffer)
+        rt.memory_return(tv.msg_pool, q)
+    assert len(got) == 1 + 58 + 2
+    delta = 90000.0 / (30000 / 1001)
+    for k in range(1, 59):                                            # filler frames: saved picture, extrapolated stamps
+        assert got[k][0] == int(900000 + k * delta) and got[k][1] == int(900000 - 3003 + k * delta) and got[k][2] == 0
+        assert np.array_equal(got[k][3], frames[0])
+    assert got[59][2] == 1 and np.array_equal(got[59][3], frames[1])  # first real frame after the gap: discontinuity
+    assert got[60][2] == 0 and np.array_equal(got[60][3], frames[2])
+    assert mon.filler_frames == 58 and not errors
+    host.ottgpu_monitor_close(C.byref(mon))
+
+
+def test_monitor_keeps_a_device_stream_on_the_device(lib, og, oracle, rt, host):
+    """A device-resident stream (converter output tagged OTTGPU_MSG_FLAG_DEVICE): the saved frame and the filler frames
+    live in the stream's device pool, produced by device-to-device copies, and run through the channel like any frame."""
+    host.ottgpu_monitor_frame.argtypes = [C.POINTER(MON), C.POINTER(Msg)]
+    host.ottgpu_monitor_dead_time.argtypes = [C.POINTER(MON)]
+    host.ottgpu_monitor_close.argtypes = [C.POINTER(MON)]
+    w, h = 96, 64
+    errors, signals = [], []
+    tv = _make_tv(rt, [(64, 40)], errors, signals)
+    nbytes = lib.frame_bytes(og.FMT_I420, w, h)
+    pool = og.Pool(lib, 0, og.MEM_DEVICE, 80, nbytes)
+    tv.input_pool = pool.handle
+    mon = _make_mon(rt, tv, errors, signals)
+    mon.device_pool = pool.handle
+    f = natural_i420(w, h, 7)
+    buf = pool.take()
+    lib.to_device(buf, f)
+    m = C.cast(rt.memory_take(tv.msg_pool, C.sizeof(Msg)), C.POINTER(Msg))
+    C.memset(m, 0, C.sizeof(Msg))
+    m.contents.buffer, m.contents.buffer_size, m.contents.flags = buf, nbytes, 0x4f540001
+    m.contents.pts, m.contents.dts, m.contents.width, m.contents.height = 3003, 0, w, h
+    m.contents.fps_num, m.contents.fps_den = 60000, 1001              # progressive-flagged: pass-through, one frame late
+    assert host.ottgpu_monitor_frame(C.byref(mon), m) == 0
+    assert mon.saved_is_device == 1
+    assert host.ottgpu_monitor_dead_time(C.byref(mon)) == 59
+    n = 0
+    while True:                                                       # prepare/scale stage consumes real + filler frames
+        q = rt.dataqueue_take_back(tv.prepare_queue)
+        if not q:
+            break
+        assert q.contents.flags & 0xffff00ff == 0x4f540001
+        assert host.ottgpu_transvideo_process(C.byref(tv), q) == 0
+        n += 1
+    assert n == 60 and not errors
+    got = _drain(rt, tv, tv.encode_queue[0], oracle.i420_size(64, 40))
+    want = oracle.scale_i420(f, w, h, 64, 40)
+    assert len(got) == 59 and all(np.array_equal(g["data"], want) for g in got)
+    host.ottgpu_transvideo_close(C.byref(tv))
+    host.ottgpu_monitor_close(C.byref(mon))
+    assert pool.unused() == 80                                        # every device frame (saved, filler, real) went back
+    pool.close()
+
+
+# ------------------------------------------------------------------------------------------------ N1: encoder hand-off
+class ENC(C.Structure):                       # ott-packager_b200/host/encode_adapter.h
+    _fields_ = [("raw_video_pool", C.c_void_p), ("msg_pool", C.c_void_p), ("surface_pool", C.c_void_p), ("gpu", C.c_int),
+                ("width", C.c_int), ("height", C.c_int), ("fmt", C.c_int), ("pitch_align", C.c_int),
+                ("staging_pool", C.c_void_p), ("staging", C.c_void_p), ("staging_bytes", C.c_size_t),
+                ("frames", C.c_int64), ("d2h_frames", C.c_int64)]
+
+
+class PLANES(C.Structure):
+    _fields_ = [("plane", C.c_void_p * 3), ("stride", C.c_int * 3), ("planes", C.c_int)]
+
+
+class NVSURF(C.Structure):
+    _fields_ = [("device_ptr", C.c_void_p), ("chroma_offset", C.c_size_t), ("pitch", C.c_int), ("width", C.c_int),
+                ("height", C.c_int), ("fmt", C.c_int), ("gpu", C.c_int)]
+
+
+def _planes_to_i420(pl, w, h):
+    out = []
+    for k, (pw, ph) in enumerate(((w, h), ((w + 1) // 2, (h + 1) // 2), ((w + 1) // 2, (h + 1) // 2))):
+        a = np.ctypeslib.as_array(C.cast(pl.plane[k], C.POINTER(C.c_uint8)), (ph * pl.stride[k],)).reshape(ph, pl.stride[k])[:, :pw]
+        out.append(a.ravel())
+    return np.concatenate(out)
+
+
+def test_encoder_side_x264_x265_layout(lib, og, oracle, rt, host):
+    """The rung arrives at the encoder thread in the contiguous w*h*3/2 buffer transvideo.c:1330-1338 (x264 memcpy #6) and
+    960-967 (x265 plane pointers) read - from host pool buffers directly, from device surfaces through one pinned D2H."""
+    host.ottgpu_encode_map_host.argtypes = [C.POINTER(ENC), C.POINTER(Msg), C.POINTER(PLANES)]
+    host.ottgpu_encode_release.argtypes = [C.POINTER(ENC), C.POINTER(Msg)]
+    host.ottgpu_encode_adapter_close.argtypes = [C.POINTER(ENC)]
+    w, h = 192, 108
+    outs = [(128, 72), (64, 36)]
+    f = [natural_i420(w, h, 7, shift=2.0 * i) for i in range(3)]
+    for device_outputs in (0, 1):
+        errors, signals = [], []
+        tv = _make_tv(rt, outs, errors, signals)
+        pools = []
+        if device_outputs:
+            tv.device_outputs = 1
+            for k, (dw, dh) in enumerate(outs):
+                pools.append(og.Pool(lib, 0, og.MEM_DEVICE, 4, lib.rung_bytes(og.RungCfg(dw, dh, og.FMT_I420, 0))))
+                tv.surface_pool[k] = pools[k].handle
+        pool0 = rt.memory_unused(tv.raw_video_pool)
+        for i in range(3):
+            m = _push(rt, tv, f[i], w, h, 1000 * i, interlaced=0, fps=(60000, 1001))
+            assert host.ottgpu_transvideo_process(C.byref(tv), m) == 0
+        for k, (dw, dh) in enumerate(outs):
+            ad = ENC()
+            ad.raw_video_pool, ad.msg_pool = tv.raw_video_pool, tv.msg_pool
+            ad.surface_pool = pools[k].handle if device_outputs else None
+            ad.gpu, ad.width, ad.height, ad.fmt, ad.pitch_align = 0, dw, dh, og.FMT_I420, 0
+            n = 0
+            while True:
+                m = rt.dataqueue_take_back(tv.encode_queue[k])
+                if not m:
+                    break
+                pl = PLANES()
+                assert host.ottgpu_encode_map_host(C.byref(ad), m, C.byref(pl)) == 0
+                assert pl.planes == 3 and list(pl.stride) == [dw, (dw + 1) // 2, (dw + 1) // 2]      # x265 strides, 962-964
+                if not device_outputs:                                                              # x265: pointers INTO the buffer
+                    assert pl.plane[0] == m.contents.buffer and pl.plane[1] == m.contents.buffer + dw * dh
+                assert np.array_equal(_planes_to_i420(pl, dw, dh), oracle.scale_i420(f[n], w, h, dw, dh))
+                host.ottgpu_encode_release(C.byref(ad), m)
+                n += 1
+            assert n == 2 and ad.d2h_frames == (2 if device_outputs else 0)
+            host.ottgpu_encode_adapter_close(C.byref(ad))
+        assert not errors and rt.memory_unused(tv.raw_video_pool) == pool0
+        host.ottgpu_transvideo_close(C.byref(tv))
+        for p in pools:
+            assert p.unused() == 4
+            p.close()
+
+
+def test_encoder_side_nvenc_surface_descriptor(lib, og, oracle, rt, host):
+    """NVENC mode: the message carries a pitch-aligned NV12 device surface; the descriptor is what resource registration
+    needs, and the surface holds interleave(I420 target-A result) - the bytes transvideo.c:532-557 builds on the CPU
+    before av_hwframe_transfer_data (587)."""
+    host.ottgpu_encode_nvenc_surface.argtypes = [C.POINTER(ENC), C.POINTER(Msg), C.POINTER(NVSURF)]
+    host.ottgpu_encode_release.argtypes = [C.POINTER(ENC), C.POINTER(Msg)]
+    host.ottgpu_nvenc_probe.argtypes = [C.c_char_p, C.c_size_t]
+    w, h, dw, dh = 192, 108, 128, 72
+    errors, signals = [], []
+    tv = _make_tv(rt, [(dw, dh)], errors, signals)
+    tv.device_outputs, tv.out_fmt = 1, og.FMT_NV12
+    rung = og.RungCfg(dw, dh, og.FMT_NV12, 0)
+    pool = og.Pool(lib, 0, og.MEM_DEVICE, 4, lib.rung_bytes(rung))
+    tv.surface_pool[0] = pool.handle
+    f = [natural_i420(w, h, 7, shift=2.0 * i) for i in range(2)]
+    for i in range(2):
+        assert host.ottgpu_transvideo_process(C.byref(tv), _push(rt, tv, f[i], w, h, 1000 * i, interlaced=0, fps=(60000, 1001))) == 0
+    ad = ENC()
+    ad.raw_video_pool, ad.msg_pool, ad.surface_pool = tv.raw_video_pool, tv.msg_pool, pool.handle
+    ad.gpu, ad.width, ad.height, ad.fmt, ad.pitch_align = 0, dw, dh, og.FMT_NV12, 0
+    m = rt.dataqueue_take_back(tv.encode_queue[0])
+    s = NVSURF()
+    assert host.ottgpu_encode_nvenc_surface(C.byref(ad), m, C.byref(s)) == 0
+    assert (s.device_ptr, s.pitch, s.width, s.height, s.fmt, s.gpu, s.chroma_offset) == (m.contents.buffer, dw, dw, dh, og.FMT_NV12, 0, dw * dh)
+    want = oracle.i420_to_nv12(oracle.scale_i420(f[0], w, h, dw, dh), dw, dh)
+    assert np.array_equal(lib.from_device(s.device_ptr, lib.rung_bytes(rung)), want)
+    host.ottgpu_encode_release(C.byref(ad), m)
+    buf = C.create_string_buffer(256)
+    assert host.ottgpu_nvenc_probe(buf, 256) in (0, 1) and b"libnvidia-encode" in buf.value
+    host.ottgpu_transvideo_close(C.byref(tv))
+    assert pool.unused() == 4 and not errors
+    pool.close()
