@@ -155,6 +155,9 @@ void ottgpu_batch_destroy(ottgpu_batch *b);
 /* counters for bench.py: kernels launched / work items (CTAs) in the last submit */
 int  ottgpu_batch_last_launches(const ottgpu_batch *b);
 int  ottgpu_batch_last_items(const ottgpu_batch *b);
+/* host-to-device frame copies the last submit issued: consecutive buffers of one pinned ottgpu_pool going to channels of
+ * one batch travel as ONE copy per step */
+int  ottgpu_batch_last_uploads(const ottgpu_batch *b);
 /* device-side timing of the ladder launches (CUDA events recorded on the batch's stream around each launch).
  * enable != 0 starts/reset accumulation; read (after ottgpu_batch_wait) returns the summed milliseconds and count. */
 int  ottgpu_batch_timing(ottgpu_batch *b, int enable);

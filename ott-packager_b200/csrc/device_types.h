@@ -88,7 +88,8 @@ struct Binding {
     int active;              // 0: channel produces nothing this step (yadif priming) -> its items exit at once
     int thumb_active;        // thumbnail slot wanted this step
     uint32_t skip_mask;      // rung slots already produced elsewhere this step (yadif wrote the full-size rung)
-    const unsigned char *tmaps;  // CUtensorMap[kMaxRungSlots][3] (luma, U, V boxes) of this step's source frame, or null
+    const unsigned char *tmaps;  // CUtensorMap[kMaxRungSlots][3] (luma, U, V boxes) of the ARENA this step's source frame lives in, or null
+    int src_z;               // the frame's buffer index inside that arena (third tensor-map coordinate)
     const uint8_t *src[3];   // Y,U,V  or  Y,UV
     int src_pitch[3];        // bytes
     uint8_t *dst[kMaxRungSlots][3];

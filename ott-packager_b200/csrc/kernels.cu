@@ -27,12 +27,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// one 2-D box (tensor map coordinates: x in 32-bit elements, y in rows) -> shared memory, completion on `bar`
-__device__ __forceinline__ void tma_box_2d(void *dst_smem, const void *tmap, int x, int y, uint64_t *bar)
+// one box (tensor map coordinates: x in 32-bit elements, y in rows, z = buffer of the arena) -> shared memory, completion on `bar`
+__device__ __forceinline__ void tma_box_3d(void *dst_smem, const void *tmap, int x, int y, int z, uint64_t *bar)
 {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
                      smem_u32(dst_smem)),
-                 "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
+                 "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
                  : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
@@ -187,8 +187,8 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
                         fence_proxy_async();                   // the buffer was last read through the generic proxy
                         mbar_expect_tx(&ready[slot], (uint32_t)(g.staged_planes * g.box_bytes));
                         unsigned char *dst = smem + g.off_src;
-                        tma_box_2d(dst, g.tmap0, g.tma_x, g.sy0, &ready[slot]);
-                        if (g.staged_planes == 2) tma_box_2d(dst + g.plane_stride, g.tmap1, g.tma_x, g.sy0, &ready[slot]);
+                        tma_box_3d(dst, g.tmap0, g.tma_x, g.sy0, g.src_z, &ready[slot]);
+                        if (g.staged_planes == 2) tma_box_3d(dst + g.plane_stride, g.tmap1, g.tma_x, g.sy0, g.src_z, &ready[slot]);
                     }
                 } else if (lane == 0) {
                     mbar_arrive(&ready[slot]);                 // compute warps stage this tile through registers

@@ -192,7 +192,8 @@ OTT_DEV void zip16(uint32_t u, uint32_t v, uint32_t &lo, uint32_t &hi)
 // shared-memory pointers are kept in here so that the compiler keeps every shared access in the shared address space).
 struct alignas(16) TileGeom : Item {
     int off_src, off_mid, off_vc, off_vpos;   // byte offsets of the regions inside the CTA's shared memory
-    int bulk_ok;             // the tile's source window is fetched by the TMA engine (one 2-D box per plane)
+    int bulk_ok;             // the tile's source window is fetched by the TMA engine (one box per plane)
+    int src_z;               // the source frame's buffer index in its arena (third tensor-map coordinate)
     const unsigned char *tmap0, *tmap1;   // tensor maps of the plane(s)
     const uint8_t *src0, *src1;      // plane bases (chroma: U,V or the interleaved UV plane twice)
     int src_pitch0, src_pitch1;      // bytes
@@ -1085,6 +1086,7 @@ OTT_DEV int item_prepare(const Binding &b, const LadderLaunch &L, int buf, int m
     // TMA staging: the host supplied tensor maps for this frame (16-byte aligned planes) and the tile window fits one
     // box; otherwise the compute warps stage the window through registers
     g.bulk_ok = g.tma_ok && b.tmaps != nullptr;
+    g.src_z = b.src_z;
     g.tmap0 = b.tmaps + (size_t)(slot * 3 + (luma ? 0 : 1)) * kTensorMapBytes;
     g.tmap1 = b.tmaps + (size_t)(slot * 3 + 2) * kTensorMapBytes;
     return 1;

@@ -117,8 +117,15 @@ struct ottgpu_channel {
     // upload slots: the yadif window (3) + the frame being uploaded + one step of release delay, so that the upload
     // of step t+1 (copy stream) never targets a frame the kernels of step t may still read
     static constexpr int kSlots = 6;
-    uint8_t *slots[kSlots] = {nullptr};
+    // The slots of all channels of a batch live in ONE allocation: slot s of channel i at arena + (s * arena_n + i) * stride
+    // - when every channel of a step takes the same slot (the steady state) and the host frames are consecutive buffers of
+    // one pinned pool, the step's uploads are a single cudaMemcpyAsync.  A channel on its own owns an arena with arena_n = 1.
+    uint8_t *arena = nullptr;
+    size_t arena_stride = 0;
+    int arena_n = 1, arena_idx = 0;
+    bool own_arena = false;
     bool slot_used[kSlots] = {false};
+    uint8_t *slot_ptr(int s) const { return arena + ((size_t)s * arena_n + arena_idx) * arena_stride; }
     int slot_cooling = -1;                             // released last step, reusable from the next one
     FrameRef prev, cur, next;
     uint8_t *deint = nullptr;                          // yadif output when no rung surface can take it directly
@@ -127,11 +134,13 @@ struct ottgpu_channel {
     int thumb_count = 0;
     int direct_rung = -1;                              // rung whose surface is byte-identical to a deinterlaced frame
     ottgpu_batch *solo = nullptr;
-    // tensor maps (one set per distinct source-frame address this channel has seen), least recently used first out
-    struct MapSet { const uint8_t *base = nullptr; unsigned char *dev = nullptr; uint64_t stamp = 0; };
+    ottgpu_batch *member_of = nullptr;                 // the multi-channel batch whose upload arena this channel uses
+    // Tensor maps: one set per ARENA the channel's source frames come from (its upload arena, a caller's ottgpu_pool, the
+    // deinterlacer scratch): the maps are three-dimensional, {row words, rows, buffer index}, so any buffer of the arena
+    // is addressed by the z coordinate and no map is ever encoded, uploaded or evicted on the frame path.
+    struct MapSet { const uint8_t *base = nullptr; size_t stride = 0; unsigned char *dev = nullptr; };
     std::vector<MapSet> maps;
     unsigned char *maps_pool = nullptr;                // all sets in one allocation made at creation (no cudaMalloc mid-stream)
-    uint64_t map_clock = 0;
     bool wants_maps = false;
 };
 
@@ -162,7 +171,11 @@ struct ottgpu_batch {
     std::vector<size_t> thumb_offset;                      // per channel, into Set::h_thumbs
     size_t thumb_stage_bytes = 0;
     int turn = 0;
-    int last_launches = 0, last_items = 0;
+    int last_launches = 0, last_items = 0, last_uploads = 0;
+    uint8_t *arena = nullptr;                              // upload slots of all channels (when they share a frame size)
+    size_t arena_stride = 0;
+    struct Upload { uint8_t *dst; const void *src; size_t bytes; };
+    std::vector<Upload> uploads;
     bool timing = false;
     double ms_sum = 0.0, yadif_ms_sum = 0.0;
     int ms_count = 0, yadif_ms_count = 0;
@@ -187,19 +200,61 @@ void release_frame(ottgpu_channel *c, const FrameRef &f, ottgpu_frame_out *out)
     else if (out && out->n_released < 4) out->released[out->n_released++] = f.dev;
 }
 
+size_t arena_stride_for(size_t bytes) { return (bytes + 255) & ~(size_t)255; }      // = ottgpu_pool's buffer stride
+
 int take_slot(ottgpu_channel *c)
 {
+    if (!c->arena) {                                   // a channel that uploads for the first time outside a shared arena
+        c->arena_stride = arena_stride_for(c->src_bytes);
+        c->arena_n = 1;
+        c->arena_idx = 0;
+        if (cudaMalloc((void **)&c->arena, ottgpu_channel::kSlots * c->arena_stride + 64) != cudaSuccess) {
+            cudaGetLastError();
+            c->arena = nullptr;
+            return -1;
+        }
+        c->own_arena = true;
+    }
     for (int i = 0; i < ottgpu_channel::kSlots; ++i)
         if (!c->slot_used[i]) {
-            if (!c->slots[i] && cudaMalloc((void **)&c->slots[i], c->src_bytes + 64) != cudaSuccess) {
-                cudaGetLastError();
-                return -1;
-            }
             c->slot_used[i] = true;
             return i;
         }
     return -1;
 }
+
+// device pools created through ottgpu_pool_create: a frame pointer inside one of them is (pool base, stride, index)
+struct PoolSpan { const uint8_t *base; size_t stride; int count; int gpu; };
+std::mutex g_pools_mu;
+std::vector<PoolSpan> g_pools, g_host_pools;
+
+// both addresses inside one pinned host pool created through ottgpu_pool_create
+bool same_host_pool(const void *a, const void *b)
+{
+    std::lock_guard<std::mutex> lock(g_pools_mu);
+    for (const PoolSpan &s : g_host_pools) {
+        const uint8_t *lo = s.base, *hi = s.base + s.stride * s.count;
+        if ((const uint8_t *)a >= lo && (const uint8_t *)a < hi) return (const uint8_t *)b >= lo && (const uint8_t *)b < hi;
+    }
+    return false;
+}
+
+#if !defined(OTTGPU_EMULATE)
+bool find_span(const ottgpu_channel *c, const uint8_t *p, PoolSpan &out)
+{
+    if (c->arena && p >= c->arena && p < c->arena + (size_t)ottgpu_channel::kSlots * c->arena_n * c->arena_stride) {
+        out = {c->arena, c->arena_stride, ottgpu_channel::kSlots * c->arena_n, c->gpu};
+        return true;
+    }
+    std::lock_guard<std::mutex> lock(g_pools_mu);
+    for (const PoolSpan &s : g_pools)
+        if (s.gpu == c->gpu && p >= s.base && p < s.base + s.stride * s.count) {
+            out = s;
+            return true;
+        }
+    return false;
+}
+#endif
 
 int ensure_dev(uint8_t **p, size_t bytes)
 {
@@ -211,46 +266,46 @@ int ensure_dev(uint8_t **p, size_t bytes)
     return OTTGPU_OK;
 }
 
-// Tensor maps for the frame at `base` (device memory, packed planar 8-bit): one box per scaled rung plane.
-// Returns null when TMA cannot be used for this frame (alignment) -- the kernel then stages through registers.
-int frame_tensor_maps(ottgpu_channel *c, const uint8_t *base, cudaStream_t stream, const unsigned char **out)
+// Tensor maps for the frame at `frame` (device memory, packed planar): one 3-D box shape per scaled rung plane, shared by
+// every buffer of the arena the frame lives in; *z is the frame's index inside that arena.
+// Returns null maps when TMA cannot be used for this frame (alignment, or more distinct arenas than the channel keeps
+// sets for) -- the kernel then stages through registers; nothing on this path synchronises the device.
+int frame_tensor_maps(ottgpu_channel *c, const uint8_t *frame, cudaStream_t stream, const unsigned char **out, int *z)
 {
     *out = nullptr;
+    *z = 0;
 #if !defined(OTTGPU_EMULATE)
     if (!c->wants_maps) return OTTGPU_OK;
     const ottgpu_cfg &cfg = c->cfg;
+    PoolSpan span;
+    if (!find_span(c, frame, span)) span = {frame, arena_stride_for(c->src_bytes), 1, c->gpu};   // a lone buffer: arena of one
+    const size_t idx = (size_t)(frame - span.base) / span.stride;
+    if (span.base + idx * span.stride != frame || (span.stride & 15)) return OTTGPU_OK;        // not at a buffer start
     const uint8_t *pl[3];
     int pitch[3];
-    plane_ptrs(cfg.src_fmt, base, cfg.src_width, cfg.src_height, pl, pitch);
+    plane_ptrs(cfg.src_fmt, span.base, cfg.src_width, cfg.src_height, pl, pitch);
     for (int k = 0; k < (cfg.src_fmt == OTTGPU_FMT_P010 ? 2 : 3); ++k)
         if (((uintptr_t)pl[k] | (uintptr_t)pitch[k]) & 15) return OTTGPU_OK;
+    *z = (int)idx;
     for (auto &m : c->maps)
-        if (m.base == base) {
-            m.stamp = ++c->map_clock;
+        if (m.base == span.base && m.stride == span.stride) {
             *out = m.dev;
             return OTTGPU_OK;
         }
     constexpr size_t kSetBytes = (size_t)kMaxRungSlots * 3 * kTensorMapBytes;
-    constexpr size_t kMaxSets = 24;
-    ottgpu_channel::MapSet *slot = nullptr;
-    if (c->maps.size() < kMaxSets) {
-        if (!c->maps_pool && cudaMalloc((void **)&c->maps_pool, kMaxSets * kSetBytes) != cudaSuccess) {
-            cudaGetLastError();
-            return fail(OTTGPU_ERR_NOMEM, "cudaMalloc(tensor maps) failed");
-        }
-        c->maps.emplace_back();
-        slot = &c->maps.back();
-        slot->dev = c->maps_pool + (c->maps.size() - 1) * kSetBytes;
-    } else {
-        slot = &c->maps[0];
-        for (auto &m : c->maps)
-            if (m.stamp < slot->stamp) slot = &m;
-        CK(cudaDeviceSynchronize());                   // rare: a launch in flight (any stream) may still read the evicted set
+    constexpr size_t kMaxSets = 8;
+    if (c->maps.size() >= kMaxSets) return OTTGPU_OK;   // more source arenas than sets: this frame is staged through registers
+    if (!c->maps_pool && cudaMalloc((void **)&c->maps_pool, kMaxSets * kSetBytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(OTTGPU_ERR_NOMEM, "cudaMalloc(tensor maps) failed");
     }
+    c->maps.emplace_back();
+    ottgpu_channel::MapSet *slot = &c->maps.back();
+    slot->dev = c->maps_pool + (c->maps.size() - 1) * kSetBytes;
     alignas(64) static thread_local CUtensorMap host[kMaxRungSlots * 3];
     std::memset(host, 0, sizeof(host));
     const Plan &plan = *c->plan;
-    // planes as 2-D arrays of 32-bit elements: {elements per row, rows}; P010 has Y and the interleaved UV plane
+    // planes as 3-D arrays of 32-bit elements: {elements per row, rows, buffers}; P010 has Y and the interleaved UV plane
     const int cw = (cfg.src_width + 1) / 2, chh = (cfg.src_height + 1) / 2, bps = fmt_bps(cfg.src_fmt);
     const bool semi = cfg.src_fmt == OTTGPU_FMT_P010;
     const int nmaps = semi ? 2 : 3;
@@ -262,23 +317,26 @@ int frame_tensor_maps(ottgpu_channel *c, const uint8_t *base, cudaStream_t strea
         for (int k = 0; k < nmaps; ++k) {
             const PlaneTables &T = k ? R.chroma : R.luma;
             if (!T.tma_ok) continue;
-            const cuuint64_t gdim[2] = {(cuuint64_t)(row_bytes[k] / 4), (cuuint64_t)rows[k]};
-            const cuuint64_t gstride[1] = {(cuuint64_t)pitch[k]};
-            const cuuint32_t box[2] = {(cuuint32_t)T.sw_words, (cuuint32_t)T.sr_max};
-            const cuuint32_t estride[2] = {1, 1};
-            const CUresult r = g_encode_tiled(&host[s * 3 + k], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void *)pl[k], gdim, gstride, box,
+            const cuuint64_t gdim[3] = {(cuuint64_t)(row_bytes[k] / 4), (cuuint64_t)rows[k], (cuuint64_t)span.count};
+            const cuuint64_t gstride[2] = {(cuuint64_t)pitch[k], (cuuint64_t)span.stride};
+            const cuuint32_t box[3] = {(cuuint32_t)T.sw_words, (cuuint32_t)T.sr_max, 1};
+            const cuuint32_t estride[3] = {1, 1, 1};
+            const CUresult r = g_encode_tiled(&host[s * 3 + k], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)pl[k], gdim, gstride, box,
                                               estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) return fail(OTTGPU_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+            if (r != CUDA_SUCCESS) {
+                c->maps.pop_back();
+                return fail(OTTGPU_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+            }
         }
     }
     CK(cudaMemcpyAsync(slot->dev, host, kSetBytes, cudaMemcpyHostToDevice, stream));
-    slot->base = base;
-    slot->stamp = ++c->map_clock;
+    slot->base = span.base;
+    slot->stride = span.stride;
     *out = slot->dev;
 #else
     (void)c;
-    (void)base;
+    (void)frame;
     (void)stream;
 #endif
     return OTTGPU_OK;
@@ -473,7 +531,10 @@ void ottgpu_channel_destroy(ottgpu_channel *ch)
     cudaSetDevice(ch->gpu);
     cudaStreamSynchronize(ch->stream);
     if (ch->solo) ottgpu_batch_destroy(ch->solo);
-    for (uint8_t *p : ch->slots) cudaFree(p);
+    if (ch->member_of)                                 // destroyed before its batch: the batch must not touch it any more
+        for (ottgpu_channel *&p : ch->member_of->ch)
+            if (p == ch) p = nullptr;
+    if (ch->own_arena) cudaFree(ch->arena);
     cudaFree(ch->deint);
     for (auto &set : ch->stage)
         for (uint8_t *p : set) cudaFree(p);
@@ -531,6 +592,30 @@ static int batch_build(ottgpu_batch *b, ottgpu_channel **channels, int n)
         if (c->solo) c->solo->stream = b->stream;
     }
     if (n > 1) channels[0]->own_stream = false;
+    {
+        // one upload arena for the whole batch when every channel has the same frame size and none holds frames yet
+        bool same = true, fresh = true;
+        for (int i = 0; i < n; ++i) {
+            same = same && channels[i]->src_bytes == channels[0]->src_bytes;
+            for (bool used : channels[i]->slot_used) fresh = fresh && !used;
+            fresh = fresh && !channels[i]->prev.valid && !channels[i]->cur.valid && !channels[i]->next.valid;
+        }
+        if (n > 1 && same && fresh) {
+            b->arena_stride = arena_stride_for(channels[0]->src_bytes);
+            CK(cudaMalloc((void **)&b->arena, (size_t)ottgpu_channel::kSlots * n * b->arena_stride + 64));
+            for (int i = 0; i < n; ++i) {
+                ottgpu_channel *c = channels[i];
+                if (c->own_arena) cudaFree(c->arena);
+                c->own_arena = false;
+                c->arena = b->arena;
+                c->arena_stride = b->arena_stride;
+                c->arena_n = n;
+                c->arena_idx = i;
+                c->member_of = b;
+                c->maps.clear();                           // sets keyed on the old arena are stale
+            }
+        }
+    }
     CK(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&b->readback_stream, cudaStreamNonBlocking));
     std::vector<Item> all, big;
@@ -592,6 +677,18 @@ void ottgpu_batch_destroy(ottgpu_batch *b)
         cudaStreamSynchronize(b->readback_stream);
         cudaStreamDestroy(b->readback_stream);
     }
+    if (b->arena) {
+        for (ottgpu_channel *c : b->ch)
+            if (c && c->arena == b->arena) {               // the channel outlives the batch: it starts over with an arena of its own
+                c->arena = nullptr;
+                c->member_of = nullptr;
+                c->maps.clear();
+                for (bool &u : c->slot_used) u = false;
+                c->slot_cooling = -1;
+                c->prev = c->cur = c->next = FrameRef();
+            }
+        cudaFree(b->arena);
+    }
     cudaFree(b->d_items);
     cudaFree(b->d_big_items);
     for (ottgpu_batch::Set &st : b->set) {
@@ -617,6 +714,7 @@ void ottgpu_batch_destroy(ottgpu_batch *b)
 
 int ottgpu_batch_last_launches(const ottgpu_batch *b) { return b ? b->last_launches : 0; }
 int ottgpu_batch_last_items(const ottgpu_batch *b) { return b ? b->last_items : 0; }
+int ottgpu_batch_last_uploads(const ottgpu_batch *b) { return b ? b->last_uploads : 0; }
 
 }  // extern "C"
 
@@ -711,6 +809,8 @@ int ottgpu_batch_submit(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame
     if (!b || !in || !out) return fail(OTTGPU_ERR_ARG, "null argument");
     CK(cudaSetDevice(b->gpu));
     const int n = (int)b->ch.size(), turn = b->turn;
+    for (int i = 0; i < n; ++i)
+        if (!b->ch[i]) return fail(OTTGPU_ERR_STATE, "a channel of this batch has been destroyed");
     std::vector<ChannelState> saved(n);
     for (int i = 0; i < n; ++i) {
         const ottgpu_channel *c = b->ch[i];
@@ -770,9 +870,11 @@ int batch_submit_body(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame_o
     // uploads of this step may overwrite slots last read two steps ago: order the copy stream after that step only
     // (this set's previous use was retired above; the other set = the previous step may still be running)
     int n_jobs = 0, n_thumb_items = 0, n_thumb_items16 = 0, max_w = 0, max_h = 0, live = 0;
+    std::vector<ottgpu_batch::Upload> &uploads = b->uploads;
+    uploads.clear();
     bool all_fast = true;
     b->readbacks.clear();
-    b->last_launches = b->last_items = 0;
+    b->last_launches = b->last_items = b->last_uploads = 0;
 
     for (int i = 0; i < n; ++i) {
         ottgpu_channel *c = b->ch[i];
@@ -804,8 +906,8 @@ int batch_submit_body(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame_o
         if (in[i].mem == OTTGPU_MEM_HOST) {
             f.slot = take_slot(c);
             if (f.slot < 0) return fail(OTTGPU_ERR_NOMEM, "no device slot for the incoming frame");
-            f.dev = c->slots[f.slot];
-            CK(cudaMemcpyAsync(c->slots[f.slot], in[i].data, c->src_bytes, cudaMemcpyHostToDevice, b->copy_stream));
+            f.dev = c->slot_ptr(f.slot);
+            uploads.push_back({c->slot_ptr(f.slot), in[i].data, c->src_bytes});
         } else if (in[i].mem == OTTGPU_MEM_DEVICE) {
             f.dev = static_cast<const uint8_t *>(in[i].data);
         } else {
@@ -887,7 +989,7 @@ int batch_submit_body(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame_o
         }
         plane_ptrs(cfg.src_fmt, src_base, cfg.src_width, cfg.src_height, bind.src, bind.src_pitch);
         {
-            int rc = frame_tensor_maps(c, src_base, in[i].mem == OTTGPU_MEM_HOST ? b->copy_stream : s, &bind.tmaps);
+            int rc = frame_tensor_maps(c, src_base, b->copy_stream, &bind.tmaps, &bind.src_z);
             if (rc) return rc;
         }
         bind.active = 1;
@@ -934,6 +1036,21 @@ int batch_submit_body(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame_o
     // of sitting between two launches on the compute stream; with host frames in flight they also stay behind this step's
     // uploads instead of queueing behind the NEXT step's bulk uploads in the H2D copy engine.
     cudaStream_t ds = b->copy_stream;
+    // Frame uploads: consecutive host buffers going to consecutive arena slots are merged into one copy (the steady state
+    // of a batch fed from one pinned pool: ONE cudaMemcpyAsync per step instead of one per channel)
+    for (size_t u = 0; u < uploads.size();) {
+        size_t v = u + 1;
+        size_t bytes = uploads[u].bytes;
+        while (v < uploads.size() && b->arena_stride && uploads[v].dst == uploads[v - 1].dst + b->arena_stride &&
+               (const uint8_t *)uploads[v].src == (const uint8_t *)uploads[v - 1].src + b->arena_stride &&
+               same_host_pool(uploads[u].src, uploads[v].src)) {
+            bytes = (size_t)(uploads[v].dst - uploads[u].dst) + uploads[v].bytes;
+            ++v;
+        }
+        CK(cudaMemcpyAsync(uploads[u].dst, uploads[u].src, bytes, cudaMemcpyHostToDevice, ds));
+        b->last_uploads++;
+        u = v;
+    }
     CK(cudaMemcpyAsync(st.d_binds, st.h_binds, n * sizeof(Binding), cudaMemcpyHostToDevice, ds));
     if (n_jobs) CK(cudaMemcpyAsync(st.d_jobs, st.h_jobs, n * sizeof(YadifJob), cudaMemcpyHostToDevice, ds));
     if (n_thumb_items) CK(cudaMemcpyAsync(st.d_thumb_items, st.h_thumb_items, n_thumb_items * sizeof(Item), cudaMemcpyHostToDevice, ds));
@@ -1047,6 +1164,10 @@ int ottgpu_pool_create(int gpu, int mem, int buffer_count, size_t buffer_size, o
     }
     p->taken.assign(buffer_count, false);
     for (int i = buffer_count - 1; i >= 0; --i) p->free_list.push_back(p->base + (size_t)i * p->size);
+    {
+        std::lock_guard<std::mutex> lock(g_pools_mu);
+        (mem == OTTGPU_MEM_DEVICE ? g_pools : g_host_pools).push_back({p->base, p->size, buffer_count, gpu});
+    }
     *out = p.release();
     return OTTGPU_OK;
 }
@@ -1086,6 +1207,12 @@ void ottgpu_pool_destroy(ottgpu_pool *p)
 {
     if (!p) return;
     cudaSetDevice(p->gpu);
+    {
+        std::lock_guard<std::mutex> lock(g_pools_mu);
+        std::vector<PoolSpan> &reg = p->mem == OTTGPU_MEM_DEVICE ? g_pools : g_host_pools;
+        for (size_t i = 0; i < reg.size(); ++i)
+            if (reg[i].base == p->base) { reg.erase(reg.begin() + i); break; }
+    }
     if (p->mem == OTTGPU_MEM_DEVICE) cudaFree(p->base);
     else cudaFreeHost(p->base);
     delete p;

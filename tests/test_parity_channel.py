@@ -426,3 +426,71 @@ def test_filter_table_refuses_more_taps_than_the_callers_buffer_holds(real_lib, 
     coef = (C.c_int16 * (144 * 256))()
     assert real_lib.dll.ottgpu_filter_table(16384, 144, og.FILTER_BICUBIC, og.TARGET_A, 0, pos, coef) == og.ERR_ARG
     assert real_lib.dll.ottgpu_filter_table(1080, 144, og.FILTER_BICUBIC, og.TARGET_A, 1, pos, coef) == 30
+
+
+def test_zero_copy_inputs_from_a_large_pool_never_stall(lib, og, oracle):
+    """The reference's raw pool hands out a fresh address on every memory_take (mempool.c:196-198, 512 buffers,
+    fillet.h:84).  Device-resident input frames cycling through 72 distinct pool buffers go through ONE set of tensor
+    maps (three-dimensional, the buffer index is a coordinate): no per-address encode, no device-wide synchronisation,
+    bit-exact rungs; the frame path stays fast (time bound) instead of re-encoding / syncing per frame."""
+    import time
+    w, h = 192, 108
+    rungs = [(128, 72, og.FMT_I420), (96, 54, og.FMT_NV12)]
+    ch = og.Channel(lib, og.make_cfg(w, h, rungs, deint=og.DEINT_ALL))
+    nb = 72
+    pool = og.Pool(lib, 0, og.MEM_DEVICE, nb, lib.frame_bytes(og.FMT_I420, w, h))
+    bufs = [pool.take() for _ in range(nb)]
+    assert len(set(bufs)) == nb
+    frames = interlaced_sequence(w, h, 6, seed=31)
+    ref = oracle.YadifStream(w, h)
+    t_first, t_rest = None, 0.0
+    for i in range(nb):
+        f = frames[i % 6]
+        lib.to_device(bufs[i], f)
+        t0 = time.perf_counter()
+        r = ch.submit(bufs[i], interlaced=1, tff=1)
+        dt = time.perf_counter() - t0
+        if i < 4:
+            t_first = dt if t_first is None else max(t_first, dt)
+        else:
+            t_rest += dt
+        want = ref.push(f, 1, 1)
+        assert (r is None) == (want is None)
+        if want is not None:
+            for got, exp in zip(r["rungs"], _oracle_ladder(oracle, want[0], w, h, rungs, og)):
+                assert np.array_equal(got, exp)
+    # steady state: no call may cost anywhere near a device-wide sync + tensor-map re-encode per frame
+    assert t_rest / (nb - 4) < 0.05
+    ch.close()
+    pool.close()
+
+
+def test_batch_uploads_travel_as_one_copy(lib, og, oracle):
+    """Host frames that are consecutive buffers of one pinned pool reach the batch's upload arena in a single
+    cudaMemcpyAsync per step (the per-GPU H2D of N channels is one DMA, not N)."""
+    w, h, n = 96, 64, 5
+    rungs = [(64, 40, og.FMT_I420)]
+    chans = [og.Channel(lib, og.make_cfg(w, h, rungs, deint=og.DEINT_FLAGGED)) for _ in range(n)]
+    batch = og.Batch(lib, chans)
+    nbytes = lib.frame_bytes(og.FMT_I420, w, h)
+    hpool = og.Pool(lib, 0, og.MEM_HOST, 2 * n, nbytes)
+    host = [[hpool.take() for _ in range(n)] for _ in range(2)]          # one phase = n consecutive pool buffers
+    frames = [[natural_i420(w, h, 7, shift=1.0 * (3 * s + c)) for c in range(n)] for s in range(4)]
+    outs = [np.zeros(chans[0].rung_bytes[0], np.uint8) for _ in range(n)]
+    import ctypes as C
+    for s in range(4):
+        for c in range(n):
+            C.memmove(host[s % 2][c], frames[s][c].ctypes.data, nbytes)
+            batch.fin[c].data, batch.fin[c].mem = host[s % 2][c], og.MEM_HOST
+            batch.fin[c].interlaced, batch.fin[c].tff = 0, 1
+            batch.fout[c].dst[0], batch.fout[c].dst_mem[0] = outs[c].ctypes.data, og.MEM_HOST
+        batch.submit_raw(og.SUBMIT_SYNC)
+        assert batch.last_uploads == 1
+        if s:
+            for c in range(n):
+                assert batch.fout[c].produced == 1
+                assert np.array_equal(outs[c], oracle.scale_i420(frames[s - 1][c], w, h, 64, 40))
+    batch.close()
+    for c in chans:
+        c.close()
+    hpool.close()
