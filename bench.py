@@ -495,7 +495,8 @@ def run_workload(cx, name, Cn, steps, warmup, repeats, do_e2e, do_parity):
 
     # ---------------- end-to-end arms (host pinned source frames through the C ABI)
     if do_e2e:
-        host_pool = og.Pool(lib, local_rank, og.MEM_HOST, Cn * 2, src_bytes)
+        # OTT_WC=1: the upload ring in write-combined pinned memory (the CPU only writes it)
+        host_pool = og.Pool(lib, local_rank, og.MEM_HOST_WC if os.environ.get("OTT_WC") == "1" else og.MEM_HOST, Cn * 2, src_bytes)
         host_src = [[None, None] for _ in range(Cn)]
         for r in range(2):                                   # one phase's frames of all channels are contiguous in pinned memory
             for c in range(Cn):
@@ -564,6 +565,11 @@ def ours_main(args, wl, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; libottgpu has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    if os.environ.get("OTT_PIN") == "1":                     # experiment: each rank on its own share of the host cores
+        cores = sorted(os.sched_getaffinity(0))
+        mine = cores[local_rank::max(world, 1)]
+        if mine:
+            os.sched_setaffinity(0, mine)
     dist = None
     if world > 1:
         # keep stdout to the single JSON line: NCCL prints its version banner there at VERSION/INFO level

@@ -43,7 +43,9 @@ enum {
     OTTGPU_DEINT_FLAGGED = 1,  /* "yadif=0:-1:1"  transvideo.c:2036-2044 (fps_num 60000|50000: only flagged frames) */
     OTTGPU_DEINT_BYPASS = 2    /* no deinterlacer stage at all, zero latency (plain sws_scale replacement)          */
 };
-enum { OTTGPU_MEM_HOST = 0, OTTGPU_MEM_DEVICE = 1 };
+enum { OTTGPU_MEM_HOST = 0, OTTGPU_MEM_DEVICE = 1,
+       OTTGPU_MEM_HOST_WC = 2 /* ottgpu_pool_create only: pinned write-combined host memory for upload rings the CPU only
+                                 writes (no cache snooping on the GPU's DMA reads); frames from it are OTTGPU_MEM_HOST */ };
 
 /* error codes (functions return 0 on success, <0 on error; nothing in the library ever calls exit()) */
 enum {

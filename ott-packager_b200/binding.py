@@ -16,7 +16,7 @@ FMT_I420, FMT_NV12, FMT_P010, FMT_I420P10 = 0, 1, 2, 3
 FILTER_BICUBIC, FILTER_LANCZOS = 0, 1
 TARGET_A, TARGET_B = 0, 1
 DEINT_ALL, DEINT_FLAGGED, DEINT_BYPASS = 0, 1, 2
-MEM_HOST, MEM_DEVICE = 0, 1
+MEM_HOST, MEM_DEVICE, MEM_HOST_WC = 0, 1, 2
 SUBMIT_SYNC, SUBMIT_ASYNC = 0, 1
 OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_STATE = 0, -1, -2, -3, -4
 PIX_YUV420P, PIX_YUV422P, PIX_YUV420P10, PIX_YUV422P10 = 0, 1, 2, 3

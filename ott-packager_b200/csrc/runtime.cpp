@@ -1156,8 +1156,9 @@ int ottgpu_pool_create(int gpu, int mem, int buffer_count, size_t buffer_size, o
     p->mem = mem;
     p->count = buffer_count;
     p->size = (buffer_size + 255) & ~(size_t)255;      // every buffer 256-byte aligned: vector stores stay legal
+    if (mem != OTTGPU_MEM_DEVICE && mem != OTTGPU_MEM_HOST && mem != OTTGPU_MEM_HOST_WC) return fail(OTTGPU_ERR_ARG, "bad pool memory kind");
     cudaError_t e = mem == OTTGPU_MEM_DEVICE ? cudaMalloc((void **)&p->base, p->size * buffer_count)
-                                             : cudaMallocHost((void **)&p->base, p->size * buffer_count);
+                    : cudaHostAlloc((void **)&p->base, p->size * buffer_count, mem == OTTGPU_MEM_HOST_WC ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return fail(OTTGPU_ERR_NOMEM, "pool allocation failed");

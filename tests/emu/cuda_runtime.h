@@ -22,6 +22,8 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) { p->major = 
 inline cudaError_t cudaMalloc(void **p, size_t n) { *p = std::calloc(1, n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 inline cudaError_t cudaFree(void *p) { std::free(p); return cudaSuccess; }
 inline cudaError_t cudaMallocHost(void **p, size_t n) { return cudaMalloc(p, n); }
+enum { cudaHostAllocDefault = 0, cudaHostAllocWriteCombined = 4 };
+inline cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { return cudaMalloc(p, n); }
 inline cudaError_t cudaFreeHost(void *p) { return cudaFree(p); }
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { std::memcpy(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memcpy(d, s, n); return cudaSuccess; }
