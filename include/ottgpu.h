@@ -160,6 +160,10 @@ int  ottgpu_batch_last_items(const ottgpu_batch *b);
 /* host-to-device frame copies the last submit issued: consecutive buffers of one pinned ottgpu_pool going to channels of
  * one batch travel as ONE copy per step */
 int  ottgpu_batch_last_uploads(const ottgpu_batch *b);
+/* device-to-host copies the last submit issued for host-destined rungs and thumbnails: the surfaces of one rung of all
+ * channels live in one device allocation, so channels whose destinations are consecutive buffers of one pinned
+ * ottgpu_pool are read back with ONE copy per rung (the x264/x265 hand-off of transvideo.c:1610-1624 for N channels) */
+int  ottgpu_batch_last_readbacks(const ottgpu_batch *b);
 /* device-side timing of the ladder launches (CUDA events recorded on the batch's stream around each launch).
  * enable != 0 starts/reset accumulation; read (after ottgpu_batch_wait) returns the summed milliseconds and count. */
 int  ottgpu_batch_timing(ottgpu_batch *b, int enable);

@@ -74,6 +74,7 @@ _SIGS = {
     "ottgpu_channel_describe": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "ottgpu_channel_pending_opaque": (C.c_void_p, [C.c_void_p]),
     "ottgpu_batch_last_uploads": (C.c_int, [C.c_void_p]),
+    "ottgpu_batch_last_readbacks": (C.c_int, [C.c_void_p]),
     "ottgpu_batch_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]),
     "ottgpu_batch_submit": (C.c_int, [C.c_void_p, C.POINTER(FrameIn), C.POINTER(FrameOut), C.c_int]),
     "ottgpu_batch_wait": (C.c_int, [C.c_void_p]),
@@ -117,7 +118,7 @@ class Library:
             try:
                 fn = getattr(self.dll, name)
             except AttributeError:
-                if name in ("ottgpu_build_info", "ottgpu_channel_pending_opaque", "ottgpu_batch_last_uploads"):     # absent from older A/B builds
+                if name in ("ottgpu_build_info", "ottgpu_channel_pending_opaque", "ottgpu_batch_last_uploads", "ottgpu_batch_last_readbacks"):     # absent from older A/B builds
                     continue
                 raise
             fn.restype, fn.argtypes = res, args
@@ -404,6 +405,10 @@ class Batch:
     @property
     def last_uploads(self):
         return self.lib.dll.ottgpu_batch_last_uploads(self.handle)
+
+    @property
+    def last_readbacks(self):
+        return self.lib.dll.ottgpu_batch_last_readbacks(self.handle)
 
 
 class Pool:

@@ -179,8 +179,15 @@ struct ottgpu_batch {
     bool timing = false;
     double ms_sum = 0.0, yadif_ms_sum = 0.0;
     int ms_count = 0, yadif_ms_count = 0;
-    struct Readback { void *host; const uint8_t *dev; size_t bytes; };
+    struct Readback { void *host; const uint8_t *dev; size_t bytes; int rung; };
     std::vector<Readback> readbacks;
+    // Device surfaces of host-destined rungs, one allocation per rung and descriptor set: channel i's surface of rung r at
+    // stage_arena[set][r] + i * stage_stride[r] (stride = the largest channel's surface, 256-byte aligned = ottgpu_pool's
+    // buffer stride).  Consecutive channels landing in consecutive buffers of one pinned pool are read back with ONE copy per
+    // rung instead of one per channel per rung.
+    uint8_t *stage_arena[2][kMaxRungs] = {{nullptr}, {nullptr}};
+    size_t stage_stride[kMaxRungs] = {0};
+    int last_readbacks = 0;
 };
 
 namespace {
@@ -633,6 +640,8 @@ static int batch_build(ottgpu_batch *b, ottgpu_channel **channels, int n)
             b->mid_max[k] = std::max(b->mid_max[k], p.mid_max[k]);
             b->vc_max[k] = std::max(b->vc_max[k], p.vc_max[k]);
         }
+        for (int r = 0; r < channels[i]->cfg.n_rungs && r < kMaxRungs; ++r)
+            b->stage_stride[r] = std::max(b->stage_stride[r], arena_stride_for(p.layout[r].bytes + 64));
         b->max_thumb_items += (int)p.thumb_items.size();
         b->thumb_offset.push_back(b->thumb_stage_bytes);
         if (p.thumb_slot >= 0) b->thumb_stage_bytes += (p.layout[p.thumb_slot].bytes + 63) & ~(size_t)63;
@@ -691,6 +700,8 @@ void ottgpu_batch_destroy(ottgpu_batch *b)
     }
     cudaFree(b->d_items);
     cudaFree(b->d_big_items);
+    for (auto &per_set : b->stage_arena)
+        for (uint8_t *a : per_set) cudaFree(a);
     for (ottgpu_batch::Set &st : b->set) {
         cudaFree(st.d_thumb_items);
         cudaFree(st.d_binds);
@@ -715,6 +726,7 @@ void ottgpu_batch_destroy(ottgpu_batch *b)
 int ottgpu_batch_last_launches(const ottgpu_batch *b) { return b ? b->last_launches : 0; }
 int ottgpu_batch_last_items(const ottgpu_batch *b) { return b ? b->last_items : 0; }
 int ottgpu_batch_last_uploads(const ottgpu_batch *b) { return b ? b->last_uploads : 0; }
+int ottgpu_batch_last_readbacks(const ottgpu_batch *b) { return b ? b->last_readbacks : 0; }
 
 }  // extern "C"
 
@@ -946,10 +958,10 @@ int batch_submit_body(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame_o
             if (o.dst_mem[r] == OTTGPU_MEM_DEVICE) {
                 base = static_cast<uint8_t *>(o.dst[r]);
             } else {
-                int rc = ensure_dev(&c->stage[turn][r], plan.layout[r].bytes);
+                int rc = ensure_dev(&b->stage_arena[turn][r], b->stage_stride[r] * n);
                 if (rc) return rc;
-                base = c->stage[turn][r];
-                b->readbacks.push_back({o.dst[r], base, plan.layout[r].bytes});
+                base = b->stage_arena[turn][r] + (size_t)i * b->stage_stride[r];
+                b->readbacks.push_back({o.dst[r], base, plan.layout[r].bytes, r});
             }
             if (!base || (o.dst_mem[r] != OTTGPU_MEM_DEVICE && !o.dst[r])) return fail(OTTGPU_ERR_ARG, "missing destination buffer");
             for (int p = 0; p < plan.layout[r].planes; ++p) {
@@ -1013,7 +1025,7 @@ int batch_submit_body(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame_o
             if (!host) return fail(OTTGPU_ERR_NOMEM, "malloc(thumbnail) failed");
             o.thumbnail = host;
             uint8_t *landing = st.h_thumbs + b->thumb_offset[i];
-            b->readbacks.push_back({landing, c->stage[turn][ts], plan.layout[ts].bytes});
+            b->readbacks.push_back({landing, c->stage[turn][ts], plan.layout[ts].bytes, kMaxRungs});
             st.pending_thumbs.push_back({host, landing, plan.layout[ts].bytes});
             // 8-bit channels' items fill the list from the front, 16-bit ones from the back
             for (Item it : plan.thumb_items) {
@@ -1119,8 +1131,34 @@ int batch_submit_body(ottgpu_batch *b, const ottgpu_frame_in *in, ottgpu_frame_o
         // results for host destinations leave on their own stream: the next step's kernels do not wait for them
         CK(cudaEventRecord(st.computed, s));
         CK(cudaStreamWaitEvent(b->readback_stream, st.computed, 0));
-        for (const ottgpu_batch::Readback &r : b->readbacks)
-            CK(cudaMemcpyAsync(r.host, r.dev, r.bytes, cudaMemcpyDeviceToHost, b->readback_stream));
+        // rung by rung; a run of channels whose surfaces and host buffers advance by constant strides is one copy (linear when
+        // both strides equal the surface size, else a pitched copy with one "row" per channel)
+        std::vector<ottgpu_batch::Readback> &rb = b->readbacks;
+        std::stable_sort(rb.begin(), rb.end(), [](const ottgpu_batch::Readback &x, const ottgpu_batch::Readback &y) { return x.rung < y.rung; });
+        b->last_readbacks = 0;
+        for (size_t u = 0; u < rb.size();) {
+            size_t v = u + 1;
+            ptrdiff_t ds = 0, hs = 0;
+            if (v < rb.size() && rb[v].rung == rb[u].rung && rb[v].bytes == rb[u].bytes) {
+                ds = rb[v].dev - rb[u].dev;
+                hs = (const uint8_t *)rb[v].host - (const uint8_t *)rb[u].host;
+                if (ds >= (ptrdiff_t)rb[u].bytes && hs >= (ptrdiff_t)rb[u].bytes && same_host_pool(rb[u].host, rb[v].host)) {
+                    ++v;
+                    while (v < rb.size() && rb[v].rung == rb[u].rung && rb[v].bytes == rb[u].bytes && rb[v].dev - rb[v - 1].dev == ds &&
+                           (const uint8_t *)rb[v].host - (const uint8_t *)rb[v - 1].host == hs && same_host_pool(rb[u].host, rb[v].host))
+                        ++v;
+                }
+            }
+            const size_t count = v - u;
+            if (count == 1)
+                CK(cudaMemcpyAsync(rb[u].host, rb[u].dev, rb[u].bytes, cudaMemcpyDeviceToHost, b->readback_stream));
+            else if (ds == hs)          // the gaps between the surfaces are copied too: both sides own them (arena / pool padding)
+                CK(cudaMemcpyAsync(rb[u].host, rb[u].dev, (size_t)ds * (count - 1) + rb[u].bytes, cudaMemcpyDeviceToHost, b->readback_stream));
+            else
+                CK(cudaMemcpy2DAsync(rb[u].host, (size_t)hs, rb[u].dev, (size_t)ds, rb[u].bytes, count, cudaMemcpyDeviceToHost, b->readback_stream));
+            b->last_readbacks++;
+            u = v;
+        }
         CK(cudaEventRecord(st.read_back, b->readback_stream));
         st.has_readback = true;
     }

@@ -494,3 +494,46 @@ def test_batch_uploads_travel_as_one_copy(lib, og, oracle):
     for c in chans:
         c.close()
     hpool.close()
+
+
+def test_batch_readbacks_travel_as_one_copy_per_rung(lib, og, oracle):
+    """Host-destined rungs: the surfaces of one rung of all channels share one device allocation, so destinations that are
+    consecutive buffers of one pinned pool come back with a single copy per rung (x264/x265 hand-off, transvideo.c:1610-1624);
+    scattered destinations (every second pool buffer, plain numpy memory) still arrive bit-exact through pitched / single copies."""
+    import ctypes as C
+    w, h, n = 96, 64, 5
+    rungs = [(96, 64, og.FMT_I420), (64, 40, og.FMT_I420)]
+    chans = [og.Channel(lib, og.make_cfg(w, h, rungs, deint=og.DEINT_FLAGGED)) for _ in range(n)]
+    batch = og.Batch(lib, chans)
+    nbytes = lib.frame_bytes(og.FMT_I420, w, h)
+    rb = chans[0].rung_bytes
+    pools = [og.Pool(lib, 0, og.MEM_HOST, 2 * n, rb[r]) for r in range(2)]
+    packed = [[pools[r].take() for _ in range(2 * n)] for r in range(2)]
+    loose = [np.zeros(rb[1], np.uint8) for _ in range(n)]
+    frames = [[natural_i420(w, h, 11, shift=1.0 * (5 * s + c)) for c in range(n)] for s in range(5)]
+    for s in range(5):
+        layout = s % 3                      # 0: consecutive buffers, 1: every second buffer (pitched copy), 2: rung 1 in numpy memory
+        for c in range(n):
+            batch.fin[c].data, batch.fin[c].mem = frames[s][c].ctypes.data, og.MEM_HOST
+            batch.fin[c].interlaced, batch.fin[c].tff = 0, 1
+            for r in range(2):
+                dst = packed[r][c] if layout == 0 else packed[r][2 * c]
+                if layout == 2 and r == 1:
+                    dst = loose[c].ctypes.data
+                batch.fout[c].dst[r], batch.fout[c].dst_mem[r] = dst, og.MEM_HOST
+        batch.submit_raw(og.SUBMIT_SYNC)
+        if s == 0:
+            continue
+        assert batch.last_readbacks == (2 if layout < 2 else 1 + n)
+        for c in range(n):
+            assert batch.fout[c].produced == 1
+            want = [frames[s - 1][c], oracle.scale_i420(frames[s - 1][c], w, h, 64, 40)]
+            for r in range(2):
+                got = np.empty(rb[r], np.uint8)
+                C.memmove(got.ctypes.data, batch.fout[c].dst[r], rb[r])
+                assert np.array_equal(got, want[r]), (s, c, r)
+    batch.close()
+    for c in chans:
+        c.close()
+    for p in pools:
+        p.close()
