@@ -27,6 +27,22 @@ constexpr int kGeomSlots8 = 4, kGeomSlots16 = 2;
 constexpr int geom_slots(int bps) { return bps == 2 ? kGeomSlots16 : kGeomSlots8; }
 constexpr int kTensorMapBytes = 128;           // sizeof(CUtensorMap)
 constexpr int kThreads = 384;                  // compute threads of a ladder CTA (12 warps); the kernel adds one producer warp
+// 8-bit scale tiles in STRIP mode: a tile is up to 12 column groups of 8 output columns wide and compute warp w owns column
+// group w for BOTH passes (H pass: its 8 columns of every staged row; V pass: lane = output row, 8 columns each), so a
+// tile needs no CTA-wide barrier at all (a __syncwarp between the passes), one H-pass result region is enough (a warp only
+// ever touches its own columns of it) and the warps of a CTA drift apart freely: while one is in its V pass (multiply /
+// ALU pipes) another runs the next tile's H pass (shared loads / tensor pipe).  0 = the default layout (64-column tiles,
+// work dealt out across the CTA, one named barrier between the passes).
+// MEASURED (round 2, B200, profiles/README.md): bit-exact, and no faster -- cfg2 0.584 vs 0.583 ms per 64 frames, cfg1
+// 0.342 vs 0.316, cfg4 0.464 vs 0.452.  The barrier stalls (18 % of the samples) go away, but the kernel issues the same
+// useful instructions at the same rate (0.61 per scheduler cycle): the wider tiles stage wider source rows, so the low
+// rungs get shorter tiles (more halo rows in the H pass), lane = row costs 2-way bank conflicts on 2:1 rungs, and warps
+// without a column group in a tile idle.  Kept as a build option (scripts/build_variant.sh strip -DOTTGPU_STRIP=1).
+#if !defined(OTTGPU_STRIP)
+#define OTTGPU_STRIP 0
+#endif
+constexpr int kStripGroups = kThreads / 32;    // column groups per strip tile = compute warps
+constexpr int kStripWidth = 8 * kStripGroups;  // 96 output columns
 
 enum ItemKind : uint8_t {
     ITEM_SCALE_LUMA = 0,     // H+V polyphase of one luma tile
@@ -56,6 +72,7 @@ struct PlaneTables {
     int mid_pitch;           // H-pass result row pitch in shared memory (mid_t elements): tw + 8, so that the fragment
                              //   stores of the H pass and the 16-byte loads of the V pass are both bank-conflict free
     int vtaps;
+    int vstride;             // 32-bit entries per output row in vc (>= vtaps)
     int vbias;               // 8-bit target A fast path: per-product bias (max|c| >> 1) + 1 of the V pass, 0 = not usable
                              //   (odd tap count, or taps * (max|c| + 2) would overflow a 16-bit lane)
     int exact_from;          // 8-bit target A: first output row computed with the exact vertical formula
@@ -132,19 +149,21 @@ struct Item {
     uint8_t dst_shift;       // 6 for P010
     uint8_t tma_ok;          // the source window fits one 2-D TMA box per plane
     uint8_t thumb;           // item of the thumbnail slot: runs only on the steps the thumbnail is due
-    uint16_t pad1;
+    uint16_t vstride;        // V coefficient table: 32-bit entries per output row (>= vtaps; padded so that 32 lanes reading
+                             //   32 different rows hit different banks)
     // 8-bit H pass: the (column group, 16-row group) pairs dealt to each compute warp as one contiguous run:
     // bits 0-7 first column group, 8-19 first row group, 20-31 number of pairs
     uint32_t hrun[kThreads / 32];
     // copies of the table fields the hot loops need, so that no thread waits on a chain of global loads through T
     // at the start of a tile (measured: ~1.1 us of fixed cost per tile per CTA went there)
     const uint32_t *hmma;    // 8-bit: B fragments of the tile's first column group
-    uint16_t kw[8];          // 8-bit: K-window base of each of the tile's column groups, in 32-bit words from sx0
+    uint16_t kw[12];         // 8-bit: K-window base of each of the tile's column groups, in 32-bit words from sx0
     uint16_t vtaps, vbias, exact_from, dstW;
-    uint8_t hks, hsplit, hq, pad2;
+    uint8_t hks, hsplit, hq;
+    uint8_t strip;           // 8-bit strip mode: 1 = lane owns a row x 8 columns in the V pass, 2 = x 4 columns (short tiles)
     uint32_t pad3;
     const uint32_t *hmma2;   // 16-bit interleaved chroma: fragments of the second (V) plane, else = hmma
-    uint32_t pad4[4];
+    uint32_t pad4[2];
 };
 static_assert(sizeof(Item) == 192, "Item is copied into shared memory as twelve 16-byte vectors");
 

@@ -68,6 +68,25 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity
         if (ok) return;
     }
 }
+// compute-warp wait of the strip mode: usually the phase is complete already (one test, no loop); a warp that is ahead of
+// the others sleeps between polls instead of spinning on the barrier
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity)
+{
+    for (uint32_t ns = 32;; ns = ns < 256 ? 2 * ns : 256) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+        __nanosleep(ns);
+    }
+}
 // adds to the pending transaction bytes of the current phase without arriving
 __device__ __forceinline__ void mbar_add_tx(uint64_t *bar, uint32_t bytes)
 {
@@ -203,9 +222,13 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
     }
 
     // ---------------------------------------------------------------------- compute warps
+    constexpr bool kStrip = BPS == 1 && OTTGPU_STRIP;
     uint32_t pr = 0;
     for (int slot = 0;; slot = (slot + 1) & (kGeomSlots - 1)) {
-        mbar_wait(&ready[slot], (pr >> slot) & 1);
+        // strip mode: the warps of a CTA run apart, and one that is ahead must not spin on the barrier (a spinning warp takes
+        // issue slots from the working ones): try_wait with a time hint suspends it in hardware until the phase completes
+        if (kStrip) mbar_wait_sleep(&ready[slot], (pr >> slot) & 1);
+        else mbar_wait(&ready[slot], (pr >> slot) & 1);
         pr ^= 1u << slot;
         const int idx = s_idx[slot];
         if (idx >= L.n_items) break;
@@ -229,15 +252,18 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
 #if !defined(OTTGPU_DEBUG_SKIP_H)
             phase_hpass<BPS>(tid, g, smem);
 #endif
-            compute_sync();                        // H-pass result and V tables complete; the source buffer is free
-            mbar_arrive(&empty[s_buf[slot]]);
+            // strip mode: the V pass of a warp reads only what the same warp's H pass wrote (and the V tables, complete
+            // since ready[slot]); otherwise the H-pass result of the whole CTA must be complete
+            if (kStrip) __syncwarp();
+            else compute_sync();
+            mbar_arrive(&empty[s_buf[slot]]);      // this thread no longer reads the source buffer
 #if !defined(OTTGPU_DEBUG_SKIP_V)
             phase_vpass<BPS>(tid, g, smem);
 #endif
             // one intermediate region: everybody must be done reading it before the next tile's H pass writes it.  Two
             // regions: the next H pass writes the other one, and the region it will overwrite after that was last read
             // before the barrier above - no wait here, a warp that is done starts the next tile at once
-            if (L.mid_buffers == 1) compute_sync();
+            if (!kStrip && L.mid_buffers == 1) compute_sync();
         }
         mbar_arrive(&gfree[slot]);                 // descriptor slot may be rewritten
     }
@@ -281,7 +307,8 @@ size_t ladder_smem_bytes(int bps, int src_max, int mid_max, int vc_max, int *dou
     static const int want_two_src = [] { const char *v = std::getenv("OTTGPU_DOUBLE_SRC"); return v ? std::atoi(v) : 0; }();
     const size_t nsrc = want_two_src && 2 * (size_t)src_max + 2 * (size_t)mid_max + tables + 16 <= kMaxTileSmem ? 2 : 1;
     const size_t two_mid = nsrc * src_max + 2 * (size_t)mid_max + tables + 16, one = (size_t)src_max + mid_max + tables + 16;
-    const int mb = two_mid <= kMaxTileSmem ? 2 : 1;
+    // strip mode (8-bit): one region -- a warp only touches its own columns of it, in program order
+    const int mb = (two_mid <= kMaxTileSmem && !(OTTGPU_STRIP && bps == 1)) ? 2 : 1;
     if (double_buffer) *double_buffer = mb == 2 && nsrc == 2;
     if (mid_buffers) *mid_buffers = mb;
     return mb == 2 ? two_mid : one;

@@ -208,7 +208,7 @@ OTT_DEV void phase_tables(int tid, int nthreads, const TileGeom &g, unsigned cha
 {
     int32_t *vc_s = reinterpret_cast<int32_t *>(smem + g.off_vc);
     int32_t *vpos_s = reinterpret_cast<int32_t *>(smem + g.off_vpos);
-    const int n = g.th * g.vtaps, th = g.th;
+    const int n = g.th * g.vstride, th = g.th;
     for (int i = tid; i < n; i += nthreads) vc_s[i] = ott_ldg(g.vc_src + i);
     for (int i = tid; i < th; i += nthreads) vpos_s[i] = ott_ldg(g.vpos_src + i);
 }
@@ -394,6 +394,65 @@ OTT_DEV void hpass8_mma(int tid, const TileGeom &g, unsigned char *smem)
         }
         mt = 0;
         ++nt;
+    }
+}
+
+// STRIP mode (device_types.h): compute warp w owns column group w of the tile -- its B fragments stay in registers while it
+// walks down ALL staged rows of the plane(s) in 16-row groups; nothing is dealt out across the CTA and the results land in
+// the 8 columns of the intermediate region that only this warp will read in the V pass.
+template <int KS, int SPLIT>
+OTT_DEV void hpass8_strip(int tid, const TileGeom &g, unsigned char *smem)
+{
+    const int warp = tid >> 5, lane = tid & 31;
+    if (8 * warp >= g.tw) return;
+    const int ks_n = KS ? KS : g.hks;
+    const int spw = g.spw, pitch = g.mid_pitch;
+    const uint32_t *frag = g.hmma + (size_t)warp * ks_n * 128;
+#if !defined(OTTGPU_EMULATE)
+    uint4 B[KS ? KS : 1];
+    if (KS) {
+        OTT_UNROLL
+        for (int ks = 0; ks < KS; ++ks) B[ks] = ott_ldg(reinterpret_cast<const uint4 *>(frag) + ks * 32 + lane);
+    }
+#endif
+    const int mt_plane = (g.sr + 15) >> 4;
+    const uint32_t *src_s = reinterpret_cast<const uint32_t *>(smem + g.off_src) + (lane >> 2) * spw + (lane & 3) + g.kw[warp];
+    uint32_t *mid_s = reinterpret_cast<uint32_t *>(reinterpret_cast<mid_t *>(smem + g.off_mid) + (lane >> 2) * pitch + 2 * (lane & 3) + 8 * warp);
+    for (int p = 0; p < g.nplanes; ++p) {
+        const uint32_t *rg = src_s + p * (g.plane_stride >> 2), *rg8 = rg + 8 * spw;
+        uint32_t *o = mid_s + p * ((g.mid_rows * pitch) >> 1), *o8 = o + 4 * pitch;      // pitch is even: element offsets halve to words
+        OTT_NOUNROLL
+        for (int cnt = mt_plane; cnt > 0; --cnt, rg += 16 * spw, rg8 += 16 * spw, o += 8 * pitch, o8 += 8 * pitch) {
+            int H[4] = {0, 0, 0, 0}, L[4] = {0, 0, 0, 0};
+            if (KS) {
+                OTT_UNROLL
+                for (int ks = 0; ks < (KS ? KS : 1); ++ks) {
+#if defined(OTTGPU_EMULATE)
+                    hmma_lane(rg + 8 * ks, rg8 + 8 * ks, frag + (size_t)ks * 128, lane, H, L);
+#else
+                    const uint32_t a[4] = {rg[8 * ks], rg8[8 * ks], rg[8 * ks + 4], rg8[8 * ks + 4]};
+                    ott_mma_u8s8(H, a, B[ks].x, B[ks].y);
+                    ott_mma_u8u8(L, a, B[ks].z, B[ks].w);
+#endif
+                }
+            } else {
+                for (int ks = 0; ks < ks_n; ++ks) {             // long filters: fragments re-read per step (L1-resident)
+#if defined(OTTGPU_EMULATE)
+                    hmma_lane(rg + 8 * ks, rg8 + 8 * ks, frag + (size_t)ks * 128, lane, H, L);
+#else
+                    const uint4 b = ott_ldg(reinterpret_cast<const uint4 *>(frag) + ks * 32 + lane);
+                    const uint32_t a[4] = {rg[8 * ks], rg8[8 * ks], rg[8 * ks + 4], rg8[8 * ks + 4]};
+                    ott_mma_u8s8(H, a, b.x, b.y);
+                    ott_mma_u8u8(L, a, b.z, b.w);
+#endif
+                }
+            }
+            int v[4];
+            OTT_UNROLL
+            for (int i = 0; i < 4; ++i) v[i] = (SPLIT == 7 ? H[i] : 2 * H[i]) + (int)((uint32_t)L[i] >> 7);
+            o[0] = ott_pack_s16(v[1], v[0]);
+            o8[0] = ott_pack_s16(v[3], v[2]);
+        }
     }
 }
 
@@ -658,10 +717,17 @@ OTT_DEV void phase_hpass(int tid, const TileGeom &g, unsigned char *smem)
     const int hq = g.hq;
     if (BPS == 1) {
         const int hks = g.hks;
+#if OTTGPU_STRIP
+        if (g.hsplit != 7) hpass8_strip<0, 8>(tid, g, smem);     // a coefficient beyond 127*128+255 (border-folded taps): rare
+        else if (hks == 1) hpass8_strip<1, 7>(tid, g, smem);
+        else if (hks == 2) hpass8_strip<2, 7>(tid, g, smem);
+        else hpass8_strip<0, 7>(tid, g, smem);
+#else
         if (g.hsplit != 7) hpass8_mma<0, 8>(tid, g, smem);       // a coefficient beyond 127*128+255 (border-folded taps): rare
         else if (hks == 1) hpass8_mma<1, 7>(tid, g, smem);
         else if (hks == 2) hpass8_mma<2, 7>(tid, g, smem);
         else hpass8_mma<0, 7>(tid, g, smem);
+#endif
     } else if (g.hsplit == 16) {
         const int hks = g.hks;
         if (hks == 1) hpass16_mma<1>(tid, g, smem);
@@ -902,16 +968,19 @@ OTT_DEV void store_words(uint8_t *row, int elem, const uint32_t (&w)[NWORDS], in
 // kThreads / (tw / 8) rows.  Chroma tiles run the row function once per plane (a real loop: one copy of the code).
 // The rows of the fast path (8-bit target A, all but the bottom rows of a plane) come first in a loop of their own, so
 // that loop carries no per-row mode decision; what is left (exact rows, target B, 16-bit) goes through vcolumns.
-template <int BPS>
+template <int BPS, int NO>
 OTT_DEV void vpass_store(uint8_t *dst0, uint8_t *dst1, int dpitch0, int dpitch1, int gy, int gx, int dstW, int nplanes, int il,
-                         bool vec_ok, const uint32_t (&o0)[BPS == 1 ? 2 : 4], const uint32_t (&o1)[BPS == 1 ? 2 : 4])
+                         bool vec_ok, const uint32_t (&o0)[NO], const uint32_t (&o1)[NO])
 {
-    constexpr int NO = BPS == 1 ? 2 : 4;
     typedef typename StoreT<BPS>::type S;
     if (nplanes == 1) {
         if (BPS == 1 && vec_ok) {
-            uint2 q; q.x = o0[0]; q.y = o0[1];
-            *reinterpret_cast<uint2 *>(dst0 + (size_t)gy * dpitch0 + gx) = q;
+            if (NO == 2) {
+                uint2 q; q.x = o0[0]; q.y = o0[NO - 1];
+                *reinterpret_cast<uint2 *>(dst0 + (size_t)gy * dpitch0 + gx) = q;
+            } else {
+                *reinterpret_cast<uint32_t *>(dst0 + (size_t)gy * dpitch0 + gx) = o0[0];
+            }
         } else {
             store_words<S, NO>(dst0 + (size_t)gy * dpitch0, gx, o0, dstW);
         }
@@ -923,8 +992,13 @@ OTT_DEV void vpass_store(uint8_t *dst0, uint8_t *dst1, int dpitch0, int dpitch1,
             else zip16(o0[k], o1[k], z[2 * k], z[2 * k + 1]);
         }
         if (BPS == 1 && vec_ok) {
-            uint4 q; q.x = z[0]; q.y = z[1]; q.z = z[2]; q.w = z[3];
-            *reinterpret_cast<uint4 *>(dst0 + (size_t)gy * dpitch0 + 2 * gx) = q;
+            if (NO == 2) {
+                uint4 q; q.x = z[0]; q.y = z[1]; q.z = z[2 * NO - 2]; q.w = z[2 * NO - 1];
+                *reinterpret_cast<uint4 *>(dst0 + (size_t)gy * dpitch0 + 2 * gx) = q;
+            } else {
+                uint2 q; q.x = z[0]; q.y = z[1];
+                *reinterpret_cast<uint2 *>(dst0 + (size_t)gy * dpitch0 + 2 * gx) = q;
+            }
         } else {
             store_words<S, 2 * NO>(dst0 + (size_t)gy * dpitch0, 2 * gx, z, 2 * dstW);
         }
@@ -934,19 +1008,32 @@ OTT_DEV void vpass_store(uint8_t *dst0, uint8_t *dst1, int dpitch0, int dpitch1,
     }
 }
 
-template <int BPS>
+// CPT = adjacent columns per thread.  Round-1 layout: CPT = 8, tw / 8 lanes per output row, a CTA sweep covers
+// kThreads / (tw / 8) rows.  Strip mode (8-bit): compute warp w owns columns [8w, 8w + 8) of the tile -- the ones its H
+// pass produced; CPT = 8: lane = output row (32 rows per sweep of the warp), CPT = 4 (short tiles of steep filters): two
+// lanes per row, 16 rows per sweep.
+template <int BPS, int CPT>
 OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
 {
-    constexpr int CPT = 8, NO = BPS == 1 ? CPT / 4 : CPT / 2;   // packed output words per plane
+    constexpr int NO = BPS == 1 ? CPT / 4 : CPT / 2;            // packed output words per plane
     // the geometry lives in shared memory: copy what the loop needs into registers once
     const int tile_w = g.tw, tile_h = g.th, y0 = g.y0, sy0 = g.sy0;
     const int mid_pitch = g.mid_pitch, plane_step = g.mid_rows * g.mid_pitch, approx = g.approx_v, shift = g.dst_shift, nplanes = g.nplanes, il = g.dst_interleaved;
-    const int vtaps = g.vtaps, exact_from = g.exact_from, dstW = g.dstW;
+    const int vtaps = g.vtaps, vstride = g.vstride, exact_from = g.exact_from, dstW = g.dstW;
     uint8_t *const dst0 = g.dst0, *const dst1 = g.dst1;
     const int dpitch0 = g.dst_pitch0, dpitch1 = g.dst_pitch1;
-    const int lpr_log2 = g.tw_log2 - 3;                          // lanes per output row: tw / 8
-    const int lx = tid & ((1 << lpr_log2) - 1), ry = tid >> lpr_log2, rows_per_pass = kThreads >> lpr_log2;
-    const int x = CPT * lx;
+    int x, ry, rows_per_pass;
+    if (BPS == 1 && OTTGPU_STRIP) {
+        const int warp = tid >> 5, lane = tid & 31;
+        x = 8 * warp + (CPT == 8 ? 0 : 4 * (lane & 1));
+        ry = CPT == 8 ? lane : lane >> 1;
+        rows_per_pass = CPT == 8 ? 32 : 16;
+    } else {
+        const int lpr_log2 = g.tw_log2 - 3;                      // lanes per output row: tw / 8
+        x = CPT * (tid & ((1 << lpr_log2) - 1));
+        ry = tid >> lpr_log2;
+        rows_per_pass = kThreads >> lpr_log2;
+    }
     if (x >= tile_w) return;
     const mid_t *mid_s = reinterpret_cast<const mid_t *>(smem + g.off_mid) + x;
     const int32_t *vc_s = reinterpret_cast<const int32_t *>(smem + g.off_vc);
@@ -956,11 +1043,11 @@ OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
     if (BPS == 1 && approx && g.vbias > 0) {
         const int bias16 = g.vbias << 16, k16 = (vtaps * g.vbias - ((64 + 8 * (vtaps - 1)) >> 4)) << 16;
         const int fast_rows = ott_min(tile_h, exact_from - y0);
-        // whole 8 / 16-byte stores when the unit lies inside the plane and the surface rows are aligned
-        const bool vec_ok = gx + CPT <= dstW && (il ? ((((uintptr_t)dst0 | (uintptr_t)dpitch0) & 15) == 0)
-                                                    : (nplanes == 1 && (((uintptr_t)dst0 | (uintptr_t)dpitch0) & 7) == 0));
+        // whole-unit vector stores when the unit lies inside the plane and the surface rows are aligned to the unit
+        const bool vec_ok = gx + CPT <= dstW && (il ? ((((uintptr_t)dst0 | (uintptr_t)dpitch0) & (uintptr_t)(2 * CPT - 1)) == 0)
+                                                    : (nplanes == 1 && (((uintptr_t)dst0 | (uintptr_t)dpitch0) & (uintptr_t)(CPT - 1)) == 0));
         for (; y < fast_rows; y += rows_per_pass) {
-            const int32_t *cf = vc_s + y * vtaps;
+            const int32_t *cf = vc_s + y * vstride;
             const mid_t *m = mid_s + (vpos_s[y] - sy0) * mid_pitch;
             uint32_t o0[NO], o1[NO];
             OTT_NOUNROLL
@@ -973,12 +1060,12 @@ OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
                     else o1[k] = t[k];
                 }
             }
-            vpass_store<BPS>(dst0, dst1, dpitch0, dpitch1, y0 + y, gx, dstW, nplanes, il, vec_ok, o0, o1);
+            vpass_store<BPS, NO>(dst0, dst1, dpitch0, dpitch1, y0 + y, gx, dstW, nplanes, il, vec_ok, o0, o1);
         }
     }
     for (; y < tile_h; y += rows_per_pass) {
         const int gy = y0 + y;
-        const int32_t *cf = vc_s + y * vtaps;
+        const int32_t *cf = vc_s + y * vstride;
         int mode;
         if (BPS == 1) mode = vtaps == 1 ? VM_ONE8 : ((approx && gy < exact_from) ? VM_APPROX8 : VM_EXACT8);
         else mode = vtaps == 1 ? VM_ONE10 : VM_EXACT10;
@@ -994,14 +1081,15 @@ OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
                 else o1[k] = t[k];
             }
         }
-        vpass_store<BPS>(dst0, dst1, dpitch0, dpitch1, gy, gx, dstW, nplanes, il, false, o0, o1);
+        vpass_store<BPS, NO>(dst0, dst1, dpitch0, dpitch1, gy, gx, dstW, nplanes, il, false, o0, o1);
     }
 }
 
 template <int BPS>
 OTT_DEV void phase_vpass(int tid, const TileGeom &g, unsigned char *smem)
 {
-    vpass<BPS>(tid, g, smem);
+    if (BPS == 1 && OTTGPU_STRIP && g.strip == 2) vpass<BPS, 4>(tid, g, smem);
+    else vpass<BPS, 8>(tid, g, smem);
 }
 
 // ------------------------------------------------------------------------------------------------ copy items

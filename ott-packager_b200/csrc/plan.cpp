@@ -83,6 +83,8 @@ size_t kSrcCap = 48 * 1024;                                 // the staged-source
 size_t kMidCap = 27 * 1024;                                 // one H-pass result region (there are two)
 struct CapPair { int src_kb, mid_kb; };
 const CapPair kCaps8[] = {{48, 27}, {44, 27}, {40, 26}, {36, 26}, {32, 24}, {28, 22}, {24, 20}, {20, 16}};
+// strip mode (8-bit): ONE intermediate region, so it may be about twice as large
+const CapPair kCapsStrip[] = {{48, 50}, {44, 50}, {40, 48}, {36, 44}, {32, 40}, {28, 36}, {24, 32}, {20, 24}};
 const CapPair kCaps16[] = {{68, 18}, {64, 20}, {60, 20}, {56, 20}, {48, 20}, {40, 18}, {32, 16}, {24, 14}};
 const int kMaxTileRows = (int)(env_kb("OTTGPU_MAX_TILE_ROWS", 128) / 1024);
 const int kTileRounds = [] { const char *v = std::getenv("OTTGPU_TILE_ROUNDS"); return v ? std::atoi(v) : 1; }();   // 1: also try tile heights that fill whole V rounds          // keeps enough tiles per frame for load balance
@@ -104,13 +106,13 @@ const T *upload(Plan &plan, const std::vector<T> &v, std::string &err)
 struct TileRegions { size_t src, mid, vc; };
 
 // must match item_prepare() in ladder_core.cuh
-TileRegions tile_regions(int nplanes, int staged_planes, int sr_max, int sw_words, int tw, int th, int vtaps)
+TileRegions tile_regions(int nplanes, int staged_planes, int sr_max, int sw_words, int mid_pitch, int th, int vstride)
 {
     TileRegions r;
     r.src = (size_t)staged_planes * (((size_t)sr_max * sw_words * 4 + 127) & ~(size_t)127);   // planes 128-byte aligned (TMA)
     // rows per plane rounded up to the 16-row groups of the H pass, row pitch tw + 8 (bank-conflict free, 16-byte multiple)
-    r.mid = (size_t)nplanes * ((sr_max + 15) & ~15) * (tw + 8) * sizeof(mid_t);
-    r.vc = (size_t)th * vtaps * 4 + (size_t)th * 4;                  // 32-bit coefficients + row positions
+    r.mid = (size_t)nplanes * ((sr_max + 15) & ~15) * mid_pitch * sizeof(mid_t);
+    r.vc = (size_t)th * vstride * 4 + (size_t)th * 4;                // 32-bit coefficients + row positions
     r.vc = (r.vc + 15) & ~(size_t)15;
     return r;
 }
@@ -250,6 +252,10 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
         T.vbias = (v.taps % 2 == 0 && (long long)v.taps * (cmax + 2) < 65536) ? (cmax >> 1) + 1 : 0;
     }
     T.exact_from = exact_from;
+    const bool strip = OTTGPU_STRIP && mma8;
+    // strip mode reads the V coefficients of 32 different rows at once (lane = row), 8 bytes per lane: a row stride of an odd
+    // number of 8-byte units keeps those loads free of bank conflicts
+    T.vstride = (strip && v.taps % 2 == 0 && (v.taps / 2) % 2 == 0) ? v.taps + 2 : v.taps;
     // px_bytes = bytes per staged sample position: bps for planar samples, 4 for P010's interleaved (U,V) pairs, which are
     // staged as ONE plane of 32-bit words
     const int spv = 16 / px_bytes;                               // sample positions per 16-byte staging vector
@@ -305,7 +311,7 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
     auto best_for = [&](int tw) {
         Shape sh{tw, row_quant, tw == 64 ? 8 : 4, staged_words(tw), 0, 1e30, false, false};
         auto fits = [&](int th, bool hard) {
-            const TileRegions r = tile_regions(nplanes, staged_planes, rows_needed(th), sh.sw_words, tw, th, v.taps);
+            const TileRegions r = tile_regions(nplanes, staged_planes, rows_needed(th), sh.sw_words, tw + 8, th, T.vstride);
             return hard ? r.src + r.mid + r.vc + 16 <= kSmemHardLimit : (r.src <= kSrcCap && r.mid <= kMidCap);
         };
         // tallest tile inside the caps (measured better than minimising the modelled cost over all heights: per-tile
@@ -339,25 +345,72 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
         }
         return sh;
     };
-    Shape best = best_for(dstW > 64 ? 64 : 32);
-    if (best.tw == 64) {
-        const Shape narrow = best_for(32);
-        if (narrow.soft && (!best.soft || narrow.cost < 0.95 * best.cost)) best = narrow;
-        else if (!best.fits && narrow.fits) best = narrow;
+    Shape best;
+    if (strip) {
+        // Strip tiles: G column groups of 8 output columns wide (G <= 12 = one per compute warp; the plane's column groups are
+        // dealt out evenly over ceil(groups / G) tiles), th rows high: multiples of 32 (V pass: lane = row) or 16 / 8 / ...
+        // (two lanes per row).  Per G the tallest tile inside the caps; the winner maximises busy warps x useful H rows.
+        const int groups = (dstW + 7) / 8;
+        auto strip_words = [&](int G) {
+            const int tiles_x = (groups + G - 1) / G;
+            int nvec = 0;
+            for (int tx = 0; tx < tiles_x; ++tx) {
+                const int g0 = (int)((long long)tx * groups / tiles_x), g1 = (int)((long long)(tx + 1) * groups / tiles_x);
+                int b0 = 1 << 30, b1 = 0;
+                for (int gi = g0; gi < g1; ++gi) {
+                    b0 = std::min(b0, kbase[gi] & ~15);
+                    b1 = std::max(b1, kbase[gi] + 32 * hks);
+                }
+                nvec = std::max(nvec, (b1 - b0 + 15) / 16);
+            }
+            return (nvec | 1) * 4;                               // odd multiple of 16 bytes (fragment loads: 32 distinct banks)
+        };
+        static const int kHeights[] = {128, 96, 64, 32, 16, 8, 4, 2, 1};
+        best = Shape{0, 0, 8, 0, 0, 0.0, false, false};
+        for (int pass = 0; pass < 2 && !best.fits; ++pass)       // pass 0: inside the two-CTAs-per-SM caps, pass 1: anything that fits one CTA
+            for (int G = std::min(kStripGroups, groups); G >= 1; --G) {
+                const int sw = strip_words(G);
+                if (sw > 256 && pass == 0) continue;             // one TMA box row
+                for (int th : kHeights) {
+                    if (th > kMaxTileRows && th > 32) continue;
+                    const int nty = (dstH + th - 1) / th;
+                    const int q = th >= 32 ? 32 : th;
+                    const int th2 = std::min(th, ((dstH + nty - 1) / nty + q - 1) / q * q);           // rebalanced: no sliver at the bottom
+                    const int sr = rows_needed(th2);
+                    const TileRegions r = tile_regions(nplanes, staged_planes, sr, sw, kStripWidth + 8, th2, T.vstride);
+                    const bool ok = pass ? r.src + r.mid + (size_t)kGeomSlots8 * r.vc + 16 <= kSmemHardLimit : (r.src <= kSrcCap && r.mid <= kMidCap && sr <= 256);
+                    if (!ok) continue;
+                    const int tiles_x = (groups + G - 1) / G;
+                    const double busy = (double)groups / (tiles_x * kStripGroups);                     // compute warps with a column group
+                    const double lanes = th2 >= 32 ? (double)th2 / ((th2 + 31) / 32 * 32) : (th2 >= 16 ? 1.0 : th2 / 16.0);
+                    const double useful = (double)th2 * srcH / dstH / sr;   // staged rows an ideal (halo-free) tile would need / rows it stages
+                    const double score = busy * lanes * std::min(1.0, useful);
+                    if (score > best.cost) best = Shape{8 * G, th2, th2 >= 32 ? 8 : 4, sw, sr, score, true, pass == 0};
+                    break;                                       // shorter tiles of the same width only score lower
+                }
+            }
+    } else {
+        best = best_for(dstW > 64 ? 64 : 32);
+        if (best.tw == 64) {
+            const Shape narrow = best_for(32);
+            if (narrow.soft && (!best.soft || narrow.cost < 0.95 * best.cost)) best = narrow;
+            else if (!best.fits && narrow.fits) best = narrow;
+        }
     }
     if (!best.fits) { err = "filter too long for one tile (shared memory)"; return false; }
     soft_out = best.soft;
     T.tw = best.tw;
-    T.mid_pitch = best.tw + 8;
+    T.mid_pitch = strip ? kStripWidth + 8 : best.tw + 8;         // strip: ONE pitch for every tile of a launch (the warps' column ranges
+                                                                 // of the shared intermediate region must coincide from tile to tile)
     T.th = best.th;
     T.cpt = best.cpt;
     T.sw_words = best.sw_words;
     T.sr_max = best.sr_max;
-    T.tiles_x = (dstW + T.tw - 1) / T.tw;
+    T.tiles_x = strip ? ((dstW + 7) / 8 + T.tw / 8 - 1) / (T.tw / 8) : (dstW + T.tw - 1) / T.tw;
     T.tiles_y = (dstH + T.th - 1) / T.th;
     // one TMA box per staged plane: inner dimension <= 256 32-bit elements, <= 256 rows, rows a whole number of words
     T.tma_ok = T.sw_words <= 256 && T.sr_max <= 256 && (srcW * px_bytes) % 4 == 0;
-    regions = tile_regions(nplanes, staged_planes, T.sr_max, T.sw_words, T.tw, T.th, v.taps);
+    regions = tile_regions(nplanes, staged_planes, T.sr_max, T.sw_words, T.mid_pitch, T.th, T.vstride);
     hpos_out = h.pos;
     vpos_out = v.pos;
     kbase_out = kbase;
@@ -371,7 +424,12 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
     T.hmma2 = upload(plan, frags_v, err);
     T.hkbase = upload(plan, kbase, err);
     T.vpos = upload(plan, v.pos, err);
-    T.vc = upload(plan, std::vector<int32_t>(v.coef.begin(), v.coef.end()), err);
+    {
+        std::vector<int32_t> vcp((size_t)dstH * T.vstride, 0);
+        for (int y = 0; y < dstH; ++y)
+            for (int j = 0; j < v.taps; ++j) vcp[(size_t)y * T.vstride + j] = v.coef[(size_t)y * v.taps + j];
+        T.vc = upload(plan, vcp, err);
+    }
     return T.hpos && T.hc_hi && T.hc_lo && T.hc16 && T.hmma && T.hmma2 && T.hkbase && T.vpos && T.vc;
 }
 
@@ -435,6 +493,7 @@ std::shared_ptr<Plan> get_plan(const ottgpu_cfg &cfg_in, std::string &err)
     const char *env_src = std::getenv("OTTGPU_SRC_CAP_KB"), *env_mid = std::getenv("OTTGPU_MID_CAP_KB");
     std::vector<CapPair> tries;
     if (env_src && env_mid && std::atoi(env_src) > 0 && std::atoi(env_mid) > 0) tries.push_back({std::atoi(env_src), std::atoi(env_mid)});
+    else if (fmt_bps(cfg.src_fmt) == 1 && OTTGPU_STRIP) tries.assign(std::begin(kCapsStrip), std::end(kCapsStrip));
     else if (fmt_bps(cfg.src_fmt) == 1) tries.assign(std::begin(kCaps8), std::end(kCaps8));
     else tries.assign(std::begin(kCaps16), std::end(kCaps16));
     std::shared_ptr<Plan> plan;
@@ -552,8 +611,15 @@ std::shared_ptr<Plan> build_plan(const ottgpu_cfg &cfg, std::string &err)
                     it.slot = (uint8_t)s;
                     it.kind = kind;
                     it.thumb = is_thumb;
-                    const int x0 = tx * T.tw, y0 = ty * T.th;
-                    const int tw = std::min(T.tw, T.dstW - x0), th = std::min(T.th, T.dstH - y0);
+                    const bool strip = OTTGPU_STRIP && !kb.empty() && bps == 1;
+                    int x0 = tx * T.tw, y0 = ty * T.th;
+                    int tw = std::min(T.tw, T.dstW - x0), th = std::min(T.th, T.dstH - y0);
+                    if (strip) {                                 // the plane's column groups dealt out evenly over the tiles of a row
+                        const int groups = (T.dstW + 7) / 8;
+                        const int g0 = (int)((long long)tx * groups / T.tiles_x), g1 = (int)((long long)(tx + 1) * groups / T.tiles_x);
+                        x0 = 8 * g0;
+                        tw = std::min(8 * g1, T.dstW) - x0;
+                    }
                     const int sy0 = vp[y0], sr = std::min(vp[y0 + th - 1] + T.vtaps, T.srcH) - sy0;
                     int sx0 = hp[x0] & ~(spv - 1), last = hp[x0 + tw - 1] + 4 * T.hq + slack;   // + one word of funnel-shift slack
                     if (!kb.empty()) {                           // MMA paths: the K windows (bytes) of the tile's column groups
@@ -588,11 +654,13 @@ std::shared_ptr<Plan> build_plan(const ottgpu_cfg &cfg, std::string &err)
                     it.dst_shift = R.fmt == OTTGPU_FMT_P010 ? 6 : 0;
                     it.tma_ok = (uint8_t)T.tma_ok;
                     // the tile's slices of the V tables (device pointers); fetched by two bulk copies when 16-byte aligned
-                    it.vc_src = T.vc + (size_t)y0 * T.vtaps;
+                    it.vc_src = T.vc + (size_t)y0 * T.vstride;
                     it.vpos_src = T.vpos + y0;
-                    it.vpos_off = (uint16_t)(T.th * T.vtaps * 4);
-                    const size_t vcb = ((size_t)th * T.vtaps * 4 + 15) & ~(size_t)15, vpb = ((size_t)th * 4 + 15) & ~(size_t)15;
-                    const bool bulk = ((size_t)y0 * T.vtaps * 4) % 16 == 0 && ((size_t)y0 * 4) % 16 == 0 && it.vpos_off % 16 == 0 &&
+                    it.vpos_off = (uint16_t)(T.th * T.vstride * 4);
+                    it.vstride = (uint16_t)T.vstride;
+                    it.strip = strip ? (T.cpt == 8 ? 1 : 2) : 0;
+                    const size_t vcb = ((size_t)th * T.vstride * 4 + 15) & ~(size_t)15, vpb = ((size_t)th * 4 + 15) & ~(size_t)15;
+                    const bool bulk = ((size_t)y0 * T.vstride * 4) % 16 == 0 && ((size_t)y0 * 4) % 16 == 0 && it.vpos_off % 16 == 0 &&
                                       vcb <= (size_t)it.vpos_off && vcb < 65536;
                     it.vc_bytes = bulk ? (uint16_t)vcb : 0;
                     it.vpos_bytes = bulk ? (uint16_t)vpb : 0;
@@ -608,7 +676,7 @@ std::shared_ptr<Plan> build_plan(const ottgpu_cfg &cfg, std::string &err)
                             it.kw[gi - x0 / 8] = (uint16_t)kwv;
                         }
                     }
-                    if (!kb.empty()) {                           // H-pass runs of the compute warps (MMA paths)
+                    if (!kb.empty() && !strip) {                 // H-pass runs of the compute warps (MMA paths, round-1 layout)
                         constexpr int kWarps = kThreads / 32;
                         const int groups = (tw + 7) >> 3, mt_total = it.nplanes * ((sr + 15) >> 4);
                         const int total = groups * mt_total, per = (total + kWarps - 1) / kWarps;

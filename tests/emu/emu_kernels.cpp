@@ -14,7 +14,7 @@ size_t ladder_smem_bytes(int bps, int src_max, int mid_max, int vc_max, int *dou
 {
     const size_t tables = (size_t)geom_slots(bps) * vc_max;
     const size_t two_mid = (size_t)src_max + 2 * (size_t)mid_max + tables + 16, one = (size_t)src_max + mid_max + tables + 16;
-    const int mb = two_mid <= kMaxTileSmem ? 2 : 1;
+    const int mb = (two_mid <= kMaxTileSmem && !(OTTGPU_STRIP && bps == 1)) ? 2 : 1;
     if (double_buffer) *double_buffer = 0;
     if (mid_buffers) *mid_buffers = mb;
     return mb == 2 ? two_mid : one;
