@@ -26,7 +26,10 @@ typedef int16_t mid_t;
 constexpr int kGeomSlots8 = 4, kGeomSlots16 = 2;
 constexpr int geom_slots(int bps) { return bps == 2 ? kGeomSlots16 : kGeomSlots8; }
 constexpr int kTensorMapBytes = 128;           // sizeof(CUtensorMap)
-constexpr int kThreads = 384;                  // compute threads of a ladder CTA (12 warps); the kernel adds one producer warp
+#if !defined(OTTGPU_COMPUTE_WARPS)
+#define OTTGPU_COMPUTE_WARPS 12                /* experiments: 15 warps at 64 registers (strip mode) */
+#endif
+constexpr int kThreads = 32 * OTTGPU_COMPUTE_WARPS;   // compute threads of a ladder CTA (12 warps); the kernel adds one producer warp
 // 8-bit scale tiles in STRIP mode: a tile is up to 12 column groups of 8 output columns wide and compute warp w owns column
 // group w for BOTH passes (H pass: its 8 columns of every staged row; V pass: lane = output row, 8 columns each), so a
 // tile needs no CTA-wide barrier at all (a __syncwarp between the passes), one H-pass result region is enough (a warp only
@@ -153,19 +156,18 @@ struct Item {
                              //   32 different rows hit different banks)
     // 8-bit H pass: the (column group, 16-row group) pairs dealt to each compute warp as one contiguous run:
     // bits 0-7 first column group, 8-19 first row group, 20-31 number of pairs
-    uint32_t hrun[kThreads / 32];
+    uint32_t hrun[kThreads / 32 <= 12 ? 12 : 16];
     // copies of the table fields the hot loops need, so that no thread waits on a chain of global loads through T
     // at the start of a tile (measured: ~1.1 us of fixed cost per tile per CTA went there)
     const uint32_t *hmma;    // 8-bit: B fragments of the tile's first column group
-    uint16_t kw[12];         // 8-bit: K-window base of each of the tile's column groups, in 32-bit words from sx0
+    uint16_t kw[16];         // 8-bit: K-window base of each of the tile's column groups, in 32-bit words from sx0
     uint16_t vtaps, vbias, exact_from, dstW;
     uint8_t hks, hsplit, hq;
     uint8_t strip;           // 8-bit strip mode: 1 = lane owns a row x 8 columns in the V pass, 2 = x 4 columns (short tiles)
     uint32_t pad3;
     const uint32_t *hmma2;   // 16-bit interleaved chroma: fragments of the second (V) plane, else = hmma
-    uint32_t pad4[2];
 };
-static_assert(sizeof(Item) == 192, "Item is copied into shared memory as twelve 16-byte vectors");
+static_assert(sizeof(Item) % 16 == 0 && (sizeof(Item) == 192 || OTTGPU_COMPUTE_WARPS > 12), "Item is copied into shared memory as twelve 16-byte vectors");
 
 // Launch-wide constants of the persistent ladder kernel.
 struct LadderLaunch {
