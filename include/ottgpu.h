@@ -226,6 +226,24 @@ int ottgpu_yadif_frame(int gpu, const void *prev, const void *cur, const void *n
  * dst_n*256).  vertical selects V (12-bit) vs H (14-bit) conventions */
 int ottgpu_filter_table(int src_n, int dst_n, int filter, int target, int vertical, int32_t *pos, int16_t *coef);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Thumbnail JPEG on the GPU.  Replaces save_frame_as_jpeg() of video_thumbnail_thread
+ * (source/transvideo.c:164-198: avcodec_find_encoder(AV_CODEC_ID_MJPEG), 176x144 YUVJ420P, one frame per call).
+ * Baseline JPEG, 4:2:0, planes taken as Y/Cb/Cr as they are, ONE quantisation table for all components built the way
+ * libavcodec's MJPEG encoder builds it: q[i] = clip((ff_mpeg1_default_intra_matrix[i] * qscale) >> 3, 1, 255), q[0] = 8
+ * (qscale 3 is what it picks for natural content at the reference's 250 kb/s).  DCT, quantiser rounding and the (standard,
+ * Annex K) Huffman tables are this library's own: the files decode to the same picture quality as the reference's, they
+ * are not byte-identical to libavcodec's (no bit-exact oracle for its SIMD DCT / rate control / optimal tables exists).
+ */
+typedef struct ottgpu_jpeg ottgpu_jpeg;
+int  ottgpu_jpeg_create(int gpu, int width, int height, int qscale, ottgpu_jpeg **out);
+/* pic: three planes + strides in host or device memory (the scale_struct of the thumbnail hand-off, transvideo.c:2176-2183).
+ * dst: host buffer of dst_capacity bytes; *dst_bytes = size of the file.  Synchronous.  OTTGPU_ERR_NOMEM when dst is too
+ * small (ottgpu_jpeg_max_bytes() is always enough). */
+int  ottgpu_jpeg_encode(ottgpu_jpeg *j, const ottgpu_picture *pic, void *dst, size_t dst_capacity, size_t *dst_bytes);
+size_t ottgpu_jpeg_max_bytes(const ottgpu_jpeg *j);
+void ottgpu_jpeg_destroy(ottgpu_jpeg *j);
+
 #if defined(__cplusplus)
 }
 #endif

@@ -41,6 +41,8 @@ def lib():
         L.ora_convert_to_i420.restype = ci
         L.ora_yadif_plane.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci]
         L.ora_yadif_frame_420.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci]
+        L.ora_jpeg_encode.argtypes = [vp, ci, vp, vp, ci, ci, ci, ci, vp, ctypes.c_size_t]
+        L.ora_jpeg_encode.restype = ctypes.c_size_t
         for f in ("ora_scale_plane_u8", "ora_scale_plane_u10", "ora_scale_i420", "ora_i420_to_nv12",
                   "ora_scale_p010", "ora_yadif_plane", "ora_yadif_frame_420", "ora_filter_free"):
             getattr(L, f).restype = None
@@ -133,3 +135,15 @@ class YadifStream:
         if self.flagged and not il:
             return f.copy(), tg
         return yadif_frame(self.prev[0], f, self.next[0], self.w, self.h, il, tf, self.bps), tg
+
+
+def jpeg_encode(i420, w, h, qscale=3):
+    """packed I420 -> baseline JPEG bytes (ref_jpeg.c: the sequential restatement of the thumbnail encoder)"""
+    L = lib()
+    buf = np.ascontiguousarray(i420, np.uint8)
+    cw, ch = (w + 1) // 2, (h + 1) // 2
+    out = np.zeros(w * h * 4 + 4096, np.uint8)
+    base = buf.ctypes.data
+    n = L.ora_jpeg_encode(base, w, base + w * h, base + w * h + cw * ch, cw, w, h, qscale, out.ctypes.data, out.size)
+    assert n <= out.size
+    return out[:n].tobytes()

@@ -95,6 +95,10 @@ _SIGS = {
     "ottgpu_converter_convert_batch": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(Picture), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]),
     "ottgpu_converter_wait": (C.c_int, [C.c_void_p]),
     "ottgpu_converter_destroy": (None, [C.c_void_p]),
+    "ottgpu_jpeg_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "ottgpu_jpeg_encode": (C.c_int, [C.c_void_p, C.POINTER(Picture), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "ottgpu_jpeg_max_bytes": (C.c_size_t, [C.c_void_p]),
+    "ottgpu_jpeg_destroy": (None, [C.c_void_p]),
     "ottgpu_scale_frame": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(RungCfg),
                                      C.c_int, C.c_int]),
     "ottgpu_yadif_frame": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
@@ -315,6 +319,47 @@ class Converter:
 
     def wait(self):
         self.lib.check(self.lib.dll.ottgpu_converter_wait(self.handle))
+
+
+class Jpeg:
+    """The thumbnail JPEG encoder on the GPU (save_frame_as_jpeg, transvideo.c:164-198)."""
+
+    def __init__(self, lib, w, h, qscale=3, gpu=0):
+        self.lib, self.w, self.h = lib, w, h
+        h_ = C.c_void_p()
+        lib.check(lib.dll.ottgpu_jpeg_create(gpu, w, h, qscale, C.byref(h_)))
+        self.handle = h_
+        self.max_bytes = lib.dll.ottgpu_jpeg_max_bytes(h_)
+
+    def encode(self, i420=None, device_ptr=None, planes=None, strides=None, capacity=None):
+        """packed I420 numpy frame, a device pointer to one, or explicit host planes + strides -> JPEG bytes"""
+        w, h = self.w, self.h
+        cw, ch = (w + 1) // 2, (h + 1) // 2
+        pic = Picture()
+        if planes is not None:
+            pic.mem = MEM_HOST
+            for k in range(3):
+                pic.plane[k], pic.stride[k] = planes[k].ctypes.data, strides[k]
+        else:
+            base = device_ptr if device_ptr is not None else np.ascontiguousarray(i420, np.uint8).ctypes.data
+            pic.mem = MEM_DEVICE if device_ptr is not None else MEM_HOST
+            for k, (off, st) in enumerate(((0, w), (w * h, cw), (w * h + cw * ch, cw))):
+                pic.plane[k], pic.stride[k] = base + off, st
+        out = np.empty(self.max_bytes if capacity is None else capacity, np.uint8)
+        n = C.c_size_t(0)
+        self.lib.check(self.lib.dll.ottgpu_jpeg_encode(self.handle, C.byref(pic), out.ctypes.data, out.size, C.byref(n)))
+        return out[:n.value].tobytes()
+
+    def close(self):
+        if self.handle:
+            self.lib.dll.ottgpu_jpeg_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def convert_batch(lib, converters, planes_list, device_dsts=None, flags=SUBMIT_SYNC, mem=MEM_HOST, strides_list=None):

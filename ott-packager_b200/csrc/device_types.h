@@ -226,4 +226,30 @@ struct ConvertJob {
     uint8_t bayer[64];       // ff_dither_8x8_128
 };
 
+// thumbnail JPEG (jpeg_core.cuh)
+struct JpegHuff {
+    uint16_t dc_code[2][12];
+    uint8_t dc_len[2][12];
+    uint16_t ac_code[2][256];
+    uint8_t ac_len[2][256];
+};
+
+struct JpegJob {
+    const uint8_t *plane[3];
+    int pitch[3];
+    int width, height;           // luma size; chroma planes are ceil(w/2) x ceil(h/2)
+    int mcus_x, mcus_y, n_blocks;
+    int16_t *coef;               // [n_blocks][64], zigzag order, scan order of blocks (MCU-major: Y00 Y01 Y10 Y11 Cb Cr)
+    uint32_t *bits;              // [n_blocks + 1] code length of each block, then (after the scan) its bit position; [n] = total
+    uint32_t *stream;            // entropy-coded bits, big-endian inside each 32-bit word, zeroed before the launch
+    uint32_t stream_words;
+    uint8_t *out;                // header (header_bytes, written by the host) + stuffed entropy data + EOI
+    uint32_t out_capacity;
+    int header_bytes;
+    uint32_t *result;            // [0] total bytes of the file, [1] 1 if something did not fit
+    uint32_t *ff_count;          // [chunks + 1] scratch of the stuffing pass
+    const JpegHuff *huff;
+    uint16_t q[64];              // quantisation table, natural order
+};
+
 }  // namespace ottgpu

@@ -1,0 +1,247 @@
+// Thumbnail JPEG on the GPU: replaces save_frame_as_jpeg (transvideo.c:164-198: one libavcodec MJPEG frame,
+// YUVJ420P, written to /var/www/html/thumbnail<N>.jpg every 150th frame).  Baseline sequential JPEG, 4:2:0, the three planes
+// taken as Y/Cb/Cr as they are (the reference hands its thumbnail planes to the encoder as full-range YUVJ420P the same way).
+//
+// What is kept from the reference's encoder: the picture layout (one quantisation table for all components, MCU = 2x2 luma
+// + Cb + Cr) and the TABLE: libavcodec's MJPEG quantises with ff_mpeg1_default_intra_matrix scaled by the frame's qscale,
+// q[i] = (m[i] * qscale) >> 3, DC entry 8 -- read out of the DQT segment the real encoder of this image writes
+// (oracle/avcodec_so.py; it picks qscale 3 for natural content at the reference's 250 kb/s).  What is NOT reproduced: its
+// SIMD forward DCT / quantiser rounding, its rate control and its per-picture optimal Huffman tables (un-vendored FFmpeg;
+// no bit-exact oracle exists for them) -- this encoder is the public integer DCT of the IJG library (jfdctint: 13-bit
+// constants, results scaled by 8), round-half-away quantisation (jcdctmgr) and the Annex K Huffman tables, bit-exact to the
+// plain C restatement in oracle/ref_jpeg.c and checked against the real libavcodec output by decoding both (tests).
+//
+// Work split (every stage one thread per 8x8 block unless noted), bitstream assembled in parallel:
+//   jpeg_block_dct   : load (edge-replicated), level shift, forward DCT, quantise, zigzag -> coef[block][64]
+//   jpeg_block_bits  : entropy-code LENGTH of the block (DC differences need the previous block of the component only)
+//   (exclusive scan of the lengths -> bit position of every block; one CTA)
+//   jpeg_block_emit  : codes written at the block's bit position with atomic ORs into the zeroed stream
+//   jpeg_stuff_*     : 0xFF byte stuffing as count / scan / scatter, padding of the last byte with 1 bits, EOI
+#pragma once
+#include "ladder_core.cuh"
+
+namespace ottgpu {
+
+#if defined(OTTGPU_EMULATE)
+inline void ott_atomic_or(uint32_t *p, uint32_t v) { *p |= v; }
+#else
+OTT_DEV void ott_atomic_or(uint32_t *p, uint32_t v) { atomicOr(p, v); }
+#endif
+
+// natural index of the k-th zigzag coefficient
+OTT_DEV int jpeg_zigzag(int k)
+{
+    const unsigned char z[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                 41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+    return z[k];
+}
+
+// one 8-point pass of the IJG "islow" forward DCT (jfdctint.c): d[] in, results back into d[]; first = row pass
+OTT_DEV void jpeg_fdct8(int (&d)[8], bool first)
+{
+    const int tmp0 = d[0] + d[7], tmp7 = d[0] - d[7], tmp1 = d[1] + d[6], tmp6 = d[1] - d[6];
+    const int tmp2 = d[2] + d[5], tmp5 = d[2] - d[5], tmp3 = d[3] + d[4], tmp4 = d[3] - d[4];
+    const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+    const int sh = first ? 11 : 15;                              // CONST_BITS -/+ PASS1_BITS
+    const int rnd = 1 << (sh - 1);
+    if (first) {
+        d[0] = (tmp10 + tmp11) << 2;
+        d[4] = (tmp10 - tmp11) << 2;
+    } else {
+        d[0] = (tmp10 + tmp11 + 2) >> 2;
+        d[4] = (tmp10 - tmp11 + 2) >> 2;
+    }
+    int z1 = (tmp12 + tmp13) * 4433;
+    d[2] = (z1 + tmp13 * 6270 + rnd) >> sh;
+    d[6] = (z1 - tmp12 * 15137 + rnd) >> sh;
+    z1 = tmp4 + tmp7;
+    int z2 = tmp5 + tmp6, z3 = tmp4 + tmp6, z4 = tmp5 + tmp7;
+    const int z5 = (z3 + z4) * 9633;
+    const int t4 = tmp4 * 2446, t5 = tmp5 * 16819, t6 = tmp6 * 25172, t7 = tmp7 * 12299;
+    z1 *= -7373;
+    z2 *= -20995;
+    z3 = z3 * -16069 + z5;
+    z4 = z4 * -3196 + z5;
+    d[7] = (t4 + z1 + z3 + rnd) >> sh;
+    d[5] = (t5 + z2 + z4 + rnd) >> sh;
+    d[3] = (t6 + z2 + z3 + rnd) >> sh;
+    d[1] = (t7 + z1 + z4 + rnd) >> sh;
+}
+
+// which plane / where: block b of the scan
+OTT_DEV void jpeg_block_place(const JpegJob &j, int b, int &comp, int &bx, int &by)
+{
+    const int mcu = b / 6, k = b - 6 * mcu, mx = mcu % j.mcus_x, my = mcu / j.mcus_x;
+    if (k < 4) { comp = 0; bx = 2 * mx + (k & 1); by = 2 * my + (k >> 1); }
+    else { comp = k - 3; bx = mx; by = my; }
+}
+
+OTT_DEV void jpeg_block_dct(const JpegJob &j, int b)
+{
+    if (b >= j.n_blocks) return;
+    int comp, bx, by;
+    jpeg_block_place(j, b, comp, bx, by);
+    const int pw = comp ? (j.width + 1) >> 1 : j.width, ph = comp ? (j.height + 1) >> 1 : j.height;
+    const uint8_t *p = j.plane[comp];
+    const int pitch = j.pitch[comp];
+    int blk[64];
+    for (int r = 0; r < 8; ++r) {
+        const int y = ott_min(8 * by + r, ph - 1);
+        int d[8];
+        OTT_UNROLL
+        for (int c = 0; c < 8; ++c) d[c] = (int)ott_ldg(p + (size_t)y * pitch + ott_min(8 * bx + c, pw - 1)) - 128;
+        jpeg_fdct8(d, true);
+        OTT_UNROLL
+        for (int c = 0; c < 8; ++c) blk[8 * r + c] = d[c];
+    }
+    for (int c = 0; c < 8; ++c) {
+        int d[8];
+        OTT_UNROLL
+        for (int r = 0; r < 8; ++r) d[r] = blk[8 * r + c];
+        jpeg_fdct8(d, false);
+        OTT_UNROLL
+        for (int r = 0; r < 8; ++r) blk[8 * r + c] = d[r];
+    }
+    int16_t *out = j.coef + (size_t)b * 64;
+    for (int k = 0; k < 64; ++k) {
+        const int n = jpeg_zigzag(k);
+        const int qv = (int)j.q[n] << 3;                         // the DCT results carry a factor of 8
+        int v = blk[n];
+        const int a = (v < 0 ? -v : v) + (qv >> 1);
+        int qd = a >= qv ? a / qv : 0;
+        qd = ott_min(qd, 1023);                                  // baseline limits: AC category <= 10, DC difference category <= 11
+        out[k] = (int16_t)(v < 0 ? -qd : qd);
+    }
+}
+
+OTT_DEV int jpeg_category(int a)       // bits needed for |value|
+{
+    int s = 0;
+    while (a) { ++s; a >>= 1; }
+    return s;
+}
+
+// DC predictor of block b: the previous block of the same component in scan order (0 for the first)
+OTT_DEV int jpeg_dc_pred(const JpegJob &j, int b)
+{
+    const int mcu = b / 6, k = b - 6 * mcu;
+    int prev;
+    if (k >= 1 && k <= 3) prev = b - 1;
+    else if (mcu == 0) return 0;
+    else prev = k == 0 ? b - 3 : b - 6;                          // Y00 follows the previous MCU's Y11; chroma its own plane's block
+    return j.coef[(size_t)prev * 64];
+}
+
+struct JpegCount {
+    uint32_t n = 0;
+    OTT_DEV void put(uint32_t, int len) { n += (uint32_t)len; }
+};
+
+struct JpegEmit {
+    uint32_t *stream;
+    uint32_t pos, limit;
+    OTT_DEV void put(uint32_t code, int len)
+    {
+        if (len == 0 || pos + (uint32_t)len > limit) { pos += (uint32_t)len; return; }
+        const uint32_t w = pos >> 5, o = pos & 31u;
+        if (o + (uint32_t)len <= 32u) {
+            ott_atomic_or(stream + w, code << (32u - o - (uint32_t)len));
+        } else {
+            const uint32_t spill = o + (uint32_t)len - 32u;
+            ott_atomic_or(stream + w, code >> spill);
+            ott_atomic_or(stream + w + 1, code << (32u - spill));
+        }
+        pos += (uint32_t)len;
+    }
+};
+
+template <class Sink>
+OTT_DEV void jpeg_block_codes(const JpegJob &j, int b, Sink &sink)
+{
+    const JpegHuff &H = *j.huff;
+    const int tbl = (b % 6) >= 4;
+    const int16_t *c = j.coef + (size_t)b * 64;
+    const int diff = (int)c[0] - jpeg_dc_pred(j, b);
+    int s = jpeg_category(diff < 0 ? -diff : diff);
+    sink.put(H.dc_code[tbl][s], H.dc_len[tbl][s]);
+    if (s) sink.put((uint32_t)(diff < 0 ? diff - 1 : diff) & ((1u << s) - 1u), s);
+    int run = 0;
+    for (int k = 1; k < 64; ++k) {
+        const int v = c[k];
+        if (v == 0) { ++run; continue; }
+        while (run > 15) { sink.put(H.ac_code[tbl][0xF0], H.ac_len[tbl][0xF0]); run -= 16; }
+        s = jpeg_category(v < 0 ? -v : v);
+        const int sym = (run << 4) | s;
+        sink.put(H.ac_code[tbl][sym], H.ac_len[tbl][sym]);
+        sink.put((uint32_t)(v < 0 ? v - 1 : v) & ((1u << s) - 1u), s);
+        run = 0;
+    }
+    if (run) sink.put(H.ac_code[tbl][0], H.ac_len[tbl][0]);
+}
+
+OTT_DEV void jpeg_block_bits(const JpegJob &j, int b)
+{
+    if (b >= j.n_blocks) return;
+    JpegCount cnt;
+    jpeg_block_codes(j, b, cnt);
+    j.bits[b] = cnt.n;
+}
+
+OTT_DEV void jpeg_block_emit(const JpegJob &j, int b)
+{
+    if (b >= j.n_blocks) return;
+    JpegEmit e{j.stream, j.bits[b], j.stream_words * 32u};
+    jpeg_block_codes(j, b, e);
+}
+
+// byte k of the entropy-coded stream (the last byte is padded with 1 bits)
+OTT_DEV uint32_t jpeg_stream_byte(const JpegJob &j, uint32_t k, uint32_t total_bits)
+{
+    uint32_t v = (j.stream[k >> 2] >> (24u - 8u * (k & 3u))) & 255u;
+    if (8u * k + 8u > total_bits) v |= 0xFFu >> (total_bits & 7u);
+    return v;
+}
+
+constexpr int kJpegChunk = 64;         // stream bytes per thread in the stuffing pass
+
+OTT_DEV void jpeg_stuff_count(const JpegJob &j, int chunk)
+{
+    const uint32_t total_bits = j.bits[j.n_blocks], nbytes = (total_bits + 7u) >> 3;
+    const uint32_t k0 = (uint32_t)chunk * kJpegChunk;
+    if (k0 >= nbytes) return;
+    uint32_t n = 0;
+    for (uint32_t k = k0; k < ott_min((int)(k0 + kJpegChunk), (int)nbytes); ++k) n += jpeg_stream_byte(j, k, total_bits) == 0xFFu;
+    j.ff_count[chunk] = n;
+}
+
+// ff_count[] holds the exclusive scan of the counts; writes the chunk's bytes (and the stuffed zeros) to their place
+OTT_DEV void jpeg_stuff_write(const JpegJob &j, int chunk)
+{
+    const uint32_t total_bits = j.bits[j.n_blocks], nbytes = (total_bits + 7u) >> 3;
+    const uint32_t k0 = (uint32_t)chunk * kJpegChunk;
+    if (k0 >= nbytes) return;
+    uint32_t at = (uint32_t)j.header_bytes + k0 + j.ff_count[chunk];
+    for (uint32_t k = k0; k < ott_min((int)(k0 + kJpegChunk), (int)nbytes); ++k) {
+        const uint32_t v = jpeg_stream_byte(j, k, total_bits);
+        if (at < j.out_capacity) j.out[at] = (uint8_t)v;
+        ++at;
+        if (v == 0xFFu) {
+            if (at < j.out_capacity) j.out[at] = 0;
+            ++at;
+        }
+    }
+}
+
+// chunk 0 also closes the file: EOI after the stuffed data, total size and overflow flag for the host
+OTT_DEV void jpeg_finish(const JpegJob &j, int chunks)
+{
+    const uint32_t total_bits = j.bits[j.n_blocks], nbytes = (total_bits + 7u) >> 3;
+    const uint32_t at = (uint32_t)j.header_bytes + nbytes + j.ff_count[chunks];
+    const bool fits = at + 2u <= j.out_capacity && total_bits <= j.stream_words * 32u;
+    if (fits) { j.out[at] = 0xFF; j.out[at + 1] = 0xD9; }
+    j.result[0] = at + 2u;
+    j.result[1] = fits ? 0u : 1u;
+}
+
+}  // namespace ottgpu

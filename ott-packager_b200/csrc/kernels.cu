@@ -12,6 +12,7 @@
 #include "ladder_core.cuh"
 #include "yadif_core.cuh"
 #include "convert_core.cuh"
+#include "jpeg_core.cuh"
 
 namespace ottgpu {
 
@@ -288,6 +289,63 @@ __global__ void __launch_bounds__(256) convert_kernel(const ConvertJob j)
 __global__ void __launch_bounds__(256) convert_batch_kernel(const ConvertJob *__restrict__ jobs)
 {
     convert_position(jobs[blockIdx.z], blockIdx.x * 32 + (threadIdx.x & 31), blockIdx.y * 8 + (threadIdx.x >> 5));
+}
+
+// ---------------------------------------------------------------------------------------------- thumbnail JPEG (N4)
+__global__ void __launch_bounds__(128) jpeg_dct_kernel(const JpegJob j) { jpeg_block_dct(j, blockIdx.x * 128 + threadIdx.x); }
+__global__ void __launch_bounds__(128) jpeg_bits_kernel(const JpegJob j) { jpeg_block_bits(j, blockIdx.x * 128 + threadIdx.x); }
+__global__ void __launch_bounds__(128) jpeg_emit_kernel(const JpegJob j) { jpeg_block_emit(j, blockIdx.x * 128 + threadIdx.x); }
+__global__ void __launch_bounds__(128) jpeg_stuff_count_kernel(const JpegJob j) { jpeg_stuff_count(j, blockIdx.x * 128 + threadIdx.x); }
+__global__ void __launch_bounds__(128) jpeg_stuff_write_kernel(const JpegJob j, int chunks)
+{
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    jpeg_stuff_write(j, c);
+    if (c == 0) jpeg_finish(j, chunks);
+}
+// in-place exclusive scan of v[0..n), total to v[n]; one CTA (the arrays are a few hundred to a few ten thousand entries)
+__global__ void __launch_bounds__(1024) jpeg_scan_kernel(uint32_t *v, int n)
+{
+    __shared__ uint32_t part[1024];
+    const int t = threadIdx.x, per = (n + 1023) / 1024, i0 = t * per, i1 = min(i0 + per, n);
+    uint32_t sum = 0;
+    for (int i = i0; i < i1; ++i) sum += v[i];
+    part[t] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        const uint32_t add = t >= d ? part[t - d] : 0u;
+        __syncthreads();
+        part[t] += add;
+        __syncthreads();
+    }
+    uint32_t run = part[t] - sum;                               // exclusive prefix of this thread's segment
+    for (int i = i0; i < i1; ++i) {
+        const uint32_t x = v[i];
+        v[i] = run;
+        run += x;
+    }
+    if (t == 1023) v[n] = part[1023];
+}
+
+int jpeg_stuff_chunks(uint32_t stream_words) { return (int)(((size_t)stream_words * 4 + kJpegChunk - 1) / kJpegChunk); }
+
+cudaError_t launch_jpeg(const JpegJob &j, cudaStream_t s)
+{
+    if (j.n_blocks <= 0) return cudaSuccess;
+    const int gb = (j.n_blocks + 127) / 128;
+    cudaError_t e = cudaMemsetAsync(j.stream, 0, (size_t)j.stream_words * 4, s);
+    if (e != cudaSuccess) return e;
+    jpeg_dct_kernel<<<gb, 128, 0, s>>>(j);
+    jpeg_bits_kernel<<<gb, 128, 0, s>>>(j);
+    jpeg_scan_kernel<<<1, 1024, 0, s>>>(j.bits, j.n_blocks);
+    jpeg_emit_kernel<<<gb, 128, 0, s>>>(j);
+    // the stuffing pass is sized for the largest stream the buffers can hold; chunks beyond the real length exit at once
+    const int chunks = jpeg_stuff_chunks(j.stream_words), gc = (chunks + 127) / 128;
+    e = cudaMemsetAsync(j.ff_count, 0, (size_t)(chunks + 1) * 4, s);
+    if (e != cudaSuccess) return e;
+    jpeg_stuff_count_kernel<<<gc, 128, 0, s>>>(j);
+    jpeg_scan_kernel<<<1, 1024, 0, s>>>(j.ff_count, chunks);
+    jpeg_stuff_write_kernel<<<gc, 128, 0, s>>>(j, chunks);
+    return cudaGetLastError();
 }
 
 cudaError_t configure_kernels()

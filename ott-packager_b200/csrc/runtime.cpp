@@ -1579,3 +1579,200 @@ int ottgpu_converter_wait(ottgpu_converter *cv)
 void ottgpu_converter_destroy(ottgpu_converter *cv) { converter_free(cv); }
 
 }  // extern "C"
+
+/* ---------------------------------------------------------------------------------------------------- thumbnail JPEG (N4) */
+// transvideo.c:164-198 (save_frame_as_jpeg) on the GPU: see jpeg_core.cuh for what is and is not taken from libavcodec.
+#include "jpeg_tables.h"
+
+struct ottgpu_jpeg {
+    int gpu = 0, w = 0, h = 0, qscale = 3;
+    cudaStream_t stream = nullptr;
+    ottgpu::JpegJob job{};
+    uint8_t *d_planes = nullptr;                       // packed copy of host planes
+    size_t plane_off[3] = {0, 0, 0};
+    int plane_pitch[3] = {0, 0, 0}, plane_rows[3] = {0, 0, 0};
+    ottgpu::JpegHuff *d_huff = nullptr;
+    uint8_t *h_out = nullptr;                          // pinned: the file lands here first
+    uint32_t *h_result = nullptr;                      // pinned
+    std::vector<uint8_t> header;
+};
+
+namespace {
+
+// canonical Huffman codes from the bits / values lists (T.81 Annex C)
+void jpeg_codes(const unsigned char *bits, const unsigned char *vals, uint16_t *code, uint8_t *len)
+{
+    int k = 0;
+    uint32_t c = 0;
+    for (int l = 1; l <= 16; ++l) {
+        for (int i = 0; i < bits[l - 1]; ++i, ++k) {
+            code[vals[k]] = (uint16_t)c++;
+            len[vals[k]] = (uint8_t)l;
+        }
+        c <<= 1;
+    }
+}
+
+const unsigned char kMpeg1Intra[64] = {8,  16, 19, 22, 26, 27, 29, 34, 16, 16, 22, 24, 27, 29, 34, 37, 19, 22, 26, 27, 29, 34,
+                                       34, 38, 22, 22, 26, 27, 29, 34, 37, 40, 22, 26, 27, 29, 32, 35, 40, 48, 26, 27, 29, 32,
+                                       35, 40, 48, 58, 26, 27, 29, 34, 38, 46, 56, 69, 27, 29, 35, 38, 46, 56, 69, 83};
+const unsigned char kZigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                   41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                   30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+void put16(std::vector<uint8_t> &v, int x) { v.push_back((uint8_t)(x >> 8)); v.push_back((uint8_t)x); }
+
+void jpeg_free(ottgpu_jpeg *j)
+{
+    if (!j) return;
+    cudaSetDevice(j->gpu);
+    if (j->stream) { cudaStreamSynchronize(j->stream); cudaStreamDestroy(j->stream); }
+    cudaFree(j->d_planes);
+    cudaFree(j->d_huff);
+    cudaFree(j->job.coef);
+    cudaFree(j->job.bits);
+    cudaFree(j->job.stream);
+    cudaFree(j->job.out);
+    cudaFree(j->job.result);
+    cudaFree(j->job.ff_count);
+    cudaFreeHost(j->h_out);
+    cudaFreeHost(j->h_result);
+    delete j;
+}
+
+int jpeg_build(ottgpu_jpeg *j)
+{
+    using namespace ottgpu;
+    JpegJob &J = j->job;
+    J.width = j->w; J.height = j->h;
+    J.mcus_x = (j->w + 15) / 16; J.mcus_y = (j->h + 15) / 16;
+    J.n_blocks = 6 * J.mcus_x * J.mcus_y;
+    for (int i = 0; i < 64; ++i) J.q[i] = (uint16_t)std::min(std::max((kMpeg1Intra[i] * j->qscale) >> 3, 1), 255);
+    J.q[0] = 8;
+    // ---- header: SOI, COM, DQT, SOF0, DHT x4, SOS
+    std::vector<uint8_t> &H = j->header;
+    H = {0xFF, 0xD8};
+    const char com[] = "libottgpu";
+    H.push_back(0xFF); H.push_back(0xFE); put16(H, 2 + (int)sizeof(com) - 1);
+    H.insert(H.end(), com, com + sizeof(com) - 1);
+    H.push_back(0xFF); H.push_back(0xDB); put16(H, 67); H.push_back(0);
+    for (int k = 0; k < 64; ++k) H.push_back((uint8_t)J.q[kZigzag[k]]);
+    H.push_back(0xFF); H.push_back(0xC0); put16(H, 17); H.push_back(8); put16(H, j->h); put16(H, j->w); H.push_back(3);
+    const uint8_t comps[3][3] = {{1, 0x22, 0}, {2, 0x11, 0}, {3, 0x11, 0}};
+    for (auto &c : comps) H.insert(H.end(), c, c + 3);
+    struct T { int id; const unsigned char *bits, *vals; int n; } tabs[4] = {
+        {0x00, kJpeg_bits_dc_luma, kJpeg_val_dc_luma, 12}, {0x10, kJpeg_bits_ac_luma, kJpeg_val_ac_luma, 162},
+        {0x01, kJpeg_bits_dc_chroma, kJpeg_val_dc_chroma, 12}, {0x11, kJpeg_bits_ac_chroma, kJpeg_val_ac_chroma, 162}};
+    for (const T &t : tabs) {
+        H.push_back(0xFF); H.push_back(0xC4); put16(H, 2 + 1 + 16 + t.n); H.push_back((uint8_t)t.id);
+        H.insert(H.end(), t.bits, t.bits + 16);
+        H.insert(H.end(), t.vals, t.vals + t.n);
+    }
+    H.push_back(0xFF); H.push_back(0xDA); put16(H, 12); H.push_back(3);
+    const uint8_t scan[3][2] = {{1, 0x00}, {2, 0x11}, {3, 0x11}};
+    for (auto &c : scan) H.insert(H.end(), c, c + 2);
+    H.push_back(0); H.push_back(63); H.push_back(0);
+    J.header_bytes = (int)H.size();
+    // ---- tables and buffers
+    JpegHuff hf;
+    std::memset(&hf, 0, sizeof(hf));
+    jpeg_codes(kJpeg_bits_dc_luma, kJpeg_val_dc_luma, hf.dc_code[0], hf.dc_len[0]);
+    jpeg_codes(kJpeg_bits_dc_chroma, kJpeg_val_dc_chroma, hf.dc_code[1], hf.dc_len[1]);
+    jpeg_codes(kJpeg_bits_ac_luma, kJpeg_val_ac_luma, hf.ac_code[0], hf.ac_len[0]);
+    jpeg_codes(kJpeg_bits_ac_chroma, kJpeg_val_ac_chroma, hf.ac_code[1], hf.ac_len[1]);
+    CK(cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking));
+    CK(cudaMalloc((void **)&j->d_huff, sizeof(hf)));
+    CK(cudaMemcpy(j->d_huff, &hf, sizeof(hf), cudaMemcpyHostToDevice));
+    J.huff = j->d_huff;
+    // worst case of a block: 64 coefficients x (16-bit code + 10 bits) + DC: < 1700 bits; sized at 1728 (a multiple of 32)
+    const size_t words = (size_t)J.n_blocks * 54 + 8;
+    if (words * 4 > (1u << 30)) return fail(OTTGPU_ERR_ARG, "picture too large for the JPEG encoder");
+    J.stream_words = (uint32_t)words;
+    J.out_capacity = (uint32_t)(J.header_bytes + 2 * words * 4 + 2);     // every byte could be a stuffed 0xFF
+    CK(cudaMalloc((void **)&J.coef, (size_t)J.n_blocks * 64 * sizeof(int16_t)));
+    CK(cudaMalloc((void **)&J.bits, ((size_t)J.n_blocks + 1) * 4));
+    CK(cudaMalloc((void **)&J.stream, words * 4));
+    CK(cudaMalloc((void **)&J.out, J.out_capacity));
+    CK(cudaMalloc((void **)&J.result, 8));
+    CK(cudaMalloc((void **)&J.ff_count, ((size_t)jpeg_stuff_chunks(J.stream_words) + 1) * 4));
+    CK(cudaMemcpy(J.out, H.data(), H.size(), cudaMemcpyHostToDevice));
+    CK(cudaMallocHost((void **)&j->h_out, J.out_capacity));
+    CK(cudaMallocHost((void **)&j->h_result, 8));
+    const int cw = (j->w + 1) / 2, chh = (j->h + 1) / 2;
+    const int pw[3] = {j->w, cw, cw}, ph[3] = {j->h, chh, chh};
+    size_t at = 0;
+    for (int p = 0; p < 3; ++p) {
+        j->plane_pitch[p] = (pw[p] + 15) & ~15;
+        j->plane_rows[p] = ph[p];
+        j->plane_off[p] = at;
+        at += (size_t)j->plane_pitch[p] * ph[p];
+    }
+    CK(cudaMalloc((void **)&j->d_planes, at + 16));
+    return OTTGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ottgpu_jpeg_create(int gpu, int width, int height, int qscale, ottgpu_jpeg **out)
+{
+    if (!out) return fail(OTTGPU_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (width < 1 || height < 1 || width > 16384 || height > 16384) return fail(OTTGPU_ERR_ARG, "picture size out of range");
+    if (qscale < 1 || qscale > 31) return fail(OTTGPU_ERR_ARG, "qscale out of range (1..31, libavcodec's qmin..qmax)");
+    int rc = prepare_device(gpu);
+    if (rc) return rc;
+    ottgpu_jpeg *j = new ottgpu_jpeg();
+    j->gpu = gpu; j->w = width; j->h = height; j->qscale = qscale;
+    rc = jpeg_build(j);
+    if (rc) {
+        const std::string why = t_err;
+        jpeg_free(j);
+        t_err = why;
+        return rc;
+    }
+    *out = j;
+    return OTTGPU_OK;
+}
+
+size_t ottgpu_jpeg_max_bytes(const ottgpu_jpeg *j) { return j ? j->job.out_capacity : 0; }
+
+int ottgpu_jpeg_encode(ottgpu_jpeg *j, const ottgpu_picture *pic, void *dst, size_t dst_capacity, size_t *dst_bytes)
+{
+    if (!j || !pic || !dst || !dst_bytes) return fail(OTTGPU_ERR_ARG, "null argument");
+    if (pic->mem != OTTGPU_MEM_HOST && pic->mem != OTTGPU_MEM_DEVICE) return fail(OTTGPU_ERR_ARG, "unknown memory kind");
+    CK(cudaSetDevice(j->gpu));
+    const int cw = (j->w + 1) / 2;
+    const int row_bytes[3] = {j->w, cw, cw};
+    ottgpu::JpegJob job = j->job;
+    for (int p = 0; p < 3; ++p) {
+        if (!pic->plane[p]) return fail(OTTGPU_ERR_ARG, "null plane");
+        if (pic->stride[p] < row_bytes[p]) return fail(OTTGPU_ERR_ARG, "stride smaller than the row");
+        if (pic->mem == OTTGPU_MEM_HOST) {
+            uint8_t *d = j->d_planes + j->plane_off[p];
+            CK(cudaMemcpy2DAsync(d, (size_t)j->plane_pitch[p], pic->plane[p], (size_t)pic->stride[p], (size_t)row_bytes[p], (size_t)j->plane_rows[p],
+                                 cudaMemcpyHostToDevice, j->stream));
+            job.plane[p] = d;
+            job.pitch[p] = j->plane_pitch[p];
+        } else {
+            job.plane[p] = static_cast<const uint8_t *>(pic->plane[p]);
+            job.pitch[p] = pic->stride[p];
+        }
+    }
+    CK(ottgpu::launch_jpeg(job, j->stream));
+    CK(cudaMemcpyAsync(j->h_result, job.result, 8, cudaMemcpyDeviceToHost, j->stream));
+    CK(cudaStreamSynchronize(j->stream));
+    if (j->h_result[1]) return fail(OTTGPU_ERR_CUDA, "JPEG stream overflowed its buffer");
+    const size_t n = j->h_result[0];
+    *dst_bytes = n;
+    if (n > dst_capacity) return fail(OTTGPU_ERR_NOMEM, "destination buffer too small for the JPEG file");
+    CK(cudaMemcpyAsync(j->h_out, job.out, n, cudaMemcpyDeviceToHost, j->stream));
+    CK(cudaStreamSynchronize(j->stream));
+    std::memcpy(dst, j->h_out, n);
+    return OTTGPU_OK;
+}
+
+void ottgpu_jpeg_destroy(ottgpu_jpeg *j) { jpeg_free(j); }
+
+}  // extern "C"

@@ -5,6 +5,7 @@
 #include "ladder_core.cuh"
 #include "yadif_core.cuh"
 #include "convert_core.cuh"
+#include "jpeg_core.cuh"
 
 namespace ottgpu {
 
@@ -83,6 +84,32 @@ cudaError_t launch_convert_batch(const ConvertJob *jobs, int n_jobs, int max_w, 
     for (int z = 0; z < n_jobs; ++z)
         for (int r = 0; r < (max_rows + 7) / 8 * 8; ++r)
             for (int x = 0; x < ((max_w + kConvertGroup - 1) / kConvertGroup + 31) / 32 * 32; ++x) convert_position(jobs[z], x, r);
+    return cudaSuccess;
+}
+
+static void emu_scan(uint32_t *v, int n)
+{
+    uint32_t run = 0;
+    for (int i = 0; i < n; ++i) { const uint32_t x = v[i]; v[i] = run; run += x; }
+    v[n] = run;
+}
+
+int jpeg_stuff_chunks(uint32_t stream_words) { return (int)(((size_t)stream_words * 4 + kJpegChunk - 1) / kJpegChunk); }
+
+cudaError_t launch_jpeg(const JpegJob &j, cudaStream_t)
+{
+    if (j.n_blocks <= 0) return cudaSuccess;
+    std::memset(j.stream, 0, (size_t)j.stream_words * 4);
+    for (int b = 0; b < (j.n_blocks + 127) / 128 * 128; ++b) jpeg_block_dct(j, b);
+    for (int b = 0; b < (j.n_blocks + 127) / 128 * 128; ++b) jpeg_block_bits(j, b);
+    emu_scan(j.bits, j.n_blocks);
+    for (int b = j.n_blocks - 1; b >= 0; --b) jpeg_block_emit(j, b);        // any order: the positions are absolute
+    const int chunks = jpeg_stuff_chunks(j.stream_words);
+    std::memset(j.ff_count, 0, (size_t)(chunks + 1) * 4);
+    for (int c = 0; c < chunks; ++c) jpeg_stuff_count(j, c);
+    emu_scan(j.ff_count, chunks);
+    for (int c = 0; c < chunks; ++c) jpeg_stuff_write(j, c);
+    jpeg_finish(j, chunks);
     return cudaSuccess;
 }
 

@@ -576,3 +576,68 @@ def test_encoder_side_nvenc_surface_descriptor(lib, og, oracle, rt, host):
     host.ottgpu_transvideo_close(C.byref(tv))
     assert pool.unused() == 4 and not errors
     pool.close()
+
+
+# ------------------------------------------------------------------------------------------------ N4: thumbnail JPEG thread
+class Thumbnailer(C.Structure):               # ott-packager_b200/host/thumbnail_gpu.h
+    _fields_ = [("thumbnail_queue", C.c_void_p), ("msg_pool", C.c_void_p), ("gpu", C.c_int), ("identity", C.c_int),
+                ("directory", C.c_char_p), ("qscale", C.c_int), ("running", C.POINTER(C.c_int)), ("encoder", C.c_void_p),
+                ("file_buffer", C.c_void_p), ("file_capacity", C.c_size_t), ("written", C.c_int64), ("failed", C.c_int64),
+                ("last_bytes", C.c_size_t)]
+
+
+class ScaleStruct(C.Structure):               # transvideo.c:124-127
+    _fields_ = [("output_data", C.c_void_p * 4), ("output_stride", C.c_int * 4)]
+
+
+def test_thumbnail_thread_writes_the_jpeg_on_the_gpu(lib, og, oracle, rt, host, tmp_path):
+    """video_thumbnail_thread (transvideo.c:200-262) with save_frame_as_jpeg on the GPU: the scale_struct of the hand-off
+    (one allocation, strides 176/88/88, transvideo.c:2176-2183) comes off the reference's own queue, the file appears as
+    thumbnail<identity>.jpg, picture and struct are freed, the message goes back to the pool."""
+    import threading
+    libc = C.CDLL(None)
+    libc.malloc.restype, libc.malloc.argtypes = C.c_void_p, [C.c_size_t]
+    host.ottgpu_thumbnail_process.argtypes = [C.POINTER(Thumbnailer), C.POINTER(Msg)]
+    host.ottgpu_video_thumbnail_thread.argtypes = [C.c_void_p]
+    host.ottgpu_video_thumbnail_thread.restype = C.c_void_p
+    host.ottgpu_thumbnailer_close.argtypes = [C.POINTER(Thumbnailer)]
+    w, h = 176, 144
+    th = Thumbnailer()
+    th.thumbnail_queue = rt.dataqueue_create()
+    th.msg_pool = rt.memory_create(16, C.sizeof(Msg))
+    th.gpu, th.identity, th.directory, th.qscale = 0, 7, str(tmp_path).encode(), 0
+    run = C.c_int(1)
+    th.running = C.pointer(run)
+    free0 = rt.memory_unused(th.msg_pool)
+
+    def hand_off(frame):
+        pic = libc.malloc(frame.nbytes)                              # av_image_alloc(176, 144, YUV420P, align 1): one allocation
+        C.memmove(pic, frame.ctypes.data, frame.nbytes)
+        ss = C.cast(libc.malloc(C.sizeof(ScaleStruct)), C.POINTER(ScaleStruct))
+        ss.contents.output_data[0], ss.contents.output_data[1], ss.contents.output_data[2] = pic, pic + w * h, pic + w * h + 88 * 72
+        ss.contents.output_data[3] = None
+        ss.contents.output_stride[0], ss.contents.output_stride[1], ss.contents.output_stride[2], ss.contents.output_stride[3] = w, 88, 88, 0
+        m = C.cast(rt.memory_take(th.msg_pool, C.sizeof(Msg)), C.POINTER(Msg))
+        C.memset(m, 0, C.sizeof(Msg))
+        m.contents.buffer = C.cast(ss, C.c_void_p)
+        return m
+
+    f1, f2 = natural_i420(w, h, 12), natural_i420(w, h, 13, shift=40.0)
+    assert host.ottgpu_thumbnail_process(C.byref(th), hand_off(f1)) == 0
+    path = tmp_path / "thumbnail7.jpg"
+    assert path.read_bytes() == oracle.jpeg_encode(f1, w, h, 3)
+    assert th.written == 1 and th.last_bytes == path.stat().st_size and rt.memory_unused(th.msg_pool) == free0
+    # as the pthread body: polls the queue like the reference does
+    t = threading.Thread(target=host.ottgpu_video_thumbnail_thread, args=(C.addressof(th),))
+    t.start()
+    rt.dataqueue_put_front(th.thumbnail_queue, hand_off(f2))
+    for _ in range(300):
+        if th.written == 2:
+            break
+        time.sleep(0.01)
+    run.value = 0
+    t.join(5)
+    assert th.written == 2 and th.failed == 0
+    assert path.read_bytes() == oracle.jpeg_encode(f2, w, h, 3)
+    assert rt.memory_unused(th.msg_pool) == free0
+    host.ottgpu_thumbnailer_close(C.byref(th))
