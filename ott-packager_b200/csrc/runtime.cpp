@@ -367,7 +367,7 @@ const char *ottgpu_build_info(void)
 #if defined(OTTGPU_EMULATE)
     return "libottgpu EMULATION (tests/emu: kernel source compiled for the CPU; test infrastructure, not a product build)";
 #else
-    return "libottgpu sm_100a (hand-written CUDA kernels: ladder_kernel<1|2>, yadif_kernel, convert_kernel; no CPU fallback)";
+    return "libottgpu sm_100a (hand-written CUDA kernels: ladder_kernel<1|2>, yadif_kernel, convert_kernel, jpeg_*_kernel; no CPU fallback)";
 #endif
 }
 
