@@ -535,6 +535,43 @@ def run_workload(cx, name, Cn, steps, warmup, repeats, do_e2e, do_parity):
         for p in out_pools:
             p.close()
         host_pool.close()
+        # The box's own floor for one step's traffic: plain pinned copies of the same byte counts, every rank copying at the
+        # same time (uploads alone for the device-out variant, uploads + read-backs at once for the host-out one).  Not part
+        # of any timed region; it says how much of an end-to-end step is the PCIe / host-memory system of this box.
+        def link_floor(h2d_bytes, d2h_bytes, reps=6):
+            hin = torch.empty(int(h2d_bytes), dtype=torch.uint8).pin_memory()
+            din = torch.empty(int(h2d_bytes), dtype=torch.uint8, device="cuda")
+            hout = torch.empty(max(int(d2h_bytes), 1), dtype=torch.uint8).pin_memory()
+            dout = torch.empty(max(int(d2h_bytes), 1), dtype=torch.uint8, device="cuda")
+            s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+            def once():
+                with torch.cuda.stream(s1):
+                    din.copy_(hin, non_blocking=True)
+                if d2h_bytes > 65536:
+                    with torch.cuda.stream(s2):
+                        hout.copy_(dout, non_blocking=True)
+            once()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                once()
+            torch.cuda.synchronize()
+            ms = (time.perf_counter() - t0) * 1000.0 / reps
+            if dist is not None:
+                t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            del hin, din, hout, dout
+            return ms
+        for key in ("e2e_device_out", "e2e_host_out"):
+            e = res[key]
+            floor_ms = link_floor(e["h2d_bytes_per_step"], e["d2h_bytes_per_step"])
+            e["link_floor_ms_per_step"] = floor_ms
+            e["link_floor_share"] = floor_ms / e["ms_per_step"]
+            e["link_floor_note"] = ("plain pinned cudaMemcpyAsync of the step's %d H2D%s bytes, all %d rank(s) at once: the PCIe / host-memory "
+                                    "floor of THIS box at this rank count; share = floor / measured step" %
+                                    (e["h2d_bytes_per_step"], (" + %d D2H" % e["d2h_bytes_per_step"]) if e["d2h_bytes_per_step"] > 65536 else "", world))
     for p in dst_pools:
         p.close()
     src_pool.close()
