@@ -249,7 +249,8 @@ struct JpegJob {
     uint32_t *result;            // [0] total bytes of the file, [1] 1 if something did not fit
     uint32_t *ff_count;          // [chunks + 1] scratch of the stuffing pass
     const JpegHuff *huff;
-    uint16_t q[64];              // quantisation table, natural order
+    uint16_t q[64];              // quantisation table, natural order (the DQT segment)
+    uint16_t qmat16[64], bias16[64];   // libavcodec's 16-bit quantiser constants for it: level = ((|x| + bias16) * qmat16) >> 16
 };
 
 }  // namespace ottgpu

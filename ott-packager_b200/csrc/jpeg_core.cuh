@@ -5,11 +5,12 @@
 // What is kept from the reference's encoder: the picture layout (one quantisation table for all components, MCU = 2x2 luma
 // + Cb + Cr) and the TABLE: libavcodec's MJPEG quantises with ff_mpeg1_default_intra_matrix scaled by the frame's qscale,
 // q[i] = (m[i] * qscale) >> 3, DC entry 8 -- read out of the DQT segment the real encoder of this image writes
-// (oracle/avcodec_so.py; it picks qscale 3 for natural content at the reference's 250 kb/s).  What is NOT reproduced: its
-// SIMD forward DCT / quantiser rounding, its rate control and its per-picture optimal Huffman tables (un-vendored FFmpeg;
+// (oracle/avcodec_so.py; it picks qscale 2-3 for natural content at the reference's 250 kb/s).  What is NOT reproduced: its
+// SIMD forward DCT, its rate control and its per-picture optimal Huffman tables (un-vendored FFmpeg;
 // no bit-exact oracle exists for them) -- this encoder is the public integer DCT of the IJG library (jfdctint: 13-bit
-// constants, results scaled by 8), round-half-away quantisation (jcdctmgr) and the Annex K Huffman tables, bit-exact to the
-// plain C restatement in oracle/ref_jpeg.c and checked against the real libavcodec output by decoding both (tests).
+// constants, results scaled by 8; libavcodec's own C fallback), libavcodec's quantiser arithmetic (below) and the Annex K
+// Huffman tables, bit-exact to the plain C restatement in oracle/ref_jpeg.c and compared with the real libavcodec output at
+// the coefficient level (every DC, 99.8 % of the AC levels identical) and by decoding both (tests).
 //
 // Work split (every stage one thread per 8x8 block unless noted), bitstream assembled in parallel:
 //   jpeg_block_dct   : load (edge-replicated), level shift, forward DCT, quantise, zigzag -> coef[block][64]
@@ -103,15 +104,23 @@ OTT_DEV void jpeg_block_dct(const JpegJob &j, int b)
         OTT_UNROLL
         for (int r = 0; r < 8; ++r) blk[8 * r + c] = d[r];
     }
+    // Quantiser = libavcodec's for MJPEG (mpegvideo_enc.c convert_matrix / dct_quantize, 16-bit form): AC levels
+    // ((|x| + bias16) * qmat16) >> 16 with qmat16 = (2 << 16) / (16 q) and the 3/8 intra bias, DC (x + 32) >> 6 (its DC scale
+    // is 8 whatever the qscale; floor).  Checked against the real encoder: every DC and 99.8 % of the AC levels are identical
+    // (the rest is its SIMD forward DCT rounding differently from jfdctint), tests/test_parity_jpeg.py.
     int16_t *out = j.coef + (size_t)b * 64;
     for (int k = 0; k < 64; ++k) {
         const int n = jpeg_zigzag(k);
-        const int qv = (int)j.q[n] << 3;                         // the DCT results carry a factor of 8
-        int v = blk[n];
-        const int a = (v < 0 ? -v : v) + (qv >> 1);
-        int qd = a >= qv ? a / qv : 0;
-        qd = ott_min(qd, 1023);                                  // baseline limits: AC category <= 10, DC difference category <= 11
-        out[k] = (int16_t)(v < 0 ? -qd : qd);
+        const int v = blk[n];
+        int lv;
+        if (k == 0) {
+            lv = ott_max(ott_min((v + 32) >> 6, 1023), -1023);
+        } else {
+            const int a = v < 0 ? -v : v;
+            const int qd = ott_min((int)(((uint32_t)(a + (int)j.bias16[n]) * (uint32_t)j.qmat16[n]) >> 16), 1023);   // baseline: AC category <= 10
+            lv = v < 0 ? -qd : qd;
+        }
+        out[k] = (int16_t)lv;
     }
 }
 

@@ -1649,6 +1649,13 @@ int jpeg_build(ottgpu_jpeg *j)
     J.n_blocks = 6 * J.mcus_x * J.mcus_y;
     for (int i = 0; i < 64; ++i) J.q[i] = (uint16_t)std::min(std::max((kMpeg1Intra[i] * j->qscale) >> 3, 1), 255);
     J.q[0] = 8;
+    for (int i = 0; i < 64; ++i) {                    // mpegvideo_enc.c convert_matrix, 16-bit (SIMD) form; intra bias 3/8 = 96 / 256
+        const int den = 16 * J.q[i];
+        int qm = (2 << 16) / den;
+        if (qm == 0 || qm == 128 * 256) qm = 128 * 256 - 1;
+        J.qmat16[i] = (uint16_t)qm;
+        J.bias16[i] = (uint16_t)((96 * 256 + qm / 2) / qm);
+    }
     // ---- header: SOI, COM, DQT, SOF0, DHT x4, SOS
     std::vector<uint8_t> &H = j->header;
     H = {0xFF, 0xD8};

@@ -3,8 +3,9 @@
  * bit-exact: the parallel GPU formulation == the sequential CPU restatement (oracle/ref_jpeg.c), byte for byte;
  * decodes: libjpeg (cv2.imdecode) accepts the file and returns the picture;
  * pinned to the REAL reference encoder (oracle/avcodec_so.py drives the bundled libavcodec the way the reference does):
-   same quantisation table for the qscale its rate control picked, luma PSNR not below its file's (-0.35 / +1 dB), size below 1.6x
-   (standard Annex K tables instead of its per-picture optimal Huffman tables).  libavcodec's BYTES are not reproduced (see jpeg_core.cuh).
+   same quantisation table for the qscale its rate control picked, the same quantised levels (every DC, > 99.5 % of the AC
+   levels: the quantiser is libavcodec's, the rest is its SIMD DCT), luma PSNR within 0.1 dB, size below 1.3x (standard Annex K
+   tables instead of its per-picture optimal Huffman tables).  libavcodec's BYTES are not reproduced (see jpeg_core.cuh).
 """
 import numpy as np
 import pytest
@@ -78,8 +79,17 @@ def test_against_the_real_libavcodec_encoder(lib, og, oracle):
         seg_ref, seg_our = dict(A.segments(ref)), dict(A.segments(ours))
         assert seg_our[0xDB] == seg_ref[0xDB]                    # identical quantisation table segment
         assert seg_our[0xC0] == seg_ref[0xC0]                    # identical frame header: 8 bit, size, 3 components 2x2/1x1/1x1, table 0
+        # coefficient level: both files entropy-decoded (oracle/jpeg_parse.py).  Every DC level is identical; so are the AC
+        # levels except where libavcodec's SIMD forward DCT rounds differently from the integer DCT used here (~0.2 %)
+        from oracle import jpeg_parse as P
+        cr, co = P.parse(ref)["blocks"], P.parse(ours)["blocks"]
+        for comp in (1, 2, 3):
+            assert cr[comp].shape == co[comp].shape
+            assert np.array_equal(cr[comp][:, 0], co[comp][:, 0]), "DC levels differ from libavcodec's"
+            same = np.mean(cr[comp][:, 1:] == co[comp][:, 1:])
+            assert same > 0.995 and np.abs(cr[comp] - co[comp]).max() <= 1, (comp, same)
         src = fr[:w * h].reshape(h, w)
         p_ref, p_our = _psnr(_decode_luma(ref), src), _psnr(_decode_luma(ours), src)
-        assert p_ref - 0.35 < p_our < p_ref + 1.0, (p_ref, p_our)   # same table, same picture: the same quality (ours rounds to nearest)
+        assert abs(p_ref - p_our) < 0.1, (p_ref, p_our)          # same table, same quantiser: the same quality
         # Annex K tables (four DHT segments, 420 bytes) against libavcodec's per-picture optimal ones: larger, but bounded
-        assert len(ours) < 1.6 * len(ref), (len(ours), len(ref))
+        assert len(ours) < 1.3 * len(ref), (len(ours), len(ref))
