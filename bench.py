@@ -538,7 +538,7 @@ def run_workload(cx, name, Cn, steps, warmup, repeats, do_e2e, do_parity):
         # The box's own floor for one step's traffic: plain pinned copies of the same byte counts, every rank copying at the
         # same time (uploads alone for the device-out variant, uploads + read-backs at once for the host-out one).  Not part
         # of any timed region; it says how much of an end-to-end step is the PCIe / host-memory system of this box.
-        def link_floor(h2d_bytes, d2h_bytes, reps=6):
+        def link_floor(h2d_bytes, d2h_bytes, reps=8):
             hin = torch.empty(int(h2d_bytes), dtype=torch.uint8).pin_memory()
             din = torch.empty(int(h2d_bytes), dtype=torch.uint8, device="cuda")
             hout = torch.empty(max(int(d2h_bytes), 1), dtype=torch.uint8).pin_memory()
@@ -552,12 +552,23 @@ def run_workload(cx, name, Cn, steps, warmup, repeats, do_e2e, do_parity):
                     with torch.cuda.stream(s2):
                         hout.copy_(dout, non_blocking=True)
             once()
+            once()
             barrier()
-            t0 = time.perf_counter()
-            for _ in range(reps):
+            best = None
+            for _ in range(reps):                            # the floor is the best repetition: event-timed on the device
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                barrier()                                    # all ranks copy at the same time
+                e0.record()
+                s1.wait_event(e0)
+                s2.wait_event(e0)
                 once()
-            torch.cuda.synchronize()
-            ms = (time.perf_counter() - t0) * 1000.0 / reps
+                torch.cuda.current_stream().wait_stream(s1)
+                torch.cuda.current_stream().wait_stream(s2)
+                e1.record()
+                torch.cuda.synchronize()
+                t = e0.elapsed_time(e1)
+                best = t if best is None else min(best, t)
+            ms = best
             if dist is not None:
                 t = torch.tensor([ms], device="cuda", dtype=torch.float64)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -232,9 +232,10 @@ int ottgpu_filter_table(int src_n, int dst_n, int filter, int target, int vertic
  * Baseline JPEG, 4:2:0, planes taken as Y/Cb/Cr as they are, ONE quantisation table for all components built the way
  * libavcodec's MJPEG encoder builds it: q[i] = clip((ff_mpeg1_default_intra_matrix[i] * qscale) >> 3, 1, 255), q[0] = 8
  * (it picks qscale 2-3 for natural content at the reference's 250 kb/s), and its quantiser arithmetic (3/8 intra bias, DC
- * scale 8): every DC level and > 99.5 % of the AC levels equal the real encoder's.  The forward DCT (IJG integer DCT) and
- * the (standard, Annex K) Huffman tables are this library's own: the files decode to the same picture as the reference's,
- * they are not byte-identical to libavcodec's (no bit-exact oracle for its SIMD DCT / rate control / optimal tables).
+ * scale 8): every DC level and > 99.5 % of the AC levels equal the real encoder's; like libavcodec the picture is coded
+ * with its own optimal Huffman tables (same segment sequence COM DQT DHT SOF0 SOS, file size within 2 % of its file).
+ * The forward DCT (IJG integer DCT) and the table construction are this library's own: the files decode to the same
+ * picture as the reference's, they are not byte-identical (no bit-exact oracle for its SIMD DCT / rate control).
  */
 typedef struct ottgpu_jpeg ottgpu_jpeg;
 int  ottgpu_jpeg_create(int gpu, int width, int height, int qscale, ottgpu_jpeg **out);

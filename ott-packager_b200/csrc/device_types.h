@@ -248,7 +248,8 @@ struct JpegJob {
     int header_bytes;
     uint32_t *result;            // [0] total bytes of the file, [1] 1 if something did not fit
     uint32_t *ff_count;          // [chunks + 1] scratch of the stuffing pass
-    const JpegHuff *huff;
+    uint32_t *hist;              // [4][256] symbol counts of the picture: DC luma, DC chroma, AC luma, AC chroma
+    const JpegHuff *huff;        // the picture's tables (device memory, written between the two launches)
     uint16_t q[64];              // quantisation table, natural order (the DQT segment)
     uint16_t qmat16[64], bias16[64];   // libavcodec's 16-bit quantiser constants for it: level = ((|x| + bias16) * qmat16) >> 16
 };

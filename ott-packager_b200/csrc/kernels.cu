@@ -297,6 +297,7 @@ __global__ void __launch_bounds__(256) convert_batch_kernel(const ConvertJob *__
 
 // ---------------------------------------------------------------------------------------------- thumbnail JPEG (N4)
 __global__ void __launch_bounds__(128) jpeg_dct_kernel(const JpegJob j) { jpeg_block_dct(j, blockIdx.x * 128 + threadIdx.x); }
+__global__ void __launch_bounds__(128) jpeg_hist_kernel(const JpegJob j) { jpeg_block_hist(j, blockIdx.x * 128 + threadIdx.x); }
 __global__ void __launch_bounds__(128) jpeg_bits_kernel(const JpegJob j) { jpeg_block_bits(j, blockIdx.x * 128 + threadIdx.x); }
 __global__ void __launch_bounds__(128) jpeg_emit_kernel(const JpegJob j) { jpeg_block_emit(j, blockIdx.x * 128 + threadIdx.x); }
 __global__ void __launch_bounds__(128) jpeg_stuff_count_kernel(const JpegJob j) { jpeg_stuff_count(j, blockIdx.x * 128 + threadIdx.x); }
@@ -332,13 +333,25 @@ __global__ void __launch_bounds__(1024) jpeg_scan_kernel(uint32_t *v, int n)
 
 int jpeg_stuff_chunks(uint32_t stream_words) { return (int)(((size_t)stream_words * 4 + kJpegChunk - 1) / kJpegChunk); }
 
-cudaError_t launch_jpeg(const JpegJob &j, cudaStream_t s)
+// phase 1: coefficients + symbol histogram (the host then builds the picture's Huffman tables)
+cudaError_t launch_jpeg_analyse(const JpegJob &j, cudaStream_t s)
+{
+    if (j.n_blocks <= 0) return cudaSuccess;
+    const int gb = (j.n_blocks + 127) / 128;
+    cudaError_t e = cudaMemsetAsync(j.hist, 0, 4 * 256 * sizeof(uint32_t), s);
+    if (e != cudaSuccess) return e;
+    jpeg_dct_kernel<<<gb, 128, 0, s>>>(j);
+    jpeg_hist_kernel<<<gb, 128, 0, s>>>(j);
+    return cudaGetLastError();
+}
+
+// phase 2: lengths, positions, codes, byte stuffing with the tables in j.huff
+cudaError_t launch_jpeg_encode(const JpegJob &j, cudaStream_t s)
 {
     if (j.n_blocks <= 0) return cudaSuccess;
     const int gb = (j.n_blocks + 127) / 128;
     cudaError_t e = cudaMemsetAsync(j.stream, 0, (size_t)j.stream_words * 4, s);
     if (e != cudaSuccess) return e;
-    jpeg_dct_kernel<<<gb, 128, 0, s>>>(j);
     jpeg_bits_kernel<<<gb, 128, 0, s>>>(j);
     jpeg_scan_kernel<<<1, 1024, 0, s>>>(j.bits, j.n_blocks);
     jpeg_emit_kernel<<<gb, 128, 0, s>>>(j);

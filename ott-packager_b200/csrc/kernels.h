@@ -26,10 +26,12 @@ cudaError_t launch_convert(const ConvertJob &job, cudaStream_t s);
 // many pictures in one launch; jobs live in device memory; max_w / max_rows bound the grid (rows = Y + U + V rows)
 cudaError_t launch_convert_batch(const ConvertJob *jobs, int n_jobs, int max_w, int max_rows, cudaStream_t s);
 
-// thumbnail JPEG: DCT / entropy length / scan / emit / byte stuffing launches on `s`; j.stream and j.ff_count
-// are zeroed here.  The job is passed by value (kernel parameter).
+// thumbnail JPEG, two phases on `s` with the job passed by value (kernel parameter):
+//   analyse: DCT + quantiser -> j.coef, symbol histogram -> j.hist (zeroed here); the host builds the picture's tables
+//   encode : entropy length / scan / emit / byte stuffing with the tables in j.huff (j.stream and j.ff_count zeroed here)
 struct JpegJob;
-cudaError_t launch_jpeg(const JpegJob &j, cudaStream_t s);
+cudaError_t launch_jpeg_analyse(const JpegJob &j, cudaStream_t s);
+cudaError_t launch_jpeg_encode(const JpegJob &j, cudaStream_t s);
 int jpeg_stuff_chunks(uint32_t stream_words);
 
 cudaError_t configure_kernels();

@@ -1582,7 +1582,6 @@ void ottgpu_converter_destroy(ottgpu_converter *cv) { converter_free(cv); }
 
 /* ---------------------------------------------------------------------------------------------------- thumbnail JPEG (N4) */
 // transvideo.c:164-198 (save_frame_as_jpeg) on the GPU: see jpeg_core.cuh for what is and is not taken from libavcodec.
-#include "jpeg_tables.h"
 
 struct ottgpu_jpeg {
     int gpu = 0, w = 0, h = 0, qscale = 3;
@@ -1593,11 +1592,73 @@ struct ottgpu_jpeg {
     int plane_pitch[3] = {0, 0, 0}, plane_rows[3] = {0, 0, 0};
     ottgpu::JpegHuff *d_huff = nullptr;
     uint8_t *h_out = nullptr;                          // pinned: the file lands here first
-    uint32_t *h_result = nullptr;                      // pinned
-    std::vector<uint8_t> header;
+    uint32_t *h_result = nullptr, *h_hist = nullptr;   // pinned
+    ottgpu::JpegHuff *h_huff = nullptr;                // pinned
+    uint8_t *h_header = nullptr;                       // pinned: SOI .. SOS of this picture
+    std::vector<uint8_t> prefix, sof;                  // SOI, COM, DQT | SOF0: the same for every picture; the picture's DHT goes between them
 };
 
 namespace {
+
+constexpr size_t kJpegMaxHeader = 2048;               // prefix (~110 bytes) + four DHT segments (<= 4 x 277) + SOS (14)
+
+const unsigned char kMpeg1Intra[64] = {8,  16, 19, 22, 26, 27, 29, 34, 16, 16, 22, 24, 27, 29, 34, 37, 19, 22, 26, 27, 29, 34,
+                                       34, 38, 22, 22, 26, 27, 29, 34, 37, 40, 22, 26, 27, 29, 32, 35, 40, 48, 26, 27, 29, 32,
+                                       35, 40, 48, 58, 26, 27, 29, 34, 38, 46, 56, 69, 27, 29, 35, 38, 46, 56, 69, 83};
+const unsigned char kZigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                   41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                   30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+void put16(std::vector<uint8_t> &v, int x) { v.push_back((uint8_t)(x >> 8)); v.push_back((uint8_t)x); }
+
+// Optimal Huffman table of one symbol histogram, code lengths limited to 16 bits: the procedure of ITU-T T.81 Annex K.2 as
+// the IJG library implements it (jpeg_gen_optimal_table): merge the two least frequent entries until one tree is left, with
+// one reserved code point so that no code is all ones; then shorten codes longer than 16 bits.
+// bits[l-1] = number of codes of length l, vals = the symbols in order of increasing code length.
+void jpeg_optimal_table(const uint32_t *hist, int nsym, unsigned char bits[16], unsigned char *vals, int *nvals)
+{
+    long freq[257];
+    int codesize[257], others[257];
+    unsigned char nbits[33];
+    for (int i = 0; i < 257; ++i) { freq[i] = i < nsym ? (long)hist[i] : 0; codesize[i] = 0; others[i] = -1; }
+    std::memset(nbits, 0, sizeof(nbits));
+    freq[256] = 1;
+    for (;;) {
+        int c1 = -1, c2 = -1;
+        long v = 1000000000L;
+        for (int i = 0; i <= 256; ++i)
+            if (freq[i] && freq[i] <= v) { v = freq[i]; c1 = i; }
+        v = 1000000000L;
+        for (int i = 0; i <= 256; ++i)
+            if (freq[i] && freq[i] <= v && i != c1) { v = freq[i]; c2 = i; }
+        if (c2 < 0) break;
+        freq[c1] += freq[c2];
+        freq[c2] = 0;
+        for (codesize[c1]++; others[c1] >= 0;) { c1 = others[c1]; codesize[c1]++; }
+        others[c1] = c2;
+        for (codesize[c2]++; others[c2] >= 0;) { c2 = others[c2]; codesize[c2]++; }
+    }
+    for (int i = 0; i <= 256; ++i)
+        if (codesize[i]) nbits[std::min(codesize[i], 32)]++;
+    for (int i = 32; i > 16; --i)
+        while (nbits[i] > 0) {
+            int j = i - 2;
+            while (nbits[j] == 0) --j;
+            nbits[i] -= 2;
+            nbits[i - 1]++;
+            nbits[j + 1] += 2;
+            nbits[j]--;
+        }
+    int i = 16;
+    while (i > 0 && nbits[i] == 0) --i;
+    if (i > 0) nbits[i]--;                              // the reserved code point
+    std::memcpy(bits, nbits + 1, 16);
+    int p = 0;
+    for (int l = 1; l <= 32; ++l)
+        for (int sym = 0; sym < 256; ++sym)
+            if (codesize[sym] == l) vals[p++] = (unsigned char)sym;
+    *nvals = p;
+}
 
 // canonical Huffman codes from the bits / values lists (T.81 Annex C)
 void jpeg_codes(const unsigned char *bits, const unsigned char *vals, uint16_t *code, uint8_t *len)
@@ -1613,15 +1674,6 @@ void jpeg_codes(const unsigned char *bits, const unsigned char *vals, uint16_t *
     }
 }
 
-const unsigned char kMpeg1Intra[64] = {8,  16, 19, 22, 26, 27, 29, 34, 16, 16, 22, 24, 27, 29, 34, 37, 19, 22, 26, 27, 29, 34,
-                                       34, 38, 22, 22, 26, 27, 29, 34, 37, 40, 22, 26, 27, 29, 32, 35, 40, 48, 26, 27, 29, 32,
-                                       35, 40, 48, 58, 26, 27, 29, 34, 38, 46, 56, 69, 27, 29, 35, 38, 46, 56, 69, 83};
-const unsigned char kZigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
-                                   41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
-                                   30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
-
-void put16(std::vector<uint8_t> &v, int x) { v.push_back((uint8_t)(x >> 8)); v.push_back((uint8_t)x); }
-
 void jpeg_free(ottgpu_jpeg *j)
 {
     if (!j) return;
@@ -1635,8 +1687,12 @@ void jpeg_free(ottgpu_jpeg *j)
     cudaFree(j->job.out);
     cudaFree(j->job.result);
     cudaFree(j->job.ff_count);
+    cudaFree(j->job.hist);
     cudaFreeHost(j->h_out);
     cudaFreeHost(j->h_result);
+    cudaFreeHost(j->h_hist);
+    cudaFreeHost(j->h_huff);
+    cudaFreeHost(j->h_header);
     delete j;
 }
 
@@ -1656,55 +1712,40 @@ int jpeg_build(ottgpu_jpeg *j)
         J.qmat16[i] = (uint16_t)qm;
         J.bias16[i] = (uint16_t)((96 * 256 + qm / 2) / qm);
     }
-    // ---- header: SOI, COM, DQT, SOF0, DHT x4, SOS
-    std::vector<uint8_t> &H = j->header;
+    // ---- the parts of the header every picture shares (segment order as libavcodec writes it: SOI COM DQT DHT SOF0 SOS)
+    std::vector<uint8_t> &H = j->prefix;
     H = {0xFF, 0xD8};
     const char com[] = "libottgpu";
     H.push_back(0xFF); H.push_back(0xFE); put16(H, 2 + (int)sizeof(com) - 1);
     H.insert(H.end(), com, com + sizeof(com) - 1);
     H.push_back(0xFF); H.push_back(0xDB); put16(H, 67); H.push_back(0);
     for (int k = 0; k < 64; ++k) H.push_back((uint8_t)J.q[kZigzag[k]]);
-    H.push_back(0xFF); H.push_back(0xC0); put16(H, 17); H.push_back(8); put16(H, j->h); put16(H, j->w); H.push_back(3);
+    std::vector<uint8_t> &F = j->sof;
+    F = {0xFF, 0xC0};
+    put16(F, 17); F.push_back(8); put16(F, j->h); put16(F, j->w); F.push_back(3);
     const uint8_t comps[3][3] = {{1, 0x22, 0}, {2, 0x11, 0}, {3, 0x11, 0}};
-    for (auto &c : comps) H.insert(H.end(), c, c + 3);
-    struct T { int id; const unsigned char *bits, *vals; int n; } tabs[4] = {
-        {0x00, kJpeg_bits_dc_luma, kJpeg_val_dc_luma, 12}, {0x10, kJpeg_bits_ac_luma, kJpeg_val_ac_luma, 162},
-        {0x01, kJpeg_bits_dc_chroma, kJpeg_val_dc_chroma, 12}, {0x11, kJpeg_bits_ac_chroma, kJpeg_val_ac_chroma, 162}};
-    for (const T &t : tabs) {
-        H.push_back(0xFF); H.push_back(0xC4); put16(H, 2 + 1 + 16 + t.n); H.push_back((uint8_t)t.id);
-        H.insert(H.end(), t.bits, t.bits + 16);
-        H.insert(H.end(), t.vals, t.vals + t.n);
-    }
-    H.push_back(0xFF); H.push_back(0xDA); put16(H, 12); H.push_back(3);
-    const uint8_t scan[3][2] = {{1, 0x00}, {2, 0x11}, {3, 0x11}};
-    for (auto &c : scan) H.insert(H.end(), c, c + 2);
-    H.push_back(0); H.push_back(63); H.push_back(0);
-    J.header_bytes = (int)H.size();
-    // ---- tables and buffers
-    JpegHuff hf;
-    std::memset(&hf, 0, sizeof(hf));
-    jpeg_codes(kJpeg_bits_dc_luma, kJpeg_val_dc_luma, hf.dc_code[0], hf.dc_len[0]);
-    jpeg_codes(kJpeg_bits_dc_chroma, kJpeg_val_dc_chroma, hf.dc_code[1], hf.dc_len[1]);
-    jpeg_codes(kJpeg_bits_ac_luma, kJpeg_val_ac_luma, hf.ac_code[0], hf.ac_len[0]);
-    jpeg_codes(kJpeg_bits_ac_chroma, kJpeg_val_ac_chroma, hf.ac_code[1], hf.ac_len[1]);
+    for (auto &c : comps) F.insert(F.end(), c, c + 3);
+    // ---- buffers
     CK(cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking));
-    CK(cudaMalloc((void **)&j->d_huff, sizeof(hf)));
-    CK(cudaMemcpy(j->d_huff, &hf, sizeof(hf), cudaMemcpyHostToDevice));
+    CK(cudaMalloc((void **)&j->d_huff, sizeof(JpegHuff)));
     J.huff = j->d_huff;
     // worst case of a block: 64 coefficients x (16-bit code + 10 bits) + DC: < 1700 bits; sized at 1728 (a multiple of 32)
     const size_t words = (size_t)J.n_blocks * 54 + 8;
     if (words * 4 > (1u << 30)) return fail(OTTGPU_ERR_ARG, "picture too large for the JPEG encoder");
     J.stream_words = (uint32_t)words;
-    J.out_capacity = (uint32_t)(J.header_bytes + 2 * words * 4 + 2);     // every byte could be a stuffed 0xFF
+    J.out_capacity = (uint32_t)(kJpegMaxHeader + 2 * words * 4 + 2);     // every byte could be a stuffed 0xFF
     CK(cudaMalloc((void **)&J.coef, (size_t)J.n_blocks * 64 * sizeof(int16_t)));
     CK(cudaMalloc((void **)&J.bits, ((size_t)J.n_blocks + 1) * 4));
     CK(cudaMalloc((void **)&J.stream, words * 4));
     CK(cudaMalloc((void **)&J.out, J.out_capacity));
     CK(cudaMalloc((void **)&J.result, 8));
     CK(cudaMalloc((void **)&J.ff_count, ((size_t)jpeg_stuff_chunks(J.stream_words) + 1) * 4));
-    CK(cudaMemcpy(J.out, H.data(), H.size(), cudaMemcpyHostToDevice));
+    CK(cudaMalloc((void **)&J.hist, 4 * 256 * sizeof(uint32_t)));
     CK(cudaMallocHost((void **)&j->h_out, J.out_capacity));
     CK(cudaMallocHost((void **)&j->h_result, 8));
+    CK(cudaMallocHost((void **)&j->h_hist, 4 * 256 * sizeof(uint32_t)));
+    CK(cudaMallocHost((void **)&j->h_huff, sizeof(JpegHuff)));
+    CK(cudaMallocHost((void **)&j->h_header, kJpegMaxHeader));
     const int cw = (j->w + 1) / 2, chh = (j->h + 1) / 2;
     const int pw[3] = {j->w, cw, cw}, ph[3] = {j->h, chh, chh};
     size_t at = 0;
@@ -1716,6 +1757,36 @@ int jpeg_build(ottgpu_jpeg *j)
     }
     CK(cudaMalloc((void **)&j->d_planes, at + 16));
     return OTTGPU_OK;
+}
+
+// this picture's tables from its symbol histogram: JpegHuff for the kernels, DHT x4 + SOS appended to the prefix
+size_t jpeg_picture_header(ottgpu_jpeg *j)
+{
+    ottgpu::JpegHuff &hf = *j->h_huff;
+    std::memset(&hf, 0, sizeof(hf));
+    uint8_t *H = j->h_header;
+    size_t n = j->prefix.size();
+    std::memcpy(H, j->prefix.data(), n);
+    // ONE DHT segment holding the four tables in libavcodec's order: DC luma, DC chroma, AC luma, AC chroma
+    const int ids[4] = {0x00, 0x01, 0x10, 0x11};
+    const size_t len_at = n + 2;
+    H[n++] = 0xFF; H[n++] = 0xC4; n += 2;
+    for (int t = 0; t < 4; ++t) {
+        unsigned char bits[16], vals[256];
+        int nv = 0;
+        jpeg_optimal_table(j->h_hist + 256 * t, t < 2 ? 12 : 256, bits, vals, &nv);
+        if (t < 2) jpeg_codes(bits, vals, hf.dc_code[t], hf.dc_len[t]);
+        else jpeg_codes(bits, vals, hf.ac_code[t - 2], hf.ac_len[t - 2]);
+        H[n++] = (uint8_t)ids[t];
+        std::memcpy(H + n, bits, 16); n += 16;
+        std::memcpy(H + n, vals, nv); n += nv;
+    }
+    const size_t seg = n - len_at;
+    H[len_at] = (uint8_t)(seg >> 8); H[len_at + 1] = (uint8_t)seg;
+    std::memcpy(H + n, j->sof.data(), j->sof.size()); n += j->sof.size();
+    const uint8_t sos[14] = {0xFF, 0xDA, 0, 12, 3, 1, 0x00, 2, 0x11, 3, 0x11, 0, 63, 0};
+    std::memcpy(H + n, sos, sizeof(sos));
+    return n + sizeof(sos);
 }
 
 }  // namespace
@@ -1767,7 +1838,15 @@ int ottgpu_jpeg_encode(ottgpu_jpeg *j, const ottgpu_picture *pic, void *dst, siz
             job.pitch[p] = pic->stride[p];
         }
     }
-    CK(ottgpu::launch_jpeg(job, j->stream));
+    // phase 1: coefficients and the symbol histogram; the picture's optimal Huffman tables are built here from 4 KB of counts
+    CK(ottgpu::launch_jpeg_analyse(job, j->stream));
+    CK(cudaMemcpyAsync(j->h_hist, job.hist, 4 * 256 * sizeof(uint32_t), cudaMemcpyDeviceToHost, j->stream));
+    CK(cudaStreamSynchronize(j->stream));
+    job.header_bytes = (int)jpeg_picture_header(j);
+    CK(cudaMemcpyAsync(j->d_huff, j->h_huff, sizeof(ottgpu::JpegHuff), cudaMemcpyHostToDevice, j->stream));
+    CK(cudaMemcpyAsync(job.out, j->h_header, (size_t)job.header_bytes, cudaMemcpyHostToDevice, j->stream));
+    // phase 2: lengths, positions, codes, byte stuffing
+    CK(ottgpu::launch_jpeg_encode(job, j->stream));
     CK(cudaMemcpyAsync(j->h_result, job.result, 8, cudaMemcpyDeviceToHost, j->stream));
     CK(cudaStreamSynchronize(j->stream));
     if (j->h_result[1]) return fail(OTTGPU_ERR_CUDA, "JPEG stream overflowed its buffer");

@@ -96,11 +96,19 @@ static void emu_scan(uint32_t *v, int n)
 
 int jpeg_stuff_chunks(uint32_t stream_words) { return (int)(((size_t)stream_words * 4 + kJpegChunk - 1) / kJpegChunk); }
 
-cudaError_t launch_jpeg(const JpegJob &j, cudaStream_t)
+cudaError_t launch_jpeg_analyse(const JpegJob &j, cudaStream_t)
+{
+    if (j.n_blocks <= 0) return cudaSuccess;
+    std::memset(j.hist, 0, 4 * 256 * sizeof(uint32_t));
+    for (int b = 0; b < (j.n_blocks + 127) / 128 * 128; ++b) jpeg_block_dct(j, b);
+    for (int b = 0; b < (j.n_blocks + 127) / 128 * 128; ++b) jpeg_block_hist(j, b);
+    return cudaSuccess;
+}
+
+cudaError_t launch_jpeg_encode(const JpegJob &j, cudaStream_t)
 {
     if (j.n_blocks <= 0) return cudaSuccess;
     std::memset(j.stream, 0, (size_t)j.stream_words * 4);
-    for (int b = 0; b < (j.n_blocks + 127) / 128 * 128; ++b) jpeg_block_dct(j, b);
     for (int b = 0; b < (j.n_blocks + 127) / 128 * 128; ++b) jpeg_block_bits(j, b);
     emu_scan(j.bits, j.n_blocks);
     for (int b = j.n_blocks - 1; b >= 0; --b) jpeg_block_emit(j, b);        // any order: the positions are absolute
