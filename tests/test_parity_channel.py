@@ -537,3 +537,24 @@ def test_batch_readbacks_travel_as_one_copy_per_rung(lib, og, oracle):
         c.close()
     for p in pools:
         p.close()
+
+
+def test_batch_of_unlike_channels_with_host_destinations(lib, og, oracle):
+    """Channels of one batch may differ in source size and ladder; the shared per-rung staging allocation is sized for the
+    largest surface and every channel's host-destined rungs still arrive bit-exact."""
+    specs = [(96, 64, [(96, 64), (64, 40)]), (128, 72, [(64, 36), (48, 28), (32, 18)]), (96, 64, [(48, 32)])]
+    chans = [og.Channel(lib, og.make_cfg(w, h, [(dw, dh, og.FMT_I420) for dw, dh in rungs], deint=og.DEINT_FLAGGED)) for w, h, rungs in specs]
+    batch = og.Batch(lib, chans)
+    frames = [[natural_i420(w, h, 21 + s, shift=3.0 * s + c) for c, (w, h, _) in enumerate(specs)] for s in range(3)]
+    for s in range(3):
+        res = batch.submit(frames[s], interlaced=0)
+        if s == 0:
+            assert all(r is None for r in res)
+            continue
+        for c, (w, h, rungs) in enumerate(specs):
+            for got, (dw, dh) in zip(res[c]["rungs"], rungs):
+                want = frames[s - 1][c] if (dw, dh) == (w, h) else oracle.scale_i420(frames[s - 1][c], w, h, dw, dh)
+                assert np.array_equal(got, want), (s, c, dw, dh)
+    batch.close()
+    for c in chans:
+        c.close()
