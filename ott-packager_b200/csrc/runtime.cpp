@@ -1847,14 +1847,19 @@ int ottgpu_jpeg_encode(ottgpu_jpeg *j, const ottgpu_picture *pic, void *dst, siz
     CK(cudaMemcpyAsync(job.out, j->h_header, (size_t)job.header_bytes, cudaMemcpyHostToDevice, j->stream));
     // phase 2: lengths, positions, codes, byte stuffing
     CK(ottgpu::launch_jpeg_encode(job, j->stream));
+    // the size and, speculatively, the first 24 KB of the file in one round trip (a thumbnail is 3-15 KB)
+    const size_t head = std::min<size_t>(job.out_capacity, 24 * 1024);
     CK(cudaMemcpyAsync(j->h_result, job.result, 8, cudaMemcpyDeviceToHost, j->stream));
+    CK(cudaMemcpyAsync(j->h_out, job.out, head, cudaMemcpyDeviceToHost, j->stream));
     CK(cudaStreamSynchronize(j->stream));
     if (j->h_result[1]) return fail(OTTGPU_ERR_CUDA, "JPEG stream overflowed its buffer");
     const size_t n = j->h_result[0];
     *dst_bytes = n;
     if (n > dst_capacity) return fail(OTTGPU_ERR_NOMEM, "destination buffer too small for the JPEG file");
-    CK(cudaMemcpyAsync(j->h_out, job.out, n, cudaMemcpyDeviceToHost, j->stream));
-    CK(cudaStreamSynchronize(j->stream));
+    if (n > head) {
+        CK(cudaMemcpyAsync(j->h_out + head, job.out + head, n - head, cudaMemcpyDeviceToHost, j->stream));
+        CK(cudaStreamSynchronize(j->stream));
+    }
     std::memcpy(dst, j->h_out, n);
     return OTTGPU_OK;
 }
