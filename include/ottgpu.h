@@ -33,7 +33,9 @@ extern "C" {
 enum {
     OTTGPU_FMT_I420 = 0,       /* 8-bit planar Y,U,V        (AV_PIX_FMT_YUV420P, transvideo.c:1563-1564)            */
     OTTGPU_FMT_NV12 = 1,       /* 8-bit Y + interleaved UV  (NVENC sw_format, transvideo.c:403, repack 532-557)     */
-    OTTGPU_FMT_P010 = 2,       /* 10-bit MSB-aligned in 16, Y + interleaved UV (little endian)                      */
+    OTTGPU_FMT_P010 = 2,       /* 10-bit MSB-aligned in 16, Y + interleaved UV (little endian); the six low bits of a
+                                  SOURCE sample must be zero, as decoders write them (libswscale shifts them out, the
+                                  tensor-core H pass reads the raw bytes)                                            */
     OTTGPU_FMT_I420P10 = 3     /* 10-bit LSB-aligned in 16, planar (the only >8-bit layout vf_yadif accepts)        */
 };
 enum { OTTGPU_FILTER_BICUBIC = 0 /* SWS_BICUBIC, transvideo.c:1565 */, OTTGPU_FILTER_LANCZOS = 1 /* SWS_LANCZOS */ };

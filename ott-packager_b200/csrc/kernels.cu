@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
                 phase_stage(tid, g, smem);
                 compute_sync();
             }
-            if (BPS == 2 && (g.src_shift || g.hsplit == 16)) {   // P010: right-align the 10 significant bits; MMA path: split into bytes
+            if (BPS == 2 && g.src_shift && g.hsplit != 16) {     // P010 on the dp2a fallback: right-align the 10 significant bits (the MMA path reads the raw bytes)
                 phase_fixup16(tid, g, smem);
                 compute_sync();
             }

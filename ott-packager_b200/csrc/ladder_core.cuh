@@ -263,16 +263,10 @@ OTT_COLD void phase_stage(int tid, const TileGeom &g, unsigned char *smem)
 
 // P010 keeps its 10 significant bits in the upper part of each 16-bit sample: right-align them in place (both halves of
 // every staged word, i.e. two luma samples or one (U,V) pair) before the H pass reads the window.
-OTT_DEV uint32_t split_bytes16(uint32_t v10x2)         // two right-aligned 10-bit samples -> (s0, s1) byte pairs: s0 = v & 127, s1 = v >> 7
-{
-    return (v10x2 & 0x007f007fu) | ((v10x2 << 1) & 0x0f000f00u);
-}
-
 OTT_DEV void phase_fixup16(int tid, const TileGeom &g, unsigned char *smem)
 {
     const int shift = g.src_shift;
-    const bool split = g.hsplit == 16;                    // the MMA path reads every sample as two bytes (s0, s1)
-    if (!shift && !split) return;
+    if (!shift || g.hsplit == 16) return;                 // the MMA path reads the raw bytes: only the dp2a fallback gets here
     uint32_t *src_s = reinterpret_cast<uint32_t *>(smem + g.off_src);
     int lpr_log2 = 0;
     while ((1 << lpr_log2) < g.nvec && lpr_log2 < 5) ++lpr_log2;
@@ -285,7 +279,6 @@ OTT_DEV void phase_fixup16(int tid, const TileGeom &g, unsigned char *smem)
                 uint4 q = srow[v];
                 q.x = shift_mask16(q.x, shift); q.y = shift_mask16(q.y, shift);
                 q.z = shift_mask16(q.z, shift); q.w = shift_mask16(q.w, shift);
-                if (split) { q.x = split_bytes16(q.x); q.y = split_bytes16(q.y); q.z = split_bytes16(q.z); q.w = split_bytes16(q.w); }
                 srow[v] = q;
             }
         }
@@ -603,13 +596,17 @@ OTT_DEV void hpass16_any(int tid, const TileGeom &g, unsigned char *smem)
     }
 }
 
-// 16-bit sources on the tensor cores: three int8 MMAs per K step over the byte-split staged rows (see plan.cpp):
-//     P0 = sum s0*c0    P1 = sum (s0*c1 + s1*c0)    P2 = sum s1*c1      sum v*c = 16384*P2 + 128*P1 + P0
-//     (sum >> 9) = 32*P2 + ((P1 + (P0 >> 7)) >> 2)          exactly (P0 >= 0, the other terms are multiples of 128)
+// 16-bit sources on the tensor cores: four int8 MMAs per K step over the RAW staged bytes.  A little-endian 16-bit sample
+// is already the byte pair (b0, b1), raw = 256*b1 + b0, so nothing has to be rewritten in shared memory (round 2 first
+// split every staged sample at bit 7 in a fix-up pass: 27 % of the 16-bit kernel's instructions); P010's "<< 6" is folded
+// into the final shift (raw = v << 6: sum raw*c = 64 * sum v*c exactly).  With c = 128*c1 + c0 (c0 < 128, c1 signed):
+//     Q0 = sum b0*c0   Q1 = sum b0*c1   Q2 = sum b1*c0   Q3 = sum b1*c1      sum raw*c = 2^15 Q3 + 2^8 Q2 + 2^7 Q1 + Q0
+//     (sum >> sh) = (Q3 << (15 - sh)) + ((2 Q2 + Q1 + (Q0 >> 7)) >> (sh - 7))     exactly (Q0 >= 0), sh = 9 + src_shift
+// (P010 must carry zeros in its six low bits, as every decoder writes it: libswscale shifts them out, here they would count.)
 // Same work distribution as the 8-bit pass; interleaved P010 chroma reads the same staged rows for both planes with a
-// fragment table per plane.
+// fragment table per plane (the byte positions of its samples differ).
 #if defined(OTTGPU_EMULATE)
-inline void hmma16_lane(const uint32_t *row_g, const uint32_t *row_g8, const uint32_t *frag32x8, int lane, int (&P0)[4], int (&P1)[4], int (&P2)[4])
+inline void hmma16_lane(const uint32_t *row_g, const uint32_t *row_g8, const uint32_t *frag32x8, int lane, int (&Q0)[4], int (&Q1)[4], int (&Q2)[4], int (&Q3)[4])
 {
     const int t = lane & 3;
     for (int i = 0; i < 4; ++i) {
@@ -619,9 +616,10 @@ inline void hmma16_lane(const uint32_t *row_g, const uint32_t *row_g8, const uin
             const int src = (int)((row[(k >> 2) - t] >> (8 * (k & 3))) & 255u);
             const uint32_t *f = frag32x8 + (size_t)(4 * n + ((k & 15) >> 2)) * 8;
             const int r = k >> 4, b = k & 3;
-            P0[i] += src * (int)(int8_t)((f[r] >> (8 * b)) & 255u);
-            P1[i] += src * (int)(int8_t)((f[2 + r] >> (8 * b)) & 255u);
-            P2[i] += src * (int)(int8_t)((f[4 + r] >> (8 * b)) & 255u);
+            Q0[i] += src * (int)(int8_t)((f[r] >> (8 * b)) & 255u);
+            Q1[i] += src * (int)(int8_t)((f[2 + r] >> (8 * b)) & 255u);
+            Q2[i] += src * (int)(int8_t)((f[4 + r] >> (8 * b)) & 255u);
+            Q3[i] += src * (int)(int8_t)((f[6 + r] >> (8 * b)) & 255u);
         }
     }
 }
@@ -637,6 +635,7 @@ OTT_DEV void hpass16_mma(int tid, const TileGeom &g, unsigned char *smem)
     int left = (int)(hr >> 20);
     if (left == 0) return;
     const int spw = g.spw, pitch = g.mid_pitch;
+    const int shl = 6 - g.src_shift, shr = 2 + g.src_shift;     // sh = 9 (right-aligned samples) or 15 (P010)
     const int lane_src = (lane >> 2) * spw + (lane & 3), lane_mid = (lane >> 2) * pitch + 2 * (lane & 3);
     const uint32_t *src_s = reinterpret_cast<const uint32_t *>(smem + g.off_src) + lane_src;
     mid_t *mid_s = reinterpret_cast<mid_t *>(smem + g.off_mid) + lane_mid;
@@ -654,13 +653,12 @@ OTT_DEV void hpass16_mma(int tid, const TileGeom &g, unsigned char *smem)
             mt += cnt;
             const uint32_t *frag = (p ? g.hmma2 : g.hmma) + (size_t)nt * ks_n * 256;
 #if !defined(OTTGPU_EMULATE)
-            uint4 Ba[KS ? KS : 1];
-            uint2 Bc[KS ? KS : 1];
+            uint4 Ba[KS ? KS : 1], Bb[KS ? KS : 1];
             if (KS) {
                 OTT_UNROLL
                 for (int ks = 0; ks < KS; ++ks) {
                     Ba[ks] = ott_ldg(reinterpret_cast<const uint4 *>(frag) + (ks * 32 + lane) * 2);
-                    Bc[ks] = ott_ldg(reinterpret_cast<const uint2 *>(frag) + (ks * 32 + lane) * 4 + 2);
+                    Bb[ks] = ott_ldg(reinterpret_cast<const uint4 *>(frag) + (ks * 32 + lane) * 2 + 1);
                 }
             }
 #endif
@@ -670,36 +668,38 @@ OTT_DEV void hpass16_mma(int tid, const TileGeom &g, unsigned char *smem)
             uint32_t *o8 = o + 4 * pitch;
             OTT_NOUNROLL
             for (; cnt > 0; --cnt, rg += 16 * spw, rg8 += 16 * spw, o += 8 * pitch, o8 += 8 * pitch) {
-                int P0[4] = {0, 0, 0, 0}, P1[4] = {0, 0, 0, 0}, P2[4] = {0, 0, 0, 0};
+                int Q0[4] = {0, 0, 0, 0}, Q1[4] = {0, 0, 0, 0}, Q2[4] = {0, 0, 0, 0}, Q3[4] = {0, 0, 0, 0};
                 if (KS) {
                     OTT_UNROLL
                     for (int ks = 0; ks < (KS ? KS : 1); ++ks) {
 #if defined(OTTGPU_EMULATE)
-                        hmma16_lane(rg + 8 * ks, rg8 + 8 * ks, frag + (size_t)ks * 256, lane, P0, P1, P2);
+                        hmma16_lane(rg + 8 * ks, rg8 + 8 * ks, frag + (size_t)ks * 256, lane, Q0, Q1, Q2, Q3);
 #else
                         const uint32_t a[4] = {rg[8 * ks], rg8[8 * ks], rg[8 * ks + 4], rg8[8 * ks + 4]};
-                        ott_mma_u8s8(P0, a, Ba[ks].x, Ba[ks].y);
-                        ott_mma_u8s8(P1, a, Ba[ks].z, Ba[ks].w);
-                        ott_mma_u8s8(P2, a, Bc[ks].x, Bc[ks].y);
+                        ott_mma_u8s8(Q0, a, Ba[ks].x, Ba[ks].y);
+                        ott_mma_u8s8(Q1, a, Ba[ks].z, Ba[ks].w);
+                        ott_mma_u8s8(Q2, a, Bb[ks].x, Bb[ks].y);
+                        ott_mma_u8s8(Q3, a, Bb[ks].z, Bb[ks].w);
 #endif
                     }
                 } else {
                     for (int ks = 0; ks < ks_n; ++ks) {
 #if defined(OTTGPU_EMULATE)
-                        hmma16_lane(rg + 8 * ks, rg8 + 8 * ks, frag + (size_t)ks * 256, lane, P0, P1, P2);
+                        hmma16_lane(rg + 8 * ks, rg8 + 8 * ks, frag + (size_t)ks * 256, lane, Q0, Q1, Q2, Q3);
 #else
                         const uint4 ba = ott_ldg(reinterpret_cast<const uint4 *>(frag) + (ks * 32 + lane) * 2);
-                        const uint2 bc = ott_ldg(reinterpret_cast<const uint2 *>(frag) + (ks * 32 + lane) * 4 + 2);
+                        const uint4 bb = ott_ldg(reinterpret_cast<const uint4 *>(frag) + (ks * 32 + lane) * 2 + 1);
                         const uint32_t a[4] = {rg[8 * ks], rg8[8 * ks], rg[8 * ks + 4], rg8[8 * ks + 4]};
-                        ott_mma_u8s8(P0, a, ba.x, ba.y);
-                        ott_mma_u8s8(P1, a, ba.z, ba.w);
-                        ott_mma_u8s8(P2, a, bc.x, bc.y);
+                        ott_mma_u8s8(Q0, a, ba.x, ba.y);
+                        ott_mma_u8s8(Q1, a, ba.z, ba.w);
+                        ott_mma_u8s8(Q2, a, bb.x, bb.y);
+                        ott_mma_u8s8(Q3, a, bb.z, bb.w);
 #endif
                     }
                 }
                 int v[4];
                 OTT_UNROLL
-                for (int i = 0; i < 4; ++i) v[i] = 32 * P2[i] + ((P1[i] + (int)((uint32_t)P0[i] >> 7)) >> 2);
+                for (int i = 0; i < 4; ++i) v[i] = (Q3[i] << shl) + ((2 * Q2[i] + Q1[i] + (int)((uint32_t)Q0[i] >> 7)) >> shr);
                 o[0] = ott_pack_s16(v[1], v[0]);
                 o8[0] = ott_pack_s16(v[3], v[2]);
             }

@@ -190,12 +190,13 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
                         }
                 }
     }
-    // 16-bit path (10 significant bits): samples and coefficients are both split at bit 7, v = 128*s1 + s0 and
-    // c = 128*c1 + c0 (s0, c0 < 128; s1 < 8; c1 signed), and the contraction becomes three int8 MMAs over the staged BYTES
-    // (every sample position holds s0 then s1 after the staging fix-up; P010 chroma holds U.s0 U.s1 V.s0 V.s1):
-    //     P0 = sum s0*c0     P1 = sum (s0*c1 + s1*c0)     P2 = sum s1*c1        sum v*c = 16384*P2 + 128*P1 + P0
-    // Fragments per (column group, K step, lane): {A.r0, A.r1, B.r0, B.r1, C.r0, C.r1, 0, 0}; interleaved chroma gets one
-    // table per plane (the non-zero byte positions differ).  hsplit = 16 marks the plane as running this path.
+    // 16-bit path (10 significant bits in a 16-bit container): the contraction runs as four int8 MMAs over the RAW staged
+    // bytes -- a little-endian sample is the byte pair (b0, b1) -- with the coefficient split at bit 7, c = 128*c1 + c0
+    // (c0 < 128, c1 signed):
+    //     Q0 = sum b0*c0    Q1 = sum b0*c1    Q2 = sum b1*c0    Q3 = sum b1*c1     sum raw*c = 2^15 Q3 + 2^8 Q2 + 2^7 Q1 + Q0
+    // Fragments per (column group, K step, lane): {Q0.r0, Q0.r1, Q1.r0, Q1.r1, Q2.r0, Q2.r1, Q3.r0, Q3.r1}; interleaved chroma
+    // (P010: U.b0 U.b1 V.b0 V.b1) gets one table per plane (the non-zero byte positions differ).  hsplit = 16 marks the plane
+    // as running this path.
     std::vector<uint32_t> frags_v;
     bool mma16 = false;
     if (bps == 2) {
@@ -230,13 +231,14 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
                                 const int pos = kbase[gi] + 32 * ks + 16 * r + 4 * t + b;      // byte in the staged row
                                 const int xs = pos / px_bytes, w = pos % px_bytes;
                                 const int lo_byte = px_bytes == 4 ? 2 * pl : 0;                // where this plane's s0 sits
-                                const bool is_s0 = w == lo_byte, is_s1 = w == lo_byte + 1;
+                                const bool is_b0 = w == lo_byte, is_b1 = w == lo_byte + 1;
                                 const int j = xs - h.pos[x];
                                 const int c = (j >= 0 && j < h.taps) ? h.coef[(size_t)x * h.taps + j] : 0;
                                 const int c0 = c & 127, c1 = c >> 7;
-                                f[r] |= (uint32_t)((is_s0 ? c0 : 0) & 255) << (8 * b);
-                                f[2 + r] |= (uint32_t)((is_s0 ? c1 : (is_s1 ? c0 : 0)) & 255) << (8 * b);
-                                f[4 + r] |= (uint32_t)((is_s1 ? c1 : 0) & 255) << (8 * b);
+                                f[r] |= (uint32_t)((is_b0 ? c0 : 0) & 255) << (8 * b);
+                                f[2 + r] |= (uint32_t)((is_b0 ? c1 : 0) & 255) << (8 * b);
+                                f[4 + r] |= (uint32_t)((is_b1 ? c0 : 0) & 255) << (8 * b);
+                                f[6 + r] |= (uint32_t)((is_b1 ? c1 : 0) & 255) << (8 * b);
                             }
                     }
         }

@@ -499,7 +499,7 @@ int ottgpu_channel_describe(const ottgpu_channel *ch, char *buf, size_t size)
         for (int k = 0; k < 2; ++k) {
             const PlaneTables &T = k ? R.chroma : R.luma;
             const char *hpath = p.host_copy.bps == 1 ? (T.hsplit == 7 ? "IMMA u8 (7-bit split)" : "IMMA u8 (8-bit split)")
-                                                     : (T.hsplit == 16 ? "IMMA 10-bit (3 products)" : "dp2a");
+                                                     : (T.hsplit == 16 ? "IMMA 16-bit raw bytes (4 products)" : "dp2a");
             snprintf(line, sizeof line, "  slot %d %s %s %dx%d -> %dx%d  taps H %d V %d  H pass %s, %d K step(s)  tile %dx%d  tiles %dx%d  src rows/tile %d  staged row %d B  exact_from %d  V bias %d\n",
                      s, s == p.thumb_slot ? "thumb" : "rung", k ? "chroma" : "luma", T.srcW, T.srcH, T.dstW, T.dstH, 4 * T.hq,
                      T.vtaps, hpath, T.hks, T.tw, T.th, T.tiles_x, T.tiles_y, T.sr_max, T.sw_words * 4, T.exact_from, T.vbias);

@@ -11,7 +11,7 @@ rep = sys.argv[1]
 lib = os.path.abspath(sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "ott-packager_b200", "libottgpu.so"))
 frames = int(sys.argv[3]) if len(sys.argv) > 3 else 8
 out_md = sys.argv[4] if len(sys.argv) > 4 else None
-KERNEL = "ladder_kernelILi1"          # the 8-bit instance in the cubin (mangled); ncu reports it as ladder_kernel<1>
+KERNEL = os.environ.get("OTT_PHASE_KERNEL", "ladder_kernelILi1")   # instance in the cubin (mangled): ILi1 = 8-bit (ncu: ladder_kernel<1>), ILi2 = 16-bit
 NCU_KERNEL = "ladder_kernel"
 
 # ---- source line -> enclosing function (top-level definitions of the .cuh / .cu files)
