@@ -78,6 +78,9 @@ struct PlaneTables {
     int vstride;             // 32-bit entries per output row in vc (>= vtaps)
     int vbias;               // 8-bit target A fast path: per-product bias (max|c| >> 1) + 1 of the V pass, 0 = not usable
                              //   (odd tap count, or taps * (max|c| + 2) would overflow a 16-bit lane)
+    int vsum;                // 8-bit target A FMA path (round 3): the common sum of every row's V coefficients (4096) when the
+                             //   vertical pass may run as round-down FP32 FMAs (even taps, sum|c| small enough for the float
+                             //   accumulator to stay inside one binade), 0 = not usable
     int exact_from;          // 8-bit target A: first output row computed with the exact vertical formula
     int tw, th;              // tile size in output samples
     int cpt;                 // V pass: adjacent columns per thread (8 | 4), chosen so the tile's work divides evenly
@@ -164,7 +167,8 @@ struct Item {
     uint16_t vtaps, vbias, exact_from, dstW;
     uint8_t hks, hsplit, hq;
     uint8_t strip;           // 8-bit strip mode: 1 = lane owns a row x 8 columns in the V pass, 2 = x 4 columns (short tiles)
-    uint32_t pad3;
+    uint16_t vsum;           // copy of T->vsum (0: the V pass may not use the FMA path)
+    uint16_t pad3;
     const uint32_t *hmma2;   // 16-bit interleaved chroma: fragments of the second (V) plane, else = hmma
 };
 static_assert(sizeof(Item) % 16 == 0 && (sizeof(Item) == 192 || OTTGPU_COMPUTE_WARPS > 12), "Item is copied into shared memory as twelve 16-byte vectors");

@@ -19,6 +19,7 @@
 
 #if defined(OTTGPU_EMULATE)
 #include <cstring>
+#include <cmath>
 #define OTT_DEV inline
 #define OTT_COLD inline
 #define OTT_NOUNROLL
@@ -92,6 +93,17 @@ inline uint32_t ott_hi16x2(uint32_t a, uint32_t b) { return (a >> 16) | (b & 0xf
 inline int ott_sat(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 inline uint32_t ott_pack_s16(int hi, int lo) { return ((uint32_t)ott_sat(hi, -32768, 32767) << 16) | ((uint32_t)ott_sat(lo, -32768, 32767) & 0xffffu); }
 inline uint32_t ott_pack_u8(int b1, int b0, uint32_t upper) { return (upper << 16) | ((uint32_t)ott_sat(b1, 0, 255) << 8) | (uint32_t)ott_sat(b0, 0, 255); }
+inline float ott_fma_rd(float a, float b, float c)                 // a*b + c rounded ONCE, toward minus infinity (FFMA.RM)
+{
+    const double r = (double)a * (double)b + (double)c;            // exact for the operand ranges of the V pass (< 53 bits)
+    float f = (float)r;
+    if ((double)f > r) f = std::nextafterf(f, -INFINITY);
+    return f;
+}
+inline float ott_as_float(uint32_t v) { float f; std::memcpy(&f, &v, 4); return f; }
+inline uint32_t ott_as_u32(float f) { uint32_t v; std::memcpy(&v, &f, 4); return v; }
+inline float ott_i2f(int v) { return (float)v; }
+inline long long ott_emu_vrows[2] = {0, 0};                       // test counters: fast V rows taken by the FMA path / the bias path
 }  // namespace ottgpu
 #else
 #define OTT_DEV __device__ __forceinline__
@@ -153,6 +165,10 @@ OTT_DEV uint32_t ott_pack_u8(int b1, int b0, uint32_t upper)
     asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(b1), "r"(b0), "r"(upper));
     return d;
 }
+OTT_DEV float ott_fma_rd(float a, float b, float c) { return __fmaf_rd(a, b, c); }                    // FFMA.RM
+OTT_DEV float ott_as_float(uint32_t v) { return __uint_as_float(v); }
+OTT_DEV uint32_t ott_as_u32(float f) { return __float_as_uint(f); }
+OTT_DEV float ott_i2f(int v) { return __int2float_rn(v); }
 // m16n8k32 int8 MMA, A = u8 source bytes (rows), B = coefficient bytes (columns); accumulates into d
 OTT_DEV void ott_mma_u8s8(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
 {
@@ -199,6 +215,8 @@ struct alignas(16) TileGeom : Item {
     int src_pitch0, src_pitch1;      // bytes
     uint8_t *dst0, *dst1;
     int dst_pitch0, dst_pitch1;
+    mutable int mid_neg;     // set by the H pass when any intermediate of the tile is negative (the V pass's FMA path needs
+                             //   them all >= 0 and falls back to the integer path for such a tile); cleared by item_prepare
 };
 
 // ------------------------------------------------------------------------------------------------ phase 0: tables
@@ -330,6 +348,11 @@ OTT_DEV void hpass8_mma(int tid, const TileGeom &g, unsigned char *smem)
     const uint32_t *src_s = reinterpret_cast<const uint32_t *>(smem + g.off_src) + lane_src;
     mid_t *mid_s = reinterpret_cast<mid_t *>(smem + g.off_mid) + lane_mid;
     int nt = (int)(hr & 255u), mt = (int)((hr >> 8) & 4095u);
+    // OR of every packed result pair: bits 15 / 31 = "one was negative".  Tiles with fewer than 16 staged rows compute rows
+    // beyond the window (stale bytes): they take the integer V path unconditionally.
+    const int sr_ = g.sr;
+    uint32_t signs = ((sr_ & 15) && sr_ < 16) ? 0x8000u : 0u;
+    const int last_mt = ((sr_ & 15) && sr_ >= 16) ? mt_plane - 1 : mt_plane, last_row0 = sr_ - 16;
     while (left > 0) {
         const int kw = g.kw[nt];                                  // window base as a word offset into the staged rows
         const uint32_t *frag = g.hmma + (size_t)nt * ks_n * 128;
@@ -344,12 +367,16 @@ OTT_DEV void hpass8_mma(int tid, const TileGeom &g, unsigned char *smem)
         left -= run;
         while (run > 0) {
             const int p = mt >= mt_plane, m0 = mt - p * mt_plane;
-            int cnt = ott_min(run, mt_plane - m0);                // ... inside one plane
+            // a plane's last row group, when partial, is moved up to end at the last staged row (it recomputes rows of the
+            // group above, same values): no result is ever derived from bytes beyond the staged window, which keeps the
+            // sign flag below exact
+            int cnt = ott_min(run, (m0 < last_mt ? last_mt : mt_plane) - m0);   // ... inside one plane
             run -= cnt;
             mt += cnt;
-            const uint32_t *rg = src_s + p * (g.plane_stride >> 2) + (m0 << 4) * spw + kw;
+            const int row0 = m0 < last_mt ? m0 << 4 : last_row0;
+            const uint32_t *rg = src_s + p * (g.plane_stride >> 2) + row0 * spw + kw;
             const uint32_t *rg8 = rg + 8 * spw;
-            uint32_t *o = reinterpret_cast<uint32_t *>(mid_s + (p * g.mid_rows + (m0 << 4)) * pitch + 8 * nt);
+            uint32_t *o = reinterpret_cast<uint32_t *>(mid_s + (p * g.mid_rows + row0) * pitch + 8 * nt);
             uint32_t *o8 = o + 4 * pitch;                          // 8 rows down: 8 * pitch elements = 4 * pitch words
             OTT_NOUNROLL
             for (; cnt > 0; --cnt, rg += 16 * spw, rg8 += 16 * spw, o += 8 * pitch, o8 += 8 * pitch) {
@@ -381,13 +408,16 @@ OTT_DEV void hpass8_mma(int tid, const TileGeom &g, unsigned char *smem)
                 int v[4];
                 OTT_UNROLL
                 for (int i = 0; i < 4; ++i) v[i] = (SPLIT == 7 ? H[i] : 2 * H[i]) + (int)((uint32_t)L[i] >> 7);
-                o[0] = ott_pack_s16(v[1], v[0]);
-                o8[0] = ott_pack_s16(v[3], v[2]);
+                const uint32_t w0 = ott_pack_s16(v[1], v[0]), w8 = ott_pack_s16(v[3], v[2]);
+                o[0] = w0;
+                o8[0] = w8;
+                signs |= w0 | w8;
             }
         }
         mt = 0;
         ++nt;
     }
+    if (signs & 0x80008000u) g.mid_neg = 1;                       // needs an overshoot below level 0: rare in video, see vrow_fma8
 }
 
 // STRIP mode (device_types.h): compute warp w owns column group w of the tile -- its B fragments stay in registers while it
@@ -932,6 +962,54 @@ OTT_DEV void vrow_bias8(const mid_t *m, int step, const int32_t *cf, int vtaps, 
     }
 }
 
+// Round 3: the same rows as round-down FP32 FMAs.  pmulhw is floor(t*c / 65536), and an FMA rounds ONCE: with an
+// accumulator that is a multiple of 65536 inside the binade [2^39, 2^40) (ulp = 65536) and round-toward-minus-infinity,
+//     fma.rm(g, c, acc) = floor_65536(acc + g*c) = acc + 65536 * floor(g*c / 65536)        exactly
+// (g*c is exact inside the FMA: 24 x 13 bits).  The operand g = 2^23 + t is built from the packed int16 intermediate with
+// ONE byte permute (float bits 0x4B000000 | t, valid for t >= 0: the H pass raises TileGeom::mid_neg otherwise and the tile
+// takes vrow_bias8); its 2^23 adds 128*c per tap, a multiple of the ulp, so the floor is untouched, and over a row that is
+// 128 * vsum, taken out of the initial accumulator.  Per tap-sample: one PRMT (ALU pipe) + one FFMA (FMA pipe) - the
+// multiply, the floor and the accumulation in one instruction, against IMAD + extraction + 1/2 PRMT + 1/4 IADD3 of the
+// bias-lane path.  The plan checks that the accumulator cannot leave the binade (PlaneTables::vsum).
+template <int NV>
+OTT_DEV void vrow_fma8(const mid_t *m, int step, const int32_t *cf, int vtaps, float acc0, uint32_t (&out)[NV / 4])
+{
+    constexpr int NW = NV / 2;
+    constexpr uint32_t kOne23 = 0x4B000000u;                      // 2^23: a float whose low mantissa bits are an integer
+    float acc[NV];
+    OTT_UNROLL
+    for (int k = 0; k < NV; ++k) acc[k] = acc0;
+    const uint32_t *m0 = reinterpret_cast<const uint32_t *>(m), *m1 = reinterpret_cast<const uint32_t *>(m + step);
+    const uint2 *c2 = reinterpret_cast<const uint2 *>(cf);
+    OTT_NOUNROLL
+    for (int j = vtaps; j > 0; j -= 2, m0 += step, m1 += step, ++c2) {
+        const uint2 cc = *c2;
+        const float c0 = ott_i2f((int)cc.x), c1 = ott_i2f((int)cc.y);
+        uint32_t w0[NW], w1[NW];
+        load_words<NW>(m0, w0);
+        load_words<NW>(m1, w1);
+        OTT_UNROLL
+        for (int k = 0; k < NW; ++k) {
+            acc[2 * k] = ott_fma_rd(ott_as_float(ott_prmt(w0[k], kOne23, 0x7610)), c0, acc[2 * k]);
+            acc[2 * k + 1] = ott_fma_rd(ott_as_float(ott_prmt(w0[k], kOne23, 0x7632)), c0, acc[2 * k + 1]);
+        }
+        OTT_UNROLL
+        for (int k = 0; k < NW; ++k) {
+            acc[2 * k] = ott_fma_rd(ott_as_float(ott_prmt(w1[k], kOne23, 0x7610)), c1, acc[2 * k]);
+            acc[2 * k + 1] = ott_fma_rd(ott_as_float(ott_prmt(w1[k], kOne23, 0x7632)), c1, acc[2 * k + 1]);
+        }
+    }
+    // acc = 1.5 * 2^39 + 65536 * (init + sum of floors): one bit step per unit, so the integer falls out of the bits
+    int r[NV];
+    OTT_UNROLL
+    for (int k = 0; k < NV; ++k) r[k] = (int)(ott_as_u32(acc[k]) - 0x53400000u) >> 3;      // psraw 3 (no paddw wrap: |sum| < 2^15)
+    OTT_UNROLL
+    for (int k = 0; k < NV / 4; ++k) {
+        const uint32_t upper = ott_pack_u8(r[4 * k + 3], r[4 * k + 2], 0u);
+        out[k] = ott_pack_u8(r[4 * k + 1], r[4 * k], upper);
+    }
+}
+
 // NWORDS packed 32-bit words = NWORDS*4/sizeof(S) samples starting at element `elem` of a row of `total` samples
 template <typename S, int NWORDS>
 OTT_DEV void store_words(uint8_t *row, int elem, const uint32_t (&w)[NWORDS], int total)
@@ -1046,6 +1124,10 @@ OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
         // whole-unit vector stores when the unit lies inside the plane and the surface rows are aligned to the unit
         const bool vec_ok = gx + CPT <= dstW && (il ? ((((uintptr_t)dst0 | (uintptr_t)dpitch0) & (uintptr_t)(2 * CPT - 1)) == 0)
                                                     : (nplanes == 1 && (((uintptr_t)dst0 | (uintptr_t)dpitch0) & (uintptr_t)(CPT - 1)) == 0));
+        // FMA path: every intermediate of the tile is >= 0 (flag raised by the H pass before the barrier)
+        const bool fma = !OTTGPU_STRIP && sizeof(mid_t) == 2 && g.vsum != 0 && g.mid_neg == 0;
+        // 1.5 * 2^39 + 65536 * (init - 128 * vsum): exact (a multiple of the binade's ulp)
+        const float acc0 = 824633720832.0f + 65536.0f * (float)(((64 + 8 * (vtaps - 1)) >> 4) - 128 * (int)g.vsum);
         for (; y < fast_rows; y += rows_per_pass) {
             const int32_t *cf = vc_s + y * vstride;
             const mid_t *m = mid_s + (vpos_s[y] - sy0) * mid_pitch;
@@ -1053,7 +1135,11 @@ OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
             OTT_NOUNROLL
             for (int p = 0; p < nplanes; ++p, m += plane_step) {
                 uint32_t t[CPT / 4];
-                vrow_bias8<CPT>(m, mid_pitch, cf, vtaps, bias16, k16, t);
+#if defined(OTTGPU_EMULATE)
+                ++ott_emu_vrows[fma ? 0 : 1];
+#endif
+                if (fma) vrow_fma8<CPT>(m, mid_pitch, cf, vtaps, acc0, t);
+                else vrow_bias8<CPT>(m, mid_pitch, cf, vtaps, bias16, k16, t);
                 OTT_UNROLL
                 for (int k = 0; k < CPT / 4; ++k) {
                     if (p == 0) o0[k] = t[k];
@@ -1175,6 +1261,7 @@ OTT_DEV int item_prepare(const Binding &b, const LadderLaunch &L, int buf, int m
     // box; otherwise the compute warps stage the window through registers
     g.bulk_ok = g.tma_ok && b.tmaps != nullptr;
     g.src_z = b.src_z;
+    g.mid_neg = 0;
     g.tmap0 = b.tmaps + (size_t)(slot * 3 + (luma ? 0 : 1)) * kTensorMapBytes;
     g.tmap1 = b.tmaps + (size_t)(slot * 3 + 2) * kTensorMapBytes;
     return 1;

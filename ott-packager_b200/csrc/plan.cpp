@@ -252,6 +252,18 @@ bool build_plane(Plan &plan, PlaneTables &T, int srcW, int srcH, int dstW, int d
         int cmax = 0;
         for (int16_t c : v.coef) cmax = std::max(cmax, std::abs((int)c));
         T.vbias = (v.taps % 2 == 0 && (long long)v.taps * (cmax + 2) < 65536) ? (cmax >> 1) + 1 : 0;
+        // FMA path of the same rows (vrow_fma8): every row's coefficients must add up to the same value (libswscale
+        // normalises them to 4096) and 129 * sum|c| must stay far inside the accumulator's binade (2^22 steps either way)
+        long long sum0 = 0, amax = 0;
+        bool same = dstH > 0 && v.taps > 0;
+        for (int y = 0; y < dstH && same; ++y) {
+            long long sum = 0, asum = 0;
+            for (int j = 0; j < v.taps; ++j) { const int c = v.coef[(size_t)y * v.taps + j]; sum += c; asum += std::abs(c); }
+            if (y == 0) sum0 = sum;
+            same = sum == sum0;
+            amax = std::max(amax, asum);
+        }
+        T.vsum = (T.vbias > 0 && same && sum0 > 0 && sum0 < 65536 && 129 * amax + 4096 < (1ll << 21)) ? (int)sum0 : 0;
     }
     T.exact_from = exact_from;
     const bool strip = OTTGPU_STRIP && mma8;
@@ -666,7 +678,7 @@ std::shared_ptr<Plan> build_plan(const ottgpu_cfg &cfg, std::string &err)
                                       vcb <= (size_t)it.vpos_off && vcb < 65536;
                     it.vc_bytes = bulk ? (uint16_t)vcb : 0;
                     it.vpos_bytes = bulk ? (uint16_t)vpb : 0;
-                    it.vtaps = (uint16_t)T.vtaps; it.vbias = (uint16_t)T.vbias; it.exact_from = (uint16_t)T.exact_from; it.dstW = (uint16_t)T.dstW;
+                    it.vtaps = (uint16_t)T.vtaps; it.vbias = (uint16_t)T.vbias; it.vsum = (uint16_t)T.vsum; it.exact_from = (uint16_t)T.exact_from; it.dstW = (uint16_t)T.dstW;
                     it.hks = (uint8_t)std::min(T.hks, 255); it.hsplit = (uint8_t)T.hsplit; it.hq = (uint8_t)std::min(T.hq, 255);
                     if (!kb.empty()) {
                         const int frag_words = bps == 1 ? 128 : 256;                       // per column group and K step

@@ -34,7 +34,7 @@ def func_of(path, line):
 PHASE = [("H pass (IMMA)", ("hpass8_mma", "hpass16_mma", "ott_mma_u8s8", "ott_mma_u8u8", "ott_pack_s16", "phase_hpass")),
          ("H pass (16-bit dp2a fallback)", ("hpass16", "hdot16", "hpass16il", "hdot16il", "hpass16_any", "hpass16il_any")),
          ("staging fix-up (16-bit)", ("phase_fixup16", "shift_mask16", "split_bytes16")),
-         ("V pass taps (fast path)", ("vrow_bias8", "ott_hi16x2", "load_words", "sx_lo", "sx_hi", "ott_pack_u8")),
+         ("V pass taps (fast path)", ("vrow_bias8", "vrow_fma8", "ott_fma_rd", "ott_as_float", "ott_as_u32", "ott_i2f", "ott_hi16x2", "load_words", "sx_lo", "sx_hi", "ott_pack_u8")),
          ("V pass taps (exact / 16-bit rows)", ("vcolumns", "load_vals", "pack4", "pack2", "ott_clip")),
          ("V pass rows + stores", ("vpass", "phase_vpass", "vpass_store", "store_words", "zip8", "zip16", "ott_prmt")),
          ("copy items", ("copy_rows", "interleave_rows8", "item_copy")),

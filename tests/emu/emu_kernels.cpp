@@ -7,6 +7,13 @@
 #include "convert_core.cuh"
 #include "jpeg_core.cuh"
 
+// test hook: how many fast V rows (thread x row x plane) ran as FMAs / on the integer bias path since the last call
+extern "C" void ottgpu_emu_vrows(long long *out)
+{
+    out[0] = ottgpu::ott_emu_vrows[0]; out[1] = ottgpu::ott_emu_vrows[1];
+    ottgpu::ott_emu_vrows[0] = ottgpu::ott_emu_vrows[1] = 0;
+}
+
 namespace ottgpu {
 
 cudaError_t configure_kernels() { return cudaSuccess; }
@@ -50,7 +57,10 @@ cudaError_t launch_ladder(LadderLaunch L, cudaStream_t)
         if ((size_t)g.nplanes * g.mid_rows * g.mid_pitch * 2 > (size_t)L.mid_max) return cudaErrorInvalidValue;
         if ((size_t)g.off_mid + L.mid_max > (size_t)g.off_vc) return cudaErrorInvalidValue;
         if (g.nvec * 4 > g.spw) return cudaErrorInvalidValue;
-        std::fill(smem.begin(), smem.end(), 0xA5);       // poison: stale-data reads show up as mismatches
+        {                                                 // poison: stale-data reads show up as mismatches (noise, as on the GPU)
+            uint32_t lcg = 12345u + (uint32_t)blk;
+            for (auto &byte : smem) { lcg = lcg * 1664525u + 1013904223u; byte = (unsigned char)(lcg >> 24); }
+        }
         for (int lane = 0; lane < 32; ++lane) phase_tables(lane, 32, g, sm);
         for (int tid = 0; tid < kThreads; ++tid) phase_stage(tid, g, sm);
         for (int tid = 0; tid < kThreads; ++tid) phase_fixup16(tid, g, sm);
