@@ -696,6 +696,48 @@ OTT_DEV void hpass16_mma(int tid, const TileGeom &g, unsigned char *smem)
             const uint32_t *rg8 = rg + 8 * spw;
             uint32_t *o = reinterpret_cast<uint32_t *>(mid_s + (p * g.mid_rows + (m0 << 4)) * pitch + 8 * nt);
             uint32_t *o8 = o + 4 * pitch;
+#if !defined(OTTGPU_EMULATE)
+            if (!KS) {
+                // Long filters (the fragments of all K steps do not fit the register file): two row groups share every
+                // fragment load, so the loads (L2 latency: the CTAs' shared memory leaves almost no L1) are halved and each
+                // one is followed by eight independent MMAs instead of four.
+                OTT_NOUNROLL
+                for (; cnt > 1; cnt -= 2, rg += 32 * spw, rg8 += 32 * spw, o += 16 * pitch, o8 += 16 * pitch) {
+                    int Q[2][4][4];
+                    OTT_UNROLL
+                    for (int u = 0; u < 2; ++u)
+                        OTT_UNROLL
+                        for (int q = 0; q < 4; ++q)
+                            OTT_UNROLL
+                            for (int i = 0; i < 4; ++i) Q[u][q][i] = 0;
+                    const uint32_t *rh = rg + 16 * spw, *rh8 = rg8 + 16 * spw;
+                    OTT_NOUNROLL
+                    for (int ks = 0; ks < ks_n; ++ks) {
+                        const uint4 ba = ott_ldg(reinterpret_cast<const uint4 *>(frag) + (ks * 32 + lane) * 2);
+                        const uint4 bb = ott_ldg(reinterpret_cast<const uint4 *>(frag) + (ks * 32 + lane) * 2 + 1);
+                        const uint32_t a0[4] = {rg[8 * ks], rg8[8 * ks], rg[8 * ks + 4], rg8[8 * ks + 4]};
+                        const uint32_t a1[4] = {rh[8 * ks], rh8[8 * ks], rh[8 * ks + 4], rh8[8 * ks + 4]};
+                        ott_mma_u8s8(Q[0][0], a0, ba.x, ba.y);
+                        ott_mma_u8s8(Q[1][0], a1, ba.x, ba.y);
+                        ott_mma_u8s8(Q[0][1], a0, ba.z, ba.w);
+                        ott_mma_u8s8(Q[1][1], a1, ba.z, ba.w);
+                        ott_mma_u8s8(Q[0][2], a0, bb.x, bb.y);
+                        ott_mma_u8s8(Q[1][2], a1, bb.x, bb.y);
+                        ott_mma_u8s8(Q[0][3], a0, bb.z, bb.w);
+                        ott_mma_u8s8(Q[1][3], a1, bb.z, bb.w);
+                    }
+                    OTT_UNROLL
+                    for (int u = 0; u < 2; ++u) {
+                        int v[4];
+                        OTT_UNROLL
+                        for (int i = 0; i < 4; ++i)
+                            v[i] = (Q[u][3][i] << shl) + ((2 * Q[u][2][i] + Q[u][1][i] + (int)((uint32_t)Q[u][0][i] >> 7)) >> shr);
+                        o[u * 8 * pitch] = ott_pack_s16(v[1], v[0]);
+                        o8[u * 8 * pitch] = ott_pack_s16(v[3], v[2]);
+                    }
+                }
+            }
+#endif
             OTT_NOUNROLL
             for (; cnt > 0; --cnt, rg += 16 * spw, rg8 += 16 * spw, o += 8 * pitch, o8 += 8 * pitch) {
                 int Q0[4] = {0, 0, 0, 0}, Q1[4] = {0, 0, 0, 0}, Q2[4] = {0, 0, 0, 0}, Q3[4] = {0, 0, 0, 0};
@@ -1125,7 +1167,11 @@ OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
         const bool vec_ok = gx + CPT <= dstW && (il ? ((((uintptr_t)dst0 | (uintptr_t)dpitch0) & (uintptr_t)(2 * CPT - 1)) == 0)
                                                     : (nplanes == 1 && (((uintptr_t)dst0 | (uintptr_t)dpitch0) & (uintptr_t)(CPT - 1)) == 0));
         // FMA path: every intermediate of the tile is >= 0 (flag raised by the H pass before the barrier)
+#if defined(OTTGPU_NO_VFMA)                    /* A/B experiments: the integer bias-lane path only */
+        const bool fma = false;
+#else
         const bool fma = !OTTGPU_STRIP && sizeof(mid_t) == 2 && g.vsum != 0 && g.mid_neg == 0;
+#endif
         // 1.5 * 2^39 + 65536 * (init - 128 * vsum): exact (a multiple of the binade's ulp)
         const float acc0 = 824633720832.0f + 65536.0f * (float)(((64 + 8 * (vtaps - 1)) >> 4) - 128 * (int)g.vsum);
         for (; y < fast_rows; y += rows_per_pass) {
