@@ -9,6 +9,7 @@
 // The per-thread work lives in ladder_core.cuh / yadif_core.cuh.
 #include "kernels.h"
 #include <cstdlib>
+#include <cstdio>
 #include "ladder_core.cuh"
 #include "yadif_core.cuh"
 #include "convert_core.cuh"
@@ -106,6 +107,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 }
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); }
 
+// Experiment build (scripts/build_variant.sh clocks -DOTTGPU_PHASE_CLOCKS, scripts/gpu_clocks.sh): lane 0 of every warp of two
+// CTAs adds up where its cycles go -- waiting for a tile's source window, H pass, the CTA barrier, V pass, copy items; the
+// producer: waiting for a descriptor slot, fetching the item, resolving it, table copies, waiting for the source buffer,
+// issuing the boxes -- and prints the totals of a launch.  Never part of the product build.
+#if defined(OTTGPU_PHASE_CLOCKS)
+__device__ int g_phase_prints = 0;
+#define PC_MARK(acc) { const long long t_ = clock64(); acc += t_ - pc_t0; pc_t0 = t_; }
+#define PP_MARK(acc) { const long long t_ = clock64(); acc += t_ - pp_t0; pp_t0 = t_; }
+#else
+#define PC_MARK(acc)
+#define PP_MARK(acc)
+#endif
 constexpr int kLadderThreads = kThreads + 32;     // 12 compute warps + 1 producer warp
 
 // Warp-specialised persistent kernel.
@@ -149,6 +162,9 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
             cur_end = cur + kClaim;
             nxt = atomicAdd(L.counter, kClaim);
         }
+#if defined(OTTGPU_PHASE_CLOCKS)
+        long long pp_gfree = 0, pp_item = 0, pp_prep = 0, pp_tab = 0, pp_empty = 0, pp_tma = 0, pp_t0 = clock64();
+#endif
         for (int slot = 0;; slot = (slot + 1) & (kGeomSlots - 1)) {
             int idx = 0;
             if (lane == 0) {
@@ -162,11 +178,17 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
             idx = __shfl_sync(0xffffffffu, idx, 0);
             mbar_wait_backoff(&gfree[slot], (pg >> slot) & 1);
             pg ^= 1u << slot;
+            PP_MARK(pp_gfree)
             if (idx >= L.n_items) {
                 if (lane == 0) {
                     s_idx[slot] = idx;
                     mbar_arrive(&ready[slot]);
                 }
+#if defined(OTTGPU_PHASE_CLOCKS)
+                if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 150) && L.n_items > 5000 && atomicAdd(&g_phase_prints, 1) < 104)
+                    printf("cta %d PRODUCER: gfree %lld  item %lld  prepare %lld  tables %lld  empty %lld  tma %lld (cycles)\n", (int)blockIdx.x,
+                           pp_gfree, pp_item, pp_prep, pp_tab, pp_empty, pp_tma);
+#endif
                 break;
             }
             // the item's static block: eight lanes, one 16-byte vector each, straight into the descriptor slot
@@ -174,6 +196,7 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
             if (lane < (int)(sizeof(Item) / 16))
                 reinterpret_cast<uint4 *>(&g)[lane] = __ldg(reinterpret_cast<const uint4 *>(L.items + idx) + lane);
             __syncwarp();
+            PP_MARK(pp_item)
             int what = 0;
             if (lane == 0) {
                 s_idx[slot] = idx;
@@ -183,6 +206,7 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
             }
             what = __shfl_sync(0xffffffffu, what, 0);
             __syncwarp();
+            PP_MARK(pp_prep)
             if (what == 1) {
                 if (g.vc_bytes) {                              // V coefficients / row positions: two bulk copies
                     if (lane == 0) {
@@ -195,8 +219,10 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
                     phase_tables(lane, 32, g, smem);
                     __syncwarp();
                 }
+                PP_MARK(pp_tab)
                 mbar_wait_backoff(&empty[buf], (pe >> buf) & 1);   // the tile that last used this source buffer is done
                 pe ^= 1u << buf;
+                PP_MARK(pp_empty)
 #if defined(OTTGPU_DEBUG_NO_TMA)
                 if (false) {
                     if (lane == 0) {
@@ -215,6 +241,7 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
                 }
                 buf = (buf + 1 == nbuf) ? 0 : buf + 1;
                 mid = (mid + 1 == L.mid_buffers) ? 0 : mid + 1;
+                PP_MARK(pp_tma)
             } else if (lane == 0) {
                 mbar_arrive(&ready[slot]);                     // copy item / skipped item: no source buffer involved
             }
@@ -225,18 +252,23 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
     // ---------------------------------------------------------------------- compute warps
     constexpr bool kStrip = BPS == 1 && OTTGPU_STRIP;
     uint32_t pr = 0;
+#if defined(OTTGPU_PHASE_CLOCKS)
+    long long pc_ready = 0, pc_h = 0, pc_bar = 0, pc_v = 0, pc_copy = 0, pc_t0 = clock64(), pc_tiles = 0;
+#endif
     for (int slot = 0;; slot = (slot + 1) & (kGeomSlots - 1)) {
         // strip mode: the warps of a CTA run apart, and one that is ahead must not spin on the barrier (a spinning warp takes
         // issue slots from the working ones): try_wait with a time hint suspends it in hardware until the phase completes
         if (kStrip) mbar_wait_sleep(&ready[slot], (pr >> slot) & 1);
         else mbar_wait(&ready[slot], (pr >> slot) & 1);
         pr ^= 1u << slot;
+        PC_MARK(pc_ready)
         const int idx = s_idx[slot];
         if (idx >= L.n_items) break;
         const int what = s_what[slot];
         const TileGeom &g = s_geom[slot];
         if (what == 2) {
             item_copy(tid, g, L.binds[g.chan]);
+            PC_MARK(pc_copy)
         } else if (what == 1) {
 #if defined(OTTGPU_DEBUG_NO_TMA)
             if (false) {
@@ -253,13 +285,19 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
 #if !defined(OTTGPU_DEBUG_SKIP_H)
             phase_hpass<BPS>(tid, g, smem);
 #endif
+            PC_MARK(pc_h)
             // strip mode: the V pass of a warp reads only what the same warp's H pass wrote (and the V tables, complete
             // since ready[slot]); otherwise the H-pass result of the whole CTA must be complete
             if (kStrip) __syncwarp();
             else compute_sync();
+            PC_MARK(pc_bar)
             mbar_arrive(&empty[s_buf[slot]]);      // this thread no longer reads the source buffer
 #if !defined(OTTGPU_DEBUG_SKIP_V)
             phase_vpass<BPS>(tid, g, smem);
+#endif
+            PC_MARK(pc_v)
+#if defined(OTTGPU_PHASE_CLOCKS)
+            ++pc_tiles;
 #endif
             // one intermediate region: everybody must be done reading it before the next tile's H pass writes it.  Two
             // regions: the next H pass writes the other one, and the region it will overwrite after that was last read
@@ -268,6 +306,11 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
         }
         mbar_arrive(&gfree[slot]);                 // descriptor slot may be rewritten
     }
+#if defined(OTTGPU_PHASE_CLOCKS)
+    if ((tid & 31) == 0 && (blockIdx.x == 0 || blockIdx.x == 150) && L.n_items > 5000 && atomicAdd(&g_phase_prints, 1) < 104)
+        printf("cta %d warp %d tiles %lld: ready %lld  H %lld  barrier %lld  V %lld  copy %lld  (cycles)\n", (int)blockIdx.x, tid >> 5, pc_tiles,
+               pc_ready, pc_h, pc_bar, pc_v, pc_copy);
+#endif
 }
 
 #if !defined(OTTGPU_YADIF_BLOCKS)

@@ -244,3 +244,51 @@ def test_random_geometry_vs_oracle(lib, og, oracle, case):
         ref = oracle.i420_to_nv12(ref, dw, dh)
     got = lib.scale_frame(src, og.FMT_I420, sw, sh, dw, dh, dst_fmt=og.FMT_NV12 if nv12 else og.FMT_I420, filt=f, target=t)
     assert np.array_equal(got, ref), (case, int((got != ref).sum()))
+
+
+# ---- round 3: the target-A vertical pass as round-down FP32 FMAs (vrow_fma8) and its integer fall-back -------------
+def _stripes_i420(w, h, period, lo=0, hi=255, vertical=True):
+    """hard black / white stripes: the bicubic / lanczos overshoot next to them drives H-pass intermediates below zero"""
+    cw, ch = chroma_dims(w, h)
+    def plane(pw, ph):
+        idx = (np.arange(pw)[None, :] // period) if vertical else (np.arange(ph)[:, None] // period)
+        return np.broadcast_to(np.where(idx & 1, hi, lo), (ph, pw)).astype(np.uint8)
+    return np.concatenate([plane(w, h).ravel(), plane(cw, ch).ravel(), plane(cw, ch).ravel()])
+
+
+@pytest.mark.parametrize("case", [(640, 360, 426, 240), (640, 360, 320, 180), (640, 360, 212, 120), (1280, 720, 278, 156)])
+@pytest.mark.parametrize("content", ["video-range", "stripes", "mixed", "noise"])
+def test_vertical_fma_path_and_fallback(lib, og, oracle, case, content):
+    """Tiles whose intermediates are all >= 0 take the FMA path, tiles with a negative one the integer path: both must be
+    the reference's bytes, whatever the content (the decision is per tile, so `mixed` exercises both in one picture)."""
+    sw, sh, dw, dh = case
+    if content == "video-range":
+        src = np.clip(natural_i420(sw, sh, 5), 16, 235).astype(np.uint8)
+    elif content == "stripes":
+        src = _stripes_i420(sw, sh, 3)
+    elif content == "mixed":
+        src = np.clip(natural_i420(sw, sh, 6), 16, 235).astype(np.uint8)
+        y = src[: sw * sh].reshape(sh, sw)
+        y[sh // 3: sh // 2, sw // 4: sw // 2] = _stripes_i420(sw, sh, 2)[: sw * sh].reshape(sh, sw)[sh // 3: sh // 2, sw // 4: sw // 2]
+    else:
+        src = noise_i420(sw, sh, 77)
+    for filt, k in ((og.FILTER_BICUBIC, oracle.BICUBIC), (og.FILTER_LANCZOS, oracle.LANCZOS)):
+        ref = oracle.scale_i420(src, sw, sh, dw, dh, k, og.TARGET_A)
+        got = lib.scale_frame(src, og.FMT_I420, sw, sh, dw, dh, filt=filt, target=og.TARGET_A)
+        assert np.array_equal(got, ref), (case, content, int((got != ref).sum()))
+
+
+def test_vertical_fma_path_is_taken(emu_lib, og):
+    """On the emulation the kernel source counts which path its fast rows took: video-range content must run on FMAs only,
+    hard 0/255 stripes must send tiles to the integer path (otherwise the sign flag of the H pass is broken)."""
+    import ctypes
+    emu_lib.dll.ottgpu_emu_vrows.argtypes = [ctypes.POINTER(ctypes.c_longlong)]
+    out = (ctypes.c_longlong * 2)()
+    sw, sh, dw, dh = 640, 360, 426, 240
+    emu_lib.dll.ottgpu_emu_vrows(out)
+    emu_lib.scale_frame(np.clip(natural_i420(sw, sh, 5), 16, 235).astype(np.uint8), og.FMT_I420, sw, sh, dw, dh)
+    emu_lib.dll.ottgpu_emu_vrows(out)
+    assert out[0] > 0 and out[1] == 0, (out[0], out[1])
+    emu_lib.scale_frame(_stripes_i420(sw, sh, 3), og.FMT_I420, sw, sh, dw, dh)
+    emu_lib.dll.ottgpu_emu_vrows(out)
+    assert out[1] > 0, (out[0], out[1])
