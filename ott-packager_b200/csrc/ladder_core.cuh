@@ -165,7 +165,11 @@ OTT_DEV uint32_t ott_pack_u8(int b1, int b0, uint32_t upper)
     asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(b1), "r"(b0), "r"(upper));
     return d;
 }
+#if defined(OTTGPU_EXPERIMENT_FMA_RN)       /* timing experiment only (wrong results): is FFMA.RM slower than FFMA? */
+OTT_DEV float ott_fma_rd(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+#else
 OTT_DEV float ott_fma_rd(float a, float b, float c) { return __fmaf_rd(a, b, c); }                    // FFMA.RM
+#endif
 OTT_DEV float ott_as_float(uint32_t v) { return __uint_as_float(v); }
 OTT_DEV uint32_t ott_as_u32(float f) { return __float_as_uint(f); }
 OTT_DEV float ott_i2f(int v) { return __int2float_rn(v); }
@@ -1023,8 +1027,9 @@ OTT_DEV void vrow_fma8(const mid_t *m, int step, const int32_t *cf, int vtaps, f
     for (int k = 0; k < NV; ++k) acc[k] = acc0;
     const uint32_t *m0 = reinterpret_cast<const uint32_t *>(m), *m1 = reinterpret_cast<const uint32_t *>(m + step);
     const uint2 *c2 = reinterpret_cast<const uint2 *>(cf);
-    OTT_NOUNROLL
-    for (int j = vtaps; j > 0; j -= 2, m0 += step, m1 += step, ++c2) {
+    int j = vtaps;                                 // even and >= 2 on this path (PlaneTables::vbias): a do-while, so the
+    OTT_NOUNROLL                                   // compiler does not build a second copy of the set-up for a zero-trip case
+    do {
         const uint2 cc = *c2;
         const float c0 = ott_i2f((int)cc.x), c1 = ott_i2f((int)cc.y);
         uint32_t w0[NW], w1[NW];
@@ -1040,7 +1045,8 @@ OTT_DEV void vrow_fma8(const mid_t *m, int step, const int32_t *cf, int vtaps, f
             acc[2 * k] = ott_fma_rd(ott_as_float(ott_prmt(w1[k], kOne23, 0x7610)), c1, acc[2 * k]);
             acc[2 * k + 1] = ott_fma_rd(ott_as_float(ott_prmt(w1[k], kOne23, 0x7632)), c1, acc[2 * k + 1]);
         }
-    }
+        m0 += step; m1 += step; ++c2;
+    } while ((j -= 2) > 0);
     // acc = 1.5 * 2^39 + 65536 * (init + sum of floors): one bit step per unit, so the integer falls out of the bits
     int r[NV];
     OTT_UNROLL
@@ -1139,7 +1145,11 @@ OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
     // the geometry lives in shared memory: copy what the loop needs into registers once
     const int tile_w = g.tw, tile_h = g.th, y0 = g.y0, sy0 = g.sy0;
     const int mid_pitch = g.mid_pitch, plane_step = g.mid_rows * g.mid_pitch, approx = g.approx_v, shift = g.dst_shift, nplanes = g.nplanes, il = g.dst_interleaved;
+#if defined(OTTGPU_EXPERIMENT_V_ONETRIP)   /* timing experiment only (wrong results): the per-row cost without the tap loop */
+    const int vtaps = 2, vstride = g.vstride, exact_from = g.exact_from, dstW = g.dstW;
+#else
     const int vtaps = g.vtaps, vstride = g.vstride, exact_from = g.exact_from, dstW = g.dstW;
+#endif
     uint8_t *const dst0 = g.dst0, *const dst1 = g.dst1;
     const int dpitch0 = g.dst_pitch0, dpitch1 = g.dst_pitch1;
     int x, ry, rows_per_pass;
@@ -1192,6 +1202,9 @@ OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
                     else o1[k] = t[k];
                 }
             }
+#if defined(OTTGPU_EXPERIMENT_V_NOSTORE)   /* timing experiment only: rows computed, nothing written (the stores stay reachable) */
+            if (o0[0] == 0x12345678u && o1[0] == 0x9abcdef0u)
+#endif
             vpass_store<BPS, NO>(dst0, dst1, dpitch0, dpitch1, y0 + y, gx, dstW, nplanes, il, vec_ok, o0, o1);
         }
     }
