@@ -1009,19 +1009,23 @@ OTT_DEV void vrow_bias8(const mid_t *m, int step, const int32_t *cf, int vtaps, 
 }
 
 // Round 3: the same rows as round-down FP32 FMAs.  pmulhw is floor(t*c / 65536), and an FMA rounds ONCE: with an
-// accumulator that is a multiple of 65536 inside the binade [2^39, 2^40) (ulp = 65536) and round-toward-minus-infinity,
-//     fma.rm(g, c, acc) = floor_65536(acc + g*c) = acc + 65536 * floor(g*c / 65536)        exactly
-// (g*c is exact inside the FMA: 24 x 13 bits).  The operand g = 2^23 + t is built from the packed int16 intermediate with
-// ONE byte permute (float bits 0x4B000000 | t, valid for t >= 0: the H pass raises TileGeom::mid_neg otherwise and the tile
-// takes vrow_bias8); its 2^23 adds 128*c per tap, a multiple of the ulp, so the floor is untouched, and over a row that is
+// accumulator that is a multiple of U = 65536 u inside one binade whose ulp is U, and round-toward-minus-infinity,
+//     fma.rm(g, c, acc) = floor_U(acc + g*c) = acc + U * floor(g*c / U)        exactly
+// (g*c is exact inside the FMA: 24 x 13 bits).  The operand g = (2^23 + t) u is built from the packed int16 intermediate
+// with ONE byte permute (float bits kOne23 | t, valid for t >= 0: the H pass raises TileGeom::mid_neg otherwise and the tile
+// takes vrow_bias8); its 2^23 adds 128*c*U per tap, a multiple of the ulp, so the floor is untouched, and over a row that is
 // 128 * vsum, taken out of the initial accumulator.  Per tap-sample: one PRMT (ALU pipe) + one FFMA (FMA pipe) - the
 // multiply, the floor and the accumulation in one instruction, against IMAD + extraction + 1/2 PRMT + 1/4 IADD3 of the
 // bias-lane path.  The plan checks that the accumulator cannot leave the binade (PlaneTables::vsum).
+// The unit u is 2^-64 (it rides in the exponent byte of the PRMT constant), which puts the accumulator at 1.5 * 2^-25 and
+// lets ONE more round-down FMA finish the row: (acc - 1.5 * 2^-25) * 2^-104 is (sum / 8) * 2^-149, a DENORMAL, whose
+// round-down IS psraw 3 and whose bit pattern is the integer itself (negative sums become negative floats = negative
+// integers as far as the saturating pack is concerned): no subtract, no shift.
 template <int NV>
 OTT_DEV void vrow_fma8(const mid_t *m, int step, const int32_t *cf, int vtaps, float acc0, uint32_t (&out)[NV / 4])
 {
     constexpr int NW = NV / 2;
-    constexpr uint32_t kOne23 = 0x4B000000u;                      // 2^23: a float whose low mantissa bits are an integer
+    constexpr uint32_t kOne23 = 0x2B000000u;                      // 2^23 * 2^-64: a float whose low mantissa bits are an integer
     float acc[NV];
     OTT_UNROLL
     for (int k = 0; k < NV; ++k) acc[k] = acc0;
@@ -1047,10 +1051,10 @@ OTT_DEV void vrow_fma8(const mid_t *m, int step, const int32_t *cf, int vtaps, f
         }
         m0 += step; m1 += step; ++c2;
     } while ((j -= 2) > 0);
-    // acc = 1.5 * 2^39 + 65536 * (init + sum of floors): one bit step per unit, so the integer falls out of the bits
+    // acc = 1.5 * 2^-25 + 2^-48 * (init + sum of floors)  ->  floor(sum / 8) as a denormal's bits (no paddw wrap: |sum| < 2^15)
     int r[NV];
     OTT_UNROLL
-    for (int k = 0; k < NV; ++k) r[k] = (int)(ott_as_u32(acc[k]) - 0x53400000u) >> 3;      // psraw 3 (no paddw wrap: |sum| < 2^15)
+    for (int k = 0; k < NV; ++k) r[k] = (int)ott_as_u32(ott_fma_rd(acc[k], 4.930380657631324e-32f, -2.204051907791789e-39f));
     OTT_UNROLL
     for (int k = 0; k < NV / 4; ++k) {
         const uint32_t upper = ott_pack_u8(r[4 * k + 3], r[4 * k + 2], 0u);
@@ -1182,8 +1186,8 @@ OTT_DEV void vpass(int tid, const TileGeom &g, unsigned char *smem)
 #else
         const bool fma = !OTTGPU_STRIP && sizeof(mid_t) == 2 && g.vsum != 0 && g.mid_neg == 0;
 #endif
-        // 1.5 * 2^39 + 65536 * (init - 128 * vsum): exact (a multiple of the binade's ulp)
-        const float acc0 = 824633720832.0f + 65536.0f * (float)(((64 + 8 * (vtaps - 1)) >> 4) - 128 * (int)g.vsum);
+        // 1.5 * 2^-25 + 2^-48 * (init - 128 * vsum): exact (a multiple of the binade's ulp 2^-48)
+        const float acc0 = 4.470348358154297e-08f + 3.552713678800501e-15f * (float)(((64 + 8 * (vtaps - 1)) >> 4) - 128 * (int)g.vsum);
         for (; y < fast_rows; y += rows_per_pass) {
             const int32_t *cf = vc_s + y * vstride;
             const mid_t *m = mid_s + (vpos_s[y] - sy0) * mid_pitch;
