@@ -2,7 +2,7 @@
 # Round-2 final evidence on one B200 under gpurun: GPU test tier, smoke, both bench arms, launch list, full ncu captures of the
 # main ladder launch (cfg2, cfg4) and of yadif, JPEG and single-channel figures.
 set -u
-OUT=gpurun_out; mkdir -p $OUT; T=r2f
+OUT=gpurun_out; mkdir -p $OUT; T=${TAG:-r2f}
 timeout 900 python -m pytest tests -x -q -m gpu > $OUT/${T}_pytest.log 2>&1; echo "pytest exit $?"; tail -2 $OUT/${T}_pytest.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${T}_smoke.log 2>&1; echo "smoke exit $?"
 timeout 900 python bench.py --steps 20 --warmup 5 > $OUT/${T}_bench.json 2> $OUT/${T}_bench.err; echo "bench exit $?"
@@ -26,3 +26,7 @@ d=json.load(open("$OUT/${T}_bench.json")); r=json.load(open("$OUT/${T}_bench_ref
 print("value %.0f e2e %.0f (%s) dev_out %.0f  ref %.0f  ratio e2e %.1f value %.1f" % (d["value"], d["e2e"]["value"], d["e2e"]["variant"], d["e2e_device_out"]["value"], r["value"], d["e2e"]["value"]/r["value"], d["value"]/r["value"]))
 print({n:(round(v["ms_per_launch"],4), round(v["frac"],3)) for n,v in d["roofline"]["kernels"].items()}, d["clocks"])
 PY
+# 16-bit ladder (cfg3) capture as well
+timeout 300 $SMALL --workload cfg3 > $OUT/${T}_plain_cfg3.log 2>&1 && \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:ladder_kernel -s 1 -c 1 -f -o $OUT/${T}_cfg3_ladder $SMALL --workload cfg3 > $OUT/${T}_ncu_cfg3.log 2>&1
+echo "ncu ladder cfg3 exit $?"
