@@ -39,6 +39,11 @@ def main():
         dh = max(8, int(sh * rng.uniform(0.08, 3.0))) & ~1
         lanczos, tb, nv = (int(rng.integers(0, 2)) for _ in range(3))
         src = noise_i420(sw, sh, it)
+        if it % 3 == 1:                                          # video-range content: no negative intermediates, so the V
+            src = (16 + (src.astype(np.uint16) * 220 >> 8)).astype(np.uint8)   # pass runs as FMAs (noise mostly takes the integer path)
+        elif it % 3 == 2:                                        # both paths in one picture: half the rows in video range
+            half = src[: sw * sh].reshape(sh, sw)
+            half[: sh // 2] = 16 + (half[: sh // 2].astype(np.uint16) * 220 >> 8)
         got = lib.scale_frame(src, og.FMT_I420, sw, sh, dw, dh, dst_fmt=og.FMT_NV12 if nv else og.FMT_I420,
                               filt=og.FILTER_LANCZOS if lanczos else og.FILTER_BICUBIC, target=tb)
         ref = oracle.scale_i420(src, sw, sh, dw, dh, oracle.LANCZOS if lanczos else oracle.BICUBIC, tb)
