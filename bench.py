@@ -94,6 +94,9 @@ def synth_frames(w, h, n, interlaced, p010=False):
     rng = np.random.default_rng(7)
     cw, ch = (w + 1) // 2, (h + 1) // 2
     out = []
+    if os.environ.get("OTT_BENCH_CONTENT") == "noise":       # experiments only (profiles/README.md, content dependence of the
+        n_s = frame_bytes(w, h)                              # ladder's vertical pass): full-range uniform noise
+        return [rng.integers(0, 256, n_s, dtype=np.uint8) for _ in range(n)]
     for i in range(n):
         def plane(pw, ph, k, shift):
             x = np.arange(pw, dtype=np.float32)[None, :] * k + shift
