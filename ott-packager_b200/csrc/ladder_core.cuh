@@ -168,6 +168,9 @@ OTT_DEV uint32_t ott_pack_u8(int b1, int b0, uint32_t upper)
 #if defined(OTTGPU_EXPERIMENT_FMA_RN)       /* timing experiment only (wrong results): is FFMA.RM slower than FFMA? */
 OTT_DEV float ott_fma_rd(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 #else
+#if defined(__CUDA_FTZ) && __CUDA_FTZ
+#error "libottgpu must not be built with -ftz=true / -use_fast_math: the vertical pass reads a denormal FMA result as an integer (vrow_fma8)"
+#endif
 OTT_DEV float ott_fma_rd(float a, float b, float c) { return __fmaf_rd(a, b, c); }                    // FFMA.RM
 #endif
 OTT_DEV float ott_as_float(uint32_t v) { return __uint_as_float(v); }
