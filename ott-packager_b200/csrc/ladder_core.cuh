@@ -165,14 +165,14 @@ OTT_DEV uint32_t ott_pack_u8(int b1, int b0, uint32_t upper)
     asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(b1), "r"(b0), "r"(upper));
     return d;
 }
-#if defined(OTTGPU_EXPERIMENT_FMA_RN)       /* timing experiment only (wrong results): is FFMA.RM slower than FFMA? */
-OTT_DEV float ott_fma_rd(float a, float b, float c) { return __fmaf_rn(a, b, c); }
-#else
-#if defined(__CUDA_FTZ) && __CUDA_FTZ
-#error "libottgpu must not be built with -ftz=true / -use_fast_math: the vertical pass reads a denormal FMA result as an integer (vrow_fma8)"
-#endif
-OTT_DEV float ott_fma_rd(float a, float b, float c) { return __fmaf_rd(a, b, c); }                    // FFMA.RM
-#endif
+// FFMA.RM, spelled in PTX so that a build with -ftz=true / -use_fast_math cannot turn it into the flush-to-zero form: the
+// vertical pass reads a DENORMAL result of this instruction as an integer (vrow_fma8)
+OTT_DEV float ott_fma_rd(float a, float b, float c)
+{
+    float d;
+    asm("fma.rm.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
 OTT_DEV float ott_as_float(uint32_t v) { return __uint_as_float(v); }
 OTT_DEV uint32_t ott_as_u32(float f) { return __float_as_uint(f); }
 OTT_DEV float ott_i2f(int v) { return __int2float_rn(v); }
