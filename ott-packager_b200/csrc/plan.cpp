@@ -105,6 +105,59 @@ const T *upload(Plan &plan, const std::vector<T> &v, std::string &err)
 
 struct TileRegions { size_t src, mid, vc; };
 
+
+// ---- H-pass work of one scale tile dealt to the compute warps (Item::hrun): contiguous runs of (column group, 16-row group)
+// pairs, column-group major.  There is no barrier between a tile's V pass and the next tile's H pass, so a warp reaches the
+// H->V barrier after (its V rows of the PREVIOUS tile) + (its H pairs of this one), and the V rows are dealt by thread index:
+// the low warps own the rows of the last, partial sweep.  Equal H shares therefore left the high warps waiting at the barrier
+// (17 % of the warp-time samples).  The pairs go preferentially to the warps with the lighter V share; `vload` is the V share
+// to assume per warp: null = this tile's own shape (the default: a CTA's consecutive tiles are mostly neighbours of one rung's
+// tile row), else the plan-wide average of the main launch's tiles (OTT_HBAL_MODE=1, measured worse: 0.559 vs 0.550 ms on cfg2).
+// Measured on the B200 (ms per 64 frames, cfg2 / cfg4): equal shares 0.570 / 0.444, OTT_HBAL 0.25 0.558 / 0.438, 0.5 0.554 / 0.435,
+// 0.6 0.551 / 0.433, 0.75 0.554 / 0.436, 1.0 0.555 / 0.437, 1.5 0.569 / 0.451.  Costs in instructions per warp (profiles/README.md): a V row = planes * (60 + 22 * taps), an H pair =
+// 2 + 24 * K steps (8-bit) / 20 + 14 * K steps (16-bit).  OTT_HBAL scales the V term (default 0.6, measured; 0 = equal shares).
+static void tile_vload(const Item &it, double (&load)[kThreads / 32])
+{
+    constexpr int kWarps = kThreads / 32;
+    const int lpr_log2 = it.tw_log2 - 3, rpp = kThreads >> lpr_log2, th = it.th;
+    const double vrow = it.nplanes * (60.0 + 22.0 * it.vtaps);
+    for (int w = 0; w < kWarps; ++w) {
+        const int ry0 = (32 * w) >> lpr_log2;
+        load[w] = vrow * (ry0 < th ? (th - ry0 + rpp - 1) / rpp : 0);
+    }
+}
+
+static void deal_hruns(Item &it, const double *vload)
+{
+    constexpr int kWarps = kThreads / 32;
+    static const double hbal = [] { const char *e = std::getenv("OTT_HBAL"); return e ? std::atof(e) : 0.6; }();
+    const int groups = (it.tw + 7) >> 3, mt_total = it.nplanes * ((it.sr + 15) >> 4);
+    const int total = groups * mt_total, per = (total + kWarps - 1) / kWarps;
+    const double hpair = it.bps == 1 ? 2.0 + 24.0 * it.hks : 20.0 + 14.0 * it.hks;
+    int share[kWarps];
+    double load[kWarps];
+    if (vload) for (int w = 0; w < kWarps; ++w) load[w] = vload[w];
+    else tile_vload(it, load);
+    for (int w = 0; w < kWarps; ++w) { load[w] *= hbal; share[w] = 0; }
+    if (hbal <= 0.0) {
+        for (int w = 0, f = 0; w < kWarps; ++w) { share[w] = std::max(0, std::min(per, total - f)); f += share[w]; }
+    } else {
+        for (int k = 0; k < total; ++k) {                        // greedy: the next pair to the least loaded warp
+            int best = 0;
+            for (int w = 1; w < kWarps; ++w)
+                if (load[w] < load[best]) best = w;
+            load[best] += hpair;
+            ++share[best];
+        }
+    }
+    int nt = 0, mt = 0;
+    for (int w = 0; w < kWarps; ++w) {
+        it.hrun[w] = (uint32_t)nt | ((uint32_t)mt << 8) | ((uint32_t)share[w] << 20);
+        mt += share[w];
+        while (mt_total > 0 && mt >= mt_total) { mt -= mt_total; ++nt; }
+    }
+}
+
 // must match item_prepare() in ladder_core.cuh
 TileRegions tile_regions(int nplanes, int staged_planes, int sr_max, int sw_words, int mid_pitch, int th, int vstride)
 {
@@ -690,19 +743,7 @@ std::shared_ptr<Plan> build_plan(const ottgpu_cfg &cfg, std::string &err)
                             it.kw[gi - x0 / 8] = (uint16_t)kwv;
                         }
                     }
-                    if (!kb.empty() && !strip) {                 // H-pass runs of the compute warps (MMA paths, round-1 layout)
-                        constexpr int kWarps = kThreads / 32;
-                        const int groups = (tw + 7) >> 3, mt_total = it.nplanes * ((sr + 15) >> 4);
-                        const int total = groups * mt_total, per = (total + kWarps - 1) / kWarps;
-                        int nt = 0, mt = 0;
-                        for (int w = 0, f = 0; w < kWarps; ++w) {
-                            const int n = std::max(0, std::min(per, total - f));
-                            it.hrun[w] = (uint32_t)nt | ((uint32_t)mt << 8) | ((uint32_t)n << 20);
-                            f += n;
-                            mt += n;
-                            while (mt_total > 0 && mt >= mt_total) { mt -= mt_total; ++nt; }
-                        }
-                    }
+                    if (!kb.empty() && !strip) deal_hruns(it, nullptr);   // H-pass runs of the compute warps (MMA paths, round-1 layout)
                     if (cls == 2) plan->thumb_items.push_back(it);
                     else if (cls == 1) plan->big_items.push_back(it);
                     else ordered.push_back({it, band_scale * sy0});
@@ -714,6 +755,24 @@ std::shared_ptr<Plan> build_plan(const ottgpu_cfg &cfg, std::string &err)
         if (bad_item) return nullptr;
     }
     std::stable_sort(ordered.begin(), ordered.end(), [](const Sortable &a, const Sortable &b) { return a.band < b.band; });
+    if (!OTTGPU_STRIP) {                                          // second pass: H shares against the plan-wide average V share
+        static const int mode = [] { const char *e = std::getenv("OTT_HBAL_MODE"); return e ? std::atoi(e) : 0; }();   // measured: 0 wins
+        constexpr int kWarps = kThreads / 32;
+        double avg[kWarps] = {0};
+        int n_tiles = 0;
+        for (const Sortable &so : ordered)
+            if ((so.it.kind == ITEM_SCALE_LUMA || so.it.kind == ITEM_SCALE_CHROMA) && so.it.hmma) {
+                double l[kWarps];
+                tile_vload(so.it, l);
+                for (int w = 0; w < kWarps; ++w) avg[w] += l[w];
+                ++n_tiles;
+            }
+        if (mode == 1 && n_tiles > 0) {
+            for (int w = 0; w < kWarps; ++w) avg[w] /= n_tiles;
+            for (Sortable &so : ordered)
+                if ((so.it.kind == ITEM_SCALE_LUMA || so.it.kind == ITEM_SCALE_CHROMA) && so.it.hmma) deal_hruns(so.it, avg);
+        }
+    }
     for (const Sortable &so : ordered) plan->items.push_back(so.it);
 
     if (cudaMemcpy(plan->dev, &P, sizeof(PlanDev), cudaMemcpyHostToDevice) != cudaSuccess) { err = "cudaMemcpy(plan) failed"; return nullptr; }
