@@ -367,7 +367,11 @@ OTT_DEV void hpass8_mma(int tid, const TileGeom &g, unsigned char *smem)
         uint4 B[KS ? KS : 1];
         if (KS) {
             OTT_UNROLL
+#if defined(OTTGPU_EXPERIMENT_NO_BLOAD)      /* timing experiment only (wrong results): what do the fragment loads from L2 cost? */
+            for (int ks = 0; ks < KS; ++ks) { B[ks].x = lane + nt; B[ks].y = lane ^ nt; B[ks].z = lane * 3 + nt; B[ks].w = lane + ks; }
+#else
             for (int ks = 0; ks < KS; ++ks) B[ks] = ott_ldg(reinterpret_cast<const uint4 *>(frag) + ks * 32 + lane);
+#endif
         }
 #endif
         int run = ott_min(left, mt_total - mt);                   // row groups of this column group (both planes)
