@@ -227,8 +227,13 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
                 if (false) {
                     if (lane == 0) {
 #else
+#if defined(OTTGPU_EXPERIMENT_NO_WINDOW_WAIT)   /* timing experiment only (stale windows, no fetch at all): upper bound of a fully hidden source fetch */
+                if (false) {
+                    if (lane == 0) {
+#else
                 if (g.bulk_ok) {
                     if (lane == 0) {
+#endif
 #endif
                         fence_proxy_async();                   // the buffer was last read through the generic proxy
                         mbar_expect_tx(&ready[slot], (uint32_t)(g.staged_planes * g.box_bytes));
@@ -267,7 +272,9 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
         const int what = s_what[slot];
         const TileGeom &g = s_geom[slot];
         if (what == 2) {
+#if !defined(OTTGPU_EXPERIMENT_NO_COPY)     /* timing experiment only: upper bound of moving the copy items out of this kernel */
             item_copy(tid, g, L.binds[g.chan]);
+#endif
             PC_MARK(pc_copy)
         } else if (what == 1) {
 #if defined(OTTGPU_DEBUG_NO_TMA)
@@ -288,8 +295,12 @@ __global__ void __launch_bounds__(kLadderThreads, 2) ladder_kernel(const LadderL
             PC_MARK(pc_h)
             // strip mode: the V pass of a warp reads only what the same warp's H pass wrote (and the V tables, complete
             // since ready[slot]); otherwise the H-pass result of the whole CTA must be complete
+#if defined(OTTGPU_EXPERIMENT_NO_BARRIER)   /* timing experiment only (races): upper bound of a perfectly balanced H -> V hand-over */
+            __syncwarp();
+#else
             if (kStrip) __syncwarp();
             else compute_sync();
+#endif
             PC_MARK(pc_bar)
             mbar_arrive(&empty[s_buf[slot]]);      // this thread no longer reads the source buffer
 #if !defined(OTTGPU_DEBUG_SKIP_V)
