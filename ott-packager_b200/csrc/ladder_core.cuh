@@ -1256,17 +1256,24 @@ OTT_DEV void copy_rows(int tid, const uint8_t *src, int spitch, uint8_t *dst, in
     const int warp = tid >> 5, lane = tid & 31;
     constexpr int kWarps = kThreads / 32;
     const int nvec = vec ? row_bytes >> 4 : 0;
-    // a warp takes a row, its lanes stride over the row's 16-byte vectors (two in flight per lane)
+    // a warp takes a row, its lanes stride over the row's 16-byte vectors
     for (int r = warp; r < rows; r += kWarps) {
         const uint8_t *s = src + (size_t)(y0 + r) * spitch;
         uint8_t *d = dst + (size_t)(y0 + r) * dpitch;
         int v = lane;
-        for (; v + 32 < nvec; v += 64) {
-            const uint4 a = ott_ldg(reinterpret_cast<const uint4 *>(s) + v), b = ott_ldg(reinterpret_cast<const uint4 *>(s) + v + 32);
-            reinterpret_cast<uint4 *>(d)[v] = a;
-            reinterpret_cast<uint4 *>(d)[v + 32] = b;
+        for (; v < nvec; v += 128) {                             // up to four vectors in flight per lane (predicated, no
+            const uint4 *sv = reinterpret_cast<const uint4 *>(s) + v;   // divergence): one round trip per 2 KB of row
+            uint4 *dv = reinterpret_cast<uint4 *>(d) + v;
+            const bool p1 = v + 32 < nvec, p2 = v + 64 < nvec, p3 = v + 96 < nvec;
+            uint4 a = ott_ldg(sv), b = a, c = a, e = a;
+            if (p1) b = ott_ldg(sv + 32);
+            if (p2) c = ott_ldg(sv + 64);
+            if (p3) e = ott_ldg(sv + 96);
+            dv[0] = a;
+            if (p1) dv[32] = b;
+            if (p2) dv[64] = c;
+            if (p3) dv[96] = e;
         }
-        for (; v < nvec; v += 32) reinterpret_cast<uint4 *>(d)[v] = ott_ldg(reinterpret_cast<const uint4 *>(s) + v);
         for (int i = (nvec << 4) + lane; i < row_bytes; i += 32) d[i] = ott_ldg(s + i);
     }
 }
