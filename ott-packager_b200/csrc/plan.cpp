@@ -115,7 +115,8 @@ struct TileRegions { size_t src, mid, vc; };
 // tile row), else the plan-wide average of the main launch's tiles (OTT_HBAL_MODE=1, measured worse: 0.559 vs 0.550 ms on cfg2).
 // Measured on the B200 (ms per 64 frames, cfg2 / cfg4): equal shares 0.570 / 0.444, OTT_HBAL 0.25 0.558 / 0.438, 0.5 0.554 / 0.435,
 // 0.6 0.551 / 0.433, 0.75 0.554 / 0.436, 1.0 0.555 / 0.437, 1.5 0.569 / 0.451.  Costs in instructions per warp (profiles/README.md): a V row = planes * (60 + 22 * taps), an H pair =
-// 2 + 24 * K steps (8-bit) / 20 + 14 * K steps (16-bit).  OTT_HBAL scales the V term (default 0.6, measured; 0 = equal shares).
+// 2 + 24 * K steps (8-bit) / 40 + 28 * K steps (16-bit; cfg3, ms per 64 frames at half that cost: OTT_HBAL 0 6.19, 0.3 5.96,
+// 0.6 6.02, 1.0 6.09, 1.5 6.27).  OTT_HBAL scales the V term (default 0.6, measured; 0 = equal shares).
 static void tile_vload(const Item &it, double (&load)[kThreads / 32])
 {
     constexpr int kWarps = kThreads / 32;
@@ -133,7 +134,7 @@ static void deal_hruns(Item &it, const double *vload)
     static const double hbal = [] { const char *e = std::getenv("OTT_HBAL"); return e ? std::atof(e) : 0.6; }();
     const int groups = (it.tw + 7) >> 3, mt_total = it.nplanes * ((it.sr + 15) >> 4);
     const int total = groups * mt_total, per = (total + kWarps - 1) / kWarps;
-    const double hpair = it.bps == 1 ? 2.0 + 24.0 * it.hks : 20.0 + 14.0 * it.hks;
+    const double hpair = it.bps == 1 ? 2.0 + 24.0 * it.hks : 40.0 + 28.0 * it.hks;   // 16-bit: four products, fragments from L2 (measured: cfg3 best at twice the count)
     int share[kWarps];
     double load[kWarps];
     if (vload) for (int w = 0; w < kWarps; ++w) load[w] = vload[w];
