@@ -22,8 +22,12 @@ typedef int16_t mid_t;
 #endif
 // tile descriptors (and V-table regions) in flight per CTA (powers of two).  16-bit ladders run long lanczos filters whose
 // V tables are large (tile rows x taps x 4 bytes): two regions instead of four leave the shared memory to the tiles
-// (measured on cfg3: 167 -> 146 us per frame); the 8-bit ladders are 1 % faster with four.
-constexpr int kGeomSlots8 = 4, kGeomSlots16 = 2;
+// (measured on cfg3: 167 -> 146 us per frame); the 8-bit ladders are fastest with four (final build, cfg4, ms per 64 frames:
+// two 0.446, four 0.430, eight 0.439; -DOTTGPU_SLOTS8=n).
+#if !defined(OTTGPU_SLOTS8)
+#define OTTGPU_SLOTS8 4
+#endif
+constexpr int kGeomSlots8 = OTTGPU_SLOTS8, kGeomSlots16 = 2;
 constexpr int geom_slots(int bps) { return bps == 2 ? kGeomSlots16 : kGeomSlots8; }
 constexpr int kTensorMapBytes = 128;           // sizeof(CUtensorMap)
 #if !defined(OTTGPU_COMPUTE_WARPS)
