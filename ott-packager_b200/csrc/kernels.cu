@@ -472,7 +472,14 @@ cudaError_t launch_ladder(LadderLaunch L, cudaStream_t s)
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorInvalidValue;
     const int grid = L.n_items < sms * per_sm ? L.n_items : sms * per_sm;     // one wave of resident CTAs
-    L.claim = L.n_items / (grid * 4) >= 4 ? 4 : (L.n_items / (grid * 4) >= 2 ? 2 : 1);   // small launches keep every CTA busy
+    // two items per claim on big launches, one on small ones (they keep every CTA busy).  Measured on the final build, ms
+    // per 64 frames on cfg4 / cfg2: 1 -> 0.427 / 0.540, 2 -> 0.426 / 0.536, 4 -> 0.431 / 0.539, 8 -> 0.441, 16 -> 0.459 (longer
+    // runs of one CTA lose the fine interleaving of heavy and light tiles); OTT_CLAIM=n overrides it for experiments
+    L.claim = L.n_items / (grid * 4) >= 2 ? 2 : 1;
+    {
+        static const int env_claim = [] { const char *e = std::getenv("OTT_CLAIM"); return e ? std::atoi(e) : 0; }();
+        if (env_claim > 0 && L.claim == 2) L.claim = env_claim;
+    }
     if (L.bps == 2) ladder_kernel<2><<<grid, kLadderThreads, smem_bytes, s>>>(L);
     else ladder_kernel<1><<<grid, kLadderThreads, smem_bytes, s>>>(L);
     return cudaGetLastError();
